@@ -1,0 +1,295 @@
+// oracle/ref_driver.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT.
+//
+// Log-driven driver that links the UNMODIFIED reference sources (compiled in place from
+// /root/reference by oracle/Makefile, objects only under oracle/_ref/).  It restates the
+// reference's offline loop (openslam_gmapping/gui/gsp_thread.cpp:305-337, 393-394, 417-453,
+// which itself does not build with a modern g++ and needs Qt3) using only the reference's
+// public/protected API, and
+//   * `trace` mode: dumps a binary per-stage trace (golden vectors) through the virtual hooks
+//     onOdometryUpdate / onScanmatchUpdate / onResampleUpdate (gridslamprocessor.h:214-216),
+//   * `time`  mode: times processScan() with steady_clock (the CPU baseline of bench.py).
+//
+// Nothing here is copied from the reference; it only *calls* it.
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include <gmapping/gridfastslam/gridslamprocessor.h>
+#include <gmapping/log/carmenconfiguration.h>
+#include <gmapping/log/sensorstream.h>
+#include <gmapping/utils/stat.h>
+
+using namespace GMapping;
+
+namespace {
+
+struct Opts {
+    std::string mode = "time", log, out;
+    int particles = 30, max_scans = 1 << 30, maps_every = 0, seed = 12345, probe_particles = 2;
+    double xmin = -100, ymin = -100, xmax = 100, ymax = 100, delta = 0.05;
+    double sigma = 0.05, maxrange = 80, maxurange = 80, lstep = 0.05, astep = 0.05, lsigma = 0.075, ogain = 3;
+    int kernel = 1, iterations = 5, lskip = 0;
+    double srr = 0.01, srt = 0.01, str = 0.01, stt = 0.01;
+    double linear_update = 1.0, angular_update = 0.5, resample_thr = 0.5, min_score = 0.0, period = -1.0;
+    bool generate_map = true, init_from_log = true, quiet = true;
+};
+
+struct Writer {
+    FILE* f = nullptr;
+    void rec(const char tag[4], const void* p, size_t bytes) {
+        if (!f) return;
+        uint64_t n = bytes;
+        fwrite(tag, 1, 4, f);
+        fwrite(&n, 8, 1, f);
+        if (bytes) fwrite(p, 1, bytes, f);
+    }
+    template <class T> void vec(const char tag[4], const std::vector<T>& v) { rec(tag, v.data(), v.size() * sizeof(T)); }
+};
+
+uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
+    x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; return x ^ (x >> 31);
+}
+
+// order-independent digest of a particle map in WORLD cell coordinates (ix - sizeX2, iy - sizeY2)
+struct MapDigest { int64_t patches, cells, sum_n, sum_visits; uint64_t hash_counts, hash_acc; double sum_accx, sum_accy; };
+
+class TraceProcessor : public GridSlamProcessor {
+  public:
+    TraceProcessor(std::ostream& info) : GridSlamProcessor(info) {}
+    Writer w;
+    const double* cur_ranges = nullptr;
+    bool resampled = false;
+    int probe_particles = 2;
+    std::vector<double> pre_pose;
+
+    void onOdometryUpdate() override {
+        pre_pose.clear();
+        for (auto& p : m_particles) { pre_pose.push_back(p.pose.x); pre_pose.push_back(p.pose.y); pre_pose.push_back(p.pose.theta); }
+    }
+    void onScanmatchUpdate() override {
+        if (!w.f) return;
+        // per particle: re-run the (const) matcher calls on the pre-update maps to expose score/s/l/c
+        std::vector<double> rows;
+        for (size_t i = 0; i < m_particles.size(); i++) {
+            const Particle& p = m_particles[i];
+            OrientedPoint init(pre_pose[3 * i], pre_pose[3 * i + 1], pre_pose[3 * i + 2]), corr;
+            double sc = m_matcher.optimize(corr, p.map, init, cur_ranges);
+            double s, l; unsigned c = m_matcher.likelihoodAndScore(s, l, p.map, p.pose, cur_ranges);
+            double row[12] = {init.x, init.y, init.theta, sc, corr.x, corr.y, corr.theta, s, l, (double)c, p.pose.x, p.pose.y};
+            rows.insert(rows.end(), row, row + 12); rows.push_back(p.pose.theta); rows.push_back(p.weight); rows.push_back(p.weightSum);
+        }
+        w.vec("SMAT", rows);
+        // stage-level probes: score / likelihoodAndScore at perturbed poses for the first few particles
+        std::vector<double> probes;
+        static const double dxs[5][3] = {{0, 0, 0}, {0.05, 0, 0}, {0, -0.05, 0.01}, {-0.025, 0.0125, -0.05}, {0.3, 0.2, 0.1}};
+        for (int i = 0; i < probe_particles && i < (int)m_particles.size(); i++)
+            for (auto& d : dxs) {
+                const Particle& p = m_particles[i];
+                OrientedPoint q(p.pose.x + d[0], p.pose.y + d[1], p.pose.theta + d[2]);
+                double s2, l2; unsigned c2 = m_matcher.likelihoodAndScore(s2, l2, p.map, q, cur_ranges);
+                double s1 = m_matcher.score(p.map, q, cur_ranges);
+                double row[8] = {(double)i, q.x, q.y, q.theta, s1, s2, l2, (double)c2};
+                probes.insert(probes.end(), row, row + 8);
+            }
+        w.vec("PROB", probes);
+    }
+    void onResampleUpdate() override {
+        resampled = true;
+        if (!w.f) return;
+        double ne = m_neff; w.rec("RNEF", &ne, 8);
+        w.vec("RWGT", m_weights);
+        std::vector<uint32_t> idx(m_indexes.begin(), m_indexes.end());
+        w.vec("RIDX", idx);
+    }
+    void dumpState() {
+        if (!w.f) return;
+        std::vector<double> st;
+        for (auto& p : m_particles) {
+            double row[6] = {p.pose.x, p.pose.y, p.pose.theta, p.weight, p.weightSum, (double)p.previousIndex};
+            st.insert(st.end(), row, row + 6);
+        }
+        w.vec("STAT", st);
+        double ne = m_neff; w.rec("NEFF", &ne, 8);
+        w.vec("WGTS", m_weights);
+    }
+    static MapDigest digest(const ScanMatcherMap& m, std::vector<int32_t>* full) {
+        MapDigest d; memset(&d, 0, sizeof d);
+        IntPoint c = m.world2map(m.getCenter());  // == (sizeX2, sizeY2): round(0) == 0
+        const auto& st = m.storage();
+        for (int px = 0; px < st.getXSize(); px++)
+            for (int py = 0; py < st.getYSize(); py++) {
+                const auto& ptr = st.m_cells[px][py];
+                if (!ptr.m_reference) continue;
+                d.patches++;
+                const Array2D<PointAccumulator>& patch = *ptr;
+                for (int lx = 0; lx < 32; lx++)
+                    for (int ly = 0; ly < 32; ly++) {
+                        const PointAccumulator& a = patch.m_cells[lx][ly];
+                        if (!a.visits && !a.n) continue;
+                        int32_t wx = px * 32 + lx - c.x, wy = py * 32 + ly - c.y;
+                        d.cells++; d.sum_n += a.n; d.sum_visits += a.visits; d.sum_accx += a.acc.x; d.sum_accy += a.acc.y;
+                        uint64_t key = ((uint64_t)(uint32_t)wx << 32) | (uint32_t)wy;
+                        d.hash_counts += mix64(key ^ mix64(((uint64_t)(uint32_t)a.n << 32) | (uint32_t)a.visits));
+                        uint32_t ax, ay; memcpy(&ax, &a.acc.x, 4); memcpy(&ay, &a.acc.y, 4);
+                        d.hash_acc += mix64(key ^ mix64(((uint64_t)ax << 32) | ay) ^ 0x5555);
+                        if (full) { int32_t row[6] = {wx, wy, a.n, a.visits, (int32_t)ax, (int32_t)ay}; full->insert(full->end(), row, row + 6); }
+                    }
+            }
+        return d;
+    }
+    void dumpMaps(bool full_first) {
+        if (!w.f) return;
+        std::vector<MapDigest> ds;
+        for (size_t i = 0; i < m_particles.size(); i++) ds.push_back(digest(m_particles[i].map, nullptr));
+        w.vec("MDIG", ds);
+        std::vector<int32_t> geo;
+        for (auto& p : m_particles) {
+            IntPoint c = p.map.world2map(p.map.getCenter());
+            int32_t row[6] = {c.x, c.y, p.map.getMapSizeX(), p.map.getMapSizeY(), p.map.storage().getXSize(), p.map.storage().getYSize()};
+            geo.insert(geo.end(), row, row + 6);
+        }
+        w.vec("MGEO", geo);
+        if (full_first) {
+            int bi = getBestParticleIndex();
+            std::vector<int32_t> cells; cells.push_back(bi);
+            digest(m_particles[bi].map, &cells);
+            w.vec("MCEL", cells);
+        }
+    }
+    size_t size() const { return m_particles.size(); }
+    int count() const { return m_count; }
+};
+
+bool arg(int& i, int argc, char** argv, const char* name, std::string& v) {
+    if (strcmp(argv[i], name)) return false;
+    if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", name); exit(2); }
+    v = argv[++i]; return true;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    Opts o;
+    for (int i = 1; i < argc; i++) {
+        std::string v;
+#define S(flag, field) if (arg(i, argc, argv, flag, v)) { o.field = v; continue; }
+#define I(flag, field) if (arg(i, argc, argv, flag, v)) { o.field = atoi(v.c_str()); continue; }
+#define D(flag, field) if (arg(i, argc, argv, flag, v)) { o.field = atof(v.c_str()); continue; }
+        S("-mode", mode) S("-log", log) S("-out", out)
+        I("-particles", particles) I("-scans", max_scans) I("-maps-every", maps_every) I("-seed", seed) I("-probe", probe_particles)
+        D("-xmin", xmin) D("-ymin", ymin) D("-xmax", xmax) D("-ymax", ymax) D("-delta", delta)
+        D("-sigma", sigma) D("-maxrange", maxrange) D("-maxUrange", maxurange) D("-lstep", lstep) D("-astep", astep)
+        D("-lsigma", lsigma) D("-ogain", ogain) I("-kernelSize", kernel) I("-iterations", iterations) I("-lskip", lskip)
+        D("-srr", srr) D("-srt", srt) D("-str", str) D("-stt", stt)
+        D("-linearUpdate", linear_update) D("-angularUpdate", angular_update) D("-resampleThreshold", resample_thr)
+        D("-minimumScore", min_score) D("-period", period)
+        if (!strcmp(argv[i], "-no-generateMap")) { o.generate_map = false; continue; }
+        if (!strcmp(argv[i], "-init-zero")) { o.init_from_log = false; continue; }
+        if (!strcmp(argv[i], "-verbose")) { o.quiet = false; continue; }
+        fprintf(stderr, "unknown flag %s\n", argv[i]); return 2;
+    }
+    if (o.log.empty()) { fprintf(stderr, "usage: ref_driver -mode trace|time -log file.log [-out trace.bin] ...\n"); return 2; }
+
+    // silence the reference's unconditional cerr/cout chatter (gridslamprocessor.hxx:224-297)
+    std::ofstream devnull("/dev/null");
+    std::streambuf* old_cerr = std::cerr.rdbuf();
+    std::streambuf* old_cout = std::cout.rdbuf();
+    if (o.quiet) { std::cerr.rdbuf(devnull.rdbuf()); std::cout.rdbuf(devnull.rdbuf()); }
+
+    std::ifstream cfg_is(o.log.c_str());
+    if (!cfg_is) { fprintf(stderr, "cannot open %s\n", o.log.c_str()); return 1; }
+    CarmenConfiguration conf;
+    conf.load(cfg_is);
+    cfg_is.close();
+    SensorMap sensorMap = conf.computeSensorMap();
+
+    std::ifstream is(o.log.c_str());
+    InputSensorStream input(sensorMap, is);
+
+    std::ostream* info = o.quiet ? static_cast<std::ostream*>(&devnull) : &std::cout;
+    TraceProcessor gsp(*info);
+    gsp.probe_particles = o.probe_particles;
+    gsp.setSensorMap(sensorMap);
+    gsp.setMatchingParameters(o.maxurange, o.maxrange, o.sigma, o.kernel, o.lstep, o.astep, o.iterations, o.lsigma, o.ogain, o.lskip);
+    gsp.setMotionModelParameters(o.srr, o.srt, o.str, o.stt);
+    gsp.setUpdateDistances(o.linear_update, o.angular_update, o.resample_thr);
+    gsp.setUpdatePeriod(o.period);
+    gsp.setgenerateMap(o.generate_map);
+    gsp.setminimumScore(o.min_score);
+
+    bool inited = false;
+    if (o.mode == "trace" && !o.out.empty()) {
+        gsp.w.f = fopen(o.out.c_str(), "wb");
+        if (!gsp.w.f) { fprintf(stderr, "cannot write %s\n", o.out.c_str()); return 1; }
+    }
+
+    std::vector<double> ms;
+    int processed_n = 0, read_n = 0;
+    while (input && processed_n < o.max_scans) {
+        const SensorReading* r = nullptr;
+        input >> r;
+        if (!r) continue;
+        const RangeReading* rr = dynamic_cast<const RangeReading*>(r);
+        if (!rr) { delete r; continue; }
+        if (!inited) {
+            OrientedPoint init = o.init_from_log ? rr->getPose() : OrientedPoint(0, 0, 0);
+            gsp.GridSlamProcessor::init(o.particles, o.xmin, o.ymin, o.xmax, o.ymax, o.delta, init);
+            sampleGaussian(1, o.seed);  // srand48(seed), as gsp_thread.cpp:393-394 / slam_gmapping.cpp:676
+            if (gsp.w.f) {
+                double hdr[8] = {(double)o.particles, (double)rr->size(), init.x, init.y, init.theta, o.delta, (double)o.seed, 0};
+                gsp.w.rec("HEAD", hdr, sizeof hdr);
+                std::vector<double> ang(gsp.m_matcher.laserAngles(), gsp.m_matcher.laserAngles() + gsp.m_matcher.laserBeams());
+                gsp.w.vec("ANGL", ang);
+            }
+            inited = true;
+        }
+        std::vector<double> plain(rr->begin(), rr->end());
+        gsp.cur_ranges = plain.data();
+        gsp.resampled = false;
+        if (gsp.w.f) {
+            double rd[4] = {rr->getPose().x, rr->getPose().y, rr->getPose().theta, rr->getTime()};
+            gsp.w.rec("READ", rd, sizeof rd);
+            gsp.w.vec("RNGS", plain);
+        }
+        auto t0 = std::chrono::steady_clock::now();
+        bool processed = gsp.processScan(*rr);
+        auto t1 = std::chrono::steady_clock::now();
+        read_n++;
+        if (gsp.w.f) {
+            gsp.w.vec("ODOM", gsp.pre_pose);
+            int32_t flags[2] = {processed ? 1 : 0, gsp.resampled ? 1 : 0};
+            gsp.w.rec("PROC", flags, sizeof flags);
+        }
+        if (processed) {
+            ms.push_back(std::chrono::duration<double, std::milli>(t1 - t0).count());
+            processed_n++;
+            gsp.dumpState();
+            if (o.maps_every > 0 && (processed_n % o.maps_every == 0 || processed_n == 1)) gsp.dumpMaps(false);
+        }
+        // the filter keeps a pointer to its own copy of the reading (gridslamprocessor.cpp:556-561)
+        delete r;
+    }
+    if (gsp.w.f) {
+        gsp.dumpMaps(true);
+        gsp.w.rec("DONE", nullptr, 0);
+        fclose(gsp.w.f);
+    }
+    std::cerr.rdbuf(old_cerr);
+    std::cout.rdbuf(old_cout);
+    double sum = 0, sum_sm = 0;
+    for (size_t i = 0; i < ms.size(); i++) { sum += ms[i]; if (i > 0) sum_sm += ms[i]; }
+    // JSON on stdout: mean over processed scans; `ms_matched` excludes the first (registration-only) scan
+    printf("{\"impl\": \"reference\", \"particles\": %d, \"read\": %d, \"processed\": %d, \"ms_total\": %.3f, "
+           "\"ms_per_scan\": %.4f, \"ms_per_matched_scan\": %.4f}\n",
+           o.particles, read_n, processed_n, sum, ms.empty() ? 0.0 : sum / ms.size(),
+           ms.size() > 1 ? sum_sm / (ms.size() - 1) : 0.0);
+    return 0;
+}
