@@ -1,0 +1,143 @@
+/* gm_b200.h -- C ABI of the B200-native GMapping per-scan particle update.
+ *
+ * One gm_ctx per GMapping::GridSlamProcessor (per GPU).  The context owns, in HBM: the patch pool
+ * (32x32-cell patches of 16-byte cells), per-particle patch directories + map geometry, refcounts,
+ * the beam table and the matcher parameters.  The host owns poses, weights, the trajectory tree and
+ * the drand48 stream.
+ *
+ * All entry points: plain pointers and sizes, host buffers owned by the caller and copied during the
+ * call, return 0 on success or a negative gm_status; gm_last_error() gives the message.  Calls on one
+ * context are serialised by the caller (the reference is single-threaded per processor) and are
+ * synchronous at return.  There is NO CPU fallback: without a CUDA device gm_create fails.
+ *
+ * "replaces:" cites the reference code each entry point stands in for (paths relative to
+ * openslam_gmapping/ in the reference tree).
+ */
+#ifndef GM_B200_H
+#define GM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GM_MAXBEAMS 2048 /* LASER_MAXBEAMS, include/gmapping/scanmatcher/scanmatcher.h:11 */
+#define GM_PATCH 32      /* 2^5 cells per patch side, include/gmapping/grid/harray2d.h:28 */
+
+typedef enum gm_status {
+    GM_OK = 0,
+    GM_ERR_CUDA = -1,       /* a CUDA runtime call failed */
+    GM_ERR_ARG = -2,        /* bad argument / call order */
+    GM_ERR_POOL = -3,       /* patch pool exhausted */
+    GM_ERR_NO_DEVICE = -4,  /* no usable CUDA device (there is no CPU path) */
+    GM_ERR_LINE = -5        /* a ray longer than the reference's 20000-point buffer (scanmatcher.cpp:55) */
+} gm_status;
+
+typedef struct gm_ctx gm_ctx;
+
+typedef struct gm_config {
+    int32_t device;         /* CUDA device ordinal */
+    uint32_t max_particles; /* capacity; gm_init_particles may use fewer */
+    uint64_t pool_patches;  /* patch-pool capacity (16 KiB each); 0 = size from free HBM */
+    uint32_t block_threads; /* threads per particle CTA, 0 = default (256) */
+    uint32_t flags;         /* reserved, 0 */
+} gm_config;
+
+/* replaces: the ScanMatcher parameter block, include/gmapping/scanmatcher/scanmatcher.h:61-82,
+ * defaults scanmatcher/scanmatcher.cpp:17-56, setMatchingParameters scanmatcher.cpp:872-883 */
+typedef struct gm_match_params {
+    double laser_max_range, usable_range, gaussian_sigma, likelihood_sigma;
+    int32_t kernel_size;
+    int32_t generate_map;
+    double opt_linear_delta, opt_angular_delta;
+    uint32_t opt_recursive_iterations, likelihood_skip;
+    double enlarge_step, fullness_threshold, angular_odometry_reliability, linear_odometry_reliability, free_cell_ratio;
+    uint32_t initial_beams_skip;
+    uint32_t reserved;
+} gm_match_params;
+
+/* the reference's cell, include/gmapping/scanmatcher/smmap.h:35-36 (sizeof == 16) */
+typedef struct gm_cell { float acc_x, acc_y; int32_t n, visits; } gm_cell;
+
+/* per-particle map geometry, include/gmapping/grid/map.h:137-141 */
+typedef struct gm_map_info {
+    double center_x, center_y, delta;
+    int32_t size_x2, size_y2;     /* m_sizeX2 / m_sizeY2 */
+    int32_t patches_x, patches_y; /* directory dims (storage xsize/ysize); map size = patches << 5 */
+    int32_t allocated_patches;
+    int32_t reserved;
+} gm_map_info;
+
+/* order-independent map digest in world-cell coordinates (test / consistency aid) */
+typedef struct gm_digest {
+    int64_t patches, cells, sum_n, sum_visits;
+    uint64_t hash_counts, hash_acc;
+} gm_digest;
+
+typedef struct gm_stats {
+    uint64_t pool_capacity, pool_in_use;
+    uint64_t score_evals;     /* sum over particles of score() evaluations in the last gm_scanmatch (incl. the initial one) */
+    uint64_t beam_evals;      /* (particle, pose, valid beam) window searches in the last gm_scanmatch incl. likelihoodAndScore */
+    uint64_t cow_copies, patch_allocs; /* last gm_register */
+    uint64_t free_updates, hit_updates; /* last gm_register: visits++ along rays / endpoint updates */
+    uint64_t resizes;         /* particles whose map was resized in the last gm_register */
+    float ms_scanmatch, ms_register, ms_remap, ms_weights; /* CUDA-event device time of the last calls */
+    uint32_t launches;        /* kernels launched by this context since gm_create */
+    uint32_t reserved;
+} gm_stats;
+
+int gm_create(gm_ctx** out, const gm_config* cfg);
+int gm_destroy(gm_ctx* ctx);
+const char* gm_last_error(const gm_ctx* ctx); /* ctx may be NULL: last gm_create failure */
+
+/* replaces: ScanMatcher::setLaserParameters, scanmatcher/scanmatcher.cpp:699-709 */
+int gm_set_laser(gm_ctx* ctx, uint32_t nbeams, const double* angles, const double laser_pose[3]);
+/* replaces: ScanMatcher::setMatchingParameters + the PARAM_SET_GET setters */
+int gm_set_matching(gm_ctx* ctx, const gm_match_params* p);
+void gm_default_matching(gm_match_params* p);
+
+/* replaces: GridSlamProcessor::init's map/particle construction, gridfastslam/gridslamprocessor.cpp:354-403
+ * (Map(center, worldSizeX, worldSizeY, delta), include/gmapping/grid/map.h:171-184) */
+int gm_init_particles(gm_ctx* ctx, uint32_t n, const double center[2], double world_w, double world_h, double delta);
+
+/* replaces: ScanMatcher::score, include/gmapping/scanmatcher/scanmatcher.h:171-259, for `count`
+ * (particle map, pose) queries.  particle_idx[i] selects whose map is read. */
+int gm_score(gm_ctx* ctx, uint32_t count, const uint32_t* particle_idx, const double* poses /*count*3*/,
+             const double* ranges, double* score_out);
+/* replaces: ScanMatcher::likelihoodAndScore, scanmatcher.h:271-380 */
+int gm_likelihood_and_score(gm_ctx* ctx, uint32_t count, const uint32_t* particle_idx, const double* poses,
+                            const double* ranges, double* s_out, double* l_out, uint32_t* c_out);
+
+/* replaces: GridSlamProcessor::scanMatch, include/gmapping/gridfastslam/gridslamprocessor.hxx:15-75
+ * (ScanMatcher::optimize scanmatcher.cpp:386-529, then likelihoodAndScore at the accepted pose).
+ * poses_inout: N*3 motion-model poses in, scan-matched poses out (kept when score <= minimum_score).
+ * score_out: optimize()'s return; s_out/l_out/c_out: likelihoodAndScore at the final pose;
+ * evals_out: number of score() evaluations per particle.  Any *_out may be NULL. */
+int gm_scanmatch(gm_ctx* ctx, const double* ranges, double* poses_inout, double minimum_score,
+                 double* score_out, double* s_out, double* l_out, uint32_t* c_out, uint32_t* evals_out);
+
+/* replaces: GridSlamProcessor::normalize, gridslamprocessor.hxx:82-121 (sequential sums kept) */
+int gm_normalize_neff(gm_ctx* ctx, const double* log_weights, uint32_t n, double obs_sigma_gain,
+                      double* weights_out, double* neff_out);
+/* replaces: uniform_resampler<double,double>::resampleIndexes, include/gmapping/particlefilter/particlefilter.h:180-229;
+ * u01 is the caller's drand48() draw.  emitted_out: how many indexes the walk produced (== n normally). */
+int gm_resample_indexes(gm_ctx* ctx, const double* weights, uint32_t n, double u01, uint32_t* idx_out, uint32_t* emitted_out);
+
+/* replaces: the particle-copy + registerScan loops of GridSlamProcessor::resample, gridslamprocessor.hxx:184-296,
+ * and the first-scan loop gridslamprocessor.cpp:617-633: (optional) remap particle j <- parent idx[j] by
+ * patch-reference copy, then computeActiveArea (scanmatcher.cpp:83-254) + registerScan (:266-354) for all. */
+int gm_register(gm_ctx* ctx, const double* ranges, const double* poses /*N*3*/, const uint32_t* idx_or_null);
+
+/* replaces: host access to Particle::map (ScanMatcherMap cells / geometry).  Fills up to max_patches patches:
+ * patch_coords[2k..2k+1] = (px,py) and cells[k*1024 + lx*32 + ly].  Returns patch count via info. */
+int gm_map_info_get(gm_ctx* ctx, uint32_t particle, gm_map_info* info);
+int gm_download_map(gm_ctx* ctx, uint32_t particle, gm_map_info* info, int32_t* patch_coords, gm_cell* cells, uint32_t max_patches);
+int gm_map_digest(gm_ctx* ctx, uint32_t first, uint32_t count, gm_digest* out /*count*/);
+
+int gm_get_stats(gm_ctx* ctx, gm_stats* out);
+uint32_t gm_particles(const gm_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -563,7 +563,7 @@ struct orc_filter {
     double *weights, *pre_poses, *match_rows;
     uint32_t* indexes;
     int last_resampled;
-    double neff_at_resample, *w_at_resample;
+    double neff_at_resample, *w_at_resample, last_u01;
 };
 
 /* GridSlamProcessor::init: gridslamprocessor.cpp:354-403 */
@@ -649,6 +649,7 @@ int orc_filter_process(orc_filter* f, const double* ranges, const double rel[3],
                 f->neff_at_resample = f->neff;
                 memcpy(f->w_at_resample, f->weights, sizeof(double) * f->n);
                 double u = drand48();
+                f->last_u01 = u;
                 orc_resample_indexes(f->weights, f->n, u, f->indexes);
                 orc_particle* np = (orc_particle*)calloc(f->n, sizeof(orc_particle));
                 for (uint32_t i = 0; i < f->n; i++) {
@@ -713,3 +714,4 @@ int orc_filter_best(const orc_filter* f) { /* gridslamprocessor.cpp:677-688 */
     return (int)bi;
 }
 orc_matcher* orc_filter_matcher(orc_filter* f) { return &f->sm; }
+double orc_filter_last_u01(const orc_filter* f) { return f->last_u01; }

@@ -99,6 +99,8 @@ int orc_filter_last_resampled(const orc_filter* f, uint32_t* idx_out, double* ne
 const orc_map* orc_filter_map(const orc_filter* f, uint32_t i);
 int orc_filter_best(const orc_filter* f);
 orc_matcher* orc_filter_matcher(orc_filter* f);
+/* the drand48() draw consumed by the last resample (particlefilter.h:199) */
+double orc_filter_last_u01(const orc_filter* f);
 
 #ifdef __cplusplus
 }

@@ -101,6 +101,7 @@ def lib():
     L.orc_filter_map.restype = vp; L.orc_filter_map.argtypes = [vp, C.c_uint32]
     L.orc_filter_best.restype = C.c_int; L.orc_filter_best.argtypes = [vp]
     L.orc_filter_matcher.restype = C.POINTER(Matcher); L.orc_filter_matcher.argtypes = [vp]
+    L.orc_filter_last_u01.restype = C.c_double; L.orc_filter_last_u01.argtypes = [vp]
     _lib = L
     return L
 
@@ -258,3 +259,6 @@ class Filter:
 
     def matcher(self):
         return lib().orc_filter_matcher(self.h).contents
+
+    def last_u01(self):
+        return lib().orc_filter_last_u01(self.h)

@@ -1,0 +1,223 @@
+"""ctypes binding of libgm_b200.so (include/gm_b200.h).  Plumbing only: every call goes to the CUDA
+library; if the library or a B200 is missing this raises -- there is no CPU path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgm_b200.so")
+
+EXPORTS = ["gm_create", "gm_destroy", "gm_last_error", "gm_set_laser", "gm_set_matching", "gm_default_matching",
+           "gm_init_particles", "gm_score", "gm_likelihood_and_score", "gm_scanmatch", "gm_normalize_neff",
+           "gm_resample_indexes", "gm_register", "gm_map_info_get", "gm_download_map", "gm_map_digest",
+           "gm_get_stats", "gm_particles"]
+
+
+class GmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("gm_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_particles", C.c_uint32), ("pool_patches", C.c_uint64),
+                ("block_threads", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class MatchParams(C.Structure):
+    _fields_ = [("laser_max_range", C.c_double), ("usable_range", C.c_double), ("gaussian_sigma", C.c_double),
+                ("likelihood_sigma", C.c_double), ("kernel_size", C.c_int32), ("generate_map", C.c_int32),
+                ("opt_linear_delta", C.c_double), ("opt_angular_delta", C.c_double),
+                ("opt_recursive_iterations", C.c_uint32), ("likelihood_skip", C.c_uint32),
+                ("enlarge_step", C.c_double), ("fullness_threshold", C.c_double),
+                ("angular_odometry_reliability", C.c_double), ("linear_odometry_reliability", C.c_double),
+                ("free_cell_ratio", C.c_double), ("initial_beams_skip", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class MapInfo(C.Structure):
+    _fields_ = [("center_x", C.c_double), ("center_y", C.c_double), ("delta", C.c_double),
+                ("size_x2", C.c_int32), ("size_y2", C.c_int32), ("patches_x", C.c_int32), ("patches_y", C.c_int32),
+                ("allocated_patches", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("pool_capacity", C.c_uint64), ("pool_in_use", C.c_uint64), ("score_evals", C.c_uint64),
+                ("beam_evals", C.c_uint64), ("cow_copies", C.c_uint64), ("patch_allocs", C.c_uint64),
+                ("free_updates", C.c_uint64), ("hit_updates", C.c_uint64), ("resizes", C.c_uint64),
+                ("ms_scanmatch", C.c_float), ("ms_register", C.c_float), ("ms_remap", C.c_float), ("ms_weights", C.c_float),
+                ("launches", C.c_uint32), ("reserved", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+CELL_DTYPE = np.dtype([("ax", "<f4"), ("ay", "<f4"), ("n", "<i4"), ("visits", "<i4")])
+DIGEST_DTYPE = np.dtype([("patches", "<i8"), ("cells", "<i8"), ("sum_n", "<i8"), ("sum_visits", "<i8"),
+                         ("hash_counts", "<u8"), ("hash_acc", "<u8")])
+
+_lib = None
+
+
+def load_library(path=LIB_PATH):
+    """dlopen the CUDA library.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise GmError(-4, "%s is missing: build it with `python slam-gmapping-learn_b200/build.py` (no CPU fallback exists)" % path)
+    L = C.CDLL(path)
+    dp, up, vp = C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.c_void_p
+    L.gm_create.argtypes = [C.POINTER(vp), C.POINTER(Config)]
+    L.gm_destroy.argtypes = [vp]
+    L.gm_last_error.restype = C.c_char_p; L.gm_last_error.argtypes = [vp]
+    L.gm_set_laser.argtypes = [vp, C.c_uint32, dp, dp]
+    L.gm_set_matching.argtypes = [vp, C.POINTER(MatchParams)]
+    L.gm_default_matching.restype = None; L.gm_default_matching.argtypes = [C.POINTER(MatchParams)]
+    L.gm_init_particles.argtypes = [vp, C.c_uint32, dp, C.c_double, C.c_double, C.c_double]
+    L.gm_score.argtypes = [vp, C.c_uint32, up, dp, dp, dp]
+    L.gm_likelihood_and_score.argtypes = [vp, C.c_uint32, up, dp, dp, dp, dp, up]
+    L.gm_scanmatch.argtypes = [vp, dp, dp, C.c_double, dp, dp, dp, up, up]
+    L.gm_normalize_neff.argtypes = [vp, dp, C.c_uint32, C.c_double, dp, dp]
+    L.gm_resample_indexes.argtypes = [vp, dp, C.c_uint32, C.c_double, up, up]
+    L.gm_register.argtypes = [vp, dp, dp, up]
+    L.gm_map_info_get.argtypes = [vp, C.c_uint32, C.POINTER(MapInfo)]
+    L.gm_download_map.argtypes = [vp, C.c_uint32, C.POINTER(MapInfo), vp, vp, C.c_uint32]
+    L.gm_map_digest.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
+    L.gm_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.gm_particles.restype = C.c_uint32; L.gm_particles.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _up(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class GmContext:
+    """One gm_ctx: a particle set with its maps on one GPU."""
+
+    def __init__(self, max_particles, device=0, pool_patches=0, block_threads=0):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        cfg = Config(device, max_particles, pool_patches, block_threads, 0)
+        rc = self.L.gm_create(C.byref(self.h), C.byref(cfg))
+        if rc:
+            raise GmError(rc, self.L.gm_last_error(None).decode())
+        self.nbeams = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.gm_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise GmError(rc, self.L.gm_last_error(self.h).decode())
+
+    # ---- configuration
+    def set_laser(self, angles, laser_pose=(0., 0., 0.)):
+        a = _f64(angles); lp = _f64(laser_pose)
+        self._ck(self.L.gm_set_laser(self.h, len(a), _dp(a), _dp(lp)))
+        self.nbeams = len(a)
+
+    def default_matching(self):
+        p = MatchParams(); self.L.gm_default_matching(C.byref(p)); return p
+
+    def set_matching(self, urange=80., range_=80., sigma=0.05, kernel=1, lopt=0.05, aopt=0.05, iterations=5, lsigma=0.075,
+                     lskip=0, generate_map=True, **extra):
+        """ScanMatcher::setMatchingParameters (reference scanmatcher.cpp:872-883) + setgenerateMap."""
+        p = self.default_matching()
+        p.usable_range = urange; p.laser_max_range = range_; p.gaussian_sigma = sigma; p.kernel_size = kernel
+        p.opt_linear_delta = lopt; p.opt_angular_delta = aopt; p.opt_recursive_iterations = iterations
+        p.likelihood_sigma = lsigma; p.likelihood_skip = lskip; p.generate_map = 1 if generate_map else 0
+        for k, v in extra.items():
+            setattr(p, k, v)
+        self._ck(self.L.gm_set_matching(self.h, C.byref(p)))
+        self.params = p
+
+    def init_particles(self, n, bounds=(-100., -100., 100., 100.), delta=0.05):
+        xmin, ymin, xmax, ymax = bounds
+        c = _f64([(xmin + xmax) * .5, (ymin + ymax) * .5])
+        self._ck(self.L.gm_init_particles(self.h, n, _dp(c), xmax - xmin, ymax - ymin, delta))
+        self.n = n
+
+    # ---- stages
+    def _ranges(self, ranges):
+        r = _f64(ranges)
+        assert r.shape == (self.nbeams,), "expected %d ranges" % self.nbeams
+        return r
+
+    def score(self, particle_idx, poses, ranges):
+        idx = np.ascontiguousarray(particle_idx, dtype=np.uint32); p = _f64(poses).reshape(-1, 3); r = self._ranges(ranges)
+        out = np.zeros(len(idx))
+        self._ck(self.L.gm_score(self.h, len(idx), _up(idx), _dp(p), _dp(r), _dp(out)))
+        return out
+
+    def likelihood_and_score(self, particle_idx, poses, ranges):
+        idx = np.ascontiguousarray(particle_idx, dtype=np.uint32); p = _f64(poses).reshape(-1, 3); r = self._ranges(ranges)
+        s = np.zeros(len(idx)); l = np.zeros(len(idx)); c = np.zeros(len(idx), dtype=np.uint32)
+        self._ck(self.L.gm_likelihood_and_score(self.h, len(idx), _up(idx), _dp(p), _dp(r), _dp(s), _dp(l), _up(c)))
+        return s, l, c
+
+    def scanmatch(self, ranges, poses, minimum_score=0.0):
+        """-> (poses, score, s, l, c, evals)"""
+        r = self._ranges(ranges); p = _f64(poses).reshape(self.n, 3).copy()
+        sc = np.zeros(self.n); s = np.zeros(self.n); l = np.zeros(self.n)
+        c = np.zeros(self.n, dtype=np.uint32); ev = np.zeros(self.n, dtype=np.uint32)
+        self._ck(self.L.gm_scanmatch(self.h, _dp(r), _dp(p), float(minimum_score), _dp(sc), _dp(s), _dp(l), _up(c), _up(ev)))
+        return p, sc, s, l, c, ev
+
+    def normalize(self, log_weights, obs_sigma_gain=1.0):
+        lw = _f64(log_weights); w = np.zeros_like(lw); ne = C.c_double()
+        self._ck(self.L.gm_normalize_neff(self.h, _dp(lw), len(lw), float(obs_sigma_gain), _dp(w), C.byref(ne)))
+        return w, ne.value
+
+    def resample_indexes(self, weights, u01):
+        w = _f64(weights); idx = np.zeros(len(w), dtype=np.uint32); em = C.c_uint32()
+        self._ck(self.L.gm_resample_indexes(self.h, _dp(w), len(w), float(u01), _up(idx), C.byref(em)))
+        return idx, em.value
+
+    def register(self, ranges, poses, idx=None):
+        r = self._ranges(ranges); p = _f64(poses).reshape(self.n, 3)
+        ip = None
+        if idx is not None:
+            idx = np.ascontiguousarray(idx, dtype=np.uint32); assert idx.shape == (self.n,)
+            ip = _up(idx)
+        self._ck(self.L.gm_register(self.h, _dp(r), _dp(p), ip))
+
+    # ---- read-back
+    def map_info(self, particle):
+        mi = MapInfo(); self._ck(self.L.gm_map_info_get(self.h, particle, C.byref(mi))); return mi
+
+    def download_map(self, particle):
+        mi = self.map_info(particle)
+        n = mi.allocated_patches
+        coords = np.zeros((n, 2), dtype=np.int32); cells = np.zeros((n, 1024), dtype=CELL_DTYPE)
+        if n:
+            self._ck(self.L.gm_download_map(self.h, particle, C.byref(mi), coords.ctypes.data, cells.ctypes.data, n))
+        return mi, coords, cells
+
+    def digests(self, first=0, count=None):
+        count = self.n - first if count is None else count
+        out = np.zeros(count, dtype=DIGEST_DTYPE)
+        self._ck(self.L.gm_map_digest(self.h, first, count, out.ctypes.data))
+        return out
+
+    def stats(self):
+        s = Stats(); self._ck(self.L.gm_get_stats(self.h, C.byref(s))); return s.as_dict()

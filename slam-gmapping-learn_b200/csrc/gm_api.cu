@@ -1,0 +1,551 @@
+// gm_api.cu -- the C ABI (include/gm_b200.h) over the sm_100a kernels of gm_kernels.cu.
+//
+// One gm_ctx owns, on one GPU: the patch pool, the per-particle patch directories (double buffered),
+// per-particle map geometry, the beam table and all staging buffers.  Every entry point copies the
+// caller's host buffers in, launches on the context's stream, copies results out and synchronises.
+// There is no CPU path: without a device gm_create fails with GM_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gm_b200.h"
+#include "gm_kernels.h"
+
+using namespace gm;
+
+static thread_local std::string g_create_error;
+
+struct gm_ctx {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint32_t max_particles = 0, n = 0, threads = 256;
+    DevParams P{};
+    bool laser_set = false, match_set = false, inited = false;
+    double angles_h[GM_MAXBEAMS];
+
+    Pool pool{};
+    int* refcnt_new = nullptr;
+    int *dir = nullptr, *dir_alt = nullptr;
+    int dir_cap = 0;
+    Geom *geom = nullptr, *geom_alt = nullptr, *geom_new = nullptr;
+    int4* shift = nullptr;
+
+    double *d_ranges = nullptr, *d_angles = nullptr, *d_poses = nullptr;
+    double *d_score = nullptr, *d_s = nullptr, *d_l = nullptr;
+    unsigned *d_c = nullptr, *d_evals = nullptr, *d_idx = nullptr, *d_emitted = nullptr;
+    double *d_w = nullptr, *d_logw = nullptr, *d_cum = nullptr, *d_tgt = nullptr, *d_neff = nullptr;
+    // query staging (gm_score / gm_likelihood_and_score)
+    unsigned* d_qidx = nullptr; double *d_qposes = nullptr, *d_qs = nullptr, *d_ql = nullptr; unsigned* d_qc = nullptr;
+    uint32_t q_cap = 0;
+    Counters* d_counters = nullptr;
+    unsigned long long* d_digest = nullptr;
+    int *d_list = nullptr, *d_count = nullptr; int4* d_export = nullptr; size_t export_cap = 0; size_t list_cap = 0;
+
+    gm_stats stats{};
+    std::string err;
+    size_t register_smem = 0;
+};
+
+namespace {
+
+int fail(gm_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) return fail(ctx, GM_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T> cudaError_t dalloc(T*& p, size_t count) {
+    if (p) { cudaFree(p); p = nullptr; }
+    return cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T));
+}
+
+int bind(gm_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    return GM_OK;
+}
+
+int read_counters(gm_ctx* ctx, Counters& h) {
+    CK(cudaMemcpyAsync(&h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return GM_OK;
+}
+
+int zero_counters(gm_ctx* ctx) {
+    CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->st));
+    return GM_OK;
+}
+
+int check_launch(gm_ctx* ctx, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, GM_ERR_CUDA, "launch %s: %s", what, cudaGetErrorString(e));
+    return GM_OK;
+}
+
+unsigned count_score_beams(const gm_ctx* ctx, const double* ranges) {
+    const DevParams& P = ctx->P;
+    unsigned v = 0;
+    for (unsigned b = P.beam_skip; b < P.nbeams; b++) {
+        if (((b - P.beam_skip + 1u) % (P.lskip + 1u)) != 0u) continue;
+        double r = ranges[b];
+        if (r > P.usable_range || r == 0.0) continue;
+        v++;
+    }
+    return v;
+}
+
+int ensure_query(gm_ctx* ctx, uint32_t count) {
+    if (count <= ctx->q_cap) return GM_OK;
+    CK(dalloc(ctx->d_qidx, count)); CK(dalloc(ctx->d_qposes, (size_t)count * 3));
+    CK(dalloc(ctx->d_qs, count)); CK(dalloc(ctx->d_ql, count)); CK(dalloc(ctx->d_qc, count));
+    ctx->q_cap = count;
+    return GM_OK;
+}
+
+int ready(gm_ctx* ctx, bool need_particles) {
+    if (!ctx) return GM_ERR_ARG;
+    if (!ctx->laser_set) return fail(ctx, GM_ERR_ARG, "gm_set_laser has not been called");
+    if (!ctx->match_set) return fail(ctx, GM_ERR_ARG, "gm_set_matching has not been called");
+    if (need_particles && !ctx->inited) return fail(ctx, GM_ERR_ARG, "gm_init_particles has not been called");
+    return bind(ctx);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gm_last_error(const gm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void gm_default_matching(gm_match_params* p) {  // scanmatcher.cpp:17-56
+    memset(p, 0, sizeof *p);
+    p->laser_max_range = 80; p->usable_range = 80; p->gaussian_sigma = 1; p->likelihood_sigma = 1;
+    p->kernel_size = 1; p->generate_map = 1;
+    p->opt_linear_delta = 0.05; p->opt_angular_delta = 0.1;
+    p->opt_recursive_iterations = 3; p->likelihood_skip = 0;
+    p->enlarge_step = 10.; p->fullness_threshold = 0.1;
+    p->angular_odometry_reliability = 0.; p->linear_odometry_reliability = 0.;
+    p->free_cell_ratio = sqrt(2.);
+    p->initial_beams_skip = 0;
+}
+
+int gm_create(gm_ctx** out, const gm_config* cfg) {
+    gm_ctx* ctx = nullptr;  // CK() reports into g_create_error while ctx is null
+    if (!out || !cfg) return fail(nullptr, GM_ERR_ARG, "gm_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(nullptr, GM_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, GM_ERR_ARG, "gm_create: device %d of %d", cfg->device, ndev);
+    if (!cfg->max_particles) return fail(nullptr, GM_ERR_ARG, "gm_create: max_particles == 0");
+    CK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) return fail(nullptr, GM_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+
+    gm_ctx* c = new gm_ctx();
+    c->device = cfg->device;
+    c->max_particles = cfg->max_particles;
+    c->threads = cfg->block_threads ? cfg->block_threads : 256;
+    if (c->threads % 32 || c->threads > 256 || c->threads < 32) { delete c; return fail(nullptr, GM_ERR_ARG, "block_threads must be a multiple of 32 in [32,256]"); }
+    ctx = c;
+#define CKC(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { fail(nullptr, GM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2_)); gm_destroy(c); return GM_ERR_CUDA; } } while (0)
+    CKC(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    CKC(cudaEventCreate(&c->ev0)); CKC(cudaEventCreate(&c->ev1));
+    size_t cap = cfg->pool_patches;
+    if (!cap) {
+        size_t free_b = 0, total_b = 0;
+        CKC(cudaMemGetInfo(&free_b, &total_b));
+        cap = (size_t)((double)free_b * 0.5 / (kPatchCells * sizeof(int4)));
+        cap = std::min<size_t>(cap, (size_t)1 << 22);  // 64 GiB of patches at most by default
+    }
+    if (cap > 0x7fffffff) cap = 0x7fffffff;
+    c->pool.cap = (int)cap;
+    CKC(dalloc(c->pool.cells, cap * kPatchCells));
+    CKC(dalloc(c->pool.refcnt, cap)); CKC(dalloc(c->pool.free_list, cap)); CKC(dalloc(c->pool.pending, cap));
+    CKC(dalloc(c->pool.free_top, 1)); CKC(dalloc(c->pool.pending_n, 1));
+    CKC(dalloc(c->refcnt_new, cap));
+    CKC(cudaMemsetAsync(c->refcnt_new, 0, cap * sizeof(int), c->st));
+    const uint32_t N = c->max_particles;
+    CKC(dalloc(c->geom, N)); CKC(dalloc(c->geom_alt, N)); CKC(dalloc(c->geom_new, N)); CKC(dalloc(c->shift, N));
+    CKC(dalloc(c->d_ranges, GM_MAXBEAMS)); CKC(dalloc(c->d_angles, GM_MAXBEAMS)); CKC(dalloc(c->d_poses, (size_t)N * 3));
+    CKC(dalloc(c->d_score, N)); CKC(dalloc(c->d_s, N)); CKC(dalloc(c->d_l, N));
+    CKC(dalloc(c->d_c, N)); CKC(dalloc(c->d_evals, N)); CKC(dalloc(c->d_idx, N)); CKC(dalloc(c->d_emitted, 1));
+    CKC(dalloc(c->d_counters, 1));
+    CKC(dalloc(c->d_digest, (size_t)N * 6));
+    CKC(dalloc(c->d_count, 1));
+    launch_pool_init(c->pool, c->st);
+    CKC(cudaGetLastError());
+    CKC(cudaStreamSynchronize(c->st));
+#undef CKC
+    c->stats.pool_capacity = cap;
+    c->stats.launches = 1;
+    *out = c;
+    return GM_OK;
+}
+
+int gm_destroy(gm_ctx* c) {
+    if (!c) return GM_OK;
+    cudaSetDevice(c->device);
+    if (c->st) cudaStreamSynchronize(c->st);
+    cudaFree(c->pool.cells); cudaFree(c->pool.refcnt); cudaFree(c->pool.free_list); cudaFree(c->pool.pending);
+    cudaFree(c->pool.free_top); cudaFree(c->pool.pending_n); cudaFree(c->refcnt_new);
+    cudaFree(c->dir); cudaFree(c->dir_alt); cudaFree(c->geom); cudaFree(c->geom_alt); cudaFree(c->geom_new); cudaFree(c->shift);
+    cudaFree(c->d_ranges); cudaFree(c->d_angles); cudaFree(c->d_poses); cudaFree(c->d_score); cudaFree(c->d_s); cudaFree(c->d_l);
+    cudaFree(c->d_c); cudaFree(c->d_evals); cudaFree(c->d_idx); cudaFree(c->d_emitted);
+    cudaFree(c->d_w); cudaFree(c->d_logw); cudaFree(c->d_cum); cudaFree(c->d_tgt); cudaFree(c->d_neff);
+    cudaFree(c->d_qidx); cudaFree(c->d_qposes); cudaFree(c->d_qs); cudaFree(c->d_ql); cudaFree(c->d_qc);
+    cudaFree(c->d_counters); cudaFree(c->d_digest); cudaFree(c->d_list); cudaFree(c->d_count); cudaFree(c->d_export);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->st) cudaStreamDestroy(c->st);
+    delete c;
+    return GM_OK;
+}
+
+int gm_set_laser(gm_ctx* ctx, uint32_t nbeams, const double* angles, const double laser_pose[3]) {
+    if (!ctx) return GM_ERR_ARG;
+    if (!angles || !laser_pose) return fail(ctx, GM_ERR_ARG, "gm_set_laser: null argument");
+    if (nbeams == 0 || nbeams >= GM_MAXBEAMS)  // the reference asserts beams < LASER_MAXBEAMS (scanmatcher.cpp:704)
+        return fail(ctx, GM_ERR_ARG, "gm_set_laser: %u beams (must be in [1, %d))", nbeams, GM_MAXBEAMS);
+    if (int r = bind(ctx)) return r;
+    ctx->P.nbeams = nbeams;
+    memcpy(ctx->angles_h, angles, sizeof(double) * nbeams);
+    for (int i = 0; i < 3; i++) ctx->P.laser_pose[i] = laser_pose[i];
+    CK(cudaMemcpyAsync(ctx->d_angles, angles, sizeof(double) * nbeams, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->laser_set = true;
+    return GM_OK;
+}
+
+int gm_set_matching(gm_ctx* ctx, const gm_match_params* p) {
+    if (!ctx) return GM_ERR_ARG;
+    if (!p) return fail(ctx, GM_ERR_ARG, "gm_set_matching: null argument");
+    if (p->kernel_size < 0 || p->kernel_size > 8) return fail(ctx, GM_ERR_ARG, "gm_set_matching: kernel_size %d outside [0,8]", p->kernel_size);
+    DevParams& P = ctx->P;
+    P.laser_max_range = p->laser_max_range; P.usable_range = p->usable_range;
+    P.gaussian_sigma = p->gaussian_sigma; P.likelihood_sigma = p->likelihood_sigma;
+    P.kernel_size = p->kernel_size; P.generate_map = p->generate_map;
+    P.opt_linear_delta = p->opt_linear_delta; P.opt_angular_delta = p->opt_angular_delta;
+    P.opt_iters = p->opt_recursive_iterations; P.lskip = p->likelihood_skip;
+    P.enlarge_step = p->enlarge_step; P.fullness_threshold = p->fullness_threshold;
+    P.ang_rel = p->angular_odometry_reliability; P.lin_rel = p->linear_odometry_reliability;
+    P.free_cell_ratio = p->free_cell_ratio; P.beam_skip = p->initial_beams_skip;
+    P.thr_is_tenth = (p->fullness_threshold == 0.1) ? 1 : 0;
+    ctx->match_set = true;
+    return GM_OK;
+}
+
+int gm_init_particles(gm_ctx* ctx, uint32_t n, const double center[2], double world_w, double world_h, double delta) {
+    if (!ctx) return GM_ERR_ARG;
+    if (!center || !n || n > ctx->max_particles || !(delta > 0)) return fail(ctx, GM_ERR_ARG, "gm_init_particles: bad argument (n=%u, max=%u)", n, ctx->max_particles);
+    if (int r = bind(ctx)) return r;
+    // Map(center, worldSizeX, worldSizeY, delta): map.h:171-184; HierarchicalArray2D(xsize>>5, ysize>>5): harray2d.h:54-59
+    const int xs = (int)ceil(world_w / delta), ys = (int)ceil(world_h / delta);
+    Geom g;
+    g.npx = xs >> kPatchMag; g.npy = ys >> kPatchMag;
+    if (g.npx <= 0 || g.npy <= 0) return fail(ctx, GM_ERR_ARG, "gm_init_particles: map smaller than one patch");
+    g.sx2 = (g.npx << kPatchMag) >> 1; g.sy2 = (g.npy << kPatchMag) >> 1;
+    ctx->P.cx = center[0]; ctx->P.cy = center[1]; ctx->P.delta = delta;
+    ctx->n = n;
+    ctx->dir_cap = g.npx * g.npy;
+    const size_t dn = (size_t)ctx->max_particles * ctx->dir_cap;
+    CK(dalloc(ctx->dir, dn)); CK(dalloc(ctx->dir_alt, dn));
+    launch_pool_init(ctx->pool, ctx->st);
+    launch_fill_int(ctx->dir, dn, -1, ctx->st);
+    launch_fill_int(ctx->dir_alt, dn, -1, ctx->st);
+    launch_fill_geom(ctx->geom, ctx->max_particles, g, ctx->st);
+    ctx->stats.launches += 4;
+    if (int r = check_launch(ctx, "init")) return r;
+    CK(cudaMemsetAsync(ctx->refcnt_new, 0, (size_t)ctx->pool.cap * sizeof(int), ctx->st));
+    CK(dalloc(ctx->d_w, ctx->max_particles)); CK(dalloc(ctx->d_logw, ctx->max_particles));
+    CK(dalloc(ctx->d_cum, ctx->max_particles)); CK(dalloc(ctx->d_tgt, ctx->max_particles)); CK(dalloc(ctx->d_neff, 1));
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->stats.pool_in_use = 0;
+    ctx->inited = true;
+    return GM_OK;
+}
+
+uint32_t gm_particles(const gm_ctx* ctx) { return ctx ? ctx->n : 0; }
+
+static int run_eval(gm_ctx* ctx, int mode, uint32_t count, const uint32_t* particle_idx, const double* poses,
+                    const double* ranges, double* s_out, double* l_out, uint32_t* c_out) {
+    if (int r = ready(ctx, true)) return r;
+    if (!count) return GM_OK;
+    if (!particle_idx || !poses || !ranges) return fail(ctx, GM_ERR_ARG, "eval: null argument");
+    for (uint32_t i = 0; i < count; i++)
+        if (particle_idx[i] >= ctx->n) return fail(ctx, GM_ERR_ARG, "eval: particle index %u >= %u", particle_idx[i], ctx->n);
+    if (int r = ensure_query(ctx, count)) return r;
+    CK(cudaMemcpyAsync(ctx->d_ranges, ranges, sizeof(double) * ctx->P.nbeams, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->d_qidx, particle_idx, sizeof(uint32_t) * count, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->d_qposes, poses, sizeof(double) * 3 * count, cudaMemcpyHostToDevice, ctx->st));
+    EvalArgs a;
+    a.P = ctx->P; a.ranges = ctx->d_ranges; a.angles = ctx->d_angles; a.particle_idx = ctx->d_qidx; a.poses = ctx->d_qposes;
+    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.mode = mode;
+    a.s = ctx->d_qs; a.l = ctx->d_ql; a.c = ctx->d_qc;
+    launch_eval(a, count, ctx->threads, ctx->st);
+    ctx->stats.launches++;
+    if (int r = check_launch(ctx, "k_eval")) return r;
+    if (s_out) CK(cudaMemcpyAsync(s_out, ctx->d_qs, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->st));
+    if (mode == 1 && l_out) CK(cudaMemcpyAsync(l_out, ctx->d_ql, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->st));
+    if (mode == 1 && c_out) CK(cudaMemcpyAsync(c_out, ctx->d_qc, sizeof(uint32_t) * count, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return GM_OK;
+}
+
+int gm_score(gm_ctx* ctx, uint32_t count, const uint32_t* particle_idx, const double* poses, const double* ranges, double* score_out) {
+    return run_eval(ctx, 0, count, particle_idx, poses, ranges, score_out, nullptr, nullptr);
+}
+
+int gm_likelihood_and_score(gm_ctx* ctx, uint32_t count, const uint32_t* particle_idx, const double* poses, const double* ranges,
+                            double* s_out, double* l_out, uint32_t* c_out) {
+    return run_eval(ctx, 1, count, particle_idx, poses, ranges, s_out, l_out, c_out);
+}
+
+int gm_scanmatch(gm_ctx* ctx, const double* ranges, double* poses_inout, double minimum_score, double* score_out, double* s_out,
+                 double* l_out, uint32_t* c_out, uint32_t* evals_out) {
+    if (int r = ready(ctx, true)) return r;
+    if (!ranges || !poses_inout) return fail(ctx, GM_ERR_ARG, "gm_scanmatch: null argument");
+    const uint32_t n = ctx->n;
+    CK(cudaMemcpyAsync(ctx->d_ranges, ranges, sizeof(double) * ctx->P.nbeams, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->d_poses, poses_inout, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->st));
+    if (int r = zero_counters(ctx)) return r;
+    ScanMatchArgs a;
+    a.P = ctx->P; a.ranges = ctx->d_ranges; a.angles = ctx->d_angles; a.poses = ctx->d_poses;
+    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells;
+    a.minimum_score = minimum_score;
+    a.score = ctx->d_score; a.s = ctx->d_s; a.l = ctx->d_l; a.c = ctx->d_c; a.evals = ctx->d_evals;
+    a.counters = ctx->d_counters;
+    a.valid_score_beams = count_score_beams(ctx, ranges);
+    CK(cudaEventRecord(ctx->ev0, ctx->st));
+    launch_scanmatch(a, n, ctx->threads, ctx->st);
+    CK(cudaEventRecord(ctx->ev1, ctx->st));
+    ctx->stats.launches++;
+    if (int r = check_launch(ctx, "k_scanmatch")) return r;
+    CK(cudaMemcpyAsync(poses_inout, ctx->d_poses, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->st));
+    if (score_out) CK(cudaMemcpyAsync(score_out, ctx->d_score, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->st));
+    if (s_out) CK(cudaMemcpyAsync(s_out, ctx->d_s, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->st));
+    if (l_out) CK(cudaMemcpyAsync(l_out, ctx->d_l, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->st));
+    if (c_out) CK(cudaMemcpyAsync(c_out, ctx->d_c, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->st));
+    if (evals_out) CK(cudaMemcpyAsync(evals_out, ctx->d_evals, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->st));
+    Counters h;
+    if (int r = read_counters(ctx, h)) return r;
+    ctx->stats.score_evals = h.score_evals; ctx->stats.beam_evals = h.beam_evals;
+    CK(cudaEventElapsedTime(&ctx->stats.ms_scanmatch, ctx->ev0, ctx->ev1));
+    return GM_OK;
+}
+
+int gm_normalize_neff(gm_ctx* ctx, const double* log_weights, uint32_t n, double obs_sigma_gain, double* weights_out, double* neff_out) {
+    if (int r = ready(ctx, true)) return r;
+    if (!log_weights || !n || n > ctx->max_particles) return fail(ctx, GM_ERR_ARG, "gm_normalize_neff: bad argument");
+    CK(cudaMemcpyAsync(ctx->d_logw, log_weights, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaEventRecord(ctx->ev0, ctx->st));
+    launch_normalize(ctx->d_logw, n, obs_sigma_gain, ctx->d_w, ctx->d_neff, ctx->st);
+    CK(cudaEventRecord(ctx->ev1, ctx->st));
+    ctx->stats.launches++;
+    if (int r = check_launch(ctx, "k_normalize")) return r;
+    if (weights_out) CK(cudaMemcpyAsync(weights_out, ctx->d_w, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->st));
+    if (neff_out) CK(cudaMemcpyAsync(neff_out, ctx->d_neff, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaEventElapsedTime(&ctx->stats.ms_weights, ctx->ev0, ctx->ev1));
+    return GM_OK;
+}
+
+int gm_resample_indexes(gm_ctx* ctx, const double* weights, uint32_t n, double u01, uint32_t* idx_out, uint32_t* emitted_out) {
+    if (int r = ready(ctx, true)) return r;
+    if (!weights || !idx_out || !n || n > ctx->max_particles) return fail(ctx, GM_ERR_ARG, "gm_resample_indexes: bad argument");
+    CK(cudaMemcpyAsync(ctx->d_w, weights, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemsetAsync(ctx->d_emitted, 0, sizeof(unsigned), ctx->st));
+    launch_resample(ctx->d_w, n, u01, ctx->d_cum, ctx->d_tgt, ctx->d_idx, ctx->d_emitted, ctx->st);
+    ctx->stats.launches++;
+    if (int r = check_launch(ctx, "k_resample")) return r;
+    CK(cudaMemcpyAsync(idx_out, ctx->d_idx, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->st));
+    uint32_t em = 0;
+    CK(cudaMemcpyAsync(&em, ctx->d_emitted, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    if (emitted_out) *emitted_out = em;
+    return GM_OK;
+}
+
+int gm_register(gm_ctx* ctx, const double* ranges, const double* poses, const uint32_t* idx) {
+    if (int r = ready(ctx, true)) return r;
+    if (!ranges || !poses) return fail(ctx, GM_ERR_ARG, "gm_register: null argument");
+    const uint32_t n = ctx->n;
+    if (idx)
+        for (uint32_t i = 0; i < n; i++)
+            if (idx[i] >= n) return fail(ctx, GM_ERR_ARG, "gm_register: parent index %u >= %u", idx[i], n);
+    CK(cudaMemcpyAsync(ctx->d_ranges, ranges, sizeof(double) * ctx->P.nbeams, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->d_poses, poses, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->st));
+    if (int r = zero_counters(ctx)) return r;
+    ctx->stats.ms_remap = 0.f;
+
+    // ---- particle copy by patch reference (gridslamprocessor.hxx:184-213)
+    if (idx) {
+        CK(cudaMemcpyAsync(ctx->d_idx, idx, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaEventRecord(ctx->ev0, ctx->st));
+        RemapArgs r;
+        r.idx = ctx->d_idx; r.geom = ctx->geom; r.geom_alt = ctx->geom_alt; r.dir = ctx->dir; r.dir_alt = ctx->dir_alt;
+        r.dir_cap = ctx->dir_cap; r.refcnt_new = ctx->refcnt_new;
+        launch_remap(r, n, ctx->st);
+        SweepArgs s; s.pool = ctx->pool; s.refcnt_new = ctx->refcnt_new;
+        launch_sweep(s, ctx->st);
+        launch_merge_free(ctx->pool, ctx->st);
+        CK(cudaEventRecord(ctx->ev1, ctx->st));
+        ctx->stats.launches += 3;
+        if (int rc = check_launch(ctx, "remap")) return rc;
+        std::swap(ctx->dir, ctx->dir_alt);
+        std::swap(ctx->geom, ctx->geom_alt);
+        CK(cudaStreamSynchronize(ctx->st));
+        CK(cudaEventElapsedTime(&ctx->stats.ms_remap, ctx->ev0, ctx->ev1));
+    }
+
+    // ---- computeActiveArea: bounding box + Map::resize (scanmatcher.cpp:96-166)
+    CK(cudaEventRecord(ctx->ev0, ctx->st));
+    BoundsArgs b;
+    b.P = ctx->P; b.ranges = ctx->d_ranges; b.angles = ctx->d_angles; b.poses = ctx->d_poses;
+    b.geom = ctx->geom; b.geom_new = ctx->geom_new; b.shift = ctx->shift; b.counters = ctx->d_counters;
+    launch_bounds(b, n, ctx->threads, ctx->st);
+    ctx->stats.launches++;
+    if (int rc = check_launch(ctx, "k_bounds")) return rc;
+    Counters h;
+    if (int rc = read_counters(ctx, h)) return rc;
+    if (h.error) return fail(ctx, h.error, "gm_register: a ray exceeds the reference's %d-point line buffer", kLineCap);
+    if (h.any_resize) {
+        RelayoutArgs r;
+        r.geom = ctx->geom; r.geom_new = ctx->geom_new; r.shift = ctx->shift;
+        r.dir = ctx->dir; r.dir_cap_old = ctx->dir_cap; r.pool = ctx->pool;
+        int new_cap = std::max(ctx->dir_cap, h.need_dir_cap);
+        int* grown = nullptr;
+        if (new_cap > ctx->dir_cap) {
+            // directory stride grows for everybody: dir_alt is re-allocated as scratch, a new buffer becomes dir
+            const size_t dn = (size_t)ctx->max_particles * new_cap;
+            CK(dalloc(ctx->dir_alt, dn));
+            CK(cudaMalloc(reinterpret_cast<void**>(&grown), dn * sizeof(int)));
+            launch_fill_int(grown, dn, -1, ctx->st);
+            ctx->stats.launches++;
+        }
+        r.dir_alt = ctx->dir_alt; r.dir_cap_new = new_cap; r.dir_out = grown ? grown : ctx->dir;
+        launch_relayout(r, n, ctx->st);
+        launch_relayout_commit(r, n, ctx->st);
+        launch_merge_free(ctx->pool, ctx->st);
+        ctx->stats.launches += 3;
+        if (int rc = check_launch(ctx, "relayout")) { if (grown) cudaFree(grown); return rc; }
+        CK(cudaStreamSynchronize(ctx->st));
+        if (grown) {
+            cudaFree(ctx->dir);
+            ctx->dir = grown;
+            ctx->dir_cap = new_cap;
+            launch_fill_int(ctx->dir_alt, (size_t)ctx->max_particles * new_cap, -1, ctx->st);
+            ctx->stats.launches++;
+        }
+    }
+
+    // ---- active area + copy-on-write + ray/endpoint updates (scanmatcher.cpp:168-354)
+    RegisterArgs a;
+    a.P = ctx->P; a.ranges = ctx->d_ranges; a.angles = ctx->d_angles; a.poses = ctx->d_poses;
+    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool; a.counters = ctx->d_counters;
+    a.bitmap_words = (ctx->dir_cap + 31) / 32;
+    int sort_n = 32;
+    while (sort_n < (int)ctx->P.nbeams) sort_n <<= 1;
+    a.sort_n = sort_n;
+    const size_t smem = register_smem_bytes(a.bitmap_words, a.sort_n);
+    if (smem > 200 * 1024) return fail(ctx, GM_ERR_ARG, "gm_register: patch directory of %d entries needs %zu B of shared memory", ctx->dir_cap, smem);
+    if (smem != ctx->register_smem) { CK(register_prepare(smem)); ctx->register_smem = smem; }
+    launch_register(a, n, ctx->threads, smem, ctx->st);
+    launch_merge_free(ctx->pool, ctx->st);
+    CK(cudaEventRecord(ctx->ev1, ctx->st));
+    ctx->stats.launches += 2;
+    if (int rc = check_launch(ctx, "k_register")) return rc;
+    if (int rc = read_counters(ctx, h)) return rc;
+    int top = 0;
+    CK(cudaMemcpyAsync(&top, ctx->pool.free_top, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaEventElapsedTime(&ctx->stats.ms_register, ctx->ev0, ctx->ev1));
+    ctx->stats.cow_copies = h.cow_copies; ctx->stats.patch_allocs = h.patch_allocs;
+    ctx->stats.free_updates = h.free_updates; ctx->stats.hit_updates = h.hit_updates; ctx->stats.resizes = h.resizes;
+    ctx->stats.pool_in_use = (uint64_t)(ctx->pool.cap - top);
+    if (h.error == GM_ERR_POOL) return fail(ctx, GM_ERR_POOL, "gm_register: patch pool of %d patches exhausted", ctx->pool.cap);
+    if (h.error) return fail(ctx, h.error, "gm_register: device-side error %d", h.error);
+    return GM_OK;
+}
+
+int gm_map_info_get(gm_ctx* ctx, uint32_t particle, gm_map_info* info) {
+    return gm_download_map(ctx, particle, info, nullptr, nullptr, 0);
+}
+
+int gm_download_map(gm_ctx* ctx, uint32_t particle, gm_map_info* info, int32_t* patch_coords, gm_cell* cells, uint32_t max_patches) {
+    if (int r = ready(ctx, true)) return r;
+    if (particle >= ctx->n || !info) return fail(ctx, GM_ERR_ARG, "gm_download_map: bad argument");
+    Geom g;
+    CK(cudaMemcpyAsync(&g, ctx->geom + particle, sizeof g, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    const size_t nent = (size_t)g.npx * g.npy;
+    if (nent > ctx->list_cap) { CK(dalloc(ctx->d_list, nent * 2)); ctx->list_cap = nent; }
+    CK(cudaMemsetAsync(ctx->d_count, 0, sizeof(int), ctx->st));
+    launch_export_list(ctx->dir + (size_t)particle * ctx->dir_cap, g, ctx->d_list, ctx->d_count, ctx->st);
+    ctx->stats.launches++;
+    if (int r = check_launch(ctx, "k_export_list")) return r;
+    int cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, ctx->d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    info->center_x = ctx->P.cx; info->center_y = ctx->P.cy; info->delta = ctx->P.delta;
+    info->size_x2 = g.sx2; info->size_y2 = g.sy2; info->patches_x = g.npx; info->patches_y = g.npy;
+    info->allocated_patches = cnt; info->reserved = 0;
+    if (!patch_coords || !cells || !max_patches || !cnt) return GM_OK;
+    std::vector<int> list((size_t)cnt * 2);
+    CK(cudaMemcpyAsync(list.data(), ctx->d_list, sizeof(int) * 2 * cnt, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    std::vector<std::pair<int, int>> ent(cnt);
+    for (int k = 0; k < cnt; k++) ent[k] = {list[2 * k], list[2 * k + 1]};
+    std::sort(ent.begin(), ent.end());  // directory order: px-major, like the reference's storage walk
+    const int m = std::min<int>(cnt, (int)max_patches);
+    for (int k = 0; k < m; k++) {
+        list[2 * k] = ent[k].first; list[2 * k + 1] = ent[k].second;
+        patch_coords[2 * k] = ent[k].first / g.npy; patch_coords[2 * k + 1] = ent[k].first % g.npy;
+    }
+    CK(cudaMemcpyAsync(ctx->d_list, list.data(), sizeof(int) * 2 * m, cudaMemcpyHostToDevice, ctx->st));
+    if ((size_t)m > ctx->export_cap) { CK(dalloc(ctx->d_export, (size_t)m * kPatchCells)); ctx->export_cap = m; }
+    launch_export_gather(ctx->pool.cells, ctx->d_list, ctx->d_export, m, ctx->st);
+    ctx->stats.launches++;
+    if (int r = check_launch(ctx, "k_export_gather")) return r;
+    CK(cudaMemcpyAsync(cells, ctx->d_export, sizeof(int4) * kPatchCells * (size_t)m, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return GM_OK;
+}
+
+int gm_map_digest(gm_ctx* ctx, uint32_t first, uint32_t count, gm_digest* out) {
+    if (int r = ready(ctx, true)) return r;
+    if (!out || first + count > ctx->n) return fail(ctx, GM_ERR_ARG, "gm_map_digest: bad argument");
+    if (!count) return GM_OK;
+    DigestArgs a;
+    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.first = first; a.out = ctx->d_digest;
+    launch_digest(a, count, ctx->st);
+    ctx->stats.launches++;
+    if (int r = check_launch(ctx, "k_digest")) return r;
+    static_assert(sizeof(gm_digest) == 48, "gm_digest is six 64-bit words");
+    CK(cudaMemcpyAsync(out, ctx->d_digest, sizeof(gm_digest) * count, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return GM_OK;
+}
+
+int gm_get_stats(gm_ctx* ctx, gm_stats* out) {
+    if (!ctx || !out) return GM_ERR_ARG;
+    *out = ctx->stats;
+    return GM_OK;
+}
+
+}  // extern "C"

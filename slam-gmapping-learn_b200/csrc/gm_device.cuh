@@ -1,0 +1,131 @@
+// gm_device.cuh -- device-side data layout and helpers shared by the kernels (sm_100a).
+//
+// HBM layout:
+//   pool   : int4[pool_cap * 1024]   patch p, cell (lx,ly) at pool[p*1024 + lx*32 + ly] = {acc.x, acc.y, n, visits}
+//            (bit layout of the reference's 16-byte PointAccumulator, smmap.h:35-36; x-major like
+//            Array2D::m_cells[x][y], array2d.h:39, so a window's yy-inner cells are contiguous)
+//   dir    : int[N * dir_cap]        particle i, patch (px,py) at dir[i*dir_cap + px*npy + py], -1 = unallocated
+//   geom   : Geom[N]                 per-particle m_sizeX2/m_sizeY2 + directory dims (diverge after Map::resize)
+//   refcnt : int[pool_cap]           number of directory entries that reference a patch (autoptr::shares)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gm {
+
+constexpr int kPatchMag = 5;
+constexpr int kPatch = 32;
+constexpr int kPatchCells = 1024;
+constexpr int kLineCap = 20000;  // scanmatcher.cpp:55
+
+struct Geom { int sx2, sy2, npx, npy; };
+
+struct DevParams {
+    double cx, cy, delta;
+    double laser_pose[3];
+    double laser_max_range, usable_range, gaussian_sigma, likelihood_sigma;
+    double opt_linear_delta, opt_angular_delta;
+    double enlarge_step, fullness_threshold, ang_rel, lin_rel, free_cell_ratio;
+    int kernel_size, generate_map;
+    unsigned opt_iters, lskip, beam_skip, nbeams;
+    int thr_is_tenth;  // fullness_threshold is exactly the default 0.1 -> exact integer occupancy tests
+};
+
+struct Counters {  // zeroed per stage, read back by the host
+    unsigned long long score_evals, beam_evals, cow_copies, patch_allocs, free_updates, hit_updates, resizes;
+    int error;          // gm_status of the first device-side failure
+    int need_dir_cap;   // largest npx*npy any particle needs (k_bounds)
+    int any_resize;
+    int pad;
+};
+
+struct Pool {
+    int4* cells;       // [cap*1024]
+    int* refcnt;       // [cap]
+    int* free_list;    // [cap] stack of free patch ids, top at *free_top
+    int* free_top;     // number of ids on the stack
+    int* pending;      // [cap] ids released during a kernel (merged afterwards)
+    int* pending_n;
+    int cap;
+};
+
+// ---- world <-> map (map.h:283-298).  No FMA contraction: this file is compiled with --fmad=false.
+__device__ __forceinline__ int w2m(double v, double c, double delta, int s2) {
+    return (int)round((v - c) / delta) + s2;
+}
+__device__ __forceinline__ double m2w(int i, double c, double delta, int s2) { return (i - s2) * delta + c; }
+
+// const Map::cell(): unknown (n=0, visits=0) when outside or unallocated (map.h:347-354)
+__device__ __forceinline__ bool cell_addr(const Geom& g, const int* __restrict__ dirp, int x, int y, long long& idx) {
+    if (x < 0 || y < 0) return false;
+    int px = x >> kPatchMag, py = y >> kPatchMag;
+    if (px >= g.npx || py >= g.npy) return false;
+    int id = __ldg(dirp + px * g.npy + py);
+    if (id < 0) return false;
+    idx = (long long)id * kPatchCells + ((x & 31) << kPatchMag) + (y & 31);
+    return true;
+}
+
+// PointAccumulator::operator double (smmap.h:25) compared against fullnessThreshold.
+// For thr == 0.1 the FP64 quotient n/visits can never round across the threshold unless 10n == visits
+// (|n/v - 1/10| >= 1/(10 v) >> ulp), so the tests are done in exact integer arithmetic.
+__device__ __forceinline__ bool occ_gt(int n, int v, const DevParams& P) {
+    if (!v) return -1.0 > P.fullness_threshold;
+    return P.thr_is_tenth ? (10ll * n > (long long)v) : ((double)n / (double)v > P.fullness_threshold);
+}
+__device__ __forceinline__ bool occ_lt(int n, int v, const DevParams& P) {
+    if (!v) return -1.0 < P.fullness_threshold;
+    return P.thr_is_tenth ? (10ll * n < (long long)v) : ((double)n / (double)v < P.fullness_threshold);
+}
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; return x ^ (x >> 31);
+}
+
+// ---- closed-form Bresenham (gridlinetraversal.h:20-124).  The reference walks the major axis upward
+// from the lower endpoint with d0 = 2db-da, stepping the minor axis when d >= 0; after j steps the
+// minor coordinate has moved floor((2*db*j + da) / (2*da)) cells.  The point list is then put into
+// start->end order.  Random access lets a warp own one ray with lanes on consecutive cells.
+struct Line {
+    int a_lo, b_lo, da, db, bstep, n;  // n = number of points
+    bool steep, from_end;
+};
+__device__ __forceinline__ Line make_line(int x0, int y0, int x1, int y1) {
+    Line L;
+    int dx = abs(x1 - x0), dy = abs(y1 - y0);
+    L.steep = !(dy <= dx);
+    int a0 = L.steep ? y0 : x0, b0 = L.steep ? x0 : y0, a1 = L.steep ? y1 : x1, b1 = L.steep ? x1 : y1;
+    L.da = L.steep ? dy : dx; L.db = L.steep ? dx : dy;
+    L.from_end = a0 > a1;
+    L.a_lo = L.from_end ? a1 : a0; L.b_lo = L.from_end ? b1 : b0;
+    int dirflag = L.from_end ? -1 : 1;
+    L.bstep = ((b1 - b0) * dirflag) > 0 ? 1 : -1;
+    L.n = L.da + 1;
+    return L;
+}
+// i-th point in start->end order
+__device__ __forceinline__ void line_point(const Line& L, int i, int& x, int& y) {
+    int j = L.from_end ? (L.n - 1 - i) : i;
+    int inc = L.da ? (int)((2u * (unsigned)L.db * (unsigned)j + (unsigned)L.da) / (2u * (unsigned)L.da)) : 0;
+    int a = L.a_lo + j, b = L.b_lo + L.bstep * inc;
+    x = L.steep ? b : a; y = L.steep ? a : b;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace gm

@@ -1,0 +1,688 @@
+// gm_kernels.cu -- hand-written sm_100a kernels for GMapping's per-scan particle update.
+// Compiled with --fmad=false: the reference x86-64 build has no FMA contraction and the hill-climb's
+// decisions depend on the exact FP64 evaluation order (SURVEY.md §7 "hard parts").
+//
+// Kernels (one CTA per particle unless noted):
+//   k_scanmatch   ScanMatcher::optimize + likelihoodAndScore           (scanmatcher.cpp:386-529, scanmatcher.h:171-380)
+//   k_eval        standalone score / likelihoodAndScore queries         (scanmatcher.h:171-380)
+//   k_bounds      computeActiveArea's bounding box + Map::resize maths  (scanmatcher.cpp:83-166, map.h:218-241)
+//   k_relayout    HierarchicalArray2D::resize                           (harray2d.h:80-109)
+//   k_register    active area + copy-on-write + ray update + hits       (scanmatcher.cpp:168-354, harray2d.h:169-185)
+//   k_remap/k_sweep/k_merge_free   particle copy by patch reference     (gridslamprocessor.hxx:184-213)
+//   k_normalize / k_resample       (gridslamprocessor.hxx:82-121, particlefilter.h:180-229)
+//   k_digest / k_export_*          map read-back
+#include "gm_device.cuh"
+#include "gm_kernels.h"
+
+namespace gm {
+
+// ------------------------------------------------------------------------------------------------
+// Window search for one beam (scanmatcher.h:198-252 / :311-365).  `free_off` is delta*freeDelta for
+// score() and freeDelta for likelihoodAndScore().  Returns found and bestMu.
+__device__ __forceinline__ bool beam_match(const DevParams& P, const Geom& g, const int* __restrict__ dirp,
+                                           const int4* __restrict__ pool, double lpx, double lpy, double lpt, double r,
+                                           double ang, double free_off, double& bmx, double& bmy) {
+    double s, c;
+    sincos(lpt + ang, &s, &c);
+    double phx = lpx + r * c, phy = lpy + r * s;
+    int ihx = w2m(phx, P.cx, P.delta, g.sx2), ihy = w2m(phy, P.cy, P.delta, g.sy2);
+    double pfx = lpx + (r - free_off) * c, pfy = lpy + (r - free_off) * s;
+    pfx = pfx - phx; pfy = pfy - phy;
+    // world2map applied to a difference vector: reproduces the reference's `ipfree` quirk
+    int ifx = w2m(pfx, P.cx, P.delta, g.sx2), ify = w2m(pfy, P.cy, P.delta, g.sy2);
+    bool found = false;
+    double bx = 0., by = 0., bn = 0.;
+    const int k = P.kernel_size;
+    for (int xx = -k; xx <= k; xx++)
+        for (int yy = -k; yy <= k; yy++) {
+            int prx = ihx + xx, pry = ihy + yy;
+            long long ci;
+            int4 cell = make_int4(0, 0, 0, 0);
+            if (cell_addr(g, dirp, prx, pry, ci)) cell = __ldg(pool + ci);
+            if (!occ_gt(cell.z, cell.w, P)) continue;
+            long long fi;
+            int fn = 0, fv = 0;
+            if (cell_addr(g, dirp, prx + ifx, pry + ify, fi)) { int4 f = __ldg(pool + fi); fn = f.z; fv = f.w; }
+            if (!occ_lt(fn, fv, P)) continue;
+            double inv = 1. / cell.z;  // mean() = (1./n) * Point(acc.x, acc.y), smmap.h:24
+            double mx = phx - (double)__int_as_float(cell.x) * inv;
+            double my = phy - (double)__int_as_float(cell.y) * inv;
+            double nn = mx * mx + my * my;
+            if (!found) { bx = mx; by = my; bn = nn; found = true; }
+            else if (nn < bn) { bx = mx; by = my; bn = nn; }
+        }
+    bmx = bx; bmy = by;
+    return found;
+}
+
+// laser pose in the map frame (scanmatcher.h:177-180)
+__device__ __forceinline__ void laser_pose(const DevParams& P, double x, double y, double t, double& lx, double& ly, double& lt) {
+    double s, c;
+    sincos(t, &s, &c);
+    lx = x + (c * P.laser_pose[0] - s * P.laser_pose[1]);
+    ly = y + (s * P.laser_pose[0] + c * P.laser_pose[1]);
+    lt = t + P.laser_pose[2];
+}
+
+// beam i (counted from initialBeamsSkip) is evaluated iff the reference's `skip` counter wraps to 0
+// there: skip++ ; skip = skip > likelihoodSkip ? 0 : skip  (scanmatcher.h:189-196)
+__device__ __forceinline__ bool beam_selected(const DevParams& P, unsigned b) {
+    return ((b - P.beam_skip + 1u) % (P.lskip + 1u)) == 0u;
+}
+
+// Evaluate score() for K candidate poses of one particle with the whole CTA.  Every thread returns the
+// same K sums (fixed-shape reduction: per-thread beam-ordered partials, xor-shuffle tree, warps in order).
+template <int K>
+__device__ __forceinline__ void cta_scores(const DevParams& P, const Geom& g, const int* __restrict__ dirp,
+                                           const int4* __restrict__ pool, const double* __restrict__ ranges,
+                                           const double* __restrict__ angles, const double (*lp)[3], double* red,
+                                           double (&out)[K]) {
+    double acc[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) acc[k] = 0.;
+    const double free_off = P.delta * (P.delta * P.free_cell_ratio);  // map.getDelta()*freeDelta, scanmatcher.h:208
+    const double cexp = -1. / P.gaussian_sigma;
+    for (unsigned b = P.beam_skip + threadIdx.x; b < P.nbeams; b += blockDim.x) {
+        double r = __ldg(ranges + b);
+        if (!beam_selected(P, b) || r > P.usable_range || r == 0.0) continue;
+        double ang = __ldg(angles + b);
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            double mx, my;
+            if (beam_match(P, g, dirp, pool, lp[k][0], lp[k][1], lp[k][2], r, ang, free_off, mx, my))
+                acc[k] += exp((mx * cexp) * mx + (my * cexp) * my);  // ((-1/sigma)*mu)*mu, point.h:34-49
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        double v = warp_sum(acc[k]);
+        if (lane == 0) red[k * 32 + warp] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        double v = 0.;
+        for (int w = 0; w < nw; w++) v += red[k * 32 + w];
+        out[k] = v;
+    }
+    __syncthreads();
+}
+
+// likelihoodAndScore for one pose with the whole CTA (scanmatcher.h:271-380)
+__device__ __forceinline__ void cta_likelihood(const DevParams& P, const Geom& g, const int* __restrict__ dirp,
+                                               const int4* __restrict__ pool, const double* __restrict__ ranges,
+                                               const double* __restrict__ angles, const double lp[3], double* red,
+                                               double& s_out, double& l_out, unsigned& c_out, unsigned& valid_out) {
+    double s = 0., l = 0.;
+    unsigned c = 0, valid = 0;
+    const double free_off = P.delta * P.free_cell_ratio;  // freeDelta, scanmatcher.h:320
+    const double cexp = -1. / P.gaussian_sigma, clik = -1. / P.likelihood_sigma;
+    const double noHit = -.5 / P.likelihood_sigma;  // nullLikelihood, scanmatcher.cpp:15
+    for (unsigned b = P.beam_skip + threadIdx.x; b < P.nbeams; b += blockDim.x) {
+        double r = __ldg(ranges + b);
+        if (r > P.usable_range || !beam_selected(P, b)) continue;
+        double mx, my;
+        valid++;
+        bool found = beam_match(P, g, dirp, pool, lp[0], lp[1], lp[2], r, __ldg(angles + b), free_off, mx, my);
+        if (found) { s += exp((mx * cexp) * mx + (my * cexp) * my); c++; }
+        double f = clik * (mx * mx + my * my);
+        l += found ? f : noHit;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    s = warp_sum(s); l = warp_sum(l);
+    c = __reduce_add_sync(0xffffffffu, c); valid = __reduce_add_sync(0xffffffffu, valid);
+    if (lane == 0) { red[warp] = s; red[32 + warp] = l; red[64 + warp] = (double)c; red[96 + warp] = (double)valid; }
+    __syncthreads();
+    double ss = 0., ll = 0., cc = 0., vv = 0.;
+    for (int w = 0; w < nw; w++) { ss += red[w]; ll += red[32 + w]; cc += red[64 + w]; vv += red[96 + w]; }
+    s_out = ss; l_out = ll; c_out = (unsigned)cc; valid_out = (unsigned)vv;
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// scanMatch for one particle per CTA: hill-climb (optimize), accept/reject, likelihoodAndScore.
+__global__ void __launch_bounds__(256) k_scanmatch(ScanMatchArgs A) {
+    __shared__ double red[6 * 32];
+    __shared__ double lp[6][3];
+    const DevParams& P = A.P;
+    const unsigned p = blockIdx.x;
+    const Geom g = A.geom[p];
+    const int* dirp = A.dir + (size_t)p * A.dir_cap;
+    const double init[3] = {A.poses[3 * p], A.poses[3 * p + 1], A.poses[3 * p + 2]};
+
+    double cur[3] = {init[0], init[1], init[2]};
+    if (threadIdx.x == 0) laser_pose(P, cur[0], cur[1], cur[2], lp[0][0], lp[0][1], lp[0][2]);
+    __syncthreads();
+    double s1[1];
+    cta_scores<1>(P, g, dirp, A.pool, A.ranges, A.angles, lp, red, s1);
+    double currentScore = s1[0], bestScore = -1;
+    double adelta = P.opt_angular_delta, ldelta = P.opt_linear_delta;
+    unsigned refinement = 0, evals = 1;
+    do {
+        if (bestScore >= currentScore) { refinement++; adelta *= .5; ldelta *= .5; }
+        bestScore = currentScore;
+        double cand[6][3];
+#pragma unroll
+        for (int m = 0; m < 6; m++) { cand[m][0] = cur[0]; cand[m][1] = cur[1]; cand[m][2] = cur[2]; }
+        cand[0][0] += ldelta;  // Front
+        cand[1][0] -= ldelta;  // Back
+        cand[2][1] -= ldelta;  // Left
+        cand[3][1] += ldelta;  // Right
+        cand[4][2] += adelta;  // TurnLeft
+        cand[5][2] -= adelta;  // TurnRight
+        if (threadIdx.x < 6) {
+            int m = threadIdx.x;
+            laser_pose(P, cand[m][0], cand[m][1], cand[m][2], lp[m][0], lp[m][1], lp[m][2]);
+        }
+        __syncthreads();
+        double sc[6];
+        cta_scores<6>(P, g, dirp, A.pool, A.ranges, A.angles, lp, red, sc);
+        evals += 6;
+        double best[3] = {cur[0], cur[1], cur[2]};
+#pragma unroll
+        for (int m = 0; m < 6; m++) {
+            double odo_gain = 1;
+            if (P.ang_rel > 0.) {
+                double dth = init[2] - cand[m][2];
+                dth = atan2(sin(dth), cos(dth));
+                dth *= dth;
+                odo_gain *= exp(-P.ang_rel * dth);
+            }
+            if (P.lin_rel > 0.) {
+                double dx = init[0] - cand[m][0], dy = init[1] - cand[m][1];
+                double drho = dx * dx + dy * dy;
+                odo_gain *= exp(-P.lin_rel * drho);
+            }
+            double localScore = odo_gain * sc[m];
+            if (localScore > currentScore) {
+                currentScore = localScore;
+                best[0] = cand[m][0]; best[1] = cand[m][1]; best[2] = cand[m][2];
+            }
+        }
+        cur[0] = best[0]; cur[1] = best[1]; cur[2] = best[2];
+    } while (currentScore > bestScore || refinement < P.opt_iters);
+
+    // gridslamprocessor.hxx:34-48: keep the motion-model pose when the match is not good enough
+    double fin[3];
+    const bool accept = bestScore > A.minimum_score;
+    fin[0] = accept ? cur[0] : init[0]; fin[1] = accept ? cur[1] : init[1]; fin[2] = accept ? cur[2] : init[2];
+    if (threadIdx.x == 0) laser_pose(P, fin[0], fin[1], fin[2], lp[0][0], lp[0][1], lp[0][2]);
+    __syncthreads();
+    double s, l; unsigned c, valid;
+    cta_likelihood(P, g, dirp, A.pool, A.ranges, A.angles, lp[0], red, s, l, c, valid);
+    if (threadIdx.x == 0) {
+        A.poses[3 * p] = fin[0]; A.poses[3 * p + 1] = fin[1]; A.poses[3 * p + 2] = fin[2];
+        A.score[p] = bestScore; A.s[p] = s; A.l[p] = l; A.c[p] = c; A.evals[p] = evals;
+        atomicAdd(&A.counters->score_evals, (unsigned long long)evals);
+        atomicAdd(&A.counters->beam_evals, (unsigned long long)evals * A.valid_score_beams + valid);
+    }
+}
+
+// standalone score()/likelihoodAndScore() queries: one CTA per (particle, pose)
+__global__ void __launch_bounds__(256) k_eval(EvalArgs A) {
+    __shared__ double red[4 * 32];
+    __shared__ double lp[1][3];
+    const DevParams& P = A.P;
+    const unsigned q = blockIdx.x, p = A.particle_idx[q];
+    const Geom g = A.geom[p];
+    const int* dirp = A.dir + (size_t)p * A.dir_cap;
+    if (threadIdx.x == 0) laser_pose(P, A.poses[3 * q], A.poses[3 * q + 1], A.poses[3 * q + 2], lp[0][0], lp[0][1], lp[0][2]);
+    __syncthreads();
+    if (A.mode == 0) {
+        double s1[1];
+        cta_scores<1>(P, g, dirp, A.pool, A.ranges, A.angles, lp, red, s1);
+        if (threadIdx.x == 0) A.s[q] = s1[0];
+    } else {
+        double s, l; unsigned c, valid;
+        cta_likelihood(P, g, dirp, A.pool, A.ranges, A.angles, lp[0], red, s, l, c, valid);
+        if (threadIdx.x == 0) { A.s[q] = s; A.l[q] = l; A.c[q] = c; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// computeActiveArea part 1: bounding box of the laser pose and the clipped endpoints, and the
+// Map::resize arithmetic when it leaves the map (scanmatcher.cpp:96-166, map.h:218-241).
+__global__ void __launch_bounds__(256) k_bounds(BoundsArgs A) {
+    __shared__ double red[4 * 32];
+    const DevParams& P = A.P;
+    const unsigned p = blockIdx.x;
+    const Geom g = A.geom[p];
+    double lx, ly, lt;
+    laser_pose(P, A.poses[3 * p], A.poses[3 * p + 1], A.poses[3 * p + 2], lx, ly, lt);
+    double minx = lx, miny = ly, maxx = lx, maxy = ly;
+    int too_long = 0;
+    const int p0x = w2m(lx, P.cx, P.delta, g.sx2), p0y = w2m(ly, P.cy, P.delta, g.sy2);
+    for (unsigned b = P.beam_skip + threadIdx.x; b < P.nbeams; b += blockDim.x) {
+        double r = __ldg(A.ranges + b);
+        if (r > P.laser_max_range || r == 0.0 || isnan(r)) continue;
+        double d = r > P.usable_range ? P.usable_range : r;
+        double s, c;
+        sincos(lt + __ldg(A.angles + b), &s, &c);
+        double phx = lx + d * c, phy = ly + d * s;
+        minx = fmin(minx, phx); miny = fmin(miny, phy); maxx = fmax(maxx, phx); maxy = fmax(maxy, phy);
+        int p1x = w2m(phx, P.cx, P.delta, g.sx2), p1y = w2m(phy, P.cy, P.delta, g.sy2);
+        if (max(abs(p1x - p0x), abs(p1y - p0y)) + 1 > kLineCap) too_long = 1;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    minx = warp_min(minx); miny = warp_min(miny); maxx = warp_max(maxx); maxy = warp_max(maxy);
+    too_long = __any_sync(0xffffffffu, too_long);
+    if (lane == 0) { red[warp] = minx; red[32 + warp] = miny; red[64 + warp] = maxx; red[96 + warp] = maxy; if (too_long) atomicCAS(&A.counters->error, 0, -5); }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    for (int w = 1; w < nw; w++) { minx = fmin(minx, red[w]); miny = fmin(miny, red[32 + w]); maxx = fmax(maxx, red[64 + w]); maxy = fmax(maxy, red[96 + w]); }
+    // the box starts from the current map extent (scanmatcher.cpp:102-114)
+    const int mw = g.npx << kPatchMag, mh = g.npy << kPatchMag;
+    const double lminx = m2w(0, P.cx, P.delta, g.sx2), lminy = m2w(0, P.cy, P.delta, g.sy2);
+    const double lmaxx = m2w(mw - 1, P.cx, P.delta, g.sx2), lmaxy = m2w(mh - 1, P.cy, P.delta, g.sy2);
+    minx = fmin(minx, lminx); miny = fmin(miny, lminy); maxx = fmax(maxx, lmaxx); maxy = fmax(maxy, lmaxy);
+    auto inside = [&](double x, double y) {
+        int ix = w2m(x, P.cx, P.delta, g.sx2), iy = w2m(y, P.cy, P.delta, g.sy2);
+        return ix >= 0 && iy >= 0 && (ix >> kPatchMag) < g.npx && (iy >> kPatchMag) < g.npy;
+    };
+    Geom ng = g;
+    int4 shift = make_int4(0, 0, 0, 0);
+    if (!inside(minx, miny) || !inside(maxx, maxy)) {
+        minx = (minx >= lminx) ? lminx : minx - P.enlarge_step;
+        maxx = (maxx <= lmaxx) ? lmaxx : maxx + P.enlarge_step;
+        miny = (miny >= lminy) ? lminy : miny - P.enlarge_step;
+        maxy = (maxy <= lmaxy) ? lmaxy : maxy + P.enlarge_step;
+        int iminx = w2m(minx, P.cx, P.delta, g.sx2), iminy = w2m(miny, P.cy, P.delta, g.sy2);
+        int imaxx = w2m(maxx, P.cx, P.delta, g.sx2), imaxy = w2m(maxy, P.cy, P.delta, g.sy2);
+        int pxmin = (int)floorf((float)iminx / (float)kPatch), pxmax = (int)ceilf((float)imaxx / (float)kPatch);
+        int pymin = (int)floorf((float)iminy / (float)kPatch), pymax = (int)ceilf((float)imaxy / (float)kPatch);
+        ng.npx = pxmax - pxmin; ng.npy = pymax - pymin;
+        ng.sx2 = g.sx2 - pxmin * kPatch; ng.sy2 = g.sy2 - pymin * kPatch;
+        shift = make_int4(pxmin, pymin, 1, 0);
+        atomicAdd(&A.counters->resizes, 1ull);
+        atomicMax(&A.counters->need_dir_cap, ng.npx * ng.npy);
+        atomicExch(&A.counters->any_resize, 1);
+    }
+    A.geom_new[p] = ng;
+    A.shift[p] = shift;
+}
+
+// HierarchicalArray2D::resize for the flagged particles: dir_alt[p] <- re-based dir[p]; patches that fall
+// outside the new directory lose this particle's reference (harray2d.h:80-109).
+__global__ void k_relayout(RelayoutArgs A) {
+    const unsigned p = blockIdx.x;
+    const int4 sh = A.shift[p];
+    if (!sh.z) return;
+    const Geom og = A.geom[p], ng = A.geom_new[p];
+    const int* src = A.dir + (size_t)p * A.dir_cap_old;
+    int* dst = A.dir_alt + (size_t)p * A.dir_cap_new;
+    for (int e = threadIdx.x; e < ng.npx * ng.npy; e += blockDim.x) {
+        int x = e / ng.npy + sh.x, y = e % ng.npy + sh.y;
+        dst[e] = (x >= 0 && y >= 0 && x < og.npx && y < og.npy) ? src[x * og.npy + y] : -1;
+    }
+    for (int e = threadIdx.x; e < og.npx * og.npy; e += blockDim.x) {
+        int x = e / og.npy - sh.x, y = e % og.npy - sh.y;
+        int id = src[e];
+        if (id >= 0 && !(x >= 0 && y >= 0 && x < ng.npx && y < ng.npy))
+            if (atomicSub(&A.pool.refcnt[id], 1) == 1) A.pool.pending[atomicAdd(A.pool.pending_n, 1)] = id;
+    }
+}
+__global__ void k_relayout_commit(RelayoutArgs A) {
+    const unsigned p = blockIdx.x;
+    const int4 sh = A.shift[p];
+    const Geom ng = A.geom_new[p];
+    // after a capacity growth every particle moves to the new stride; otherwise only resized ones change
+    const int* src = sh.z ? A.dir_alt + (size_t)p * A.dir_cap_new : A.dir + (size_t)p * A.dir_cap_old;
+    int* dst = A.dir_out + (size_t)p * A.dir_cap_new;
+    if (src != dst)
+        for (int e = threadIdx.x; e < ng.npx * ng.npy; e += blockDim.x) dst[e] = src[e];
+    if (threadIdx.x == 0) A.geom[p] = ng;
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pool_alloc(const Pool& pool, Counters* ctr) {
+    int k = atomicSub(pool.free_top, 1) - 1;
+    if (k < 0) { atomicCAS(&ctr->error, 0, -3); return -1; }
+    return pool.free_list[k];
+}
+
+// computeActiveArea part 2 + allocActiveArea + registerScan for one particle per CTA.
+//   1. mark the patches under every ray cell (all but the last point) and under the endpoint when
+//      d < usableRange (scanmatcher.cpp:181-218), in a shared-memory bitmap over the directory;
+//   2. make every active patch private: create it, or copy it when another particle still references
+//      it (harray2d.h:169-185 copies always; copying only shared patches yields identical cells);
+//   3. visits++ along the rays (scanmatcher.cpp:317-325): a warp owns a ray, lanes take consecutive cells
+//      through the closed-form Bresenham; integer atomics commute, so the counts are bit-exact;
+//   4. endpoint hits (scanmatcher.cpp:327-334): float `acc` is order dependent, so hits are sorted by
+//      (cell, beam) and each cell's run is accumulated sequentially in beam order by one thread.
+__global__ void __launch_bounds__(256) k_register(RegisterArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const DevParams& P = A.P;
+    const unsigned p = blockIdx.x;
+    const Geom g = A.geom[p];
+    int* dirp = A.dir + (size_t)p * A.dir_cap;
+    const int nent = g.npx * g.npy, nwords = (nent + 31) >> 5;
+    unsigned* active = reinterpret_cast<unsigned*>(smem_raw);
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + (((size_t)A.bitmap_words * 4 + 15) & ~(size_t)15));
+    float* hx = reinterpret_cast<float*>(keys + A.sort_n);
+    float* hy = hx + A.sort_n;
+    __shared__ unsigned long long s_free, s_hit, s_cow, s_alloc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) active[i] = 0u;
+    for (int i = threadIdx.x; i < A.sort_n; i += blockDim.x) keys[i] = ~0ull;
+    if (threadIdx.x == 0) { s_free = 0; s_hit = 0; s_cow = 0; s_alloc = 0; }
+    double lx, ly, lt;
+    laser_pose(P, A.poses[3 * p], A.poses[3 * p + 1], A.poses[3 * p + 2], lx, ly, lt);
+    const int p0x = w2m(lx, P.cx, P.delta, g.sx2), p0y = w2m(ly, P.cy, P.delta, g.sy2);
+    __syncthreads();
+
+    // ---- 1. active area
+    for (unsigned b = P.beam_skip + warp; b < P.nbeams; b += nw) {
+        double r = __ldg(A.ranges + b);
+        bool hit;
+        if (P.generate_map) {
+            if (r > P.laser_max_range || r == 0.0 || isnan(r)) continue;
+            hit = !(r >= P.usable_range);  // d < usableRange after clipping
+            if (r > P.usable_range) r = P.usable_range;
+        } else {
+            if (r > P.laser_max_range || r > P.usable_range || r == 0.0 || isnan(r)) continue;
+            hit = true;
+        }
+        double s, c;
+        sincos(lt + __ldg(A.angles + b), &s, &c);
+        const double phx = lx + r * c, phy = ly + r * s;
+        const int p1x = w2m(phx, P.cx, P.delta, g.sx2), p1y = w2m(phy, P.cy, P.delta, g.sy2);
+        if (P.generate_map) {
+            const Line L = make_line(p0x, p0y, p1x, p1y);
+            for (int i0 = 0; i0 < L.n - 1; i0 += 32) {
+                int i = i0 + lane, e = -1;
+                if (i < L.n - 1) {
+                    int x, y; line_point(L, i, x, y);
+                    if (x >= 0 && y >= 0 && (x >> kPatchMag) < g.npx && (y >> kPatchMag) < g.npy) e = (x >> kPatchMag) * g.npy + (y >> kPatchMag);
+                }
+                int prev = __shfl_up_sync(0xffffffffu, e, 1);
+                if (e >= 0 && (lane == 0 || prev != e)) atomicOr(&active[e >> 5], 1u << (e & 31));
+            }
+        }
+        if (lane == 0 && hit) {
+            if (p1x >= 0 && p1y >= 0 && (p1x >> kPatchMag) < g.npx && (p1y >> kPatchMag) < g.npy) {
+                int e = (p1x >> kPatchMag) * g.npy + (p1y >> kPatchMag);
+                atomicOr(&active[e >> 5], 1u << (e & 31));
+                keys[b] = ((unsigned long long)(unsigned)p1x << 36) | ((unsigned long long)(unsigned)p1y << 12) | b;
+                hx[b] = (float)phx; hy[b] = (float)phy;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 2. copy-on-write: a warp per active patch
+    for (int wi = warp; wi < nwords; wi += nw) {
+        unsigned bits = active[wi];
+        while (bits) {
+            int bit = __ffs(bits) - 1; bits &= bits - 1;
+            int e = (wi << 5) + bit;
+            int id = dirp[e], nid = id, mode = 0;  // 0 keep, 1 zero-fill new, 2 copy
+            if (lane == 0) {
+                if (id < 0) { nid = pool_alloc(A.pool, A.counters); mode = 1; }
+                else if (atomicAdd(&A.pool.refcnt[id], 0) > 1) { nid = pool_alloc(A.pool, A.counters); mode = 2; }
+            }
+            nid = __shfl_sync(0xffffffffu, nid, 0); mode = __shfl_sync(0xffffffffu, mode, 0);
+            if (mode == 0 || nid < 0) continue;
+            int4* dst = A.pool.cells + (size_t)nid * kPatchCells;
+            if (mode == 1) {
+                for (int i = lane; i < kPatchCells; i += 32) dst[i] = make_int4(0, 0, 0, 0);
+            } else {
+                const int4* src = A.pool.cells + (size_t)id * kPatchCells;
+                for (int i = lane; i < kPatchCells; i += 32) dst[i] = __ldcg(src + i);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                A.pool.refcnt[nid] = 1;
+                dirp[e] = nid;
+                if (mode == 2) {
+                    // release our share only AFTER the copy: whoever then reads refcnt==1 is the sole owner
+                    // and may write in place (see DESIGN.md "copy-on-write protocol")
+                    __threadfence();
+                    if (atomicSub(&A.pool.refcnt[id], 1) == 1) A.pool.pending[atomicAdd(A.pool.pending_n, 1)] = id;
+                    atomicAdd(&s_cow, 1ull);
+                } else atomicAdd(&s_alloc, 1ull);
+            }
+        }
+    }
+    __threadfence();
+    __syncthreads();
+
+    // ---- 3. free-space updates along the rays
+    unsigned long long nfree = 0;
+    for (unsigned b = P.beam_skip + warp; P.generate_map && b < P.nbeams; b += nw) {
+        double r = __ldg(A.ranges + b);
+        if (r > P.laser_max_range || r == 0.0 || isnan(r)) continue;
+        if (r > P.usable_range) r = P.usable_range;
+        double s, c;
+        sincos(lt + __ldg(A.angles + b), &s, &c);
+        const double phx = lx + r * c, phy = ly + r * s;
+        const int p1x = w2m(phx, P.cx, P.delta, g.sx2), p1y = w2m(phy, P.cy, P.delta, g.sy2);
+        const Line L = make_line(p0x, p0y, p1x, p1y);
+        for (int i = lane; i < L.n - 1; i += 32) {
+            int x, y; line_point(L, i, x, y);
+            if (x < 0 || y < 0 || (x >> kPatchMag) >= g.npx || (y >> kPatchMag) >= g.npy) continue;
+            int id = dirp[(x >> kPatchMag) * g.npy + (y >> kPatchMag)];
+            if (id < 0) continue;
+            int* cell = reinterpret_cast<int*>(A.pool.cells + (size_t)id * kPatchCells + ((x & 31) << kPatchMag) + (y & 31));
+            atomicAdd(cell + 3, 1);  // update(false): visits++
+            nfree++;
+        }
+    }
+
+    // ---- 4. endpoint hits in beam order per cell: bitonic sort of (cell, beam) keys
+    for (int k = 2; k <= A.sort_n; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < A.sort_n; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = keys[i], bb = keys[ixj];
+                    bool up = (i & k) == 0;
+                    if ((a > bb) == up) { keys[i] = bb; keys[ixj] = a; }
+                }
+            }
+        }
+    __syncthreads();
+    unsigned long long nhit = 0;
+    for (int i = threadIdx.x; i < A.sort_n; i += blockDim.x) {
+        unsigned long long key = keys[i];
+        if (key == ~0ull) continue;
+        unsigned long long ck = key >> 12;
+        if (i > 0 && (keys[i - 1] >> 12) == ck) continue;  // not the head of this cell's run
+        int x = (int)(ck >> 24), y = (int)(ck & 0xffffffu);
+        int id = dirp[(x >> kPatchMag) * g.npy + (y >> kPatchMag)];
+        if (id < 0) continue;
+        int* cell = reinterpret_cast<int*>(A.pool.cells + (size_t)id * kPatchCells + ((x & 31) << kPatchMag) + (y & 31));
+        float ax = __int_as_float(__ldcg(cell)), ay = __int_as_float(__ldcg(cell + 1));
+        int cnt = 0;
+        for (int q = i; q < A.sort_n && (keys[q] >> 12) == ck; q++) {
+            unsigned b = (unsigned)(keys[q] & 0xfffu);
+            ax += hx[b]; ay += hy[b]; cnt++;  // acc += (float)phit, smmap.h:51-52
+        }
+        cell[0] = __float_as_int(ax); cell[1] = __float_as_int(ay);
+        atomicAdd(cell + 2, cnt); atomicAdd(cell + 3, cnt);
+        nhit += cnt;
+    }
+    if (nfree) atomicAdd(&s_free, nfree);
+    if (nhit) atomicAdd(&s_hit, nhit);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(&A.counters->free_updates, s_free); atomicAdd(&A.counters->hit_updates, s_hit);
+        atomicAdd(&A.counters->cow_copies, s_cow); atomicAdd(&A.counters->patch_allocs, s_alloc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Particle copy by patch reference (gridslamprocessor.hxx:184-213: Particle copy -> HierarchicalArray2D
+// copy-ctor -> autoptr share++).  dir_alt[j] <- dir[idx[j]], new refcounts counted from scratch.
+__global__ void k_remap(RemapArgs A) {
+    const unsigned j = blockIdx.x, src = A.idx[j];
+    const Geom g = A.geom[src];
+    const int* s = A.dir + (size_t)src * A.dir_cap;
+    int* d = A.dir_alt + (size_t)j * A.dir_cap;
+    for (int e = threadIdx.x; e < g.npx * g.npy; e += blockDim.x) {
+        int id = s[e];
+        d[e] = id;
+        if (id >= 0) atomicAdd(&A.refcnt_new[id], 1);
+    }
+    if (threadIdx.x == 0) A.geom_alt[j] = g;
+}
+// patches nobody references any more go back to the free list
+__global__ void k_sweep(SweepArgs A) {
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= A.pool.cap) return;
+    int o = A.pool.refcnt[id], n = A.refcnt_new[id];
+    if (o > 0 && n == 0) A.pool.pending[atomicAdd(A.pool.pending_n, 1)] = id;
+    A.pool.refcnt[id] = n;
+    A.refcnt_new[id] = 0;
+}
+__global__ void k_merge_free(Pool pool) {
+    int n = *pool.pending_n, top = *pool.free_top;
+    if (top < 0) top = 0;  // exhausted during the stage (error already flagged)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) pool.free_list[top + i] = pool.pending[i];
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *pool.free_top = top + n; *pool.pending_n = 0; }
+}
+__global__ void k_pool_init(Pool pool) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < pool.cap) { pool.free_list[i] = pool.cap - 1 - i; pool.refcnt[i] = 0; }
+    if (i == 0) { *pool.free_top = pool.cap; *pool.pending_n = 0; }
+}
+__global__ void k_fill_int(int* p, size_t n, int v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void k_fill_geom(Geom* g, unsigned n, Geom v) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) g[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// normalize (gridslamprocessor.hxx:82-121).  exp() in parallel; the two sums are sequential in the
+// reference, so one thread walks them in order (N <= 64K doubles: tens of microseconds).
+__global__ void __launch_bounds__(1024) k_normalize(const double* __restrict__ logw, unsigned n, double gain_sigma,
+                                                    double* __restrict__ w, double* __restrict__ neff_out) {
+    __shared__ double red[32];
+    __shared__ double s_val;
+    double lmax = -1.7976931348623157e308;
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) { double v = logw[i]; lmax = v > lmax ? v : lmax; }
+    lmax = warp_max(lmax);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lmax;
+    __syncthreads();
+    if (threadIdx.x == 0) { for (unsigned k = 1; k < (blockDim.x >> 5); k++) lmax = red[k] > lmax ? red[k] : lmax; s_val = lmax; }
+    __syncthreads();
+    lmax = s_val;
+    const double gain = 1. / (gain_sigma * n);
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) w[i] = exp(gain * (logw[i] - lmax));
+    __syncthreads();
+    if (threadIdx.x == 0) { double wcum = 0; for (unsigned i = 0; i < n; i++) wcum += w[i]; s_val = wcum; }
+    __syncthreads();
+    const double wcum = s_val;
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) w[i] = w[i] / wcum;
+    __syncthreads();
+    if (threadIdx.x == 0) { double ne = 0; for (unsigned i = 0; i < n; i++) { double x = w[i]; ne += x * x; } *neff_out = 1. / ne; }
+}
+
+// resampleIndexes (particlefilter.h:180-229).  The cumulative weights c[i] and the targets t[k] are the
+// reference's sequentially rounded sums (two serial chains); since both are monotone, the walk
+// "while (c[i] > target) emit i" is exactly idx[k] = min{ i : c[i] > t[k] }, found by binary search.
+__global__ void __launch_bounds__(1024) k_resample(const double* __restrict__ w, unsigned n, double u01, double* __restrict__ cum,
+                                                   double* __restrict__ tgt, unsigned* __restrict__ idx, unsigned* __restrict__ emitted) {
+    __shared__ double s_interval;
+    if (threadIdx.x == 0) {
+        double c = 0;
+        for (unsigned i = 0; i < n; i++) { c += w[i]; cum[i] = c; }
+        s_interval = c / n;
+    }
+    __syncthreads();
+    const double interval = s_interval;
+    if (threadIdx.x == 0) {
+        double t = interval * u01;
+        for (unsigned k = 0; k < n; k++) { tgt[k] = t; t += interval; }
+    }
+    __syncthreads();
+    const double total = cum[n - 1];
+    unsigned cnt = 0;
+    for (unsigned k = threadIdx.x; k < n; k += blockDim.x) {
+        double t = tgt[k];
+        unsigned r = 0;
+        if (total > t) {
+            unsigned lo = 0, hi = n - 1;  // smallest i with cum[i] > t
+            while (lo < hi) { unsigned mid = (lo + hi) >> 1; if (cum[mid] > t) hi = mid; else lo = mid + 1; }
+            r = lo; cnt++;
+        }
+        idx[k] = r;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(emitted, cnt);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_digest(DigestArgs A) {
+    __shared__ unsigned long long acc[6];
+    const unsigned p = A.first + blockIdx.x;
+    const Geom g = A.geom[p];
+    const int* dirp = A.dir + (size_t)p * A.dir_cap;
+    if (threadIdx.x < 6) acc[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long patches = 0, cells = 0, sn = 0, sv = 0, hc = 0, ha = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int e = warp; e < g.npx * g.npy; e += nw) {
+        int id = dirp[e];
+        if (id < 0) continue;
+        if (lane == 0) patches++;
+        int px = e / g.npy, py = e % g.npy;
+        const int4* pc = A.pool + (size_t)id * kPatchCells;
+        for (int i = lane; i < kPatchCells; i += 32) {
+            int4 c = pc[i];
+            if (!c.w && !c.z) continue;
+            int wx = px * kPatch + (i >> 5) - g.sx2, wy = py * kPatch + (i & 31) - g.sy2;
+            cells++; sn += (unsigned)c.z; sv += (unsigned)c.w;
+            unsigned long long key = ((unsigned long long)(unsigned)wx << 32) | (unsigned)wy;
+            hc += mix64(key ^ mix64(((unsigned long long)(unsigned)c.z << 32) | (unsigned)c.w));
+            ha += mix64(key ^ mix64(((unsigned long long)(unsigned)c.x << 32) | (unsigned)c.y) ^ 0x5555ull);
+        }
+    }
+    atomicAdd(&acc[0], patches); atomicAdd(&acc[1], cells); atomicAdd(&acc[2], sn);
+    atomicAdd(&acc[3], sv); atomicAdd(&acc[4], hc); atomicAdd(&acc[5], ha);
+    __syncthreads();
+    if (threadIdx.x < 6) A.out[(size_t)blockIdx.x * 6 + threadIdx.x] = acc[threadIdx.x];
+}
+
+__global__ void k_export_list(const int* __restrict__ dirp, Geom g, int* __restrict__ list, int* __restrict__ count) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < g.npx * g.npy; e += gridDim.x * blockDim.x) {
+        int id = dirp[e];
+        if (id >= 0) { int k = atomicAdd(count, 1); list[2 * k] = e; list[2 * k + 1] = id; }
+    }
+}
+__global__ void k_export_gather(const int4* __restrict__ pool, const int* __restrict__ list, int4* __restrict__ out) {
+    const int k = blockIdx.x, id = list[2 * k + 1];
+    for (int i = threadIdx.x; i < kPatchCells; i += blockDim.x) out[(size_t)k * kPatchCells + i] = pool[(size_t)id * kPatchCells + i];
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+void launch_scanmatch(const ScanMatchArgs& a, unsigned n, unsigned threads, cudaStream_t st) { k_scanmatch<<<n, threads, 0, st>>>(a); }
+void launch_eval(const EvalArgs& a, unsigned n, unsigned threads, cudaStream_t st) { k_eval<<<n, threads, 0, st>>>(a); }
+void launch_bounds(const BoundsArgs& a, unsigned n, unsigned threads, cudaStream_t st) { k_bounds<<<n, threads, 0, st>>>(a); }
+void launch_relayout(const RelayoutArgs& a, unsigned n, cudaStream_t st) { k_relayout<<<n, 256, 0, st>>>(a); }
+void launch_relayout_commit(const RelayoutArgs& a, unsigned n, cudaStream_t st) { k_relayout_commit<<<n, 256, 0, st>>>(a); }
+size_t register_smem_bytes(int bitmap_words, int sort_n) { return (((size_t)bitmap_words * 4 + 15) & ~(size_t)15) + (size_t)sort_n * 16; }
+cudaError_t register_prepare(size_t smem) {
+    return cudaFuncSetAttribute(k_register, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+void launch_register(const RegisterArgs& a, unsigned n, unsigned threads, size_t smem, cudaStream_t st) { k_register<<<n, threads, smem, st>>>(a); }
+void launch_remap(const RemapArgs& a, unsigned n, cudaStream_t st) { k_remap<<<n, 256, 0, st>>>(a); }
+void launch_sweep(const SweepArgs& a, cudaStream_t st) { k_sweep<<<(a.pool.cap + 255) / 256, 256, 0, st>>>(a); }
+void launch_merge_free(const Pool& p, cudaStream_t st) { k_merge_free<<<1, 1024, 0, st>>>(p); }
+void launch_pool_init(const Pool& p, cudaStream_t st) { k_pool_init<<<(p.cap + 255) / 256, 256, 0, st>>>(p); }
+void launch_fill_int(int* p, size_t n, int v, cudaStream_t st) { k_fill_int<<<1184, 256, 0, st>>>(p, n, v); }
+void launch_fill_geom(Geom* g, unsigned n, Geom v, cudaStream_t st) { k_fill_geom<<<(n + 255) / 256, 256, 0, st>>>(g, n, v); }
+void launch_normalize(const double* logw, unsigned n, double gain, double* w, double* neff, cudaStream_t st) { k_normalize<<<1, 1024, 0, st>>>(logw, n, gain, w, neff); }
+void launch_resample(const double* w, unsigned n, double u01, double* cum, double* tgt, unsigned* idx, unsigned* emitted, cudaStream_t st) {
+    k_resample<<<1, 1024, 0, st>>>(w, n, u01, cum, tgt, idx, emitted);
+}
+void launch_digest(const DigestArgs& a, unsigned n, cudaStream_t st) { k_digest<<<n, 256, 0, st>>>(a); }
+void launch_export_list(const int* dirp, Geom g, int* list, int* count, cudaStream_t st) { k_export_list<<<64, 256, 0, st>>>(dirp, g, list, count); }
+void launch_export_gather(const int4* pool, const int* list, int4* out, int n, cudaStream_t st) { k_export_gather<<<n, 256, 0, st>>>(pool, list, out); }
+
+}  // namespace gm

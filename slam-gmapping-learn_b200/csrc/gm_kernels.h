@@ -1,0 +1,79 @@
+// gm_kernels.h -- kernel argument blocks and launchers (internal; the public boundary is include/gm_b200.h)
+#pragma once
+#include "gm_device.cuh"
+
+namespace gm {
+
+struct ScanMatchArgs {
+    DevParams P;
+    const double* ranges; const double* angles;
+    double* poses;
+    const Geom* geom; const int* dir; int dir_cap;
+    const int4* pool;
+    double minimum_score;
+    double *score, *s, *l; unsigned *c, *evals;
+    Counters* counters;
+    unsigned valid_score_beams;
+};
+struct EvalArgs {
+    DevParams P;
+    const double* ranges; const double* angles;
+    const unsigned* particle_idx; const double* poses;
+    const Geom* geom; const int* dir; int dir_cap;
+    const int4* pool;
+    int mode;  // 0 score, 1 likelihoodAndScore
+    double *s, *l; unsigned* c;
+};
+struct BoundsArgs {
+    DevParams P;
+    const double* ranges; const double* angles; const double* poses;
+    const Geom* geom; Geom* geom_new; int4* shift;
+    Counters* counters;
+};
+struct RelayoutArgs {
+    Geom* geom; const Geom* geom_new; const int4* shift;
+    const int* dir; int* dir_alt; int* dir_out;
+    int dir_cap_old, dir_cap_new;
+    Pool pool;
+};
+struct RegisterArgs {
+    DevParams P;
+    const double* ranges; const double* angles; const double* poses;
+    const Geom* geom; int* dir; int dir_cap;
+    Pool pool;
+    Counters* counters;
+    int bitmap_words, sort_n;
+};
+struct RemapArgs {
+    const unsigned* idx;
+    const Geom* geom; Geom* geom_alt;
+    const int* dir; int* dir_alt; int dir_cap;
+    int* refcnt_new;
+};
+struct SweepArgs { Pool pool; int* refcnt_new; };
+struct DigestArgs {
+    const Geom* geom; const int* dir; int dir_cap; const int4* pool;
+    unsigned first; unsigned long long* out;
+};
+
+void launch_scanmatch(const ScanMatchArgs& a, unsigned n, unsigned threads, cudaStream_t st);
+void launch_eval(const EvalArgs& a, unsigned n, unsigned threads, cudaStream_t st);
+void launch_bounds(const BoundsArgs& a, unsigned n, unsigned threads, cudaStream_t st);
+void launch_relayout(const RelayoutArgs& a, unsigned n, cudaStream_t st);
+void launch_relayout_commit(const RelayoutArgs& a, unsigned n, cudaStream_t st);
+size_t register_smem_bytes(int bitmap_words, int sort_n);
+cudaError_t register_prepare(size_t smem);
+void launch_register(const RegisterArgs& a, unsigned n, unsigned threads, size_t smem, cudaStream_t st);
+void launch_remap(const RemapArgs& a, unsigned n, cudaStream_t st);
+void launch_sweep(const SweepArgs& a, cudaStream_t st);
+void launch_merge_free(const Pool& p, cudaStream_t st);
+void launch_pool_init(const Pool& p, cudaStream_t st);
+void launch_fill_int(int* p, size_t n, int v, cudaStream_t st);
+void launch_fill_geom(Geom* g, unsigned n, Geom v, cudaStream_t st);
+void launch_normalize(const double* logw, unsigned n, double gain, double* w, double* neff, cudaStream_t st);
+void launch_resample(const double* w, unsigned n, double u01, double* cum, double* tgt, unsigned* idx, unsigned* emitted, cudaStream_t st);
+void launch_digest(const DigestArgs& a, unsigned n, cudaStream_t st);
+void launch_export_list(const int* dirp, Geom g, int* list, int* count, cudaStream_t st);
+void launch_export_gather(const int4* pool, const int* list, int4* out, int n, cudaStream_t st);
+
+}  // namespace gm

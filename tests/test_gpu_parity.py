@@ -1,0 +1,244 @@
+"""GPU parity (run with `-m gpu` on a B200): the CUDA path, called through the C ABI, against
+  (1) the golden traces of the unmodified reference (tests/golden), teacher-forced: every stage gets the
+      reference's inputs (motion-model poses, weights, the drand48 draw) and must reproduce its outputs --
+      integer cell counts (n, visits) and resample indexes bit-exact, poses within 1e-4 m / 1e-4 rad,
+      log-likelihoods within 1e-3 relative (BASELINE.json north_star);
+  (2) the oracle on seeded random queries, including the edge cases (zero / NaN / out-of-range beams,
+      empty scans, degenerate weights).
+"""
+import numpy as np
+import pytest
+
+from common import CASES, Golden, digest_rows
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL = 1e-4   # metres / radians (north_star)
+LOGW_RTOL = 1e-3  # relative (north_star)
+# what the kernels actually achieve given identical inputs: FP64 with libm-level (1-2 ulp) differences
+TIGHT = 1e-9
+
+
+def check_maps(ctx, f, want_rows, what):
+    """(n, visits) bit-exact via the order-independent digest; float acc exact or, if a (float) rounding of an
+    endpoint differed in the last place, within 1e-6 of the oracle's cells."""
+    from gpu_common import gpu_digest_rows, map_cells_world
+    got = gpu_digest_rows(ctx)
+    assert np.array_equal(got[:, :5], want_rows[:, :5]), "%s: integer map digest (patches, cells, n, visits)" % what
+    bad = np.nonzero(got[:, 5] != want_rows[:, 5])[0]
+    for j in bad:
+        info, coords, cells = ctx.download_map(int(j))
+        ocoords, ocells = f.map(int(j)).export()
+        ogeo = f.map(int(j)).geometry()
+        r1, a1 = map_cells_world((info.size_x2, info.size_y2), coords, cells)
+        r2, a2 = map_cells_world(ogeo[:2], ocoords, ocells)
+        assert np.array_equal(r1, r2)
+        np.testing.assert_allclose(a1, a2, rtol=1e-6, atol=1e-5, err_msg="%s: acc of particle %d" % (what, j))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_teacher_forced_trace(case):
+    from gpu_common import context_for
+    g = Golden(case)
+    ctx = context_for(g)
+    f = g.oracle_filter()  # runs alongside: supplies the drand48 draw of each resample and full maps for diagnostics
+    first = True
+    n_match = n_res = n_dig = 0
+    for i in range(g.S):
+        processed = f.process(g.ranges[i], g.odom[i], g.stamps[i])
+        assert processed == bool(g.processed[i])
+        if not processed:
+            continue
+        ranges = g.ranges[i]
+        if first:
+            ctx.register(ranges, g.state[i][:, :3])
+            first = False
+        else:
+            poses, sc, s, l, c, ev = ctx.scanmatch(ranges, g.pre_pose[i], g.p["minimumScore"])
+            ref = g.smat[i]
+            np.testing.assert_allclose(sc, ref[:, 3], rtol=TIGHT, atol=TIGHT, err_msg="%s[%d] optimize score" % (case, i))
+            assert np.abs(poses - ref[:, 10:13]).max() <= POSE_TOL, "%s[%d] scan-matched pose" % (case, i)
+            np.testing.assert_allclose(poses, ref[:, 10:13], rtol=0, atol=TIGHT, err_msg="%s[%d] pose (tight)" % (case, i))
+            np.testing.assert_allclose(l, ref[:, 8], rtol=LOGW_RTOL, err_msg="%s[%d] log-likelihood" % (case, i))
+            np.testing.assert_allclose(l, ref[:, 8], rtol=TIGHT, atol=TIGHT, err_msg="%s[%d] log-likelihood (tight)" % (case, i))
+            np.testing.assert_allclose(s, ref[:, 7], rtol=TIGHT, atol=TIGHT)
+            assert np.array_equal(c, ref[:, 9].astype(np.uint32)), "%s[%d] match count" % (case, i)
+            assert np.array_equal(ev, f.match_rows()[:, 7].astype(np.uint32)), "%s[%d] score() evaluations" % (case, i)
+            n_match += 1
+            # weights: normalize the reference's accumulated log-weights
+            w, neff = ctx.normalize(ref[:, 13], g.p["ogain"])
+            if g.resampled[i]:
+                np.testing.assert_allclose(w, g.rw[i], rtol=1e-12, atol=0)
+                np.testing.assert_allclose(neff, g.rneff[i], rtol=1e-12)
+                idx, emitted = ctx.resample_indexes(g.rw[i], f.last_u01())
+                assert np.array_equal(idx, g.ridx[i]), "%s[%d] resample indexes" % (case, i)
+                assert emitted == g.N
+                ctx.register(ranges, g.state[i][:, :3], idx)
+                n_res += 1
+            else:
+                np.testing.assert_allclose(w, g.weights[i], rtol=1e-12, atol=0)
+                np.testing.assert_allclose(neff, g.neff[i], rtol=1e-12)
+                ctx.register(ranges, g.state[i][:, :3])
+        for k in np.nonzero(g.dig_scan == i)[0]:
+            check_maps(ctx, f, digest_rows(g.digests[k]), "%s[%d]" % (case, i))
+            geo = np.array([[m.size_x2, m.size_y2, m.patches_x, m.patches_y] for m in (ctx.map_info(j) for j in range(g.N))])
+            assert np.array_equal(geo[:, :2], g.geometry[k][:, :2]) and np.array_equal(geo[:, 2:], g.geometry[k][:, 4:6])
+            n_dig += 1
+    assert n_match >= 10 and n_dig >= 2
+    assert n_res == int(g.resampled.sum())
+    st = ctx.stats()
+    assert st["launches"] > 0 and st["pool_in_use"] > 0
+    ctx.close()
+
+
+def _random_world(seed, beams=181, particles=5, scans=6):
+    """A few scans registered at jittered poses in both the oracle maps and the GPU maps."""
+    import importlib
+    synth = importlib.import_module("slam-gmapping-learn_b200.synth")
+    gm = importlib.import_module("slam-gmapping-learn_b200")
+    laser = synth.LMS200 if beams == 181 else synth.UTM30
+    log = synth.make_log("room", laser, scans=scans, step=0.4, seed=seed)
+    rng = np.random.default_rng(seed)
+    m = orc.make_matcher(laser.angles(), urange=laser.max_range - 1.0, range_=laser.max_range)
+    ctx = gm.GmContext(particles, pool_patches=4096)
+    ctx.set_laser(laser.angles())
+    ctx.set_matching(urange=laser.max_range - 1.0, range_=laser.max_range)
+    ctx.init_particles(particles)
+    maps = [orc.Map() for _ in range(particles)]
+    poses = None
+    for k in range(scans):
+        poses = log.odom[k][None, :] + rng.normal(0, [0.02, 0.02, 0.01], size=(particles, 3))
+        r = log.ranges[k].copy()
+        if k == 2:  # edge cases inside a scan: zero, NaN, beyond max range, exactly usable range
+            r[3] = 0.0; r[7] = np.nan; r[11] = laser.max_range + 5; r[15] = laser.max_range - 1.0
+        for j in range(particles):
+            orc.register(m, maps[j], poses[j], r)
+        ctx.register(r, poses)
+    return log, m, ctx, maps, poses, rng
+
+
+@pytest.mark.parametrize("beams", [181, 1081])
+def test_score_and_likelihood_vs_oracle(beams):
+    log, m, ctx, maps, poses, rng = _random_world(7, beams=beams)
+    n = len(maps)
+    got = np.stack([np.array(ctx.digests()[k]) for k in ("patches", "cells", "sum_n", "sum_visits")], axis=1)
+    want = np.array([[d.patches, d.cells, d.sum_n, d.sum_visits] for d in (mp.digest() for mp in maps)])
+    assert np.array_equal(got.astype(np.int64), want)
+    r = log.ranges[-1].copy()
+    r[5] = 0.0  # score() skips r == 0, likelihoodAndScore() does not (scanmatcher.h:195 vs :303-308)
+    q = 64
+    idx = rng.integers(0, n, size=q).astype(np.uint32)
+    qp = poses[idx] + rng.normal(0, [0.05, 0.05, 0.03], size=(q, 3))
+    s_gpu = ctx.score(idx, qp, r)
+    s2, l2, c2 = ctx.likelihood_and_score(idx, qp, r)
+    for k in range(q):
+        s = orc.score(m, maps[idx[k]], qp[k], r)
+        so, lo, co = orc.likelihood_and_score(m, maps[idx[k]], qp[k], r)
+        assert abs(s_gpu[k] - s) <= TIGHT * max(1.0, abs(s))
+        assert abs(s2[k] - so) <= TIGHT * max(1.0, abs(so)) and abs(l2[k] - lo) <= TIGHT * max(1.0, abs(lo)) and c2[k] == co
+    assert s_gpu.max() > 10  # the queries really hit the map
+    ctx.close()
+
+
+def test_scanmatch_vs_oracle_random():
+    log, m, ctx, maps, poses, rng = _random_world(11, beams=181, particles=16, scans=5)
+    r = log.ranges[-1]
+    init = poses + rng.normal(0, [0.08, 0.08, 0.04], size=poses.shape)
+    out, sc, s, l, c, ev = ctx.scanmatch(r, init, 0.0)
+    for j in range(len(maps)):
+        m.score_calls = 0
+        so, po = orc.optimize(m, maps[j], init[j], r)
+        assert ev[j] == m.score_calls
+        assert abs(sc[j] - so) <= TIGHT * max(1.0, abs(so))
+        assert np.abs(out[j] - po).max() <= TIGHT
+        s1, l1, c1 = orc.likelihood_and_score(m, maps[j], po, r)
+        assert abs(l[j] - l1) <= TIGHT * max(1.0, abs(l1)) and c[j] == c1
+    st = ctx.stats()
+    assert st["score_evals"] == int(ev.sum()) and st["beam_evals"] > 0
+    ctx.close()
+
+
+def test_empty_and_degenerate_scans():
+    """all-zero scan: nothing matches, nothing is registered; minimum score keeps the odometry pose."""
+    log, m, ctx, maps, poses, rng = _random_world(3, beams=181, particles=4, scans=3)
+    before = ctx.digests()
+    zero = np.zeros(181)
+    out, sc, s, l, c, ev = ctx.scanmatch(zero, poses, 0.0)
+    assert np.array_equal(out, poses) and np.all(sc == 0) and np.all(ev == 1 + 6 * (m.opt_recursive_iterations + 1))
+    # likelihoodAndScore still evaluates r == 0 beams (they match the robot's own cell or nothing)
+    for j in range(4):
+        s1, l1, c1 = orc.likelihood_and_score(m, maps[j], poses[j], zero)
+        assert abs(l[j] - l1) <= TIGHT * max(1.0, abs(l1)) and c[j] == c1
+    ctx.register(zero, poses)
+    after = ctx.digests()
+    assert np.array_equal(before, after)
+    # a huge minimum score rejects every match
+    out, sc, *_ = ctx.scanmatch(log.ranges[2], poses + 0.03, 1e9)
+    assert np.array_equal(out, poses + 0.03) and np.all(sc > 0)
+    ctx.close()
+
+
+def test_normalize_and_resample_vs_oracle():
+    import importlib
+    gm = importlib.import_module("slam-gmapping-learn_b200")
+    ctx = gm.GmContext(4096, pool_patches=64)
+    ctx.set_laser(np.linspace(-1, 1, 181)); ctx.set_matching(); ctx.init_particles(4096)
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 30, 513, 4096):
+        for spread in (0.0, 1.0, 50.0, 5000.0):
+            lw = rng.normal(0, 1, size=n) * spread - 300.0
+            w, neff = ctx.normalize(lw, 3.0)
+            wo, neffo = orc.normalize(lw, 3.0)
+            np.testing.assert_allclose(w, wo, rtol=1e-13, atol=0)
+            assert abs(neff - neffo) <= 1e-12 * neffo
+            for u in (0.0, 0.25, 0.999999, float(rng.random())):
+                idx, em = ctx.resample_indexes(wo, u)
+                io, ko = orc.resample_indexes(wo, u)
+                assert np.array_equal(idx, io), (n, spread, u)
+                assert em == min(ko, n)
+    # all the weight on one particle
+    w = np.zeros(64); w[17] = 1.0
+    idx, em = ctx.resample_indexes(w, 0.5)
+    assert np.all(idx == 17) and em == 64
+    ctx.close()
+
+
+def test_copy_on_write_refcounts():
+    """resample to a single parent: children share patches (no deep copy), the next registration makes the
+    touched patches private again, and the pool returns to its steady size."""
+    log, m, ctx, maps, poses, rng = _random_world(9, beams=181, particles=6, scans=3)
+    in_use0 = ctx.stats()["pool_in_use"]
+    idx = np.zeros(6, dtype=np.uint32) + 2
+    r = log.ranges[2]
+    p2 = np.repeat(poses[2:3], 6, axis=0)
+    ctx.register(r, p2, idx)
+    st = ctx.stats()
+    d = ctx.digests()
+    assert len(set(d["hash_counts"].tolist())) == 1  # identical maps
+    assert st["cow_copies"] > 0
+    # every child copied only the active patches; the parent's other patches are shared
+    patches = int(d["patches"][0])
+    assert st["pool_in_use"] < 6 * patches + 1 and st["pool_in_use"] >= patches
+    # oracle: clone map 2 six times and register
+    want = []
+    for j in range(6):
+        mp = maps[2].clone(); orc.register(m, mp, p2[j], r); want.append(mp.digest())
+    assert all(int(d["hash_counts"][j]) == want[j].hash_counts for j in range(6))
+    assert in_use0 > 0
+    ctx.close()
+
+
+def test_errors_are_loud():
+    import importlib
+    gm = importlib.import_module("slam-gmapping-learn_b200")
+    ctx = gm.GmContext(4, pool_patches=8)  # far too small a pool
+    with pytest.raises(gm.GmError):
+        ctx.scanmatch(np.zeros(3), np.zeros((4, 3)))  # laser not set
+    ctx.set_laser(np.linspace(-1.5, 1.5, 181)); ctx.set_matching(); ctx.init_particles(4)
+    with pytest.raises(gm.GmError) as e:
+        ctx.register(np.full(181, 20.0), np.zeros((4, 3)))
+    assert e.value.code == -3  # GM_ERR_POOL
+    with pytest.raises(gm.GmError):
+        ctx.set_laser(np.zeros(2048))  # beams must be < 2048 (reference asserts, scanmatcher.cpp:704)
+    ctx.close()

@@ -1,0 +1,116 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the UNMODIFIED reference build (oracle/_ref/ref_driver).
+
+Run in the build container (needs /root/reference to have been compiled by `make -C oracle ref`):
+
+    python tools/make_golden.py
+
+For every case: write a seeded synthetic CARMEN log (slam-gmapping-learn_b200/synth.py), run the
+reference driver in trace mode on it, and store the per-stage trace (poses after the motion model,
+optimize/likelihoodAndScore results, weights, Neff, resample indexes, per-particle map digests and
+geometry) as one compressed npz.  The fixtures are what pins the oracle (tests/test_oracle_vs_reference.py)
+and what the GPU parity tests compare against; the GPU box never sees /root/reference.
+"""
+from __future__ import annotations
+
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+synth = importlib.import_module("slam-gmapping-learn_b200.synth")
+from oracle.trace import read_trace  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+REF = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+
+# name -> (log kwargs, filter parameters).  Parameters not listed keep gfs-carmen's defaults
+# (reference: openslam_gmapping/gfs-carmen/gfs-carmen.cpp:52-84), see oracle/ref_driver.cpp Opts.
+CASES = {
+    # ROS-default motion noise => weights spread => resampling fires; every scan passes the gate
+    "room181_n30": (dict(world="room", laser="LMS200", scans=40, step=0.5),
+                    dict(particles=30, linearUpdate=0.4, angularUpdate=0.2, srr=0.1, srt=0.2, str=0.1, stt=0.2, maps_every=5)),
+    # small initial map => Map::resize on the first scans; linearUpdate 1.0 => ungated readings in between
+    "room181_resize": (dict(world="room", laser="LMS200", scans=36, step=0.5),
+                       dict(particles=12, xmin=-4, ymin=-4, xmax=4, ymax=4, linearUpdate=1.0, angularUpdate=0.5, maps_every=3)),
+    # the benchmark's scan shape: 1081 beams, 0.25 deg, beams beyond maxUrange are traced free without a hit
+    "room1081_n8": (dict(world="room", laser="UTM30", scans=12, step=0.5),
+                    dict(particles=8, maxrange=30.0, maxUrange=29.0, linearUpdate=0.4, angularUpdate=0.2,
+                         srr=0.1, srt=0.2, str=0.1, stt=0.2, maps_every=4)),
+    # kernelSize 2, likelihoodSkip 2, endpoint-only maps (generateMap false), minimumScore rejects
+    "room181_k2_lskip": (dict(world="room", laser="LMS200", scans=16, step=0.5),
+                         dict(particles=6, kernelSize=2, lskip=2, generate_map=False, minimumScore=60.0,
+                              linearUpdate=0.4, angularUpdate=0.2, srr=0.05, srt=0.1, str=0.05, stt=0.1, maps_every=4)),
+}
+
+DEFAULTS = dict(particles=30, xmin=-100., ymin=-100., xmax=100., ymax=100., delta=0.05, sigma=0.05, maxrange=80., maxUrange=80.,
+                lstep=0.05, astep=0.05, lsigma=0.075, ogain=3., kernelSize=1, iterations=5, lskip=0,
+                srr=0.01, srt=0.01, str=0.01, stt=0.01, linearUpdate=1.0, angularUpdate=0.5, resampleThreshold=0.5,
+                minimumScore=0.0, period=-1.0, seed=12345, generate_map=True, maps_every=0)
+
+
+def run_case(name, log_kw, par):
+    p = dict(DEFAULTS); p.update(par)
+    lk = dict(log_kw); laser = getattr(synth, lk.pop("laser"))
+    log = synth.make_log(laser=laser, **lk)
+    with tempfile.TemporaryDirectory() as td:
+        lp, tp = os.path.join(td, "in.log"), os.path.join(td, "trace.bin")
+        synth.write_carmen(log, lp)
+        cmd = [REF, "-mode", "trace", "-log", lp, "-out", tp, "-probe", "2", "-maps-every", str(p["maps_every"])]
+        for k in ("particles", "seed", "kernelSize", "iterations", "lskip"):
+            cmd += ["-" + k, str(int(p[k]))]
+        for k in ("xmin", "ymin", "xmax", "ymax", "delta", "sigma", "maxrange", "maxUrange", "lstep", "astep", "lsigma", "ogain",
+                  "srr", "srt", "str", "stt", "linearUpdate", "angularUpdate", "resampleThreshold", "minimumScore", "period"):
+            cmd += ["-" + k, repr(float(p[k]))]
+        if not p["generate_map"]:
+            cmd.append("-no-generateMap")
+        out = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout
+        tr = read_trace(tp)
+    R = tr["readings"]
+    S, N, B = len(R), tr["head"]["particles"], tr["head"]["beams"]
+    a = dict(
+        params=np.array(json.dumps(p)), head_init=tr["head"]["init"], angles=tr["angles"],
+        odom=np.stack([r["odom"] for r in R]), stamps=np.array([r["stamp"] for r in R]),
+        ranges=np.stack([r["ranges"] for r in R]), pre_pose=np.stack([r["pre_pose"] for r in R]),
+        processed=np.array([r["processed"] for r in R]), resampled=np.array([r["resampled"] for r in R]),
+    )
+    assert a["ranges"].shape == (S, B) and a["pre_pose"].shape == (S, N, 3)
+    smat = np.full((S, N, 15), np.nan); probes = np.full((S, 10, 8), np.nan)
+    state = np.full((S, N, 6), np.nan); neff = np.full(S, np.nan); weights = np.full((S, N), np.nan)
+    ridx = np.zeros((S, N), dtype=np.uint32); rw = np.full((S, N), np.nan); rneff = np.full(S, np.nan)
+    dig_scan, digs, geos = [], [], []
+    for i, r in enumerate(R):
+        if "smat" in r: smat[i] = r["smat"]
+        if "probes" in r and len(r["probes"]): probes[i, :len(r["probes"])] = r["probes"]
+        if "state" in r: state[i] = r["state"]; neff[i] = r["neff"]; weights[i] = r["weights"]
+        if "indexes" in r: ridx[i] = r["indexes"]; rw[i] = r["w_at_resample"]; rneff[i] = r["neff_at_resample"]
+        if "digests" in r: dig_scan.append(i); digs.append(r["digests"]); geos.append(r["geometry"])
+    # the driver also dumps all maps after the last reading
+    dig_scan.append(S - 1); digs.append(tr["final"]["digests"]); geos.append(tr["final"]["geometry"])
+    a.update(smat=smat, probes=probes, state=state, neff=neff, weights=weights, ridx=ridx, rw=rw, rneff=rneff,
+             dig_scan=np.array(dig_scan), digests=np.stack(digs), geometry=np.stack(geos),
+             best=np.array(tr["final"]["best"]))
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **a)
+    print("%-18s readings %3d processed %3d resamples %2d  %6.1f KB   %s" % (
+        name, S, int(a["processed"].sum()), int(a["resampled"].sum()), os.path.getsize(path) / 1024, out.strip()[:80]))
+
+
+def main():
+    if not os.path.exists(REF):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    os.makedirs(GOLD, exist_ok=True)
+    for name, (lk, par) in CASES.items():
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
+        run_case(name, lk, par)
+
+
+if __name__ == "__main__":
+    main()
