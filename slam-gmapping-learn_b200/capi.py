@@ -160,7 +160,10 @@ class GmContext:
     # ---- stages
     def _ranges(self, ranges):
         r = _f64(ranges)
-        assert r.shape == (self.nbeams,), "expected %d ranges" % self.nbeams
+        if not self.nbeams:
+            raise GmError(-2, "gm_set_laser has not been called")
+        if r.shape != (self.nbeams,):
+            raise GmError(-2, "expected %d ranges, got %r" % (self.nbeams, r.shape))
         return r
 
     def score(self, particle_idx, poses, ranges):
