@@ -45,6 +45,8 @@ struct gm_ctx {
     unsigned* d_qidx = nullptr; double *d_qposes = nullptr, *d_qs = nullptr, *d_ql = nullptr; unsigned* d_qc = nullptr;
     uint32_t q_cap = 0;
     Counters* d_counters = nullptr;
+    double* d_inv_n = nullptr;
+    size_t scanmatch_smem = 0;
     unsigned long long* d_digest = nullptr;
     int *d_list = nullptr, *d_count = nullptr; int4* d_export = nullptr; size_t export_cap = 0; size_t list_cap = 0;
 
@@ -112,6 +114,12 @@ int ensure_query(gm_ctx* ctx, uint32_t count) {
     CK(dalloc(ctx->d_qidx, count)); CK(dalloc(ctx->d_qposes, (size_t)count * 3));
     CK(dalloc(ctx->d_qs, count)); CK(dalloc(ctx->d_ql, count)); CK(dalloc(ctx->d_qc, count));
     ctx->q_cap = count;
+    return GM_OK;
+}
+
+int prepare_scanmatch(gm_ctx* ctx) {
+    const size_t smem = scanmatch_smem_bytes(ctx->P.nbeams);
+    if (smem != ctx->scanmatch_smem) { CK(scanmatch_prepare(smem)); ctx->scanmatch_smem = smem; }
     return GM_OK;
 }
 
@@ -188,6 +196,13 @@ int gm_create(gm_ctx** out, const gm_config* cfg) {
     CKC(dalloc(c->d_counters, 1));
     CKC(dalloc(c->d_digest, (size_t)N * 6));
     CKC(dalloc(c->d_count, 1));
+    {
+        // 1./n exactly as the host FPU divides (IEEE): PointAccumulator::mean() = (1./n) * acc, smmap.h:24
+        std::vector<double> inv(kInvTable);
+        for (int i = 0; i < kInvTable; i++) { volatile double one = 1., den = (double)i; inv[i] = one / den; }
+        CKC(dalloc(c->d_inv_n, kInvTable));
+        CKC(cudaMemcpy(c->d_inv_n, inv.data(), sizeof(double) * kInvTable, cudaMemcpyHostToDevice));
+    }
     launch_pool_init(c->pool, c->st);
     CKC(cudaGetLastError());
     CKC(cudaStreamSynchronize(c->st));
@@ -209,7 +224,7 @@ int gm_destroy(gm_ctx* c) {
     cudaFree(c->d_c); cudaFree(c->d_evals); cudaFree(c->d_idx); cudaFree(c->d_emitted);
     cudaFree(c->d_w); cudaFree(c->d_logw); cudaFree(c->d_cum); cudaFree(c->d_tgt); cudaFree(c->d_neff);
     cudaFree(c->d_qidx); cudaFree(c->d_qposes); cudaFree(c->d_qs); cudaFree(c->d_ql); cudaFree(c->d_qc);
-    cudaFree(c->d_counters); cudaFree(c->d_digest); cudaFree(c->d_list); cudaFree(c->d_count); cudaFree(c->d_export);
+    cudaFree(c->d_counters); cudaFree(c->d_inv_n); cudaFree(c->d_digest); cudaFree(c->d_list); cudaFree(c->d_count); cudaFree(c->d_export);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->st) cudaStreamDestroy(c->st);
@@ -293,11 +308,12 @@ static int run_eval(gm_ctx* ctx, int mode, uint32_t count, const uint32_t* parti
     CK(cudaMemcpyAsync(ctx->d_ranges, ranges, sizeof(double) * ctx->P.nbeams, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemcpyAsync(ctx->d_qidx, particle_idx, sizeof(uint32_t) * count, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemcpyAsync(ctx->d_qposes, poses, sizeof(double) * 3 * count, cudaMemcpyHostToDevice, ctx->st));
-    EvalArgs a;
-    a.P = ctx->P; a.ranges = ctx->d_ranges; a.angles = ctx->d_angles; a.particle_idx = ctx->d_qidx; a.poses = ctx->d_qposes;
-    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.mode = mode;
-    a.s = ctx->d_qs; a.l = ctx->d_ql; a.c = ctx->d_qc;
-    launch_eval(a, count, ctx->threads, ctx->st);
+    ScanMatchArgs a{};
+    a.P = ctx->P; a.ranges = ctx->d_ranges; a.angles = ctx->d_angles; a.poses = ctx->d_qposes;
+    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.inv_n = ctx->d_inv_n;
+    a.s = ctx->d_qs; a.l = ctx->d_ql; a.c = ctx->d_qc; a.query = mode; a.particle_idx = ctx->d_qidx;
+    if (int r = prepare_scanmatch(ctx)) return r;
+    launch_scanmatch(a, count, ctx->st);
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_eval")) return r;
     if (s_out) CK(cudaMemcpyAsync(s_out, ctx->d_qs, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->st));
@@ -324,15 +340,17 @@ int gm_scanmatch(gm_ctx* ctx, const double* ranges, double* poses_inout, double 
     CK(cudaMemcpyAsync(ctx->d_ranges, ranges, sizeof(double) * ctx->P.nbeams, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemcpyAsync(ctx->d_poses, poses_inout, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->st));
     if (int r = zero_counters(ctx)) return r;
-    ScanMatchArgs a;
+    ScanMatchArgs a{};
+    a.query = -1;
     a.P = ctx->P; a.ranges = ctx->d_ranges; a.angles = ctx->d_angles; a.poses = ctx->d_poses;
-    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells;
+    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.inv_n = ctx->d_inv_n;
     a.minimum_score = minimum_score;
     a.score = ctx->d_score; a.s = ctx->d_s; a.l = ctx->d_l; a.c = ctx->d_c; a.evals = ctx->d_evals;
     a.counters = ctx->d_counters;
     a.valid_score_beams = count_score_beams(ctx, ranges);
+    if (int r = prepare_scanmatch(ctx)) return r;
     CK(cudaEventRecord(ctx->ev0, ctx->st));
-    launch_scanmatch(a, n, ctx->threads, ctx->st);
+    launch_scanmatch(a, n, ctx->st);
     CK(cudaEventRecord(ctx->ev1, ctx->st));
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_scanmatch")) return r;

@@ -17,6 +17,7 @@ constexpr int kPatchMag = 5;
 constexpr int kPatch = 32;
 constexpr int kPatchCells = 1024;
 constexpr int kLineCap = 20000;  // scanmatcher.cpp:55
+constexpr int kInvTable = 4096;  // exactly rounded 1./n for n < kInvTable (PointAccumulator::mean, smmap.h:24)
 
 struct Geom { int sx2, sy2, npx, npy; };
 
@@ -69,13 +70,14 @@ __device__ __forceinline__ bool cell_addr(const Geom& g, const int* __restrict__
 // PointAccumulator::operator double (smmap.h:25) compared against fullnessThreshold.
 // For thr == 0.1 the FP64 quotient n/visits can never round across the threshold unless 10n == visits
 // (|n/v - 1/10| >= 1/(10 v) >> ulp), so the tests are done in exact integer arithmetic.
+static __device__ __noinline__ double occ_ratio(int n, int v) { return (double)n / (double)v; }  // cold: non-default thresholds only
 __device__ __forceinline__ bool occ_gt(int n, int v, const DevParams& P) {
     if (!v) return -1.0 > P.fullness_threshold;
-    return P.thr_is_tenth ? (10ll * n > (long long)v) : ((double)n / (double)v > P.fullness_threshold);
+    return P.thr_is_tenth ? (10ll * n > (long long)v) : (occ_ratio(n, v) > P.fullness_threshold);
 }
 __device__ __forceinline__ bool occ_lt(int n, int v, const DevParams& P) {
     if (!v) return -1.0 < P.fullness_threshold;
-    return P.thr_is_tenth ? (10ll * n < (long long)v) : ((double)n / (double)v < P.fullness_threshold);
+    return P.thr_is_tenth ? (10ll * n < (long long)v) : (occ_ratio(n, v) < P.fullness_threshold);
 }
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {

@@ -17,226 +17,395 @@
 namespace gm {
 
 // ------------------------------------------------------------------------------------------------
-// Window search for one beam (scanmatcher.h:198-252 / :311-365).  `free_off` is delta*freeDelta for
-// score() and freeDelta for likelihoodAndScore().  Returns found and bestMu.
-__device__ __forceinline__ bool beam_match(const DevParams& P, const Geom& g, const int* __restrict__ dirp,
-                                           const int4* __restrict__ pool, double lpx, double lpy, double lpt, double r,
-                                           double ang, double free_off, double& bmx, double& bmy) {
-    double s, c;
-    sincos(lpt + ang, &s, &c);
-    double phx = lpx + r * c, phy = lpy + r * s;
-    int ihx = w2m(phx, P.cx, P.delta, g.sx2), ihy = w2m(phy, P.cy, P.delta, g.sy2);
-    double pfx = lpx + (r - free_off) * c, pfy = lpy + (r - free_off) * s;
-    pfx = pfx - phx; pfy = pfy - phy;
-    // world2map applied to a difference vector: reproduces the reference's `ipfree` quirk
-    int ifx = w2m(pfx, P.cx, P.delta, g.sx2), ify = w2m(pfy, P.cy, P.delta, g.sy2);
+// Scan matching.  What the reference computes per (pose, beam) -- a "beam evaluation" -- is restated so that
+// the result is unchanged but the instruction count and, above all, the code size drop (the literal
+// transcription was 226 KB of SASS and stalled on instruction fetch):
+//   * ONE copy of the beam evaluation: the kernel is a small state machine (initial score -> hill-climb
+//     rounds -> likelihoodAndScore) whose steps all go through the same evaluation loop; thread 0 plans each
+//     step in shared memory (candidate laser poses, which trig table each candidate uses), everybody
+//     evaluates, warps reduce, thread 0 decides.  The hill-climb state lives in shared memory, not registers;
+//   * sin/cos of (laser theta + beam angle) live in shared memory, one table per distinct theta: the four
+//     translation moves of a round share the current theta, the two turns have their own, and a table is
+//     recomputed only when its theta changes (a few times per optimize(), not 6x per round);
+//   * world2map's division by delta is a multiply by 1/delta with an exactness guard: whenever the product is
+//     within 1e-6 of a rounding boundary the reference's division + round() is evaluated (out of line), so the
+//     integer cell index is always the reference's;
+//   * the (2k+1)^2 window: when no lane of the warp straddles a patch edge, one directory lookup and nine
+//     independent 8-byte loads of (n, visits) issued together; cells with n == 0 (free or unknown) drop out
+//     with one compare; only occupied cells load acc and look at the free cell.  The free-cell window is
+//     resolved once per beam: the reference's world2map-of-a-difference quirk puts it half a map away, where
+//     it is almost always wholly unknown;
+//   * mean() = acc * (1./n): 1./n comes from a table of exactly rounded reciprocals (n < 4096).
+// Generic code paths (negative fullnessThreshold, any kernelSize, windows across patch edges) remain.
+
+__device__ __noinline__ int cell_index_slow(double d, double delta) { return (int)round(d / delta); }
+__device__ __noinline__ double recip_slow(int n) { return 1. / n; }
+
+// reference-exact (int)round(d / delta), d = world coordinate minus map centre (map.h:283-287)
+__device__ __forceinline__ int cell_index(double d, double delta, double inv_delta) {
+    const double q = d * inv_delta;
+    int i = __double2int_rn(q);
+    const double f = fabs(q - (double)i);
+    if (fabs(f - 0.5) < 1e-6 || !(fabs(q) < 1e9)) i = cell_index_slow(d, delta);
+    return i;
+}
+
+struct MatchCtx {
+    const int* __restrict__ dirp;
+    const int4* __restrict__ pool;
+    const double* __restrict__ inv_n;
+    Geom g;
+    double inv_delta;
+    bool fast;  // fullnessThreshold >= 0: cells with n == 0 never match, unknown cells always pass as free
+};
+
+__device__ __forceinline__ int dir_at(const MatchCtx& M, int px, int py) {
+    return ((unsigned)px < (unsigned)M.g.npx && (unsigned)py < (unsigned)M.g.npy) ? __ldg(M.dirp + px * M.g.npy + py) : -1;
+}
+
+// window search for one beam (scanmatcher.h:198-252 / :311-365).  (c, s) = cos/sin(lp.theta + angle);
+// `free_off` is delta*freeDelta for score() and freeDelta for likelihoodAndScore().
+// occupancy tests (smmap.h:25 against fullnessThreshold); DEF = the default threshold 0.1, decided in exact integers
+template <bool DEF> __device__ __forceinline__ bool is_occ(int n, int v, const DevParams& P) {
+    return DEF ? (v != 0 && 10ll * n > (long long)v) : occ_gt(n, v, P);
+}
+template <bool DEF> __device__ __forceinline__ bool is_free(int n, int v, const DevParams& P) {
+    return DEF ? (v == 0 || 10ll * n < (long long)v) : occ_lt(n, v, P);
+}
+
+// K1: kernelSize 1 and fullnessThreshold 0.1 (the defaults) -> specialised window code
+template <bool K1>
+__device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M, double lpx, double lpy, double r, double c, double s,
+                                           double free_off, double& bmx, double& bmy) {
+    const Geom& g = M.g;
+    const double phx = lpx + r * c, phy = lpy + r * s;
+    const int ihx = cell_index(phx - P.cx, P.delta, M.inv_delta) + g.sx2;
+    const int ihy = cell_index(phy - P.cy, P.delta, M.inv_delta) + g.sy2;
+    const int k = K1 ? 1 : P.kernel_size;
+    const int x0 = ihx - k, y0 = ihy - k, x1 = ihx + k, y1 = ihy + k;
     bool found = false;
     double bx = 0., by = 0., bn = 0.;
-    const int k = P.kernel_size;
-    for (int xx = -k; xx <= k; xx++)
-        for (int yy = -k; yy <= k; yy++) {
-            int prx = ihx + xx, pry = ihy + yy;
+    const bool single = x0 >= 0 && y0 >= 0 && (x0 >> kPatchMag) == (x1 >> kPatchMag) && (y0 >> kPatchMag) == (y1 >> kPatchMag);
+
+    if (K1 && M.fast && __all_sync(__activemask(), single)) {
+        // ---- fast path (warp-uniform): 3x3 window inside one patch
+        const int id = dir_at(M, x0 >> kPatchMag, y0 >> kPatchMag);
+        if (id < 0) return false;
+        const int4* hbase = M.pool + (size_t)id * kPatchCells + ((x0 & 31) << kPatchMag) + (y0 & 31);
+        int2 nv[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) nv[i] = __ldg(reinterpret_cast<const int2*>(hbase + ((i / 3) << kPatchMag) + (i % 3)) + 1);
+        unsigned mask = 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++)
+            if (nv[i].x != 0 && is_occ<K1>(nv[i].x, nv[i].y, P)) mask |= 1u << i;
+        if (!mask) return false;
+        // free window (the reference's `ipfree` quirk: world2map applied to the difference pfree - phit)
+        const double pfx = (lpx + (r - free_off) * c) - phx, pfy = (lpy + (r - free_off) * s) - phy;
+        const int ifx = cell_index(pfx - P.cx, P.delta, M.inv_delta) + g.sx2;
+        const int ify = cell_index(pfy - P.cy, P.delta, M.inv_delta) + g.sy2;
+        const int fx0 = x0 + ifx, fy0 = y0 + ify, fx1 = x1 + ifx, fy1 = y1 + ify;
+        int fmode = 2;  // 0 every free cell unknown, 2 per-cell lookups
+        if (fx1 < 0 || fy1 < 0 || (fx0 >> kPatchMag) >= g.npx || (fy0 >> kPatchMag) >= g.npy) fmode = 0;
+        else if (fx0 >= 0 && fy0 >= 0 && (fx0 >> kPatchMag) == (fx1 >> kPatchMag) && (fy0 >> kPatchMag) == (fy1 >> kPatchMag) &&
+                 dir_at(M, fx0 >> kPatchMag, fy0 >> kPatchMag) < 0) fmode = 0;
+        while (mask) {
+            const int i = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int xx = i / 3, yy = i - 3 * xx;
+            if (fmode) {
+                long long fi; int fn = 0, fv = 0;
+                if (cell_addr(g, M.dirp, x0 + xx + ifx, y0 + yy + ify, fi)) { const int4 f = __ldg(M.pool + fi); fn = f.z; fv = f.w; }
+                if (!is_free<K1>(fn, fv, P)) continue;
+            }
+            const float2 acc = __ldg(reinterpret_cast<const float2*>(hbase + (xx << kPatchMag) + yy));
+            int n = nv[0].x;
+#pragma unroll
+            for (int q = 1; q < 9; q++) if (i == q) n = nv[q].x;
+            const double inv = n < kInvTable ? __ldg(M.inv_n + n) : recip_slow(n);  // mean() = (1./n) * acc, smmap.h:24
+            const double mx = phx - (double)acc.x * inv, my = phy - (double)acc.y * inv;
+            const double nn = mx * mx + my * my;
+            if (!found || nn < bn) { bx = mx; by = my; bn = nn; found = true; }
+        }
+        bmx = bx; bmy = by;
+        return found;
+    }
+
+    // ---- generic path: per-cell directory lookups, any kernel size / threshold
+    int ifx = 0, ify = 0;
+    bool have_free = false;
+    for (int xx = 0; xx <= 2 * k; xx++)
+        for (int yy = 0; yy <= 2 * k; yy++) {
             long long ci;
+            if (!cell_addr(g, M.dirp, x0 + xx, y0 + yy, ci)) { if (!(-1.0 > P.fullness_threshold)) continue; ci = -1; }
             int4 cell = make_int4(0, 0, 0, 0);
-            if (cell_addr(g, dirp, prx, pry, ci)) cell = __ldg(pool + ci);
-            if (!occ_gt(cell.z, cell.w, P)) continue;
-            long long fi;
-            int fn = 0, fv = 0;
-            if (cell_addr(g, dirp, prx + ifx, pry + ify, fi)) { int4 f = __ldg(pool + fi); fn = f.z; fv = f.w; }
-            if (!occ_lt(fn, fv, P)) continue;
-            double inv = 1. / cell.z;  // mean() = (1./n) * Point(acc.x, acc.y), smmap.h:24
-            double mx = phx - (double)__int_as_float(cell.x) * inv;
-            double my = phy - (double)__int_as_float(cell.y) * inv;
-            double nn = mx * mx + my * my;
-            if (!found) { bx = mx; by = my; bn = nn; found = true; }
-            else if (nn < bn) { bx = mx; by = my; bn = nn; }
+            if (ci >= 0) cell = __ldg(M.pool + ci);
+            if (!is_occ<K1>(cell.z, cell.w, P)) continue;
+            if (!have_free) {
+                const double pfx = (lpx + (r - free_off) * c) - phx, pfy = (lpy + (r - free_off) * s) - phy;
+                ifx = cell_index(pfx - P.cx, P.delta, M.inv_delta) + g.sx2;
+                ify = cell_index(pfy - P.cy, P.delta, M.inv_delta) + g.sy2;
+                have_free = true;
+            }
+            long long fi; int fn = 0, fv = 0;
+            if (cell_addr(g, M.dirp, x0 + xx + ifx, y0 + yy + ify, fi)) { const int4 f = __ldg(M.pool + fi); fn = f.z; fv = f.w; }
+            if (!is_free<K1>(fn, fv, P)) continue;
+            const double inv = (cell.z >= 0 && cell.z < kInvTable) ? __ldg(M.inv_n + cell.z) : recip_slow(cell.z);
+            const double mx = phx - (double)__int_as_float(cell.x) * inv, my = phy - (double)__int_as_float(cell.y) * inv;
+            const double nn = mx * mx + my * my;
+            if (!found || nn < bn) { bx = mx; by = my; bn = nn; found = true; }
         }
     bmx = bx; bmy = by;
     return found;
 }
 
+__device__ __noinline__ void sincos_cold(double t, double* s, double* c) { sincos(t, s, c); }
+
+// the odometry prior of optimize() (scanmatcher.cpp:497-509); 1 unless the odometry reliabilities are set
+__device__ __noinline__ double odo_gain_of(double ang_rel, double lin_rel, const double* init, const double* cm) {
+    double odo_gain = 1;
+    if (ang_rel > 0.) {
+        double dth = init[2] - cm[2];
+        dth = atan2(sin(dth), cos(dth));
+        dth *= dth;
+        odo_gain *= exp(-ang_rel * dth);
+    }
+    if (lin_rel > 0.) {
+        double dx = init[0] - cm[0], dy = init[1] - cm[1];
+        double drho = dx * dx + dy * dy;
+        odo_gain *= exp(-lin_rel * drho);
+    }
+    return odo_gain;
+}
+
 // laser pose in the map frame (scanmatcher.h:177-180)
 __device__ __forceinline__ void laser_pose(const DevParams& P, double x, double y, double t, double& lx, double& ly, double& lt) {
-    double s, c;
-    sincos(t, &s, &c);
-    lx = x + (c * P.laser_pose[0] - s * P.laser_pose[1]);
-    ly = y + (s * P.laser_pose[0] + c * P.laser_pose[1]);
+    if (P.laser_pose[0] == 0. && P.laser_pose[1] == 0.) {  // x + (c*0 - s*0) == x exactly
+        lx = x; ly = y;
+    } else {
+        double s, c;
+        sincos_cold(t, &s, &c);
+        lx = x + (c * P.laser_pose[0] - s * P.laser_pose[1]);
+        ly = y + (s * P.laser_pose[0] + c * P.laser_pose[1]);
+    }
     lt = t + P.laser_pose[2];
 }
 
 // beam i (counted from initialBeamsSkip) is evaluated iff the reference's `skip` counter wraps to 0
 // there: skip++ ; skip = skip > likelihoodSkip ? 0 : skip  (scanmatcher.h:189-196)
 __device__ __forceinline__ bool beam_selected(const DevParams& P, unsigned b) {
-    return ((b - P.beam_skip + 1u) % (P.lskip + 1u)) == 0u;
+    return P.lskip == 0u || ((b - P.beam_skip + 1u) % (P.lskip + 1u)) == 0u;
 }
 
-// Evaluate score() for K candidate poses of one particle with the whole CTA.  Every thread returns the
-// same K sums (fixed-shape reduction: per-thread beam-ordered partials, xor-shuffle tree, warps in order).
-template <int K>
-__device__ __forceinline__ void cta_scores(const DevParams& P, const Geom& g, const int* __restrict__ dirp,
-                                           const int4* __restrict__ pool, const double* __restrict__ ranges,
-                                           const double* __restrict__ angles, const double (*lp)[3], double* red,
-                                           double (&out)[K]) {
-    double acc[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) acc[k] = 0.;
-    const double free_off = P.delta * (P.delta * P.free_cell_ratio);  // map.getDelta()*freeDelta, scanmatcher.h:208
-    const double cexp = -1. / P.gaussian_sigma;
-    for (unsigned b = P.beam_skip + threadIdx.x; b < P.nbeams; b += blockDim.x) {
-        double r = __ldg(ranges + b);
-        if (!beam_selected(P, b) || r > P.usable_range || r == 0.0) continue;
-        double ang = __ldg(angles + b);
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            double mx, my;
-            if (beam_match(P, g, dirp, pool, lp[k][0], lp[k][1], lp[k][2], r, ang, free_off, mx, my))
-                acc[k] += exp((mx * cexp) * mx + (my * cexp) * my);  // ((-1/sigma)*mu)*mu, point.h:34-49
-        }
+constexpr int kSmThreads = 256;
+constexpr int kSmGroups = kSmThreads / 6;  // 42 beam groups x 6 candidate poses = 252 working threads
+
+struct SmShared {
+    // plan of the next evaluation step (thread 0 writes, everybody reads after a barrier)
+    double lx[6], ly[6];   // laser position of each candidate pose
+    double fill_theta[3];  // theta for the trig tables listed in fill[]
+    int fill[3];           // physical trig tables to recompute before evaluating (-1: none)
+    int tab_of[3];         // physical table of: the current theta, theta + adelta, theta - adelta
+    int ncand;             // 1 or 6 poses
+    int mode;              // 0 score(), 1 likelihoodAndScore()
+    int done;
+    // reduction scratch
+    double part[kSmThreads];
+    double red[8], red_l[8];
+    unsigned red_c[8], red_v[8];
+    // hill-climb state (thread 0 only; shared memory keeps it out of everybody's registers)
+    double cur[3], init[3], key[3], currentScore, bestScore, adelta, ldelta;
+    unsigned refinement, evals, valid_lik;
+    int phase, key_ok[3];
+};
+
+// candidate pose m of a hill-climb round around `cur` (scanmatcher.cpp:441-494: Front, Back, Left, Right, TurnLeft, TurnRight)
+__device__ __forceinline__ void candidate(const double* cur, int m, double ldelta, double adelta, double (&out)[3]) {
+    out[0] = cur[0]; out[1] = cur[1]; out[2] = cur[2];
+    switch (m) {
+        case 0: out[0] += ldelta; break;
+        case 1: out[0] -= ldelta; break;
+        case 2: out[1] -= ldelta; break;
+        case 3: out[1] += ldelta; break;
+        case 4: out[2] += adelta; break;
+        default: out[2] -= adelta; break;
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        double v = warp_sum(acc[k]);
-        if (lane == 0) red[k * 32 + warp] = v;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        double v = 0.;
-        for (int w = 0; w < nw; w++) v += red[k * 32 + w];
-        out[k] = v;
-    }
-    __syncthreads();
 }
 
-// likelihoodAndScore for one pose with the whole CTA (scanmatcher.h:271-380)
-__device__ __forceinline__ void cta_likelihood(const DevParams& P, const Geom& g, const int* __restrict__ dirp,
-                                               const int4* __restrict__ pool, const double* __restrict__ ranges,
-                                               const double* __restrict__ angles, const double lp[3], double* red,
-                                               double& s_out, double& l_out, unsigned& c_out, unsigned& valid_out) {
-    double s = 0., l = 0.;
-    unsigned c = 0, valid = 0;
-    const double free_off = P.delta * P.free_cell_ratio;  // freeDelta, scanmatcher.h:320
-    const double cexp = -1. / P.gaussian_sigma, clik = -1. / P.likelihood_sigma;
-    const double noHit = -.5 / P.likelihood_sigma;  // nullLikelihood, scanmatcher.cpp:15
-    for (unsigned b = P.beam_skip + threadIdx.x; b < P.nbeams; b += blockDim.x) {
-        double r = __ldg(ranges + b);
-        if (r > P.usable_range || !beam_selected(P, b)) continue;
-        double mx, my;
-        valid++;
-        bool found = beam_match(P, g, dirp, pool, lp[0], lp[1], lp[2], r, __ldg(angles + b), free_off, mx, my);
-        if (found) { s += exp((mx * cexp) * mx + (my * cexp) * my); c++; }
-        double f = clik * (mx * mx + my * my);
-        l += found ? f : noHit;
+// thread 0: make logical table `which` hold theta (recompute only when its key differs)
+__device__ __forceinline__ void want_table(SmShared& S, int which, double theta, int& nfill) {
+    const int phys = S.tab_of[which];
+    if (!S.key_ok[phys] || S.key[phys] != theta) {
+        S.key[phys] = theta; S.key_ok[phys] = 1;
+        S.fill[nfill] = phys; S.fill_theta[nfill] = theta; nfill++;
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    s = warp_sum(s); l = warp_sum(l);
-    c = __reduce_add_sync(0xffffffffu, c); valid = __reduce_add_sync(0xffffffffu, valid);
-    if (lane == 0) { red[warp] = s; red[32 + warp] = l; red[64 + warp] = (double)c; red[96 + warp] = (double)valid; }
-    __syncthreads();
-    double ss = 0., ll = 0., cc = 0., vv = 0.;
-    for (int w = 0; w < nw; w++) { ss += red[w]; ll += red[32 + w]; cc += red[64 + w]; vv += red[96 + w]; }
-    s_out = ss; l_out = ll; c_out = (unsigned)cc; valid_out = (unsigned)vv;
-    __syncthreads();
 }
 
-// ------------------------------------------------------------------------------------------------
-// scanMatch for one particle per CTA: hill-climb (optimize), accept/reject, likelihoodAndScore.
-__global__ void __launch_bounds__(256) k_scanmatch(ScanMatchArgs A) {
-    __shared__ double red[6 * 32];
-    __shared__ double lp[6][3];
+// thread 0: plan one hill-climb round (scanmatcher.cpp:418-440)
+__device__ __noinline__ void plan_round(const DevParams& P, SmShared& S) {
+    if (S.bestScore >= S.currentScore) { S.refinement++; S.adelta *= .5; S.ldelta *= .5; }
+    S.bestScore = S.currentScore;
+    int nfill = 0;
+    for (int m = 0; m < 6; m++) {
+        double cm[3], lx, ly, lt;
+        candidate(S.cur, m, S.ldelta, S.adelta, cm);
+        laser_pose(P, cm[0], cm[1], cm[2], lx, ly, lt);
+        S.lx[m] = lx; S.ly[m] = ly;
+        if (m >= 4) want_table(S, m - 3, lt, nfill);
+    }
+    for (int j = nfill; j < 3; j++) S.fill[j] = -1;
+    S.ncand = 6; S.mode = 0; S.phase = 1;
+}
+
+// scanMatch for one particle per CTA: hill-climb (optimize), accept/reject, likelihoodAndScore; or, with
+// A.query >= 0, one standalone score()/likelihoodAndScore() per CTA.
+// dynamic shared memory: three (cos, sin) tables of nbeams double2 each.
+template <bool K1>
+__global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ SmShared S;
     const DevParams& P = A.P;
-    const unsigned p = blockIdx.x;
-    const Geom g = A.geom[p];
-    const int* dirp = A.dir + (size_t)p * A.dir_cap;
-    const double init[3] = {A.poses[3 * p], A.poses[3 * p + 1], A.poses[3 * p + 2]};
+    double2* const tabs = reinterpret_cast<double2*>(smem_raw);
+    const unsigned q = blockIdx.x, p = A.query >= 0 ? A.particle_idx[q] : q;
+    const int t = threadIdx.x;
+    MatchCtx M;
+    M.dirp = A.dir + (size_t)p * A.dir_cap; M.pool = A.pool; M.inv_n = A.inv_n; M.g = A.geom[p];
+    M.inv_delta = 1. / P.delta;
+    M.fast = P.fullness_threshold >= 0.;
 
-    double cur[3] = {init[0], init[1], init[2]};
-    if (threadIdx.x == 0) laser_pose(P, cur[0], cur[1], cur[2], lp[0][0], lp[0][1], lp[0][2]);
-    __syncthreads();
-    double s1[1];
-    cta_scores<1>(P, g, dirp, A.pool, A.ranges, A.angles, lp, red, s1);
-    double currentScore = s1[0], bestScore = -1;
-    double adelta = P.opt_angular_delta, ldelta = P.opt_linear_delta;
-    unsigned refinement = 0, evals = 1;
-    do {
-        if (bestScore >= currentScore) { refinement++; adelta *= .5; ldelta *= .5; }
-        bestScore = currentScore;
-        double cand[6][3];
-#pragma unroll
-        for (int m = 0; m < 6; m++) { cand[m][0] = cur[0]; cand[m][1] = cur[1]; cand[m][2] = cur[2]; }
-        cand[0][0] += ldelta;  // Front
-        cand[1][0] -= ldelta;  // Back
-        cand[2][1] -= ldelta;  // Left
-        cand[3][1] += ldelta;  // Right
-        cand[4][2] += adelta;  // TurnLeft
-        cand[5][2] -= adelta;  // TurnRight
-        if (threadIdx.x < 6) {
-            int m = threadIdx.x;
-            laser_pose(P, cand[m][0], cand[m][1], cand[m][2], lp[m][0], lp[m][1], lp[m][2]);
+    if (t == 0) {
+        S.init[0] = S.cur[0] = A.poses[3 * q]; S.init[1] = S.cur[1] = A.poses[3 * q + 1]; S.init[2] = S.cur[2] = A.poses[3 * q + 2];
+        S.adelta = P.opt_angular_delta; S.ldelta = P.opt_linear_delta;
+        S.refinement = 0; S.evals = 1; S.bestScore = -1; S.done = 0;
+        S.tab_of[0] = 0; S.tab_of[1] = 1; S.tab_of[2] = 2;
+        S.key_ok[0] = S.key_ok[1] = S.key_ok[2] = 0;
+        double lx, ly, lt;
+        laser_pose(P, S.cur[0], S.cur[1], S.cur[2], lx, ly, lt);
+        S.lx[0] = lx; S.ly[0] = ly;
+        int nfill = 0;
+        want_table(S, 0, lt, nfill);
+        S.fill[1] = S.fill[2] = -1;
+        S.ncand = 1; S.mode = A.query == 1 ? 1 : 0; S.phase = A.query >= 0 ? 3 : 0;
+    }
+    for (;;) {
+        __syncthreads();  // the plan is visible
+        if (S.done) break;
+        // ---- trig tables that changed
+        bool filled = false;
+        for (int j = 0; j < 3; j++) {
+            const int phys = S.fill[j];
+            if (phys < 0) break;
+            const double theta = S.fill_theta[j];
+            double2* tab = tabs + (size_t)phys * P.nbeams;
+            for (unsigned b = P.beam_skip + t; b < P.nbeams; b += kSmThreads) {
+                double sn, cs;
+                sincos(theta + __ldg(A.angles + b), &sn, &cs);
+                tab[b] = make_double2(cs, sn);
+            }
+            filled = true;
+        }
+        if (filled) __syncthreads();
+        // ---- evaluate: thread t works for candidate t % ncand on beams t / ncand, + ngroups, ...
+        const int mode = S.mode;
+        const bool six = S.ncand == 6;
+        const int m = six ? t % 6 : 0, grp = six ? t / 6 : t, ngroups = six ? kSmGroups : kSmThreads;
+        double acc_s = 0., acc_l = 0.;
+        unsigned cnt = 0, valid = 0;
+        if (!six || t < 6 * kSmGroups) {
+            const double mlx = S.lx[m], mly = S.ly[m];
+            const double2* tab = tabs + (size_t)S.tab_of[m < 4 ? 0 : m - 3] * P.nbeams;
+            // pfree offset: map.getDelta()*freeDelta in score() (scanmatcher.h:208), freeDelta in likelihoodAndScore() (:320)
+            const double free_off = mode ? P.delta * P.free_cell_ratio : P.delta * (P.delta * P.free_cell_ratio);
+            const double cexp = -1. / P.gaussian_sigma, clik = -1. / P.likelihood_sigma;
+            const double noHit = -.5 / P.likelihood_sigma;  // nullLikelihood, scanmatcher.cpp:15
+            for (unsigned b = P.beam_skip + grp; b < P.nbeams; b += ngroups) {
+                const double r = __ldg(A.ranges + b);
+                // score() also skips r == 0 (scanmatcher.h:195); likelihoodAndScore() does not (:303-308)
+                if (!beam_selected(P, b) || r > P.usable_range || (mode == 0 && r == 0.0)) continue;
+                const double2 cs = tab[b];
+                double mx, my;
+                valid++;
+                const bool found = beam_match<K1>(P, M, mlx, mly, r, cs.x, cs.y, free_off, mx, my);
+                if (found) { acc_s += exp((mx * cexp) * mx + (my * cexp) * my); cnt++; }  // ((-1/sigma)*mu)*mu, point.h:34-49
+                if (mode) { const double f = clik * (mx * mx + my * my); acc_l += found ? f : noHit; }
+            }
+        }
+        // ---- reduce (fixed shape: the sums do not depend on scheduling)
+        const int warp = t >> 5, lane = t & 31;
+        if (six) {
+            S.part[t] = acc_s;
+            __syncthreads();
+            if (warp < 6) {  // warp w sums candidate w's 42 partials: lane j takes groups j and j + 32
+                double v = S.part[6 * lane + warp];
+                if (lane + 32 < kSmGroups) v += S.part[6 * (lane + 32) + warp];
+                v = warp_sum(v);
+                if (lane == 0) S.red[warp] = v;
+            }
+        } else {
+            acc_s = warp_sum(acc_s); acc_l = warp_sum(acc_l);
+            cnt = __reduce_add_sync(0xffffffffu, cnt); valid = __reduce_add_sync(0xffffffffu, valid);
+            if (lane == 0) { S.red[warp] = acc_s; S.red_l[warp] = acc_l; S.red_c[warp] = cnt; S.red_v[warp] = valid; }
         }
         __syncthreads();
-        double sc[6];
-        cta_scores<6>(P, g, dirp, A.pool, A.ranges, A.angles, lp, red, sc);
-        evals += 6;
-        double best[3] = {cur[0], cur[1], cur[2]};
-#pragma unroll
-        for (int m = 0; m < 6; m++) {
-            double odo_gain = 1;
-            if (P.ang_rel > 0.) {
-                double dth = init[2] - cand[m][2];
-                dth = atan2(sin(dth), cos(dth));
-                dth *= dth;
-                odo_gain *= exp(-P.ang_rel * dth);
+        if (t != 0) continue;
+
+        // ---- thread 0: the reference's sequential decision logic
+        if (S.phase == 1) {
+            // scanmatcher.cpp:441-517: pick the best of the six moves (strict >, first wins)
+            S.evals += 6;
+            int bm = -1;
+            for (int mm = 0; mm < 6; mm++) {
+                double odo_gain = 1;
+                if (P.ang_rel > 0. || P.lin_rel > 0.) {
+                    double cm[3];
+                    candidate(S.cur, mm, S.ldelta, S.adelta, cm);
+                    odo_gain = odo_gain_of(P.ang_rel, P.lin_rel, S.init, cm);
+                }
+                const double localScore = odo_gain * S.red[mm];
+                if (localScore > S.currentScore) { S.currentScore = localScore; bm = mm; }
             }
-            if (P.lin_rel > 0.) {
-                double dx = init[0] - cand[m][0], dy = init[1] - cand[m][1];
-                double drho = dx * dx + dy * dy;
-                odo_gain *= exp(-P.lin_rel * drho);
+            if (bm >= 0) {
+                double nb[3];
+                candidate(S.cur, bm, S.ldelta, S.adelta, nb);
+                S.cur[0] = nb[0]; S.cur[1] = nb[1]; S.cur[2] = nb[2];
+                if (bm >= 4) {  // a turn won: its table now holds the current theta
+                    const int o = S.tab_of[0];
+                    S.tab_of[0] = S.tab_of[bm - 3]; S.tab_of[bm - 3] = o;
+                }
             }
-            double localScore = odo_gain * sc[m];
-            if (localScore > currentScore) {
-                currentScore = localScore;
-                best[0] = cand[m][0]; best[1] = cand[m][1]; best[2] = cand[m][2];
+            if (S.currentScore > S.bestScore || S.refinement < P.opt_iters) { plan_round(P, S); continue; }
+        } else if (S.phase == 0) {
+            double v = 0.;
+            for (int w = 0; w < kSmThreads / 32; w++) v += S.red[w];
+            S.currentScore = v;
+            plan_round(P, S);
+            continue;
+        } else {
+            // phase 2: likelihoodAndScore of the accepted pose; phase 3: standalone query
+            double ss = 0., ll = 0.; unsigned cc = 0, vv = 0;
+            for (int w = 0; w < kSmThreads / 32; w++) { ss += S.red[w]; ll += S.red_l[w]; cc += S.red_c[w]; vv += S.red_v[w]; }
+            if (S.phase == 3) {
+                A.s[q] = ss;
+                if (A.query == 1) { A.l[q] = ll; A.c[q] = cc; }
+            } else {
+                A.poses[3 * p] = S.cur[0]; A.poses[3 * p + 1] = S.cur[1]; A.poses[3 * p + 2] = S.cur[2];
+                A.score[p] = S.bestScore; A.s[p] = ss; A.l[p] = ll; A.c[p] = cc; A.evals[p] = S.evals;
+                atomicAdd(&A.counters->score_evals, (unsigned long long)S.evals);
+                atomicAdd(&A.counters->beam_evals, (unsigned long long)S.evals * A.valid_score_beams + vv);
             }
+            S.done = 1;
+            continue;
         }
-        cur[0] = best[0]; cur[1] = best[1]; cur[2] = best[2];
-    } while (currentScore > bestScore || refinement < P.opt_iters);
-
-    // gridslamprocessor.hxx:34-48: keep the motion-model pose when the match is not good enough
-    double fin[3];
-    const bool accept = bestScore > A.minimum_score;
-    fin[0] = accept ? cur[0] : init[0]; fin[1] = accept ? cur[1] : init[1]; fin[2] = accept ? cur[2] : init[2];
-    if (threadIdx.x == 0) laser_pose(P, fin[0], fin[1], fin[2], lp[0][0], lp[0][1], lp[0][2]);
-    __syncthreads();
-    double s, l; unsigned c, valid;
-    cta_likelihood(P, g, dirp, A.pool, A.ranges, A.angles, lp[0], red, s, l, c, valid);
-    if (threadIdx.x == 0) {
-        A.poses[3 * p] = fin[0]; A.poses[3 * p + 1] = fin[1]; A.poses[3 * p + 2] = fin[2];
-        A.score[p] = bestScore; A.s[p] = s; A.l[p] = l; A.c[p] = c; A.evals[p] = evals;
-        atomicAdd(&A.counters->score_evals, (unsigned long long)evals);
-        atomicAdd(&A.counters->beam_evals, (unsigned long long)evals * A.valid_score_beams + valid);
-    }
-}
-
-// standalone score()/likelihoodAndScore() queries: one CTA per (particle, pose)
-__global__ void __launch_bounds__(256) k_eval(EvalArgs A) {
-    __shared__ double red[4 * 32];
-    __shared__ double lp[1][3];
-    const DevParams& P = A.P;
-    const unsigned q = blockIdx.x, p = A.particle_idx[q];
-    const Geom g = A.geom[p];
-    const int* dirp = A.dir + (size_t)p * A.dir_cap;
-    if (threadIdx.x == 0) laser_pose(P, A.poses[3 * q], A.poses[3 * q + 1], A.poses[3 * q + 2], lp[0][0], lp[0][1], lp[0][2]);
-    __syncthreads();
-    if (A.mode == 0) {
-        double s1[1];
-        cta_scores<1>(P, g, dirp, A.pool, A.ranges, A.angles, lp, red, s1);
-        if (threadIdx.x == 0) A.s[q] = s1[0];
-    } else {
-        double s, l; unsigned c, valid;
-        cta_likelihood(P, g, dirp, A.pool, A.ranges, A.angles, lp[0], red, s, l, c, valid);
-        if (threadIdx.x == 0) { A.s[q] = s; A.l[q] = l; A.c[q] = c; }
+        // ---- optimize() finished (gridslamprocessor.hxx:34-48): keep the motion-model pose when the match is
+        // not good enough, then likelihoodAndScore at the accepted pose
+        if (!(S.bestScore > A.minimum_score)) { S.cur[0] = S.init[0]; S.cur[1] = S.init[1]; S.cur[2] = S.init[2]; }
+        double lx, ly, lt;
+        laser_pose(P, S.cur[0], S.cur[1], S.cur[2], lx, ly, lt);
+        S.lx[0] = lx; S.ly[0] = ly;
+        int nfill = 0;
+        want_table(S, 0, lt, nfill);
+        for (int j = nfill; j < 3; j++) S.fill[j] = -1;
+        S.ncand = 1; S.mode = 1; S.phase = 2;
     }
 }
 
@@ -661,8 +830,18 @@ __global__ void k_export_gather(const int4* __restrict__ pool, const int* __rest
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-void launch_scanmatch(const ScanMatchArgs& a, unsigned n, unsigned threads, cudaStream_t st) { k_scanmatch<<<n, threads, 0, st>>>(a); }
-void launch_eval(const EvalArgs& a, unsigned n, unsigned threads, cudaStream_t st) { k_eval<<<n, threads, 0, st>>>(a); }
+size_t scanmatch_smem_bytes(unsigned nbeams) { return (size_t)3 * nbeams * sizeof(double2); }
+cudaError_t scanmatch_prepare(size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(k_scanmatch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scanmatch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return e;
+}
+void launch_scanmatch(const ScanMatchArgs& a, unsigned n, cudaStream_t st) {
+    const size_t smem = scanmatch_smem_bytes(a.P.nbeams);
+    if (a.P.kernel_size == 1 && a.P.thr_is_tenth) k_scanmatch<true><<<n, kSmThreads, smem, st>>>(a);
+    else k_scanmatch<false><<<n, kSmThreads, smem, st>>>(a);
+}
+
 void launch_bounds(const BoundsArgs& a, unsigned n, unsigned threads, cudaStream_t st) { k_bounds<<<n, threads, 0, st>>>(a); }
 void launch_relayout(const RelayoutArgs& a, unsigned n, cudaStream_t st) { k_relayout<<<n, 256, 0, st>>>(a); }
 void launch_relayout_commit(const RelayoutArgs& a, unsigned n, cudaStream_t st) { k_relayout_commit<<<n, 256, 0, st>>>(a); }

@@ -10,19 +10,14 @@ struct ScanMatchArgs {
     double* poses;
     const Geom* geom; const int* dir; int dir_cap;
     const int4* pool;
+    const double* inv_n;
     double minimum_score;
     double *score, *s, *l; unsigned *c, *evals;
     Counters* counters;
     unsigned valid_score_beams;
-};
-struct EvalArgs {
-    DevParams P;
-    const double* ranges; const double* angles;
-    const unsigned* particle_idx; const double* poses;
-    const Geom* geom; const int* dir; int dir_cap;
-    const int4* pool;
-    int mode;  // 0 score, 1 likelihoodAndScore
-    double *s, *l; unsigned* c;
+    // standalone queries: query = 0 score(), 1 likelihoodAndScore() of pose q on particle_idx[q]'s map; -1 = scanMatch
+    int query;
+    const unsigned* particle_idx;
 };
 struct BoundsArgs {
     DevParams P;
@@ -56,8 +51,9 @@ struct DigestArgs {
     unsigned first; unsigned long long* out;
 };
 
-void launch_scanmatch(const ScanMatchArgs& a, unsigned n, unsigned threads, cudaStream_t st);
-void launch_eval(const EvalArgs& a, unsigned n, unsigned threads, cudaStream_t st);
+size_t scanmatch_smem_bytes(unsigned nbeams);
+cudaError_t scanmatch_prepare(size_t smem);
+void launch_scanmatch(const ScanMatchArgs& a, unsigned n, cudaStream_t st);
 void launch_bounds(const BoundsArgs& a, unsigned n, unsigned threads, cudaStream_t st);
 void launch_relayout(const RelayoutArgs& a, unsigned n, cudaStream_t st);
 void launch_relayout_commit(const RelayoutArgs& a, unsigned n, cudaStream_t st);
