@@ -117,6 +117,18 @@ int ensure_query(gm_ctx* ctx, uint32_t count) {
     return GM_OK;
 }
 
+// constants of score()/likelihoodAndScore() evaluated once on the host with the reference's expressions
+void derive_params(DevParams& P) {
+    volatile double delta = P.delta, ratio = P.free_cell_ratio, gs = P.gaussian_sigma, ls = P.likelihood_sigma;
+    volatile double free_delta = delta * ratio;
+    P.inv_delta = 1. / delta;
+    P.free_off_score = delta * free_delta;
+    P.free_off_lik = free_delta;
+    P.cexp = -1. / gs;
+    P.clik = -1. / ls;
+    P.no_hit = -.5 / ls;
+}
+
 int prepare_scanmatch(gm_ctx* ctx) {
     const size_t smem = scanmatch_smem_bytes(ctx->P.nbeams);
     if (smem != ctx->scanmatch_smem) { CK(scanmatch_prepare(smem)); ctx->scanmatch_smem = smem; }
@@ -181,9 +193,10 @@ int gm_create(gm_ctx** out, const gm_config* cfg) {
         cap = (size_t)((double)free_b * 0.5 / (kPatchCells * sizeof(int4)));
         cap = std::min<size_t>(cap, (size_t)1 << 22);  // 64 GiB of patches at most by default
     }
-    if (cap > 0x7fffffff) cap = 0x7fffffff;
+    if (cap > ((size_t)1 << 22) - 2) cap = ((size_t)1 << 22) - 2;  // cell indexes (patch * 1024 + cell) stay below 2^32
     c->pool.cap = (int)cap;
-    CKC(dalloc(c->pool.cells, cap * kPatchCells));
+    CKC(dalloc(c->pool.cells, (cap + 1) * kPatchCells));  // + the all-zero patch at index cap (unknown cells)
+    CKC(cudaMemsetAsync(c->pool.cells + cap * kPatchCells, 0, kPatchCells * sizeof(int4), c->st));
     CKC(dalloc(c->pool.refcnt, cap)); CKC(dalloc(c->pool.free_list, cap)); CKC(dalloc(c->pool.pending, cap));
     CKC(dalloc(c->pool.free_top, 1)); CKC(dalloc(c->pool.pending_n, 1));
     CKC(dalloc(c->refcnt_new, cap));
@@ -311,7 +324,8 @@ static int run_eval(gm_ctx* ctx, int mode, uint32_t count, const uint32_t* parti
     ScanMatchArgs a{};
     a.P = ctx->P; a.ranges = ctx->d_ranges; a.angles = ctx->d_angles; a.poses = ctx->d_qposes;
     a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.inv_n = ctx->d_inv_n;
-    a.s = ctx->d_qs; a.l = ctx->d_ql; a.c = ctx->d_qc; a.query = mode; a.particle_idx = ctx->d_qidx;
+    a.s = ctx->d_qs; a.l = ctx->d_ql; a.c = ctx->d_qc; a.query = mode; a.particle_idx = ctx->d_qidx; a.zero_patch = ctx->pool.cap;
+    derive_params(a.P);
     if (int r = prepare_scanmatch(ctx)) return r;
     launch_scanmatch(a, count, ctx->st);
     ctx->stats.launches++;
@@ -347,6 +361,8 @@ int gm_scanmatch(gm_ctx* ctx, const double* ranges, double* poses_inout, double 
     a.minimum_score = minimum_score;
     a.score = ctx->d_score; a.s = ctx->d_s; a.l = ctx->d_l; a.c = ctx->d_c; a.evals = ctx->d_evals;
     a.counters = ctx->d_counters;
+    a.zero_patch = ctx->pool.cap;
+    derive_params(a.P);
     a.valid_score_beams = count_score_beams(ctx, ranges);
     if (int r = prepare_scanmatch(ctx)) return r;
     CK(cudaEventRecord(ctx->ev0, ctx->st));

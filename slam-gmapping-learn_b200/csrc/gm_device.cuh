@@ -30,6 +30,13 @@ struct DevParams {
     int kernel_size, generate_map;
     unsigned opt_iters, lskip, beam_skip, nbeams;
     int thr_is_tenth;  // fullness_threshold is exactly the default 0.1 -> exact integer occupancy tests
+    // derived on the host with the reference's own expressions (IEEE double, no contraction)
+    double inv_delta;       // 1. / delta
+    double free_off_score;  // map.getDelta() * freeDelta, freeDelta = delta * freeCellRatio (scanmatcher.h:187,208)
+    double free_off_lik;    // freeDelta (scanmatcher.h:290,320)
+    double cexp;            // -1. / gaussianSigma (scanmatcher.h:257,368)
+    double clik;            // -1. / likelihoodSigma (scanmatcher.h:375)
+    double no_hit;          // nullLikelihood / likelihoodSigma, nullLikelihood = -.5 (scanmatcher.cpp:15, scanmatcher.h:288)
 };
 
 struct Counters {  // zeroed per stage, read back by the host

@@ -38,15 +38,21 @@ namespace gm {
 //   * mean() = acc * (1./n): 1./n comes from a table of exactly rounded reciprocals (n < 4096).
 // Generic code paths (negative fullnessThreshold, any kernelSize, windows across patch edges) remain.
 
-__device__ __noinline__ int cell_index_slow(double d, double delta) { return (int)round(d / delta); }
+// (int)round(d / delta) the way the reference's x86-64 build evaluates it: cvttsd2si yields INT_MIN for NaN and for
+// values outside int range (a NaN range reading is not skipped by score(), scanmatcher.h:195)
+__device__ __noinline__ int cell_index_slow(double d, double delta) {
+    const double q = round(d / delta);
+    return fabs(q) < 2147483648.0 ? (int)q : (int)0x80000000;
+}
 __device__ __noinline__ double recip_slow(int n) { return 1. / n; }
 
-// reference-exact (int)round(d / delta), d = world coordinate minus map centre (map.h:283-287)
+// reference-exact (int)round(d / delta), d = world coordinate minus map centre (map.h:283-287): multiply by
+// 1/delta, and fall back to the division whenever the product is within 1e-6 of a rounding boundary (this
+// also catches NaN and out-of-range values, for which |q - rn(q)| is not <= 0.499999)
 __device__ __forceinline__ int cell_index(double d, double delta, double inv_delta) {
     const double q = d * inv_delta;
     int i = __double2int_rn(q);
-    const double f = fabs(q - (double)i);
-    if (fabs(f - 0.5) < 1e-6 || !(fabs(q) < 1e9)) i = cell_index_slow(d, delta);
+    if (!(fabs(q - (double)i) <= 0.499999)) i = cell_index_slow(d, delta);
     return i;
 }
 
@@ -55,16 +61,13 @@ struct MatchCtx {
     const int4* __restrict__ pool;
     const double* __restrict__ inv_n;
     Geom g;
-    double inv_delta;
-    bool fast;  // fullnessThreshold >= 0: cells with n == 0 never match, unknown cells always pass as free
+    int zero_patch;  // id of an all-zero patch: stands in for unallocated / outside patches (const Map::cell, map.h:347-354)
 };
 
 __device__ __forceinline__ int dir_at(const MatchCtx& M, int px, int py) {
     return ((unsigned)px < (unsigned)M.g.npx && (unsigned)py < (unsigned)M.g.npy) ? __ldg(M.dirp + px * M.g.npy + py) : -1;
 }
 
-// window search for one beam (scanmatcher.h:198-252 / :311-365).  (c, s) = cos/sin(lp.theta + angle);
-// `free_off` is delta*freeDelta for score() and freeDelta for likelihoodAndScore().
 // occupancy tests (smmap.h:25 against fullnessThreshold); DEF = the default threshold 0.1, decided in exact integers
 template <bool DEF> __device__ __forceinline__ bool is_occ(int n, int v, const DevParams& P) {
     return DEF ? (v != 0 && 10ll * n > (long long)v) : occ_gt(n, v, P);
@@ -73,57 +76,71 @@ template <bool DEF> __device__ __forceinline__ bool is_free(int n, int v, const 
     return DEF ? (v == 0 || 10ll * n < (long long)v) : occ_lt(n, v, P);
 }
 
-// K1: kernelSize 1 and fullnessThreshold 0.1 (the defaults) -> specialised window code
+// window search for one beam (scanmatcher.h:198-252 / :311-365).  (c, s) = cos/sin(lp.theta + angle);
+// `free_off` is delta*freeDelta for score() and freeDelta for likelihoodAndScore().
+// K1: kernelSize 1 and fullnessThreshold 0.1 (the defaults) -> specialised, branch-light window code
 template <bool K1>
 __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M, double lpx, double lpy, double r, double c, double s,
                                            double free_off, double& bmx, double& bmy) {
     const Geom& g = M.g;
     const double phx = lpx + r * c, phy = lpy + r * s;
-    const int ihx = cell_index(phx - P.cx, P.delta, M.inv_delta) + g.sx2;
-    const int ihy = cell_index(phy - P.cy, P.delta, M.inv_delta) + g.sy2;
+    const int ihx = cell_index(phx - P.cx, P.delta, P.inv_delta) + g.sx2;
+    const int ihy = cell_index(phy - P.cy, P.delta, P.inv_delta) + g.sy2;
     const int k = K1 ? 1 : P.kernel_size;
     const int x0 = ihx - k, y0 = ihy - k, x1 = ihx + k, y1 = ihy + k;
     bool found = false;
     double bx = 0., by = 0., bn = 0.;
-    const bool single = x0 >= 0 && y0 >= 0 && (x0 >> kPatchMag) == (x1 >> kPatchMag) && (y0 >> kPatchMag) == (y1 >> kPatchMag);
 
-    if (K1 && M.fast && __all_sync(__activemask(), single)) {
-        // ---- fast path (warp-uniform): 3x3 window inside one patch
-        const int id = dir_at(M, x0 >> kPatchMag, y0 >> kPatchMag);
-        if (id < 0) return false;
-        const int4* hbase = M.pool + (size_t)id * kPatchCells + ((x0 & 31) << kPatchMag) + (y0 & 31);
-        int2 nv[9];
+    if (K1) {
+        // ---- the 3x3 window spans at most 2x2 patches: four directory entries, unknown ones mapped to the
+        // all-zero patch, then nine independent 4-byte loads of n issued together
+        const int pxa = x0 >> kPatchMag, pya = y0 >> kPatchMag, pxb = x1 >> kPatchMag, pyb = y1 >> kPatchMag;
+        const int ida = dir_at(M, pxa, pya);
+        const int idb = pyb != pya ? dir_at(M, pxa, pyb) : ida;
+        const int idc = pxb != pxa ? dir_at(M, pxb, pya) : ida;
+        const int idd = pxb != pxa ? (pyb != pya ? dir_at(M, pxb, pyb) : idc) : idb;
+        if ((ida & idb & idc & idd) < 0) return false;  // every patch unknown: nothing can match
+        const unsigned ea = (unsigned)(ida < 0 ? M.zero_patch : ida) << 10, eb = (unsigned)(idb < 0 ? M.zero_patch : idb) << 10;
+        const unsigned ec = (unsigned)(idc < 0 ? M.zero_patch : idc) << 10, ed = (unsigned)(idd < 0 ? M.zero_patch : idd) << 10;
+        const int nxa = ((pxa + 1) << kPatchMag) - x0, nya = ((pya + 1) << kPatchMag) - y0;  // rows / columns inside patch a
+        unsigned ci[9];
 #pragma unroll
-        for (int i = 0; i < 9; i++) nv[i] = __ldg(reinterpret_cast<const int2*>(hbase + ((i / 3) << kPatchMag) + (i % 3)) + 1);
+        for (int xx = 0; xx < 3; xx++) {
+            const unsigned rowoff = (unsigned)((x0 + xx) & 31) << kPatchMag;
+            const unsigned ra = (xx < nxa ? ea : ec) + rowoff, rb = (xx < nxa ? eb : ed) + rowoff;
+#pragma unroll
+            for (int yy = 0; yy < 3; yy++) ci[3 * xx + yy] = (yy < nya ? ra : rb) + (unsigned)((y0 + yy) & 31);
+        }
+        int nn9[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) nn9[i] = __ldg(reinterpret_cast<const int*>(M.pool + ci[i]) + 2);
         unsigned mask = 0;
 #pragma unroll
-        for (int i = 0; i < 9; i++)
-            if (nv[i].x != 0 && is_occ<K1>(nv[i].x, nv[i].y, P)) mask |= 1u << i;
+        for (int i = 0; i < 9; i++) mask |= nn9[i] != 0 ? 1u << i : 0u;  // n == 0: free or unknown, never "occupied"
         if (!mask) return false;
         // free window (the reference's `ipfree` quirk: world2map applied to the difference pfree - phit)
         const double pfx = (lpx + (r - free_off) * c) - phx, pfy = (lpy + (r - free_off) * s) - phy;
-        const int ifx = cell_index(pfx - P.cx, P.delta, M.inv_delta) + g.sx2;
-        const int ify = cell_index(pfy - P.cy, P.delta, M.inv_delta) + g.sy2;
+        const int ifx = cell_index(pfx - P.cx, P.delta, P.inv_delta) + g.sx2;
+        const int ify = cell_index(pfy - P.cy, P.delta, P.inv_delta) + g.sy2;
         const int fx0 = x0 + ifx, fy0 = y0 + ify, fx1 = x1 + ifx, fy1 = y1 + ify;
-        int fmode = 2;  // 0 every free cell unknown, 2 per-cell lookups
-        if (fx1 < 0 || fy1 < 0 || (fx0 >> kPatchMag) >= g.npx || (fy0 >> kPatchMag) >= g.npy) fmode = 0;
+        bool fcheck = true;  // false: every free cell of this window is unknown, i.e. passes
+        if (fx1 < 0 || fy1 < 0 || (fx0 >> kPatchMag) >= g.npx || (fy0 >> kPatchMag) >= g.npy) fcheck = false;
         else if (fx0 >= 0 && fy0 >= 0 && (fx0 >> kPatchMag) == (fx1 >> kPatchMag) && (fy0 >> kPatchMag) == (fy1 >> kPatchMag) &&
-                 dir_at(M, fx0 >> kPatchMag, fy0 >> kPatchMag) < 0) fmode = 0;
-        while (mask) {
+                 dir_at(M, fx0 >> kPatchMag, fy0 >> kPatchMag) < 0) fcheck = false;
+        while (mask) {  // ascending bit order == the reference's xx-outer / yy-inner scan order
             const int i = __ffs(mask) - 1;
             mask &= mask - 1;
-            const int xx = i / 3, yy = i - 3 * xx;
-            if (fmode) {
+            const int xx = (i * 11) >> 5, yy = i - 3 * xx;  // i / 3 for i < 9
+            const unsigned e = xx < nxa ? (yy < nya ? ea : eb) : (yy < nya ? ec : ed);
+            const int4 cell = __ldg(M.pool + (e + ((unsigned)((x0 + xx) & 31) << kPatchMag) + (unsigned)((y0 + yy) & 31)));
+            if (!is_occ<true>(cell.z, cell.w, P)) continue;
+            if (fcheck) {
                 long long fi; int fn = 0, fv = 0;
                 if (cell_addr(g, M.dirp, x0 + xx + ifx, y0 + yy + ify, fi)) { const int4 f = __ldg(M.pool + fi); fn = f.z; fv = f.w; }
-                if (!is_free<K1>(fn, fv, P)) continue;
+                if (!is_free<true>(fn, fv, P)) continue;
             }
-            const float2 acc = __ldg(reinterpret_cast<const float2*>(hbase + (xx << kPatchMag) + yy));
-            int n = nv[0].x;
-#pragma unroll
-            for (int q = 1; q < 9; q++) if (i == q) n = nv[q].x;
-            const double inv = n < kInvTable ? __ldg(M.inv_n + n) : recip_slow(n);  // mean() = (1./n) * acc, smmap.h:24
-            const double mx = phx - (double)acc.x * inv, my = phy - (double)acc.y * inv;
+            const double inv = cell.z < kInvTable ? __ldg(M.inv_n + cell.z) : recip_slow(cell.z);  // mean() = (1./n) * acc, smmap.h:24
+            const double mx = phx - (double)__int_as_float(cell.x) * inv, my = phy - (double)__int_as_float(cell.y) * inv;
             const double nn = mx * mx + my * my;
             if (!found || nn < bn) { bx = mx; by = my; bn = nn; found = true; }
         }
@@ -137,19 +154,18 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
     for (int xx = 0; xx <= 2 * k; xx++)
         for (int yy = 0; yy <= 2 * k; yy++) {
             long long ci;
-            if (!cell_addr(g, M.dirp, x0 + xx, y0 + yy, ci)) { if (!(-1.0 > P.fullness_threshold)) continue; ci = -1; }
             int4 cell = make_int4(0, 0, 0, 0);
-            if (ci >= 0) cell = __ldg(M.pool + ci);
-            if (!is_occ<K1>(cell.z, cell.w, P)) continue;
+            if (cell_addr(g, M.dirp, x0 + xx, y0 + yy, ci)) cell = __ldg(M.pool + ci);
+            if (!is_occ<false>(cell.z, cell.w, P)) continue;
             if (!have_free) {
                 const double pfx = (lpx + (r - free_off) * c) - phx, pfy = (lpy + (r - free_off) * s) - phy;
-                ifx = cell_index(pfx - P.cx, P.delta, M.inv_delta) + g.sx2;
-                ify = cell_index(pfy - P.cy, P.delta, M.inv_delta) + g.sy2;
+                ifx = cell_index(pfx - P.cx, P.delta, P.inv_delta) + g.sx2;
+                ify = cell_index(pfy - P.cy, P.delta, P.inv_delta) + g.sy2;
                 have_free = true;
             }
             long long fi; int fn = 0, fv = 0;
             if (cell_addr(g, M.dirp, x0 + xx + ifx, y0 + yy + ify, fi)) { const int4 f = __ldg(M.pool + fi); fn = f.z; fv = f.w; }
-            if (!is_free<K1>(fn, fv, P)) continue;
+            if (!is_free<false>(fn, fv, P)) continue;
             const double inv = (cell.z >= 0 && cell.z < kInvTable) ? __ldg(M.inv_n + cell.z) : recip_slow(cell.z);
             const double mx = phx - (double)__int_as_float(cell.x) * inv, my = phy - (double)__int_as_float(cell.y) * inv;
             const double nn = mx * mx + my * my;
@@ -270,8 +286,7 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
     const int t = threadIdx.x;
     MatchCtx M;
     M.dirp = A.dir + (size_t)p * A.dir_cap; M.pool = A.pool; M.inv_n = A.inv_n; M.g = A.geom[p];
-    M.inv_delta = 1. / P.delta;
-    M.fast = P.fullness_threshold >= 0.;
+    M.zero_patch = A.zero_patch;
 
     if (t == 0) {
         S.init[0] = S.cur[0] = A.poses[3 * q]; S.init[1] = S.cur[1] = A.poses[3 * q + 1]; S.init[2] = S.cur[2] = A.poses[3 * q + 2];
@@ -315,9 +330,8 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
             const double mlx = S.lx[m], mly = S.ly[m];
             const double2* tab = tabs + (size_t)S.tab_of[m < 4 ? 0 : m - 3] * P.nbeams;
             // pfree offset: map.getDelta()*freeDelta in score() (scanmatcher.h:208), freeDelta in likelihoodAndScore() (:320)
-            const double free_off = mode ? P.delta * P.free_cell_ratio : P.delta * (P.delta * P.free_cell_ratio);
-            const double cexp = -1. / P.gaussian_sigma, clik = -1. / P.likelihood_sigma;
-            const double noHit = -.5 / P.likelihood_sigma;  // nullLikelihood, scanmatcher.cpp:15
+            const double free_off = mode ? P.free_off_lik : P.free_off_score;
+            const double cexp = P.cexp, clik = P.clik, noHit = P.no_hit;
             for (unsigned b = P.beam_skip + grp; b < P.nbeams; b += ngroups) {
                 const double r = __ldg(A.ranges + b);
                 // score() also skips r == 0 (scanmatcher.h:195); likelihoodAndScore() does not (:303-308)

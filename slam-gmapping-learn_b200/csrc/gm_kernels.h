@@ -18,6 +18,7 @@ struct ScanMatchArgs {
     // standalone queries: query = 0 score(), 1 likelihoodAndScore() of pose q on particle_idx[q]'s map; -1 = scanMatch
     int query;
     const unsigned* particle_idx;
+    int zero_patch;  // pool index of the all-zero patch
 };
 struct BoundsArgs {
     DevParams P;

@@ -127,6 +127,7 @@ def test_score_and_likelihood_vs_oracle(beams):
     assert np.array_equal(got.astype(np.int64), want)
     r = log.ranges[-1].copy()
     r[5] = 0.0  # score() skips r == 0, likelihoodAndScore() does not (scanmatcher.h:195 vs :303-308)
+    r[9] = np.nan  # neither skips NaN: the x86 reference turns it into cell INT_MIN (unknown)
     q = 64
     idx = rng.integers(0, n, size=q).astype(np.uint32)
     qp = poses[idx] + rng.normal(0, [0.05, 0.05, 0.03], size=(q, 3))
