@@ -108,6 +108,11 @@ int gm_score(gm_ctx* ctx, uint32_t count, const uint32_t* particle_idx, const do
 int gm_likelihood_and_score(gm_ctx* ctx, uint32_t count, const uint32_t* particle_idx, const double* poses,
                             const double* ranges, double* s_out, double* l_out, uint32_t* c_out);
 
+/* replaces: ScanMatcher::optimize(pnew, map, init, readings), scanmatcher/scanmatcher.cpp:386-529, for `count`
+ * (particle map, initial pose) queries: poses_out[i] = the hill-climbed pose, score_out[i] = its score. */
+int gm_optimize(gm_ctx* ctx, uint32_t count, const uint32_t* particle_idx, const double* poses_in, const double* ranges,
+                double* poses_out, double* score_out);
+
 /* replaces: GridSlamProcessor::scanMatch, include/gmapping/gridfastslam/gridslamprocessor.hxx:15-75
  * (ScanMatcher::optimize scanmatcher.cpp:386-529, then likelihoodAndScore at the accepted pose).
  * poses_inout: N*3 motion-model poses in, scan-matched poses out (kept when score <= minimum_score).
@@ -127,6 +132,17 @@ int gm_resample_indexes(gm_ctx* ctx, const double* weights, uint32_t n, double u
  * and the first-scan loop gridslamprocessor.cpp:617-633: (optional) remap particle j <- parent idx[j] by
  * patch-reference copy, then computeActiveArea (scanmatcher.cpp:83-254) + registerScan (:266-354) for all. */
 int gm_register(gm_ctx* ctx, const double* ranges, const double* poses /*N*3*/, const uint32_t* idx_or_null);
+
+/* replaces: ScanMatcher::computeActiveArea, scanmatcher/scanmatcher.cpp:83-254, as far as it is observable: the
+ * bounding box of the scan at each particle's pose and the Map::resize it triggers.  (The active patch set itself
+ * is recomputed inside gm_register, like registerScan does after invalidateActiveArea.) */
+int gm_compute_active_area(gm_ctx* ctx, const double* ranges, const double* poses /*N*3*/);
+
+/* the inverse of gm_download_map: replace one particle's map by host content (geometry from info->size_x2/size_y2/
+ * patches_x/patches_y, `npatches` patches at patch_coords with 1024 cells each).  Used to make a host-built
+ * ScanMatcherMap device-resident (standalone ScanMatcher users such as slam_gmapping.cpp:866-927). */
+int gm_upload_map(gm_ctx* ctx, uint32_t particle, const gm_map_info* info, const int32_t* patch_coords, const gm_cell* cells,
+                  uint32_t npatches);
 
 /* replaces: host access to Particle::map (ScanMatcherMap cells / geometry).  Fills up to max_patches patches:
  * patch_coords[2k..2k+1] = (px,py) and cells[k*1024 + lx*32 + ly].  Returns patch count via info. */

@@ -42,7 +42,7 @@ struct gm_ctx {
     unsigned *d_c = nullptr, *d_evals = nullptr, *d_idx = nullptr, *d_emitted = nullptr;
     double *d_w = nullptr, *d_logw = nullptr, *d_cum = nullptr, *d_tgt = nullptr, *d_neff = nullptr;
     // query staging (gm_score / gm_likelihood_and_score)
-    unsigned* d_qidx = nullptr; double *d_qposes = nullptr, *d_qs = nullptr, *d_ql = nullptr; unsigned* d_qc = nullptr;
+    unsigned* d_qidx = nullptr; double *d_qposes = nullptr, *d_qposes_out = nullptr, *d_qs = nullptr, *d_ql = nullptr; unsigned* d_qc = nullptr;
     uint32_t q_cap = 0;
     Counters* d_counters = nullptr;
     double* d_inv_n = nullptr;
@@ -111,7 +111,7 @@ unsigned count_score_beams(const gm_ctx* ctx, const double* ranges) {
 
 int ensure_query(gm_ctx* ctx, uint32_t count) {
     if (count <= ctx->q_cap) return GM_OK;
-    CK(dalloc(ctx->d_qidx, count)); CK(dalloc(ctx->d_qposes, (size_t)count * 3));
+    CK(dalloc(ctx->d_qidx, count)); CK(dalloc(ctx->d_qposes, (size_t)count * 3)); CK(dalloc(ctx->d_qposes_out, (size_t)count * 3));
     CK(dalloc(ctx->d_qs, count)); CK(dalloc(ctx->d_ql, count)); CK(dalloc(ctx->d_qc, count));
     ctx->q_cap = count;
     return GM_OK;
@@ -236,7 +236,7 @@ int gm_destroy(gm_ctx* c) {
     cudaFree(c->d_ranges); cudaFree(c->d_angles); cudaFree(c->d_poses); cudaFree(c->d_score); cudaFree(c->d_s); cudaFree(c->d_l);
     cudaFree(c->d_c); cudaFree(c->d_evals); cudaFree(c->d_idx); cudaFree(c->d_emitted);
     cudaFree(c->d_w); cudaFree(c->d_logw); cudaFree(c->d_cum); cudaFree(c->d_tgt); cudaFree(c->d_neff);
-    cudaFree(c->d_qidx); cudaFree(c->d_qposes); cudaFree(c->d_qs); cudaFree(c->d_ql); cudaFree(c->d_qc);
+    cudaFree(c->d_qidx); cudaFree(c->d_qposes); cudaFree(c->d_qposes_out); cudaFree(c->d_qs); cudaFree(c->d_ql); cudaFree(c->d_qc);
     cudaFree(c->d_counters); cudaFree(c->d_inv_n); cudaFree(c->d_digest); cudaFree(c->d_list); cudaFree(c->d_count); cudaFree(c->d_export);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -311,7 +311,7 @@ int gm_init_particles(gm_ctx* ctx, uint32_t n, const double center[2], double wo
 uint32_t gm_particles(const gm_ctx* ctx) { return ctx ? ctx->n : 0; }
 
 static int run_eval(gm_ctx* ctx, int mode, uint32_t count, const uint32_t* particle_idx, const double* poses,
-                    const double* ranges, double* s_out, double* l_out, uint32_t* c_out) {
+                    const double* ranges, double* s_out, double* l_out, uint32_t* c_out, double* poses_out) {
     if (int r = ready(ctx, true)) return r;
     if (!count) return GM_OK;
     if (!particle_idx || !poses || !ranges) return fail(ctx, GM_ERR_ARG, "eval: null argument");
@@ -324,26 +324,33 @@ static int run_eval(gm_ctx* ctx, int mode, uint32_t count, const uint32_t* parti
     ScanMatchArgs a{};
     a.P = ctx->P; a.ranges = ctx->d_ranges; a.angles = ctx->d_angles; a.poses = ctx->d_qposes;
     a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.inv_n = ctx->d_inv_n;
-    a.s = ctx->d_qs; a.l = ctx->d_ql; a.c = ctx->d_qc; a.query = mode; a.particle_idx = ctx->d_qidx; a.zero_patch = ctx->pool.cap;
+    a.s = ctx->d_qs; a.l = ctx->d_ql; a.c = ctx->d_qc; a.score = ctx->d_qs; a.poses_out = ctx->d_qposes_out;
+    a.query = mode; a.particle_idx = ctx->d_qidx; a.zero_patch = ctx->pool.cap;
     derive_params(a.P);
     if (int r = prepare_scanmatch(ctx)) return r;
     launch_scanmatch(a, count, ctx->st);
     ctx->stats.launches++;
-    if (int r = check_launch(ctx, "k_eval")) return r;
+    if (int r = check_launch(ctx, "k_scanmatch (query)")) return r;
     if (s_out) CK(cudaMemcpyAsync(s_out, ctx->d_qs, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->st));
     if (mode == 1 && l_out) CK(cudaMemcpyAsync(l_out, ctx->d_ql, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->st));
     if (mode == 1 && c_out) CK(cudaMemcpyAsync(c_out, ctx->d_qc, sizeof(uint32_t) * count, cudaMemcpyDeviceToHost, ctx->st));
+    if (mode == 2 && poses_out) CK(cudaMemcpyAsync(poses_out, ctx->d_qposes_out, sizeof(double) * 3 * count, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     return GM_OK;
 }
 
 int gm_score(gm_ctx* ctx, uint32_t count, const uint32_t* particle_idx, const double* poses, const double* ranges, double* score_out) {
-    return run_eval(ctx, 0, count, particle_idx, poses, ranges, score_out, nullptr, nullptr);
+    return run_eval(ctx, 0, count, particle_idx, poses, ranges, score_out, nullptr, nullptr, nullptr);
 }
 
 int gm_likelihood_and_score(gm_ctx* ctx, uint32_t count, const uint32_t* particle_idx, const double* poses, const double* ranges,
                             double* s_out, double* l_out, uint32_t* c_out) {
-    return run_eval(ctx, 1, count, particle_idx, poses, ranges, s_out, l_out, c_out);
+    return run_eval(ctx, 1, count, particle_idx, poses, ranges, s_out, l_out, c_out, nullptr);
+}
+
+int gm_optimize(gm_ctx* ctx, uint32_t count, const uint32_t* particle_idx, const double* poses_in, const double* ranges,
+                double* poses_out, double* score_out) {
+    return run_eval(ctx, 2, count, particle_idx, poses_in, ranges, score_out, nullptr, nullptr, poses_out);
 }
 
 int gm_scanmatch(gm_ctx* ctx, const double* ranges, double* poses_inout, double minimum_score, double* score_out, double* s_out,
@@ -415,40 +422,11 @@ int gm_resample_indexes(gm_ctx* ctx, const double* weights, uint32_t n, double u
     return GM_OK;
 }
 
-int gm_register(gm_ctx* ctx, const double* ranges, const double* poses, const uint32_t* idx) {
-    if (int r = ready(ctx, true)) return r;
-    if (!ranges || !poses) return fail(ctx, GM_ERR_ARG, "gm_register: null argument");
+// computeActiveArea's observable part for all particles: bounding box of the scan at the pose in d_poses and the
+// Map::resize it triggers (scanmatcher.cpp:96-166, map.h:218-241, harray2d.h:80-109).  d_ranges / d_poses are staged.
+static int bounds_and_resize(gm_ctx* ctx) {
     const uint32_t n = ctx->n;
-    if (idx)
-        for (uint32_t i = 0; i < n; i++)
-            if (idx[i] >= n) return fail(ctx, GM_ERR_ARG, "gm_register: parent index %u >= %u", idx[i], n);
-    CK(cudaMemcpyAsync(ctx->d_ranges, ranges, sizeof(double) * ctx->P.nbeams, cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemcpyAsync(ctx->d_poses, poses, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->st));
-    if (int r = zero_counters(ctx)) return r;
-    ctx->stats.ms_remap = 0.f;
-
-    // ---- particle copy by patch reference (gridslamprocessor.hxx:184-213)
-    if (idx) {
-        CK(cudaMemcpyAsync(ctx->d_idx, idx, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->st));
-        CK(cudaEventRecord(ctx->ev0, ctx->st));
-        RemapArgs r;
-        r.idx = ctx->d_idx; r.geom = ctx->geom; r.geom_alt = ctx->geom_alt; r.dir = ctx->dir; r.dir_alt = ctx->dir_alt;
-        r.dir_cap = ctx->dir_cap; r.refcnt_new = ctx->refcnt_new;
-        launch_remap(r, n, ctx->st);
-        SweepArgs s; s.pool = ctx->pool; s.refcnt_new = ctx->refcnt_new;
-        launch_sweep(s, ctx->st);
-        launch_merge_free(ctx->pool, ctx->st);
-        CK(cudaEventRecord(ctx->ev1, ctx->st));
-        ctx->stats.launches += 3;
-        if (int rc = check_launch(ctx, "remap")) return rc;
-        std::swap(ctx->dir, ctx->dir_alt);
-        std::swap(ctx->geom, ctx->geom_alt);
-        CK(cudaStreamSynchronize(ctx->st));
-        CK(cudaEventElapsedTime(&ctx->stats.ms_remap, ctx->ev0, ctx->ev1));
-    }
-
     // ---- computeActiveArea: bounding box + Map::resize (scanmatcher.cpp:96-166)
-    CK(cudaEventRecord(ctx->ev0, ctx->st));
     BoundsArgs b;
     b.P = ctx->P; b.ranges = ctx->d_ranges; b.angles = ctx->d_angles; b.poses = ctx->d_poses;
     b.geom = ctx->geom; b.geom_new = ctx->geom_new; b.shift = ctx->shift; b.counters = ctx->d_counters;
@@ -488,6 +466,45 @@ int gm_register(gm_ctx* ctx, const double* ranges, const double* poses, const ui
         }
     }
 
+    return GM_OK;
+}
+
+int gm_register(gm_ctx* ctx, const double* ranges, const double* poses, const uint32_t* idx) {
+    if (int r = ready(ctx, true)) return r;
+    if (!ranges || !poses) return fail(ctx, GM_ERR_ARG, "gm_register: null argument");
+    const uint32_t n = ctx->n;
+    if (idx)
+        for (uint32_t i = 0; i < n; i++)
+            if (idx[i] >= n) return fail(ctx, GM_ERR_ARG, "gm_register: parent index %u >= %u", idx[i], n);
+    CK(cudaMemcpyAsync(ctx->d_ranges, ranges, sizeof(double) * ctx->P.nbeams, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->d_poses, poses, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->st));
+    if (int r = zero_counters(ctx)) return r;
+    ctx->stats.ms_remap = 0.f;
+
+    // ---- particle copy by patch reference (gridslamprocessor.hxx:184-213)
+    if (idx) {
+        CK(cudaMemcpyAsync(ctx->d_idx, idx, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaEventRecord(ctx->ev0, ctx->st));
+        RemapArgs r;
+        r.idx = ctx->d_idx; r.geom = ctx->geom; r.geom_alt = ctx->geom_alt; r.dir = ctx->dir; r.dir_alt = ctx->dir_alt;
+        r.dir_cap = ctx->dir_cap; r.refcnt_new = ctx->refcnt_new;
+        launch_remap(r, n, ctx->st);
+        SweepArgs s; s.pool = ctx->pool; s.refcnt_new = ctx->refcnt_new;
+        launch_sweep(s, ctx->st);
+        launch_merge_free(ctx->pool, ctx->st);
+        CK(cudaEventRecord(ctx->ev1, ctx->st));
+        ctx->stats.launches += 3;
+        if (int rc = check_launch(ctx, "remap")) return rc;
+        std::swap(ctx->dir, ctx->dir_alt);
+        std::swap(ctx->geom, ctx->geom_alt);
+        CK(cudaStreamSynchronize(ctx->st));
+        CK(cudaEventElapsedTime(&ctx->stats.ms_remap, ctx->ev0, ctx->ev1));
+    }
+
+    CK(cudaEventRecord(ctx->ev0, ctx->st));
+    if (int rc = bounds_and_resize(ctx)) return rc;
+    Counters h;
+
     // ---- active area + copy-on-write + ray/endpoint updates (scanmatcher.cpp:168-354)
     RegisterArgs a;
     a.P = ctx->P; a.ranges = ctx->d_ranges; a.angles = ctx->d_angles; a.poses = ctx->d_poses;
@@ -514,6 +531,67 @@ int gm_register(gm_ctx* ctx, const double* ranges, const double* poses, const ui
     ctx->stats.pool_in_use = (uint64_t)(ctx->pool.cap - top);
     if (h.error == GM_ERR_POOL) return fail(ctx, GM_ERR_POOL, "gm_register: patch pool of %d patches exhausted", ctx->pool.cap);
     if (h.error) return fail(ctx, h.error, "gm_register: device-side error %d", h.error);
+    return GM_OK;
+}
+
+int gm_compute_active_area(gm_ctx* ctx, const double* ranges, const double* poses) {
+    if (int r = ready(ctx, true)) return r;
+    if (!ranges || !poses) return fail(ctx, GM_ERR_ARG, "gm_compute_active_area: null argument");
+    CK(cudaMemcpyAsync(ctx->d_ranges, ranges, sizeof(double) * ctx->P.nbeams, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->d_poses, poses, sizeof(double) * 3 * ctx->n, cudaMemcpyHostToDevice, ctx->st));
+    if (int r = zero_counters(ctx)) return r;
+    if (int r = bounds_and_resize(ctx)) return r;
+    CK(cudaStreamSynchronize(ctx->st));
+    return GM_OK;
+}
+
+int gm_upload_map(gm_ctx* ctx, uint32_t particle, const gm_map_info* info, const int32_t* patch_coords, const gm_cell* cells,
+                  uint32_t npatches) {
+    if (int r = ready(ctx, true)) return r;
+    if (particle >= ctx->n || !info || (npatches && (!patch_coords || !cells))) return fail(ctx, GM_ERR_ARG, "gm_upload_map: bad argument");
+    Geom g;
+    g.sx2 = info->size_x2; g.sy2 = info->size_y2; g.npx = info->patches_x; g.npy = info->patches_y;
+    if (g.npx <= 0 || g.npy <= 0) return fail(ctx, GM_ERR_ARG, "gm_upload_map: empty directory");
+    for (uint32_t k = 0; k < npatches; k++)
+        if (patch_coords[2 * k] < 0 || patch_coords[2 * k] >= g.npx || patch_coords[2 * k + 1] < 0 || patch_coords[2 * k + 1] >= g.npy)
+            return fail(ctx, GM_ERR_ARG, "gm_upload_map: patch (%d,%d) outside the %dx%d directory", patch_coords[2 * k], patch_coords[2 * k + 1], g.npx, g.npy);
+    Geom old;
+    CK(cudaMemcpyAsync(&old, ctx->geom + particle, sizeof old, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    if (int r = zero_counters(ctx)) return r;
+    launch_release_particle(ctx->dir + (size_t)particle * ctx->dir_cap, old.npx * old.npy, ctx->pool, ctx->st);
+    launch_merge_free(ctx->pool, ctx->st);
+    ctx->stats.launches += 2;
+    if (g.npx * g.npy > ctx->dir_cap) {
+        // grow the directory stride for everybody (same path as a device-side Map::resize that outgrows it)
+        const int new_cap = g.npx * g.npy;
+        const size_t dn = (size_t)ctx->max_particles * new_cap;
+        int* grown = nullptr;
+        CK(cudaMalloc(reinterpret_cast<void**>(&grown), dn * sizeof(int)));
+        launch_fill_int(grown, dn, -1, ctx->st);
+        for (uint32_t p = 0; p < ctx->n; p++)
+            CK(cudaMemcpyAsync(grown + (size_t)p * new_cap, ctx->dir + (size_t)p * ctx->dir_cap, sizeof(int) * ctx->dir_cap, cudaMemcpyDeviceToDevice, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        cudaFree(ctx->dir);
+        ctx->dir = grown;
+        CK(dalloc(ctx->dir_alt, dn));
+        launch_fill_int(ctx->dir_alt, dn, -1, ctx->st);
+        ctx->dir_cap = new_cap;
+        ctx->stats.launches += 2;
+    }
+    CK(cudaMemcpyAsync(ctx->geom + particle, &g, sizeof g, cudaMemcpyHostToDevice, ctx->st));
+    if (npatches) {
+        if (2 * (size_t)npatches > 2 * ctx->list_cap) { CK(dalloc(ctx->d_list, (size_t)npatches * 2)); ctx->list_cap = npatches; }
+        if ((size_t)npatches > ctx->export_cap) { CK(dalloc(ctx->d_export, (size_t)npatches * kPatchCells)); ctx->export_cap = npatches; }
+        CK(cudaMemcpyAsync(ctx->d_list, patch_coords, sizeof(int) * 2 * npatches, cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaMemcpyAsync(ctx->d_export, cells, sizeof(int4) * kPatchCells * (size_t)npatches, cudaMemcpyHostToDevice, ctx->st));
+        launch_install_patches(ctx->dir + (size_t)particle * ctx->dir_cap, g, ctx->d_list, ctx->d_export, ctx->pool, ctx->d_counters, (int)npatches, ctx->st);
+        ctx->stats.launches++;
+    }
+    if (int r = check_launch(ctx, "gm_upload_map")) return r;
+    Counters h;
+    if (int r = read_counters(ctx, h)) return r;
+    if (h.error) return fail(ctx, h.error, "gm_upload_map: patch pool of %d patches exhausted", ctx->pool.cap);
     return GM_OK;
 }
 

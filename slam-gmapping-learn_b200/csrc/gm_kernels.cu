@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
         int nfill = 0;
         want_table(S, 0, lt, nfill);
         S.fill[1] = S.fill[2] = -1;
-        S.ncand = 1; S.mode = A.query == 1 ? 1 : 0; S.phase = A.query >= 0 ? 3 : 0;
+        S.ncand = 1; S.mode = A.query == 1 ? 1 : 0; S.phase = (A.query == 0 || A.query == 1) ? 3 : 0;
     }
     for (;;) {
         __syncthreads();  // the plan is visible
@@ -407,6 +407,12 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
                 atomicAdd(&A.counters->score_evals, (unsigned long long)S.evals);
                 atomicAdd(&A.counters->beam_evals, (unsigned long long)S.evals * A.valid_score_beams + vv);
             }
+            S.done = 1;
+            continue;
+        }
+        if (A.query == 2) {  // standalone optimize(): report the climbed pose and its score
+            A.poses_out[3 * q] = S.cur[0]; A.poses_out[3 * q + 1] = S.cur[1]; A.poses_out[3 * q + 2] = S.cur[2];
+            A.score[q] = S.bestScore;
             S.done = 1;
             continue;
         }
@@ -843,7 +849,31 @@ __global__ void k_export_gather(const int4* __restrict__ pool, const int* __rest
     for (int i = threadIdx.x; i < kPatchCells; i += blockDim.x) out[(size_t)k * kPatchCells + i] = pool[(size_t)id * kPatchCells + i];
 }
 
+// drop every patch reference of one particle (before its map is replaced by gm_upload_map)
+__global__ void k_release_particle(int* dirp, int nent, Pool pool) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nent; e += gridDim.x * blockDim.x) {
+        const int id = dirp[e];
+        if (id >= 0 && atomicSub(&pool.refcnt[id], 1) == 1) pool.pending[atomicAdd(pool.pending_n, 1)] = id;
+        dirp[e] = -1;
+    }
+}
+// install uploaded patches: block k takes a free patch, copies the staged cells, writes the directory entry
+__global__ void k_install_patches(int* dirp, Geom g, const int* __restrict__ coords, const int4* __restrict__ staged, Pool pool, Counters* ctr) {
+    __shared__ int s_id;
+    const int k = blockIdx.x;
+    if (threadIdx.x == 0) s_id = pool_alloc(pool, ctr);
+    __syncthreads();
+    const int id = s_id;
+    if (id < 0) return;
+    for (int i = threadIdx.x; i < kPatchCells; i += blockDim.x) pool.cells[(size_t)id * kPatchCells + i] = staged[(size_t)k * kPatchCells + i];
+    if (threadIdx.x == 0) { pool.refcnt[id] = 1; dirp[coords[2 * k] * g.npy + coords[2 * k + 1]] = id; }
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
+void launch_release_particle(int* dirp, int nent, const Pool& pool, cudaStream_t st) { k_release_particle<<<64, 256, 0, st>>>(dirp, nent, pool); }
+void launch_install_patches(int* dirp, Geom g, const int* coords, const int4* staged, const Pool& pool, Counters* ctr, int n, cudaStream_t st) {
+    k_install_patches<<<n, 256, 0, st>>>(dirp, g, coords, staged, pool, ctr);
+}
 size_t scanmatch_smem_bytes(unsigned nbeams) { return (size_t)3 * nbeams * sizeof(double2); }
 cudaError_t scanmatch_prepare(size_t smem) {
     cudaError_t e = cudaFuncSetAttribute(k_scanmatch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

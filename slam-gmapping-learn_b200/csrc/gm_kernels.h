@@ -19,6 +19,7 @@ struct ScanMatchArgs {
     int query;
     const unsigned* particle_idx;
     int zero_patch;  // pool index of the all-zero patch
+    double* poses_out;  // query 2 (standalone optimize): climbed poses
 };
 struct BoundsArgs {
     DevParams P;
@@ -70,6 +71,8 @@ void launch_fill_geom(Geom* g, unsigned n, Geom v, cudaStream_t st);
 void launch_normalize(const double* logw, unsigned n, double gain, double* w, double* neff, cudaStream_t st);
 void launch_resample(const double* w, unsigned n, double u01, double* cum, double* tgt, unsigned* idx, unsigned* emitted, cudaStream_t st);
 void launch_digest(const DigestArgs& a, unsigned n, cudaStream_t st);
+void launch_release_particle(int* dirp, int nent, const Pool& pool, cudaStream_t st);
+void launch_install_patches(int* dirp, Geom g, const int* coords, const int4* staged, const Pool& pool, Counters* ctr, int n, cudaStream_t st);
 void launch_export_list(const int* dirp, Geom g, int* list, int* count, cudaStream_t st);
 void launch_export_gather(const int4* pool, const int* list, int4* out, int n, cudaStream_t st);
 

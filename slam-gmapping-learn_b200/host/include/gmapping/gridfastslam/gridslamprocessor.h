@@ -1,0 +1,188 @@
+// gridslamprocessor.h -- GMapping::GridSlamProcessor with the reference's API
+// (include/gmapping/gridfastslam/gridslamprocessor.h:35-367).
+//
+// What stays on the host: the drand48-driven motion model, the update gate, the trajectory tree,
+// the .gfs trace and the weight bookkeeping.  What runs on the B200 through the C ABI (include/gm_b200.h):
+// scanMatch (gm_scanmatch), normalize/Neff (gm_normalize_neff), resampleIndexes (gm_resample_indexes) and the
+// particle copy + registerScan loop (gm_register).  Particle::map is a device-resident ScanMatcherMap: reading it
+// from the host downloads that particle's patches on first use after every update (grid/map.h).
+#ifndef GMB200_GRIDSLAMPROCESSOR_H
+#define GMB200_GRIDSLAMPROCESSOR_H
+#include <gmapping/gridfastslam/gridfastslam_export.h>
+#include <gmapping/gridfastslam/motionmodel.h>
+#include <gmapping/particlefilter/particlefilter.h>
+#include <gmapping/scanmatcher/scanmatcher.h>
+#include <gmapping/sensor/sensor_odometry/odometryreading.h>
+#include <gmapping/sensor/sensor_range/rangereading.h>
+#include <gmapping/sensor/sensor_range/rangesensor.h>
+#include <gmapping/utils/macro_params.h>
+#include <gmapping/utils/point.h>
+
+#include <climits>
+#include <deque>
+#include <fstream>
+#include <limits>
+#include <map>
+#include <memory>
+#include <vector>
+
+namespace GMapping {
+
+namespace b200 { class DeviceContext; }
+
+class GRIDFASTSLAM_EXPORT GridSlamProcessor {
+  public:
+    // node of the reversed trajectory tree: every particle points at its newest node, nodes point at their parent,
+    // `childs` counts the references; deleting a node whose parent has no other child deletes the parent too
+    struct TNode {
+        TNode(const OrientedPoint& pose, double weight, TNode* parent = 0, unsigned int childs = 0);
+        ~TNode();
+        OrientedPoint pose;
+        double weight;
+        double accWeight;  // sum of the (normalised) weights of the leaves below this node
+        double gweight;
+        TNode* parent;
+        const RangeReading* reading;
+        unsigned int childs;
+        mutable unsigned int visitCounter;
+        mutable bool flag;
+        mutable unsigned int epoch;  // B200 build: pass stamp so that shared ancestors are reset once per pass
+    };
+    typedef std::vector<GridSlamProcessor::TNode*> TNodeVector;
+    typedef std::deque<GridSlamProcessor::TNode*> TNodeDeque;
+
+    struct Particle {
+        Particle(const ScanMatcherMap& map);
+        inline operator double() const { return weight; }
+        inline operator OrientedPoint() const { return pose; }
+        inline void setWeight(double w) { weight = w; }
+        ScanMatcherMap map;  // host mirror of the particle's device-resident map
+        OrientedPoint pose;
+        OrientedPoint previousPose;
+        double weight;     // log-weight accumulated since the last resampling
+        double weightSum;  // log-weight accumulated over the whole run
+        double gweight;
+        int previousIndex;
+        TNode* node;
+    };
+    typedef std::vector<Particle> ParticleVector;
+
+    GridSlamProcessor();
+    GridSlamProcessor(std::ostream& infoStr);
+    // deep copy of the filter including the trajectory tree (device-side clone is not in this
+    // round; aborts with a message)
+    GridSlamProcessor* clone() const;
+    virtual ~GridSlamProcessor();
+
+    void setSensorMap(const SensorMap& smap);
+    void init(unsigned int size, double xmin, double ymin, double xmax, double ymax, double delta,
+              OrientedPoint initialPose = OrientedPoint(0, 0, 0));
+    void setMatchingParameters(double urange, double range, double sigma, int kernsize, double lopt, double aopt, int iterations,
+                               double likelihoodSigma = 1, double likelihoodGain = 1, unsigned int likelihoodSkip = 0);
+    void setMotionModelParameters(double srr, double srt, double str, double stt);
+    void setUpdateDistances(double linear, double angular, double resampleThreshold);
+    void setUpdatePeriod(double p) { period_ = p; }
+
+    void processTruePos(const OdometryReading& odometry);
+    // one laser reading: motion-model sampling always; when the robot moved enough (or the period elapsed) scan
+    // matching, weighting, resampling and map update.  Returns whether the filter was updated.
+    bool processScan(const RangeReading& reading, int adaptParticles = 0);
+
+    TNodeVector getTrajectories() const;
+    void integrateScanSequence(TNode* node);
+
+    ScanMatcher m_matcher;
+    std::ofstream& outputStream();
+    std::ostream& infoStream();
+    inline const ParticleVector& getParticles() const { return m_particles; }
+    inline const std::vector<unsigned int>& getIndexes() const { return m_indexes; }
+    int getBestParticleIndex() const;
+
+    virtual void onOdometryUpdate();
+    virtual void onResampleUpdate();
+    virtual void onScanmatchUpdate();
+
+    MEMBER_PARAM_SET_GET(m_matcher, double, laserMaxRange, protected, public, public);
+    MEMBER_PARAM_SET_GET(m_matcher, double, usableRange, protected, public, public);
+    MEMBER_PARAM_SET_GET(m_matcher, double, gaussianSigma, protected, public, public);
+    MEMBER_PARAM_SET_GET(m_matcher, double, likelihoodSigma, protected, public, public);
+    MEMBER_PARAM_SET_GET(m_matcher, int, kernelSize, protected, public, public);
+    MEMBER_PARAM_SET_GET(m_matcher, double, optAngularDelta, protected, public, public);
+    MEMBER_PARAM_SET_GET(m_matcher, double, optLinearDelta, protected, public, public);
+    MEMBER_PARAM_SET_GET(m_matcher, unsigned int, optRecursiveIterations, protected, public, public);
+    MEMBER_PARAM_SET_GET(m_matcher, unsigned int, likelihoodSkip, protected, public, public);
+    MEMBER_PARAM_SET_GET(m_matcher, double, llsamplerange, protected, public, public);
+    MEMBER_PARAM_SET_GET(m_matcher, double, lasamplerange, protected, public, public);
+    MEMBER_PARAM_SET_GET(m_matcher, double, llsamplestep, protected, public, public);
+    MEMBER_PARAM_SET_GET(m_matcher, double, lasamplestep, protected, public, public);
+    MEMBER_PARAM_SET_GET(m_matcher, bool, generateMap, protected, public, public);
+    MEMBER_PARAM_SET_GET(m_matcher, bool, enlargeStep, protected, public, public);
+    MEMBER_PARAM_SET_GET(m_matcher, OrientedPoint, laserPose, protected, public, public);
+
+    STRUCT_PARAM_SET_GET(m_motionModel, double, srr, protected, public, public);
+    STRUCT_PARAM_SET_GET(m_motionModel, double, srt, protected, public, public);
+    STRUCT_PARAM_SET_GET(m_motionModel, double, str, protected, public, public);
+    STRUCT_PARAM_SET_GET(m_motionModel, double, stt, protected, public, public);
+
+    PARAM_SET_GET(double, minimumScore, protected, public, public);
+
+    // ---- B200 additions (not in the reference API)
+    // device time of the last processed scan's stages and the work they did (C ABI gm_stats)
+    struct DeviceStats {
+        double msScanMatch, msWeights, msRemap, msRegister;
+        unsigned long long beamEvals, scoreEvals, cowCopies, patchAllocs, freeUpdates, hitUpdates, poolInUse, launches;
+    };
+    DeviceStats deviceStats() const;
+    // order-independent digests of all particle maps (patches, cells, sum n, sum visits, hash of (cell, n, visits), hash of acc)
+    std::vector<unsigned long long> mapDigests() const;
+
+  protected:
+    GridSlamProcessor(const GridSlamProcessor& gsp);
+
+    unsigned int m_beams;
+    double last_update_time_;
+    double period_;
+    ParticleVector m_particles;
+    std::vector<unsigned int> m_indexes;
+    std::vector<double> m_weights;
+    MotionModel m_motionModel;
+    PARAM_SET_GET(double, resampleThreshold, protected, public, public);
+    int m_count, m_readingCount;
+    OrientedPoint m_lastPartPose;
+    OrientedPoint m_odoPose;
+    OrientedPoint m_pose;
+    double m_linearDistance, m_angularDistance;
+    PARAM_GET(double, neff, protected, public);
+    PARAM_GET(double, xmin, protected, public);
+    PARAM_GET(double, ymin, protected, public);
+    PARAM_GET(double, xmax, protected, public);
+    PARAM_GET(double, ymax, protected, public);
+    PARAM_GET(double, delta, protected, public);
+    PARAM_SET_GET(double, regScore, protected, public, public);
+    PARAM_SET_GET(double, critScore, protected, public, public);
+    PARAM_SET_GET(double, maxMove, protected, public, public);
+    PARAM_SET_GET(double, linearThresholdDistance, protected, public, public);
+    PARAM_SET_GET(double, angularThresholdDistance, protected, public, public);
+    PARAM_SET_GET(double, obsSigmaGain, protected, public, public);
+    std::ofstream m_outputStream;
+    std::ostream& m_infoStream;
+
+  private:
+    void scanMatch(const double* plainReading);
+    void normalize();
+    bool resample(const double* plainReading, int adaptParticles, const RangeReading* rr = 0);
+    void updateTreeWeights(bool weightsAlreadyNormalized = false);
+    void resetTree();
+    double propagateWeights();
+    void registerAll(const double* plainReading, const unsigned int* parents);
+    void markMapsStale();
+
+    std::shared_ptr<b200::DeviceContext> m_device;
+    unsigned int m_treeEpoch;
+    std::vector<double> m_poseBuf, m_scoreBuf, m_likBuf;
+};
+
+typedef std::multimap<const GridSlamProcessor::TNode*, GridSlamProcessor::TNode*> TNodeMultimap;
+
+}  // namespace GMapping
+#endif

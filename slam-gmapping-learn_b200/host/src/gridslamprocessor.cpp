@@ -1,0 +1,503 @@
+// gridslamprocessor.cpp -- the per-scan particle update with the heavy stages on the B200
+// (reference: gridfastslam/gridslamprocessor.cpp, gridslamprocessor_tree.cpp, gridslamprocessor.hxx).
+//
+// processScan keeps the reference's order of side effects exactly -- motion-model draws for every particle on
+// every reading, the gate, scanMatch, onScanmatchUpdate, tree weights, resample (one drand48 draw only when it
+// fires), tree weights again -- because the drand48 stream, the .gfs trace and the virtual hooks are all visible
+// to users.  The four stages that are O(particles x beams) are single calls into the C ABI.
+#include <gmapping/gridfastslam/gridslamprocessor.h>
+#include <gmapping/utils/stat.h>
+#include <stdlib.h>
+
+#include <cassert>
+#include <cmath>
+#include <iomanip>
+#include <iostream>
+#include <set>
+#include <string>
+
+#include "devicemap.h"
+
+namespace GMapping {
+
+using std::endl;
+
+static const double kOdometryJumpWarning = 20;  // metres between two readings (reference: gridslamprocessor.cpp:17)
+
+// ------------------------------------------------------------------------------------------ trajectory tree
+GridSlamProcessor::TNode::TNode(const OrientedPoint& p, double w, TNode* n, unsigned int c)
+    : pose(p), weight(w), accWeight(0), gweight(0), parent(n), reading(0), childs(c), visitCounter(0), flag(false), epoch(0) {
+    if (parent) parent->childs++;
+}
+
+GridSlamProcessor::TNode::~TNode() {
+    if (parent && --parent->childs == 0) delete parent;
+    assert(!childs);
+}
+
+GridSlamProcessor::Particle::Particle(const ScanMatcherMap& m)
+    : map(m), pose(0, 0, 0), previousPose(0, 0, 0), weight(0), weightSum(0), gweight(0), previousIndex(0), node(0) {}
+
+// ------------------------------------------------------------------------------------------ construction
+static void defaults(GridSlamProcessor& g) {
+    g.setobsSigmaGain(1);
+    g.setresampleThreshold(0.5);
+    g.setminimumScore(0.);
+}
+
+GridSlamProcessor::GridSlamProcessor()
+    : m_beams(0), last_update_time_(0.0), period_(5.0), m_count(0), m_readingCount(0), m_linearDistance(0), m_angularDistance(0),
+      m_neff(0), m_xmin(0), m_ymin(0), m_xmax(0), m_ymax(0), m_delta(0), m_regScore(0), m_critScore(0), m_maxMove(0),
+      m_linearThresholdDistance(0), m_angularThresholdDistance(0), m_infoStream(std::cout), m_treeEpoch(0) {
+    m_motionModel.srr = m_motionModel.srt = m_motionModel.str = m_motionModel.stt = 0;
+    defaults(*this);
+}
+
+GridSlamProcessor::GridSlamProcessor(std::ostream& infoS)
+    : m_beams(0), last_update_time_(0.0), period_(5.0), m_count(0), m_readingCount(0), m_linearDistance(0), m_angularDistance(0),
+      m_neff(0), m_xmin(0), m_ymin(0), m_xmax(0), m_ymax(0), m_delta(0), m_regScore(0), m_critScore(0), m_maxMove(0),
+      m_linearThresholdDistance(0), m_angularThresholdDistance(0), m_infoStream(infoS), m_treeEpoch(0) {
+    m_motionModel.srr = m_motionModel.srt = m_motionModel.str = m_motionModel.stt = 0;
+    defaults(*this);
+}
+
+GridSlamProcessor::GridSlamProcessor(const GridSlamProcessor& gsp) : m_infoStream(std::cout) {
+    (void)gsp;
+    b200::fatal("GridSlamProcessor copy / clone(): a device-side filter clone is not part of this build (SURVEY.md §8 row f3)");
+}
+
+GridSlamProcessor* GridSlamProcessor::clone() const { return new GridSlamProcessor(*this); }
+
+// free the trajectory tree: deleting a leaf walks up and frees every ancestor that loses its last child.
+// Before the first processed scan all particles share the root, so each distinct node is deleted once.
+static void releaseLeaves(GridSlamProcessor::ParticleVector& particles) {
+    std::set<GridSlamProcessor::TNode*> leaves;
+    for (GridSlamProcessor::ParticleVector::iterator it = particles.begin(); it != particles.end(); ++it) {
+        if (it->node) leaves.insert(it->node);
+        it->node = 0;
+    }
+    for (std::set<GridSlamProcessor::TNode*>::iterator it = leaves.begin(); it != leaves.end(); ++it) delete *it;
+}
+
+GridSlamProcessor::~GridSlamProcessor() { releaseLeaves(m_particles); }
+
+// the beam table comes from the front laser ("FLASER", or "ROBOTLASER1" for the newer CARMEN format)
+void GridSlamProcessor::setSensorMap(const SensorMap& smap) {
+    SensorMap::const_iterator it = smap.find(std::string("FLASER"));
+    if (it == smap.end()) it = smap.find(std::string("ROBOTLASER1"));
+    assert(it != smap.end());
+    const RangeSensor* rs = dynamic_cast<const RangeSensor*>(it->second);
+    assert(rs && rs->beams().size());
+    m_beams = static_cast<unsigned int>(rs->beams().size());
+    std::vector<double> angles(m_beams);
+    for (unsigned int i = 0; i < m_beams; i++) angles[i] = rs->beams()[i].pose.theta;
+    m_matcher.setLaserParameters(m_beams, angles.data(), rs->getPose());
+}
+
+void GridSlamProcessor::setMatchingParameters(double urange, double range, double sigma, int kernsize, double lopt, double aopt, int iterations,
+                                              double likelihoodSigma, double likelihoodGain, unsigned int likelihoodSkip) {
+    m_obsSigmaGain = likelihoodGain;
+    m_matcher.setMatchingParameters(urange, range, sigma, kernsize, lopt, aopt, iterations, likelihoodSigma, likelihoodSkip);
+    if (m_infoStream)
+        m_infoStream << " -maxUrange " << urange << " -maxUrange " << range << " -sigma     " << sigma << " -kernelSize " << kernsize
+                     << " -lstep " << lopt << " -lobsGain " << m_obsSigmaGain << " -astep " << aopt << endl;
+}
+
+void GridSlamProcessor::setMotionModelParameters(double srr, double srt, double str, double stt) {
+    m_motionModel.srr = srr; m_motionModel.srt = srt; m_motionModel.str = str; m_motionModel.stt = stt;
+    if (m_infoStream) m_infoStream << " -srr " << srr << " -srt " << srt << " -str " << str << " -stt " << stt << endl;
+}
+
+void GridSlamProcessor::setUpdateDistances(double linear, double angular, double resampleThreshold) {
+    m_linearThresholdDistance = linear;
+    m_angularThresholdDistance = angular;
+    m_resampleThreshold = resampleThreshold;
+    if (m_infoStream) m_infoStream << " -linearUpdate " << linear << " -angularUpdate " << angular << " -resampleThreshold " << m_resampleThreshold << endl;
+}
+
+// `size` particles at initialPose, all on empty maps covering [xmin,xmax] x [ymin,ymax] at resolution delta.
+// The maps are created on the device; the host Particle::map objects start as empty mirrors.
+void GridSlamProcessor::init(unsigned int size, double xmin, double ymin, double xmax, double ymax, double delta, OrientedPoint initialPose) {
+    m_xmin = xmin; m_ymin = ymin; m_xmax = xmax; m_ymax = ymax; m_delta = delta;
+    if (m_infoStream)
+        m_infoStream << " -xmin " << m_xmin << " -xmax " << m_xmax << " -ymin " << m_ymin << " -ymax " << m_ymax << " -delta " << m_delta
+                     << " -particles " << size << endl;
+    releaseLeaves(m_particles);
+    m_particles.clear();
+
+    unsigned long long pool = (unsigned long long)size * 512;  // patches; GM_B200_POOL_PATCHES overrides
+    if (pool < 65536) pool = 65536;
+    m_device.reset(new b200::DeviceContext(size, pool));
+    m_device->configure(m_matcher);
+    const double center[2] = {(xmin + xmax) * .5, (ymin + ymax) * .5};
+    m_device->check(gm_init_particles(m_device->h, size, center, xmax - xmin, ymax - ymin, delta), "gm_init_particles");
+    m_device->particles = size;
+
+    TNode* root = new TNode(initialPose, 0, 0, 0);
+    ScanMatcherMap mirror(Point(center[0], center[1]), 0., 0., delta);  // geometry + cells arrive with the first pull
+    m_particles.reserve(size);
+    for (unsigned int i = 0; i < size; i++) {
+        m_particles.push_back(Particle(mirror));
+        Particle& p = m_particles.back();
+        p.pose = initialPose;
+        p.previousPose = initialPose;
+        p.setWeight(0);
+        p.previousIndex = 0;
+        p.node = root;  // all particles share the root; it is not counted as their child (reference: gridslamprocessor.cpp:381-396)
+        std::shared_ptr<b200::DeviceMapResidency> r(new b200::DeviceMapResidency);
+        r->ctx = m_device;
+        r->slot = i;
+        r->stale = true;
+        p.map.setResidency(r);
+    }
+    m_neff = (double)size;
+    m_count = 0;
+    m_readingCount = 0;
+    m_linearDistance = m_angularDistance = 0;
+}
+
+void GridSlamProcessor::processTruePos(const OdometryReading& o) {
+    const OdometrySensor* os = dynamic_cast<const OdometrySensor*>(o.getSensor());
+    if (os && os->isIdeal() && m_outputStream) {
+        m_outputStream << std::setiosflags(std::ios::fixed) << std::setprecision(3);
+        m_outputStream << "SIMULATOR_POS " << o.getPose().x << " " << o.getPose().y << " ";
+        m_outputStream << std::setiosflags(std::ios::fixed) << std::setprecision(6) << o.getPose().theta << " " << o.getTime() << endl;
+    }
+}
+
+void GridSlamProcessor::markMapsStale() {
+    for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it)
+        if (it->map.residency()) it->map.residency()->stale = true;
+}
+
+// ------------------------------------------------------------------------------------------ the GPU stages
+// scanMatch (reference: gridslamprocessor.hxx:15-75): optimize + accept/reject + likelihoodAndScore for all particles
+void GridSlamProcessor::scanMatch(const double* plainReading) {
+    const size_t n = m_particles.size();
+    m_poseBuf.resize(3 * n); m_scoreBuf.resize(n); m_likBuf.resize(n);
+    for (size_t i = 0; i < n; i++) {
+        m_poseBuf[3 * i] = m_particles[i].pose.x; m_poseBuf[3 * i + 1] = m_particles[i].pose.y; m_poseBuf[3 * i + 2] = m_particles[i].pose.theta;
+    }
+    m_device->configure(m_matcher);
+    m_device->check(gm_scanmatch(m_device->h, plainReading, m_poseBuf.data(), m_minimumScore, m_scoreBuf.data(), 0, m_likBuf.data(), 0, 0),
+                    "gm_scanmatch");
+    double sumScore = 0;
+    for (size_t i = 0; i < n; i++) {
+        Particle& p = m_particles[i];
+        sumScore += m_scoreBuf[i];
+        if (!(m_scoreBuf[i] > m_minimumScore) && m_infoStream) {
+            m_infoStream << "Scan Matching Failed, using odometry. Likelihood=" << m_likBuf[i] << endl;
+            m_infoStream << "lp:" << m_lastPartPose.x << " " << m_lastPartPose.y << " " << m_lastPartPose.theta << endl;
+            m_infoStream << "op:" << m_odoPose.x << " " << m_odoPose.y << " " << m_odoPose.theta << endl;
+        }
+        p.pose = OrientedPoint(m_poseBuf[3 * i], m_poseBuf[3 * i + 1], m_poseBuf[3 * i + 2]);
+        p.weight += m_likBuf[i];
+        p.weightSum += m_likBuf[i];
+    }
+    if (m_infoStream) m_infoStream << "Average Scan Matching Score=" << sumScore / n << endl;
+}
+
+// normalize (reference: gridslamprocessor.hxx:82-121): weights = softmax(gain * log-weights), Neff = 1 / sum w^2
+void GridSlamProcessor::normalize() {
+    const size_t n = m_particles.size();
+    std::vector<double> logw(n);
+    for (size_t i = 0; i < n; i++) logw[i] = m_particles[i].weight;
+    m_weights.resize(n);
+    m_device->check(gm_normalize_neff(m_device->h, logw.data(), (uint32_t)n, m_obsSigmaGain, m_weights.data(), &m_neff), "gm_normalize_neff");
+}
+
+// particle copy by patch reference (when `parents` is given) + computeActiveArea + registerScan for every particle
+void GridSlamProcessor::registerAll(const double* plainReading, const unsigned int* parents) {
+    const size_t n = m_particles.size();
+    m_poseBuf.resize(3 * n);
+    for (size_t i = 0; i < n; i++) {
+        m_poseBuf[3 * i] = m_particles[i].pose.x; m_poseBuf[3 * i + 1] = m_particles[i].pose.y; m_poseBuf[3 * i + 2] = m_particles[i].pose.theta;
+    }
+    m_device->configure(m_matcher);
+    m_device->check(gm_register(m_device->h, plainReading, m_poseBuf.data(), parents), "gm_register");
+    markMapsStale();
+}
+
+// resample (reference: gridslamprocessor.hxx:131-302)
+bool GridSlamProcessor::resample(const double* plainReading, int adaptSize, const RangeReading* reading) {
+    const size_t n = m_particles.size();
+    if (!(m_neff < m_resampleThreshold * n)) {
+        // no resampling: every particle grows its own trajectory by one node and registers the scan
+        for (size_t i = 0; i < n; i++) {
+            Particle& p = m_particles[i];
+            TNode* node = new TNode(p.pose, 0.0, p.node, 0);
+            node->reading = reading;
+            p.node = node;
+            p.previousIndex = (int)i;
+        }
+        registerAll(plainReading, 0);
+        return false;
+    }
+    if (m_infoStream) m_infoStream << "*************RESAMPLE***************" << endl;
+    if (adaptSize > 0 && (size_t)adaptSize != n)
+        b200::fatal("processScan(reading, adaptParticles): changing the particle count while resampling is not supported by the device layout");
+    // systematic resampling; the single uniform draw is taken here, on the host stream (particlefilter.h:199)
+    const double u01 = drand48();
+    m_indexes.resize(n);
+    uint32_t emitted = 0;
+    static_assert(sizeof(unsigned int) == sizeof(uint32_t), "index type");
+    m_device->check(gm_resample_indexes(m_device->h, m_weights.data(), (uint32_t)n, u01, m_indexes.data(), &emitted), "gm_resample_indexes");
+    if (m_outputStream.is_open()) {
+        m_outputStream << "RESAMPLE " << m_indexes.size() << " ";
+        for (size_t i = 0; i < m_indexes.size(); i++) m_outputStream << m_indexes[i] << " ";
+        m_outputStream << endl;
+    }
+    onResampleUpdate();
+
+    // new generation: slot j continues parent m_indexes[j].  The maps stay where they are (slot j's host mirror is
+    // bound to device slot j); gm_register re-points slot j's patch directory at its parent's patches.
+    struct Carry { OrientedPoint pose, previousPose; double weightSum, gweight; TNode* node; };
+    std::vector<Carry> next(n);
+    std::vector<char> kept(n, 0);
+    for (size_t j = 0; j < n; j++) {
+        const Particle& src = m_particles[m_indexes[j]];
+        kept[m_indexes[j]] = 1;
+        TNode* node = new TNode(src.pose, 0, src.node, 0);
+        node->reading = reading;
+        next[j].pose = src.pose; next[j].previousPose = src.previousPose;
+        next[j].weightSum = src.weightSum; next[j].gweight = src.gweight; next[j].node = node;
+    }
+    for (size_t i = 0; i < n; i++)
+        if (!kept[i]) { delete m_particles[i].node; m_particles[i].node = 0; }  // leaves of trajectories that died out
+    for (size_t j = 0; j < n; j++) {
+        Particle& p = m_particles[j];
+        p.pose = next[j].pose; p.previousPose = next[j].previousPose;
+        p.weightSum = next[j].weightSum; p.gweight = next[j].gweight; p.node = next[j].node;
+        p.previousIndex = (int)m_indexes[j];
+        p.setWeight(0);
+    }
+    registerAll(plainReading, m_indexes.data());
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------ tree weights
+void GridSlamProcessor::updateTreeWeights(bool weightsAlreadyNormalized) {
+    if (!weightsAlreadyNormalized) normalize();
+    resetTree();
+    propagateWeights();
+}
+
+// zero accWeight / visitCounter on every node reachable from a particle (reference: gridslamprocessor_tree.cpp:255-268);
+// the epoch stamp stops each walk at the first ancestor another particle already reset in this pass
+void GridSlamProcessor::resetTree() {
+    m_treeEpoch++;
+    for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it)
+        for (TNode* n = it->node; n && n->epoch != m_treeEpoch; n = n->parent) {
+            n->accWeight = 0;
+            n->visitCounter = 0;
+            n->epoch = m_treeEpoch;
+        }
+}
+
+// push a leaf's weight towards the root: a node forwards its sum once all of its children have reported
+static double pushUp(GridSlamProcessor::TNode* n, double weight) {
+    while (n) {
+        n->visitCounter++;
+        n->accWeight += weight;
+        assert(n->visitCounter <= n->childs);
+        if (n->visitCounter != n->childs) return 0;
+        weight = n->accWeight;
+        n = n->parent;
+    }
+    return weight;
+}
+
+double GridSlamProcessor::propagateWeights() {
+    double rootWeight = 0, leafSum = 0;
+    for (size_t i = 0; i < m_particles.size(); i++) {
+        const double w = m_weights[i];
+        leafSum += w;
+        TNode* n = m_particles[i].node;
+        n->accWeight = w;
+        rootWeight += pushUp(n->parent, n->accWeight);
+    }
+    if (fabs(leafSum - 1.0) > 0.0001 || fabs(rootWeight - 1.0) > 0.0001) {
+        std::cerr << "ERROR: root->accWeight=" << rootWeight << "    sum_leaf_weights=" << leafSum << endl;
+        assert(0);
+    }
+    return rootWeight;
+}
+
+// ------------------------------------------------------------------------------------------ processScan
+bool GridSlamProcessor::processScan(const RangeReading& reading, int adaptParticles) {
+    const OrientedPoint relPose = reading.getPose();
+    if (!m_count) m_lastPartPose = m_odoPose = relPose;
+
+    // motion model: every reading, every particle, in order -- this is where the drand48 stream advances
+    for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it)
+        it->pose = m_motionModel.drawFromMotion(it->pose, relPose, m_odoPose);
+
+    if (m_outputStream.is_open()) {
+        m_outputStream << std::setiosflags(std::ios::fixed) << std::setprecision(6);
+        m_outputStream << "ODOM ";
+        m_outputStream << std::setiosflags(std::ios::fixed) << std::setprecision(3) << m_odoPose.x << " " << m_odoPose.y << " ";
+        m_outputStream << std::setiosflags(std::ios::fixed) << std::setprecision(6) << m_odoPose.theta << " ";
+        m_outputStream << reading.getTime() << endl;
+        m_outputStream << std::setiosflags(std::ios::fixed) << std::setprecision(6);
+        m_outputStream << "ODO_UPDATE " << m_particles.size() << " ";
+        for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it) {
+            m_outputStream << std::setiosflags(std::ios::fixed) << std::setprecision(3) << it->pose.x << " " << it->pose.y << " ";
+            m_outputStream << std::setiosflags(std::ios::fixed) << std::setprecision(6) << it->pose.theta << " " << it->weight << " ";
+        }
+        m_outputStream << reading.getTime() << endl;
+    }
+    onOdometryUpdate();
+
+    OrientedPoint move = relPose - m_odoPose;
+    move.theta = atan2(sin(move.theta), cos(move.theta));
+    m_linearDistance += sqrt(move * move);
+    m_angularDistance += fabs(move.theta);
+    if (m_linearDistance > kOdometryJumpWarning)
+        std::cerr << "gmapping-b200: odometry jumped " << m_linearDistance << " m between two readings (from " << m_odoPose.x << " " << m_odoPose.y
+                  << " to " << relPose.x << " " << relPose.y << "); continuing, the map may not fit" << endl;
+    m_odoPose = relPose;
+
+    bool processed = false;
+    if (!m_count || m_linearDistance >= m_linearThresholdDistance || m_angularDistance >= m_angularThresholdDistance ||
+        (period_ >= 0.0 && (reading.getTime() - last_update_time_) > period_)) {
+        last_update_time_ = reading.getTime();
+        if (m_outputStream.is_open()) {
+            m_outputStream << std::setiosflags(std::ios::fixed) << std::setprecision(6);
+            m_outputStream << "FRAME " << m_readingCount << " " << m_linearDistance << " " << m_angularDistance << endl;
+        }
+        if (m_infoStream) m_infoStream << "update frame " << m_readingCount << endl << "update ld=" << m_linearDistance << " ad=" << m_angularDistance << endl;
+        assert(reading.size() == m_beams);
+        const std::vector<double> plain(reading.begin(), reading.end());
+        // the trajectory nodes keep their own copy of the scan (the caller may free `reading`)
+        RangeReading* readingCopy = new RangeReading(reading.size(), &(reading[0]), static_cast<const RangeSensor*>(reading.getSensor()), reading.getTime());
+
+        if (m_count > 0) {
+            scanMatch(plain.data());
+            if (m_outputStream.is_open()) {
+                m_outputStream << "LASER_READING " << reading.size() << " ";
+                m_outputStream << std::setiosflags(std::ios::fixed) << std::setprecision(2);
+                for (RangeReading::const_iterator b = reading.begin(); b != reading.end(); ++b) m_outputStream << *b << " ";
+                const OrientedPoint p = reading.getPose();
+                m_outputStream << std::setiosflags(std::ios::fixed) << std::setprecision(6);
+                m_outputStream << p.x << " " << p.y << " " << p.theta << " " << reading.getTime() << endl;
+                m_outputStream << "SM_UPDATE " << m_particles.size() << " ";
+                for (ParticleVector::const_iterator it = m_particles.begin(); it != m_particles.end(); ++it) {
+                    m_outputStream << std::setiosflags(std::ios::fixed) << std::setprecision(3) << it->pose.x << " " << it->pose.y << " ";
+                    m_outputStream << std::setiosflags(std::ios::fixed) << std::setprecision(6) << it->pose.theta << " " << it->weight << " ";
+                }
+                m_outputStream << endl;
+            }
+            onScanmatchUpdate();
+            updateTreeWeights(false);
+            if (m_infoStream) m_infoStream << "neff= " << m_neff << endl;
+            if (m_outputStream.is_open()) {
+                m_outputStream << std::setiosflags(std::ios::fixed) << std::setprecision(6);
+                m_outputStream << "NEFF " << m_neff << endl;
+            }
+            resample(plain.data(), adaptParticles, readingCopy);
+        } else {
+            if (m_infoStream) m_infoStream << "Registering First Scan" << endl;
+            for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it) {
+                TNode* node = new TNode(it->pose, 0., it->node, 0);
+                node->reading = readingCopy;
+                it->node = node;
+            }
+            registerAll(plain.data(), 0);
+        }
+        updateTreeWeights(false);
+        m_lastPartPose = m_odoPose;
+        m_linearDistance = 0;
+        m_angularDistance = 0;
+        m_count++;
+        processed = true;
+        for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it) it->previousPose = it->pose;
+    }
+    if (m_outputStream.is_open()) m_outputStream << std::flush;
+    m_readingCount++;
+    return processed;
+}
+
+std::ofstream& GridSlamProcessor::outputStream() { return m_outputStream; }
+std::ostream& GridSlamProcessor::infoStream() { return m_infoStream; }
+
+// argmax of weightSum, first wins (reference: gridslamprocessor.cpp:677-688)
+int GridSlamProcessor::getBestParticleIndex() const {
+    unsigned int best = 0;
+    double bw = -std::numeric_limits<double>::max();
+    for (unsigned int i = 0; i < m_particles.size(); i++)
+        if (bw < m_particles[i].weightSum) { bw = m_particles[i].weightSum; best = i; }
+    return (int)best;
+}
+
+void GridSlamProcessor::onScanmatchUpdate() {}
+void GridSlamProcessor::onResampleUpdate() {}
+void GridSlamProcessor::onOdometryUpdate() {}
+
+// ------------------------------------------------------------------------------------------ trajectories
+// deep copy of the trajectory tree: one new leaf per particle, shared ancestors copied once
+// (reference: gridslamprocessor_tree.cpp:57-147)
+GridSlamProcessor::TNodeVector GridSlamProcessor::getTrajectories() const {
+    std::map<const TNode*, TNode*> copyOf;
+    TNodeVector leaves;
+    leaves.reserve(m_particles.size());
+    for (ParticleVector::const_iterator it = m_particles.begin(); it != m_particles.end(); ++it) {
+        // collect the not-yet-copied part of this particle's chain, then build it top-down
+        std::vector<const TNode*> chain;
+        const TNode* n = it->node;
+        while (n && !copyOf.count(n)) { chain.push_back(n); n = n->parent; }
+        TNode* parentCopy = n ? copyOf[n] : 0;
+        for (size_t k = chain.size(); k-- > 0;) {
+            const TNode* src = chain[k];
+            TNode* c = new TNode(src->pose, src->weight, parentCopy, 0);
+            c->reading = src->reading;
+            c->accWeight = src->accWeight;
+            c->gweight = src->gweight;
+            copyOf[src] = c;
+            parentCopy = c;
+        }
+        leaves.push_back(copyOf[it->node]);
+    }
+    return leaves;
+}
+
+// replay a stored trajectory (root first) into every particle map (reference: gridslamprocessor_tree.cpp:149-224)
+void GridSlamProcessor::integrateScanSequence(TNode* node) {
+    std::vector<TNode*> order;
+    for (TNode* n = node; n; n = n->parent) order.push_back(n);
+    for (size_t k = order.size(); k-- > 0;) {
+        TNode* n = order[k];
+        if (!n->reading) continue;
+        assert(n->reading->size() == m_beams);
+        for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it) it->pose = n->pose;
+        const std::vector<double> plain(n->reading->begin(), n->reading->end());
+        registerAll(plain.data(), 0);
+        m_count++;
+    }
+    updateTreeWeights(false);
+}
+
+// ------------------------------------------------------------------------------------------ B200 additions
+GridSlamProcessor::DeviceStats GridSlamProcessor::deviceStats() const {
+    DeviceStats d = DeviceStats();
+    if (!m_device) return d;
+    gm_stats s;
+    m_device->check(gm_get_stats(m_device->h, &s), "gm_get_stats");
+    d.msScanMatch = s.ms_scanmatch; d.msWeights = s.ms_weights; d.msRemap = s.ms_remap; d.msRegister = s.ms_register;
+    d.beamEvals = s.beam_evals; d.scoreEvals = s.score_evals; d.cowCopies = s.cow_copies; d.patchAllocs = s.patch_allocs;
+    d.freeUpdates = s.free_updates; d.hitUpdates = s.hit_updates; d.poolInUse = s.pool_in_use; d.launches = s.launches;
+    return d;
+}
+
+std::vector<unsigned long long> GridSlamProcessor::mapDigests() const {
+    const size_t n = m_particles.size();
+    std::vector<gm_digest> d(n);
+    if (n) m_device->check(gm_map_digest(m_device->h, 0, (uint32_t)n, d.data()), "gm_map_digest");
+    std::vector<unsigned long long> out(6 * n);
+    for (size_t i = 0; i < n; i++) {
+        out[6 * i] = d[i].patches; out[6 * i + 1] = d[i].cells; out[6 * i + 2] = d[i].sum_n; out[6 * i + 3] = d[i].sum_visits;
+        out[6 * i + 4] = d[i].hash_counts; out[6 * i + 5] = d[i].hash_acc;
+    }
+    return out;
+}
+
+}  // namespace GMapping
