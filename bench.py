@@ -8,8 +8,9 @@ normalisation / Neff, resampling when Neff drops, and the grid update (registerS
 a seeded synthetic 1081-beam log (18 x 12 m room, 0.05 m grid, 200 x 200 m map).  Prints ONE JSON line.
 
   value      scans/s from device time only (CUDA events around the kernels of each stage, maps resident in HBM)
-  e2e        scans/s through the C ABI with HOST buffers (ranges + poses in, poses + likelihoods out, every
-             step), wall clock bracketed by synchronisation
+  e2e        scans/s through the reference-facing API, GMapping::GridSlamProcessor::processScan of the C++ host layer,
+             with HOST buffers (ranges + odometry in; poses, weights, Neff out every step), wall clock bracketed by
+             barrier + synchronisation, max over ranks
   roofline   the scan-match kernel: beam-evaluations x 144 B (3x3 window of 16-byte cells)
              over its CUDA-event time, against the measured HBM copy bandwidth
   cpu_baseline   the unmodified reference (oracle/_ref/ref_driver) on one host core, bounded sample,
@@ -91,72 +92,6 @@ def make_log(scans, seed=1):
     return synth, synth.make_log("room", synth.UTM30, scans=scans, step=0.25, seed=seed)
 
 
-class HostFilter:
-    """The host side of processScan over the C ABI (reference: gridslamprocessor.cpp:425-662): motion-model
-    sampling, weights bookkeeping and the resample decision stay on the host; the four heavy stages are gm_* calls."""
-
-    def __init__(self, gm, particles, angles, init_pose, device=0, seed=12345):
-        self.n = particles
-        # pool: ~160 patches per particle covers the 18 x 12 m room with private copies of the active area
-        self.ctx = gm.GmContext(particles, device=device, pool_patches=max(8192, particles * 256))
-        self.ctx.set_laser(angles)
-        self.ctx.set_matching(urange=PARAMS["maxUrange"], range_=PARAMS["maxrange"], sigma=PARAMS["sigma"], kernel=PARAMS["kernelSize"],
-                              lopt=PARAMS["lstep"], aopt=PARAMS["astep"], iterations=PARAMS["iterations"], lsigma=PARAMS["lsigma"],
-                              lskip=PARAMS["lskip"], generate_map=True)
-        self.ctx.init_particles(particles, bounds=(PARAMS["xmin"], PARAMS["ymin"], PARAMS["xmax"], PARAMS["ymax"]), delta=PARAMS["delta"])
-        self.pose = np.repeat(np.asarray(init_pose, dtype=np.float64)[None, :], particles, axis=0)
-        self.weight = np.zeros(particles); self.weight_sum = np.zeros(particles)
-        self.rng = np.random.default_rng(seed)
-        self.odo = None
-        self.count = 0
-        self.resamples = 0
-
-    def draw_from_motion(self, pnew, pold):
-        """MotionModel::drawFromMotion (motionmodel.cpp:40-60), vectorised over particles."""
-        srr, srt, str_, stt = PARAMS["srr"], PARAMS["srt"], PARAMS["str"], PARAMS["stt"]
-        d = pnew - pold
-        dth = np.arctan2(np.sin(d[2]), np.cos(d[2]))
-        s, c = np.sin(pold[2]), np.cos(pold[2])
-        dx, dy = c * d[0] + s * d[1], -s * d[0] + c * d[1]
-        sxy = 0.3 * srr
-        n = self.n
-        nx = dx + self.rng.normal(0, 1, n) * (srr * abs(dx) + str_ * abs(dth) + sxy * abs(dy))
-        ny = dy + self.rng.normal(0, 1, n) * (srr * abs(dy) + str_ * abs(dth) + sxy * abs(dx))
-        nth = dth + self.rng.normal(0, 1, n) * (stt * abs(dth) + srt * np.hypot(dx, dy))
-        nth = np.fmod(nth, 2 * np.pi); nth = np.where(nth > np.pi, nth - 2 * np.pi, nth)
-        s1, c1 = np.sin(self.pose[:, 2]), np.cos(self.pose[:, 2])
-        self.pose = np.stack([c1 * nx - s1 * ny + self.pose[:, 0], s1 * nx + c1 * ny + self.pose[:, 1], nth + self.pose[:, 2]], axis=1)
-
-    def process_scan(self, ranges, odom):
-        """-> dict of device stage times (ms) for this scan; every scan of the bench log passes the update gate."""
-        ctx = self.ctx
-        if self.odo is None:
-            self.odo = odom.copy()
-        self.draw_from_motion(odom, self.odo)
-        self.odo = odom.copy()
-        t = dict(scanmatch=0.0, weights=0.0, remap=0.0, register=0.0, beam_evals=0, score_evals=0)
-        if self.count == 0:
-            ctx.register(ranges, self.pose)
-        else:
-            self.pose, score, s, l, c, ev = ctx.scanmatch(ranges, self.pose, 0.0)
-            self.weight += l; self.weight_sum += l
-            w, neff = ctx.normalize(self.weight, PARAMS["ogain"])
-            st = ctx.stats()
-            t["scanmatch"] = st["ms_scanmatch"]; t["weights"] = st["ms_weights"]
-            t["beam_evals"] = st["beam_evals"]; t["score_evals"] = st["score_evals"]
-            if neff < PARAMS["resampleThreshold"] * self.n:
-                idx, _ = ctx.resample_indexes(w, float(self.rng.random()))
-                self.pose = self.pose[idx]; self.weight_sum = self.weight_sum[idx]; self.weight = np.zeros(self.n)
-                ctx.register(ranges, self.pose, idx)
-                self.resamples += 1
-            else:
-                ctx.register(ranges, self.pose)
-        st = ctx.stats()
-        t["register"] = st["ms_register"]; t["remap"] = st["ms_remap"]
-        self.count += 1
-        return t
-
-
 def run_cpu_reference(particles, scans, procs, log_path):
     """oracle/_ref/ref_driver -mode time, `procs` independent single-threaded processes.  Returns
     (particle-scans per second summed over processes, per-process ms per matched scan)."""
@@ -228,59 +163,103 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        raise SystemExit("multi-GPU sharding is not wired into bench.py yet")
     torch.cuda.set_device(local)
-    gm = importlib.import_module("slam-gmapping-learn_b200")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hostapi = importlib.import_module("slam-gmapping-learn_b200.hostapi")
     K, W = args.steps, args.warmup
     synth, log = make_log(1 + W + K)
-    f = HostFilter(gm, args.particles, log.laser.angles(), log.odom[0], device=local)
-    f.process_scan(log.ranges[0], log.odom[0])  # first scan: registration only
-    for i in range(1, 1 + W):
-        f.process_scan(log.ranges[i], log.odom[i])
-    launches0 = f.ctx.stats()["launches"]
-    torch.cuda.synchronize()
+    n, B = args.particles, log.laser.beams
+    if n % world:
+        raise SystemExit("--particles must be a multiple of the number of GPUs")
+    nccl_id = None
+    if world > 1:  # rank 0 draws the NCCL id of the filter's own communicator, torch.distributed carries it to the others
+        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            t = torch.tensor(list(hostapi.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        nccl_id = bytes(t.cpu().tolist())
+    # every scan of the log passes the update gate (0.25 m per step >= linearUpdate)
+    proc = hostapi.Processor(log.laser.angles(), n, log.odom[0], bounds=(PARAMS["xmin"], PARAMS["ymin"], PARAMS["xmax"], PARAMS["ymax"]),
+                             delta=PARAMS["delta"], seed=12345, rank=rank, world=world, nccl_id=nccl_id,
+                             maxUrange=PARAMS["maxUrange"], maxrange=PARAMS["maxrange"], sigma=PARAMS["sigma"], kernelSize=PARAMS["kernelSize"],
+                             lstep=PARAMS["lstep"], astep=PARAMS["astep"], iterations=PARAMS["iterations"], lsigma=PARAMS["lsigma"],
+                             ogain=PARAMS["ogain"], lskip=PARAMS["lskip"], srr=PARAMS["srr"], srt=PARAMS["srt"], str=PARAMS["str"], stt=PARAMS["stt"],
+                             linearUpdate=0.2, angularUpdate=0.1, resampleThreshold=PARAMS["resampleThreshold"])
+    for i in range(0, 1 + W):  # first scan registers only; then W warm-up steps
+        assert proc.process_scan(log.ranges[i], log.odom[i], log.stamps[i])
+    launches0 = proc.stats()["launches"]; resamples0 = proc.resamples()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
     stage = []
+    barrier()
     with ClockSampler(local) as clk:
         t0 = time.perf_counter()
         for i in range(1 + W, 1 + W + K):
-            stage.append(f.process_scan(log.ranges[i], log.odom[i]))
-        torch.cuda.synchronize()
+            proc.process_scan(log.ranges[i], log.odom[i], log.stamps[i])  # host buffers in, poses / weights out, synchronous
+            stage.append(proc.stats())
+        barrier()
         t1 = time.perf_counter()
-    launches = f.ctx.stats()["launches"] - launches0
-    wall_ms = (t1 - t0) * 1000.0 / K
-    dev_ms = float(np.mean([s["scanmatch"] + s["weights"] + s["remap"] + s["register"] for s in stage]))
-    sm_ms = float(np.mean([s["scanmatch"] for s in stage]))
-    beam_evals = float(np.mean([s["beam_evals"] for s in stage]))
-    peak, peak_src = measured_peak()
-    achieved = beam_evals * BYTES_PER_BEAM_EVAL / (sm_ms * 1e-3) / 1e9
-    n, B = args.particles, log.laser.beams
-    h2d = 2 * (B * 8 + n * 24) + n * 8  # ranges+poses for scanmatch and register, weights for normalize
-    d2h = n * (24 + 8 * 3 + 4 * 2) + n * 8 + 8
-    line = {"metric": METRIC, "value": 1000.0 / dev_ms, "unit": "scans/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": dev_ms,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%d particles x %d beams (270 deg, 0.25 deg), 0.05 m grid, 200x200 m map, synthetic 18x12 m room log" % (n, B),
-                       "particles": n, "beams": B, "l2": "inputs larger than L2 (per-scan working set ~%.1f GB of map patches)" % (n * 70 * 16384 / 1e9),
-                       "resamples_in_timed_region": f.resamples, "params": "gfs-carmen defaults, maxUrange 29 / maxrange 30"},
-            "beam_evals_per_s": beam_evals / (dev_ms * 1e-3), "beam_evals_per_scan": beam_evals,
-            "score_evals_per_particle": float(np.mean([s["score_evals"] for s in stage])) / n,
-            "stage_ms": {k: float(np.mean([s[k] for s in stage])) for k in ("scanmatch", "weights", "remap", "register")},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "k_scanmatch", "peak_source": peak_src, "bytes_per_beam_eval": BYTES_PER_BEAM_EVAL},
-            "e2e": {"value": 1000.0 / wall_ms, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": wall_ms},
-            "gpu_launches": launches, "clocks": clk.summary()}
-    if not args.no_cpu_baseline:
-        with tempfile.TemporaryDirectory() as td:
-            ns = min(1 + W + K, 40)
-            lp = os.path.join(td, "bench.log"); synth.write_carmen(synth.make_log("room", synth.UTM30, scans=ns, step=0.25, seed=1), lp)
-            r = run_cpu_reference(16, ns, 1, lp)
-        if r is not None:
-            rate, ms, wall = r
-            line["cpu_baseline"] = {"value": rate / n, "unit": "scans/s", "cores": 1, "kind": "reference",
-                                    "sample": "unmodified reference, 16 particles x %d matched scans of the same log on 1 core "
-                                              "(%.0f ms per scan, %.1f s wall), scaled linearly to %d particles" % (ns - 1, ms, wall, n)}
-    print(json.dumps(line))
-    f.ctx.close()
+    keys = ("ms_scanmatch", "ms_weights", "ms_remap", "ms_register", "ms_migrate", "ms_allgather")
+    dev_ms_local = float(np.sum([sum(s[k] for k in keys) for s in stage])) / K
+    wall_ms_local = (t1 - t0) * 1000.0 / K
+    sm_ms = float(np.mean([s["ms_scanmatch"] for s in stage]))
+    beam_local = float(np.mean([s["beam_evals"] for s in stage]))
+    launches_local = proc.stats()["launches"] - launches0
+    if dist is not None:
+        mx = torch.tensor([dev_ms_local, wall_ms_local, sm_ms], dtype=torch.float64, device="cuda"); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = torch.tensor([beam_local, launches_local, float(np.mean([s["score_evals"] for s in stage])),
+                           float(np.sum([s["migrated_particles"] for s in stage])), float(np.sum([s["migrated_bytes"] for s in stage]))],
+                          dtype=torch.float64, device="cuda"); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms, wall_ms, sm_ms_max = mx.tolist(); beam_evals, launches, score_evals, migrated, migrated_bytes = sm.tolist()
+    else:
+        dev_ms, wall_ms, sm_ms_max = dev_ms_local, wall_ms_local, sm_ms
+        beam_evals, launches, score_evals = beam_local, launches_local, float(np.mean([s["score_evals"] for s in stage]))
+        migrated, migrated_bytes = 0.0, 0.0
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = beam_local * BYTES_PER_BEAM_EVAL / (sm_ms * 1e-3) / 1e9  # rank 0's kernel on rank 0's GPU
+        nl = n // world
+        h2d = world * (2 * (B * 8 + nl * 24) + n * 8)
+        d2h = world * (nl * (24 + 8 + 8) + n * 8 + 8 + 2 * 96) + (world > 1) * world * n * 40
+        line = {"metric": METRIC, "value": 1000.0 / dev_ms, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "%d particles x %d beams (270 deg, 0.25 deg), 0.05 m grid, 200x200 m map, synthetic 18x12 m room log" % (n, B),
+                           "particles": n, "beams": B, "particles_per_gpu": nl,
+                           "l2": "inputs larger than L2 (per-scan working set ~%.1f GB of map patches per GPU)" % (nl * 70 * 16384 / 1e9),
+                           "resamples_in_timed_region": proc.resamples() - resamples0, "params": "gfs-carmen defaults, maxUrange 29 / maxrange 30",
+                           "api": "GMapping::GridSlamProcessor::processScan (C++ host layer over the C ABI)"},
+                "beam_evals_per_s": beam_evals / (dev_ms * 1e-3), "beam_evals_per_scan": beam_evals, "score_evals_per_particle": score_evals / n,
+                "stage_ms": {k[3:]: float(np.mean([s[k] for s in stage])) for k in keys},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "kernel": "k_scanmatch", "peak_source": peak_src, "bytes_per_beam_eval": BYTES_PER_BEAM_EVAL,
+                             "note": "algorithmic bytes; the window reads are served from L1/L2 (see profiles/), DRAM traffic is ~60x smaller"},
+                "e2e": {"value": 1000.0 / wall_ms, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": wall_ms},
+                "gpu_launches": int(launches), "clocks": clk.summary()}
+        if world > 1:
+            line["migration"] = {"particles": migrated, "bytes": migrated_bytes}
+        if not args.no_cpu_baseline and world == 1:
+            with tempfile.TemporaryDirectory() as td:
+                ns = min(1 + W + K, 40)
+                lp = os.path.join(td, "bench.log"); synth.write_carmen(synth.make_log("room", synth.UTM30, scans=ns, step=0.25, seed=1), lp)
+                r = run_cpu_reference(16, ns, 1, lp)
+            if r is not None:
+                rate, ms, wall = r
+                line["cpu_baseline"] = {"value": rate / n, "unit": "scans/s", "cores": 1, "kind": "reference",
+                                        "sample": "unmodified reference, 16 particles x %d matched scans of the same log on 1 core "
+                                                  "(%.0f ms per scan, %.1f s wall), scaled linearly to %d particles" % (ns - 1, ms, wall, n)}
+        print(json.dumps(line))
+    proc.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -41,6 +41,8 @@ typedef struct gm_config {
     uint64_t pool_patches;  /* patch-pool capacity (16 KiB each); 0 = size from free HBM */
     uint32_t block_threads; /* threads per particle CTA, 0 = default (256) */
     uint32_t flags;         /* reserved, 0 */
+    uint32_t global_particles; /* multi-GPU: particles over all ranks (sizes the weight buffers); 0 = max_particles */
+    uint32_t reserved;
 } gm_config;
 
 /* replaces: the ScanMatcher parameter block, include/gmapping/scanmatcher/scanmatcher.h:61-82,
@@ -82,6 +84,8 @@ typedef struct gm_stats {
     uint64_t free_updates, hit_updates; /* last gm_register: visits++ along rays / endpoint updates */
     uint64_t resizes;         /* particles whose map was resized in the last gm_register */
     float ms_scanmatch, ms_register, ms_remap, ms_weights; /* CUDA-event device time of the last calls */
+    float ms_migrate, ms_allgather;  /* multi-GPU: last gm_dist_register's patch migration / last gm_dist_allgather */
+    uint64_t migrated_particles, migrated_bytes; /* last gm_dist_register: imported parents, bytes received */
     uint32_t launches;        /* kernels launched by this context since gm_create */
     uint32_t reserved;
 } gm_stats;
@@ -149,6 +153,23 @@ int gm_upload_map(gm_ctx* ctx, uint32_t particle, const gm_map_info* info, const
 int gm_map_info_get(gm_ctx* ctx, uint32_t particle, gm_map_info* info);
 int gm_download_map(gm_ctx* ctx, uint32_t particle, gm_map_info* info, int32_t* patch_coords, gm_cell* cells, uint32_t max_patches);
 int gm_map_digest(gm_ctx* ctx, uint32_t first, uint32_t count, gm_digest* out /*count*/);
+
+/* ---- multi-GPU (one process and one gm_ctx per GPU; NCCL over NVLink).  Rank r owns the global particles
+ * [r*n, (r+1)*n), n = gm_particles(ctx); the host state (poses, weights, trajectory tree, drand48 stream) is replicated.
+ * replaces: nothing in the reference (it is single-threaded); see DESIGN.md "multi-GPU". */
+#define GM_DIST_ID_BYTES 128
+int gm_dist_unique_id(void* id_out /* GM_DIST_ID_BYTES */);  /* ncclGetUniqueId, call on one rank and broadcast */
+int gm_dist_init(gm_ctx* ctx, int rank, int world, const void* id /* GM_DIST_ID_BYTES */);
+/* all-gather `count` doubles per rank (host buffers; out has world*count doubles in rank order) */
+int gm_dist_allgather(gm_ctx* ctx, const double* local, uint32_t count, double* all);
+/* gm_register across ranks: idx_global[N] are the resampled parents as GLOBAL particle indexes (identical on every
+ * rank) or NULL.  Parents that live on another rank are migrated here first: their patch directory and patches are
+ * packed on the owner, sent with ncclSend/ncclRecv and installed in spare slots; then the local patch-reference
+ * remap and the registration run as in gm_register.  poses: the n local particles. */
+int gm_dist_register(gm_ctx* ctx, const double* ranges, const double* poses, const uint32_t* idx_global);
+/* planning only (no device work): which global parents this rank must import for idx_global, in import order;
+ * returns the count, fills parents_out (capacity n) -- used by the tests of the host-side logic */
+int gm_dist_plan(uint32_t n_local, int rank, int world, const uint32_t* idx_global, uint32_t* parents_out, uint32_t* local_idx_out);
 
 int gm_get_stats(gm_ctx* ctx, gm_stats* out);
 uint32_t gm_particles(const gm_ctx* ctx);

@@ -37,10 +37,10 @@ def nvcc_path():
 
 
 def build_cuda(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("gm_kernels.cu", "gm_api.cu")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("gm_kernels.h", "gm_device.cuh")] + [os.path.join(ROOT, "include", "gm_b200.h")]
+    srcs = [os.path.join(CSRC, f) for f in ("gm_kernels.cu", "gm_api.cu", "gm_dist.cu")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("gm_kernels.h", "gm_device.cuh", "gm_ctx.h")] + [os.path.join(ROOT, "include", "gm_b200.h")]
     if force or _newer(LIB, deps):
-        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs + ["-ldl"]
         subprocess.check_call(cmd)
     return LIB
 

@@ -24,7 +24,7 @@ class GmError(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("max_particles", C.c_uint32), ("pool_patches", C.c_uint64),
-                ("block_threads", C.c_uint32), ("flags", C.c_uint32)]
+                ("block_threads", C.c_uint32), ("flags", C.c_uint32), ("global_particles", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class MatchParams(C.Structure):
@@ -48,6 +48,7 @@ class Stats(C.Structure):
                 ("beam_evals", C.c_uint64), ("cow_copies", C.c_uint64), ("patch_allocs", C.c_uint64),
                 ("free_updates", C.c_uint64), ("hit_updates", C.c_uint64), ("resizes", C.c_uint64),
                 ("ms_scanmatch", C.c_float), ("ms_register", C.c_float), ("ms_remap", C.c_float), ("ms_weights", C.c_float),
+                ("ms_migrate", C.c_float), ("ms_allgather", C.c_float), ("migrated_particles", C.c_uint64), ("migrated_bytes", C.c_uint64),
                 ("launches", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
@@ -107,10 +108,10 @@ def _f64(a):
 class GmContext:
     """One gm_ctx: a particle set with its maps on one GPU."""
 
-    def __init__(self, max_particles, device=0, pool_patches=0, block_threads=0):
+    def __init__(self, max_particles, device=0, pool_patches=0, block_threads=0, global_particles=0):
         self.L = load_library()
         self.h = C.c_void_p()
-        cfg = Config(device, max_particles, pool_patches, block_threads, 0)
+        cfg = Config(device, max_particles, pool_patches, block_threads, 0, global_particles, 0)
         rc = self.L.gm_create(C.byref(self.h), C.byref(cfg))
         if rc:
             raise GmError(rc, self.L.gm_last_error(None).decode())

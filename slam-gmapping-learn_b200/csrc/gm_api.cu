@@ -4,150 +4,11 @@
 // per-particle map geometry, the beam table and all staging buffers.  Every entry point copies the
 // caller's host buffers in, launches on the context's stream, copies results out and synchronises.
 // There is no CPU path: without a device gm_create fails with GM_ERR_NO_DEVICE.
-#include <cuda_runtime.h>
-
-#include <algorithm>
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
-#include <string>
-#include <vector>
-
-#include "../../include/gm_b200.h"
-#include "gm_kernels.h"
-
-using namespace gm;
-
-static thread_local std::string g_create_error;
-
-struct gm_ctx {
-    int device = 0;
-    cudaStream_t st = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    uint32_t max_particles = 0, n = 0, threads = 256;
-    DevParams P{};
-    bool laser_set = false, match_set = false, inited = false;
-    double angles_h[GM_MAXBEAMS];
-
-    Pool pool{};
-    int* refcnt_new = nullptr;
-    int *dir = nullptr, *dir_alt = nullptr;
-    int dir_cap = 0;
-    Geom *geom = nullptr, *geom_alt = nullptr, *geom_new = nullptr;
-    int4* shift = nullptr;
-
-    double *d_ranges = nullptr, *d_angles = nullptr, *d_poses = nullptr;
-    double *d_score = nullptr, *d_s = nullptr, *d_l = nullptr;
-    unsigned *d_c = nullptr, *d_evals = nullptr, *d_idx = nullptr, *d_emitted = nullptr;
-    double *d_w = nullptr, *d_logw = nullptr, *d_cum = nullptr, *d_tgt = nullptr, *d_neff = nullptr;
-    // query staging (gm_score / gm_likelihood_and_score)
-    unsigned* d_qidx = nullptr; double *d_qposes = nullptr, *d_qposes_out = nullptr, *d_qs = nullptr, *d_ql = nullptr; unsigned* d_qc = nullptr;
-    uint32_t q_cap = 0;
-    Counters* d_counters = nullptr;
-    double* d_inv_n = nullptr;
-    size_t scanmatch_smem = 0;
-    unsigned long long* d_digest = nullptr;
-    int *d_list = nullptr, *d_count = nullptr; int4* d_export = nullptr; size_t export_cap = 0; size_t list_cap = 0;
-
-    gm_stats stats{};
-    std::string err;
-    size_t register_smem = 0;
-};
-
-namespace {
-
-int fail(gm_ctx* c, int code, const char* fmt, ...) {
-    char buf[512];
-    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
-    if (c) c->err = buf; else g_create_error = buf;
-    return code;
-}
-
-#define CK(call)                                                                                              \
-    do {                                                                                                      \
-        cudaError_t e_ = (call);                                                                              \
-        if (e_ != cudaSuccess) return fail(ctx, GM_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
-
-template <class T> cudaError_t dalloc(T*& p, size_t count) {
-    if (p) { cudaFree(p); p = nullptr; }
-    return cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T));
-}
-
-int bind(gm_ctx* ctx) {
-    CK(cudaSetDevice(ctx->device));
-    return GM_OK;
-}
-
-int read_counters(gm_ctx* ctx, Counters& h) {
-    CK(cudaMemcpyAsync(&h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));
-    return GM_OK;
-}
-
-int zero_counters(gm_ctx* ctx) {
-    CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->st));
-    return GM_OK;
-}
-
-int check_launch(gm_ctx* ctx, const char* what) {
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(ctx, GM_ERR_CUDA, "launch %s: %s", what, cudaGetErrorString(e));
-    return GM_OK;
-}
-
-unsigned count_score_beams(const gm_ctx* ctx, const double* ranges) {
-    const DevParams& P = ctx->P;
-    unsigned v = 0;
-    for (unsigned b = P.beam_skip; b < P.nbeams; b++) {
-        if (((b - P.beam_skip + 1u) % (P.lskip + 1u)) != 0u) continue;
-        double r = ranges[b];
-        if (r > P.usable_range || r == 0.0) continue;
-        v++;
-    }
-    return v;
-}
-
-int ensure_query(gm_ctx* ctx, uint32_t count) {
-    if (count <= ctx->q_cap) return GM_OK;
-    CK(dalloc(ctx->d_qidx, count)); CK(dalloc(ctx->d_qposes, (size_t)count * 3)); CK(dalloc(ctx->d_qposes_out, (size_t)count * 3));
-    CK(dalloc(ctx->d_qs, count)); CK(dalloc(ctx->d_ql, count)); CK(dalloc(ctx->d_qc, count));
-    ctx->q_cap = count;
-    return GM_OK;
-}
-
-// constants of score()/likelihoodAndScore() evaluated once on the host with the reference's expressions
-void derive_params(DevParams& P) {
-    volatile double delta = P.delta, ratio = P.free_cell_ratio, gs = P.gaussian_sigma, ls = P.likelihood_sigma;
-    volatile double free_delta = delta * ratio;
-    P.inv_delta = 1. / delta;
-    P.free_off_score = delta * free_delta;
-    P.free_off_lik = free_delta;
-    P.cexp = -1. / gs;
-    P.clik = -1. / ls;
-    P.no_hit = -.5 / ls;
-}
-
-int prepare_scanmatch(gm_ctx* ctx) {
-    const size_t smem = scanmatch_smem_bytes(ctx->P.nbeams);
-    if (smem != ctx->scanmatch_smem) { CK(scanmatch_prepare(smem)); ctx->scanmatch_smem = smem; }
-    return GM_OK;
-}
-
-int ready(gm_ctx* ctx, bool need_particles) {
-    if (!ctx) return GM_ERR_ARG;
-    if (!ctx->laser_set) return fail(ctx, GM_ERR_ARG, "gm_set_laser has not been called");
-    if (!ctx->match_set) return fail(ctx, GM_ERR_ARG, "gm_set_matching has not been called");
-    if (need_particles && !ctx->inited) return fail(ctx, GM_ERR_ARG, "gm_init_particles has not been called");
-    return bind(ctx);
-}
-
-}  // namespace
+#include "gm_ctx.h"
 
 extern "C" {
 
-const char* gm_last_error(const gm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+const char* gm_last_error(const gm_ctx* ctx) { return ctx ? ctx->err.c_str() : create_error().c_str(); }
 
 void gm_default_matching(gm_match_params* p) {  // scanmatcher.cpp:17-56
     memset(p, 0, sizeof *p);
@@ -202,6 +63,7 @@ int gm_create(gm_ctx** out, const gm_config* cfg) {
     CKC(dalloc(c->refcnt_new, cap));
     CKC(cudaMemsetAsync(c->refcnt_new, 0, cap * sizeof(int), c->st));
     const uint32_t N = c->max_particles;
+    c->weights_cap = std::max(cfg->max_particles, cfg->global_particles);
     CKC(dalloc(c->geom, N)); CKC(dalloc(c->geom_alt, N)); CKC(dalloc(c->geom_new, N)); CKC(dalloc(c->shift, N));
     CKC(dalloc(c->d_ranges, GM_MAXBEAMS)); CKC(dalloc(c->d_angles, GM_MAXBEAMS)); CKC(dalloc(c->d_poses, (size_t)N * 3));
     CKC(dalloc(c->d_score, N)); CKC(dalloc(c->d_s, N)); CKC(dalloc(c->d_l, N));
@@ -229,13 +91,14 @@ int gm_create(gm_ctx** out, const gm_config* cfg) {
 int gm_destroy(gm_ctx* c) {
     if (!c) return GM_OK;
     cudaSetDevice(c->device);
+    gmi_dist_destroy(c);
     if (c->st) cudaStreamSynchronize(c->st);
     cudaFree(c->pool.cells); cudaFree(c->pool.refcnt); cudaFree(c->pool.free_list); cudaFree(c->pool.pending);
     cudaFree(c->pool.free_top); cudaFree(c->pool.pending_n); cudaFree(c->refcnt_new);
     cudaFree(c->dir); cudaFree(c->dir_alt); cudaFree(c->geom); cudaFree(c->geom_alt); cudaFree(c->geom_new); cudaFree(c->shift);
     cudaFree(c->d_ranges); cudaFree(c->d_angles); cudaFree(c->d_poses); cudaFree(c->d_score); cudaFree(c->d_s); cudaFree(c->d_l);
     cudaFree(c->d_c); cudaFree(c->d_evals); cudaFree(c->d_idx); cudaFree(c->d_emitted);
-    cudaFree(c->d_w); cudaFree(c->d_logw); cudaFree(c->d_cum); cudaFree(c->d_tgt); cudaFree(c->d_neff);
+    cudaFree(c->d_w); cudaFree(c->d_widx); cudaFree(c->d_logw); cudaFree(c->d_cum); cudaFree(c->d_tgt); cudaFree(c->d_neff);
     cudaFree(c->d_qidx); cudaFree(c->d_qposes); cudaFree(c->d_qposes_out); cudaFree(c->d_qs); cudaFree(c->d_ql); cudaFree(c->d_qc);
     cudaFree(c->d_counters); cudaFree(c->d_inv_n); cudaFree(c->d_digest); cudaFree(c->d_list); cudaFree(c->d_count); cudaFree(c->d_export);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -300,8 +163,9 @@ int gm_init_particles(gm_ctx* ctx, uint32_t n, const double center[2], double wo
     ctx->stats.launches += 4;
     if (int r = check_launch(ctx, "init")) return r;
     CK(cudaMemsetAsync(ctx->refcnt_new, 0, (size_t)ctx->pool.cap * sizeof(int), ctx->st));
-    CK(dalloc(ctx->d_w, ctx->max_particles)); CK(dalloc(ctx->d_logw, ctx->max_particles));
-    CK(dalloc(ctx->d_cum, ctx->max_particles)); CK(dalloc(ctx->d_tgt, ctx->max_particles)); CK(dalloc(ctx->d_neff, 1));
+    CK(dalloc(ctx->d_w, ctx->weights_cap)); CK(dalloc(ctx->d_logw, ctx->weights_cap));
+    CK(dalloc(ctx->d_cum, ctx->weights_cap)); CK(dalloc(ctx->d_tgt, ctx->weights_cap)); CK(dalloc(ctx->d_neff, 1));
+    CK(dalloc(ctx->d_widx, ctx->weights_cap));
     CK(cudaStreamSynchronize(ctx->st));
     ctx->stats.pool_in_use = 0;
     ctx->inited = true;
@@ -392,7 +256,7 @@ int gm_scanmatch(gm_ctx* ctx, const double* ranges, double* poses_inout, double 
 
 int gm_normalize_neff(gm_ctx* ctx, const double* log_weights, uint32_t n, double obs_sigma_gain, double* weights_out, double* neff_out) {
     if (int r = ready(ctx, true)) return r;
-    if (!log_weights || !n || n > ctx->max_particles) return fail(ctx, GM_ERR_ARG, "gm_normalize_neff: bad argument");
+    if (!log_weights || !n || n > ctx->weights_cap) return fail(ctx, GM_ERR_ARG, "gm_normalize_neff: bad argument");
     CK(cudaMemcpyAsync(ctx->d_logw, log_weights, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaEventRecord(ctx->ev0, ctx->st));
     launch_normalize(ctx->d_logw, n, obs_sigma_gain, ctx->d_w, ctx->d_neff, ctx->st);
@@ -408,13 +272,13 @@ int gm_normalize_neff(gm_ctx* ctx, const double* log_weights, uint32_t n, double
 
 int gm_resample_indexes(gm_ctx* ctx, const double* weights, uint32_t n, double u01, uint32_t* idx_out, uint32_t* emitted_out) {
     if (int r = ready(ctx, true)) return r;
-    if (!weights || !idx_out || !n || n > ctx->max_particles) return fail(ctx, GM_ERR_ARG, "gm_resample_indexes: bad argument");
+    if (!weights || !idx_out || !n || n > ctx->weights_cap) return fail(ctx, GM_ERR_ARG, "gm_resample_indexes: bad argument");
     CK(cudaMemcpyAsync(ctx->d_w, weights, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemsetAsync(ctx->d_emitted, 0, sizeof(unsigned), ctx->st));
-    launch_resample(ctx->d_w, n, u01, ctx->d_cum, ctx->d_tgt, ctx->d_idx, ctx->d_emitted, ctx->st);
+    launch_resample(ctx->d_w, n, u01, ctx->d_cum, ctx->d_tgt, ctx->d_widx, ctx->d_emitted, ctx->st);
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_resample")) return r;
-    CK(cudaMemcpyAsync(idx_out, ctx->d_idx, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(idx_out, ctx->d_widx, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->st));
     uint32_t em = 0;
     CK(cudaMemcpyAsync(&em, ctx->d_emitted, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
@@ -424,7 +288,7 @@ int gm_resample_indexes(gm_ctx* ctx, const double* weights, uint32_t n, double u
 
 // computeActiveArea's observable part for all particles: bounding box of the scan at the pose in d_poses and the
 // Map::resize it triggers (scanmatcher.cpp:96-166, map.h:218-241, harray2d.h:80-109).  d_ranges / d_poses are staged.
-static int bounds_and_resize(gm_ctx* ctx) {
+int gmi_bounds_and_resize(gm_ctx* ctx) {
     const uint32_t n = ctx->n;
     // ---- computeActiveArea: bounding box + Map::resize (scanmatcher.cpp:96-166)
     BoundsArgs b;
@@ -469,43 +333,45 @@ static int bounds_and_resize(gm_ctx* ctx) {
     return GM_OK;
 }
 
-int gm_register(gm_ctx* ctx, const double* ranges, const double* poses, const uint32_t* idx) {
-    if (int r = ready(ctx, true)) return r;
-    if (!ranges || !poses) return fail(ctx, GM_ERR_ARG, "gm_register: null argument");
-    const uint32_t n = ctx->n;
-    if (idx)
-        for (uint32_t i = 0; i < n; i++)
-            if (idx[i] >= n) return fail(ctx, GM_ERR_ARG, "gm_register: parent index %u >= %u", idx[i], n);
+// ---- the phases of gm_register, shared with the multi-GPU path (gm_dist.cu)
+
+// stage the scan and the poses of the ctx->n local particles
+int gmi_stage(gm_ctx* ctx, const double* ranges, const double* poses) {
     CK(cudaMemcpyAsync(ctx->d_ranges, ranges, sizeof(double) * ctx->P.nbeams, cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemcpyAsync(ctx->d_poses, poses, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->d_poses, poses, sizeof(double) * 3 * ctx->n, cudaMemcpyHostToDevice, ctx->st));
     if (int r = zero_counters(ctx)) return r;
     ctx->stats.ms_remap = 0.f;
+    return GM_OK;
+}
 
-    // ---- particle copy by patch reference (gridslamprocessor.hxx:184-213)
-    if (idx) {
-        CK(cudaMemcpyAsync(ctx->d_idx, idx, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->st));
-        CK(cudaEventRecord(ctx->ev0, ctx->st));
-        RemapArgs r;
-        r.idx = ctx->d_idx; r.geom = ctx->geom; r.geom_alt = ctx->geom_alt; r.dir = ctx->dir; r.dir_alt = ctx->dir_alt;
-        r.dir_cap = ctx->dir_cap; r.refcnt_new = ctx->refcnt_new;
-        launch_remap(r, n, ctx->st);
-        SweepArgs s; s.pool = ctx->pool; s.refcnt_new = ctx->refcnt_new;
-        launch_sweep(s, ctx->st);
-        launch_merge_free(ctx->pool, ctx->st);
-        CK(cudaEventRecord(ctx->ev1, ctx->st));
-        ctx->stats.launches += 3;
-        if (int rc = check_launch(ctx, "remap")) return rc;
-        std::swap(ctx->dir, ctx->dir_alt);
-        std::swap(ctx->geom, ctx->geom_alt);
-        CK(cudaStreamSynchronize(ctx->st));
-        CK(cudaEventElapsedTime(&ctx->stats.ms_remap, ctx->ev0, ctx->ev1));
-    }
-
+// particle copy by patch reference (gridslamprocessor.hxx:184-213): slot j <- slot idx[j] for the ctx->n local
+// particles; idx may name any slot below src_limit (imported parents sit above ctx->n)
+int gmi_remap(gm_ctx* ctx, const uint32_t* idx, uint32_t src_limit) {
+    const uint32_t n = ctx->n;
+    for (uint32_t i = 0; i < n; i++)
+        if (idx[i] >= src_limit) return fail(ctx, GM_ERR_ARG, "gm_register: parent index %u >= %u", idx[i], src_limit);
+    CK(cudaMemcpyAsync(ctx->d_idx, idx, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaEventRecord(ctx->ev0, ctx->st));
-    if (int rc = bounds_and_resize(ctx)) return rc;
-    Counters h;
+    RemapArgs r;
+    r.idx = ctx->d_idx; r.geom = ctx->geom; r.geom_alt = ctx->geom_alt; r.dir = ctx->dir; r.dir_alt = ctx->dir_alt;
+    r.dir_cap = ctx->dir_cap; r.refcnt_new = ctx->refcnt_new;
+    launch_remap(r, n, ctx->st);
+    SweepArgs s; s.pool = ctx->pool; s.refcnt_new = ctx->refcnt_new;
+    launch_sweep(s, ctx->st);
+    launch_merge_free(ctx->pool, ctx->st);
+    CK(cudaEventRecord(ctx->ev1, ctx->st));
+    ctx->stats.launches += 3;
+    if (int rc = check_launch(ctx, "remap")) return rc;
+    std::swap(ctx->dir, ctx->dir_alt);
+    std::swap(ctx->geom, ctx->geom_alt);
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaEventElapsedTime(&ctx->stats.ms_remap, ctx->ev0, ctx->ev1));
+    return GM_OK;
+}
 
-    // ---- active area + copy-on-write + ray/endpoint updates (scanmatcher.cpp:168-354)
+// active area + copy-on-write + ray/endpoint updates (scanmatcher.cpp:168-354) for the ctx->n local particles
+int gmi_register_update(gm_ctx* ctx) {
+    const uint32_t n = ctx->n;
     RegisterArgs a;
     a.P = ctx->P; a.ranges = ctx->d_ranges; a.angles = ctx->d_angles; a.poses = ctx->d_poses;
     a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool; a.counters = ctx->d_counters;
@@ -521,6 +387,7 @@ int gm_register(gm_ctx* ctx, const double* ranges, const double* poses, const ui
     CK(cudaEventRecord(ctx->ev1, ctx->st));
     ctx->stats.launches += 2;
     if (int rc = check_launch(ctx, "k_register")) return rc;
+    Counters h;
     if (int rc = read_counters(ctx, h)) return rc;
     int top = 0;
     CK(cudaMemcpyAsync(&top, ctx->pool.free_top, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
@@ -534,13 +401,43 @@ int gm_register(gm_ctx* ctx, const double* ranges, const double* poses, const ui
     return GM_OK;
 }
 
+// make every directory slot at least `need` entries long (a Map::resize or an imported map that outgrows the stride)
+int gmi_ensure_dir_cap(gm_ctx* ctx, int need) {
+    if (need <= ctx->dir_cap) return GM_OK;
+    const size_t dn = (size_t)ctx->max_particles * need;
+    int* grown = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void**>(&grown), dn * sizeof(int)));
+    launch_fill_int(grown, dn, -1, ctx->st);
+    CK(cudaMemcpy2DAsync(grown, sizeof(int) * need, ctx->dir, sizeof(int) * ctx->dir_cap, sizeof(int) * ctx->dir_cap, ctx->max_particles,
+                         cudaMemcpyDeviceToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    cudaFree(ctx->dir);
+    ctx->dir = grown;
+    CK(dalloc(ctx->dir_alt, dn));
+    launch_fill_int(ctx->dir_alt, dn, -1, ctx->st);
+    ctx->dir_cap = need;
+    ctx->stats.launches += 2;
+    return check_launch(ctx, "directory growth");
+}
+
+int gm_register(gm_ctx* ctx, const double* ranges, const double* poses, const uint32_t* idx) {
+    if (int r = ready(ctx, true)) return r;
+    if (!ranges || !poses) return fail(ctx, GM_ERR_ARG, "gm_register: null argument");
+    if (int r = gmi_stage(ctx, ranges, poses)) return r;
+    if (idx)
+        if (int r = gmi_remap(ctx, idx, ctx->n)) return r;
+    CK(cudaEventRecord(ctx->ev0, ctx->st));
+    if (int rc = gmi_bounds_and_resize(ctx)) return rc;
+    return gmi_register_update(ctx);
+}
+
 int gm_compute_active_area(gm_ctx* ctx, const double* ranges, const double* poses) {
     if (int r = ready(ctx, true)) return r;
     if (!ranges || !poses) return fail(ctx, GM_ERR_ARG, "gm_compute_active_area: null argument");
     CK(cudaMemcpyAsync(ctx->d_ranges, ranges, sizeof(double) * ctx->P.nbeams, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemcpyAsync(ctx->d_poses, poses, sizeof(double) * 3 * ctx->n, cudaMemcpyHostToDevice, ctx->st));
     if (int r = zero_counters(ctx)) return r;
-    if (int r = bounds_and_resize(ctx)) return r;
+    if (int r = gmi_bounds_and_resize(ctx)) return r;
     CK(cudaStreamSynchronize(ctx->st));
     return GM_OK;
 }
@@ -562,23 +459,7 @@ int gm_upload_map(gm_ctx* ctx, uint32_t particle, const gm_map_info* info, const
     launch_release_particle(ctx->dir + (size_t)particle * ctx->dir_cap, old.npx * old.npy, ctx->pool, ctx->st);
     launch_merge_free(ctx->pool, ctx->st);
     ctx->stats.launches += 2;
-    if (g.npx * g.npy > ctx->dir_cap) {
-        // grow the directory stride for everybody (same path as a device-side Map::resize that outgrows it)
-        const int new_cap = g.npx * g.npy;
-        const size_t dn = (size_t)ctx->max_particles * new_cap;
-        int* grown = nullptr;
-        CK(cudaMalloc(reinterpret_cast<void**>(&grown), dn * sizeof(int)));
-        launch_fill_int(grown, dn, -1, ctx->st);
-        for (uint32_t p = 0; p < ctx->n; p++)
-            CK(cudaMemcpyAsync(grown + (size_t)p * new_cap, ctx->dir + (size_t)p * ctx->dir_cap, sizeof(int) * ctx->dir_cap, cudaMemcpyDeviceToDevice, ctx->st));
-        CK(cudaStreamSynchronize(ctx->st));
-        cudaFree(ctx->dir);
-        ctx->dir = grown;
-        CK(dalloc(ctx->dir_alt, dn));
-        launch_fill_int(ctx->dir_alt, dn, -1, ctx->st);
-        ctx->dir_cap = new_cap;
-        ctx->stats.launches += 2;
-    }
+    if (int r = gmi_ensure_dir_cap(ctx, g.npx * g.npy)) return r;
     CK(cudaMemcpyAsync(ctx->geom + particle, &g, sizeof g, cudaMemcpyHostToDevice, ctx->st));
     if (npatches) {
         if (2 * (size_t)npatches > 2 * ctx->list_cap) { CK(dalloc(ctx->d_list, (size_t)npatches * 2)); ctx->list_cap = npatches; }

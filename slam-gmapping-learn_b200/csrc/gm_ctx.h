@@ -1,0 +1,152 @@
+// gm_ctx.h -- the context object behind the C ABI and the helpers shared by gm_api.cu / gm_dist.cu (internal)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gm_b200.h"
+#include "gm_kernels.h"
+
+using namespace gm;
+
+inline std::string& create_error() { static thread_local std::string e; return e; }
+
+struct gm_ctx {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint32_t max_particles = 0, n = 0, threads = 256;
+    DevParams P{};
+    bool laser_set = false, match_set = false, inited = false;
+    double angles_h[GM_MAXBEAMS];
+
+    Pool pool{};
+    int* refcnt_new = nullptr;
+    int *dir = nullptr, *dir_alt = nullptr;
+    int dir_cap = 0;
+    Geom *geom = nullptr, *geom_alt = nullptr, *geom_new = nullptr;
+    int4* shift = nullptr;
+
+    double *d_ranges = nullptr, *d_angles = nullptr, *d_poses = nullptr;
+    double *d_score = nullptr, *d_s = nullptr, *d_l = nullptr;
+    unsigned *d_c = nullptr, *d_evals = nullptr, *d_idx = nullptr, *d_emitted = nullptr, *d_widx = nullptr;
+    double *d_w = nullptr, *d_logw = nullptr, *d_cum = nullptr, *d_tgt = nullptr, *d_neff = nullptr;
+    // query staging (gm_score / gm_likelihood_and_score)
+    unsigned* d_qidx = nullptr; double *d_qposes = nullptr, *d_qposes_out = nullptr, *d_qs = nullptr, *d_ql = nullptr; unsigned* d_qc = nullptr;
+    uint32_t q_cap = 0;
+    Counters* d_counters = nullptr;
+    double* d_inv_n = nullptr;
+    size_t scanmatch_smem = 0;
+    unsigned long long* d_digest = nullptr;
+    int *d_list = nullptr, *d_count = nullptr; int4* d_export = nullptr; size_t export_cap = 0; size_t list_cap = 0;
+
+    gm_stats stats{};
+    std::string err;
+    size_t register_smem = 0;
+    uint32_t weights_cap = 0;  // capacity of the weight buffers: max(max_particles, global particle count)
+    struct gm_dist* dist = nullptr;  // multi-GPU state (gm_dist.cu), null on a single GPU
+};
+
+
+inline int fail(gm_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf; else create_error() = buf;
+    return code;
+}
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) return fail(ctx, GM_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T> inline cudaError_t dalloc(T*& p, size_t count) {
+    if (p) { cudaFree(p); p = nullptr; }
+    return cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T));
+}
+
+inline int bind(gm_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    return GM_OK;
+}
+
+inline int read_counters(gm_ctx* ctx, Counters& h) {
+    CK(cudaMemcpyAsync(&h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return GM_OK;
+}
+
+inline int zero_counters(gm_ctx* ctx) {
+    CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->st));
+    return GM_OK;
+}
+
+inline int check_launch(gm_ctx* ctx, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, GM_ERR_CUDA, "launch %s: %s", what, cudaGetErrorString(e));
+    return GM_OK;
+}
+
+inline unsigned count_score_beams(const gm_ctx* ctx, const double* ranges) {
+    const DevParams& P = ctx->P;
+    unsigned v = 0;
+    for (unsigned b = P.beam_skip; b < P.nbeams; b++) {
+        if (((b - P.beam_skip + 1u) % (P.lskip + 1u)) != 0u) continue;
+        double r = ranges[b];
+        if (r > P.usable_range || r == 0.0) continue;
+        v++;
+    }
+    return v;
+}
+
+inline int ensure_query(gm_ctx* ctx, uint32_t count) {
+    if (count <= ctx->q_cap) return GM_OK;
+    CK(dalloc(ctx->d_qidx, count)); CK(dalloc(ctx->d_qposes, (size_t)count * 3)); CK(dalloc(ctx->d_qposes_out, (size_t)count * 3));
+    CK(dalloc(ctx->d_qs, count)); CK(dalloc(ctx->d_ql, count)); CK(dalloc(ctx->d_qc, count));
+    ctx->q_cap = count;
+    return GM_OK;
+}
+
+// constants of score()/likelihoodAndScore() evaluated once on the host with the reference's expressions
+inline void derive_params(DevParams& P) {
+    volatile double delta = P.delta, ratio = P.free_cell_ratio, gs = P.gaussian_sigma, ls = P.likelihood_sigma;
+    volatile double free_delta = delta * ratio;
+    P.inv_delta = 1. / delta;
+    P.free_off_score = delta * free_delta;
+    P.free_off_lik = free_delta;
+    P.cexp = -1. / gs;
+    P.clik = -1. / ls;
+    P.no_hit = -.5 / ls;
+}
+
+inline int prepare_scanmatch(gm_ctx* ctx) {
+    const size_t smem = scanmatch_smem_bytes(ctx->P.nbeams);
+    if (smem != ctx->scanmatch_smem) { CK(scanmatch_prepare(smem)); ctx->scanmatch_smem = smem; }
+    return GM_OK;
+}
+
+inline int ready(gm_ctx* ctx, bool need_particles) {
+    if (!ctx) return GM_ERR_ARG;
+    if (!ctx->laser_set) return fail(ctx, GM_ERR_ARG, "gm_set_laser has not been called");
+    if (!ctx->match_set) return fail(ctx, GM_ERR_ARG, "gm_set_matching has not been called");
+    if (need_particles && !ctx->inited) return fail(ctx, GM_ERR_ARG, "gm_init_particles has not been called");
+    return bind(ctx);
+}
+
+
+// phases of gm_register (gm_api.cu), reused by the multi-GPU path (gm_dist.cu)
+extern "C" {
+int gmi_stage(gm_ctx* ctx, const double* ranges, const double* poses);
+int gmi_remap(gm_ctx* ctx, const uint32_t* idx, uint32_t src_limit);
+int gmi_bounds_and_resize(gm_ctx* ctx);
+int gmi_register_update(gm_ctx* ctx);
+int gmi_ensure_dir_cap(gm_ctx* ctx, int need);
+void gmi_dist_destroy(gm_ctx* ctx);
+}

@@ -57,6 +57,13 @@ struct Pool {
     int cap;
 };
 
+// take a patch off the free stack (no pushes happen while a kernel runs: released patches go to `pending`)
+__device__ __forceinline__ int pool_alloc(const Pool& pool, Counters* ctr) {
+    int k = atomicSub(pool.free_top, 1) - 1;
+    if (k < 0) { atomicCAS(&ctr->error, 0, -3); return -1; }
+    return pool.free_list[k];
+}
+
 // ---- world <-> map (map.h:283-298).  No FMA contraction: this file is compiled with --fmad=false.
 __device__ __forceinline__ int w2m(double v, double c, double delta, int s2) {
     return (int)round((v - c) / delta) + s2;

@@ -524,11 +524,6 @@ __global__ void k_relayout_commit(RelayoutArgs A) {
 }
 
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int pool_alloc(const Pool& pool, Counters* ctr) {
-    int k = atomicSub(pool.free_top, 1) - 1;
-    if (k < 0) { atomicCAS(&ctr->error, 0, -3); return -1; }
-    return pool.free_list[k];
-}
 
 // computeActiveArea part 2 + allocActiveArea + registerScan for one particle per CTA.
 //   1. mark the patches under every ray cell (all but the last point) and under the endpoint when

@@ -129,11 +129,19 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     // ---- B200 additions (not in the reference API)
     // device time of the last processed scan's stages and the work they did (C ABI gm_stats)
     struct DeviceStats {
-        double msScanMatch, msWeights, msRemap, msRegister;
+        double msScanMatch, msWeights, msRemap, msRegister, msMigrate, msAllGather;
         unsigned long long beamEvals, scoreEvals, cowCopies, patchAllocs, freeUpdates, hitUpdates, poolInUse, launches;
+        unsigned long long migratedParticles, migratedBytes;
     };
     DeviceStats deviceStats() const;
-    // order-independent digests of all particle maps (patches, cells, sum n, sum visits, hash of (cell, n, visits), hash of acc)
+    // Multi-GPU sharding (call before init): this process is rank `rank` of `world`, one GPU each; ncclId is the 128-byte
+    // id from gm_dist_unique_id(), the same on every rank.  Every rank keeps the full host state (poses, weights,
+    // trajectory tree, drand48 stream -- seed all ranks identically); rank r owns the device maps of particles
+    // [r*N/world, (r+1)*N/world), the other particles' Particle::map stay empty on this rank.
+    void setDistributed(int rank, int world, const void* ncclId);
+    inline unsigned int firstLocalParticle() const { return m_firstLocal; }
+    inline unsigned int localParticles() const { return m_localCount; }
+    // order-independent digests of the LOCAL particle maps (patches, cells, sum n, sum visits, hash of (cell, n, visits), hash of acc)
     std::vector<unsigned long long> mapDigests() const;
 
   protected:
@@ -178,6 +186,9 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     void markMapsStale();
 
     std::shared_ptr<b200::DeviceContext> m_device;
+    int m_rank, m_world;
+    unsigned char m_ncclId[128];
+    unsigned int m_firstLocal, m_localCount;
     unsigned int m_treeEpoch;
     std::vector<double> m_poseBuf, m_scoreBuf, m_likBuf;
 };

@@ -20,12 +20,13 @@ int deviceOrdinal() {
     return 0;
 }
 
-DeviceContext::DeviceContext(unsigned int maxParticles, unsigned long long poolPatches) {
+DeviceContext::DeviceContext(unsigned int maxParticles, unsigned long long poolPatches, unsigned int globalParticles) {
     gm_config cfg;
     std::memset(&cfg, 0, sizeof cfg);
     cfg.device = deviceOrdinal();
     cfg.max_particles = maxParticles;
     cfg.pool_patches = poolPatches;
+    cfg.global_particles = globalParticles;
     if (const char* e = std::getenv("GM_B200_POOL_PATCHES")) cfg.pool_patches = std::strtoull(e, nullptr, 10);
     const int rc = gm_create(&h, &cfg);
     if (rc) fatal(std::string("gm_create: ") + gm_last_error(nullptr));

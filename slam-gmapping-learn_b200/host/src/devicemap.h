@@ -17,7 +17,7 @@ namespace b200 {
 // RAII owner of one gm_ctx
 class DeviceContext {
   public:
-    DeviceContext(unsigned int maxParticles, unsigned long long poolPatches);
+    DeviceContext(unsigned int maxParticles, unsigned long long poolPatches, unsigned int globalParticles = 0);
     ~DeviceContext();
     DeviceContext(const DeviceContext&) = delete;
     DeviceContext& operator=(const DeviceContext&) = delete;

@@ -11,6 +11,7 @@
 
 #include <cassert>
 #include <cmath>
+#include <cstring>
 #include <iomanip>
 #include <iostream>
 #include <set>
@@ -48,7 +49,8 @@ static void defaults(GridSlamProcessor& g) {
 GridSlamProcessor::GridSlamProcessor()
     : m_beams(0), last_update_time_(0.0), period_(5.0), m_count(0), m_readingCount(0), m_linearDistance(0), m_angularDistance(0),
       m_neff(0), m_xmin(0), m_ymin(0), m_xmax(0), m_ymax(0), m_delta(0), m_regScore(0), m_critScore(0), m_maxMove(0),
-      m_linearThresholdDistance(0), m_angularThresholdDistance(0), m_infoStream(std::cout), m_treeEpoch(0) {
+      m_linearThresholdDistance(0), m_angularThresholdDistance(0), m_infoStream(std::cout), m_rank(0), m_world(1), m_firstLocal(0),
+      m_localCount(0), m_treeEpoch(0) {
     m_motionModel.srr = m_motionModel.srt = m_motionModel.str = m_motionModel.stt = 0;
     defaults(*this);
 }
@@ -56,7 +58,8 @@ GridSlamProcessor::GridSlamProcessor()
 GridSlamProcessor::GridSlamProcessor(std::ostream& infoS)
     : m_beams(0), last_update_time_(0.0), period_(5.0), m_count(0), m_readingCount(0), m_linearDistance(0), m_angularDistance(0),
       m_neff(0), m_xmin(0), m_ymin(0), m_xmax(0), m_ymax(0), m_delta(0), m_regScore(0), m_critScore(0), m_maxMove(0),
-      m_linearThresholdDistance(0), m_angularThresholdDistance(0), m_infoStream(infoS), m_treeEpoch(0) {
+      m_linearThresholdDistance(0), m_angularThresholdDistance(0), m_infoStream(infoS), m_rank(0), m_world(1), m_firstLocal(0),
+      m_localCount(0), m_treeEpoch(0) {
     m_motionModel.srr = m_motionModel.srt = m_motionModel.str = m_motionModel.stt = 0;
     defaults(*this);
 }
@@ -125,13 +128,18 @@ void GridSlamProcessor::init(unsigned int size, double xmin, double ymin, double
     releaseLeaves(m_particles);
     m_particles.clear();
 
-    unsigned long long pool = (unsigned long long)size * 512;  // patches; GM_B200_POOL_PATCHES overrides
+    if (size % m_world) b200::fatal("GridSlamProcessor::init: the particle count must be a multiple of the number of ranks");
+    m_localCount = size / m_world;
+    m_firstLocal = m_rank * m_localCount;
+    unsigned long long pool = (unsigned long long)m_localCount * 512;  // patches; GM_B200_POOL_PATCHES overrides
     if (pool < 65536) pool = 65536;
-    m_device.reset(new b200::DeviceContext(size, pool));
+    // sharded: as many spare slots as local particles, for resampled parents imported from other ranks
+    m_device.reset(new b200::DeviceContext(m_world > 1 ? 2 * m_localCount : m_localCount, pool, size));
     m_device->configure(m_matcher);
     const double center[2] = {(xmin + xmax) * .5, (ymin + ymax) * .5};
-    m_device->check(gm_init_particles(m_device->h, size, center, xmax - xmin, ymax - ymin, delta), "gm_init_particles");
-    m_device->particles = size;
+    m_device->check(gm_init_particles(m_device->h, m_localCount, center, xmax - xmin, ymax - ymin, delta), "gm_init_particles");
+    m_device->particles = m_localCount;
+    if (m_world > 1) m_device->check(gm_dist_init(m_device->h, m_rank, m_world, m_ncclId), "gm_dist_init");
 
     TNode* root = new TNode(initialPose, 0, 0, 0);
     ScanMatcherMap mirror(Point(center[0], center[1]), 0., 0., delta);  // geometry + cells arrive with the first pull
@@ -144,11 +152,13 @@ void GridSlamProcessor::init(unsigned int size, double xmin, double ymin, double
         p.setWeight(0);
         p.previousIndex = 0;
         p.node = root;  // all particles share the root; it is not counted as their child (reference: gridslamprocessor.cpp:381-396)
-        std::shared_ptr<b200::DeviceMapResidency> r(new b200::DeviceMapResidency);
-        r->ctx = m_device;
-        r->slot = i;
-        r->stale = true;
-        p.map.setResidency(r);
+        if (i >= m_firstLocal && i < m_firstLocal + m_localCount) {  // this rank holds the particle's map
+            std::shared_ptr<b200::DeviceMapResidency> r(new b200::DeviceMapResidency);
+            r->ctx = m_device;
+            r->slot = i - m_firstLocal;
+            r->stale = true;
+            p.map.setResidency(r);
+        }
     }
     m_neff = (double)size;
     m_count = 0;
@@ -173,26 +183,39 @@ void GridSlamProcessor::markMapsStale() {
 // ------------------------------------------------------------------------------------------ the GPU stages
 // scanMatch (reference: gridslamprocessor.hxx:15-75): optimize + accept/reject + likelihoodAndScore for all particles
 void GridSlamProcessor::scanMatch(const double* plainReading) {
-    const size_t n = m_particles.size();
-    m_poseBuf.resize(3 * n); m_scoreBuf.resize(n); m_likBuf.resize(n);
-    for (size_t i = 0; i < n; i++) {
-        m_poseBuf[3 * i] = m_particles[i].pose.x; m_poseBuf[3 * i + 1] = m_particles[i].pose.y; m_poseBuf[3 * i + 2] = m_particles[i].pose.theta;
+    const size_t n = m_particles.size(), nl = m_localCount;
+    m_poseBuf.resize(3 * nl); m_scoreBuf.resize(n); m_likBuf.resize(n);
+    for (size_t j = 0; j < nl; j++) {
+        const OrientedPoint& q = m_particles[m_firstLocal + j].pose;
+        m_poseBuf[3 * j] = q.x; m_poseBuf[3 * j + 1] = q.y; m_poseBuf[3 * j + 2] = q.theta;
     }
     m_device->configure(m_matcher);
     m_device->check(gm_scanmatch(m_device->h, plainReading, m_poseBuf.data(), m_minimumScore, m_scoreBuf.data(), 0, m_likBuf.data(), 0, 0),
                     "gm_scanmatch");
+    std::vector<double> all;  // rows of (x, y, theta, score, l) for all particles, in global order
+    if (m_world > 1) {
+        std::vector<double> mine(5 * nl);
+        for (size_t j = 0; j < nl; j++) {
+            mine[5 * j] = m_poseBuf[3 * j]; mine[5 * j + 1] = m_poseBuf[3 * j + 1]; mine[5 * j + 2] = m_poseBuf[3 * j + 2];
+            mine[5 * j + 3] = m_scoreBuf[j]; mine[5 * j + 4] = m_likBuf[j];
+        }
+        all.resize(5 * n);
+        m_device->check(gm_dist_allgather(m_device->h, mine.data(), (uint32_t)(5 * nl), all.data()), "gm_dist_allgather");
+    }
     double sumScore = 0;
     for (size_t i = 0; i < n; i++) {
         Particle& p = m_particles[i];
-        sumScore += m_scoreBuf[i];
-        if (!(m_scoreBuf[i] > m_minimumScore) && m_infoStream) {
-            m_infoStream << "Scan Matching Failed, using odometry. Likelihood=" << m_likBuf[i] << endl;
+        const double score = m_world > 1 ? all[5 * i + 3] : m_scoreBuf[i], lik = m_world > 1 ? all[5 * i + 4] : m_likBuf[i];
+        sumScore += score;
+        if (!(score > m_minimumScore) && m_infoStream) {
+            m_infoStream << "Scan Matching Failed, using odometry. Likelihood=" << lik << endl;
             m_infoStream << "lp:" << m_lastPartPose.x << " " << m_lastPartPose.y << " " << m_lastPartPose.theta << endl;
             m_infoStream << "op:" << m_odoPose.x << " " << m_odoPose.y << " " << m_odoPose.theta << endl;
         }
-        p.pose = OrientedPoint(m_poseBuf[3 * i], m_poseBuf[3 * i + 1], m_poseBuf[3 * i + 2]);
-        p.weight += m_likBuf[i];
-        p.weightSum += m_likBuf[i];
+        p.pose = m_world > 1 ? OrientedPoint(all[5 * i], all[5 * i + 1], all[5 * i + 2])
+                             : OrientedPoint(m_poseBuf[3 * i], m_poseBuf[3 * i + 1], m_poseBuf[3 * i + 2]);
+        p.weight += lik;
+        p.weightSum += lik;
     }
     if (m_infoStream) m_infoStream << "Average Scan Matching Score=" << sumScore / n << endl;
 }
@@ -208,13 +231,17 @@ void GridSlamProcessor::normalize() {
 
 // particle copy by patch reference (when `parents` is given) + computeActiveArea + registerScan for every particle
 void GridSlamProcessor::registerAll(const double* plainReading, const unsigned int* parents) {
-    const size_t n = m_particles.size();
-    m_poseBuf.resize(3 * n);
-    for (size_t i = 0; i < n; i++) {
-        m_poseBuf[3 * i] = m_particles[i].pose.x; m_poseBuf[3 * i + 1] = m_particles[i].pose.y; m_poseBuf[3 * i + 2] = m_particles[i].pose.theta;
+    const size_t nl = m_localCount;
+    m_poseBuf.resize(3 * nl);
+    for (size_t j = 0; j < nl; j++) {
+        const OrientedPoint& q = m_particles[m_firstLocal + j].pose;
+        m_poseBuf[3 * j] = q.x; m_poseBuf[3 * j + 1] = q.y; m_poseBuf[3 * j + 2] = q.theta;
     }
     m_device->configure(m_matcher);
-    m_device->check(gm_register(m_device->h, plainReading, m_poseBuf.data(), parents), "gm_register");
+    if (m_world > 1)  // parents are global indexes; maps of parents on other ranks migrate here first
+        m_device->check(gm_dist_register(m_device->h, plainReading, m_poseBuf.data(), parents), "gm_dist_register");
+    else
+        m_device->check(gm_register(m_device->h, plainReading, m_poseBuf.data(), parents), "gm_register");
     markMapsStale();
 }
 
@@ -485,11 +512,19 @@ GridSlamProcessor::DeviceStats GridSlamProcessor::deviceStats() const {
     d.msScanMatch = s.ms_scanmatch; d.msWeights = s.ms_weights; d.msRemap = s.ms_remap; d.msRegister = s.ms_register;
     d.beamEvals = s.beam_evals; d.scoreEvals = s.score_evals; d.cowCopies = s.cow_copies; d.patchAllocs = s.patch_allocs;
     d.freeUpdates = s.free_updates; d.hitUpdates = s.hit_updates; d.poolInUse = s.pool_in_use; d.launches = s.launches;
+    d.msMigrate = s.ms_migrate; d.msAllGather = s.ms_allgather; d.migratedParticles = s.migrated_particles; d.migratedBytes = s.migrated_bytes;
     return d;
 }
 
+void GridSlamProcessor::setDistributed(int rank, int world, const void* ncclId) {
+    if (world < 1 || rank < 0 || rank >= world || (world > 1 && !ncclId)) b200::fatal("GridSlamProcessor::setDistributed: bad rank / world / id");
+    m_rank = rank;
+    m_world = world;
+    if (ncclId) memcpy(m_ncclId, ncclId, sizeof m_ncclId);
+}
+
 std::vector<unsigned long long> GridSlamProcessor::mapDigests() const {
-    const size_t n = m_particles.size();
+    const size_t n = m_localCount;
     std::vector<gm_digest> d(n);
     if (n) m_device->check(gm_map_digest(m_device->h, 0, (uint32_t)n, d.data()), "gm_map_digest");
     std::vector<unsigned long long> out(6 * n);

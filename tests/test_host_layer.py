@@ -146,3 +146,16 @@ def test_cli_runs_and_writes_gfs():
         want = g.neff[g.processed & ~np.isnan(g.smat[:, 0, 0])]
         # the .gfs NEFF record is written before resampling: compare with the reference where no resample happened
         assert len(neff) == len(want)
+
+
+def test_host_shim_loads_under_python():
+    """The C++ host library must be loadable into a Python process (ctypes) and stream numbers through its own
+    iostreams: a toolchain that links libstdc++ statically into the .so crashes exactly here."""
+    build_host()
+    hostapi = importlib.import_module("slam-gmapping-learn_b200.hostapi")
+    L = hostapi.load()
+    h = L.gmh_create(0)
+    a = np.linspace(-1.0, 1.0, 181); lp = np.zeros(3)
+    pv = np.array([float(hostapi.DEFAULTS[k]) for k in hostapi.PARAM_ORDER])
+    L.gmh_setup(h, 181, hostapi._dp(a), hostapi._dp(lp), hostapi._dp(pv))
+    L.gmh_destroy(h)
