@@ -27,14 +27,16 @@ def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    t = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        t = torch.tensor(list(hostapi.nccl_unique_id()), dtype=torch.uint8, device="cuda")
-    dist.broadcast(t, 0)
-    nccl_id = bytes(t.cpu().tolist())
+    def fresh_id():  # an NCCL unique id makes exactly one communicator
+        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            t = torch.tensor(list(hostapi.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        return bytes(t.cpu().tolist())
+
     for case in ("room181_n30", "room181_k2_lskip"):
         g = Golden(case)
-        sharded = make(g, rank, world, nccl_id)
+        sharded = make(g, rank, world, fresh_id())
         lo, hi = sharded.local_range()
         assert hi - lo == g.N // world
         migrated = 0
