@@ -238,6 +238,7 @@ def main():
                            "api": "GMapping::GridSlamProcessor::processScan (C++ host layer over the C ABI)"},
                 "beam_evals_per_s": beam_evals / (dev_ms * 1e-3), "beam_evals_per_scan": beam_evals, "score_evals_per_particle": score_evals / n,
                 "stage_ms": {k[3:]: float(np.mean([s[k] for s in stage])) for k in keys},
+                "host_ms": {k[8:]: float(np.mean([s[k] for s in stage])) for k in ("host_ms_motion", "host_ms_scanmatch", "host_ms_treeweights", "host_ms_resample")},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                              "kernel": "k_scanmatch", "peak_source": peak_src, "bytes_per_beam_eval": BYTES_PER_BEAM_EVAL,
                              "note": "algorithmic bytes; the window reads are served from L1/L2 (see profiles/), DRAM traffic is ~60x smaller"},

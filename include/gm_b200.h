@@ -152,6 +152,10 @@ int gm_upload_map(gm_ctx* ctx, uint32_t particle, const gm_map_info* info, const
  * patch_coords[2k..2k+1] = (px,py) and cells[k*1024 + lx*32 + ly].  Returns patch count via info. */
 int gm_map_info_get(gm_ctx* ctx, uint32_t particle, gm_map_info* info);
 int gm_download_map(gm_ctx* ctx, uint32_t particle, gm_map_info* info, int32_t* patch_coords, gm_cell* cells, uint32_t max_patches);
+/* replaces: the occupancy-grid fill of the ROS wrapper, gmapping/src/slam_gmapping.cpp:956-993:
+ * out[y * width + x] = -1 never visited, 100 if n/visits > occ_thresh, else 0; width/height = the particle's map size in cells
+ * (gm_map_info: patches_x * 32, patches_y * 32). */
+int gm_export_occupancy(gm_ctx* ctx, uint32_t particle, double occ_thresh, int8_t* out, uint32_t width, uint32_t height);
 int gm_map_digest(gm_ctx* ctx, uint32_t first, uint32_t count, gm_digest* out /*count*/);
 
 /* ---- multi-GPU (one process and one gm_ctx per GPU; NCCL over NVLink).  Rank r owns the global particles

@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(HERE, "libgm_b200.so")
 EXPORTS = ["gm_create", "gm_destroy", "gm_last_error", "gm_set_laser", "gm_set_matching", "gm_default_matching",
            "gm_init_particles", "gm_score", "gm_likelihood_and_score", "gm_scanmatch", "gm_normalize_neff",
            "gm_resample_indexes", "gm_register", "gm_map_info_get", "gm_download_map", "gm_map_digest",
-           "gm_get_stats", "gm_particles"]
+           "gm_get_stats", "gm_particles", "gm_optimize", "gm_compute_active_area", "gm_upload_map", "gm_export_occupancy",
+           "gm_dist_unique_id", "gm_dist_init", "gm_dist_allgather", "gm_dist_register", "gm_dist_plan"]
 
 
 class GmError(RuntimeError):
@@ -87,6 +88,8 @@ def load_library(path=LIB_PATH):
     L.gm_map_info_get.argtypes = [vp, C.c_uint32, C.POINTER(MapInfo)]
     L.gm_download_map.argtypes = [vp, C.c_uint32, C.POINTER(MapInfo), vp, vp, C.c_uint32]
     L.gm_map_digest.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
+    L.gm_export_occupancy.argtypes = [vp, C.c_uint32, C.c_double, vp, C.c_uint32, C.c_uint32]
+    L.gm_optimize.argtypes = [vp, C.c_uint32, up, dp, dp, dp, dp]
     L.gm_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.gm_particles.restype = C.c_uint32; L.gm_particles.argtypes = [vp]
     _lib = L
@@ -222,6 +225,20 @@ class GmContext:
         out = np.zeros(count, dtype=DIGEST_DTYPE)
         self._ck(self.L.gm_map_digest(self.h, first, count, out.ctypes.data))
         return out
+
+    def occupancy_grid(self, particle, occ_thresh=0.25):
+        """-> int8 [height, width] (row y, column x): -1 unknown, 0 free, 100 occupied"""
+        mi = self.map_info(particle)
+        w, h = mi.patches_x * 32, mi.patches_y * 32
+        out = np.zeros((h, w), dtype=np.int8)
+        self._ck(self.L.gm_export_occupancy(self.h, particle, float(occ_thresh), out.ctypes.data, w, h))
+        return out
+
+    def optimize(self, particle_idx, poses, ranges):
+        idx = np.ascontiguousarray(particle_idx, dtype=np.uint32); p = _f64(poses).reshape(-1, 3); r = self._ranges(ranges)
+        out = np.zeros_like(p); sc = np.zeros(len(idx))
+        self._ck(self.L.gm_optimize(self.h, len(idx), _up(idx), _dp(p), _dp(r), _dp(out), _dp(sc)))
+        return out, sc
 
     def stats(self):
         s = Stats(); self._ck(self.L.gm_get_stats(self.h, C.byref(s))); return s.as_dict()

@@ -100,7 +100,7 @@ int gm_destroy(gm_ctx* c) {
     cudaFree(c->d_c); cudaFree(c->d_evals); cudaFree(c->d_idx); cudaFree(c->d_emitted);
     cudaFree(c->d_w); cudaFree(c->d_widx); cudaFree(c->d_logw); cudaFree(c->d_cum); cudaFree(c->d_tgt); cudaFree(c->d_neff);
     cudaFree(c->d_qidx); cudaFree(c->d_qposes); cudaFree(c->d_qposes_out); cudaFree(c->d_qs); cudaFree(c->d_ql); cudaFree(c->d_qc);
-    cudaFree(c->d_counters); cudaFree(c->d_inv_n); cudaFree(c->d_digest); cudaFree(c->d_list); cudaFree(c->d_count); cudaFree(c->d_export);
+    cudaFree(c->d_occ); cudaFree(c->d_counters); cudaFree(c->d_inv_n); cudaFree(c->d_digest); cudaFree(c->d_list); cudaFree(c->d_count); cudaFree(c->d_export);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->st) cudaStreamDestroy(c->st);
@@ -379,10 +379,22 @@ int gmi_register_update(gm_ctx* ctx) {
     int sort_n = 32;
     while (sort_n < (int)ctx->P.nbeams) sort_n <<= 1;
     a.sort_n = sort_n;
-    const size_t smem = register_smem_bytes(a.bitmap_words, a.sort_n);
-    if (smem > 200 * 1024) return fail(ctx, GM_ERR_ARG, "gm_register: patch directory of %d entries needs %zu B of shared memory", ctx->dir_cap, smem);
+    // visit-count tiles: as many as fit (one pass over the rays when the active area has at most that many patches);
+    // with few active patches a smaller allocation lets two CTAs share an SM
+    const size_t fixed = register_smem_bytes(a.bitmap_words, a.sort_n, (int)ctx->P.nbeams, 0);
+    const size_t budget = 200 * 1024;
+    if (fixed + 2048 > budget) return fail(ctx, GM_ERR_ARG, "gm_register: patch directory of %d entries needs %zu B of shared memory", ctx->dir_cap, fixed);
+    int tile_cap = (int)((budget - fixed) / 2048);
+    const int want = ctx->reg_active_hint > 0 ? ctx->reg_active_hint + 8 : tile_cap;
+    if (want < tile_cap) {
+        const size_t half = (budget + 24 * 1024) / 2;  // two CTAs per SM (227 KB)
+        const int cap2 = fixed + 2048 <= half ? (int)((half - fixed) / 2048) : 0;
+        tile_cap = want <= cap2 ? cap2 : tile_cap;
+    }
+    a.tile_cap = tile_cap;
+    const size_t smem = register_smem_bytes(a.bitmap_words, a.sort_n, (int)ctx->P.nbeams, tile_cap);
     if (smem != ctx->register_smem) { CK(register_prepare(smem)); ctx->register_smem = smem; }
-    launch_register(a, n, ctx->threads, smem, ctx->st);
+    launch_register(a, n, smem, ctx->st);
     launch_merge_free(ctx->pool, ctx->st);
     CK(cudaEventRecord(ctx->ev1, ctx->st));
     ctx->stats.launches += 2;
@@ -396,6 +408,7 @@ int gmi_register_update(gm_ctx* ctx) {
     ctx->stats.cow_copies = h.cow_copies; ctx->stats.patch_allocs = h.patch_allocs;
     ctx->stats.free_updates = h.free_updates; ctx->stats.hit_updates = h.hit_updates; ctx->stats.resizes = h.resizes;
     ctx->stats.pool_in_use = (uint64_t)(ctx->pool.cap - top);
+    ctx->reg_active_hint = h.max_active;
     if (h.error == GM_ERR_POOL) return fail(ctx, GM_ERR_POOL, "gm_register: patch pool of %d patches exhausted", ctx->pool.cap);
     if (h.error) return fail(ctx, h.error, "gm_register: device-side error %d", h.error);
     return GM_OK;
@@ -516,6 +529,24 @@ int gm_download_map(gm_ctx* ctx, uint32_t particle, gm_map_info* info, int32_t* 
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_export_gather")) return r;
     CK(cudaMemcpyAsync(cells, ctx->d_export, sizeof(int4) * kPatchCells * (size_t)m, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return GM_OK;
+}
+
+int gm_export_occupancy(gm_ctx* ctx, uint32_t particle, double occ_thresh, int8_t* out, uint32_t width, uint32_t height) {
+    if (int r = ready(ctx, true)) return r;
+    if (particle >= ctx->n || !out || !width || !height) return fail(ctx, GM_ERR_ARG, "gm_export_occupancy: bad argument");
+    Geom g;
+    CK(cudaMemcpyAsync(&g, ctx->geom + particle, sizeof g, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    if ((int)width != (g.npx << kPatchMag) || (int)height != (g.npy << kPatchMag))
+        return fail(ctx, GM_ERR_ARG, "gm_export_occupancy: the map is %d x %d cells, the buffer %u x %u", g.npx << kPatchMag, g.npy << kPatchMag, width, height);
+    const size_t bytes = (size_t)width * height;
+    if (bytes > ctx->occ_cap) { CK(dalloc(ctx->d_occ, bytes)); ctx->occ_cap = bytes; }
+    launch_export_occupancy(ctx->dir + (size_t)particle * ctx->dir_cap, g, ctx->pool.cells, occ_thresh, ctx->d_occ, (int)width, (int)height, ctx->st);
+    ctx->stats.launches++;
+    if (int r = check_launch(ctx, "k_export_occupancy")) return r;
+    CK(cudaMemcpyAsync(out, ctx->d_occ, bytes, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     return GM_OK;
 }

@@ -49,6 +49,8 @@ struct gm_ctx {
     gm_stats stats{};
     std::string err;
     size_t register_smem = 0;
+    signed char* d_occ = nullptr; size_t occ_cap = 0;  // gm_export_occupancy staging
+    int reg_active_hint = 0;  // largest active-patch count seen by the last k_register (sizes its tile allocation)
     uint32_t weights_cap = 0;  // capacity of the weight buffers: max(max_particles, global particle count)
     struct gm_dist* dist = nullptr;  // multi-GPU state (gm_dist.cu), null on a single GPU
 };

@@ -44,7 +44,7 @@ struct Counters {  // zeroed per stage, read back by the host
     int error;          // gm_status of the first device-side failure
     int need_dir_cap;   // largest npx*npy any particle needs (k_bounds)
     int any_resize;
-    int pad;
+    int max_active;     // largest active-patch count of a particle (k_register)
 };
 
 struct Pool {

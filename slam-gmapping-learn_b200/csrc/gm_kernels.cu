@@ -11,6 +11,8 @@
 //   k_remap/k_sweep/k_merge_free   particle copy by patch reference     (gridslamprocessor.hxx:184-213)
 //   k_normalize / k_resample       (gridslamprocessor.hxx:82-121, particlefilter.h:180-229)
 //   k_digest / k_export_*          map read-back
+#include <climits>
+
 #include "gm_device.cuh"
 #include "gm_kernels.h"
 
@@ -526,26 +528,79 @@ __global__ void k_relayout_commit(RelayoutArgs A) {
 // ------------------------------------------------------------------------------------------------
 
 // computeActiveArea part 2 + allocActiveArea + registerScan for one particle per CTA.
+//   0. one thread per beam: endpoint cell, (float) endpoint, validity -- sin/cos and the reference's divide+round
+//      once per beam, kept in shared memory for the later phases;
 //   1. mark the patches under every ray cell (all but the last point) and under the endpoint when
 //      d < usableRange (scanmatcher.cpp:181-218), in a shared-memory bitmap over the directory;
 //   2. make every active patch private: create it, or copy it when another particle still references
 //      it (harray2d.h:169-185 copies always; copying only shared patches yields identical cells);
-//   3. visits++ along the rays (scanmatcher.cpp:317-325): a warp owns a ray, lanes take consecutive cells
-//      through the closed-form Bresenham; integer atomics commute, so the counts are bit-exact;
+//   3. visits++ along the rays (scanmatcher.cpp:317-325); integer atomics commute, so the counts are bit-exact;
 //   4. endpoint hits (scanmatcher.cpp:327-334): float `acc` is order dependent, so hits are sorted by
 //      (cell, beam) and each cell's run is accumulated sequentially in beam order by one thread.
-__global__ void __launch_bounds__(256) k_register(RegisterArgs A) {
+// Ray walks (1 and 3): a thread owns a ray and steps the reference's Bresenham incrementally, looking the patch up
+// again only when the cell leaves it; neighbouring lanes walk neighbouring beams, i.e. rays of similar length.
+struct BeamRec { int p1x, p1y; float hx, hy; int flags; };  // flags: 1 = ray is traced, 2 = endpoint is a hit
+
+// visit every cell of the line p0 -> p1 except p1 itself, walking the reference's Bresenham (gridlinetraversal.h:20-108:
+// major axis upward from the lower endpoint) step by step in ONE thread; f(x, y, px, py, enteredNewPatch)
+template <class F>
+__device__ __forceinline__ void walk_ray(int p0x, int p0y, int p1x, int p1y, F f) {
+    const Line L = make_line(p0x, p0y, p1x, p1y);
+    int m = L.n - 1;  // all points but the last one in start->end order, i.e. but p1
+    if (m <= 0) return;
+    int a = L.a_lo, bb = L.b_lo;
+    int d = 2 * L.db - L.da;
+    const int incr1 = 2 * L.db, incr2 = 2 * (L.db - L.da);
+    if (L.from_end) {  // p1 is the LOW end: skip it
+        a++;
+        if (d < 0) d += incr1; else { bb += L.bstep; d += incr2; }
+    }
+    int lpx = INT_MIN, lpy = INT_MIN;
+    for (; m > 0; m--) {
+        const int x = L.steep ? bb : a, y = L.steep ? a : bb;
+        const int px = x >> kPatchMag, py = y >> kPatchMag;
+        const bool np = px != lpx || py != lpy;
+        lpx = px; lpy = py;
+        f(x, y, px, py, np);
+        a++;
+        if (d < 0) d += incr1; else { bb += L.bstep; d += incr2; }
+    }
+}
+
+constexpr int kRegThreads = 512;
+constexpr int kTileWords = kPatchCells / 2;  // a tile counts visits of one patch: 1024 cells x 16 bit, two per word
+
+// dynamic shared memory of k_register (see register_smem_bytes): active-patch bitmap over the directory, its
+// running popcount per word, sort keys of the hits, per-beam records, visit-count tiles
+struct RegSmem {
+    unsigned* active; unsigned short* prefix; unsigned long long* keys; BeamRec* rec; unsigned* tiles;
+};
+__host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+__device__ __forceinline__ RegSmem carve(unsigned char* raw, int bitmap_words, int sort_n, int nbeams) {
+    RegSmem m;
+    size_t o = 0;
+    m.active = reinterpret_cast<unsigned*>(raw + o); o += align16((size_t)bitmap_words * 4);
+    m.prefix = reinterpret_cast<unsigned short*>(raw + o); o += align16((size_t)bitmap_words * 2);
+    m.keys = reinterpret_cast<unsigned long long*>(raw + o); o += (size_t)sort_n * 8;
+    m.rec = reinterpret_cast<BeamRec*>(raw + o); o += align16((size_t)nbeams * sizeof(BeamRec));
+    m.tiles = reinterpret_cast<unsigned*>(raw + o);
+    return m;
+}
+
+__global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevParams& P = A.P;
     const unsigned p = blockIdx.x;
     const Geom g = A.geom[p];
     int* dirp = A.dir + (size_t)p * A.dir_cap;
     const int nent = g.npx * g.npy, nwords = (nent + 31) >> 5;
-    unsigned* active = reinterpret_cast<unsigned*>(smem_raw);
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + (((size_t)A.bitmap_words * 4 + 15) & ~(size_t)15));
-    float* hx = reinterpret_cast<float*>(keys + A.sort_n);
-    float* hy = hx + A.sort_n;
+    const RegSmem M = carve(smem_raw, A.bitmap_words, A.sort_n, (int)P.nbeams);
+    unsigned* active = M.active;
+    unsigned long long* keys = M.keys;
+    BeamRec* rec = M.rec;
     __shared__ unsigned long long s_free, s_hit, s_cow, s_alloc;
+    __shared__ int s_part[kRegThreads / 32];
+    __shared__ int s_nactive;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 
     for (int i = threadIdx.x; i < nwords; i += blockDim.x) active[i] = 0u;
@@ -556,44 +611,67 @@ __global__ void __launch_bounds__(256) k_register(RegisterArgs A) {
     const int p0x = w2m(lx, P.cx, P.delta, g.sx2), p0y = w2m(ly, P.cy, P.delta, g.sy2);
     __syncthreads();
 
-    // ---- 1. active area
-    for (unsigned b = P.beam_skip + warp; b < P.nbeams; b += nw) {
+    // ---- 0. per-beam endpoints
+    for (unsigned b = threadIdx.x; b < P.nbeams; b += blockDim.x) {
+        BeamRec R; R.p1x = R.p1y = 0; R.hx = R.hy = 0.f; R.flags = 0;
         double r = __ldg(A.ranges + b);
-        bool hit;
+        bool ok = b >= P.beam_skip, hit;
         if (P.generate_map) {
-            if (r > P.laser_max_range || r == 0.0 || isnan(r)) continue;
+            ok = ok && !(r > P.laser_max_range || r == 0.0 || isnan(r));
             hit = !(r >= P.usable_range);  // d < usableRange after clipping
             if (r > P.usable_range) r = P.usable_range;
         } else {
-            if (r > P.laser_max_range || r > P.usable_range || r == 0.0 || isnan(r)) continue;
+            ok = ok && !(r > P.laser_max_range || r > P.usable_range || r == 0.0 || isnan(r));
             hit = true;
         }
-        double s, c;
-        sincos(lt + __ldg(A.angles + b), &s, &c);
-        const double phx = lx + r * c, phy = ly + r * s;
-        const int p1x = w2m(phx, P.cx, P.delta, g.sx2), p1y = w2m(phy, P.cy, P.delta, g.sy2);
-        if (P.generate_map) {
-            const Line L = make_line(p0x, p0y, p1x, p1y);
-            for (int i0 = 0; i0 < L.n - 1; i0 += 32) {
-                int i = i0 + lane, e = -1;
-                if (i < L.n - 1) {
-                    int x, y; line_point(L, i, x, y);
-                    if (x >= 0 && y >= 0 && (x >> kPatchMag) < g.npx && (y >> kPatchMag) < g.npy) e = (x >> kPatchMag) * g.npy + (y >> kPatchMag);
-                }
-                int prev = __shfl_up_sync(0xffffffffu, e, 1);
-                if (e >= 0 && (lane == 0 || prev != e)) atomicOr(&active[e >> 5], 1u << (e & 31));
-            }
-        }
-        if (lane == 0 && hit) {
-            if (p1x >= 0 && p1y >= 0 && (p1x >> kPatchMag) < g.npx && (p1y >> kPatchMag) < g.npy) {
-                int e = (p1x >> kPatchMag) * g.npy + (p1y >> kPatchMag);
+        if (ok) {
+            double s, c;
+            sincos(lt + __ldg(A.angles + b), &s, &c);
+            const double phx = lx + r * c, phy = ly + r * s;
+            R.p1x = w2m(phx, P.cx, P.delta, g.sx2); R.p1y = w2m(phy, P.cy, P.delta, g.sy2);
+            R.hx = (float)phx; R.hy = (float)phy;
+            R.flags = (P.generate_map ? 1 : 0) | (hit ? 2 : 0);
+            if (hit && R.p1x >= 0 && R.p1y >= 0 && (R.p1x >> kPatchMag) < g.npx && (R.p1y >> kPatchMag) < g.npy) {
+                const int e = (R.p1x >> kPatchMag) * g.npy + (R.p1y >> kPatchMag);
                 atomicOr(&active[e >> 5], 1u << (e & 31));
-                keys[b] = ((unsigned long long)(unsigned)p1x << 36) | ((unsigned long long)(unsigned)p1y << 12) | b;
-                hx[b] = (float)phx; hy[b] = (float)phy;
+                keys[b] = ((unsigned long long)(unsigned)R.p1x << 36) | ((unsigned long long)(unsigned)R.p1y << 12) | b;
             }
         }
+        rec[b] = R;
     }
     __syncthreads();
+
+    // ---- 1. active area: patches under the rays
+    for (unsigned b = threadIdx.x; b < P.nbeams; b += blockDim.x) {
+        const BeamRec R = rec[b];
+        if (!(R.flags & 1)) continue;
+        walk_ray(p0x, p0y, R.p1x, R.p1y, [&](int, int, int px, int py, bool np) {
+            if (np && (unsigned)px < (unsigned)g.npx && (unsigned)py < (unsigned)g.npy) {
+                const int e = px * g.npy + py;
+                atomicOr(&active[e >> 5], 1u << (e & 31));
+            }
+        });
+    }
+    __syncthreads();
+
+    // ---- 1b. rank of every active patch: prefix[w] = number of active patches in words < w
+    {
+        const int per = (nwords + blockDim.x - 1) / blockDim.x;
+        const int w0 = threadIdx.x * per, w1 = min(nwords, w0 + per);
+        int c = 0;
+        for (int w = w0; w < w1; w++) c += __popc(active[w]);
+        int incl = c;  // inclusive scan over the block: warp scan, then warp totals
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) s_part[warp] = incl;
+        __syncthreads();
+        int base = 0;
+        for (int w = 0; w < warp; w++) base += s_part[w];
+        int run = base + incl - c;
+        for (int w = w0; w < w1; w++) { M.prefix[w] = (unsigned short)run; run += __popc(active[w]); }
+        if (threadIdx.x == blockDim.x - 1) { s_nactive = base + incl; atomicMax(&A.counters->max_active, base + incl); }
+    }
+    __syncthreads();
+    const int nactive = s_nactive;
 
     // ---- 2. copy-on-write: a warp per active patch
     for (int wi = warp; wi < nwords; wi += nw) {
@@ -632,27 +710,53 @@ __global__ void __launch_bounds__(256) k_register(RegisterArgs A) {
     __threadfence();
     __syncthreads();
 
-    // ---- 3. free-space updates along the rays
+    // ---- 3. free-space updates (scanmatcher.cpp:317-325).  visits++ is counted per cell in shared-memory tiles
+    // (16-bit counters: a cell is crossed by at most nbeams < 2048 rays), `tile_cap` active patches per pass, then
+    // added to the now private patches with plain read-modify-writes: no global atomics.
     unsigned long long nfree = 0;
-    for (unsigned b = P.beam_skip + warp; P.generate_map && b < P.nbeams; b += nw) {
-        double r = __ldg(A.ranges + b);
-        if (r > P.laser_max_range || r == 0.0 || isnan(r)) continue;
-        if (r > P.usable_range) r = P.usable_range;
-        double s, c;
-        sincos(lt + __ldg(A.angles + b), &s, &c);
-        const double phx = lx + r * c, phy = ly + r * s;
-        const int p1x = w2m(phx, P.cx, P.delta, g.sx2), p1y = w2m(phy, P.cy, P.delta, g.sy2);
-        const Line L = make_line(p0x, p0y, p1x, p1y);
-        for (int i = lane; i < L.n - 1; i += 32) {
-            int x, y; line_point(L, i, x, y);
-            if (x < 0 || y < 0 || (x >> kPatchMag) >= g.npx || (y >> kPatchMag) >= g.npy) continue;
-            int id = dirp[(x >> kPatchMag) * g.npy + (y >> kPatchMag)];
-            if (id < 0) continue;
-            int* cell = reinterpret_cast<int*>(A.pool.cells + (size_t)id * kPatchCells + ((x & 31) << kPatchMag) + (y & 31));
-            atomicAdd(cell + 3, 1);  // update(false): visits++
-            nfree++;
+    for (int first = 0; first < nactive && P.generate_map; first += A.tile_cap) {
+        const int ntile = min(A.tile_cap, nactive - first);
+        for (int i = threadIdx.x; i < ntile * kTileWords; i += blockDim.x) M.tiles[i] = 0u;
+        __syncthreads();
+        for (unsigned b = threadIdx.x; b < P.nbeams; b += blockDim.x) {
+            const BeamRec R = rec[b];
+            if (!(R.flags & 1)) continue;
+            unsigned* tile = nullptr;  // counters of the current patch, null when it is not in this pass / outside the map
+            walk_ray(p0x, p0y, R.p1x, R.p1y, [&](int x, int y, int px, int py, bool np) {
+                if (np) {
+                    tile = nullptr;
+                    if ((unsigned)px < (unsigned)g.npx && (unsigned)py < (unsigned)g.npy) {
+                        const int e = px * g.npy + py;
+                        const int slot = (int)M.prefix[e >> 5] + __popc(active[e >> 5] & ((1u << (e & 31)) - 1u)) - first;
+                        if ((unsigned)slot < (unsigned)ntile) tile = M.tiles + slot * kTileWords;
+                    }
+                }
+                if (tile) {
+                    const int ci = ((x & 31) << kPatchMag) + (y & 31);
+                    atomicAdd(tile + (ci >> 1), 1u << ((ci & 1) << 4));
+                }
+            });
         }
+        __syncthreads();
+        // flush: a warp per tile; the directory entry of rank first + t is found from the prefix sums
+        for (int t = warp; t < ntile; t += nw) {
+            const int rank = first + t;
+            int lo = 0, hi = nwords - 1;  // last word whose prefix <= rank and that holds the rank-th bit
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((int)M.prefix[mid] <= rank) lo = mid; else hi = mid - 1; }
+            const int e = (lo << 5) + (int)__fns(active[lo], 0, rank - (int)M.prefix[lo] + 1);
+            const int id = dirp[e];
+            if (id < 0) continue;
+            int* cells = reinterpret_cast<int*>(A.pool.cells + (size_t)id * kPatchCells);
+            const unsigned* tile = M.tiles + t * kTileWords;
+            for (int ci = lane; ci < kPatchCells; ci += 32) {
+                const unsigned c = (tile[ci >> 1] >> ((ci & 1) << 4)) & 0xffffu;
+                if (c) { cells[(ci << 2) + 3] += (int)c; nfree += c; }  // update(false) c times: visits += c
+            }
+        }
+        __syncthreads();
     }
+    __threadfence();
+    __syncthreads();
 
     // ---- 4. endpoint hits in beam order per cell: bitonic sort of (cell, beam) keys
     for (int k = 2; k <= A.sort_n; k <<= 1)
@@ -682,10 +786,10 @@ __global__ void __launch_bounds__(256) k_register(RegisterArgs A) {
         int cnt = 0;
         for (int q = i; q < A.sort_n && (keys[q] >> 12) == ck; q++) {
             unsigned b = (unsigned)(keys[q] & 0xfffu);
-            ax += hx[b]; ay += hy[b]; cnt++;  // acc += (float)phit, smmap.h:51-52
+            ax += rec[b].hx; ay += rec[b].hy; cnt++;  // acc += (float)phit, smmap.h:51-52
         }
         cell[0] = __float_as_int(ax); cell[1] = __float_as_int(ay);
-        atomicAdd(cell + 2, cnt); atomicAdd(cell + 3, cnt);
+        cell[2] += cnt; cell[3] += cnt;  // the cell belongs to this thread alone now
         nhit += cnt;
     }
     if (nfree) atomicAdd(&s_free, nfree);
@@ -844,6 +948,21 @@ __global__ void k_export_gather(const int4* __restrict__ pool, const int* __rest
     for (int i = threadIdx.x; i < kPatchCells; i += blockDim.x) out[(size_t)k * kPatchCells + i] = pool[(size_t)id * kPatchCells + i];
 }
 
+// occupancy grid of one particle (the nav_msgs::OccupancyGrid fill of gmapping/src/slam_gmapping.cpp:956-993):
+// out[y * width + x] = -1 unknown (never visited), 100 if n / visits > occ_thresh, else 0
+__global__ void k_export_occupancy(const int* __restrict__ dirp, Geom g, const int4* __restrict__ pool, double occ_thresh, signed char* __restrict__ out,
+                                   int width, int height) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= width || y >= height) return;
+    long long ci;
+    signed char v = -1;
+    if (cell_addr(g, dirp, x, y, ci)) {
+        const int4 c = __ldg(pool + ci);
+        if (c.w) v = ((double)c.z / (double)c.w > occ_thresh) ? 100 : 0;
+    }
+    out[(size_t)y * width + x] = v;
+}
+
 // drop every patch reference of one particle (before its map is replaced by gm_upload_map)
 __global__ void k_release_particle(int* dirp, int nent, Pool pool) {
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nent; e += gridDim.x * blockDim.x) {
@@ -865,6 +984,10 @@ __global__ void k_install_patches(int* dirp, Geom g, const int* __restrict__ coo
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
+void launch_export_occupancy(const int* dirp, Geom g, const int4* pool, double occ_thresh, signed char* out, int width, int height, cudaStream_t st) {
+    dim3 grid((width + 255) / 256, height);
+    k_export_occupancy<<<grid, 256, 0, st>>>(dirp, g, pool, occ_thresh, out, width, height);
+}
 void launch_release_particle(int* dirp, int nent, const Pool& pool, cudaStream_t st) { k_release_particle<<<64, 256, 0, st>>>(dirp, nent, pool); }
 void launch_install_patches(int* dirp, Geom g, const int* coords, const int4* staged, const Pool& pool, Counters* ctr, int n, cudaStream_t st) {
     k_install_patches<<<n, 256, 0, st>>>(dirp, g, coords, staged, pool, ctr);
@@ -884,11 +1007,14 @@ void launch_scanmatch(const ScanMatchArgs& a, unsigned n, cudaStream_t st) {
 void launch_bounds(const BoundsArgs& a, unsigned n, unsigned threads, cudaStream_t st) { k_bounds<<<n, threads, 0, st>>>(a); }
 void launch_relayout(const RelayoutArgs& a, unsigned n, cudaStream_t st) { k_relayout<<<n, 256, 0, st>>>(a); }
 void launch_relayout_commit(const RelayoutArgs& a, unsigned n, cudaStream_t st) { k_relayout_commit<<<n, 256, 0, st>>>(a); }
-size_t register_smem_bytes(int bitmap_words, int sort_n) { return (((size_t)bitmap_words * 4 + 15) & ~(size_t)15) + (size_t)sort_n * 16; }
+size_t register_smem_bytes(int bitmap_words, int sort_n, int nbeams, int tile_cap) {
+    return align16((size_t)bitmap_words * 4) + align16((size_t)bitmap_words * 2) + (size_t)sort_n * 8 + align16((size_t)nbeams * sizeof(BeamRec)) +
+           (size_t)tile_cap * kTileWords * 4;
+}
 cudaError_t register_prepare(size_t smem) {
     return cudaFuncSetAttribute(k_register, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
-void launch_register(const RegisterArgs& a, unsigned n, unsigned threads, size_t smem, cudaStream_t st) { k_register<<<n, threads, smem, st>>>(a); }
+void launch_register(const RegisterArgs& a, unsigned n, size_t smem, cudaStream_t st) { k_register<<<n, kRegThreads, smem, st>>>(a); }
 void launch_remap(const RemapArgs& a, unsigned n, cudaStream_t st) { k_remap<<<n, 256, 0, st>>>(a); }
 void launch_sweep(const SweepArgs& a, cudaStream_t st) { k_sweep<<<(a.pool.cap + 255) / 256, 256, 0, st>>>(a); }
 void launch_merge_free(const Pool& p, cudaStream_t st) { k_merge_free<<<1, 1024, 0, st>>>(p); }

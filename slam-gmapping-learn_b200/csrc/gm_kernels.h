@@ -40,6 +40,7 @@ struct RegisterArgs {
     Pool pool;
     Counters* counters;
     int bitmap_words, sort_n;
+    int tile_cap;  // visit-count tiles (active patches) per pass of the free-space update
 };
 struct RemapArgs {
     const unsigned* idx;
@@ -59,9 +60,9 @@ void launch_scanmatch(const ScanMatchArgs& a, unsigned n, cudaStream_t st);
 void launch_bounds(const BoundsArgs& a, unsigned n, unsigned threads, cudaStream_t st);
 void launch_relayout(const RelayoutArgs& a, unsigned n, cudaStream_t st);
 void launch_relayout_commit(const RelayoutArgs& a, unsigned n, cudaStream_t st);
-size_t register_smem_bytes(int bitmap_words, int sort_n);
+size_t register_smem_bytes(int bitmap_words, int sort_n, int nbeams, int tile_cap);
 cudaError_t register_prepare(size_t smem);
-void launch_register(const RegisterArgs& a, unsigned n, unsigned threads, size_t smem, cudaStream_t st);
+void launch_register(const RegisterArgs& a, unsigned n, size_t smem, cudaStream_t st);
 void launch_remap(const RemapArgs& a, unsigned n, cudaStream_t st);
 void launch_sweep(const SweepArgs& a, cudaStream_t st);
 void launch_merge_free(const Pool& p, cudaStream_t st);
@@ -71,6 +72,7 @@ void launch_fill_geom(Geom* g, unsigned n, Geom v, cudaStream_t st);
 void launch_normalize(const double* logw, unsigned n, double gain, double* w, double* neff, cudaStream_t st);
 void launch_resample(const double* w, unsigned n, double u01, double* cum, double* tgt, unsigned* idx, unsigned* emitted, cudaStream_t st);
 void launch_digest(const DigestArgs& a, unsigned n, cudaStream_t st);
+void launch_export_occupancy(const int* dirp, Geom g, const int4* pool, double occ_thresh, signed char* out, int width, int height, cudaStream_t st);
 void launch_release_particle(int* dirp, int nent, const Pool& pool, cudaStream_t st);
 void launch_install_patches(int* dirp, Geom g, const int* coords, const int4* staged, const Pool& pool, Counters* ctr, int n, cudaStream_t st);
 void launch_export_list(const int* dirp, Geom g, int* list, int* count, cudaStream_t st);

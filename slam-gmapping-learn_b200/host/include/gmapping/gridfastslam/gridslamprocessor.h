@@ -132,6 +132,9 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
         double msScanMatch, msWeights, msRemap, msRegister, msMigrate, msAllGather;
         unsigned long long beamEvals, scoreEvals, cowCopies, patchAllocs, freeUpdates, hitUpdates, poolInUse, launches;
         unsigned long long migratedParticles, migratedBytes;
+        // wall clock of the host-side parts of the last processScan (ms): motion model, scanMatch call incl. transfers,
+        // both updateTreeWeights (normalize on the GPU + tree propagation), resample call incl. registration
+        double msHostMotion, msHostScanMatch, msHostTreeWeights, msHostResample;
     };
     DeviceStats deviceStats() const;
     // Multi-GPU sharding (call before init): this process is rank `rank` of `world`, one GPU each; ncclId is the 128-byte
@@ -190,6 +193,7 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     unsigned char m_ncclId[128];
     unsigned int m_firstLocal, m_localCount;
     unsigned int m_treeEpoch;
+    double m_hostMs[4];
     std::vector<double> m_poseBuf, m_scoreBuf, m_likBuf;
 };
 

@@ -92,13 +92,15 @@ void gmh_indexes(void* hv, unsigned* out) {
     if (!idx.empty()) memcpy(out, idx.data(), sizeof(unsigned) * idx.size());
 }
 
+// out[20]: ... then msHostMotion msHostScanMatch msHostTreeWeights msHostResample
 // out[16]: msScanMatch msWeights msRemap msRegister msMigrate msAllGather beamEvals scoreEvals cowCopies patchAllocs freeUpdates
 //          hitUpdates poolInUse launches migratedParticles migratedBytes
 void gmh_device_stats(void* hv, double* out) {
     const GridSlamProcessor::DeviceStats d = static_cast<Handle*>(hv)->gsp->deviceStats();
-    const double v[16] = {d.msScanMatch, d.msWeights, d.msRemap, d.msRegister, d.msMigrate, d.msAllGather, (double)d.beamEvals, (double)d.scoreEvals,
+    const double v[20] = {d.msScanMatch, d.msWeights, d.msRemap, d.msRegister, d.msMigrate, d.msAllGather, (double)d.beamEvals, (double)d.scoreEvals,
                           (double)d.cowCopies, (double)d.patchAllocs, (double)d.freeUpdates, (double)d.hitUpdates, (double)d.poolInUse,
-                          (double)d.launches, (double)d.migratedParticles, (double)d.migratedBytes};
+                          (double)d.launches, (double)d.migratedParticles, (double)d.migratedBytes,
+                          d.msHostMotion, d.msHostScanMatch, d.msHostTreeWeights, d.msHostResample};
     memcpy(out, v, sizeof v);
 }
 

@@ -17,11 +17,25 @@
 #include <set>
 #include <string>
 
+#include <chrono>
+
 #include "devicemap.h"
 
 namespace GMapping {
 
 using std::endl;
+
+namespace {
+struct Stopwatch {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double lap() {
+        const std::chrono::steady_clock::time_point t1 = std::chrono::steady_clock::now();
+        const double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        t0 = t1;
+        return ms;
+    }
+};
+}  // namespace
 
 static const double kOdometryJumpWarning = 20;  // metres between two readings (reference: gridslamprocessor.cpp:17)
 
@@ -355,9 +369,12 @@ bool GridSlamProcessor::processScan(const RangeReading& reading, int adaptPartic
     const OrientedPoint relPose = reading.getPose();
     if (!m_count) m_lastPartPose = m_odoPose = relPose;
 
+    Stopwatch sw;
+    m_hostMs[0] = m_hostMs[1] = m_hostMs[2] = m_hostMs[3] = 0;
     // motion model: every reading, every particle, in order -- this is where the drand48 stream advances
     for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it)
         it->pose = m_motionModel.drawFromMotion(it->pose, relPose, m_odoPose);
+    m_hostMs[0] = sw.lap();
 
     if (m_outputStream.is_open()) {
         m_outputStream << std::setiosflags(std::ios::fixed) << std::setprecision(6);
@@ -399,7 +416,9 @@ bool GridSlamProcessor::processScan(const RangeReading& reading, int adaptPartic
         RangeReading* readingCopy = new RangeReading(reading.size(), &(reading[0]), static_cast<const RangeSensor*>(reading.getSensor()), reading.getTime());
 
         if (m_count > 0) {
+            sw.lap();
             scanMatch(plain.data());
+            m_hostMs[1] = sw.lap();
             if (m_outputStream.is_open()) {
                 m_outputStream << "LASER_READING " << reading.size() << " ";
                 m_outputStream << std::setiosflags(std::ios::fixed) << std::setprecision(2);
@@ -415,13 +434,17 @@ bool GridSlamProcessor::processScan(const RangeReading& reading, int adaptPartic
                 m_outputStream << endl;
             }
             onScanmatchUpdate();
+            sw.lap();
             updateTreeWeights(false);
+            m_hostMs[2] += sw.lap();
             if (m_infoStream) m_infoStream << "neff= " << m_neff << endl;
             if (m_outputStream.is_open()) {
                 m_outputStream << std::setiosflags(std::ios::fixed) << std::setprecision(6);
                 m_outputStream << "NEFF " << m_neff << endl;
             }
+            sw.lap();
             resample(plain.data(), adaptParticles, readingCopy);
+            m_hostMs[3] = sw.lap();
         } else {
             if (m_infoStream) m_infoStream << "Registering First Scan" << endl;
             for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it) {
@@ -431,7 +454,9 @@ bool GridSlamProcessor::processScan(const RangeReading& reading, int adaptPartic
             }
             registerAll(plain.data(), 0);
         }
+        sw.lap();
         updateTreeWeights(false);
+        m_hostMs[2] += sw.lap();
         m_lastPartPose = m_odoPose;
         m_linearDistance = 0;
         m_angularDistance = 0;
@@ -512,6 +537,7 @@ GridSlamProcessor::DeviceStats GridSlamProcessor::deviceStats() const {
     d.msScanMatch = s.ms_scanmatch; d.msWeights = s.ms_weights; d.msRemap = s.ms_remap; d.msRegister = s.ms_register;
     d.beamEvals = s.beam_evals; d.scoreEvals = s.score_evals; d.cowCopies = s.cow_copies; d.patchAllocs = s.patch_allocs;
     d.freeUpdates = s.free_updates; d.hitUpdates = s.hit_updates; d.poolInUse = s.pool_in_use; d.launches = s.launches;
+    d.msHostMotion = m_hostMs[0]; d.msHostScanMatch = m_hostMs[1]; d.msHostTreeWeights = m_hostMs[2]; d.msHostResample = m_hostMs[3];
     d.msMigrate = s.ms_migrate; d.msAllGather = s.ms_allgather; d.migratedParticles = s.migrated_particles; d.migratedBytes = s.migrated_bytes;
     return d;
 }

@@ -243,3 +243,24 @@ def test_errors_are_loud():
     with pytest.raises(gm.GmError):
         ctx.set_laser(np.zeros(2048))  # beams must be < 2048 (reference asserts, scanmatcher.cpp:704)
     ctx.close()
+
+
+def test_occupancy_export_and_standalone_optimize():
+    """gm_export_occupancy (the ROS wrapper's grid fill, slam_gmapping.cpp:956-993) and gm_optimize against the oracle."""
+    log, m, ctx, maps, poses, rng = _random_world(5, beams=181, particles=3, scans=4)
+    grid = ctx.occupancy_grid(1, 0.25)
+    coords, cells = maps[1].export()
+    sx2, sy2, npx, npy = maps[1].geometry()
+    want = np.full((npy * 32, npx * 32), -1, dtype=np.int8)
+    for (px, py), c in zip(coords, cells):
+        c = c.reshape(32, 32)  # [lx, ly]
+        v = np.where(c["visits"] == 0, -1, np.where(c["n"] / np.maximum(c["visits"], 1) > 0.25, 100, 0)).astype(np.int8)
+        want[py * 32:(py + 1) * 32, px * 32:(px + 1) * 32] = v.T
+    assert grid.shape == want.shape and np.array_equal(grid, want)
+    assert (grid == 100).sum() > 50 and (grid == 0).sum() > 1000
+    init = poses + rng.normal(0, [0.05, 0.05, 0.02], size=poses.shape)
+    out, sc = ctx.optimize(np.arange(3, dtype=np.uint32), init, log.ranges[-1])
+    for j in range(3):
+        so, po = orc.optimize(m, maps[j], init[j], log.ranges[-1])
+        assert abs(sc[j] - so) <= TIGHT * max(1.0, abs(so)) and np.abs(out[j] - po).max() <= TIGHT
+    ctx.close()
