@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -126,6 +127,20 @@ inline void derive_params(DevParams& P) {
     P.cexp = -1. / gs;
     P.clik = -1. / ls;
     P.no_hit = -.5 / ls;
+    const double offs[2] = {P.free_off_score, P.free_off_lik}, cen[2] = {P.cx, P.cy};
+    for (int m = 0; m < 2; m++) {
+        bool constant = true;
+        int q[2] = {0, 0};
+        for (int ax = 0; ax < 2; ax++) {
+            // the computed difference pfree - phit can exceed free_off by rounding errors of the two sums: 1e-9 m of slack
+            const volatile double lo = (-(offs[m] + 1e-9) - cen[ax]) / delta, hi = ((offs[m] + 1e-9) - cen[ax]) / delta;
+            const double rl = round(lo), rh = round(hi);
+            if (rl != rh || !(fabs(rl) < 1e9)) constant = false;
+            q[ax] = (int)rl;
+        }
+        P.free_q[m][0] = constant ? q[0] : INT_MIN;
+        P.free_q[m][1] = constant ? q[1] : 0;
+    }
 }
 
 inline int prepare_scanmatch(gm_ctx* ctx) {

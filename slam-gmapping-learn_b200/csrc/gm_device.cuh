@@ -37,6 +37,10 @@ struct DevParams {
     double cexp;            // -1. / gaussianSigma (scanmatcher.h:257,368)
     double clik;            // -1. / likelihoodSigma (scanmatcher.h:375)
     double no_hit;          // nullLikelihood / likelihoodSigma, nullLikelihood = -.5 (scanmatcher.cpp:15, scanmatcher.h:288)
+    // world2map(pfree - phit) minus sizeX2/Y2 when it is the same for every beam ([0] score, [1] likelihoodAndScore; [.][0] x,
+    // [.][1] y), INT_MIN in [.][0] when it is not: |pfree - phit| <= free_off, so round((d - c) / delta) is constant as soon
+    // as it agrees at d = -free_off and d = +free_off (the map from d to the index is monotone)
+    int free_q[2][2];
 };
 
 struct Counters {  // zeroed per stage, read back by the host

@@ -58,6 +58,9 @@ __device__ __forceinline__ int cell_index(double d, double delta, double inv_del
     return i;
 }
 
+constexpr int kSmThreads = 256;
+constexpr int kSmGroups = kSmThreads / 6;  // 42 beam groups x 6 candidate poses = 252 working threads
+
 struct MatchCtx {
     const int* __restrict__ dirp;
     const int4* __restrict__ pool;
@@ -82,8 +85,9 @@ template <bool DEF> __device__ __forceinline__ bool is_free(int n, int v, const 
 // `free_off` is delta*freeDelta for score() and freeDelta for likelihoodAndScore().
 // K1: kernelSize 1 and fullnessThreshold 0.1 (the defaults) -> specialised, branch-light window code
 template <bool K1>
+// (fqx, fqy): the beam-independent free-cell index offset when it exists (see derive_params), else fqx == INT_MIN
 __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M, double lpx, double lpy, double r, double c, double s,
-                                           double free_off, double& bmx, double& bmy) {
+                                           double free_off, int fqx, int fqy, unsigned* ci_smem, double& bmx, double& bmy) {
     const Geom& g = M.g;
     const double phx = lpx + r * c, phy = lpy + r * s;
     const int ihx = cell_index(phx - P.cx, P.delta, P.inv_delta) + g.sx2;
@@ -94,53 +98,71 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
     double bx = 0., by = 0., bn = 0.;
 
     if (K1) {
-        // ---- the 3x3 window spans at most 2x2 patches: four directory entries, unknown ones mapped to the
-        // all-zero patch, then nine independent 4-byte loads of n issued together
-        const int pxa = x0 >> kPatchMag, pya = y0 >> kPatchMag, pxb = x1 >> kPatchMag, pyb = y1 >> kPatchMag;
-        const int ida = dir_at(M, pxa, pya);
-        const int idb = pyb != pya ? dir_at(M, pxa, pyb) : ida;
-        const int idc = pxb != pxa ? dir_at(M, pxb, pya) : ida;
-        const int idd = pxb != pxa ? (pyb != pya ? dir_at(M, pxb, pyb) : idc) : idb;
-        if ((ida & idb & idc & idd) < 0) return false;  // every patch unknown: nothing can match
-        const unsigned ea = (unsigned)(ida < 0 ? M.zero_patch : ida) << 10, eb = (unsigned)(idb < 0 ? M.zero_patch : idb) << 10;
-        const unsigned ec = (unsigned)(idc < 0 ? M.zero_patch : idc) << 10, ed = (unsigned)(idd < 0 ? M.zero_patch : idd) << 10;
-        const int nxa = ((pxa + 1) << kPatchMag) - x0, nya = ((pya + 1) << kPatchMag) - y0;  // rows / columns inside patch a
+        // ---- 3x3 window.  Cell indexes (patch * 1024 + cell) of the nine cells: when no lane of the warp has a
+        // window that straddles a patch edge, one directory entry and constant offsets; otherwise the window spans
+        // at most 2x2 patches: four entries, unknown ones mapped to the all-zero patch.
         unsigned ci[9];
+        const bool single = x0 >= 0 && y0 >= 0 && (x0 >> kPatchMag) == (x1 >> kPatchMag) && (y0 >> kPatchMag) == (y1 >> kPatchMag);
+        if (__all_sync(__activemask(), single)) {
+            const int id = dir_at(M, x0 >> kPatchMag, y0 >> kPatchMag);
+            if (id < 0) return false;
+            const unsigned base = ((unsigned)id << 10) + ((unsigned)(x0 & 31) << kPatchMag) + (unsigned)(y0 & 31);
 #pragma unroll
-        for (int xx = 0; xx < 3; xx++) {
-            const unsigned rowoff = (unsigned)((x0 + xx) & 31) << kPatchMag;
-            const unsigned ra = (xx < nxa ? ea : ec) + rowoff, rb = (xx < nxa ? eb : ed) + rowoff;
+            for (int i = 0; i < 9; i++) ci[i] = base + (unsigned)(((i / 3) << kPatchMag) + (i % 3));
+        } else {
+            const int pxa = x0 >> kPatchMag, pya = y0 >> kPatchMag, pxb = x1 >> kPatchMag, pyb = y1 >> kPatchMag;
+            const int ida = dir_at(M, pxa, pya);
+            const int idb = pyb != pya ? dir_at(M, pxa, pyb) : ida;
+            const int idc = pxb != pxa ? dir_at(M, pxb, pya) : ida;
+            const int idd = pxb != pxa ? (pyb != pya ? dir_at(M, pxb, pyb) : idc) : idb;
+            if ((ida & idb & idc & idd) < 0) return false;  // every patch unknown: nothing can match
+            const unsigned ea = (unsigned)(ida < 0 ? M.zero_patch : ida) << 10, eb = (unsigned)(idb < 0 ? M.zero_patch : idb) << 10;
+            const unsigned ec = (unsigned)(idc < 0 ? M.zero_patch : idc) << 10, ed = (unsigned)(idd < 0 ? M.zero_patch : idd) << 10;
+            const int nxa = ((pxa + 1) << kPatchMag) - x0, nya = ((pya + 1) << kPatchMag) - y0;  // rows / columns inside patch a
 #pragma unroll
-            for (int yy = 0; yy < 3; yy++) ci[3 * xx + yy] = (yy < nya ? ra : rb) + (unsigned)((y0 + yy) & 31);
+            for (int xx = 0; xx < 3; xx++) {
+                const unsigned rowoff = (unsigned)((x0 + xx) & 31) << kPatchMag;
+                const unsigned ra = (xx < nxa ? ea : ec) + rowoff, rb = (xx < nxa ? eb : ed) + rowoff;
+#pragma unroll
+                for (int yy = 0; yy < 3; yy++) ci[3 * xx + yy] = (yy < nya ? ra : rb) + (unsigned)((y0 + yy) & 31);
+            }
         }
-        int nn9[9];
+        // nine independent 8-byte loads of (n, visits), issued together; occupancy decided in exact integers
+        int2 nv[9];
 #pragma unroll
-        for (int i = 0; i < 9; i++) nn9[i] = __ldg(reinterpret_cast<const int*>(M.pool + ci[i]) + 2);
+        for (int i = 0; i < 9; i++) nv[i] = __ldg(reinterpret_cast<const int2*>(M.pool + ci[i]) + 1);
         unsigned mask = 0;
 #pragma unroll
-        for (int i = 0; i < 9; i++) mask |= nn9[i] != 0 ? 1u << i : 0u;  // n == 0: free or unknown, never "occupied"
+        for (int i = 0; i < 9; i++) mask |= (10ll * nv[i].x > (long long)nv[i].y) ? 1u << i : 0u;  // n/visits > 0.1 (implies visits > 0)
         if (!mask) return false;
-        // free window (the reference's `ipfree` quirk: world2map applied to the difference pfree - phit)
-        const double pfx = (lpx + (r - free_off) * c) - phx, pfy = (lpy + (r - free_off) * s) - phy;
-        const int ifx = cell_index(pfx - P.cx, P.delta, P.inv_delta) + g.sx2;
-        const int ify = cell_index(pfy - P.cy, P.delta, P.inv_delta) + g.sy2;
+        // free window (the reference's `ipfree` quirk: world2map applied to the difference pfree - phit).  |pfree - phit|
+        // <= free_off, so for score() the index is the same for every beam and comes precomputed in (fqx, fqy)
+        int ifx, ify;
+        if (fqx != INT_MIN) { ifx = fqx + g.sx2; ify = fqy + g.sy2; }
+        else {
+            const double pfx = (lpx + (r - free_off) * c) - phx, pfy = (lpy + (r - free_off) * s) - phy;
+            ifx = cell_index(pfx - P.cx, P.delta, P.inv_delta) + g.sx2;
+            ify = cell_index(pfy - P.cy, P.delta, P.inv_delta) + g.sy2;
+        }
         const int fx0 = x0 + ifx, fy0 = y0 + ify, fx1 = x1 + ifx, fy1 = y1 + ify;
         bool fcheck = true;  // false: every free cell of this window is unknown, i.e. passes
         if (fx1 < 0 || fy1 < 0 || (fx0 >> kPatchMag) >= g.npx || (fy0 >> kPatchMag) >= g.npy) fcheck = false;
         else if (fx0 >= 0 && fy0 >= 0 && (fx0 >> kPatchMag) == (fx1 >> kPatchMag) && (fy0 >> kPatchMag) == (fy1 >> kPatchMag) &&
                  dir_at(M, fx0 >> kPatchMag, fy0 >> kPatchMag) < 0) fcheck = false;
-        while (mask) {  // ascending bit order == the reference's xx-outer / yy-inner scan order
+        // occupied cells in ascending bit order == the reference's xx-outer / yy-inner scan order; the nine cell
+        // indexes wait in shared memory (one column per thread) so that the loop can pick them by a run-time index
+#pragma unroll
+        for (int i = 0; i < 9; i++) ci_smem[i * kSmThreads] = ci[i];
+        while (mask) {
             const int i = __ffs(mask) - 1;
             mask &= mask - 1;
-            const int xx = (i * 11) >> 5, yy = i - 3 * xx;  // i / 3 for i < 9
-            const unsigned e = xx < nxa ? (yy < nya ? ea : eb) : (yy < nya ? ec : ed);
-            const int4 cell = __ldg(M.pool + (e + ((unsigned)((x0 + xx) & 31) << kPatchMag) + (unsigned)((y0 + yy) & 31)));
-            if (!is_occ<true>(cell.z, cell.w, P)) continue;
             if (fcheck) {
+                const int xx = (i * 11) >> 5, yy = i - 3 * xx;  // i / 3, i % 3 for i < 9
                 long long fi; int fn = 0, fv = 0;
                 if (cell_addr(g, M.dirp, x0 + xx + ifx, y0 + yy + ify, fi)) { const int4 f = __ldg(M.pool + fi); fn = f.z; fv = f.w; }
                 if (!is_free<true>(fn, fv, P)) continue;
             }
+            const int4 cell = __ldg(M.pool + ci_smem[i * kSmThreads]);
             const double inv = cell.z < kInvTable ? __ldg(M.inv_n + cell.z) : recip_slow(cell.z);  // mean() = (1./n) * acc, smmap.h:24
             const double mx = phx - (double)__int_as_float(cell.x) * inv, my = phy - (double)__int_as_float(cell.y) * inv;
             const double nn = mx * mx + my * my;
@@ -215,8 +237,6 @@ __device__ __forceinline__ bool beam_selected(const DevParams& P, unsigned b) {
     return P.lskip == 0u || ((b - P.beam_skip + 1u) % (P.lskip + 1u)) == 0u;
 }
 
-constexpr int kSmThreads = 256;
-constexpr int kSmGroups = kSmThreads / 6;  // 42 beam groups x 6 candidate poses = 252 working threads
 
 struct SmShared {
     // plan of the next evaluation step (thread 0 writes, everybody reads after a barrier)
@@ -282,6 +302,7 @@ template <bool K1>
 __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SmShared S;
+    __shared__ unsigned S_ci[9 * kSmThreads];  // window cell indexes, column t belongs to thread t
     const DevParams& P = A.P;
     double2* const tabs = reinterpret_cast<double2*>(smem_raw);
     const unsigned q = blockIdx.x, p = A.query >= 0 ? A.particle_idx[q] : q;
@@ -333,6 +354,7 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
             const double2* tab = tabs + (size_t)S.tab_of[m < 4 ? 0 : m - 3] * P.nbeams;
             // pfree offset: map.getDelta()*freeDelta in score() (scanmatcher.h:208), freeDelta in likelihoodAndScore() (:320)
             const double free_off = mode ? P.free_off_lik : P.free_off_score;
+            const int fqx = P.free_q[mode][0], fqy = P.free_q[mode][1];
             const double cexp = P.cexp, clik = P.clik, noHit = P.no_hit;
             for (unsigned b = P.beam_skip + grp; b < P.nbeams; b += ngroups) {
                 const double r = __ldg(A.ranges + b);
@@ -341,7 +363,7 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
                 const double2 cs = tab[b];
                 double mx, my;
                 valid++;
-                const bool found = beam_match<K1>(P, M, mlx, mly, r, cs.x, cs.y, free_off, mx, my);
+                const bool found = beam_match<K1>(P, M, mlx, mly, r, cs.x, cs.y, free_off, fqx, fqy, S_ci + t, mx, my);
                 if (found) { acc_s += exp((mx * cexp) * mx + (my * cexp) * my); cnt++; }  // ((-1/sigma)*mu)*mu, point.h:34-49
                 if (mode) { const double f = clik * (mx * mx + my * my); acc_l += found ? f : noHit; }
             }
