@@ -88,6 +88,9 @@ typedef struct gm_stats {
     uint64_t migrated_particles, migrated_bytes; /* last gm_dist_register: imported parents, bytes received */
     uint32_t launches;        /* kernels launched by this context since gm_create */
     uint32_t reserved;
+    /* last gm_register: SM cycles summed over CTAs per phase of k_register (beam setup, ray marking, ranks, copy-on-write,
+     * ray counting, tile flush, hit sort, hit accumulation) */
+    uint64_t register_phase_cycles[8];
 } gm_stats;
 
 int gm_create(gm_ctx** out, const gm_config* cfg);

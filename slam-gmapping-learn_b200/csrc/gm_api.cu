@@ -409,6 +409,7 @@ int gmi_register_update(gm_ctx* ctx) {
     ctx->stats.free_updates = h.free_updates; ctx->stats.hit_updates = h.hit_updates; ctx->stats.resizes = h.resizes;
     ctx->stats.pool_in_use = (uint64_t)(ctx->pool.cap - top);
     ctx->reg_active_hint = h.max_active;
+    for (int k = 0; k < 8; k++) ctx->stats.register_phase_cycles[k] = h.reg_phase[k];
     if (h.error == GM_ERR_POOL) return fail(ctx, GM_ERR_POOL, "gm_register: patch pool of %d patches exhausted", ctx->pool.cap);
     if (h.error) return fail(ctx, h.error, "gm_register: device-side error %d", h.error);
     return GM_OK;

@@ -49,6 +49,9 @@ struct Counters {  // zeroed per stage, read back by the host
     int need_dir_cap;   // largest npx*npy any particle needs (k_bounds)
     int any_resize;
     int max_active;     // largest active-patch count of a particle (k_register)
+    // k_register: SM cycles summed over CTAs per phase (beam setup, ray marking, ranks, copy-on-write, ray counting,
+    // tile flush, hit sort, hit accumulation) -- a profiling aid read through gm_stats
+    unsigned long long reg_phase[8];
 };
 
 struct Pool {

@@ -559,26 +559,41 @@ __global__ void k_relayout_commit(RelayoutArgs A) {
 //   3. visits++ along the rays (scanmatcher.cpp:317-325); integer atomics commute, so the counts are bit-exact;
 //   4. endpoint hits (scanmatcher.cpp:327-334): float `acc` is order dependent, so hits are sorted by
 //      (cell, beam) and each cell's run is accumulated sequentially in beam order by one thread.
-// Ray walks (1 and 3): a thread owns a ray and steps the reference's Bresenham incrementally, looking the patch up
-// again only when the cell leaves it; neighbouring lanes walk neighbouring beams, i.e. rays of similar length.
+// Ray walks (1 and 3): rays are cut into work items of 32 cells; a thread starts its item from the closed form of the
+// reference's Bresenham state and steps incrementally, looking the patch up again only when the cell leaves it.
 struct BeamRec { int p1x, p1y; float hx, hy; int flags; };  // flags: 1 = ray is traced, 2 = endpoint is a hit
 
-// visit every cell of the line p0 -> p1 except p1 itself, walking the reference's Bresenham (gridlinetraversal.h:20-108:
-// major axis upward from the lower endpoint) step by step in ONE thread; f(x, y, px, py, enteredNewPatch)
+constexpr int kRayChunk = 32;  // cells per work item of a ray walk
+
+// number of cells visited on the line p0 -> p1: every point but p1 (scanmatcher.cpp:317-325)
+__device__ __forceinline__ int ray_cells(int p0x, int p0y, int p1x, int p1y) { return max(abs(p1x - p0x), abs(p1y - p0y)); }
+
+// visit chunk `chunk` (kRayChunk cells) of the line p0 -> p1 except p1 itself, following the reference's Bresenham
+// (gridlinetraversal.h:20-108: major axis upward from the lower endpoint): the chunk starts from the closed form of the
+// walk's state and then steps incrementally; f(x, y, px, py, enteredNewPatch)
 template <class F>
-__device__ __forceinline__ void walk_ray(int p0x, int p0y, int p1x, int p1y, F f) {
+__device__ __forceinline__ void walk_ray(int p0x, int p0y, int p1x, int p1y, int chunk, F f) {
     const Line L = make_line(p0x, p0y, p1x, p1y);
-    int m = L.n - 1;  // all points but the last one in start->end order, i.e. but p1
-    if (m <= 0) return;
-    int a = L.a_lo, bb = L.b_lo;
-    int d = 2 * L.db - L.da;
-    const int incr1 = 2 * L.db, incr2 = 2 * (L.db - L.da);
-    if (L.from_end) {  // p1 is the LOW end: skip it
-        a++;
-        if (d < 0) d += incr1; else { bb += L.bstep; d += incr2; }
+    const int m = L.n - 1;
+    const int jlo = L.from_end ? 1 : 0;  // p1 is the LOW end when the walk runs from the end: skip it
+    int j = jlo + chunk * kRayChunk;
+    const int jend = min(jlo + m, j + kRayChunk);
+    if (j >= jend) return;
+    // state after j steps of the reference's loop: a = a_lo + j, b = b_lo + bstep * inc(j), d = 2db(j+1) - da - 2da*inc(j),
+    // inc(j) = floor((2 db j + da) / (2 da))
+    int inc = 0;
+    if (j && L.da) {
+        const unsigned num = 2u * (unsigned)L.db * (unsigned)j + (unsigned)L.da, den = 2u * (unsigned)L.da;
+        int q = (int)((double)num * (1.0 / (double)den));  // exact after the one-step correction below
+        const long long rem = (long long)num - (long long)q * den;
+        q += rem >= (long long)den ? 1 : (rem < 0 ? -1 : 0);
+        inc = q;
     }
+    int a = L.a_lo + j, bb = L.b_lo + L.bstep * inc;
+    int d = 2 * L.db * (j + 1) - L.da - 2 * L.da * inc;
+    const int incr1 = 2 * L.db, incr2 = 2 * (L.db - L.da);
     int lpx = INT_MIN, lpy = INT_MIN;
-    for (; m > 0; m--) {
+    for (; j < jend; j++) {
         const int x = L.steep ? bb : a, y = L.steep ? a : bb;
         const int px = x >> kPatchMag, py = y >> kPatchMag;
         const bool np = px != lpx || py != lpy;
@@ -589,13 +604,13 @@ __device__ __forceinline__ void walk_ray(int p0x, int p0y, int p1x, int p1y, F f
     }
 }
 
-constexpr int kRegThreads = 512;
+constexpr int kRegThreads = 1024;
 constexpr int kTileWords = kPatchCells / 2;  // a tile counts visits of one patch: 1024 cells x 16 bit, two per word
 
 // dynamic shared memory of k_register (see register_smem_bytes): active-patch bitmap over the directory, its
 // running popcount per word, sort keys of the hits, per-beam records, visit-count tiles
 struct RegSmem {
-    unsigned* active; unsigned short* prefix; unsigned long long* keys; BeamRec* rec; unsigned* tiles;
+    unsigned* active; unsigned short* prefix; unsigned long long* keys; BeamRec* rec; int* items; unsigned* tiles;
 };
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 __device__ __forceinline__ RegSmem carve(unsigned char* raw, int bitmap_words, int sort_n, int nbeams) {
@@ -605,6 +620,7 @@ __device__ __forceinline__ RegSmem carve(unsigned char* raw, int bitmap_words, i
     m.prefix = reinterpret_cast<unsigned short*>(raw + o); o += align16((size_t)bitmap_words * 2);
     m.keys = reinterpret_cast<unsigned long long*>(raw + o); o += (size_t)sort_n * 8;
     m.rec = reinterpret_cast<BeamRec*>(raw + o); o += align16((size_t)nbeams * sizeof(BeamRec));
+    m.items = reinterpret_cast<int*>(raw + o); o += align16((size_t)(nbeams + 1) * 4);
     m.tiles = reinterpret_cast<unsigned*>(raw + o);
     return m;
 }
@@ -625,6 +641,8 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
     __shared__ int s_nactive;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 
+    long long tph = clock64();
+#define PHASE(k) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&A.counters->reg_phase[k], (unsigned long long)(now_ - tph)); tph = now_; } } while (0)
     for (int i = threadIdx.x; i < nwords; i += blockDim.x) active[i] = 0u;
     for (int i = threadIdx.x; i < A.sort_n; i += blockDim.x) keys[i] = ~0ull;
     if (threadIdx.x == 0) { s_free = 0; s_hit = 0; s_cow = 0; s_alloc = 0; }
@@ -660,14 +678,31 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
             }
         }
         rec[b] = R;
+        M.items[b + 1] = (R.flags & 1) ? (ray_cells(p0x, p0y, R.p1x, R.p1y) + kRayChunk - 1) / kRayChunk : 0;
     }
     __syncthreads();
+    // work items of the ray walks: items[b] .. items[b+1] are beam b's chunks (inclusive scan by one warp)
+    if (warp == 0) {
+        int run = 0;
+        for (unsigned b0 = 0; b0 < P.nbeams; b0 += 32) {
+            const unsigned b = b0 + lane;
+            int v = b < P.nbeams ? M.items[b + 1] : 0;
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+            if (b < P.nbeams) M.items[b + 1] = run + v;
+            run += __shfl_sync(0xffffffffu, v, 31);
+        }
+        if (lane == 0) M.items[0] = 0;
+    }
+    __syncthreads();
+    const int nitems = M.items[P.nbeams];
+    PHASE(0);
 
     // ---- 1. active area: patches under the rays
-    for (unsigned b = threadIdx.x; b < P.nbeams; b += blockDim.x) {
-        const BeamRec R = rec[b];
-        if (!(R.flags & 1)) continue;
-        walk_ray(p0x, p0y, R.p1x, R.p1y, [&](int, int, int px, int py, bool np) {
+    for (int it = threadIdx.x; it < nitems; it += blockDim.x) {
+        int lo = 0, hi = (int)P.nbeams - 1;  // the beam whose chunk range holds item `it`
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (M.items[mid] <= it) lo = mid; else hi = mid - 1; }
+        const BeamRec R = rec[lo];
+        walk_ray(p0x, p0y, R.p1x, R.p1y, it - M.items[lo], [&](int, int, int px, int py, bool np) {
             if (np && (unsigned)px < (unsigned)g.npx && (unsigned)py < (unsigned)g.npy) {
                 const int e = px * g.npy + py;
                 atomicOr(&active[e >> 5], 1u << (e & 31));
@@ -675,6 +710,7 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
         });
     }
     __syncthreads();
+    PHASE(1);
 
     // ---- 1b. rank of every active patch: prefix[w] = number of active patches in words < w
     {
@@ -694,6 +730,7 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
     }
     __syncthreads();
     const int nactive = s_nactive;
+    PHASE(2);
 
     // ---- 2. copy-on-write: a warp per active patch
     for (int wi = warp; wi < nwords; wi += nw) {
@@ -704,7 +741,7 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
             int id = dirp[e], nid = id, mode = 0;  // 0 keep, 1 zero-fill new, 2 copy
             if (lane == 0) {
                 if (id < 0) { nid = pool_alloc(A.pool, A.counters); mode = 1; }
-                else if (atomicAdd(&A.pool.refcnt[id], 0) > 1) { nid = pool_alloc(A.pool, A.counters); mode = 2; }
+                else if (__ldcg(A.pool.refcnt + id) > 1) { nid = pool_alloc(A.pool, A.counters); mode = 2; }
             }
             nid = __shfl_sync(0xffffffffu, nid, 0); mode = __shfl_sync(0xffffffffu, mode, 0);
             if (mode == 0 || nid < 0) continue;
@@ -731,6 +768,7 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
     }
     __threadfence();
     __syncthreads();
+    PHASE(3);
 
     // ---- 3. free-space updates (scanmatcher.cpp:317-325).  visits++ is counted per cell in shared-memory tiles
     // (16-bit counters: a cell is crossed by at most nbeams < 2048 rays), `tile_cap` active patches per pass, then
@@ -740,11 +778,12 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
         const int ntile = min(A.tile_cap, nactive - first);
         for (int i = threadIdx.x; i < ntile * kTileWords; i += blockDim.x) M.tiles[i] = 0u;
         __syncthreads();
-        for (unsigned b = threadIdx.x; b < P.nbeams; b += blockDim.x) {
-            const BeamRec R = rec[b];
-            if (!(R.flags & 1)) continue;
+        for (int it = threadIdx.x; it < nitems; it += blockDim.x) {
+            int lo = 0, hi = (int)P.nbeams - 1;
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (M.items[mid] <= it) lo = mid; else hi = mid - 1; }
+            const BeamRec R = rec[lo];
             unsigned* tile = nullptr;  // counters of the current patch, null when it is not in this pass / outside the map
-            walk_ray(p0x, p0y, R.p1x, R.p1y, [&](int x, int y, int px, int py, bool np) {
+            walk_ray(p0x, p0y, R.p1x, R.p1y, it - M.items[lo], [&](int x, int y, int px, int py, bool np) {
                 if (np) {
                     tile = nullptr;
                     if ((unsigned)px < (unsigned)g.npx && (unsigned)py < (unsigned)g.npy) {
@@ -760,6 +799,7 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
             });
         }
         __syncthreads();
+        PHASE(4);
         // flush: a warp per tile; the directory entry of rank first + t is found from the prefix sums
         for (int t = warp; t < ntile; t += nw) {
             const int rank = first + t;
@@ -770,12 +810,23 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
             if (id < 0) continue;
             int* cells = reinterpret_cast<int*>(A.pool.cells + (size_t)id * kPatchCells);
             const unsigned* tile = M.tiles + t * kTileWords;
-            for (int ci = lane; ci < kPatchCells; ci += 32) {
-                const unsigned c = (tile[ci >> 1] >> ((ci & 1) << 4)) & 0xffffu;
-                if (c) { cells[(ci << 2) + 3] += (int)c; nfree += c; }  // update(false) c times: visits += c
+            // eight independent loads in flight per lane: the patch is private, plain read-modify-write
+#pragma unroll 1
+            for (int g8 = 0; g8 < kPatchCells; g8 += 256) {
+                int v[8]; unsigned c[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int ci = g8 + 32 * k + lane;
+                    c[k] = (tile[ci >> 1] >> ((ci & 1) << 4)) & 0xffffu;
+                    v[k] = __ldcg(cells + (ci << 2) + 3);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (c[k]) { cells[((g8 + 32 * k + lane) << 2) + 3] = v[k] + (int)c[k]; nfree += c[k]; }  // update(false) c times
             }
         }
         __syncthreads();
+        PHASE(5);
     }
     __threadfence();
     __syncthreads();
@@ -794,6 +845,7 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
             }
         }
     __syncthreads();
+    PHASE(6);
     unsigned long long nhit = 0;
     for (int i = threadIdx.x; i < A.sort_n; i += blockDim.x) {
         unsigned long long key = keys[i];
@@ -814,9 +866,13 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
         cell[2] += cnt; cell[3] += cnt;  // the cell belongs to this thread alone now
         nhit += cnt;
     }
-    if (nfree) atomicAdd(&s_free, nfree);
-    if (nhit) atomicAdd(&s_hit, nhit);
+    // statistics: one shared atomic per warp (64-bit shared atomics are CAS loops; a thousand on one address crawl)
+    for (int o = 16; o > 0; o >>= 1) { nfree += __shfl_xor_sync(0xffffffffu, nfree, o); nhit += __shfl_xor_sync(0xffffffffu, nhit, o); }
+    if (lane == 0 && nfree) atomicAdd(&s_free, nfree);
+    if (lane == 0 && nhit) atomicAdd(&s_hit, nhit);
     __syncthreads();
+    PHASE(7);
+#undef PHASE
     if (threadIdx.x == 0) {
         atomicAdd(&A.counters->free_updates, s_free); atomicAdd(&A.counters->hit_updates, s_hit);
         atomicAdd(&A.counters->cow_copies, s_cow); atomicAdd(&A.counters->patch_allocs, s_alloc);
@@ -1031,7 +1087,7 @@ void launch_relayout(const RelayoutArgs& a, unsigned n, cudaStream_t st) { k_rel
 void launch_relayout_commit(const RelayoutArgs& a, unsigned n, cudaStream_t st) { k_relayout_commit<<<n, 256, 0, st>>>(a); }
 size_t register_smem_bytes(int bitmap_words, int sort_n, int nbeams, int tile_cap) {
     return align16((size_t)bitmap_words * 4) + align16((size_t)bitmap_words * 2) + (size_t)sort_n * 8 + align16((size_t)nbeams * sizeof(BeamRec)) +
-           (size_t)tile_cap * kTileWords * 4;
+           align16((size_t)(nbeams + 1) * 4) + (size_t)tile_cap * kTileWords * 4;
 }
 cudaError_t register_prepare(size_t smem) {
     return cudaFuncSetAttribute(k_register, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
