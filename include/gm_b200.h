@@ -178,6 +178,10 @@ int gm_dist_register(gm_ctx* ctx, const double* ranges, const double* poses, con
  * returns the count, fills parents_out (capacity n) -- used by the tests of the host-side logic */
 int gm_dist_plan(uint32_t n_local, int rank, int world, const uint32_t* idx_global, uint32_t* parents_out, uint32_t* local_idx_out);
 
+/* replaces: the map part of GridSlamProcessor's copy constructor / clone(), gridfastslam/gridslamprocessor.cpp:38-97
+ * (SURVEY.md §8 row f3): a second context on the same GPU with identical particle maps (the whole pool is copied). */
+int gm_clone(gm_ctx* src, gm_ctx** out);
+
 int gm_get_stats(gm_ctx* ctx, gm_stats* out);
 uint32_t gm_particles(const gm_ctx* ctx);
 

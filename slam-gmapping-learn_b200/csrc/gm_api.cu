@@ -567,6 +567,47 @@ int gm_map_digest(gm_ctx* ctx, uint32_t first, uint32_t count, gm_digest* out) {
     return GM_OK;
 }
 
+int gm_clone(gm_ctx* src, gm_ctx** out) {
+    if (!src || !out) return GM_ERR_ARG;
+    *out = nullptr;
+    if (src->dist) return fail(src, GM_ERR_ARG, "gm_clone: a sharded context cannot be cloned");
+    if (int r = bind(src)) return r;
+    gm_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.device = src->device; cfg.max_particles = src->max_particles; cfg.pool_patches = (uint64_t)src->pool.cap;
+    cfg.block_threads = src->threads; cfg.global_particles = src->weights_cap;
+    gm_ctx* dst = nullptr;
+    if (int r = gm_create(&dst, &cfg)) return fail(src, r, "gm_clone: %s", gm_last_error(nullptr));
+    dst->P = src->P; dst->laser_set = src->laser_set; dst->match_set = src->match_set;
+    memcpy(dst->angles_h, src->angles_h, sizeof src->angles_h);
+    auto bail = [&](cudaError_t e, const char* what) {
+        gm_destroy(dst);
+        return fail(src, GM_ERR_CUDA, "gm_clone: %s: %s", what, cudaGetErrorString(e));
+    };
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(dst->d_angles, src->d_angles, sizeof(double) * GM_MAXBEAMS, cudaMemcpyDeviceToDevice, src->st)) != cudaSuccess) return bail(e, "angles");
+    if (src->inited) {
+        dst->n = src->n; dst->dir_cap = src->dir_cap; dst->inited = true; dst->reg_active_hint = src->reg_active_hint;
+        const size_t dn = (size_t)src->max_particles * src->dir_cap, cap = (size_t)src->pool.cap;
+        if ((e = dalloc(dst->dir, dn)) != cudaSuccess || (e = dalloc(dst->dir_alt, dn)) != cudaSuccess) return bail(e, "directories");
+        if ((e = dalloc(dst->d_w, dst->weights_cap)) != cudaSuccess || (e = dalloc(dst->d_logw, dst->weights_cap)) != cudaSuccess ||
+            (e = dalloc(dst->d_cum, dst->weights_cap)) != cudaSuccess || (e = dalloc(dst->d_tgt, dst->weights_cap)) != cudaSuccess ||
+            (e = dalloc(dst->d_neff, 1)) != cudaSuccess || (e = dalloc(dst->d_widx, dst->weights_cap)) != cudaSuccess) return bail(e, "weight buffers");
+        // the whole pool is copied (ids stay valid); the clone costs as much HBM as the original
+        struct { void* d; const void* s; size_t bytes; } copies[] = {
+            {dst->pool.cells, src->pool.cells, (cap + 1) * kPatchCells * sizeof(int4)}, {dst->pool.refcnt, src->pool.refcnt, cap * sizeof(int)},
+            {dst->pool.free_list, src->pool.free_list, cap * sizeof(int)}, {dst->pool.free_top, src->pool.free_top, sizeof(int)},
+            {dst->dir, src->dir, dn * sizeof(int)}, {dst->geom, src->geom, sizeof(Geom) * src->max_particles}};
+        for (auto& c : copies)
+            if ((e = cudaMemcpyAsync(c.d, c.s, c.bytes, cudaMemcpyDeviceToDevice, src->st)) != cudaSuccess) return bail(e, "device copy");
+        launch_fill_int(dst->dir_alt, dn, -1, src->st);
+    }
+    if ((e = cudaStreamSynchronize(src->st)) != cudaSuccess) return bail(e, "synchronize");
+    dst->stats = src->stats;
+    *out = dst;
+    return GM_OK;
+}
+
 int gm_get_stats(gm_ctx* ctx, gm_stats* out) {
     if (!ctx || !out) return GM_ERR_ARG;
     *out = ctx->stats;

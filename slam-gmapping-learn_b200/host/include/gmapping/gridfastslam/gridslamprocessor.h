@@ -69,8 +69,7 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
 
     GridSlamProcessor();
     GridSlamProcessor(std::ostream& infoStr);
-    // deep copy of the filter including the trajectory tree (device-side clone is not in this
-    // round; aborts with a message)
+    // deep copy of the filter including the trajectory tree and (device-side) the particle maps
     GridSlamProcessor* clone() const;
     virtual ~GridSlamProcessor();
 
@@ -144,6 +143,11 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     void setDistributed(int rank, int world, const void* ncclId);
     inline unsigned int firstLocalParticle() const { return m_firstLocal; }
     inline unsigned int localParticles() const { return m_localCount; }
+    // occupancy grid of one local particle's map computed on the GPU (what gmapping/src/slam_gmapping.cpp:956-993 fills by
+    // walking smap.cell(p) on the host): data[y * width + x] = -1 unknown, 100 if n/visits > occThresh, else 0;
+    // (originX, originY) = world position of cell (0, 0)
+    void exportOccupancyGrid(unsigned int particle, double occThresh, std::vector<signed char>& data, int& width, int& height,
+                             double& originX, double& originY) const;
     // order-independent digests of the LOCAL particle maps (patches, cells, sum n, sum visits, hash of (cell, n, visits), hash of acc)
     std::vector<unsigned long long> mapDigests() const;
 

@@ -15,6 +15,7 @@ using namespace GMapping;
 namespace {
 struct Counting : public GridSlamProcessor {
     explicit Counting(std::ostream& os) : GridSlamProcessor(os), resamples(0), lastResampled(false) {}
+    Counting(const Counting& o) : GridSlamProcessor(o), resamples(o.resamples), lastResampled(false) {}
     void onResampleUpdate() override { resamples++; lastResampled = true; }
     int resamples;
     bool lastResampled;
@@ -25,6 +26,8 @@ struct Handle {
     RangeSensor* laser;
     SensorMap smap;
     Handle(bool verbose) : devnull("/dev/null"), gsp(new Counting(verbose ? std::cout : devnull)), laser(0) {}
+    // clone: the filter is deep-copied (GridSlamProcessor copy constructor); the sensor is re-created
+    Handle(const Handle& o) : devnull("/dev/null"), gsp(new Counting(*o.gsp)), laser(new RangeSensor(*o.laser)) { smap.insert(std::make_pair(laser->getName(), laser)); }
     ~Handle() { delete gsp; delete laser; }
 };
 }  // namespace
@@ -33,6 +36,7 @@ extern "C" {
 
 void* gmh_create(int verbose) { return new Handle(verbose != 0); }
 void gmh_destroy(void* h) { delete static_cast<Handle*>(h); }
+void* gmh_clone(void* h) { return new Handle(*static_cast<Handle*>(h)); }
 int gmh_dist_unique_id(void* id128) { return gm_dist_unique_id(id128); }
 void gmh_set_distributed(void* h, int rank, int world, const void* id) { static_cast<Handle*>(h)->gsp->setDistributed(rank, world, id); }
 
@@ -108,6 +112,13 @@ void gmh_device_stats(void* hv, double* out) {
 void gmh_map_digests(void* hv, unsigned long long* out) {
     const std::vector<unsigned long long> d = static_cast<Handle*>(hv)->gsp->mapDigests();
     if (!d.empty()) memcpy(out, d.data(), sizeof(unsigned long long) * d.size());
+}
+
+// occupancy grid of one particle on the GPU; data has width*height bytes (query the size first with data == null)
+void gmh_occupancy_grid(void* hv, unsigned particle, double thresh, signed char* data, int* width, int* height, double* origin) {
+    std::vector<signed char> buf;
+    static_cast<Handle*>(hv)->gsp->exportOccupancyGrid(particle, thresh, buf, *width, *height, origin[0], origin[1]);
+    if (data) memcpy(data, buf.data(), buf.size());
 }
 
 // occupancy of the best particle's map around a world point, through the host mirror (Particle::map.cell): a smoke check of

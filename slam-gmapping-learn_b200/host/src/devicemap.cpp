@@ -33,6 +33,15 @@ DeviceContext::DeviceContext(unsigned int maxParticles, unsigned long long poolP
     std::memset(&m_params, 0, sizeof m_params);
 }
 
+DeviceContext::DeviceContext(const DeviceContext& o, int) : particles(o.particles) {
+    const int rc = gm_clone(o.h, &h);
+    if (rc) fatal(std::string("gm_clone: ") + gm_last_error(o.h));
+    m_haveLaser = o.m_haveLaser; m_haveParams = o.m_haveParams; m_beams = o.m_beams;
+    std::memcpy(m_angles, o.m_angles, sizeof m_angles);
+    std::memcpy(m_laserPose, o.m_laserPose, sizeof m_laserPose);
+    m_params = o.m_params;
+}
+
 DeviceContext::~DeviceContext() {
     if (h) gm_destroy(h);
 }

@@ -18,6 +18,8 @@ namespace b200 {
 class DeviceContext {
   public:
     DeviceContext(unsigned int maxParticles, unsigned long long poolPatches, unsigned int globalParticles = 0);
+    // second context on the same GPU with the same maps (gm_clone)
+    explicit DeviceContext(const DeviceContext& other, int);
     ~DeviceContext();
     DeviceContext(const DeviceContext&) = delete;
     DeviceContext& operator=(const DeviceContext&) = delete;

@@ -78,9 +78,39 @@ GridSlamProcessor::GridSlamProcessor(std::ostream& infoS)
     defaults(*this);
 }
 
-GridSlamProcessor::GridSlamProcessor(const GridSlamProcessor& gsp) : m_infoStream(std::cout) {
-    (void)gsp;
-    b200::fatal("GridSlamProcessor copy / clone(): a device-side filter clone is not part of this build (SURVEY.md §8 row f3)");
+// deep copy of the filter (reference: gridslamprocessor.cpp:38-97): parameters and bookkeeping verbatim, the trajectory
+// tree through getTrajectories(), the particle maps through a device-side clone of the context.  Like the reference's,
+// the copy reports to cout, has no .gfs stream and restarts its update period.
+GridSlamProcessor::GridSlamProcessor(const GridSlamProcessor& gsp)
+    : m_matcher(gsp.m_matcher), m_minimumScore(gsp.m_minimumScore), m_beams(gsp.m_beams), last_update_time_(0.0), period_(5.0),
+      m_indexes(gsp.m_indexes), m_weights(gsp.m_weights), m_motionModel(gsp.m_motionModel), m_resampleThreshold(gsp.m_resampleThreshold),
+      m_count(gsp.m_count), m_readingCount(gsp.m_readingCount), m_lastPartPose(gsp.m_lastPartPose), m_odoPose(gsp.m_odoPose), m_pose(gsp.m_pose),
+      m_linearDistance(gsp.m_linearDistance), m_angularDistance(gsp.m_angularDistance), m_neff(gsp.m_neff), m_xmin(gsp.m_xmin), m_ymin(gsp.m_ymin),
+      m_xmax(gsp.m_xmax), m_ymax(gsp.m_ymax), m_delta(gsp.m_delta), m_regScore(gsp.m_regScore), m_critScore(gsp.m_critScore), m_maxMove(gsp.m_maxMove),
+      m_linearThresholdDistance(gsp.m_linearThresholdDistance), m_angularThresholdDistance(gsp.m_angularThresholdDistance),
+      m_obsSigmaGain(gsp.m_obsSigmaGain), m_infoStream(std::cout), m_rank(0), m_world(1), m_firstLocal(0), m_localCount(gsp.m_localCount),
+      m_treeEpoch(0) {
+    if (gsp.m_world > 1) b200::fatal("GridSlamProcessor copy / clone(): a sharded filter cannot be cloned");
+    m_hostMs[0] = m_hostMs[1] = m_hostMs[2] = m_hostMs[3] = 0;
+    if (!gsp.m_device) return;
+    m_device.reset(new b200::DeviceContext(*gsp.m_device, 0));
+    const TNodeVector leaves = gsp.getTrajectories();
+    ScanMatcherMap mirror(Point((m_xmin + m_xmax) * .5, (m_ymin + m_ymax) * .5), 0., 0., m_delta);
+    m_particles.reserve(gsp.m_particles.size());
+    for (size_t i = 0; i < gsp.m_particles.size(); i++) {
+        const Particle& src = gsp.m_particles[i];
+        m_particles.push_back(Particle(mirror));
+        Particle& p = m_particles.back();
+        p.pose = src.pose; p.previousPose = src.previousPose; p.weight = src.weight; p.weightSum = src.weightSum; p.gweight = src.gweight;
+        p.previousIndex = src.previousIndex;
+        p.node = leaves[i];
+        std::shared_ptr<b200::DeviceMapResidency> r(new b200::DeviceMapResidency);
+        r->ctx = m_device;
+        r->slot = (unsigned int)i;
+        r->stale = true;
+        p.map.setResidency(r);
+    }
+    if (m_count > 0) updateTreeWeights(false);
 }
 
 GridSlamProcessor* GridSlamProcessor::clone() const { return new GridSlamProcessor(*this); }
@@ -547,6 +577,21 @@ void GridSlamProcessor::setDistributed(int rank, int world, const void* ncclId) 
     m_rank = rank;
     m_world = world;
     if (ncclId) memcpy(m_ncclId, ncclId, sizeof m_ncclId);
+}
+
+void GridSlamProcessor::exportOccupancyGrid(unsigned int particle, double occThresh, std::vector<signed char>& data, int& width, int& height,
+                                            double& originX, double& originY) const {
+    if (particle < m_firstLocal || particle >= m_firstLocal + m_localCount) b200::fatal("exportOccupancyGrid: the particle's map lives on another rank");
+    const unsigned int slot = particle - m_firstLocal;
+    gm_map_info info;
+    m_device->check(gm_map_info_get(m_device->h, slot, &info), "gm_map_info_get");
+    width = info.patches_x * 32;
+    height = info.patches_y * 32;
+    data.resize((size_t)width * height);
+    m_device->check(gm_export_occupancy(m_device->h, slot, occThresh, reinterpret_cast<int8_t*>(data.data()), (uint32_t)width, (uint32_t)height),
+                    "gm_export_occupancy");
+    originX = (0 - info.size_x2) * info.delta + info.center_x;  // Map::map2world(0, 0)
+    originY = (0 - info.size_y2) * info.delta + info.center_y;
 }
 
 std::vector<unsigned long long> GridSlamProcessor::mapDigests() const {

@@ -45,6 +45,8 @@ def load():
     L.gmh_indexes.argtypes = [vp, vp]
     L.gmh_device_stats.argtypes = [vp, dp]
     L.gmh_map_digests.argtypes = [vp, vp]
+    L.gmh_clone.restype = vp; L.gmh_clone.argtypes = [vp]
+    L.gmh_occupancy_grid.argtypes = [vp, C.c_uint, C.c_double, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), dp]
     L.gmh_occupancy.restype = C.c_double; L.gmh_occupancy.argtypes = [vp, C.c_uint, C.c_double, C.c_double]
     _lib = L
     return L
@@ -124,6 +126,20 @@ class Processor:
     def map_digests(self):
         nl = self.L.gmh_local_particles(self.h)
         a = np.zeros((nl, 6), dtype=np.uint64); self.L.gmh_map_digests(self.h, a.ctypes.data); return a
+
+    def clone(self):
+        """GridSlamProcessor::clone(): deep copy incl. trajectory tree and (device-side) particle maps"""
+        other = object.__new__(Processor)
+        other.L = self.L; other.n = self.n; other.beams = self.beams
+        other.h = self.L.gmh_clone(self.h)
+        return other
+
+    def occupancy_grid(self, particle, thresh=0.25):
+        w, h = C.c_int(), C.c_int(); origin = np.zeros(2)
+        self.L.gmh_occupancy_grid(self.h, particle, thresh, None, C.byref(w), C.byref(h), _dp(origin))
+        data = np.zeros((h.value, w.value), dtype=np.int8)
+        self.L.gmh_occupancy_grid(self.h, particle, thresh, data.ctypes.data, C.byref(w), C.byref(h), _dp(origin))
+        return data, origin
 
     def occupancy(self, particle, wx, wy):
         return self.L.gmh_occupancy(self.h, particle, wx, wy)

@@ -159,3 +159,41 @@ def test_host_shim_loads_under_python():
     pv = np.array([float(hostapi.DEFAULTS[k]) for k in hostapi.PARAM_ORDER])
     L.gmh_setup(h, 181, hostapi._dp(a), hostapi._dp(lp), hostapi._dp(pv))
     L.gmh_destroy(h)
+
+
+@pytest.mark.gpu
+def test_clone_continues_identically_and_occupancy_grid():
+    """GridSlamProcessor::clone() (gridslamprocessor.cpp:38-97): the copy, fed the same readings and the same drand48
+    stream, stays bit-identical to the original -- poses, weights, resample indexes and every particle map."""
+    build_host()
+    hostapi = importlib.import_module("slam-gmapping-learn_b200.hostapi")
+    libc = ctypes.CDLL("libc.so.6")
+    libc.seed48.restype = ctypes.POINTER(ctypes.c_ushort * 3)
+    g = Golden("room181_n30")
+    p = g.p
+    a = hostapi.Processor(g.angles, p["particles"], g.head_init, bounds=(p["xmin"], p["ymin"], p["xmax"], p["ymax"]), delta=p["delta"], seed=p["seed"],
+                          **{k: p[k] for k in hostapi.PARAM_ORDER})
+    for i in range(12):
+        a.process_scan(g.ranges[i], g.odom[i], g.stamps[i])
+    b = a.clone()
+    assert np.array_equal(a.state(), b.state()) and np.array_equal(a.map_digests(), b.map_digests())
+    saved = (ctypes.c_ushort * 3)(*libc.seed48((ctypes.c_ushort * 3)(0, 0, 0)).contents)  # read the drand48 state ...
+    libc.seed48(saved)                                                                      # ... and put it back
+    for i in range(12, 24):
+        a.process_scan(g.ranges[i], g.odom[i], g.stamps[i])
+    resampled = a.resamples()
+    libc.seed48(saved)
+    for i in range(12, 24):
+        b.process_scan(g.ranges[i], g.odom[i], g.stamps[i])
+    assert np.array_equal(a.state(), b.state()), "clone diverged"
+    assert np.array_equal(a.map_digests(), b.map_digests())
+    assert b.resamples() == resampled and a.neff() == b.neff()
+    assert np.abs(a.state()[:, :3] - g.state[23][:, :3]).max() < 1e-4  # and both still follow the reference
+    # occupancy grid of the best particle through the C++ API
+    grid, origin = a.occupancy_grid(a.best(), 0.25)
+    assert grid.shape == (4000, 4000) and abs(origin[0] + 100.0) < 1e-9 and abs(origin[1] + 100.0) < 1e-9
+    assert (grid == 100).sum() > 200 and (grid == 0).sum() > 20000 and (grid == -1).sum() > 15000000
+    x, y = g.state[23][a.best(), 0], g.state[23][a.best(), 1]
+    assert grid[int(round((y + 100) / 0.05)), int(round((x + 100) / 0.05))] == 0  # the robot stands in free space
+    assert a.occupancy(a.best(), x, y) < 0.1
+    a.close(); b.close()
