@@ -1,0 +1,77 @@
+"""Full-size checks at BASELINE.json's headline shape (4096 particles x 1081 beams) through size-independent properties,
+plus an oracle spot check of a random subset of the particles (the oracle cannot run 4096 x 1081 in seconds)."""
+import importlib
+
+import numpy as np
+import pytest
+
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+N, SCANS = 4096, 4
+
+
+def test_c4_shape_conservation_determinism_and_subset_parity():
+    gm = importlib.import_module("slam-gmapping-learn_b200")
+    synth = importlib.import_module("slam-gmapping-learn_b200.synth")
+    log = synth.make_log("room", synth.UTM30, scans=SCANS + 1, step=0.25, seed=4)
+    ctx = gm.GmContext(N, pool_patches=N * 200)
+    ctx.set_laser(log.laser.angles()); ctx.set_matching(urange=29., range_=30.); ctx.init_particles(N)
+    m = orc.make_matcher(log.laser.angles(), urange=29., range_=30.)
+    rng = np.random.default_rng(8)
+    subset = np.sort(rng.choice(N, size=6, replace=False))
+    maps = {int(j): orc.Map() for j in subset}
+    prev = ctx.digests()
+    for k in range(SCANS):
+        poses = log.odom[k][None, :] + rng.normal(0, [0.02, 0.02, 0.01], size=(N, 3))
+        poses[N // 2:] = poses[:N // 2]  # the upper half repeats the lower half: identical maps expected
+        ctx.register(log.ranges[k], poses)
+        st = ctx.stats()
+        d = ctx.digests()
+        # conservation: every update is counted once -- visits grow by free + hit updates, n by hit updates
+        assert int(d["sum_visits"].sum() - prev["sum_visits"].sum()) == st["free_updates"] + st["hit_updates"]
+        assert int(d["sum_n"].sum() - prev["sum_n"].sum()) == st["hit_updates"]
+        assert st["hit_updates"] == N * int(np.sum(log.ranges[k] < 29.0))
+        prev = d
+        for j in subset:
+            orc.register(m, maps[int(j)], poses[j], log.ranges[k])
+        # identical poses -> identical maps (checksum of checksums)
+        assert np.array_equal(d["hash_counts"][:N // 2], d["hash_counts"][N // 2:])
+        assert np.array_equal(d["hash_acc"][:N // 2], d["hash_acc"][N // 2:])
+    for j in subset:
+        od = maps[int(j)].digest()
+        assert (int(d["patches"][j]), int(d["cells"][j]), int(d["sum_n"][j]), int(d["sum_visits"][j]), int(d["hash_counts"][j])) == \
+               (od.patches, od.cells, od.sum_n, od.sum_visits, od.hash_counts)
+    # scan matching at full size: deterministic, identical inputs give identical outputs, subset equals the oracle
+    init = log.odom[SCANS][None, :] + rng.normal(0, [0.05, 0.05, 0.02], size=(N, 3))
+    init[N // 2:] = init[:N // 2]
+    r = log.ranges[SCANS]
+    out1 = ctx.scanmatch(r, init, 0.0)
+    out2 = ctx.scanmatch(r, init, 0.0)
+    for a, b in zip(out1, out2):
+        assert np.array_equal(a, b), "scan matching is not deterministic"
+    poses, score, s, l, c, ev = out1
+    assert np.array_equal(poses[:N // 2], poses[N // 2:]) and np.array_equal(l[:N // 2], l[N // 2:])
+    assert ev.min() >= 37 and score.min() > 100
+    assert ctx.stats()["beam_evals"] == int(ev.sum()) * 1081 + N * 1081
+    for j in subset:
+        so, po = orc.optimize(m, maps[int(j)], init[j], r)
+        s1, l1, c1 = orc.likelihood_and_score(m, maps[int(j)], po, r)
+        assert np.abs(poses[j] - po).max() < 1e-9 and abs(l[j] - l1) <= 1e-9 * abs(l1) and c[j] == c1
+    # weights and resampling at full size against the oracle (sequential sums kept)
+    w, neff = ctx.normalize(l, 3.0)
+    wo, neffo = orc.normalize(l, 3.0)
+    np.testing.assert_allclose(w, wo, rtol=1e-13); assert abs(neff - neffo) < 1e-9 * neffo
+    idx, em = ctx.resample_indexes(wo, 0.4242)
+    io, _ = orc.resample_indexes(wo, 0.4242)
+    assert np.array_equal(idx, io) and em == N and np.all(np.diff(idx.astype(np.int64)) >= 0)  # sortedness
+    # resample + register: children of one parent share its patches, pool use stays far below N deep copies
+    ctx.register(r, poses[idx], idx)
+    d2 = ctx.digests()
+    st = ctx.stats()
+    assert st["pool_in_use"] < 1.6 * int(d2["patches"].max()) * N
+    first_child = {int(p): j for j, p in reversed(list(enumerate(idx)))}
+    for p_, j in list(first_child.items())[:50]:
+        same = np.nonzero(idx == p_)[0]
+        assert len(set(d2["hash_counts"][same].tolist())) == 1  # same parent, same pose -> same map
+    ctx.close()
