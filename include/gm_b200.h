@@ -91,6 +91,8 @@ typedef struct gm_stats {
     /* last gm_register: SM cycles summed over CTAs per phase of k_register (beam setup, ray marking, ranks, copy-on-write,
      * ray counting, tile flush, hit sort, hit accumulation) */
     uint64_t register_phase_cycles[8];
+    uint32_t max_active_patches; /* last gm_register: largest active area (patches) of a particle */
+    uint32_t register_tile_cap;  /* last gm_register: visit-count tiles per pass (shared memory) */
 } gm_stats;
 
 int gm_create(gm_ctx** out, const gm_config* cfg);

@@ -50,7 +50,8 @@ class Stats(C.Structure):
                 ("free_updates", C.c_uint64), ("hit_updates", C.c_uint64), ("resizes", C.c_uint64),
                 ("ms_scanmatch", C.c_float), ("ms_register", C.c_float), ("ms_remap", C.c_float), ("ms_weights", C.c_float),
                 ("ms_migrate", C.c_float), ("ms_allgather", C.c_float), ("migrated_particles", C.c_uint64), ("migrated_bytes", C.c_uint64),
-                ("launches", C.c_uint32), ("reserved", C.c_uint32), ("register_phase_cycles", C.c_uint64 * 8)]
+                ("launches", C.c_uint32), ("reserved", C.c_uint32), ("register_phase_cycles", C.c_uint64 * 8),
+                ("max_active_patches", C.c_uint32), ("register_tile_cap", C.c_uint32)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("reserved", "register_phase_cycles")}

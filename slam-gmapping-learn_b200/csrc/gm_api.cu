@@ -381,16 +381,10 @@ int gmi_register_update(gm_ctx* ctx) {
     a.sort_n = sort_n;
     // visit-count tiles: as many as fit (one pass over the rays when the active area has at most that many patches);
     // with few active patches a smaller allocation lets two CTAs share an SM
-    const size_t fixed = register_smem_bytes(a.bitmap_words, a.sort_n, (int)ctx->P.nbeams, 0);
-    const size_t budget = 200 * 1024;
-    if (fixed + 2048 > budget) return fail(ctx, GM_ERR_ARG, "gm_register: patch directory of %d entries needs %zu B of shared memory", ctx->dir_cap, fixed);
-    int tile_cap = (int)((budget - fixed) / 2048);
-    const int want = ctx->reg_active_hint > 0 ? ctx->reg_active_hint + 8 : tile_cap;
-    if (want < tile_cap) {
-        const size_t half = (budget + 24 * 1024) / 2;  // two CTAs per SM (227 KB)
-        const int cap2 = fixed + 2048 <= half ? (int)((half - fixed) / 2048) : 0;
-        tile_cap = want <= cap2 ? cap2 : tile_cap;
-    }
+    const size_t fixed = register_smem_bytes(a.bitmap_words, 0, (int)ctx->P.nbeams, 0);
+    const size_t budget = 220 * 1024;  // of the 227 KB a CTA may use
+    if (fixed + (size_t)a.sort_n * 8 > budget) return fail(ctx, GM_ERR_ARG, "gm_register: patch directory of %d entries needs %zu B of shared memory", ctx->dir_cap, fixed);
+    const int tile_cap = (int)((budget - fixed) / 2048);
     a.tile_cap = tile_cap;
     const size_t smem = register_smem_bytes(a.bitmap_words, a.sort_n, (int)ctx->P.nbeams, tile_cap);
     if (smem != ctx->register_smem) { CK(register_prepare(smem)); ctx->register_smem = smem; }
@@ -409,6 +403,7 @@ int gmi_register_update(gm_ctx* ctx) {
     ctx->stats.free_updates = h.free_updates; ctx->stats.hit_updates = h.hit_updates; ctx->stats.resizes = h.resizes;
     ctx->stats.pool_in_use = (uint64_t)(ctx->pool.cap - top);
     ctx->reg_active_hint = h.max_active;
+    ctx->stats.max_active_patches = (uint32_t)h.max_active; ctx->stats.register_tile_cap = (uint32_t)a.tile_cap;
     for (int k = 0; k < 8; k++) ctx->stats.register_phase_cycles[k] = h.reg_phase[k];
     if (h.error == GM_ERR_POOL) return fail(ctx, GM_ERR_POOL, "gm_register: patch pool of %d patches exhausted", ctx->pool.cap);
     if (h.error) return fail(ctx, h.error, "gm_register: device-side error %d", h.error);

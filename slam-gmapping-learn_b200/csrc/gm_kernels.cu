@@ -11,6 +11,7 @@
 //   k_remap/k_sweep/k_merge_free   particle copy by patch reference     (gridslamprocessor.hxx:184-213)
 //   k_normalize / k_resample       (gridslamprocessor.hxx:82-121, particlefilter.h:180-229)
 //   k_digest / k_export_*          map read-back
+#include <algorithm>
 #include <climits>
 
 #include "gm_device.cuh"
@@ -561,7 +562,7 @@ __global__ void k_relayout_commit(RelayoutArgs A) {
 //      (cell, beam) and each cell's run is accumulated sequentially in beam order by one thread.
 // Ray walks (1 and 3): rays are cut into work items of 32 cells; a thread starts its item from the closed form of the
 // reference's Bresenham state and steps incrementally, looking the patch up again only when the cell leaves it.
-struct BeamRec { int p1x, p1y; float hx, hy; int flags; };  // flags: 1 = ray is traced, 2 = endpoint is a hit
+struct BeamRec { int p1x, p1y; float hx, hy; int flags; };  // flags: 1 = ray is traced, 2 = endpoint is a hit, 4 = ... inside the map
 
 constexpr int kRayChunk = 32;  // cells per work item of a ray walk
 
@@ -604,13 +605,51 @@ __device__ __forceinline__ void walk_ray(int p0x, int p0y, int p1x, int p1y, int
     }
 }
 
+// minor coordinate of the line after j steps from its low end: the closed form of the reference's Bresenham (gm_device.cuh)
+__device__ __forceinline__ int line_minor(const Line& L, int j) {
+    int inc = 0;
+    if (j && L.da) {
+        const unsigned num = 2u * (unsigned)L.db * (unsigned)j + (unsigned)L.da, den = 2u * (unsigned)L.da;
+        int q = (int)((double)num * (1.0 / (double)den));
+        const long long rem = (long long)num - (long long)q * den;
+        q += rem >= (long long)den ? 1 : (rem < 0 ? -1 : 0);
+        inc = q;
+    }
+    return L.b_lo + L.bstep * inc;
+}
+
+// The patches (as px, py pairs) under chunk `chunk` of the line p0 -> p1 (p1 excluded), without walking it: a chunk of
+// kRayChunk <= 32 cells crosses at most one patch boundary along the major axis, and between two cells the minor
+// coordinate moves monotonically by at most one per step, so each of the (at most two) major-axis segments lies in the
+// patch rows of its first and last cell.  Returns the number of pairs written (<= 4, duplicates possible).
+__device__ __forceinline__ int item_patches(int p0x, int p0y, int p1x, int p1y, int chunk, int (&px)[4], int (&py)[4]) {
+    const Line L = make_line(p0x, p0y, p1x, p1y);
+    const int m = L.n - 1, jlo = L.from_end ? 1 : 0;
+    const int j0 = jlo + chunk * kRayChunk, j1 = min(jlo + m, j0 + kRayChunk) - 1;  // first / last step of the chunk
+    if (j0 > j1) return 0;
+    const int a0 = L.a_lo + j0, a1 = L.a_lo + j1;
+    const int aB = ((a0 >> kPatchMag) + 1) << kPatchMag;  // first major coordinate of the next patch
+    int n = 0;
+    auto put = [&](int a, int b) {
+        px[n] = (L.steep ? b : a) >> kPatchMag; py[n] = (L.steep ? a : b) >> kPatchMag; n++;
+    };
+    const int e1 = min(a1, aB - 1);
+    put(a0, line_minor(L, j0));
+    if (e1 != a0) put(e1, line_minor(L, e1 - L.a_lo));
+    if (aB <= a1) {
+        put(aB, line_minor(L, aB - L.a_lo));
+        if (a1 != aB) put(a1, line_minor(L, j1));
+    }
+    return n;
+}
+
 constexpr int kRegThreads = 1024;
 constexpr int kTileWords = kPatchCells / 2;  // a tile counts visits of one patch: 1024 cells x 16 bit, two per word
 
 // dynamic shared memory of k_register (see register_smem_bytes): active-patch bitmap over the directory, its
 // running popcount per word, sort keys of the hits, per-beam records, visit-count tiles
 struct RegSmem {
-    unsigned* active; unsigned short* prefix; unsigned long long* keys; BeamRec* rec; int* items; unsigned* tiles;
+    unsigned* active; unsigned short* prefix; BeamRec* rec; int* items; unsigned* tiles; unsigned long long* keys;  // keys alias tiles
 };
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 __device__ __forceinline__ RegSmem carve(unsigned char* raw, int bitmap_words, int sort_n, int nbeams) {
@@ -618,10 +657,10 @@ __device__ __forceinline__ RegSmem carve(unsigned char* raw, int bitmap_words, i
     size_t o = 0;
     m.active = reinterpret_cast<unsigned*>(raw + o); o += align16((size_t)bitmap_words * 4);
     m.prefix = reinterpret_cast<unsigned short*>(raw + o); o += align16((size_t)bitmap_words * 2);
-    m.keys = reinterpret_cast<unsigned long long*>(raw + o); o += (size_t)sort_n * 8;
     m.rec = reinterpret_cast<BeamRec*>(raw + o); o += align16((size_t)nbeams * sizeof(BeamRec));
     m.items = reinterpret_cast<int*>(raw + o); o += align16((size_t)(nbeams + 1) * 4);
     m.tiles = reinterpret_cast<unsigned*>(raw + o);
+    m.keys = reinterpret_cast<unsigned long long*>(raw + o);  // the hit sort runs after the last tile flush
     return m;
 }
 
@@ -644,7 +683,6 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
     long long tph = clock64();
 #define PHASE(k) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&A.counters->reg_phase[k], (unsigned long long)(now_ - tph)); tph = now_; } } while (0)
     for (int i = threadIdx.x; i < nwords; i += blockDim.x) active[i] = 0u;
-    for (int i = threadIdx.x; i < A.sort_n; i += blockDim.x) keys[i] = ~0ull;
     if (threadIdx.x == 0) { s_free = 0; s_hit = 0; s_cow = 0; s_alloc = 0; }
     double lx, ly, lt;
     laser_pose(P, A.poses[3 * p], A.poses[3 * p + 1], A.poses[3 * p + 2], lx, ly, lt);
@@ -674,7 +712,7 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
             if (hit && R.p1x >= 0 && R.p1y >= 0 && (R.p1x >> kPatchMag) < g.npx && (R.p1y >> kPatchMag) < g.npy) {
                 const int e = (R.p1x >> kPatchMag) * g.npy + (R.p1y >> kPatchMag);
                 atomicOr(&active[e >> 5], 1u << (e & 31));
-                keys[b] = ((unsigned long long)(unsigned)R.p1x << 36) | ((unsigned long long)(unsigned)R.p1y << 12) | b;
+                R.flags |= 4;  // the hit lands inside the map
             }
         }
         rec[b] = R;
@@ -697,17 +735,19 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
     const int nitems = M.items[P.nbeams];
     PHASE(0);
 
-    // ---- 1. active area: patches under the rays
+    // ---- 1. active area: patches under the rays (from each chunk's end points, see item_patches)
     for (int it = threadIdx.x; it < nitems; it += blockDim.x) {
         int lo = 0, hi = (int)P.nbeams - 1;  // the beam whose chunk range holds item `it`
         while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (M.items[mid] <= it) lo = mid; else hi = mid - 1; }
         const BeamRec R = rec[lo];
-        walk_ray(p0x, p0y, R.p1x, R.p1y, it - M.items[lo], [&](int, int, int px, int py, bool np) {
-            if (np && (unsigned)px < (unsigned)g.npx && (unsigned)py < (unsigned)g.npy) {
-                const int e = px * g.npy + py;
-                atomicOr(&active[e >> 5], 1u << (e & 31));
+        int qx[4], qy[4];
+        const int nq = item_patches(p0x, p0y, R.p1x, R.p1y, it - M.items[lo], qx, qy);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (k < nq && (unsigned)qx[k] < (unsigned)g.npx && (unsigned)qy[k] < (unsigned)g.npy) {
+                const int e = qx[k] * g.npy + qy[k];
+                if (!((active[e >> 5] >> (e & 31)) & 1u)) atomicOr(&active[e >> 5], 1u << (e & 31));
             }
-        });
     }
     __syncthreads();
     PHASE(1);
@@ -782,6 +822,19 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
             int lo = 0, hi = (int)P.nbeams - 1;
             while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (M.items[mid] <= it) lo = mid; else hi = mid - 1; }
             const BeamRec R = rec[lo];
+            if (nactive > A.tile_cap) {  // several passes: skip the chunk unless one of its patches is counted in this one
+                int qx[4], qy[4];
+                const int nq = item_patches(p0x, p0y, R.p1x, R.p1y, it - M.items[lo], qx, qy);
+                bool mine = false;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (k < nq && (unsigned)qx[k] < (unsigned)g.npx && (unsigned)qy[k] < (unsigned)g.npy) {
+                        const int e = qx[k] * g.npy + qy[k];
+                        const int slot = (int)M.prefix[e >> 5] + __popc(active[e >> 5] & ((1u << (e & 31)) - 1u)) - first;
+                        mine = mine || (unsigned)slot < (unsigned)ntile;
+                    }
+                if (!mine) continue;
+            }
             unsigned* tile = nullptr;  // counters of the current patch, null when it is not in this pass / outside the map
             walk_ray(p0x, p0y, R.p1x, R.p1y, it - M.items[lo], [&](int x, int y, int px, int py, bool np) {
                 if (np) {
@@ -831,7 +884,12 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
     __threadfence();
     __syncthreads();
 
-    // ---- 4. endpoint hits in beam order per cell: bitonic sort of (cell, beam) keys
+    // ---- 4. endpoint hits in beam order per cell: bitonic sort of (cell, beam) keys (built now: they reuse the tile area)
+    for (int i = threadIdx.x; i < A.sort_n; i += blockDim.x) {
+        unsigned long long key = ~0ull;
+        if (i < (int)P.nbeams && (rec[i].flags & 4)) key = ((unsigned long long)(unsigned)rec[i].p1x << 36) | ((unsigned long long)(unsigned)rec[i].p1y << 12) | (unsigned)i;
+        keys[i] = key;
+    }
     for (int k = 2; k <= A.sort_n; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
             __syncthreads();
@@ -1086,8 +1144,9 @@ void launch_bounds(const BoundsArgs& a, unsigned n, unsigned threads, cudaStream
 void launch_relayout(const RelayoutArgs& a, unsigned n, cudaStream_t st) { k_relayout<<<n, 256, 0, st>>>(a); }
 void launch_relayout_commit(const RelayoutArgs& a, unsigned n, cudaStream_t st) { k_relayout_commit<<<n, 256, 0, st>>>(a); }
 size_t register_smem_bytes(int bitmap_words, int sort_n, int nbeams, int tile_cap) {
-    return align16((size_t)bitmap_words * 4) + align16((size_t)bitmap_words * 2) + (size_t)sort_n * 8 + align16((size_t)nbeams * sizeof(BeamRec)) +
-           align16((size_t)(nbeams + 1) * 4) + (size_t)tile_cap * kTileWords * 4;
+    const size_t tiles = std::max((size_t)tile_cap * kTileWords * 4, (size_t)sort_n * 8);  // the sort keys reuse the tile area
+    return align16((size_t)bitmap_words * 4) + align16((size_t)bitmap_words * 2) + align16((size_t)nbeams * sizeof(BeamRec)) +
+           align16((size_t)(nbeams + 1) * 4) + tiles;
 }
 cudaError_t register_prepare(size_t smem) {
     return cudaFuncSetAttribute(k_register, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
