@@ -871,7 +871,7 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
                 for (int k = 0; k < 8; k++) {
                     const int ci = g8 + 32 * k + lane;
                     c[k] = (tile[ci >> 1] >> ((ci & 1) << 4)) & 0xffffu;
-                    v[k] = __ldcg(cells + (ci << 2) + 3);
+                    v[k] = c[k] ? __ldcg(cells + (ci << 2) + 3) : 0;  // untouched cells cost no traffic
                 }
 #pragma unroll
                 for (int k = 0; k < 8; k++)
