@@ -143,6 +143,12 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     void setDistributed(int rank, int world, const void* ncclId);
     inline unsigned int firstLocalParticle() const { return m_firstLocal; }
     inline unsigned int localParticles() const { return m_localCount; }
+    // updateTreeWeights() walks every node of the trajectory tree (O(particles x scans) while nothing is resampled away).
+    // With lazy = true processScan only normalises the weights (Neff, resampling are unaffected); TNode::accWeight is
+    // brought up to date by getTrajectories() or refreshTreeWeights().  Default: false, the reference's behaviour.
+    void setlazyTreeWeights(bool lazy) { m_lazyTree = lazy; }
+    bool getlazyTreeWeights() const { return m_lazyTree; }
+    void refreshTreeWeights();
     // occupancy grid of one local particle's map computed on the GPU (what gmapping/src/slam_gmapping.cpp:956-993 fills by
     // walking smap.cell(p) on the host): data[y * width + x] = -1 unknown, 100 if n/visits > occThresh, else 0;
     // (originX, originY) = world position of cell (0, 0)
@@ -197,6 +203,9 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     unsigned char m_ncclId[128];
     unsigned int m_firstLocal, m_localCount;
     unsigned int m_treeEpoch;
+    bool m_lazyTree = false;
+    bool m_weightsChanged = true;  // a particle's log-weight changed since the last normalize()
+    mutable bool m_treeDirty = false;
     double m_hostMs[4];
     std::vector<double> m_poseBuf, m_scoreBuf, m_likBuf;
 };

@@ -261,6 +261,7 @@ void GridSlamProcessor::scanMatch(const double* plainReading) {
         p.weight += lik;
         p.weightSum += lik;
     }
+    m_weightsChanged = true;
     if (m_infoStream) m_infoStream << "Average Scan Matching Score=" << sumScore / n << endl;
 }
 
@@ -342,15 +343,25 @@ bool GridSlamProcessor::resample(const double* plainReading, int adaptSize, cons
         p.previousIndex = (int)m_indexes[j];
         p.setWeight(0);
     }
+    m_weightsChanged = true;
     registerAll(plainReading, m_indexes.data());
     return true;
 }
 
 // ------------------------------------------------------------------------------------------ tree weights
 void GridSlamProcessor::updateTreeWeights(bool weightsAlreadyNormalized) {
-    if (!weightsAlreadyNormalized) normalize();
+    // the second call of a processScan that did not resample sees the log-weights of the first: same weights, same Neff
+    if (!weightsAlreadyNormalized && (m_weightsChanged || m_weights.size() != m_particles.size())) { normalize(); m_weightsChanged = false; }
+    if (m_lazyTree) { m_treeDirty = true; return; }
     resetTree();
     propagateWeights();
+}
+
+void GridSlamProcessor::refreshTreeWeights() {
+    if (!m_treeDirty || m_weights.size() != m_particles.size()) return;
+    resetTree();
+    propagateWeights();
+    m_treeDirty = false;
 }
 
 // zero accWeight / visitCounter on every node reachable from a particle (reference: gridslamprocessor_tree.cpp:255-268);
@@ -402,8 +413,25 @@ bool GridSlamProcessor::processScan(const RangeReading& reading, int adaptPartic
     Stopwatch sw;
     m_hostMs[0] = m_hostMs[1] = m_hostMs[2] = m_hostMs[3] = 0;
     // motion model: every reading, every particle, in order -- this is where the drand48 stream advances
-    for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it)
-        it->pose = m_motionModel.drawFromMotion(it->pose, relPose, m_odoPose);
+    // (MotionModel::drawFromMotion(p, pnew, pold) with its particle-independent part -- the odometry step in the robot
+    // frame and the three noise scales -- evaluated once per reading; same expressions, same draws, same results)
+    {
+        const MotionModel& mm = m_motionModel;
+        const double sxy = 0.3 * mm.srr;
+        const OrientedPoint delta = absoluteDifference(relPose, m_odoPose);
+        const double sx = mm.srr * fabs(delta.x) + mm.str * fabs(delta.theta) + sxy * fabs(delta.y);
+        const double sy = mm.srr * fabs(delta.y) + mm.str * fabs(delta.theta) + sxy * fabs(delta.x);
+        const double st = mm.stt * fabs(delta.theta) + mm.srt * sqrt(delta.x * delta.x + delta.y * delta.y);
+        for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it) {
+            OrientedPoint noisy(delta);
+            noisy.x += sampleGaussian(sx);
+            noisy.y += sampleGaussian(sy);
+            noisy.theta += sampleGaussian(st);
+            noisy.theta = fmod(noisy.theta, 2 * M_PI);
+            if (noisy.theta > M_PI) noisy.theta -= 2 * M_PI;
+            it->pose = absoluteSum(it->pose, noisy);
+        }
+    }
     m_hostMs[0] = sw.lap();
 
     if (m_outputStream.is_open()) {
@@ -519,6 +547,7 @@ void GridSlamProcessor::onOdometryUpdate() {}
 // deep copy of the trajectory tree: one new leaf per particle, shared ancestors copied once
 // (reference: gridslamprocessor_tree.cpp:57-147)
 GridSlamProcessor::TNodeVector GridSlamProcessor::getTrajectories() const {
+    const_cast<GridSlamProcessor*>(this)->refreshTreeWeights();
     std::map<const TNode*, TNode*> copyOf;
     TNodeVector leaves;
     leaves.reserve(m_particles.size());
