@@ -93,6 +93,9 @@ typedef struct gm_stats {
     uint64_t register_phase_cycles[8];
     uint32_t max_active_patches; /* last gm_register: largest active area (patches) of a particle */
     uint32_t register_tile_cap;  /* last gm_register: visit-count tiles per pass (shared memory) */
+    /* running totals since gm_create: device ms of scanmatch, weights, remap, register, migrate, allgather; work; call counts */
+    double total_ms[6];
+    uint64_t total_beam_evals, total_score_evals, total_scanmatches, total_registers;
 } gm_stats;
 
 int gm_create(gm_ctx** out, const gm_config* cfg);
@@ -183,6 +186,13 @@ int gm_dist_plan(uint32_t n_local, int rank, int world, const uint32_t* idx_glob
 /* replaces: the map part of GridSlamProcessor's copy constructor / clone(), gridfastslam/gridslamprocessor.cpp:38-97
  * (SURVEY.md §8 row f3): a second context on the same GPU with identical particle maps (the whole pool is copied). */
 int gm_clone(gm_ctx* src, gm_ctx** out);
+
+/* Asynchronous registration: with on != 0, gm_register / gm_dist_register return as soon as the kernels are launched so
+ * that the caller's host-side bookkeeping (trajectory tree, next motion-model draws) overlaps them.  Counters, timing and
+ * device-side errors (pool exhausted) of that registration are reported by the NEXT call on the context -- every entry
+ * point first collects a pending registration -- or by gm_synchronize.  Default: off (every call is complete at return). */
+int gm_set_async_register(gm_ctx* ctx, int on);
+int gm_synchronize(gm_ctx* ctx);
 
 int gm_get_stats(gm_ctx* ctx, gm_stats* out);
 uint32_t gm_particles(const gm_ctx* ctx);

@@ -91,6 +91,8 @@ int gm_create(gm_ctx** out, const gm_config* cfg) {
 int gm_destroy(gm_ctx* c) {
     if (!c) return GM_OK;
     cudaSetDevice(c->device);
+    if (c->st) cudaStreamSynchronize(c->st);
+    c->reg_pending = false;
     gmi_dist_destroy(c);
     if (c->st) cudaStreamSynchronize(c->st);
     cudaFree(c->pool.cells); cudaFree(c->pool.refcnt); cudaFree(c->pool.free_list); cudaFree(c->pool.pending);
@@ -251,6 +253,8 @@ int gm_scanmatch(gm_ctx* ctx, const double* ranges, double* poses_inout, double 
     if (int r = read_counters(ctx, h)) return r;
     ctx->stats.score_evals = h.score_evals; ctx->stats.beam_evals = h.beam_evals;
     CK(cudaEventElapsedTime(&ctx->stats.ms_scanmatch, ctx->ev0, ctx->ev1));
+    ctx->stats.total_ms[0] += ctx->stats.ms_scanmatch; ctx->stats.total_beam_evals += h.beam_evals; ctx->stats.total_score_evals += h.score_evals;
+    ctx->stats.total_scanmatches++;
     return GM_OK;
 }
 
@@ -267,6 +271,7 @@ int gm_normalize_neff(gm_ctx* ctx, const double* log_weights, uint32_t n, double
     if (neff_out) CK(cudaMemcpyAsync(neff_out, ctx->d_neff, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     CK(cudaEventElapsedTime(&ctx->stats.ms_weights, ctx->ev0, ctx->ev1));
+    ctx->stats.total_ms[1] += ctx->stats.ms_weights;
     return GM_OK;
 }
 
@@ -393,17 +398,30 @@ int gmi_register_update(gm_ctx* ctx) {
     CK(cudaEventRecord(ctx->ev1, ctx->st));
     ctx->stats.launches += 2;
     if (int rc = check_launch(ctx, "k_register")) return rc;
+    ctx->reg_pending = true;
+    ctx->reg_tile_cap = tile_cap;
+    // asynchronous registration: the kernel runs on while the caller does its host-side bookkeeping; counters, timing
+    // and device-side errors are collected by the next entry point (or gm_synchronize)
+    return ctx->async_register ? GM_OK : gmi_register_finish(ctx);
+}
+
+// collect what a launched registration left behind: counters, timing, pool level, device-side errors
+int gmi_register_finish(gm_ctx* ctx) {
+    if (!ctx->reg_pending) return GM_OK;
+    ctx->reg_pending = false;
     Counters h;
     if (int rc = read_counters(ctx, h)) return rc;
     int top = 0;
     CK(cudaMemcpyAsync(&top, ctx->pool.free_top, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     CK(cudaEventElapsedTime(&ctx->stats.ms_register, ctx->ev0, ctx->ev1));
+    ctx->stats.total_ms[3] += ctx->stats.ms_register; ctx->stats.total_ms[2] += ctx->stats.ms_remap; ctx->stats.total_ms[4] += ctx->stats.ms_migrate;
+    ctx->stats.total_registers++;
     ctx->stats.cow_copies = h.cow_copies; ctx->stats.patch_allocs = h.patch_allocs;
     ctx->stats.free_updates = h.free_updates; ctx->stats.hit_updates = h.hit_updates; ctx->stats.resizes = h.resizes;
     ctx->stats.pool_in_use = (uint64_t)(ctx->pool.cap - top);
     ctx->reg_active_hint = h.max_active;
-    ctx->stats.max_active_patches = (uint32_t)h.max_active; ctx->stats.register_tile_cap = (uint32_t)a.tile_cap;
+    ctx->stats.max_active_patches = (uint32_t)h.max_active; ctx->stats.register_tile_cap = (uint32_t)ctx->reg_tile_cap;
     for (int k = 0; k < 8; k++) ctx->stats.register_phase_cycles[k] = h.reg_phase[k];
     if (h.error == GM_ERR_POOL) return fail(ctx, GM_ERR_POOL, "gm_register: patch pool of %d patches exhausted", ctx->pool.cap);
     if (h.error) return fail(ctx, h.error, "gm_register: device-side error %d", h.error);
@@ -567,6 +585,7 @@ int gm_clone(gm_ctx* src, gm_ctx** out) {
     *out = nullptr;
     if (src->dist) return fail(src, GM_ERR_ARG, "gm_clone: a sharded context cannot be cloned");
     if (int r = bind(src)) return r;
+    { gm_ctx* ctx = src; if (int r = gmi_register_finish(ctx)) return r; }
     gm_config cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.device = src->device; cfg.max_particles = src->max_particles; cfg.pool_patches = (uint64_t)src->pool.cap;
@@ -603,8 +622,25 @@ int gm_clone(gm_ctx* src, gm_ctx** out) {
     return GM_OK;
 }
 
+int gm_set_async_register(gm_ctx* ctx, int on) {
+    if (!ctx) return GM_ERR_ARG;
+    if (int r = bind(ctx)) return r;
+    if (int r = gmi_register_finish(ctx)) return r;
+    ctx->async_register = on != 0;
+    return GM_OK;
+}
+
+int gm_synchronize(gm_ctx* ctx) {
+    if (!ctx) return GM_ERR_ARG;
+    if (int r = bind(ctx)) return r;
+    if (int r = gmi_register_finish(ctx)) return r;
+    CK(cudaStreamSynchronize(ctx->st));
+    return GM_OK;
+}
+
 int gm_get_stats(gm_ctx* ctx, gm_stats* out) {
     if (!ctx || !out) return GM_ERR_ARG;
+    if (ctx->reg_pending) { if (int r = bind(ctx)) return r; if (int r = gmi_register_finish(ctx)) return r; }
     *out = ctx->stats;
     return GM_OK;
 }

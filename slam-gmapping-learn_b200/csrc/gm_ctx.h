@@ -51,11 +51,15 @@ struct gm_ctx {
     std::string err;
     size_t register_smem = 0;
     signed char* d_occ = nullptr; size_t occ_cap = 0;  // gm_export_occupancy staging
+    bool async_register = false, reg_pending = false;  // gm_set_async_register: a registration may still be running
+    int reg_tile_cap = 0;
     int reg_active_hint = 0;  // largest active-patch count seen by the last k_register (sizes its tile allocation)
     uint32_t weights_cap = 0;  // capacity of the weight buffers: max(max_particles, global particle count)
     struct gm_dist* dist = nullptr;  // multi-GPU state (gm_dist.cu), null on a single GPU
 };
 
+
+extern "C" int gmi_register_finish(gm_ctx* ctx);
 
 inline int fail(gm_ctx* c, int code, const char* fmt, ...) {
     char buf[512];
@@ -154,7 +158,8 @@ inline int ready(gm_ctx* ctx, bool need_particles) {
     if (!ctx->laser_set) return fail(ctx, GM_ERR_ARG, "gm_set_laser has not been called");
     if (!ctx->match_set) return fail(ctx, GM_ERR_ARG, "gm_set_matching has not been called");
     if (need_particles && !ctx->inited) return fail(ctx, GM_ERR_ARG, "gm_init_particles has not been called");
-    return bind(ctx);
+    if (int r = bind(ctx)) return r;
+    return ctx->reg_pending ? gmi_register_finish(ctx) : GM_OK;  // an asynchronous registration reports here
 }
 
 
@@ -164,6 +169,7 @@ int gmi_stage(gm_ctx* ctx, const double* ranges, const double* poses);
 int gmi_remap(gm_ctx* ctx, const uint32_t* idx, uint32_t src_limit);
 int gmi_bounds_and_resize(gm_ctx* ctx);
 int gmi_register_update(gm_ctx* ctx);
+int gmi_register_finish(gm_ctx* ctx);
 int gmi_ensure_dir_cap(gm_ctx* ctx, int need);
 void gmi_dist_destroy(gm_ctx* ctx);
 }

@@ -206,6 +206,7 @@ int gm_dist_allgather(gm_ctx* ctx, const double* local, uint32_t count, double* 
     if (!ctx || !ctx->dist) return fail(ctx, GM_ERR_ARG, "gm_dist_allgather: gm_dist_init has not been called");
     if (!local || !all || !count) return fail(ctx, GM_ERR_ARG, "gm_dist_allgather: bad argument");
     if (int r = bind(ctx)) return r;
+    if (int r = gmi_register_finish(ctx)) return r;
     gm_dist* d = ctx->dist;
     const size_t total = (size_t)count * d->world;
     if (total > d->gather_cap) { CK(dalloc(d->d_gin, count)); CK(dalloc(d->d_gout, total)); d->gather_cap = total; }
@@ -216,6 +217,7 @@ int gm_dist_allgather(gm_ctx* ctx, const double* local, uint32_t count, double* 
     CK(cudaMemcpyAsync(all, d->d_gout, sizeof(double) * total, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     CK(cudaEventElapsedTime(&ctx->stats.ms_allgather, d->e0, d->e1));
+    ctx->stats.total_ms[5] += ctx->stats.ms_allgather;
     return GM_OK;
 }
 

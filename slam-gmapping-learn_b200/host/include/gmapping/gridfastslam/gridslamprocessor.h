@@ -134,6 +134,10 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
         // wall clock of the host-side parts of the last processScan (ms): motion model, scanMatch call incl. transfers,
         // both updateTreeWeights (normalize on the GPU + tree propagation), resample call incl. registration
         double msHostMotion, msHostScanMatch, msHostTreeWeights, msHostResample;
+        // running totals since init(): device ms per stage (scanmatch, weights, remap, register, migrate, allgather), host ms
+        // (motion, scanMatch call, tree weights, resample call), work done
+        double totalMs[6], totalHostMs[4];
+        unsigned long long totalBeamEvals, totalScoreEvals, totalScanMatches;
     };
     DeviceStats deviceStats() const;
     // Multi-GPU sharding (call before init): this process is rank `rank` of `world`, one GPU each; ncclId is the 128-byte
@@ -207,6 +211,7 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     bool m_weightsChanged = true;  // a particle's log-weight changed since the last normalize()
     mutable bool m_treeDirty = false;
     double m_hostMs[4];
+    double m_hostMsTotal[4] = {0, 0, 0, 0};
     std::vector<double> m_poseBuf, m_scoreBuf, m_likBuf;
 };
 

@@ -92,6 +92,7 @@ GridSlamProcessor::GridSlamProcessor(const GridSlamProcessor& gsp)
       m_treeEpoch(0) {
     if (gsp.m_world > 1) b200::fatal("GridSlamProcessor copy / clone(): a sharded filter cannot be cloned");
     m_hostMs[0] = m_hostMs[1] = m_hostMs[2] = m_hostMs[3] = 0;
+    m_hostMsTotal[0] = m_hostMsTotal[1] = m_hostMsTotal[2] = m_hostMsTotal[3] = 0;
     if (!gsp.m_device) return;
     m_device.reset(new b200::DeviceContext(*gsp.m_device, 0));
     const TNodeVector leaves = gsp.getTrajectories();
@@ -184,6 +185,9 @@ void GridSlamProcessor::init(unsigned int size, double xmin, double ymin, double
     m_device->check(gm_init_particles(m_device->h, m_localCount, center, xmax - xmin, ymax - ymin, delta), "gm_init_particles");
     m_device->particles = m_localCount;
     if (m_world > 1) m_device->check(gm_dist_init(m_device->h, m_rank, m_world, m_ncclId), "gm_dist_init");
+    // the registration kernels keep running while processScan finishes its host-side bookkeeping (tree weights) and the
+    // caller prepares the next reading; the next device call collects them
+    m_device->check(gm_set_async_register(m_device->h, 1), "gm_set_async_register");
 
     TNode* root = new TNode(initialPose, 0, 0, 0);
     ScanMatcherMap mirror(Point(center[0], center[1]), 0., 0., delta);  // geometry + cells arrive with the first pull
@@ -522,6 +526,7 @@ bool GridSlamProcessor::processScan(const RangeReading& reading, int adaptPartic
         processed = true;
         for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it) it->previousPose = it->pose;
     }
+    for (int k = 0; k < 4; k++) m_hostMsTotal[k] += m_hostMs[k];
     if (m_outputStream.is_open()) m_outputStream << std::flush;
     m_readingCount++;
     return processed;
@@ -596,6 +601,9 @@ GridSlamProcessor::DeviceStats GridSlamProcessor::deviceStats() const {
     d.msScanMatch = s.ms_scanmatch; d.msWeights = s.ms_weights; d.msRemap = s.ms_remap; d.msRegister = s.ms_register;
     d.beamEvals = s.beam_evals; d.scoreEvals = s.score_evals; d.cowCopies = s.cow_copies; d.patchAllocs = s.patch_allocs;
     d.freeUpdates = s.free_updates; d.hitUpdates = s.hit_updates; d.poolInUse = s.pool_in_use; d.launches = s.launches;
+    for (int k = 0; k < 6; k++) d.totalMs[k] = s.total_ms[k];
+    for (int k = 0; k < 4; k++) d.totalHostMs[k] = m_hostMsTotal[k];
+    d.totalBeamEvals = s.total_beam_evals; d.totalScoreEvals = s.total_score_evals; d.totalScanMatches = s.total_scanmatches;
     d.msHostMotion = m_hostMs[0]; d.msHostScanMatch = m_hostMs[1]; d.msHostTreeWeights = m_hostMs[2]; d.msHostResample = m_hostMs[3];
     d.msMigrate = s.ms_migrate; d.msAllGather = s.ms_allgather; d.migratedParticles = s.migrated_particles; d.migratedBytes = s.migrated_bytes;
     return d;

@@ -11,7 +11,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 HOST_LIB = os.path.join(HERE, "host", "libgridfastslam_b200.so")
 STAT_KEYS = ["ms_scanmatch", "ms_weights", "ms_remap", "ms_register", "ms_migrate", "ms_allgather", "beam_evals", "score_evals",
              "cow_copies", "patch_allocs", "free_updates", "hit_updates", "pool_in_use", "launches", "migrated_particles", "migrated_bytes",
-             "host_ms_motion", "host_ms_scanmatch", "host_ms_treeweights", "host_ms_resample"]
+             "host_ms_motion", "host_ms_scanmatch", "host_ms_treeweights", "host_ms_resample",
+             "total_ms_scanmatch", "total_ms_weights", "total_ms_remap", "total_ms_register", "total_ms_migrate", "total_ms_allgather",
+             "total_host_ms_motion", "total_host_ms_scanmatch", "total_host_ms_treeweights", "total_host_ms_resample",
+             "total_beam_evals", "total_score_evals", "total_scanmatches"]
 PARAM_ORDER = ["maxUrange", "maxrange", "sigma", "kernelSize", "lstep", "astep", "iterations", "lsigma", "ogain", "lskip", "srr", "srt", "str",
                "stt", "linearUpdate", "angularUpdate", "resampleThreshold", "period", "generate_map", "minimumScore"]
 DEFAULTS = dict(maxUrange=80., maxrange=80., sigma=0.05, kernelSize=1, lstep=0.05, astep=0.05, iterations=5, lsigma=0.075, ogain=3., lskip=0,
@@ -121,7 +124,7 @@ class Processor:
         f = self.L.gmh_first_local(self.h); return f, f + self.L.gmh_local_particles(self.h)
 
     def stats(self):
-        a = np.zeros(20); self.L.gmh_device_stats(self.h, _dp(a)); return dict(zip(STAT_KEYS, a.tolist()))
+        a = np.zeros(33); self.L.gmh_device_stats(self.h, _dp(a)); return dict(zip(STAT_KEYS, a.tolist()))
 
     def map_digests(self):
         nl = self.L.gmh_local_particles(self.h)
