@@ -101,27 +101,27 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     virtual void onResampleUpdate();
     virtual void onScanmatchUpdate();
 
-    MEMBER_PARAM_SET_GET(m_matcher, double, laserMaxRange, protected, public, public);
-    MEMBER_PARAM_SET_GET(m_matcher, double, usableRange, protected, public, public);
-    MEMBER_PARAM_SET_GET(m_matcher, double, gaussianSigma, protected, public, public);
-    MEMBER_PARAM_SET_GET(m_matcher, double, likelihoodSigma, protected, public, public);
-    MEMBER_PARAM_SET_GET(m_matcher, int, kernelSize, protected, public, public);
-    MEMBER_PARAM_SET_GET(m_matcher, double, optAngularDelta, protected, public, public);
-    MEMBER_PARAM_SET_GET(m_matcher, double, optLinearDelta, protected, public, public);
-    MEMBER_PARAM_SET_GET(m_matcher, unsigned int, optRecursiveIterations, protected, public, public);
-    MEMBER_PARAM_SET_GET(m_matcher, unsigned int, likelihoodSkip, protected, public, public);
-    MEMBER_PARAM_SET_GET(m_matcher, double, llsamplerange, protected, public, public);
-    MEMBER_PARAM_SET_GET(m_matcher, double, lasamplerange, protected, public, public);
-    MEMBER_PARAM_SET_GET(m_matcher, double, llsamplestep, protected, public, public);
-    MEMBER_PARAM_SET_GET(m_matcher, double, lasamplestep, protected, public, public);
-    MEMBER_PARAM_SET_GET(m_matcher, bool, generateMap, protected, public, public);
-    MEMBER_PARAM_SET_GET(m_matcher, bool, enlargeStep, protected, public, public);
-    MEMBER_PARAM_SET_GET(m_matcher, OrientedPoint, laserPose, protected, public, public);
-
-    STRUCT_PARAM_SET_GET(m_motionModel, double, srr, protected, public, public);
-    STRUCT_PARAM_SET_GET(m_motionModel, double, srt, protected, public, public);
-    STRUCT_PARAM_SET_GET(m_motionModel, double, str, protected, public, public);
-    STRUCT_PARAM_SET_GET(m_motionModel, double, stt, protected, public, public);
+    // parameter accessors forwarded to the matcher / the motion model: get<name>() / set<name>(value), the names the
+    // reference generates with MEMBER_PARAM_SET_GET / STRUCT_PARAM_SET_GET (gridslamprocessor.h:220-245)
+#define GMB200_MATCHER_PARAM(type, name)                               \
+    inline type get##name() const { return m_matcher.get##name(); }   \
+    inline void set##name(type value) { m_matcher.set##name(value); }
+#define GMB200_MOTION_PARAM(name)                                      \
+    inline double get##name() const { return m_motionModel.name; }    \
+    inline void set##name(double value) { m_motionModel.name = value; }
+    GMB200_MATCHER_PARAM(double, laserMaxRange) GMB200_MATCHER_PARAM(double, usableRange)
+    GMB200_MATCHER_PARAM(double, gaussianSigma) GMB200_MATCHER_PARAM(double, likelihoodSigma)
+    GMB200_MATCHER_PARAM(int, kernelSize)
+    GMB200_MATCHER_PARAM(double, optAngularDelta) GMB200_MATCHER_PARAM(double, optLinearDelta)
+    GMB200_MATCHER_PARAM(unsigned int, optRecursiveIterations) GMB200_MATCHER_PARAM(unsigned int, likelihoodSkip)
+    GMB200_MATCHER_PARAM(double, llsamplerange) GMB200_MATCHER_PARAM(double, lasamplerange)
+    GMB200_MATCHER_PARAM(double, llsamplestep) GMB200_MATCHER_PARAM(double, lasamplestep)
+    GMB200_MATCHER_PARAM(bool, generateMap)
+    GMB200_MATCHER_PARAM(bool, enlargeStep)  // sic: the reference forwards this double as a bool
+    GMB200_MATCHER_PARAM(OrientedPoint, laserPose)
+    GMB200_MOTION_PARAM(srr) GMB200_MOTION_PARAM(srt) GMB200_MOTION_PARAM(str) GMB200_MOTION_PARAM(stt)
+#undef GMB200_MATCHER_PARAM
+#undef GMB200_MOTION_PARAM
 
     PARAM_SET_GET(double, minimumScore, protected, public, public);
 

@@ -11,30 +11,40 @@
 namespace GMapping {
 
 class SENSOR_RANGE_EXPORT RangeSensor : public Sensor {
-    friend class Configuration;
-    friend class CarmenConfiguration;
-    friend class CarmenWrapper;
-
   public:
+    // one beam: where it leaves the sensor (pose.theta is the beam angle), its opening (0 = a line), its reach,
+    // and the cached sine / cosine of the angle
     struct Beam {
-        OrientedPoint pose;  // relative to the sensor centre; theta is the beam angle
-        double span;         // 0 = line-like beam
+        OrientedPoint pose;
+        double span;
         double maxRange;
-        double s, c;         // sin / cos of pose.theta
+        double s, c;
     };
-    RangeSensor(std::string name);
-    // `beams` beams, `res` radians apart, starting at -res*beams/2 and accumulated with += (not i*res)
+    typedef std::vector<Beam> BeamVector;
+
+    // a sensor whose beam table is filled in by a configuration reader (the friends below)
+    explicit RangeSensor(std::string name);
+    // `beams` beams, `res` radians apart: the first at -res*beams/2, each next one by += res (an accumulated sum, not
+    // i*res -- the table's rounding is part of what the scan matcher sees)
     RangeSensor(std::string name, unsigned int beams, double res, const OrientedPoint& position = OrientedPoint(0, 0, 0),
                 double span = 0, double maxrange = 89.0);
-    inline const std::vector<Beam>& beams() const { return m_beams; }
-    inline std::vector<Beam>& beams() { return m_beams; }
-    inline OrientedPoint getPose() const { return m_pose; }
+
+    // recompute Beam::s / Beam::c from the beam angles
     void updateBeamsLookup();
-    bool newFormat;
+
+    inline OrientedPoint getPose() const { return m_pose; }
+    inline BeamVector& beams() { return m_beams; }
+    inline const BeamVector& beams() const { return m_beams; }
+
+    bool newFormat;  // CARMEN ROBOTLASERx message layout instead of FLASER/RLASER
 
   protected:
+    BeamVector m_beams;
     OrientedPoint m_pose;
-    std::vector<Beam> m_beams;
+
+    friend class CarmenWrapper;
+    friend class CarmenConfiguration;
+    friend class Configuration;
 };
 
 }  // namespace GMapping

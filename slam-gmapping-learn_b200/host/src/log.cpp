@@ -168,9 +168,8 @@ SensorStream& InputSensorStream::operator>>(const SensorReading*& reading) {
     return *this;
 }
 
-LogSensorStream::LogSensorStream(const SensorMap& sensorMap, const SensorLog* log) : SensorStream(sensorMap), m_log(log) {
+LogSensorStream::LogSensorStream(const SensorMap& sensorMap, const SensorLog* log) : SensorStream(sensorMap), m_cursor(log->begin()), m_log(log) {
     assert(m_log);
-    m_cursor = log->begin();
 }
 LogSensorStream::operator bool() const { return m_cursor == m_log->end(); }  // sic: the reference reports "true" at the end
 bool LogSensorStream::rewind() { m_cursor = m_log->begin(); return true; }

@@ -61,7 +61,7 @@ OdometryReading::OdometryReading(const OdometrySensor* odo, double time) : Senso
 
 RangeSensor::RangeSensor(std::string name) : Sensor(name), newFormat(false) {}
 RangeSensor::RangeSensor(std::string name, unsigned int beams_num, double res, const OrientedPoint& position, double span, double maxrange)
-    : Sensor(name), newFormat(false), m_pose(position), m_beams(beams_num) {
+    : Sensor(name), newFormat(false), m_beams(beams_num), m_pose(position) {
     double angle = -.5 * res * beams_num;  // accumulated, not i * res: the table's rounding is part of the matcher's input
     for (unsigned int i = 0; i < beams_num; i++, angle += res) {
         Beam& b = m_beams[i];
