@@ -264,3 +264,57 @@ def test_occupancy_export_and_standalone_optimize():
         so, po = orc.optimize(m, maps[j], init[j], log.ranges[-1])
         assert abs(sc[j] - so) <= TIGHT * max(1.0, abs(so)) and np.abs(out[j] - po).max() <= TIGHT
     ctx.close()
+
+
+@pytest.mark.parametrize("variant", ["laser_offset", "odo_gain", "beams_skip", "kernel0", "kernel3", "threshold", "beams2047", "lskip3"])
+def test_parameter_variants_vs_oracle(variant):
+    """Paths that the default configuration never takes: laser mounted off-centre (scanmatcher.h:177-180), the odometry
+    prior of optimize() (scanmatcher.cpp:497-509), initialBeamsSkip, other kernel sizes, a non-default fullnessThreshold
+    (generic occupancy test), the largest beam count the reference allows (2047), likelihoodSkip."""
+    import importlib
+    gm = importlib.import_module("slam-gmapping-learn_b200")
+    synth = importlib.import_module("slam-gmapping-learn_b200.synth")
+    laser = synth.LaserSpec(2047, 270.0 / 2046, 30.0) if variant == "beams2047" else synth.LMS200
+    log = synth.make_log("room", laser, scans=5, step=0.4, seed=21)
+    kw = dict(urange=laser.max_range - 1.0, range_=laser.max_range)
+    lp = (0.0, 0.0, 0.0)
+    extra = {}
+    if variant == "laser_offset": lp = (0.2, 0.05, 0.1)
+    if variant == "odo_gain": extra = dict(angular_odometry_reliability=2.0, linear_odometry_reliability=5.0)
+    if variant == "beams_skip": extra = dict(initial_beams_skip=7)
+    if variant == "kernel0": kw["kernel"] = 0
+    if variant == "kernel3": kw["kernel"] = 3
+    if variant == "threshold": extra = dict(fullness_threshold=0.25)
+    if variant == "lskip3": kw["lskip"] = 3
+    n = 4
+    m = orc.make_matcher(laser.angles(), lp, **kw)
+    for k, v in extra.items():
+        setattr(m, k, v)
+    ctx = gm.GmContext(n, pool_patches=4096)
+    ctx.set_laser(laser.angles(), lp)
+    ctx.set_matching(**kw, **extra)
+    ctx.init_particles(n)
+    maps = [orc.Map() for _ in range(n)]
+    rng = np.random.default_rng(3)
+    for k in range(4):
+        poses = log.odom[k][None, :] + rng.normal(0, [0.02, 0.02, 0.01], size=(n, 3))
+        for j in range(n):
+            orc.register(m, maps[j], poses[j], log.ranges[k])
+        ctx.register(log.ranges[k], poses)
+    d = ctx.digests()
+    for j in range(n):
+        od = maps[j].digest()
+        assert (int(d["patches"][j]), int(d["cells"][j]), int(d["sum_n"][j]), int(d["sum_visits"][j]), int(d["hash_counts"][j])) == \
+               (od.patches, od.cells, od.sum_n, od.sum_visits, od.hash_counts), variant
+    r = log.ranges[4]
+    init = log.odom[4][None, :] + rng.normal(0, [0.05, 0.05, 0.03], size=(n, 3))
+    out, sc, s, l, c, ev = ctx.scanmatch(r, init, 0.0)
+    for j in range(n):
+        m.score_calls = 0
+        so, po = orc.optimize(m, maps[j], init[j], r)
+        assert ev[j] == m.score_calls, variant
+        assert abs(sc[j] - so) <= TIGHT * max(1.0, abs(so)) and np.abs(out[j] - po).max() <= TIGHT, variant
+        s1, l1, c1 = orc.likelihood_and_score(m, maps[j], po, r)
+        assert abs(l[j] - l1) <= TIGHT * max(1.0, abs(l1)) and c[j] == c1 and abs(s[j] - s1) <= TIGHT * max(1.0, abs(s1)), variant
+    assert sc.max() > 5
+    ctx.close()
