@@ -100,6 +100,18 @@ class TraceProcessor : public GridSlamProcessor {
                 probes.insert(probes.end(), row, row + 8);
             }
         w.vec("PROB", probes);
+        // sampled variants on particle 0's map: likelihood() over the pose grid and optimize(mean, cov, ...)
+        {
+            const Particle& p = m_particles[0];
+            OrientedPoint q(pre_pose[0], pre_pose[1], pre_pose[2]);
+            double lmax; OrientedPoint mean; ScanMatcher::CovarianceMatrix cov;
+            const double lsum = m_matcher.likelihood(lmax, mean, cov, p.map, q, cur_ranges);
+            OrientedPoint omean; ScanMatcher::CovarianceMatrix ocov;
+            const double osc = m_matcher.optimize(omean, ocov, p.map, q, cur_ranges);
+            const double row[22] = {lsum, lmax, mean.x, mean.y, mean.theta, cov.xx, cov.yy, cov.tt, cov.xy, cov.xt, cov.yt,
+                                    osc, omean.x, omean.y, omean.theta, ocov.xx, ocov.yy, ocov.tt, ocov.xy, ocov.xt, ocov.yt, 0};
+            w.rec("LIKE", row, sizeof row);
+        }
     }
     void onResampleUpdate() override {
         resampled = true;

@@ -46,6 +46,8 @@ def read_trace(path):
             cur["smat"] = np.frombuffer(p, dtype="<f8").reshape(-1, 15).copy()
         elif tag == "PROB":
             cur["probes"] = np.frombuffer(p, dtype="<f8").reshape(-1, 8).copy()
+        elif tag == "LIKE":
+            cur["like"] = np.frombuffer(p, dtype="<f8").copy()
         elif tag == "RNEF":
             cur["neff_at_resample"] = float(np.frombuffer(p, dtype="<f8")[0])
         elif tag == "RWGT":

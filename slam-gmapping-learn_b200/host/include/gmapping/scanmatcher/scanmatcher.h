@@ -43,13 +43,14 @@ class SCANMATCHER_EXPORT ScanMatcher {
     void setMatchingParameters(double urange, double range, double sigma, int kernsize, double lopt, double aopt, int iterations,
                                double likelihoodSigma = 1, unsigned int likelihoodSkip = 0);
 
-    // Sampled-likelihood / ICP variants (scanmatcher.cpp:356-375, 541-690, 711-856): outside the per-scan particle
-    // update.  Declared for source compatibility; calling them aborts with a message.
-    double icpOptimize(OrientedPoint& pnew, const ScanMatcherMap& map, const OrientedPoint& p, const double* readings) const;
+    // sampled variants (scanmatcher.cpp:541-690, :711-780): the pose samples are scored on the GPU in
+    // batched likelihoodAndScore queries, the moment sums over the few dozen samples are formed on the host
     double optimize(OrientedPoint& mean, CovarianceMatrix& cov, const ScanMatcherMap& map, const OrientedPoint& p, const double* readings) const;
-    double icpStep(OrientedPoint& pret, const ScanMatcherMap& map, const OrientedPoint& p, const double* readings) const;
     double likelihood(double& lmax, OrientedPoint& mean, CovarianceMatrix& cov, const ScanMatcherMap& map, const OrientedPoint& p,
                       const double* readings);
+    // ICP variants (scanmatcher.cpp:356-375): not on the particle-update path; declared for source compatibility, abort if called
+    double icpOptimize(OrientedPoint& pnew, const ScanMatcherMap& map, const OrientedPoint& p, const double* readings) const;
+    double icpStep(OrientedPoint& pret, const ScanMatcherMap& map, const OrientedPoint& p, const double* readings) const;
 
     inline const double* laserAngles() const { return m_laserAngles; }
     inline unsigned int laserBeams() const { return m_laserBeams; }

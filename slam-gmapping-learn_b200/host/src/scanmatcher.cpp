@@ -5,6 +5,7 @@
 #include <cassert>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "devicemap.h"
 
@@ -132,16 +133,137 @@ double ScanMatcher::registerScan(ScanMatcherMap& map, const OrientedPoint& p, co
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------ sampled variants
+// (reference: scanmatcher/scanmatcher.cpp:541-690 and :711-780).  The pose samples are evaluated on the GPU in one
+// batched likelihoodAndScore query per step; only the few-dozen-term moment sums are formed here.
+namespace {
+
+struct Sample { OrientedPoint pose; double score, likelihood; };
+
+// likelihoodAndScore of every pose on `map`, one launch
+void evaluate(const ScanMatcher& m, const ScanMatcherMap& map, const double* readings, std::vector<Sample>& samples, size_t first) {
+    b200::DeviceMapResidency* r = b200::makeResident(map, m);
+    const size_t n = samples.size() - first;
+    if (!n) return;
+    std::vector<uint32_t> idx(n, r->slot), c(n);
+    std::vector<double> poses(3 * n), s(n), l(n);
+    for (size_t i = 0; i < n; i++) {
+        const OrientedPoint& q = samples[first + i].pose;
+        poses[3 * i] = q.x; poses[3 * i + 1] = q.y; poses[3 * i + 2] = q.theta;
+    }
+    r->ctx->check(gm_likelihood_and_score(r->ctx->h, (uint32_t)n, idx.data(), poses.data(), readings, s.data(), l.data(), c.data()),
+                  "gm_likelihood_and_score");
+    for (size_t i = 0; i < n; i++) { samples[first + i].score = s[i]; samples[first + i].likelihood = l[i]; }
+}
+
+// second moments of the samples about `mean`, weighted by Sample::likelihood (already exponentiated), divided by `norm`
+ScanMatcher::CovarianceMatrix spread(const std::vector<Sample>& samples, const OrientedPoint& mean, double norm) {
+    ScanMatcher::CovarianceMatrix cov = {0., 0., 0., 0., 0., 0.};
+    for (size_t i = 0; i < samples.size(); i++) {
+        OrientedPoint d = samples[i].pose - mean;
+        d.theta = atan2(sin(d.theta), cos(d.theta));
+        const double w = samples[i].likelihood;
+        cov.xx += d.x * d.x * w; cov.yy += d.y * d.y * w; cov.tt += d.theta * d.theta * w;
+        cov.xy += d.x * d.y * w; cov.xt += d.x * d.theta * w; cov.yt += d.y * d.theta * w;
+    }
+    cov.xx /= norm, cov.xy /= norm, cov.xt /= norm, cov.yy /= norm, cov.yt /= norm, cov.tt /= norm;
+    return cov;
+}
+
+}  // namespace
+
+// hill-climb like optimize(pnew, ...), but driven by likelihoodAndScore's score, remembering every evaluated pose;
+// returns the best score, _mean = the climbed pose, _cov = likelihood-weighted spread of the evaluated poses
+double ScanMatcher::optimize(OrientedPoint& _mean, CovarianceMatrix& _cov, const ScanMatcherMap& map, const OrientedPoint& init,
+                             const double* readings) const {
+    std::vector<Sample> moves(1);
+    moves[0].pose = init;
+    evaluate(*this, map, readings, moves, 0);
+    OrientedPoint current = init;
+    double bestScore = -1, currentScore = moves[0].score;
+    double adelta = m_optAngularDelta, ldelta = m_optLinearDelta;
+    unsigned int refinement = 0;
+    do {
+        if (bestScore >= currentScore) { refinement++; adelta *= .5; ldelta *= .5; }
+        bestScore = currentScore;
+        const size_t first = moves.size();
+        for (int k = 0; k < 6; k++) {  // Front, Back, Left, Right, TurnLeft, TurnRight
+            Sample c;
+            c.pose = current; c.score = c.likelihood = 0;
+            switch (k) {
+                case 0: c.pose.x += ldelta; break;
+                case 1: c.pose.x -= ldelta; break;
+                case 2: c.pose.y -= ldelta; break;
+                case 3: c.pose.y += ldelta; break;
+                case 4: c.pose.theta += adelta; break;
+                default: c.pose.theta -= adelta; break;
+            }
+            moves.push_back(c);
+        }
+        evaluate(*this, map, readings, moves, first);  // the six candidates in one launch
+        OrientedPoint bestLocal = current;
+        for (size_t i = first; i < moves.size(); i++)  // the score that drives this variant is likelihoodAndScore's, undamped
+            if (moves[i].score > currentScore) { currentScore = moves[i].score; bestLocal = moves[i].pose; }
+        current = bestLocal;
+    } while (currentScore > bestScore || refinement < m_optRecursiveIterations);
+
+    double lmax = -1e9;
+    for (size_t i = 0; i < moves.size(); i++) lmax = moves[i].likelihood > lmax ? moves[i].likelihood : lmax;
+    double lacc = 0;
+    OrientedPoint mean(0, 0, 0);
+    for (size_t i = 0; i < moves.size(); i++) {
+        moves[i].likelihood = exp(moves[i].likelihood - lmax);
+        mean = mean + moves[i].pose * moves[i].likelihood;
+        lacc += moves[i].likelihood;
+    }
+    mean = mean * (1. / lacc);
+    _cov = spread(moves, mean, lacc);
+    _mean = current;
+    return bestScore;
+}
+
+// likelihood of the scan integrated over a regular grid of poses around p (+-llsamplerange in x / y, +-lasamplerange in
+// theta); returns log(sum exp(l)), _lmax = the largest log-likelihood, _mean / _cov = moments of the sampled poses
+double ScanMatcher::likelihood(double& _lmax, OrientedPoint& _mean, CovarianceMatrix& _cov, const ScanMatcherMap& map, const OrientedPoint& p,
+                               const double* readings) {
+    std::vector<Sample> samples;
+    for (double xx = -m_llsamplerange; xx <= m_llsamplerange; xx += m_llsamplestep)
+        for (double yy = -m_llsamplerange; yy <= m_llsamplerange; yy += m_llsamplestep)
+            for (double tt = -m_lasamplerange; tt <= m_lasamplerange; tt += m_lasamplestep) {
+                Sample q;
+                q.pose = OrientedPoint(p.x + xx, p.y + yy, p.theta + tt);
+                q.score = q.likelihood = 0;
+                samples.push_back(q);
+            }
+    evaluate(*this, map, readings, samples, 0);
+    double lmax = -1e9;
+    for (size_t i = 0; i < samples.size(); i++) lmax = samples[i].likelihood > lmax ? samples[i].likelihood : lmax;
+    double lcum = 0, s = 0, c = 0;
+    OrientedPoint mean(0, 0, 0);
+    for (size_t i = 0; i < samples.size(); i++) {
+        samples[i].likelihood = exp(samples[i].likelihood - lmax);
+        lcum += samples[i].likelihood;
+    }
+    for (size_t i = 0; i < samples.size(); i++) {
+        mean = mean + samples[i].pose * samples[i].likelihood;
+        s += samples[i].likelihood * sin(samples[i].pose.theta);
+        c += samples[i].likelihood * cos(samples[i].pose.theta);
+    }
+    mean = mean * (1. / lcum);
+    s /= lcum;
+    c /= lcum;
+    mean.theta = atan2(s, c);  // circular mean for the heading
+    _cov = spread(samples, mean, lcum);
+    _mean = mean;
+    _lmax = lmax;
+    return log(lcum) + lmax;
+}
+
+// ICP variants (scanmatcher.cpp:356-375, scanmatcher.h icpStep): outside the per-scan particle update
 static double notOnPath(const char* what) {
-    b200::fatal(std::string(what) + " is not part of the per-scan particle update and is not implemented in this build (SURVEY.md §8 f4)");
+    b200::fatal(std::string(what) + " is not part of the per-scan particle update and is not implemented in this build (SURVEY.md §2 row 9)");
 }
 double ScanMatcher::icpOptimize(OrientedPoint&, const ScanMatcherMap&, const OrientedPoint&, const double*) const { return notOnPath("ScanMatcher::icpOptimize"); }
-double ScanMatcher::optimize(OrientedPoint&, CovarianceMatrix&, const ScanMatcherMap&, const OrientedPoint&, const double*) const {
-    return notOnPath("ScanMatcher::optimize(mean, cov, ...)");
-}
 double ScanMatcher::icpStep(OrientedPoint&, const ScanMatcherMap&, const OrientedPoint&, const double*) const { return notOnPath("ScanMatcher::icpStep"); }
-double ScanMatcher::likelihood(double&, OrientedPoint&, CovarianceMatrix&, const ScanMatcherMap&, const OrientedPoint&, const double*) {
-    return notOnPath("ScanMatcher::likelihood");
-}
 
 }  // namespace GMapping

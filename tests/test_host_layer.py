@@ -107,6 +107,11 @@ def test_free_running_trace_matches_reference(case):
             np.testing.assert_allclose(r["smat"][:, 8], ref[:, 8], rtol=1e-3, err_msg="%s[%d] log-likelihood" % (case, i))
             np.testing.assert_allclose(r["smat"][:, 3], ref[:, 3], rtol=1e-6, err_msg="%s[%d] optimize score via m_matcher" % (case, i))
             np.testing.assert_allclose(r["probes"][:, 4:7], g.probes[i][:len(r["probes"]), 4:7], rtol=1e-6, atol=1e-9)
+            # ScanMatcher::likelihood(lmax, mean, cov, ...) and optimize(mean, cov, ...) on particle 0's map
+            np.testing.assert_allclose(r["like"][:5], g.like[i][:5], rtol=1e-6, atol=1e-9, err_msg="%s[%d] likelihood()" % (case, i))
+            np.testing.assert_allclose(r["like"][5:11], g.like[i][5:11], rtol=1e-4, atol=1e-12, err_msg="%s[%d] likelihood() covariance" % (case, i))
+            np.testing.assert_allclose(r["like"][11:15], g.like[i][11:15], rtol=1e-6, atol=1e-9, err_msg="%s[%d] optimize(mean, cov)" % (case, i))
+            np.testing.assert_allclose(r["like"][15:21], g.like[i][15:21], rtol=1e-4, atol=1e-12, err_msg="%s[%d] optimize(mean, cov) covariance" % (case, i))
         if r["resampled"]:
             assert np.array_equal(r["indexes"], g.ridx[i]), "%s[%d] resample indexes" % (case, i)
             np.testing.assert_allclose(r["neff_at_resample"], g.rneff[i], rtol=1e-6)
