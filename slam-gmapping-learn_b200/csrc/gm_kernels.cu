@@ -154,20 +154,39 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
         // indexes wait in shared memory (one column per thread) so that the loop can pick them by a run-time index
 #pragma unroll
         for (int i = 0; i < 9; i++) ci_smem[i * kSmThreads] = ci[i];
-        while (mask) {
-            const int i = __ffs(mask) - 1;
-            mask &= mask - 1;
-            if (fcheck) {
+        if (!fcheck) {
+            // two cells per trip: their load -> reciprocal -> distance chains are independent and overlap; the comparisons
+            // still run in scan order (i before j), so ties resolve as in the reference
+            while (mask) {
+                const int i = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const bool two = mask != 0;
+                const int j = two ? __ffs(mask) - 1 : i;
+                mask &= mask - 1;  // no-op when mask is already 0
+                const int4 ca = __ldg(M.pool + ci_smem[i * kSmThreads]);
+                const int4 cb = __ldg(M.pool + ci_smem[j * kSmThreads]);
+                const double ia = ca.z < kInvTable ? __ldg(M.inv_n + ca.z) : recip_slow(ca.z);  // mean() = (1./n) * acc, smmap.h:24
+                const double ib = cb.z < kInvTable ? __ldg(M.inv_n + cb.z) : recip_slow(cb.z);
+                const double ax = phx - (double)__int_as_float(ca.x) * ia, ay = phy - (double)__int_as_float(ca.y) * ia;
+                const double bxx = phx - (double)__int_as_float(cb.x) * ib, byy = phy - (double)__int_as_float(cb.y) * ib;
+                const double na = ax * ax + ay * ay, nb = bxx * bxx + byy * byy;
+                if (!found || na < bn) { bx = ax; by = ay; bn = na; found = true; }
+                if (two && nb < bn) { bx = bxx; by = byy; bn = nb; }
+            }
+        } else {
+            while (mask) {
+                const int i = __ffs(mask) - 1;
+                mask &= mask - 1;
                 const int xx = (i * 11) >> 5, yy = i - 3 * xx;  // i / 3, i % 3 for i < 9
                 long long fi; int fn = 0, fv = 0;
                 if (cell_addr(g, M.dirp, x0 + xx + ifx, y0 + yy + ify, fi)) { const int4 f = __ldg(M.pool + fi); fn = f.z; fv = f.w; }
                 if (!is_free<true>(fn, fv, P)) continue;
+                const int4 cell = __ldg(M.pool + ci_smem[i * kSmThreads]);
+                const double inv = cell.z < kInvTable ? __ldg(M.inv_n + cell.z) : recip_slow(cell.z);
+                const double mx = phx - (double)__int_as_float(cell.x) * inv, my = phy - (double)__int_as_float(cell.y) * inv;
+                const double nn = mx * mx + my * my;
+                if (!found || nn < bn) { bx = mx; by = my; bn = nn; found = true; }
             }
-            const int4 cell = __ldg(M.pool + ci_smem[i * kSmThreads]);
-            const double inv = cell.z < kInvTable ? __ldg(M.inv_n + cell.z) : recip_slow(cell.z);  // mean() = (1./n) * acc, smmap.h:24
-            const double mx = phx - (double)__int_as_float(cell.x) * inv, my = phy - (double)__int_as_float(cell.y) * inv;
-            const double nn = mx * mx + my * my;
-            if (!found || nn < bn) { bx = mx; by = my; bn = nn; found = true; }
         }
         bmx = bx; bmy = by;
         return found;
