@@ -59,8 +59,8 @@ __device__ __forceinline__ int cell_index(double d, double delta, double inv_del
     return i;
 }
 
-constexpr int kSmThreads = 256;
-constexpr int kSmGroups = kSmThreads / 6;  // 42 beam groups x 6 candidate poses = 252 working threads
+constexpr int kSmThreads = 288;
+constexpr int kSmGroups = kSmThreads / 6;  // 48 beam groups x 6 candidate poses: every thread works
 
 struct MatchCtx {
     const int* __restrict__ dirp;
@@ -269,8 +269,8 @@ struct SmShared {
     int done;
     // reduction scratch
     double part[kSmThreads];
-    double red[8], red_l[8];
-    unsigned red_c[8], red_v[8];
+    double red[16], red_l[16];
+    unsigned red_c[16], red_v[16];
     // hill-climb state (thread 0 only; shared memory keeps it out of everybody's registers)
     double cur[3], init[3], key[3], currentScore, bestScore, adelta, ldelta;
     unsigned refinement, evals, valid_lik;
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
         if (six) {
             S.part[t] = acc_s;
             __syncthreads();
-            if (warp < 6) {  // warp w sums candidate w's 42 partials: lane j takes groups j and j + 32
+            if (warp < 6) {  // warp w sums the partials of candidate w: lane j takes groups j and j + 32
                 double v = S.part[6 * lane + warp];
                 if (lane + 32 < kSmGroups) v += S.part[6 * (lane + 32) + warp];
                 v = warp_sum(v);
