@@ -387,7 +387,8 @@ int gmi_register_update(gm_ctx* ctx) {
     // visit-count tiles: as many as fit (one pass over the rays when the active area has at most that many patches);
     // with few active patches a smaller allocation lets two CTAs share an SM
     const size_t fixed = register_smem_bytes(a.bitmap_words, 0, (int)ctx->P.nbeams, 0);
-    const size_t budget = 220 * 1024;  // of the 227 KB a CTA may use
+    size_t budget = 220 * 1024;  // of the 227 KB a CTA may use
+    if (const char* e = getenv("GM_B200_REGISTER_SMEM_KB")) budget = (size_t)atoi(e) * 1024;  // experiments: e.g. 110 = two CTAs per SM
     if (fixed + (size_t)a.sort_n * 8 > budget) return fail(ctx, GM_ERR_ARG, "gm_register: patch directory of %d entries needs %zu B of shared memory", ctx->dir_cap, fixed);
     const int tile_cap = (int)((budget - fixed) / 2048);
     a.tile_cap = tile_cap;
