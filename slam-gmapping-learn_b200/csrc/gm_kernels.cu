@@ -3,14 +3,14 @@
 // decisions depend on the exact FP64 evaluation order (SURVEY.md §7 "hard parts").
 //
 // Kernels (one CTA per particle unless noted):
-//   k_scanmatch   ScanMatcher::optimize + likelihoodAndScore           (scanmatcher.cpp:386-529, scanmatcher.h:171-380)
-//   k_eval        standalone score / likelihoodAndScore queries         (scanmatcher.h:171-380)
+//   k_scanmatch   ScanMatcher::optimize + likelihoodAndScore, and the    (scanmatcher.cpp:386-529, scanmatcher.h:171-380)
+//                 standalone score / likelihoodAndScore / optimize queries (A.query)
 //   k_bounds      computeActiveArea's bounding box + Map::resize maths  (scanmatcher.cpp:83-166, map.h:218-241)
 //   k_relayout    HierarchicalArray2D::resize                           (harray2d.h:80-109)
 //   k_register    active area + copy-on-write + ray update + hits       (scanmatcher.cpp:168-354, harray2d.h:169-185)
 //   k_remap/k_sweep/k_merge_free   particle copy by patch reference     (gridslamprocessor.hxx:184-213)
 //   k_normalize / k_resample       (gridslamprocessor.hxx:82-121, particlefilter.h:180-229)
-//   k_digest / k_export_*          map read-back
+//   k_digest / k_export_* / k_export_occupancy / k_install_patches   map read-back, occupancy grid, upload
 #include <algorithm>
 #include <climits>
 
