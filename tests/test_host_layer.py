@@ -202,3 +202,38 @@ def test_clone_continues_identically_and_occupancy_grid():
     assert grid[int(round((y + 100) / 0.05)), int(round((x + 100) / 0.05))] == 0  # the robot stands in free space
     assert a.occupancy(a.best(), x, y) < 0.1
     a.close(); b.close()
+
+
+@pytest.mark.gpu
+def test_thousand_scans_free_running():
+    """BASELINE.json configs[0]/[1]: 30 particles, 181-beam scans, 1000 scans, free running through the C++ API against the
+    unmodified reference (fixture: Neff and flags for every scan, all poses / log-weights every 10th scan): the filter never
+    leaves the reference's trajectory -- same resampling scans, same indexes, poses within 1e-4, log-weights within 1e-3."""
+    build_host()
+    hostapi = importlib.import_module("slam-gmapping-learn_b200.hostapi")
+    z = np.load(os.path.join(ROOT, "tests", "golden", "room181_long.npz"))
+    p = json.loads(str(z["params"]))
+    log = synth.make_log("room", synth.LMS200, scans=int(z["scans"]), step=0.25, seed=int(z["log_seed"]))
+    assert np.array_equal(log.laser.angles(), z["angles"])
+    f = hostapi.Processor(z["angles"], p["particles"], z["head_init"], bounds=(p["xmin"], p["ymin"], p["xmax"], p["ymax"]), delta=p["delta"],
+                          seed=p["seed"], **{k: p[k] for k in hostapi.PARAM_ORDER})
+    kept = {int(s): k for k, s in enumerate(z["kept"])}
+    rsc = {int(s): k for k, s in enumerate(z["ridx_scans"])}
+    worst_pose = worst_w = 0.0
+    for i in range(int(z["scans"])):
+        done = f.process_scan(log.ranges[i], log.odom[i], log.stamps[i])
+        assert done == bool(z["processed"][i])
+        assert f.last_resampled() == bool(z["resampled"][i]), "scan %d: resampling decision" % i
+        assert abs(f.neff() - z["neff"][i]) <= 1e-6 * z["neff"][i], "scan %d: Neff" % i
+        if i in rsc:
+            assert np.array_equal(f.indexes(), z["ridx"][rsc[i]]), "scan %d: resample indexes" % i
+        if i in kept:
+            st = f.state(); k = kept[i]
+            worst_pose = max(worst_pose, float(np.abs(st[:, :3] - z["poses"][k]).max()))
+            worst_w = max(worst_w, float(np.abs(st[:, 3:5] - z["weights"][k]).max() / max(1.0, np.abs(z["weights"][k]).max())))
+            assert np.array_equal(st[:, 5], z["prev"][k])
+    assert worst_pose < 1e-4 and worst_w < 1e-3, (worst_pose, worst_w)
+    d = f.map_digests()
+    assert np.array_equal(d[:, :5], digest_rows(z["digests"])[:, :5]), "final maps: (n, visits) of every cell of every particle"
+    assert f.best() == int(z["best"])
+    f.close()

@@ -103,7 +103,45 @@ def run_case(name, log_kw, par):
         name, S, int(a["processed"].sum()), int(a["resampled"].sum()), os.path.getsize(path) / 1024, out.strip()[:80]))
 
 
+def run_long(name="room181_long", scans=1000, particles=30):
+    """BASELINE.json configs[0]/[1]: 30 particles, 181 beams, 1000 scans.  Too long for a full per-stage trace in the
+    repository: the fixture keeps, per reading, the gate / resample flags, Neff, the resample indexes and the poses +
+    log-weights of all particles (float64), plus the final map digests."""
+    p = dict(DEFAULTS); p.update(dict(particles=particles, linearUpdate=0.2, angularUpdate=0.1, srr=0.05, srt=0.1, str=0.05, stt=0.1, maps_every=0))
+    log = synth.make_log(world="room", laser=synth.LMS200, scans=scans, step=0.25, seed=7)
+    with tempfile.TemporaryDirectory() as td:
+        lp, tp = os.path.join(td, "in.log"), os.path.join(td, "trace.bin")
+        synth.write_carmen(log, lp)
+        cmd = [REF, "-mode", "trace", "-log", lp, "-out", tp, "-probe", "0", "-maps-every", "0"]
+        for k in ("particles", "seed", "kernelSize", "iterations", "lskip"):
+            cmd += ["-" + k, str(int(p[k]))]
+        for k in ("xmin", "ymin", "xmax", "ymax", "delta", "sigma", "maxrange", "maxUrange", "lstep", "astep", "lsigma", "ogain",
+                  "srr", "srt", "str", "stt", "linearUpdate", "angularUpdate", "resampleThreshold", "minimumScore", "period"):
+            cmd += ["-" + k, repr(float(p[k]))]
+        subprocess.run(cmd, check=True, capture_output=True, text=True)
+        tr = read_trace(tp)
+    R = tr["readings"]
+    S, N = len(R), particles
+    state = np.stack([r["state"] for r in R]); neff = np.array([r["neff"] for r in R])
+    resampled = np.array([r["resampled"] for r in R]); processed = np.array([r["processed"] for r in R])
+    ridx = np.zeros((S, N), dtype=np.uint16)
+    for i, r in enumerate(R):
+        if "indexes" in r: ridx[i] = r["indexes"]
+    path = os.path.join(GOLD, name + ".npz")
+    # Neff and the flags for every scan; poses / weights every 10th scan, at the last one and where the filter resampled
+    rs = np.nonzero(resampled)[0]
+    keep = np.union1d(np.union1d(np.arange(0, S, 10), [S - 1]), rs)
+    np.savez_compressed(path, params=np.array(json.dumps(p)), head_init=tr["head"]["init"], angles=tr["angles"],
+                        log_seed=np.array(7), scans=np.array(scans), processed=processed, resampled=resampled, neff=neff,
+                        ridx_scans=rs, ridx=ridx[rs], kept=keep,
+                        poses=state[keep, :, :3], weights=state[keep, :, 3:5].astype(np.float64), prev=state[keep, :, 5].astype(np.int16),
+                        digests=tr["final"]["digests"], geometry=tr["final"]["geometry"], best=np.array(tr["final"]["best"]))
+    print("%-18s readings %4d processed %4d resamples %3d  %7.1f KB" % (name, S, int(processed.sum()), int(resampled.sum()), os.path.getsize(path) / 1024))
+
+
 def main():
+    if "long" in sys.argv[1:]:
+        run_long(); return
     if not os.path.exists(REF):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
     os.makedirs(GOLD, exist_ok=True)
