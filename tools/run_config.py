@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--scans", type=int, default=30)
     ap.add_argument("--particles", type=int, default=0, help="override the particle count (e.g. one GPU's slice of C5)")
     ap.add_argument("--noise", type=float, default=0.01, help="motion noise srr=srt=str=stt")
+    ap.add_argument("--ogain", type=float, default=3.0, help="likelihood gain (obsSigmaGain): small values spread the weights and force real resampling")
+    ap.add_argument("--resample-threshold", type=float, default=0.5, help="resample when Neff < threshold * N (> 1: every scan)")
     args = ap.parse_args()
     import torch
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -54,7 +56,7 @@ def main():
     h = c["half"]
     proc = hostapi.Processor(log.laser.angles(), c["particles"], log.odom[0], bounds=(-h, -h, h, h), delta=c["delta"], seed=12345,
                              rank=rank, world=world, nccl_id=nccl_id, maxUrange=c["urange"], maxrange=c["rng"], linearUpdate=0.2, angularUpdate=0.1,
-                             srr=args.noise, srt=args.noise, str=args.noise, stt=args.noise)
+                             srr=args.noise, srt=args.noise, str=args.noise, stt=args.noise, resampleThreshold=args.resample_threshold, ogain=args.ogain)
     stats = []
     t0 = time.perf_counter()
     for i in range(args.scans):
@@ -69,11 +71,14 @@ def main():
     keys = ("ms_scanmatch", "ms_weights", "ms_remap", "ms_register", "ms_migrate", "ms_allgather")
     out = {"config": args.config, "rank": rank, "world": world, "particles": c["particles"], "beams": log.laser.beams, "delta": c["delta"],
            "scans": args.scans, "resamples": proc.resamples(), "wall_ms_per_scan": 1000 * wall / args.scans,
-           "device_ms_per_scan": float(np.mean([sum(s[k] for k in keys) for s in stats[3:]])),  # scans 0-2: registration only / NCCL connection setup
+           "device_ms_per_scan": float(np.mean([sum(s[k] for k in keys) for s in stats[3:]])),
+           "device_ms_per_scan_median": float(np.median([sum(s[k] for k in keys) for s in stats[3:]])),
+           "migrate_ms_median_when_resampling": float(np.median([s["ms_migrate"] for s in stats[3:] if s["ms_migrate"] > 0] or [0.0])),  # scans 0-2: registration only / NCCL connection setup
            "stage_ms": {k[3:]: float(np.mean([s[k] for s in stats[3:]])) for k in keys},
            "pool_patches_in_use": stats[-1]["pool_in_use"], "patches_per_particle": stats[-1]["pool_in_use"] / max(1, (proc.local_range()[1] - proc.local_range()[0])),
            "hbm_used_gb": (total_b - free_b) / 2**30, "migrated_particles": float(np.sum([s["migrated_particles"] for s in stats])),
            "migrated_mb": float(np.sum([s["migrated_bytes"] for s in stats])) / 2**20, "neff_last": proc.neff(),
+           "distinct_parents_last": int(len(set(proc.indexes().tolist()))) if proc.resamples() else None,
            "best_particle_error_m": truth_err}
     if dist is not None:
         outs = [None] * world
