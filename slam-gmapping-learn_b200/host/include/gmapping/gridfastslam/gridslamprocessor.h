@@ -195,6 +195,7 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
   private:
     void scanMatch(const double* plainReading);
     void normalize();
+    void normalizeIfNeeded();
     bool resample(const double* plainReading, int adaptParticles, const RangeReading* rr = 0);
     void updateTreeWeights(bool weightsAlreadyNormalized = false);
     void resetTree();

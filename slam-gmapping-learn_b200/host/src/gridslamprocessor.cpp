@@ -353,9 +353,14 @@ bool GridSlamProcessor::resample(const double* plainReading, int adaptSize, cons
 }
 
 // ------------------------------------------------------------------------------------------ tree weights
+// normalize() unless no log-weight changed since the last time (the second updateTreeWeights of a processScan that did
+// not resample sees the log-weights of the first: same weights, same Neff)
+void GridSlamProcessor::normalizeIfNeeded() {
+    if (m_weightsChanged || m_weights.size() != m_particles.size()) { normalize(); m_weightsChanged = false; }
+}
+
 void GridSlamProcessor::updateTreeWeights(bool weightsAlreadyNormalized) {
-    // the second call of a processScan that did not resample sees the log-weights of the first: same weights, same Neff
-    if (!weightsAlreadyNormalized && (m_weightsChanged || m_weights.size() != m_particles.size())) { normalize(); m_weightsChanged = false; }
+    if (!weightsAlreadyNormalized) normalizeIfNeeded();
     if (m_lazyTree) { m_treeDirty = true; return; }
     resetTree();
     propagateWeights();
@@ -497,7 +502,11 @@ bool GridSlamProcessor::processScan(const RangeReading& reading, int adaptPartic
             }
             onScanmatchUpdate();
             sw.lap();
-            updateTreeWeights(false);
+            // updateTreeWeights(false): the weights and Neff are needed now; the propagation into the trajectory tree can only be
+            // observed before the second updateTreeWeights below through onResampleUpdate(), i.e. when the filter resamples --
+            // otherwise it is skipped here and the second call, which recomputes every node, does it once
+            normalizeIfNeeded();
+            if (m_neff < m_resampleThreshold * m_particles.size() && !m_lazyTree) { resetTree(); propagateWeights(); }
             m_hostMs[2] += sw.lap();
             if (m_infoStream) m_infoStream << "neff= " << m_neff << endl;
             if (m_outputStream.is_open()) {
