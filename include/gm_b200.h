@@ -30,7 +30,8 @@ typedef enum gm_status {
     GM_ERR_ARG = -2,        /* bad argument / call order */
     GM_ERR_POOL = -3,       /* patch pool exhausted */
     GM_ERR_NO_DEVICE = -4,  /* no usable CUDA device (there is no CPU path) */
-    GM_ERR_LINE = -5        /* a ray longer than the reference's 20000-point buffer (scanmatcher.cpp:55) */
+    GM_ERR_LINE = -5,       /* a ray longer than the reference's 20000-point buffer (scanmatcher.cpp:55) */
+    GM_ERR_INTERNAL = -6    /* gm_map_digest: the occupancy bitmap disagrees with the cells (a bug, never expected) */
 } gm_status;
 
 typedef struct gm_ctx gm_ctx;
@@ -70,7 +71,8 @@ typedef struct gm_map_info {
     int32_t reserved;
 } gm_map_info;
 
-/* order-independent map digest in world-cell coordinates (test / consistency aid) */
+/* order-independent map digest in world-cell coordinates (test / consistency aid); gm_map_digest also verifies the derived
+ * occupancy bitmap the scan matcher reads against the cells and returns GM_ERR_INTERNAL when they disagree */
 typedef struct gm_digest {
     int64_t patches, cells, sum_n, sum_visits;
     uint64_t hash_counts, hash_acc;

@@ -58,6 +58,8 @@ int gm_create(gm_ctx** out, const gm_config* cfg) {
     c->pool.cap = (int)cap;
     CKC(dalloc(c->pool.cells, (cap + 1) * kPatchCells));  // + the all-zero patch at index cap (unknown cells)
     CKC(cudaMemsetAsync(c->pool.cells + cap * kPatchCells, 0, kPatchCells * sizeof(int4), c->st));
+    CKC(dalloc(c->pool.occ, (cap + 1) * kPatch));
+    CKC(cudaMemsetAsync(c->pool.occ, 0, (cap + 1) * kPatch * sizeof(unsigned), c->st));
     CKC(dalloc(c->pool.refcnt, cap)); CKC(dalloc(c->pool.free_list, cap)); CKC(dalloc(c->pool.pending, cap));
     CKC(dalloc(c->pool.free_top, 1)); CKC(dalloc(c->pool.pending_n, 1));
     CKC(dalloc(c->refcnt_new, cap));
@@ -69,14 +71,16 @@ int gm_create(gm_ctx** out, const gm_config* cfg) {
     CKC(dalloc(c->d_score, N)); CKC(dalloc(c->d_s, N)); CKC(dalloc(c->d_l, N));
     CKC(dalloc(c->d_c, N)); CKC(dalloc(c->d_evals, N)); CKC(dalloc(c->d_idx, N)); CKC(dalloc(c->d_emitted, 1));
     CKC(dalloc(c->d_counters, 1));
-    CKC(dalloc(c->d_digest, (size_t)N * 6));
+    CKC(dalloc(c->d_digest, (size_t)N * 7));
     CKC(dalloc(c->d_count, 1));
     {
         // 1./n exactly as the host FPU divides (IEEE): PointAccumulator::mean() = (1./n) * acc, smmap.h:24
-        std::vector<double> inv(kInvTable);
+        // followed by 2^(j/128) for exp_neg()
+        std::vector<double> inv(kInvTable + kExpTable);
         for (int i = 0; i < kInvTable; i++) { volatile double one = 1., den = (double)i; inv[i] = one / den; }
-        CKC(dalloc(c->d_inv_n, kInvTable));
-        CKC(cudaMemcpy(c->d_inv_n, inv.data(), sizeof(double) * kInvTable, cudaMemcpyHostToDevice));
+        for (int j = 0; j < kExpTable; j++) inv[kInvTable + j] = exp2((double)j / kExpTable);
+        CKC(dalloc(c->d_inv_n, inv.size()));
+        CKC(cudaMemcpy(c->d_inv_n, inv.data(), sizeof(double) * inv.size(), cudaMemcpyHostToDevice));
     }
     launch_pool_init(c->pool, c->st);
     CKC(cudaGetLastError());
@@ -95,7 +99,7 @@ int gm_destroy(gm_ctx* c) {
     c->reg_pending = false;
     gmi_dist_destroy(c);
     if (c->st) cudaStreamSynchronize(c->st);
-    cudaFree(c->pool.cells); cudaFree(c->pool.refcnt); cudaFree(c->pool.free_list); cudaFree(c->pool.pending);
+    cudaFree(c->pool.cells); cudaFree(c->pool.occ); cudaFree(c->pool.refcnt); cudaFree(c->pool.free_list); cudaFree(c->pool.pending);
     cudaFree(c->pool.free_top); cudaFree(c->pool.pending_n); cudaFree(c->refcnt_new);
     cudaFree(c->dir); cudaFree(c->dir_alt); cudaFree(c->geom); cudaFree(c->geom_alt); cudaFree(c->geom_new); cudaFree(c->shift);
     cudaFree(c->d_ranges); cudaFree(c->d_angles); cudaFree(c->d_poses); cudaFree(c->d_score); cudaFree(c->d_s); cudaFree(c->d_l);
@@ -189,7 +193,7 @@ static int run_eval(gm_ctx* ctx, int mode, uint32_t count, const uint32_t* parti
     CK(cudaMemcpyAsync(ctx->d_qposes, poses, sizeof(double) * 3 * count, cudaMemcpyHostToDevice, ctx->st));
     ScanMatchArgs a{};
     a.P = ctx->P; a.ranges = ctx->d_ranges; a.angles = ctx->d_angles; a.poses = ctx->d_qposes;
-    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.inv_n = ctx->d_inv_n;
+    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.occ = ctx->pool.occ; a.inv_n = ctx->d_inv_n;
     a.s = ctx->d_qs; a.l = ctx->d_ql; a.c = ctx->d_qc; a.score = ctx->d_qs; a.poses_out = ctx->d_qposes_out;
     a.query = mode; a.particle_idx = ctx->d_qidx; a.zero_patch = ctx->pool.cap;
     derive_params(a.P);
@@ -230,7 +234,7 @@ int gm_scanmatch(gm_ctx* ctx, const double* ranges, double* poses_inout, double 
     ScanMatchArgs a{};
     a.query = -1;
     a.P = ctx->P; a.ranges = ctx->d_ranges; a.angles = ctx->d_angles; a.poses = ctx->d_poses;
-    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.inv_n = ctx->d_inv_n;
+    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.occ = ctx->pool.occ; a.inv_n = ctx->d_inv_n;
     a.minimum_score = minimum_score;
     a.score = ctx->d_score; a.s = ctx->d_s; a.l = ctx->d_l; a.c = ctx->d_c; a.evals = ctx->d_evals;
     a.counters = ctx->d_counters;
@@ -571,13 +575,17 @@ int gm_map_digest(gm_ctx* ctx, uint32_t first, uint32_t count, gm_digest* out) {
     if (!out || first + count > ctx->n) return fail(ctx, GM_ERR_ARG, "gm_map_digest: bad argument");
     if (!count) return GM_OK;
     DigestArgs a;
-    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.first = first; a.out = ctx->d_digest;
+    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.occ = ctx->pool.occ; a.first = first; a.out = ctx->d_digest;
     launch_digest(a, count, ctx->st);
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_digest")) return r;
     static_assert(sizeof(gm_digest) == 48, "gm_digest is six 64-bit words");
-    CK(cudaMemcpyAsync(out, ctx->d_digest, sizeof(gm_digest) * count, cudaMemcpyDeviceToHost, ctx->st));
+    std::vector<unsigned long long> words((size_t)count * 7);
+    CK(cudaMemcpyAsync(words.data(), ctx->d_digest, sizeof(unsigned long long) * words.size(), cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
+    unsigned long long bad = 0;
+    for (uint32_t i = 0; i < count; i++) { memcpy(&out[i], &words[(size_t)i * 7], sizeof(gm_digest)); bad += words[(size_t)i * 7 + 6]; }
+    if (bad) return fail(ctx, GM_ERR_INTERNAL, "gm_map_digest: %llu occupancy-bitmap rows disagree with their cells", bad);
     return GM_OK;
 }
 
@@ -610,7 +618,7 @@ int gm_clone(gm_ctx* src, gm_ctx** out) {
             (e = dalloc(dst->d_neff, 1)) != cudaSuccess || (e = dalloc(dst->d_widx, dst->weights_cap)) != cudaSuccess) return bail(e, "weight buffers");
         // the whole pool is copied (ids stay valid); the clone costs as much HBM as the original
         struct { void* d; const void* s; size_t bytes; } copies[] = {
-            {dst->pool.cells, src->pool.cells, (cap + 1) * kPatchCells * sizeof(int4)}, {dst->pool.refcnt, src->pool.refcnt, cap * sizeof(int)},
+            {dst->pool.cells, src->pool.cells, (cap + 1) * kPatchCells * sizeof(int4)}, {dst->pool.occ, src->pool.occ, (cap + 1) * kPatch * sizeof(unsigned)}, {dst->pool.refcnt, src->pool.refcnt, cap * sizeof(int)},
             {dst->pool.free_list, src->pool.free_list, cap * sizeof(int)}, {dst->pool.free_top, src->pool.free_top, sizeof(int)},
             {dst->dir, src->dir, dn * sizeof(int)}, {dst->geom, src->geom, sizeof(Geom) * src->max_particles}};
         for (auto& c : copies)

@@ -7,6 +7,9 @@
 //   dir    : int[N * dir_cap]        particle i, patch (px,py) at dir[i*dir_cap + px*npy + py], -1 = unallocated
 //   geom   : Geom[N]                 per-particle m_sizeX2/m_sizeY2 + directory dims (diverge after Map::resize)
 //   refcnt : int[pool_cap]           number of directory entries that reference a patch (autoptr::shares)
+//   occ    : unsigned[pool_cap * 32] occupancy bitmap: bit ly of word p*32 + lx == (10 * n > visits) of that cell, i.e. the cell
+//            is occupied at the default fullnessThreshold 0.1 (smmap.h:25).  Derived data, kept in step by every writer of
+//            `pool`; the scan matcher reads a 3x3 window's occupancy from three words instead of nine cells
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -18,6 +21,7 @@ constexpr int kPatch = 32;
 constexpr int kPatchCells = 1024;
 constexpr int kLineCap = 20000;  // scanmatcher.cpp:55
 constexpr int kInvTable = 4096;  // exactly rounded 1./n for n < kInvTable (PointAccumulator::mean, smmap.h:24)
+constexpr int kExpTable = 128;   // 2^(j/128), stored behind the reciprocals (exp_neg in gm_kernels.cu)
 
 struct Geom { int sx2, sy2, npx, npy; };
 
@@ -55,7 +59,8 @@ struct Counters {  // zeroed per stage, read back by the host
 };
 
 struct Pool {
-    int4* cells;       // [cap*1024]
+    int4* cells;       // [(cap+1)*1024], patch `cap` is all zero
+    unsigned* occ;     // [(cap+1)*32] occupancy bitmap (see the layout note above)
     int* refcnt;       // [cap]
     int* free_list;    // [cap] stack of free patch ids, top at *free_top
     int* free_top;     // number of ids on the stack
@@ -100,6 +105,9 @@ __device__ __forceinline__ bool occ_lt(int n, int v, const DevParams& P) {
     if (!v) return -1.0 < P.fullness_threshold;
     return P.thr_is_tenth ? (10ll * n < (long long)v) : (occ_ratio(n, v) < P.fullness_threshold);
 }
+
+// the occupancy-bitmap predicate: n / visits > 0.1 decided in integers (implies visits > 0 as n >= 0)
+__device__ __forceinline__ bool occ_default(int n, int v) { return 10ll * n > (long long)v; }
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
     x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;

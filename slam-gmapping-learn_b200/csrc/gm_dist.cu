@@ -136,7 +136,11 @@ __global__ void __launch_bounds__(512) k_dist_install(int first_slot, Geom* __re
     const int4* cells = reinterpret_cast<const int4*>(base + kHeaderBytes + (((unsigned long long)count * 4 + 15) & ~15ull));
     for (long long i = threadIdx.x; i < (long long)count * kPatchCells; i += blockDim.x) {
         const int id = s_ids[i >> 10];
-        if (id >= 0) pool.cells[(size_t)id * kPatchCells + (i & 1023)] = cells[i];
+        const int4 c = cells[i];
+        if (id >= 0) pool.cells[(size_t)id * kPatchCells + (i & 1023)] = c;
+        // 512 threads, count * 1024 cells: every warp covers one whole patch row per trip
+        const unsigned bits = __ballot_sync(0xffffffffu, occ_default(c.z, c.w));
+        if (id >= 0 && (i & 31) == 0) pool.occ[(size_t)id * kPatch + ((i & 1023) >> kPatchMag)] = bits;
     }
 }
 

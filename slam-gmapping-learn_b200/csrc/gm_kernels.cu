@@ -33,11 +33,10 @@ namespace gm {
 //   * world2map's division by delta is a multiply by 1/delta with an exactness guard: whenever the product is
 //     within 1e-6 of a rounding boundary the reference's division + round() is evaluated (out of line), so the
 //     integer cell index is always the reference's;
-//   * the (2k+1)^2 window: when no lane of the warp straddles a patch edge, one directory lookup and nine
-//     independent 8-byte loads of (n, visits) issued together; cells with n == 0 (free or unknown) drop out
-//     with one compare; only occupied cells load acc and look at the free cell.  The free-cell window is
-//     resolved once per beam: the reference's world2map-of-a-difference quirk puts it half a map away, where
-//     it is almost always wholly unknown;
+//   * the 3x3 window: its occupancy (n / visits > 0.1) is read from the pool's occupancy bitmap -- three words, one per
+//     window row, kept in step by every kernel that writes cells -- so free and unknown cells are never loaded; only
+//     occupied cells load {acc, n} and look at the free cell.  The free-cell window is resolved once per beam: the
+//     reference's world2map-of-a-difference quirk puts it half a map away, where it is almost always wholly unknown;
 //   * mean() = acc * (1./n): 1./n comes from a table of exactly rounded reciprocals (n < 4096).
 // Generic code paths (negative fullnessThreshold, any kernelSize, windows across patch edges) remain.
 
@@ -48,6 +47,29 @@ __device__ __noinline__ int cell_index_slow(double d, double delta) {
     return fabs(q) < 2147483648.0 ? (int)q : (int)0x80000000;
 }
 __device__ __noinline__ double recip_slow(int n) { return 1. / n; }
+__device__ __noinline__ double exp_cold(double x) { return exp(x); }
+
+// exp(x) for the x <= 0 of the score sums (scanmatcher.h:257,368): 2^(k/128) from a table of rounded powers times a
+// degree-5 polynomial on |r| <= ln2/256, < 1 ulp like the library function it replaces (checked against expl() on the
+// host over [-700, 0]), about half its instructions and a third of its dependent chain.  Arguments below -700 (results
+// near the subnormal range), positive ones and NaN take the library call.
+__device__ __forceinline__ double exp_neg(double x, const double* __restrict__ pow2) {
+    if (!(x > -700.0 && x <= 0.0)) return exp_cold(x);
+    const double shift = 6755399441055744.0;  // 1.5 * 2^52: the sum's low word is rint(x * 128/ln2)
+    const double t = __fma_rn(x, 0x1.71547652b82fep+7, shift);
+    const int ki = __double2loint(t);
+    const double kd = t - shift;
+    double r = __fma_rn(kd, -0x1.62e42fefa0000p-8, x);  // ln2/128 in two pieces
+    r = __fma_rn(kd, -0x1.cf79abc9e3b3ap-47, r);
+    const double r2 = r * r;
+    const double p1 = __fma_rn(r, 0x1.5555555555555p-3, 0.5);
+    const double p2 = __fma_rn(r, 0x1.1111111111111p-7, 0x1.5555555555555p-5);
+    double tail = __fma_rn(r2, p1, r);
+    tail = __fma_rn(r2 * r2, p2, tail);
+    const double m = __ldg(pow2 + (ki & (kExpTable - 1)));
+    const double scale = __hiloint2double(__double2hiint(m) + ((ki >> 7) << 20), __double2loint(m));
+    return __fma_rn(scale, tail, scale);
+}
 
 // reference-exact (int)round(d / delta), d = world coordinate minus map centre (map.h:283-287): multiply by
 // 1/delta, and fall back to the division whenever the product is within 1e-6 of a rounding boundary (this
@@ -65,6 +87,7 @@ constexpr int kSmGroups = kSmThreads / 6;  // 48 beam groups x 6 candidate poses
 struct MatchCtx {
     const int* __restrict__ dirp;
     const int4* __restrict__ pool;
+    const unsigned* __restrict__ occ;
     const double* __restrict__ inv_n;
     Geom g;
     int zero_patch;  // id of an all-zero patch: stands in for unallocated / outside patches (const Map::cell, map.h:347-354)
@@ -88,7 +111,7 @@ template <bool DEF> __device__ __forceinline__ bool is_free(int n, int v, const 
 template <bool K1>
 // (fqx, fqy): the beam-independent free-cell index offset when it exists (see derive_params), else fqx == INT_MIN
 __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M, double lpx, double lpy, double r, double c, double s,
-                                           double free_off, int fqx, int fqy, unsigned* ci_smem, double& bmx, double& bmy) {
+                                           double free_off, int fqx, int fqy, double& bmx, double& bmy) {
     const Geom& g = M.g;
     const double phx = lpx + r * c, phy = lpy + r * s;
     const int ihx = cell_index(phx - P.cx, P.delta, P.inv_delta) + g.sx2;
@@ -99,43 +122,37 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
     double bx = 0., by = 0., bn = 0.;
 
     if (K1) {
-        // ---- 3x3 window.  Cell indexes (patch * 1024 + cell) of the nine cells: when no lane of the warp has a
-        // window that straddles a patch edge, one directory entry and constant offsets; otherwise the window spans
-        // at most 2x2 patches: four entries, unknown ones mapped to the all-zero patch.
-        unsigned ci[9];
-        const bool single = x0 >= 0 && y0 >= 0 && (x0 >> kPatchMag) == (x1 >> kPatchMag) && (y0 >> kPatchMag) == (y1 >> kPatchMag);
-        if (__all_sync(__activemask(), single)) {
-            const int id = dir_at(M, x0 >> kPatchMag, y0 >> kPatchMag);
-            if (id < 0) return false;
-            const unsigned base = ((unsigned)id << 10) + ((unsigned)(x0 & 31) << kPatchMag) + (unsigned)(y0 & 31);
-#pragma unroll
-            for (int i = 0; i < 9; i++) ci[i] = base + (unsigned)(((i / 3) << kPatchMag) + (i % 3));
-        } else {
-            const int pxa = x0 >> kPatchMag, pya = y0 >> kPatchMag, pxb = x1 >> kPatchMag, pyb = y1 >> kPatchMag;
-            const int ida = dir_at(M, pxa, pya);
-            const int idb = pyb != pya ? dir_at(M, pxa, pyb) : ida;
-            const int idc = pxb != pxa ? dir_at(M, pxb, pya) : ida;
-            const int idd = pxb != pxa ? (pyb != pya ? dir_at(M, pxb, pyb) : idc) : idb;
-            if ((ida & idb & idc & idd) < 0) return false;  // every patch unknown: nothing can match
-            const unsigned ea = (unsigned)(ida < 0 ? M.zero_patch : ida) << 10, eb = (unsigned)(idb < 0 ? M.zero_patch : idb) << 10;
-            const unsigned ec = (unsigned)(idc < 0 ? M.zero_patch : idc) << 10, ed = (unsigned)(idd < 0 ? M.zero_patch : idd) << 10;
-            const int nxa = ((pxa + 1) << kPatchMag) - x0, nya = ((pya + 1) << kPatchMag) - y0;  // rows / columns inside patch a
-#pragma unroll
-            for (int xx = 0; xx < 3; xx++) {
-                const unsigned rowoff = (unsigned)((x0 + xx) & 31) << kPatchMag;
-                const unsigned ra = (xx < nxa ? ea : ec) + rowoff, rb = (xx < nxa ? eb : ed) + rowoff;
-#pragma unroll
-                for (int yy = 0; yy < 3; yy++) ci[3 * xx + yy] = (yy < nya ? ra : rb) + (unsigned)((y0 + yy) & 31);
-            }
-        }
-        // nine independent 8-byte loads of (n, visits), issued together; occupancy decided in exact integers
-        int2 nv[9];
-#pragma unroll
-        for (int i = 0; i < 9; i++) nv[i] = __ldg(reinterpret_cast<const int2*>(M.pool + ci[i]) + 1);
+        // ---- 3x3 window.  It spans at most 2x2 patches (a: low x / low y, b: high y, c: high x, d: both).  Its occupancy
+        // comes from the pool's bitmap: one word per window row (two when the row crosses a patch edge in y), funnel-
+        // shifted to the window's first column; no cell is read unless it is occupied.
+        const int pxa = x0 >> kPatchMag, pya = y0 >> kPatchMag, pxb = x1 >> kPatchMag, pyb = y1 >> kPatchMag;
+        const bool twoy = pyb != pya;
+        const int ida = dir_at(M, pxa, pya);
+        const int idb = twoy ? dir_at(M, pxa, pyb) : ida;
+        const int idc = pxb != pxa ? dir_at(M, pxb, pya) : ida;
+        const int idd = pxb != pxa ? (twoy ? dir_at(M, pxb, pyb) : idc) : idb;
+        if ((ida & idb & idc & idd) < 0) return false;  // every patch unknown: nothing can match
+        // unknown patches read the all-zero patch
+        const unsigned zp = (unsigned)M.zero_patch;  // = pool capacity > every patch id; -1 as unsigned is larger still
+        const unsigned ea = min((unsigned)ida, zp), eb = min((unsigned)idb, zp), ec = min((unsigned)idc, zp), ed = min((unsigned)idd, zp);
+        const int nxa = ((pxa + 1) << kPatchMag) - x0;  // window rows inside patches a / b
+        const unsigned ysh = (unsigned)(y0 & 31);
         unsigned mask = 0;
 #pragma unroll
-        for (int i = 0; i < 9; i++) mask |= (10ll * nv[i].x > (long long)nv[i].y) ? 1u << i : 0u;  // n/visits > 0.1 (implies visits > 0)
+        for (int xx = 0; xx < 3; xx++) {
+            const unsigned row = (unsigned)((x0 + xx) & 31);
+            const unsigned lo = __ldg(M.occ + (((xx < nxa ? ea : ec) << kPatchMag) + row));
+            const unsigned hi = twoy ? __ldg(M.occ + (((xx < nxa ? eb : ed) << kPatchMag) + row)) : 0u;
+            mask |= (__funnelshift_r(lo, hi, ysh) & 7u) << (8 * xx);  // bit 8 * xx + yy: ascending bits == scan order
+        }
         if (!mask) return false;
+        // cell index (patch * 1024 + cell) of the window cell at mask bit i = 8 * xx + yy
+        const int nya = ((pya + 1) << kPatchMag) - y0;
+        auto cell_of = [&](int i) -> unsigned {
+            const int xx = i >> 3, yy = i & 7;
+            const unsigned e = xx < nxa ? (yy < nya ? ea : eb) : (yy < nya ? ec : ed);
+            return (e << 10) + ((unsigned)((x0 + xx) & 31) << kPatchMag) + (unsigned)((y0 + yy) & 31);
+        };
         // free window (the reference's `ipfree` quirk: world2map applied to the difference pfree - phit).  |pfree - phit|
         // <= free_off, so for score() the index is the same for every beam and comes precomputed in (fqx, fqy)
         int ifx, ify;
@@ -150,10 +167,7 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
         if (fx1 < 0 || fy1 < 0 || (fx0 >> kPatchMag) >= g.npx || (fy0 >> kPatchMag) >= g.npy) fcheck = false;
         else if (fx0 >= 0 && fy0 >= 0 && (fx0 >> kPatchMag) == (fx1 >> kPatchMag) && (fy0 >> kPatchMag) == (fy1 >> kPatchMag) &&
                  dir_at(M, fx0 >> kPatchMag, fy0 >> kPatchMag) < 0) fcheck = false;
-        // occupied cells in ascending bit order == the reference's xx-outer / yy-inner scan order; the nine cell
-        // indexes wait in shared memory (one column per thread) so that the loop can pick them by a run-time index
-#pragma unroll
-        for (int i = 0; i < 9; i++) ci_smem[i * kSmThreads] = ci[i];
+        // occupied cells in ascending bit order == the reference's xx-outer / yy-inner scan order
         if (!fcheck) {
             // two cells per trip: their load -> reciprocal -> distance chains are independent and overlap; the comparisons
             // still run in scan order (i before j), so ties resolve as in the reference
@@ -163,8 +177,8 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
                 const bool two = mask != 0;
                 const int j = two ? __ffs(mask) - 1 : i;
                 mask &= mask - 1;  // no-op when mask is already 0
-                const int4 ca = __ldg(M.pool + ci_smem[i * kSmThreads]);
-                const int4 cb = __ldg(M.pool + ci_smem[j * kSmThreads]);
+                const int4 ca = __ldg(M.pool + cell_of(i));
+                const int4 cb = __ldg(M.pool + cell_of(j));
                 const double ia = ca.z < kInvTable ? __ldg(M.inv_n + ca.z) : recip_slow(ca.z);  // mean() = (1./n) * acc, smmap.h:24
                 const double ib = cb.z < kInvTable ? __ldg(M.inv_n + cb.z) : recip_slow(cb.z);
                 const double ax = phx - (double)__int_as_float(ca.x) * ia, ay = phy - (double)__int_as_float(ca.y) * ia;
@@ -177,11 +191,11 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
             while (mask) {
                 const int i = __ffs(mask) - 1;
                 mask &= mask - 1;
-                const int xx = (i * 11) >> 5, yy = i - 3 * xx;  // i / 3, i % 3 for i < 9
+                const int xx = i >> 3, yy = i & 7;
                 long long fi; int fn = 0, fv = 0;
                 if (cell_addr(g, M.dirp, x0 + xx + ifx, y0 + yy + ify, fi)) { const int4 f = __ldg(M.pool + fi); fn = f.z; fv = f.w; }
                 if (!is_free<true>(fn, fv, P)) continue;
-                const int4 cell = __ldg(M.pool + ci_smem[i * kSmThreads]);
+                const int4 cell = __ldg(M.pool + cell_of(i));
                 const double inv = cell.z < kInvTable ? __ldg(M.inv_n + cell.z) : recip_slow(cell.z);
                 const double mx = phx - (double)__int_as_float(cell.x) * inv, my = phy - (double)__int_as_float(cell.y) * inv;
                 const double nn = mx * mx + my * my;
@@ -322,13 +336,12 @@ template <bool K1>
 __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SmShared S;
-    __shared__ unsigned S_ci[9 * kSmThreads];  // window cell indexes, column t belongs to thread t
     const DevParams& P = A.P;
     double2* const tabs = reinterpret_cast<double2*>(smem_raw);
     const unsigned q = blockIdx.x, p = A.query >= 0 ? A.particle_idx[q] : q;
     const int t = threadIdx.x;
     MatchCtx M;
-    M.dirp = A.dir + (size_t)p * A.dir_cap; M.pool = A.pool; M.inv_n = A.inv_n; M.g = A.geom[p];
+    M.dirp = A.dir + (size_t)p * A.dir_cap; M.pool = A.pool; M.occ = A.occ; M.inv_n = A.inv_n; M.g = A.geom[p];
     M.zero_patch = A.zero_patch;
 
     if (t == 0) {
@@ -383,8 +396,8 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
                 const double2 cs = tab[b];
                 double mx, my;
                 valid++;
-                const bool found = beam_match<K1>(P, M, mlx, mly, r, cs.x, cs.y, free_off, fqx, fqy, S_ci + t, mx, my);
-                if (found) { acc_s += exp((mx * cexp) * mx + (my * cexp) * my); cnt++; }  // ((-1/sigma)*mu)*mu, point.h:34-49
+                const bool found = beam_match<K1>(P, M, mlx, mly, r, cs.x, cs.y, free_off, fqx, fqy, mx, my);
+                if (found) { acc_s += exp_neg((mx * cexp) * mx + (my * cexp) * my, A.inv_n + kInvTable); cnt++; }  // ((-1/sigma)*mu)*mu, point.h:34-49
                 if (mode) { const double f = clik * (mx * mx + my * my); acc_l += found ? f : noHit; }
             }
         }
@@ -807,9 +820,11 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
             int4* dst = A.pool.cells + (size_t)nid * kPatchCells;
             if (mode == 1) {
                 for (int i = lane; i < kPatchCells; i += 32) dst[i] = make_int4(0, 0, 0, 0);
+                A.pool.occ[(size_t)nid * kPatch + lane] = 0u;
             } else {
                 const int4* src = A.pool.cells + (size_t)id * kPatchCells;
                 for (int i = lane; i < kPatchCells; i += 32) dst[i] = __ldcg(src + i);
+                A.pool.occ[(size_t)nid * kPatch + lane] = __ldcg(A.pool.occ + (size_t)id * kPatch + lane);
             }
             __syncwarp();
             if (lane == 0) {
@@ -881,21 +896,32 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
             const int id = dirp[e];
             if (id < 0) continue;
             int* cells = reinterpret_cast<int*>(A.pool.cells + (size_t)id * kPatchCells);
+            unsigned* occ = A.pool.occ + (size_t)id * kPatch;
             const unsigned* tile = M.tiles + t * kTileWords;
-            // eight independent loads in flight per lane: the patch is private, plain read-modify-write
+            // eight independent loads in flight per lane: the patch is private, plain read-modify-write.  A warp covers one
+            // row of the patch per k, so two ballots give the row's touched cells and their new occupancy bits; lane r
+            // keeps bitmap word r in a register and writes it back if it changed
+            const unsigned occ_old = __ldcg(occ + lane);
+            unsigned occ_new = occ_old;
 #pragma unroll 1
             for (int g8 = 0; g8 < kPatchCells; g8 += 256) {
-                int v[8]; unsigned c[8];
+                int2 nv[8]; unsigned c[8];
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     const int ci = g8 + 32 * k + lane;
                     c[k] = (tile[ci >> 1] >> ((ci & 1) << 4)) & 0xffffu;
-                    v[k] = c[k] ? __ldcg(cells + (ci << 2) + 3) : 0;  // untouched cells cost no traffic
+                    nv[k] = c[k] ? __ldcg(reinterpret_cast<const int2*>(cells + (ci << 2) + 2)) : make_int2(0, 0);  // untouched cells cost no traffic
                 }
 #pragma unroll
-                for (int k = 0; k < 8; k++)
-                    if (c[k]) { cells[((g8 + 32 * k + lane) << 2) + 3] = v[k] + (int)c[k]; nfree += c[k]; }  // update(false) c times
+                for (int k = 0; k < 8; k++) {
+                    const int nvis = nv[k].y + (int)c[k];
+                    if (c[k]) { cells[((g8 + 32 * k + lane) << 2) + 3] = nvis; nfree += c[k]; }  // update(false) c times
+                    const unsigned touched = __ballot_sync(0xffffffffu, c[k] != 0);
+                    const unsigned bits = __ballot_sync(0xffffffffu, c[k] != 0 && occ_default(nv[k].x, nvis));
+                    if (lane == (g8 >> kPatchMag) + k) occ_new = (occ_new & ~touched) | bits;
+                }
             }
+            if (occ_new != occ_old) occ[lane] = occ_new;
         }
         __syncthreads();
         PHASE(5);
@@ -940,7 +966,13 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
             ax += rec[b].hx; ay += rec[b].hy; cnt++;  // acc += (float)phit, smmap.h:51-52
         }
         cell[0] = __float_as_int(ax); cell[1] = __float_as_int(ay);
-        cell[2] += cnt; cell[3] += cnt;  // the cell belongs to this thread alone now
+        const int n0 = __ldcg(cell + 2), v0 = __ldcg(cell + 3);  // the cell belongs to this thread alone now
+        cell[2] = n0 + cnt; cell[3] = v0 + cnt;
+        const bool was = occ_default(n0, v0), is = occ_default(n0 + cnt, v0 + cnt);
+        if (was != is) {  // other cells of the row may flip at the same time: atomics on the bitmap word
+            unsigned* w = A.pool.occ + (size_t)id * kPatch + (x & 31);
+            if (is) atomicOr(w, 1u << (y & 31)); else atomicAnd(w, ~(1u << (y & 31)));
+        }
         nhit += cnt;
     }
     // statistics: one shared atomic per warp (64-bit shared atomics are CAS loops; a thousand on one address crawl)
@@ -1062,13 +1094,13 @@ __global__ void __launch_bounds__(1024) k_resample(const double* __restrict__ w,
 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_digest(DigestArgs A) {
-    __shared__ unsigned long long acc[6];
+    __shared__ unsigned long long acc[7];
     const unsigned p = A.first + blockIdx.x;
     const Geom g = A.geom[p];
     const int* dirp = A.dir + (size_t)p * A.dir_cap;
-    if (threadIdx.x < 6) acc[threadIdx.x] = 0;
+    if (threadIdx.x < 7) acc[threadIdx.x] = 0;
     __syncthreads();
-    unsigned long long patches = 0, cells = 0, sn = 0, sv = 0, hc = 0, ha = 0;
+    unsigned long long patches = 0, cells = 0, sn = 0, sv = 0, hc = 0, ha = 0, bad = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int e = warp; e < g.npx * g.npy; e += nw) {
         int id = dirp[e];
@@ -1078,6 +1110,9 @@ __global__ void __launch_bounds__(256) k_digest(DigestArgs A) {
         const int4* pc = A.pool + (size_t)id * kPatchCells;
         for (int i = lane; i < kPatchCells; i += 32) {
             int4 c = pc[i];
+            // the warp holds row i >> 5 of the patch: its occupancy bits must equal the bitmap word
+            const unsigned bits = __ballot_sync(0xffffffffu, occ_default(c.z, c.w));
+            if (lane == 0 && bits != A.occ[(size_t)id * kPatch + (i >> kPatchMag)]) bad++;
             if (!c.w && !c.z) continue;
             int wx = px * kPatch + (i >> 5) - g.sx2, wy = py * kPatch + (i & 31) - g.sy2;
             cells++; sn += (unsigned)c.z; sv += (unsigned)c.w;
@@ -1088,8 +1123,9 @@ __global__ void __launch_bounds__(256) k_digest(DigestArgs A) {
     }
     atomicAdd(&acc[0], patches); atomicAdd(&acc[1], cells); atomicAdd(&acc[2], sn);
     atomicAdd(&acc[3], sv); atomicAdd(&acc[4], hc); atomicAdd(&acc[5], ha);
+    if (bad) atomicAdd(&acc[6], bad);
     __syncthreads();
-    if (threadIdx.x < 6) A.out[(size_t)blockIdx.x * 6 + threadIdx.x] = acc[threadIdx.x];
+    if (threadIdx.x < 7) A.out[(size_t)blockIdx.x * 7 + threadIdx.x] = acc[threadIdx.x];
 }
 
 __global__ void k_export_list(const int* __restrict__ dirp, Geom g, int* __restrict__ list, int* __restrict__ count) {
@@ -1134,7 +1170,12 @@ __global__ void k_install_patches(int* dirp, Geom g, const int* __restrict__ coo
     __syncthreads();
     const int id = s_id;
     if (id < 0) return;
-    for (int i = threadIdx.x; i < kPatchCells; i += blockDim.x) pool.cells[(size_t)id * kPatchCells + i] = staged[(size_t)k * kPatchCells + i];
+    for (int i = threadIdx.x; i < kPatchCells; i += blockDim.x) {  // blockDim is a multiple of 32: a warp covers one row per trip
+        const int4 c = staged[(size_t)k * kPatchCells + i];
+        pool.cells[(size_t)id * kPatchCells + i] = c;
+        const unsigned bits = __ballot_sync(0xffffffffu, occ_default(c.z, c.w));
+        if ((i & 31) == 0) pool.occ[(size_t)id * kPatch + (i >> kPatchMag)] = bits;
+    }
     if (threadIdx.x == 0) { pool.refcnt[id] = 1; dirp[coords[2 * k] * g.npy + coords[2 * k + 1]] = id; }
 }
 

@@ -10,6 +10,7 @@ struct ScanMatchArgs {
     double* poses;
     const Geom* geom; const int* dir; int dir_cap;
     const int4* pool;
+    const unsigned* occ;  // occupancy bitmap of the pool (gm_device.cuh)
     const double* inv_n;
     double minimum_score;
     double *score, *s, *l; unsigned *c, *evals;
@@ -50,8 +51,8 @@ struct RemapArgs {
 };
 struct SweepArgs { Pool pool; int* refcnt_new; };
 struct DigestArgs {
-    const Geom* geom; const int* dir; int dir_cap; const int4* pool;
-    unsigned first; unsigned long long* out;
+    const Geom* geom; const int* dir; int dir_cap; const int4* pool; const unsigned* occ;
+    unsigned first; unsigned long long* out;  // 7 words per particle: the six of gm_digest + mismatching occupancy-bitmap rows
 };
 
 size_t scanmatch_smem_bytes(unsigned nbeams);
