@@ -385,7 +385,7 @@ int gmi_register_update(gm_ctx* ctx) {
     a.P = ctx->P; a.ranges = ctx->d_ranges; a.angles = ctx->d_angles; a.poses = ctx->d_poses;
     a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool; a.counters = ctx->d_counters;
     a.bitmap_words = (ctx->dir_cap + 31) / 32;
-    int sort_n = 32;
+    int sort_n = 64;  // power of two >= nbeams: sizes the hit table of k_register
     while (sort_n < (int)ctx->P.nbeams) sort_n <<= 1;
     a.sort_n = sort_n;
     // visit-count tiles: as many as fit (one pass over the rays when the active area has at most that many patches);
@@ -393,7 +393,7 @@ int gmi_register_update(gm_ctx* ctx) {
     const size_t fixed = register_smem_bytes(a.bitmap_words, 0, (int)ctx->P.nbeams, 0);
     size_t budget = 220 * 1024;  // of the 227 KB a CTA may use
     if (const char* e = getenv("GM_B200_REGISTER_SMEM_KB")) budget = (size_t)atoi(e) * 1024;  // experiments: e.g. 110 = two CTAs per SM
-    if (fixed + (size_t)a.sort_n * 8 > budget) return fail(ctx, GM_ERR_ARG, "gm_register: patch directory of %d entries needs %zu B of shared memory", ctx->dir_cap, fixed);
+    if (fixed + (size_t)a.sort_n * 36 > budget) return fail(ctx, GM_ERR_ARG, "gm_register: patch directory of %d entries needs %zu B of shared memory", ctx->dir_cap, fixed);
     const int tile_cap = (int)((budget - fixed) / 2048);
     a.tile_cap = tile_cap;
     const size_t smem = register_smem_bytes(a.bitmap_words, a.sort_n, (int)ctx->P.nbeams, tile_cap);

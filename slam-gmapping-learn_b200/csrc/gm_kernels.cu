@@ -677,9 +677,11 @@ __device__ __forceinline__ int item_patches(int p0x, int p0y, int p1x, int p1y, 
 
 constexpr int kRegThreads = 1024;
 constexpr int kTileWords = kPatchCells / 2;  // a tile counts visits of one patch: 1024 cells x 16 bit, two per word
+// hit grouping (k_register phase 4), per unit of sort_n: 2 table keys (8 B) + 2 first + 2 last (4 B each) + 1 slot (4 B)
+constexpr int kHitBytes = 36;
 
 // dynamic shared memory of k_register (see register_smem_bytes): active-patch bitmap over the directory, its
-// running popcount per word, sort keys of the hits, per-beam records, visit-count tiles
+// running popcount per word, per-beam records, visit-count tiles (reused by the hit table afterwards)
 struct RegSmem {
     unsigned* active; unsigned short* prefix; BeamRec* rec; int* items; unsigned* tiles; unsigned long long* keys;  // keys alias tiles
 };
@@ -692,7 +694,7 @@ __device__ __forceinline__ RegSmem carve(unsigned char* raw, int bitmap_words, i
     m.rec = reinterpret_cast<BeamRec*>(raw + o); o += align16((size_t)nbeams * sizeof(BeamRec));
     m.items = reinterpret_cast<int*>(raw + o); o += align16((size_t)(nbeams + 1) * 4);
     m.tiles = reinterpret_cast<unsigned*>(raw + o);
-    m.keys = reinterpret_cast<unsigned long long*>(raw + o);  // the hit sort runs after the last tile flush
+    m.keys = reinterpret_cast<unsigned long long*>(raw + o);  // the hit table is built after the last tile flush
     return m;
 }
 
@@ -705,7 +707,6 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
     const int nent = g.npx * g.npy, nwords = (nent + 31) >> 5;
     const RegSmem M = carve(smem_raw, A.bitmap_words, A.sort_n, (int)P.nbeams);
     unsigned* active = M.active;
-    unsigned long long* keys = M.keys;
     BeamRec* rec = M.rec;
     __shared__ unsigned long long s_free, s_hit, s_cow, s_alloc;
     __shared__ int s_part[kRegThreads / 32];
@@ -929,44 +930,49 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
     __threadfence();
     __syncthreads();
 
-    // ---- 4. endpoint hits in beam order per cell: bitonic sort of (cell, beam) keys (built now: they reuse the tile area)
-    for (int i = threadIdx.x; i < A.sort_n; i += blockDim.x) {
-        unsigned long long key = ~0ull;
-        if (i < (int)P.nbeams && (rec[i].flags & 4)) key = ((unsigned long long)(unsigned)rec[i].p1x << 36) | ((unsigned long long)(unsigned)rec[i].p1y << 12) | (unsigned)i;
-        keys[i] = key;
-    }
-    for (int k = 2; k <= A.sort_n; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            __syncthreads();
-            for (int i = threadIdx.x; i < A.sort_n; i += blockDim.x) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    unsigned long long a = keys[i], bb = keys[ixj];
-                    bool up = (i & k) == 0;
-                    if ((a > bb) == up) { keys[i] = bb; keys[ixj] = a; }
-                }
+    // ---- 4. endpoint hits, per cell in beam order (acc is a float sum: the order is part of the result).  The beams
+    // are grouped by cell in a shared-memory hash table (it reuses the tile area): slot = the cell's table entry, and per
+    // slot the first and last beam that hit it.  The first beam of a cell then adds up the cell's beams in ascending
+    // order by scanning slot_of[] from itself to the last one -- a handful of neighbouring beams in practice.
+    const int hs = A.sort_n << 1;  // table entries: a power of two >= 2 * nbeams
+    unsigned long long* hkey = M.keys;
+    int* hfirst = reinterpret_cast<int*>(hkey + hs);
+    int* hlast = hfirst + hs;
+    int* slot_of = hlast + hs;
+    for (int i = threadIdx.x; i < hs; i += blockDim.x) { hkey[i] = ~0ull; hfirst[i] = INT_MAX; hlast[i] = -1; }
+    __syncthreads();
+    for (int b = threadIdx.x; b < (int)P.nbeams; b += blockDim.x) {
+        int slot = -1;
+        if (rec[b].flags & 4) {
+            const unsigned long long key = ((unsigned long long)(unsigned)rec[b].p1x << 32) | (unsigned)rec[b].p1y;
+            slot = (int)(mix64(key) & (unsigned long long)(hs - 1));
+            for (;;) {
+                const unsigned long long prev = atomicCAS(hkey + slot, ~0ull, key);
+                if (prev == ~0ull || prev == key) break;
+                slot = (slot + 1) & (hs - 1);
             }
+            atomicMin(hfirst + slot, b);
+            atomicMax(hlast + slot, b);
         }
+        slot_of[b] = slot;
+    }
     __syncthreads();
     PHASE(6);
     unsigned long long nhit = 0;
-    for (int i = threadIdx.x; i < A.sort_n; i += blockDim.x) {
-        unsigned long long key = keys[i];
-        if (key == ~0ull) continue;
-        unsigned long long ck = key >> 12;
-        if (i > 0 && (keys[i - 1] >> 12) == ck) continue;  // not the head of this cell's run
-        int x = (int)(ck >> 24), y = (int)(ck & 0xffffffu);
+    for (int b = threadIdx.x; b < (int)P.nbeams; b += blockDim.x) {
+        const int slot = slot_of[b];
+        if (slot < 0 || hfirst[slot] != b) continue;  // not the first beam of its cell
+        const int x = rec[b].p1x, y = rec[b].p1y;
         int id = dirp[(x >> kPatchMag) * g.npy + (y >> kPatchMag)];
         if (id < 0) continue;
         int* cell = reinterpret_cast<int*>(A.pool.cells + (size_t)id * kPatchCells + ((x & 31) << kPatchMag) + (y & 31));
         float ax = __int_as_float(__ldcg(cell)), ay = __int_as_float(__ldcg(cell + 1));
-        int cnt = 0;
-        for (int q = i; q < A.sort_n && (keys[q] >> 12) == ck; q++) {
-            unsigned b = (unsigned)(keys[q] & 0xfffu);
-            ax += rec[b].hx; ay += rec[b].hy; cnt++;  // acc += (float)phit, smmap.h:51-52
-        }
-        cell[0] = __float_as_int(ax); cell[1] = __float_as_int(ay);
         const int n0 = __ldcg(cell + 2), v0 = __ldcg(cell + 3);  // the cell belongs to this thread alone now
+        int cnt = 0;
+        const int last = hlast[slot];
+        for (int q = b; q <= last; q++)
+            if (slot_of[q] == slot) { ax += rec[q].hx; ay += rec[q].hy; cnt++; }  // acc += (float)phit, smmap.h:51-52
+        cell[0] = __float_as_int(ax); cell[1] = __float_as_int(ay);
         cell[2] = n0 + cnt; cell[3] = v0 + cnt;
         const bool was = occ_default(n0, v0), is = occ_default(n0 + cnt, v0 + cnt);
         if (was != is) {  // other cells of the row may flip at the same time: atomics on the bitmap word
@@ -1204,7 +1210,7 @@ void launch_bounds(const BoundsArgs& a, unsigned n, unsigned threads, cudaStream
 void launch_relayout(const RelayoutArgs& a, unsigned n, cudaStream_t st) { k_relayout<<<n, 256, 0, st>>>(a); }
 void launch_relayout_commit(const RelayoutArgs& a, unsigned n, cudaStream_t st) { k_relayout_commit<<<n, 256, 0, st>>>(a); }
 size_t register_smem_bytes(int bitmap_words, int sort_n, int nbeams, int tile_cap) {
-    const size_t tiles = std::max((size_t)tile_cap * kTileWords * 4, (size_t)sort_n * 8);  // the sort keys reuse the tile area
+    const size_t tiles = std::max((size_t)tile_cap * kTileWords * 4, (size_t)sort_n * kHitBytes);  // the hit table reuses the tile area
     return align16((size_t)bitmap_words * 4) + align16((size_t)bitmap_words * 2) + align16((size_t)nbeams * sizeof(BeamRec)) +
            align16((size_t)(nbeams + 1) * 4) + tiles;
 }
