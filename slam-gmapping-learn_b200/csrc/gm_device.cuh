@@ -1,9 +1,12 @@
 // gm_device.cuh -- device-side data layout and helpers shared by the kernels (sm_100a).
 //
 // HBM layout:
-//   pool   : int4[pool_cap * 1024]   patch p, cell (lx,ly) at pool[p*1024 + lx*32 + ly] = {acc.x, acc.y, n, visits}
-//            (bit layout of the reference's 16-byte PointAccumulator, smmap.h:35-36; x-major like
+//   pool   : int4[pool_cap * 1024]   patch p, cell (lx,ly) at pool[p*1024 + lx*32 + ly] = {acc.x, acc.y, n, unused (0)}
+//            (the reference's PointAccumulator, smmap.h:35-36, without its visit counter; x-major like
 //            Array2D::m_cells[x][y], array2d.h:39, so a window's yy-inner cells are contiguous)
+//   visits : int[pool_cap * 1024]    PointAccumulator::visits of the same cells, in a plane of its own: the free-space
+//            update of a scan touches ~40 visit counters for every cell it hits, and eight of them share a 32-byte sector
+//            here (two would inside the 16-byte cells)
 //   dir    : int[N * dir_cap]        particle i, patch (px,py) at dir[i*dir_cap + px*npy + py], -1 = unallocated
 //   geom   : Geom[N]                 per-particle m_sizeX2/m_sizeY2 + directory dims (diverge after Map::resize)
 //   refcnt : int[pool_cap]           number of directory entries that reference a patch (autoptr::shares)
@@ -59,7 +62,8 @@ struct Counters {  // zeroed per stage, read back by the host
 };
 
 struct Pool {
-    int4* cells;       // [(cap+1)*1024], patch `cap` is all zero
+    int4* cells;       // [(cap+1)*1024] {acc.x, acc.y, n, 0}; patch `cap` is all zero
+    int* visits;       // [(cap+1)*1024]
     unsigned* occ;     // [(cap+1)*32] occupancy bitmap (see the layout note above)
     int* refcnt;       // [cap]
     int* free_list;    // [cap] stack of free patch ids, top at *free_top

@@ -92,7 +92,7 @@ __global__ void k_dist_count(const int* __restrict__ slots, const Geom* __restri
 
 // pack one parent per block: header, directory entries that are allocated, their patches
 __global__ void __launch_bounds__(512) k_dist_pack(const int* __restrict__ slots, const Geom* __restrict__ geom, const int* __restrict__ dir, int dir_cap,
-                                                   const int4* __restrict__ pool, const unsigned long long* __restrict__ off, unsigned char* __restrict__ buf) {
+                                                   const int4* __restrict__ pool, const int* __restrict__ visits, const unsigned long long* __restrict__ off, unsigned char* __restrict__ buf) {
     __shared__ int s_n;
     const int s = blockIdx.x, slot = slots[s];
     const Geom g = geom[slot];
@@ -110,7 +110,10 @@ __global__ void __launch_bounds__(512) k_dist_pack(const int* __restrict__ slots
     int4* cells = reinterpret_cast<int4*>(base + kHeaderBytes + (((unsigned long long)count * 4 + 15) & ~15ull));
     for (long long i = threadIdx.x; i < (long long)count * kPatchCells; i += blockDim.x) {
         const int k = (int)(i >> 10);
-        cells[i] = __ldcg(pool + (size_t)dirp[entries[k]] * kPatchCells + (i & 1023));
+        const size_t ci = (size_t)dirp[entries[k]] * kPatchCells + (i & 1023);
+        int4 c = __ldcg(pool + ci);
+        c.w = __ldcg(visits + ci);  // on the wire a cell is the reference's PointAccumulator: {acc.x, acc.y, n, visits}
+        cells[i] = c;
     }
 }
 
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(512) k_dist_install(int first_slot, Geom* __re
     for (long long i = threadIdx.x; i < (long long)count * kPatchCells; i += blockDim.x) {
         const int id = s_ids[i >> 10];
         const int4 c = cells[i];
-        if (id >= 0) pool.cells[(size_t)id * kPatchCells + (i & 1023)] = c;
+        if (id >= 0) { pool.cells[(size_t)id * kPatchCells + (i & 1023)] = make_int4(c.x, c.y, c.z, 0); pool.visits[(size_t)id * kPatchCells + (i & 1023)] = c.w; }
         // 512 threads, count * 1024 cells: every warp covers one whole patch row per trip
         const unsigned bits = __ballot_sync(0xffffffffu, occ_default(c.z, c.w));
         if (id >= 0 && (i & 31) == 0) pool.occ[(size_t)id * kPatch + ((i & 1023) >> kPatchMag)] = bits;
@@ -311,7 +314,7 @@ int gm_dist_register(gm_ctx* ctx, const double* ranges, const double* poses, con
             if (recv_off[nrecv] > d->recv_cap) { CK(dalloc(d->d_recv, (size_t)recv_off[nrecv])); d->recv_cap = recv_off[nrecv]; }
             if (nsend) {
                 CK(cudaMemcpyAsync(d->d_off, send_off.data(), sizeof(unsigned long long) * nsend, cudaMemcpyHostToDevice, ctx->st));
-                gm::k_dist_pack<<<(unsigned)nsend, 512, 0, ctx->st>>>(d->d_slots, ctx->geom, ctx->dir, ctx->dir_cap, ctx->pool.cells, d->d_off, d->d_send);
+                gm::k_dist_pack<<<(unsigned)nsend, 512, 0, ctx->st>>>(d->d_slots, ctx->geom, ctx->dir, ctx->dir_cap, ctx->pool.cells, ctx->pool.visits, d->d_off, d->d_send);
                 ctx->stats.launches++;
             }
             NK(g_nccl.GroupStart());

@@ -87,6 +87,7 @@ constexpr int kSmGroups = kSmThreads / 6;  // 48 beam groups x 6 candidate poses
 struct MatchCtx {
     const int* __restrict__ dirp;
     const int4* __restrict__ pool;
+    const int* __restrict__ visits;
     const unsigned* __restrict__ occ;
     const double* __restrict__ inv_n;
     Geom g;
@@ -193,7 +194,7 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
                 mask &= mask - 1;
                 const int xx = i >> 3, yy = i & 7;
                 long long fi; int fn = 0, fv = 0;
-                if (cell_addr(g, M.dirp, x0 + xx + ifx, y0 + yy + ify, fi)) { const int4 f = __ldg(M.pool + fi); fn = f.z; fv = f.w; }
+                if (cell_addr(g, M.dirp, x0 + xx + ifx, y0 + yy + ify, fi)) { fn = __ldg(M.pool + fi).z; fv = __ldg(M.visits + fi); }
                 if (!is_free<true>(fn, fv, P)) continue;
                 const int4 cell = __ldg(M.pool + cell_of(i));
                 const double inv = cell.z < kInvTable ? __ldg(M.inv_n + cell.z) : recip_slow(cell.z);
@@ -213,7 +214,7 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
         for (int yy = 0; yy <= 2 * k; yy++) {
             long long ci;
             int4 cell = make_int4(0, 0, 0, 0);
-            if (cell_addr(g, M.dirp, x0 + xx, y0 + yy, ci)) cell = __ldg(M.pool + ci);
+            if (cell_addr(g, M.dirp, x0 + xx, y0 + yy, ci)) { cell = __ldg(M.pool + ci); cell.w = __ldg(M.visits + ci); }
             if (!is_occ<false>(cell.z, cell.w, P)) continue;
             if (!have_free) {
                 const double pfx = (lpx + (r - free_off) * c) - phx, pfy = (lpy + (r - free_off) * s) - phy;
@@ -222,7 +223,7 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
                 have_free = true;
             }
             long long fi; int fn = 0, fv = 0;
-            if (cell_addr(g, M.dirp, x0 + xx + ifx, y0 + yy + ify, fi)) { const int4 f = __ldg(M.pool + fi); fn = f.z; fv = f.w; }
+            if (cell_addr(g, M.dirp, x0 + xx + ifx, y0 + yy + ify, fi)) { fn = __ldg(M.pool + fi).z; fv = __ldg(M.visits + fi); }
             if (!is_free<false>(fn, fv, P)) continue;
             const double inv = (cell.z >= 0 && cell.z < kInvTable) ? __ldg(M.inv_n + cell.z) : recip_slow(cell.z);
             const double mx = phx - (double)__int_as_float(cell.x) * inv, my = phy - (double)__int_as_float(cell.y) * inv;
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
     const unsigned q = blockIdx.x, p = A.query >= 0 ? A.particle_idx[q] : q;
     const int t = threadIdx.x;
     MatchCtx M;
-    M.dirp = A.dir + (size_t)p * A.dir_cap; M.pool = A.pool; M.occ = A.occ; M.inv_n = A.inv_n; M.g = A.geom[p];
+    M.dirp = A.dir + (size_t)p * A.dir_cap; M.pool = A.pool; M.visits = A.visits; M.occ = A.occ; M.inv_n = A.inv_n; M.g = A.geom[p];
     M.zero_patch = A.zero_patch;
 
     if (t == 0) {
@@ -679,6 +680,7 @@ constexpr int kRegThreads = 1024;
 constexpr int kTileWords = kPatchCells / 2;  // a tile counts visits of one patch: 1024 cells x 16 bit, two per word
 // hit grouping (k_register phase 4), per unit of sort_n: 2 table keys (8 B) + 2 first + 2 last (4 B each) + 1 slot (4 B)
 constexpr int kHitBytes = 36;
+constexpr int kMaxTiles = 112;  // tiles that fit the 227 KB of shared memory a CTA can have
 
 // dynamic shared memory of k_register (see register_smem_bytes): active-patch bitmap over the directory, its
 // running popcount per word, per-beam records, visit-count tiles (reused by the hit table afterwards)
@@ -711,6 +713,7 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
     __shared__ unsigned long long s_free, s_hit, s_cow, s_alloc;
     __shared__ int s_part[kRegThreads / 32];
     __shared__ int s_nactive;
+    __shared__ int s_tile_id[kMaxTiles];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 
     long long tph = clock64();
@@ -819,12 +822,16 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
             nid = __shfl_sync(0xffffffffu, nid, 0); mode = __shfl_sync(0xffffffffu, mode, 0);
             if (mode == 0 || nid < 0) continue;
             int4* dst = A.pool.cells + (size_t)nid * kPatchCells;
+            int4* vdst = reinterpret_cast<int4*>(A.pool.visits + (size_t)nid * kPatchCells);
             if (mode == 1) {
                 for (int i = lane; i < kPatchCells; i += 32) dst[i] = make_int4(0, 0, 0, 0);
+                for (int i = lane; i < kPatchCells / 4; i += 32) vdst[i] = make_int4(0, 0, 0, 0);
                 A.pool.occ[(size_t)nid * kPatch + lane] = 0u;
             } else {
                 const int4* src = A.pool.cells + (size_t)id * kPatchCells;
                 for (int i = lane; i < kPatchCells; i += 32) dst[i] = __ldcg(src + i);
+                const int4* vsrc = reinterpret_cast<const int4*>(A.pool.visits + (size_t)id * kPatchCells);
+                for (int i = lane; i < kPatchCells / 4; i += 32) vdst[i] = __ldcg(vsrc + i);
                 A.pool.occ[(size_t)nid * kPatch + lane] = __ldcg(A.pool.occ + (size_t)id * kPatch + lane);
             }
             __syncwarp();
@@ -852,6 +859,12 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
     for (int first = 0; first < nactive && P.generate_map; first += A.tile_cap) {
         const int ntile = min(A.tile_cap, nactive - first);
         for (int i = threadIdx.x; i < ntile * kTileWords; i += blockDim.x) M.tiles[i] = 0u;
+        if ((int)threadIdx.x < ntile) {  // patch of tile t: the directory entry of rank first + t, found from the prefix sums
+            const int rank = first + threadIdx.x;
+            int lo = 0, hi = nwords - 1;  // last word whose prefix <= rank and that holds the rank-th bit
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((int)M.prefix[mid] <= rank) lo = mid; else hi = mid - 1; }
+            s_tile_id[threadIdx.x] = dirp[(lo << 5) + (int)__fns(active[lo], 0, rank - (int)M.prefix[lo] + 1)];
+        }
         __syncthreads();
         for (int it = threadIdx.x; it < nitems; it += blockDim.x) {
             int lo = 0, hi = (int)P.nbeams - 1;
@@ -888,39 +901,38 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
         }
         __syncthreads();
         PHASE(4);
-        // flush: a warp per tile; the directory entry of rank first + t is found from the prefix sums
-        for (int t = warp; t < ntile; t += nw) {
-            const int rank = first + t;
-            int lo = 0, hi = nwords - 1;  // last word whose prefix <= rank and that holds the rank-th bit
-            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((int)M.prefix[mid] <= rank) lo = mid; else hi = mid - 1; }
-            const int e = (lo << 5) + (int)__fns(active[lo], 0, rank - (int)M.prefix[lo] + 1);
-            const int id = dirp[e];
+        // flush in units of a quarter tile (8 patch rows) dealt round-robin to the warps: tiles differ a lot in how many
+        // of their cells were crossed
+        for (int u = warp; u < ntile * 4; u += nw) {
+            const int t = u >> 2, g8 = (u & 3) << 8, row0 = (u & 3) << 3;
+            const int id = s_tile_id[t];
             if (id < 0) continue;
-            int* cells = reinterpret_cast<int*>(A.pool.cells + (size_t)id * kPatchCells);
-            unsigned* occ = A.pool.occ + (size_t)id * kPatch;
+            int* vis = A.pool.visits + (size_t)id * kPatchCells;
+            const int4* cells = A.pool.cells + (size_t)id * kPatchCells;
+            unsigned* occ = A.pool.occ + (size_t)id * kPatch + row0;
             const unsigned* tile = M.tiles + t * kTileWords;
-            // eight independent loads in flight per lane: the patch is private, plain read-modify-write.  A warp covers one
-            // row of the patch per k, so two ballots give the row's touched cells and their new occupancy bits; lane r
-            // keeps bitmap word r in a register and writes it back if it changed
-            const unsigned occ_old = __ldcg(occ + lane);
+            // eight independent loads in flight per lane: the patch is private, plain read-modify-write of the visits
+            // plane (a warp covers one row of the patch per k: 128 contiguous bytes).  More visits can only clear an
+            // occupancy bit: lane k keeps the bitmap word of row k, and n is fetched for the few crossed cells whose bit is set
+            const unsigned occ_old = lane < 8 ? __ldcg(occ + lane) : 0u;
             unsigned occ_new = occ_old;
-#pragma unroll 1
-            for (int g8 = 0; g8 < kPatchCells; g8 += 256) {
-                int2 nv[8]; unsigned c[8];
+            int v[8]; unsigned c[8];
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int ci = g8 + 32 * k + lane;
-                    c[k] = (tile[ci >> 1] >> ((ci & 1) << 4)) & 0xffffu;
-                    nv[k] = c[k] ? __ldcg(reinterpret_cast<const int2*>(cells + (ci << 2) + 2)) : make_int2(0, 0);  // untouched cells cost no traffic
-                }
+            for (int k = 0; k < 8; k++) {
+                const int ci = g8 + 32 * k + lane;
+                c[k] = (tile[ci >> 1] >> ((ci & 1) << 4)) & 0xffffu;
+                v[k] = c[k] ? __ldcg(vis + ci) : 0;  // untouched cells cost no traffic
+            }
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int nvis = nv[k].y + (int)c[k];
-                    if (c[k]) { cells[((g8 + 32 * k + lane) << 2) + 3] = nvis; nfree += c[k]; }  // update(false) c times
-                    const unsigned touched = __ballot_sync(0xffffffffu, c[k] != 0);
-                    const unsigned bits = __ballot_sync(0xffffffffu, c[k] != 0 && occ_default(nv[k].x, nvis));
-                    if (lane == (g8 >> kPatchMag) + k) occ_new = (occ_new & ~touched) | bits;
-                }
+            for (int k = 0; k < 8; k++) {
+                const int ci = g8 + 32 * k + lane;
+                const int nvis = v[k] + (int)c[k];
+                if (c[k]) { vis[ci] = nvis; nfree += c[k]; }  // update(false) c times
+                const unsigned roww = __shfl_sync(0xffffffffu, occ_old, k);
+                bool clear = false;
+                if (c[k] && ((roww >> lane) & 1u)) clear = !occ_default(__ldcg(cells + ci).z, nvis);
+                const unsigned cleared = __ballot_sync(0xffffffffu, clear);
+                if (lane == k) occ_new &= ~cleared;
             }
             if (occ_new != occ_old) occ[lane] = occ_new;
         }
@@ -967,13 +979,14 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
         if (id < 0) continue;
         int* cell = reinterpret_cast<int*>(A.pool.cells + (size_t)id * kPatchCells + ((x & 31) << kPatchMag) + (y & 31));
         float ax = __int_as_float(__ldcg(cell)), ay = __int_as_float(__ldcg(cell + 1));
-        const int n0 = __ldcg(cell + 2), v0 = __ldcg(cell + 3);  // the cell belongs to this thread alone now
+        int* visp = A.pool.visits + (size_t)id * kPatchCells + ((x & 31) << kPatchMag) + (y & 31);
+        const int n0 = __ldcg(cell + 2), v0 = __ldcg(visp);  // the cell belongs to this thread alone now
         int cnt = 0;
         const int last = hlast[slot];
         for (int q = b; q <= last; q++)
             if (slot_of[q] == slot) { ax += rec[q].hx; ay += rec[q].hy; cnt++; }  // acc += (float)phit, smmap.h:51-52
         cell[0] = __float_as_int(ax); cell[1] = __float_as_int(ay);
-        cell[2] = n0 + cnt; cell[3] = v0 + cnt;
+        cell[2] = n0 + cnt; *visp = v0 + cnt;
         const bool was = occ_default(n0, v0), is = occ_default(n0 + cnt, v0 + cnt);
         if (was != is) {  // other cells of the row may flip at the same time: atomics on the bitmap word
             unsigned* w = A.pool.occ + (size_t)id * kPatch + (x & 31);
@@ -1116,6 +1129,7 @@ __global__ void __launch_bounds__(256) k_digest(DigestArgs A) {
         const int4* pc = A.pool + (size_t)id * kPatchCells;
         for (int i = lane; i < kPatchCells; i += 32) {
             int4 c = pc[i];
+            c.w = A.visits[(size_t)id * kPatchCells + i];
             // the warp holds row i >> 5 of the patch: its occupancy bits must equal the bitmap word
             const unsigned bits = __ballot_sync(0xffffffffu, occ_default(c.z, c.w));
             if (lane == 0 && bits != A.occ[(size_t)id * kPatch + (i >> kPatchMag)]) bad++;
@@ -1140,21 +1154,26 @@ __global__ void k_export_list(const int* __restrict__ dirp, Geom g, int* __restr
         if (id >= 0) { int k = atomicAdd(count, 1); list[2 * k] = e; list[2 * k + 1] = id; }
     }
 }
-__global__ void k_export_gather(const int4* __restrict__ pool, const int* __restrict__ list, int4* __restrict__ out) {
+__global__ void k_export_gather(const int4* __restrict__ pool, const int* __restrict__ visits, const int* __restrict__ list, int4* __restrict__ out) {
     const int k = blockIdx.x, id = list[2 * k + 1];
-    for (int i = threadIdx.x; i < kPatchCells; i += blockDim.x) out[(size_t)k * kPatchCells + i] = pool[(size_t)id * kPatchCells + i];
+    for (int i = threadIdx.x; i < kPatchCells; i += blockDim.x) {  // gm_cell: {acc.x, acc.y, n, visits}
+        int4 c = pool[(size_t)id * kPatchCells + i];
+        c.w = visits[(size_t)id * kPatchCells + i];
+        out[(size_t)k * kPatchCells + i] = c;
+    }
 }
 
 // occupancy grid of one particle (the nav_msgs::OccupancyGrid fill of gmapping/src/slam_gmapping.cpp:956-993):
 // out[y * width + x] = -1 unknown (never visited), 100 if n / visits > occ_thresh, else 0
-__global__ void k_export_occupancy(const int* __restrict__ dirp, Geom g, const int4* __restrict__ pool, double occ_thresh, signed char* __restrict__ out,
+__global__ void k_export_occupancy(const int* __restrict__ dirp, Geom g, const int4* __restrict__ pool, const int* __restrict__ visits, double occ_thresh, signed char* __restrict__ out,
                                    int width, int height) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= width || y >= height) return;
     long long ci;
     signed char v = -1;
     if (cell_addr(g, dirp, x, y, ci)) {
-        const int4 c = __ldg(pool + ci);
+        int4 c = __ldg(pool + ci);
+        c.w = __ldg(visits + ci);
         if (c.w) v = ((double)c.z / (double)c.w > occ_thresh) ? 100 : 0;
     }
     out[(size_t)y * width + x] = v;
@@ -1178,7 +1197,8 @@ __global__ void k_install_patches(int* dirp, Geom g, const int* __restrict__ coo
     if (id < 0) return;
     for (int i = threadIdx.x; i < kPatchCells; i += blockDim.x) {  // blockDim is a multiple of 32: a warp covers one row per trip
         const int4 c = staged[(size_t)k * kPatchCells + i];
-        pool.cells[(size_t)id * kPatchCells + i] = c;
+        pool.cells[(size_t)id * kPatchCells + i] = make_int4(c.x, c.y, c.z, 0);
+        pool.visits[(size_t)id * kPatchCells + i] = c.w;
         const unsigned bits = __ballot_sync(0xffffffffu, occ_default(c.z, c.w));
         if ((i & 31) == 0) pool.occ[(size_t)id * kPatch + (i >> kPatchMag)] = bits;
     }
@@ -1186,9 +1206,9 @@ __global__ void k_install_patches(int* dirp, Geom g, const int* __restrict__ coo
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-void launch_export_occupancy(const int* dirp, Geom g, const int4* pool, double occ_thresh, signed char* out, int width, int height, cudaStream_t st) {
+void launch_export_occupancy(const int* dirp, Geom g, const int4* pool, const int* visits, double occ_thresh, signed char* out, int width, int height, cudaStream_t st) {
     dim3 grid((width + 255) / 256, height);
-    k_export_occupancy<<<grid, 256, 0, st>>>(dirp, g, pool, occ_thresh, out, width, height);
+    k_export_occupancy<<<grid, 256, 0, st>>>(dirp, g, pool, visits, occ_thresh, out, width, height);
 }
 void launch_release_particle(int* dirp, int nent, const Pool& pool, cudaStream_t st) { k_release_particle<<<64, 256, 0, st>>>(dirp, nent, pool); }
 void launch_install_patches(int* dirp, Geom g, const int* coords, const int4* staged, const Pool& pool, Counters* ctr, int n, cudaStream_t st) {
@@ -1230,6 +1250,6 @@ void launch_resample(const double* w, unsigned n, double u01, double* cum, doubl
 }
 void launch_digest(const DigestArgs& a, unsigned n, cudaStream_t st) { k_digest<<<n, 256, 0, st>>>(a); }
 void launch_export_list(const int* dirp, Geom g, int* list, int* count, cudaStream_t st) { k_export_list<<<64, 256, 0, st>>>(dirp, g, list, count); }
-void launch_export_gather(const int4* pool, const int* list, int4* out, int n, cudaStream_t st) { k_export_gather<<<n, 256, 0, st>>>(pool, list, out); }
+void launch_export_gather(const int4* pool, const int* visits, const int* list, int4* out, int n, cudaStream_t st) { k_export_gather<<<n, 256, 0, st>>>(pool, visits, list, out); }
 
 }  // namespace gm

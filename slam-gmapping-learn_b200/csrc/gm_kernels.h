@@ -9,7 +9,7 @@ struct ScanMatchArgs {
     const double* ranges; const double* angles;
     double* poses;
     const Geom* geom; const int* dir; int dir_cap;
-    const int4* pool;
+    const int4* pool; const int* visits;
     const unsigned* occ;  // occupancy bitmap of the pool (gm_device.cuh)
     const double* inv_n;
     double minimum_score;
@@ -51,7 +51,7 @@ struct RemapArgs {
 };
 struct SweepArgs { Pool pool; int* refcnt_new; };
 struct DigestArgs {
-    const Geom* geom; const int* dir; int dir_cap; const int4* pool; const unsigned* occ;
+    const Geom* geom; const int* dir; int dir_cap; const int4* pool; const int* visits; const unsigned* occ;
     unsigned first; unsigned long long* out;  // 7 words per particle: the six of gm_digest + mismatching occupancy-bitmap rows
 };
 
@@ -73,10 +73,10 @@ void launch_fill_geom(Geom* g, unsigned n, Geom v, cudaStream_t st);
 void launch_normalize(const double* logw, unsigned n, double gain, double* w, double* neff, cudaStream_t st);
 void launch_resample(const double* w, unsigned n, double u01, double* cum, double* tgt, unsigned* idx, unsigned* emitted, cudaStream_t st);
 void launch_digest(const DigestArgs& a, unsigned n, cudaStream_t st);
-void launch_export_occupancy(const int* dirp, Geom g, const int4* pool, double occ_thresh, signed char* out, int width, int height, cudaStream_t st);
+void launch_export_occupancy(const int* dirp, Geom g, const int4* pool, const int* visits, double occ_thresh, signed char* out, int width, int height, cudaStream_t st);
 void launch_release_particle(int* dirp, int nent, const Pool& pool, cudaStream_t st);
 void launch_install_patches(int* dirp, Geom g, const int* coords, const int4* staged, const Pool& pool, Counters* ctr, int n, cudaStream_t st);
 void launch_export_list(const int* dirp, Geom g, int* list, int* count, cudaStream_t st);
-void launch_export_gather(const int4* pool, const int* list, int4* out, int n, cudaStream_t st);
+void launch_export_gather(const int4* pool, const int* visits, const int* list, int4* out, int n, cudaStream_t st);
 
 }  // namespace gm
