@@ -279,7 +279,9 @@ struct SmShared {
     double fill_theta[3];  // theta for the trig tables listed in fill[]
     int fill[3];           // physical trig tables to recompute before evaluating (-1: none)
     int tab_of[3];         // physical table of: the current theta, theta + adelta, theta - adelta
-    int ncand;             // 1 or 6 poses
+    int ncand;             // poses to evaluate: 1, or the 6 moves of a round, or 5 of them (see plan_round)
+    int cand[6];           // which moves
+    int skip;              // the move left out (-1: none)
     int mode;              // 0 score(), 1 likelihoodAndScore()
     int done;
     // reduction scratch
@@ -288,8 +290,9 @@ struct SmShared {
     unsigned red_c[16], red_v[16];
     // hill-climb state (thread 0 only; shared memory keeps it out of everybody's registers)
     double cur[3], init[3], key[3], currentScore, bestScore, adelta, ldelta;
-    unsigned refinement, evals, valid_lik;
-    int phase, key_ok[3];
+    double prev[3];        // the pose the last winning move started from
+    unsigned refinement, evals, evaluated, valid_lik;
+    int phase, key_ok[3], last_move;
 };
 
 // candidate pose m of a hill-climb round around `cur` (scanmatcher.cpp:441-494: Front, Back, Left, Right, TurnLeft, TurnRight)
@@ -314,20 +317,33 @@ __device__ __forceinline__ void want_table(SmShared& S, int which, double theta,
     }
 }
 
-// thread 0: plan one hill-climb round (scanmatcher.cpp:418-440)
+// thread 0: plan one hill-climb round (scanmatcher.cpp:418-440).
+// The round after a winning move re-evaluates, as the move opposite to it, the pose it came from -- whose score (odometry
+// gain included) is the previous currentScore, strictly below the present one, so it cannot win the `localScore >
+// currentScore` test of scanmatcher.cpp:510.  When that candidate is bit for bit the previous pose ((x + d) - d == x almost
+// always) it is counted but not evaluated.
 __device__ __noinline__ void plan_round(const DevParams& P, SmShared& S) {
-    if (S.bestScore >= S.currentScore) { S.refinement++; S.adelta *= .5; S.ldelta *= .5; }
+    const bool halved = S.bestScore >= S.currentScore;
+    if (halved) { S.refinement++; S.adelta *= .5; S.ldelta *= .5; }
     S.bestScore = S.currentScore;
-    int nfill = 0;
+    S.skip = -1;
+    if (S.last_move >= 0 && !halved) {
+        double back[3];
+        candidate(S.cur, S.last_move ^ 1, S.ldelta, S.adelta, back);
+        if (back[0] == S.prev[0] && back[1] == S.prev[1] && back[2] == S.prev[2]) S.skip = S.last_move ^ 1;
+    }
+    int nfill = 0, nc = 0;
     for (int m = 0; m < 6; m++) {
+        if (m == S.skip) continue;
         double cm[3], lx, ly, lt;
         candidate(S.cur, m, S.ldelta, S.adelta, cm);
         laser_pose(P, cm[0], cm[1], cm[2], lx, ly, lt);
         S.lx[m] = lx; S.ly[m] = ly;
         if (m >= 4) want_table(S, m - 3, lt, nfill);
+        S.cand[nc++] = m;
     }
     for (int j = nfill; j < 3; j++) S.fill[j] = -1;
-    S.ncand = 6; S.mode = 0; S.phase = 1;
+    S.ncand = nc; S.mode = 0; S.phase = 1;
 }
 
 // scanMatch for one particle per CTA: hill-climb (optimize), accept/reject, likelihoodAndScore; or, with
@@ -348,7 +364,7 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
     if (t == 0) {
         S.init[0] = S.cur[0] = A.poses[3 * q]; S.init[1] = S.cur[1] = A.poses[3 * q + 1]; S.init[2] = S.cur[2] = A.poses[3 * q + 2];
         S.adelta = P.opt_angular_delta; S.ldelta = P.opt_linear_delta;
-        S.refinement = 0; S.evals = 1; S.bestScore = -1; S.done = 0;
+        S.refinement = 0; S.evals = 1; S.evaluated = 1; S.bestScore = -1; S.done = 0; S.last_move = -1; S.skip = -1; S.cand[0] = 0;
         S.tab_of[0] = 0; S.tab_of[1] = 1; S.tab_of[2] = 2;
         S.key_ok[0] = S.key_ok[1] = S.key_ok[2] = 0;
         double lx, ly, lt;
@@ -377,13 +393,14 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
             filled = true;
         }
         if (filled) __syncthreads();
-        // ---- evaluate: thread t works for candidate t % ncand on beams t / ncand, + ngroups, ...
-        const int mode = S.mode;
-        const bool six = S.ncand == 6;
-        const int m = six ? t % 6 : 0, grp = six ? t / 6 : t, ngroups = six ? kSmGroups : kSmThreads;
+        // ---- evaluate: thread t works for candidate cand[t % ncand] on beams t / ncand, + ngroups, ...
+        const int mode = S.mode, nc = S.ncand;
+        const bool multi = nc > 1;
+        const int ngroups = nc == 6 ? kSmGroups : kSmThreads / nc, grp = nc == 6 ? t / 6 : t / nc;
+        const int m = multi ? S.cand[nc == 6 ? t % 6 : t - grp * nc] : 0;
         double acc_s = 0., acc_l = 0.;
         unsigned cnt = 0, valid = 0;
-        if (!six || t < 6 * kSmGroups) {
+        if (grp < ngroups) {
             const double mlx = S.lx[m], mly = S.ly[m];
             const double2* tab = tabs + (size_t)S.tab_of[m < 4 ? 0 : m - 3] * P.nbeams;
             // pfree offset: map.getDelta()*freeDelta in score() (scanmatcher.h:208), freeDelta in likelihoodAndScore() (:320)
@@ -404,14 +421,14 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
         }
         // ---- reduce (fixed shape: the sums do not depend on scheduling)
         const int warp = t >> 5, lane = t & 31;
-        if (six) {
+        if (multi) {
             S.part[t] = acc_s;
             __syncthreads();
-            if (warp < 6) {  // warp w sums the partials of candidate w: lane j takes groups j and j + 32
-                double v = S.part[6 * lane + warp];
-                if (lane + 32 < kSmGroups) v += S.part[6 * (lane + 32) + warp];
+            if (warp < nc) {  // warp w sums the partials of candidate cand[w]: lane j takes groups j and j + 32 (ngroups <= 64)
+                double v = lane < ngroups ? S.part[nc * lane + warp] : 0.;
+                if (lane + 32 < ngroups) v += S.part[nc * (lane + 32) + warp];
                 v = warp_sum(v);
-                if (lane == 0) S.red[warp] = v;
+                if (lane == 0) S.red[S.cand[warp]] = v;
             }
         } else {
             acc_s = warp_sum(acc_s); acc_l = warp_sum(acc_l);
@@ -425,8 +442,10 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
         if (S.phase == 1) {
             // scanmatcher.cpp:441-517: pick the best of the six moves (strict >, first wins)
             S.evals += 6;
+            S.evaluated += (unsigned)S.ncand;
             int bm = -1;
             for (int mm = 0; mm < 6; mm++) {
+                if (mm == S.skip) continue;
                 double odo_gain = 1;
                 if (P.ang_rel > 0. || P.lin_rel > 0.) {
                     double cm[3];
@@ -436,9 +455,11 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
                 const double localScore = odo_gain * S.red[mm];
                 if (localScore > S.currentScore) { S.currentScore = localScore; bm = mm; }
             }
+            S.last_move = bm;
             if (bm >= 0) {
                 double nb[3];
                 candidate(S.cur, bm, S.ldelta, S.adelta, nb);
+                S.prev[0] = S.cur[0]; S.prev[1] = S.cur[1]; S.prev[2] = S.cur[2];
                 S.cur[0] = nb[0]; S.cur[1] = nb[1]; S.cur[2] = nb[2];
                 if (bm >= 4) {  // a turn won: its table now holds the current theta
                     const int o = S.tab_of[0];
@@ -463,7 +484,7 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
                 A.poses[3 * p] = S.cur[0]; A.poses[3 * p + 1] = S.cur[1]; A.poses[3 * p + 2] = S.cur[2];
                 A.score[p] = S.bestScore; A.s[p] = ss; A.l[p] = ll; A.c[p] = cc; A.evals[p] = S.evals;
                 atomicAdd(&A.counters->score_evals, (unsigned long long)S.evals);
-                atomicAdd(&A.counters->beam_evals, (unsigned long long)S.evals * A.valid_score_beams + vv);
+                atomicAdd(&A.counters->beam_evals, (unsigned long long)S.evaluated * A.valid_score_beams + vv);
             }
             S.done = 1;
             continue;
@@ -866,6 +887,12 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
             s_tile_id[threadIdx.x] = dirp[(lo << 5) + (int)__fns(active[lo], 0, rank - (int)M.prefix[lo] + 1)];
         }
         __syncthreads();
+        // the counting below keeps to shared memory: meanwhile pull the visit planes of this pass (4 KB per patch) into
+        // L2, where the flush will find them
+        for (int i = threadIdx.x; i < ntile * 32; i += blockDim.x) {
+            const int id = s_tile_id[i >> 5];
+            if (id >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.pool.visits + (size_t)id * kPatchCells + ((i & 31) << 5)));
+        }
         for (int it = threadIdx.x; it < nitems; it += blockDim.x) {
             int lo = 0, hi = (int)P.nbeams - 1;
             while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (M.items[mid] <= it) lo = mid; else hi = mid - 1; }

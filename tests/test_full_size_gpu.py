@@ -53,7 +53,10 @@ def test_c4_shape_conservation_determinism_and_subset_parity():
     poses, score, s, l, c, ev = out1
     assert np.array_equal(poses[:N // 2], poses[N // 2:]) and np.array_equal(l[:N // 2], l[N // 2:])
     assert ev.min() >= 37 and score.min() > 100
-    assert ctx.stats()["beam_evals"] == int(ev.sum()) * 1081 + N * 1081
+    # beam_evals counts the window searches actually run: every score() of the reference's count `ev` except the
+    # candidates k_scanmatch proves to be losers without evaluating them (the pose a winning move came from)
+    be, ref_total = ctx.stats()["beam_evals"], int(ev.sum()) * 1081 + N * 1081
+    assert 0.85 * ref_total < be <= ref_total and (ref_total - be) % 1081 == 0
     for j in subset:
         so, po = orc.optimize(m, maps[int(j)], init[j], r)
         s1, l1, c1 = orc.likelihood_and_score(m, maps[int(j)], po, r)
