@@ -85,7 +85,9 @@ constexpr int kSmThreads = 288;
 constexpr int kSmGroups = kSmThreads / 6;  // 48 beam groups x 6 candidate poses: every thread works
 
 struct MatchCtx {
-    const int* __restrict__ dirp;
+    // the particle's directory, read through a shared-memory slot at every use: kept in registers the compiler spends ten
+    // instructions per lookup rebuilding the 64-bit address from the kernel parameters instead
+    const int* const* dirp_s;
     const int4* __restrict__ pool;
     const int* __restrict__ visits;
     const unsigned* __restrict__ occ;
@@ -95,7 +97,7 @@ struct MatchCtx {
 };
 
 __device__ __forceinline__ int dir_at(const MatchCtx& M, int px, int py) {
-    return ((unsigned)px < (unsigned)M.g.npx && (unsigned)py < (unsigned)M.g.npy) ? __ldg(M.dirp + px * M.g.npy + py) : -1;
+    return ((unsigned)px < (unsigned)M.g.npx && (unsigned)py < (unsigned)M.g.npy) ? __ldg(*M.dirp_s + (px * M.g.npy + py)) : -1;
 }
 
 // occupancy tests (smmap.h:25 against fullnessThreshold); DEF = the default threshold 0.1, decided in exact integers
@@ -180,8 +182,12 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
                 mask &= mask - 1;  // no-op when mask is already 0
                 const int4 ca = __ldg(M.pool + cell_of(i));
                 const int4 cb = __ldg(M.pool + cell_of(j));
-                const double ia = ca.z < kInvTable ? __ldg(M.inv_n + ca.z) : recip_slow(ca.z);  // mean() = (1./n) * acc, smmap.h:24
-                const double ib = cb.z < kInvTable ? __ldg(M.inv_n + cb.z) : recip_slow(cb.z);
+                // mean() = (1./n) * acc, smmap.h:24; n > 0 here, and the table covers n < kInvTable
+                double ia = __ldg(M.inv_n + min(ca.z, kInvTable - 1)), ib = __ldg(M.inv_n + min(cb.z, kInvTable - 1));
+                if ((ca.z | cb.z) >= kInvTable) {
+                    if (ca.z >= kInvTable) ia = recip_slow(ca.z);
+                    if (cb.z >= kInvTable) ib = recip_slow(cb.z);
+                }
                 const double ax = phx - (double)__int_as_float(ca.x) * ia, ay = phy - (double)__int_as_float(ca.y) * ia;
                 const double bxx = phx - (double)__int_as_float(cb.x) * ib, byy = phy - (double)__int_as_float(cb.y) * ib;
                 const double na = ax * ax + ay * ay, nb = bxx * bxx + byy * byy;
@@ -194,7 +200,7 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
                 mask &= mask - 1;
                 const int xx = i >> 3, yy = i & 7;
                 long long fi; int fn = 0, fv = 0;
-                if (cell_addr(g, M.dirp, x0 + xx + ifx, y0 + yy + ify, fi)) { fn = __ldg(M.pool + fi).z; fv = __ldg(M.visits + fi); }
+                if (cell_addr(g, *M.dirp_s, x0 + xx + ifx, y0 + yy + ify, fi)) { fn = __ldg(M.pool + fi).z; fv = __ldg(M.visits + fi); }
                 if (!is_free<true>(fn, fv, P)) continue;
                 const int4 cell = __ldg(M.pool + cell_of(i));
                 const double inv = cell.z < kInvTable ? __ldg(M.inv_n + cell.z) : recip_slow(cell.z);
@@ -214,7 +220,7 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
         for (int yy = 0; yy <= 2 * k; yy++) {
             long long ci;
             int4 cell = make_int4(0, 0, 0, 0);
-            if (cell_addr(g, M.dirp, x0 + xx, y0 + yy, ci)) { cell = __ldg(M.pool + ci); cell.w = __ldg(M.visits + ci); }
+            if (cell_addr(g, *M.dirp_s, x0 + xx, y0 + yy, ci)) { cell = __ldg(M.pool + ci); cell.w = __ldg(M.visits + ci); }
             if (!is_occ<false>(cell.z, cell.w, P)) continue;
             if (!have_free) {
                 const double pfx = (lpx + (r - free_off) * c) - phx, pfy = (lpy + (r - free_off) * s) - phy;
@@ -223,7 +229,7 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
                 have_free = true;
             }
             long long fi; int fn = 0, fv = 0;
-            if (cell_addr(g, M.dirp, x0 + xx + ifx, y0 + yy + ify, fi)) { fn = __ldg(M.pool + fi).z; fv = __ldg(M.visits + fi); }
+            if (cell_addr(g, *M.dirp_s, x0 + xx + ifx, y0 + yy + ify, fi)) { fn = __ldg(M.pool + fi).z; fv = __ldg(M.visits + fi); }
             if (!is_free<false>(fn, fv, P)) continue;
             const double inv = (cell.z >= 0 && cell.z < kInvTable) ? __ldg(M.inv_n + cell.z) : recip_slow(cell.z);
             const double mx = phx - (double)__int_as_float(cell.x) * inv, my = phy - (double)__int_as_float(cell.y) * inv;
@@ -279,6 +285,7 @@ struct SmShared {
     double fill_theta[3];  // theta for the trig tables listed in fill[]
     int fill[3];           // physical trig tables to recompute before evaluating (-1: none)
     int tab_of[3];         // physical table of: the current theta, theta + adelta, theta - adelta
+    const int* dirp;       // directory of this CTA's particle
     int ncand;             // poses to evaluate: 1, or the 6 moves of a round, or 5 of them (see plan_round)
     int cand[6];           // which moves
     int skip;              // the move left out (-1: none)
@@ -349,19 +356,21 @@ __device__ __noinline__ void plan_round(const DevParams& P, SmShared& S) {
 // scanMatch for one particle per CTA: hill-climb (optimize), accept/reject, likelihoodAndScore; or, with
 // A.query >= 0, one standalone score()/likelihoodAndScore() per CTA.
 // dynamic shared memory: three (cos, sin) tables of nbeams double2 each.
-template <bool K1>
+// QUERY = (A.query >= 0); without it the particle is the block index, which keeps the per-particle pointers in uniform registers
+template <bool K1, bool QUERY>
 __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SmShared S;
     const DevParams& P = A.P;
     double2* const tabs = reinterpret_cast<double2*>(smem_raw);
-    const unsigned q = blockIdx.x, p = A.query >= 0 ? A.particle_idx[q] : q;
+    const unsigned q = blockIdx.x, p = QUERY ? A.particle_idx[q] : q;
     const int t = threadIdx.x;
     MatchCtx M;
-    M.dirp = A.dir + (size_t)p * A.dir_cap; M.pool = A.pool; M.visits = A.visits; M.occ = A.occ; M.inv_n = A.inv_n; M.g = A.geom[p];
+    M.dirp_s = &S.dirp; M.pool = A.pool; M.visits = A.visits; M.occ = A.occ; M.inv_n = A.inv_n; M.g = A.geom[p];
     M.zero_patch = A.zero_patch;
 
     if (t == 0) {
+        S.dirp = A.dir + (size_t)p * A.dir_cap;
         S.init[0] = S.cur[0] = A.poses[3 * q]; S.init[1] = S.cur[1] = A.poses[3 * q + 1]; S.init[2] = S.cur[2] = A.poses[3 * q + 2];
         S.adelta = P.opt_angular_delta; S.ldelta = P.opt_linear_delta;
         S.refinement = 0; S.evals = 1; S.evaluated = 1; S.bestScore = -1; S.done = 0; S.last_move = -1; S.skip = -1; S.cand[0] = 0;
@@ -402,7 +411,7 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
         unsigned cnt = 0, valid = 0;
         if (grp < ngroups) {
             const double mlx = S.lx[m], mly = S.ly[m];
-            const double2* tab = tabs + (size_t)S.tab_of[m < 4 ? 0 : m - 3] * P.nbeams;
+            const unsigned tab_s = (unsigned)__cvta_generic_to_shared(tabs + (size_t)S.tab_of[m < 4 ? 0 : m - 3] * P.nbeams);
             // pfree offset: map.getDelta()*freeDelta in score() (scanmatcher.h:208), freeDelta in likelihoodAndScore() (:320)
             const double free_off = mode ? P.free_off_lik : P.free_off_score;
             const int fqx = P.free_q[mode][0], fqy = P.free_q[mode][1];
@@ -411,7 +420,8 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
                 const double r = __ldg(A.ranges + b);
                 // score() also skips r == 0 (scanmatcher.h:195); likelihoodAndScore() does not (:303-308)
                 if (!beam_selected(P, b) || r > P.usable_range || (mode == 0 && r == 0.0)) continue;
-                const double2 cs = tab[b];
+                double2 cs;
+                asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(cs.x), "=d"(cs.y) : "r"(tab_s + b * 16u));
                 double mx, my;
                 valid++;
                 const bool found = beam_match<K1>(P, M, mlx, mly, r, cs.x, cs.y, free_off, fqx, fqy, mx, my);
@@ -1243,14 +1253,22 @@ void launch_install_patches(int* dirp, Geom g, const int* coords, const int4* st
 }
 size_t scanmatch_smem_bytes(unsigned nbeams) { return (size_t)3 * nbeams * sizeof(double2); }
 cudaError_t scanmatch_prepare(size_t smem) {
-    cudaError_t e = cudaFuncSetAttribute(k_scanmatch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scanmatch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_scanmatch<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scanmatch<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scanmatch<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scanmatch<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     return e;
 }
 void launch_scanmatch(const ScanMatchArgs& a, unsigned n, cudaStream_t st) {
     const size_t smem = scanmatch_smem_bytes(a.P.nbeams);
-    if (a.P.kernel_size == 1 && a.P.thr_is_tenth) k_scanmatch<true><<<n, kSmThreads, smem, st>>>(a);
-    else k_scanmatch<false><<<n, kSmThreads, smem, st>>>(a);
+    const bool k1 = a.P.kernel_size == 1 && a.P.thr_is_tenth;
+    if (a.query < 0) {
+        if (k1) k_scanmatch<true, false><<<n, kSmThreads, smem, st>>>(a);
+        else k_scanmatch<false, false><<<n, kSmThreads, smem, st>>>(a);
+    } else {
+        if (k1) k_scanmatch<true, true><<<n, kSmThreads, smem, st>>>(a);
+        else k_scanmatch<false, true><<<n, kSmThreads, smem, st>>>(a);
+    }
 }
 
 void launch_bounds(const BoundsArgs& a, unsigned n, unsigned threads, cudaStream_t st) { k_bounds<<<n, threads, 0, st>>>(a); }
