@@ -81,6 +81,21 @@ __device__ __forceinline__ int cell_index(double d, double delta, double inv_del
     return i;
 }
 
+// both coordinates of a point at once: one guard, one (cold) branch
+__device__ __forceinline__ void cell_index2(double dx, double dy, double delta, double inv_delta, int& ix, int& iy) {
+    const double qx = dx * inv_delta, qy = dy * inv_delta;
+    ix = __double2int_rn(qx); iy = __double2int_rn(qy);
+    const bool okx = fabs(qx - (double)ix) <= 0.499999, oky = fabs(qy - (double)iy) <= 0.499999;
+    if (!(okx && oky)) { ix = cell_index_slow(dx, delta); iy = cell_index_slow(dy, delta); }
+}
+
+// predicated load of a directory entry: no branch, no access when `pred` is false
+__device__ __forceinline__ int ldg_if(const int* p, bool pred, int dflt) {
+    int v;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.s32 %0, %3;\n\t@q ld.global.nc.s32 %0, [%1];\n\t}" : "=&r"(v) : "l"(p), "r"((int)pred), "r"(dflt));
+    return v;
+}
+
 constexpr int kSmThreads = 288;
 constexpr int kSmGroups = kSmThreads / 6;  // 48 beam groups x 6 candidate poses: every thread works
 
@@ -117,8 +132,9 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
                                            double free_off, int fqx, int fqy, double& bmx, double& bmy) {
     const Geom& g = M.g;
     const double phx = lpx + r * c, phy = lpy + r * s;
-    const int ihx = cell_index(phx - P.cx, P.delta, P.inv_delta) + g.sx2;
-    const int ihy = cell_index(phy - P.cy, P.delta, P.inv_delta) + g.sy2;
+    int ihx, ihy;
+    cell_index2(phx - P.cx, phy - P.cy, P.delta, P.inv_delta, ihx, ihy);
+    ihx += g.sx2; ihy += g.sy2;
     const int k = K1 ? 1 : P.kernel_size;
     const int x0 = ihx - k, y0 = ihy - k, x1 = ihx + k, y1 = ihy + k;
     bool found = false;
@@ -129,11 +145,17 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
         // comes from the pool's bitmap: one word per window row (two when the row crosses a patch edge in y), funnel-
         // shifted to the window's first column; no cell is read unless it is occupied.
         const int pxa = x0 >> kPatchMag, pya = y0 >> kPatchMag, pxb = x1 >> kPatchMag, pyb = y1 >> kPatchMag;
-        const bool twoy = pyb != pya;
-        const int ida = dir_at(M, pxa, pya);
-        const int idb = twoy ? dir_at(M, pxa, pyb) : ida;
-        const int idc = pxb != pxa ? dir_at(M, pxb, pya) : ida;
-        const int idd = pxb != pxa ? (twoy ? dir_at(M, pxb, pyb) : idc) : idb;
+        const bool twoy = pyb != pya, twox = pxb != pxa;
+        // four directory entries (-1 outside the directory) with predicated loads: lanes whose window crosses a patch edge
+        // are few, but nearly every warp has one, and a branch would run its body for the whole warp
+        const bool xa_in = (unsigned)pxa < (unsigned)g.npx, xb_in = (unsigned)pxb < (unsigned)g.npx;
+        const bool ya_in = (unsigned)pya < (unsigned)g.npy, yb_in = (unsigned)pyb < (unsigned)g.npy;
+        const int* da = *M.dirp_s + (pxa * g.npy + pya);
+        const int* dc = da + (twox ? g.npy : 0);
+        const int ida = ldg_if(da, xa_in && ya_in, -1);
+        const int idb = ldg_if(da + 1, twoy && xa_in && yb_in, twoy ? -1 : ida);
+        const int idc = ldg_if(dc, twox && xb_in && ya_in, twox ? -1 : ida);
+        const int idd = ldg_if(dc + 1, twox && twoy && xb_in && yb_in, twox ? (twoy ? -1 : idc) : idb);
         if ((ida & idb & idc & idd) < 0) return false;  // every patch unknown: nothing can match
         // unknown patches read the all-zero patch
         const unsigned zp = (unsigned)M.zero_patch;  // = pool capacity > every patch id; -1 as unsigned is larger still
