@@ -51,7 +51,7 @@ int gm_create(gm_ctx** out, const gm_config* cfg) {
     if (!cap) {
         size_t free_b = 0, total_b = 0;
         CKC(cudaMemGetInfo(&free_b, &total_b));
-        cap = (size_t)((double)free_b * 0.5 / (kPatchCells * (sizeof(int4) + sizeof(int)) + kPatch * sizeof(unsigned)));
+        cap = (size_t)((double)free_b * 0.5 / (kPatchCells * (sizeof(int4) + sizeof(int) + sizeof(double2)) + kPatch * sizeof(unsigned)));
         cap = std::min<size_t>(cap, (size_t)1 << 22);  // 64 GiB of patches at most by default
     }
     if (cap > ((size_t)1 << 22) - 2) cap = ((size_t)1 << 22) - 2;  // cell indexes (patch * 1024 + cell) stay below 2^32
@@ -60,6 +60,8 @@ int gm_create(gm_ctx** out, const gm_config* cfg) {
     CKC(cudaMemsetAsync(c->pool.cells + cap * kPatchCells, 0, kPatchCells * sizeof(int4), c->st));
     CKC(dalloc(c->pool.visits, (cap + 1) * kPatchCells));
     CKC(cudaMemsetAsync(c->pool.visits + cap * kPatchCells, 0, kPatchCells * sizeof(int), c->st));
+    CKC(dalloc(c->pool.means, (cap + 1) * kPatchCells));
+    CKC(cudaMemsetAsync(c->pool.means + cap * kPatchCells, 0, kPatchCells * sizeof(double2), c->st));
     CKC(dalloc(c->pool.occ, (cap + 1) * kPatch));
     CKC(cudaMemsetAsync(c->pool.occ, 0, (cap + 1) * kPatch * sizeof(unsigned), c->st));
     CKC(dalloc(c->pool.refcnt, cap)); CKC(dalloc(c->pool.free_list, cap)); CKC(dalloc(c->pool.pending, cap));
@@ -101,7 +103,7 @@ int gm_destroy(gm_ctx* c) {
     c->reg_pending = false;
     gmi_dist_destroy(c);
     if (c->st) cudaStreamSynchronize(c->st);
-    cudaFree(c->pool.cells); cudaFree(c->pool.visits); cudaFree(c->pool.occ); cudaFree(c->pool.refcnt); cudaFree(c->pool.free_list); cudaFree(c->pool.pending);
+    cudaFree(c->pool.cells); cudaFree(c->pool.visits); cudaFree(c->pool.means); cudaFree(c->pool.occ); cudaFree(c->pool.refcnt); cudaFree(c->pool.free_list); cudaFree(c->pool.pending);
     cudaFree(c->pool.free_top); cudaFree(c->pool.pending_n); cudaFree(c->refcnt_new);
     cudaFree(c->dir); cudaFree(c->dir_alt); cudaFree(c->geom); cudaFree(c->geom_alt); cudaFree(c->geom_new); cudaFree(c->shift);
     cudaFree(c->d_ranges); cudaFree(c->d_angles); cudaFree(c->d_poses); cudaFree(c->d_score); cudaFree(c->d_s); cudaFree(c->d_l);
@@ -195,7 +197,7 @@ static int run_eval(gm_ctx* ctx, int mode, uint32_t count, const uint32_t* parti
     CK(cudaMemcpyAsync(ctx->d_qposes, poses, sizeof(double) * 3 * count, cudaMemcpyHostToDevice, ctx->st));
     ScanMatchArgs a{};
     a.P = ctx->P; a.ranges = ctx->d_ranges; a.angles = ctx->d_angles; a.poses = ctx->d_qposes;
-    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.visits = ctx->pool.visits; a.occ = ctx->pool.occ; a.inv_n = ctx->d_inv_n;
+    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.visits = ctx->pool.visits; a.means = ctx->pool.means; a.occ = ctx->pool.occ; a.inv_n = ctx->d_inv_n;
     a.s = ctx->d_qs; a.l = ctx->d_ql; a.c = ctx->d_qc; a.score = ctx->d_qs; a.poses_out = ctx->d_qposes_out;
     a.query = mode; a.particle_idx = ctx->d_qidx; a.zero_patch = ctx->pool.cap;
     derive_params(a.P);
@@ -236,7 +238,7 @@ int gm_scanmatch(gm_ctx* ctx, const double* ranges, double* poses_inout, double 
     ScanMatchArgs a{};
     a.query = -1;
     a.P = ctx->P; a.ranges = ctx->d_ranges; a.angles = ctx->d_angles; a.poses = ctx->d_poses;
-    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.visits = ctx->pool.visits; a.occ = ctx->pool.occ; a.inv_n = ctx->d_inv_n;
+    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.visits = ctx->pool.visits; a.means = ctx->pool.means; a.occ = ctx->pool.occ; a.inv_n = ctx->d_inv_n;
     a.minimum_score = minimum_score;
     a.score = ctx->d_score; a.s = ctx->d_s; a.l = ctx->d_l; a.c = ctx->d_c; a.evals = ctx->d_evals;
     a.counters = ctx->d_counters;
@@ -577,7 +579,7 @@ int gm_map_digest(gm_ctx* ctx, uint32_t first, uint32_t count, gm_digest* out) {
     if (!out || first + count > ctx->n) return fail(ctx, GM_ERR_ARG, "gm_map_digest: bad argument");
     if (!count) return GM_OK;
     DigestArgs a;
-    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.visits = ctx->pool.visits; a.occ = ctx->pool.occ; a.first = first; a.out = ctx->d_digest;
+    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.visits = ctx->pool.visits; a.means = ctx->pool.means; a.occ = ctx->pool.occ; a.first = first; a.out = ctx->d_digest;
     launch_digest(a, count, ctx->st);
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_digest")) return r;
@@ -621,6 +623,7 @@ int gm_clone(gm_ctx* src, gm_ctx** out) {
         // the whole pool is copied (ids stay valid); the clone costs as much HBM as the original
         struct { void* d; const void* s; size_t bytes; } copies[] = {
             {dst->pool.cells, src->pool.cells, (cap + 1) * kPatchCells * sizeof(int4)}, {dst->pool.visits, src->pool.visits, (cap + 1) * kPatchCells * sizeof(int)},
+            {dst->pool.means, src->pool.means, (cap + 1) * kPatchCells * sizeof(double2)},
             {dst->pool.occ, src->pool.occ, (cap + 1) * kPatch * sizeof(unsigned)}, {dst->pool.refcnt, src->pool.refcnt, cap * sizeof(int)},
             {dst->pool.free_list, src->pool.free_list, cap * sizeof(int)}, {dst->pool.free_top, src->pool.free_top, sizeof(int)},
             {dst->dir, src->dir, dn * sizeof(int)}, {dst->geom, src->geom, sizeof(Geom) * src->max_particles}};

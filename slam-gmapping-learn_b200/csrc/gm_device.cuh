@@ -9,6 +9,9 @@
 //            here (two would inside the 16-byte cells)
 //   dir    : int[N * dir_cap]        particle i, patch (px,py) at dir[i*dir_cap + px*npy + py], -1 = unallocated
 //   geom   : Geom[N]                 per-particle m_sizeX2/m_sizeY2 + directory dims (diverge after Map::resize)
+//   means  : double2[pool_cap * 1024] PointAccumulator::mean() = (1./n) * acc of the same cells (smmap.h:24), valid where n > 0:
+//            derived data, rewritten whenever a hit changes acc and n (at most one cell per beam and scan) and read by the
+//            scan matcher ~10^5 times as often -- one 16-byte load instead of cell -> 1/n lookup -> two conversions and products
 //   refcnt : int[pool_cap]           number of directory entries that reference a patch (autoptr::shares)
 //   occ    : unsigned[pool_cap * 32] occupancy bitmap: bit ly of word p*32 + lx == (10 * n > visits) of that cell, i.e. the cell
 //            is occupied at the default fullnessThreshold 0.1 (smmap.h:25).  Derived data, kept in step by every writer of
@@ -64,6 +67,7 @@ struct Counters {  // zeroed per stage, read back by the host
 struct Pool {
     int4* cells;       // [(cap+1)*1024] {acc.x, acc.y, n, 0}; patch `cap` is all zero
     int* visits;       // [(cap+1)*1024]
+    double2* means;    // [(cap+1)*1024] mean() where n > 0
     unsigned* occ;     // [(cap+1)*32] occupancy bitmap (see the layout note above)
     int* refcnt;       // [cap]
     int* free_list;    // [cap] stack of free patch ids, top at *free_top
@@ -108,6 +112,13 @@ __device__ __forceinline__ bool occ_gt(int n, int v, const DevParams& P) {
 __device__ __forceinline__ bool occ_lt(int n, int v, const DevParams& P) {
     if (!v) return -1.0 < P.fullness_threshold;
     return P.thr_is_tenth ? (10ll * n < (long long)v) : (occ_ratio(n, v) < P.fullness_threshold);
+}
+
+// PointAccumulator::mean() (smmap.h:24): 1./n * Point(acc.x, acc.y), IEEE double division and products, no contraction
+__device__ __forceinline__ double2 cell_mean(int acc_x_bits, int acc_y_bits, int n) {
+    if (n == 0) return make_double2(0., 0.);
+    const double inv = 1. / (double)n;
+    return make_double2((double)__int_as_float(acc_x_bits) * inv, (double)__int_as_float(acc_y_bits) * inv);
 }
 
 // the occupancy-bitmap predicate: n / visits > 0.1 decided in integers (implies visits > 0 as n >= 0)

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(512) k_dist_install(int first_slot, Geom* __re
     for (long long i = threadIdx.x; i < (long long)count * kPatchCells; i += blockDim.x) {
         const int id = s_ids[i >> 10];
         const int4 c = cells[i];
-        if (id >= 0) { pool.cells[(size_t)id * kPatchCells + (i & 1023)] = make_int4(c.x, c.y, c.z, 0); pool.visits[(size_t)id * kPatchCells + (i & 1023)] = c.w; }
+        if (id >= 0) { pool.cells[(size_t)id * kPatchCells + (i & 1023)] = make_int4(c.x, c.y, c.z, 0); pool.visits[(size_t)id * kPatchCells + (i & 1023)] = c.w; pool.means[(size_t)id * kPatchCells + (i & 1023)] = cell_mean(c.x, c.y, c.z); }
         // 512 threads, count * 1024 cells: every warp covers one whole patch row per trip
         const unsigned bits = __ballot_sync(0xffffffffu, occ_default(c.z, c.w));
         if (id >= 0 && (i & 31) == 0) pool.occ[(size_t)id * kPatch + ((i & 1023) >> kPatchMag)] = bits;

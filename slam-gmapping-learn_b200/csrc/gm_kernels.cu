@@ -89,6 +89,12 @@ __device__ __forceinline__ void cell_index2(double dx, double dy, double delta, 
     if (!(okx && oky)) { ix = cell_index_slow(dx, delta); iy = cell_index_slow(dy, delta); }
 }
 
+__device__ __forceinline__ double2 ldg_d2(const double2* p) {
+    double2 v;
+    asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
 // predicated load of a directory entry: no branch, no access when `pred` is false
 __device__ __forceinline__ int ldg_if(const int* p, bool pred, int dflt) {
     int v;
@@ -105,6 +111,7 @@ struct MatchCtx {
     const int* const* dirp_s;
     const int4* __restrict__ pool;
     const int* __restrict__ visits;
+    const double2* __restrict__ means;
     const unsigned* __restrict__ occ;
     const double* __restrict__ inv_n;
     Geom g;
@@ -202,16 +209,8 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
                 const bool two = mask != 0;
                 const int j = two ? __ffs(mask) - 1 : i;
                 mask &= mask - 1;  // no-op when mask is already 0
-                const int4 ca = __ldg(M.pool + cell_of(i));
-                const int4 cb = __ldg(M.pool + cell_of(j));
-                // mean() = (1./n) * acc, smmap.h:24; n > 0 here, and the table covers n < kInvTable
-                double ia = __ldg(M.inv_n + min(ca.z, kInvTable - 1)), ib = __ldg(M.inv_n + min(cb.z, kInvTable - 1));
-                if ((ca.z | cb.z) >= kInvTable) {
-                    if (ca.z >= kInvTable) ia = recip_slow(ca.z);
-                    if (cb.z >= kInvTable) ib = recip_slow(cb.z);
-                }
-                const double ax = phx - (double)__int_as_float(ca.x) * ia, ay = phy - (double)__int_as_float(ca.y) * ia;
-                const double bxx = phx - (double)__int_as_float(cb.x) * ib, byy = phy - (double)__int_as_float(cb.y) * ib;
+                const double2 ma = ldg_d2(M.means + cell_of(i)), mb = ldg_d2(M.means + cell_of(j));  // mean(), smmap.h:24
+                const double ax = phx - ma.x, ay = phy - ma.y, bxx = phx - mb.x, byy = phy - mb.y;
                 const double na = ax * ax + ay * ay, nb = bxx * bxx + byy * byy;
                 if (!found || na < bn) { bx = ax; by = ay; bn = na; found = true; }
                 if (two && nb < bn) { bx = bxx; by = byy; bn = nb; }
@@ -224,9 +223,8 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
                 long long fi; int fn = 0, fv = 0;
                 if (cell_addr(g, *M.dirp_s, x0 + xx + ifx, y0 + yy + ify, fi)) { fn = __ldg(M.pool + fi).z; fv = __ldg(M.visits + fi); }
                 if (!is_free<true>(fn, fv, P)) continue;
-                const int4 cell = __ldg(M.pool + cell_of(i));
-                const double inv = cell.z < kInvTable ? __ldg(M.inv_n + cell.z) : recip_slow(cell.z);
-                const double mx = phx - (double)__int_as_float(cell.x) * inv, my = phy - (double)__int_as_float(cell.y) * inv;
+                const double2 mean = ldg_d2(M.means + cell_of(i));
+                const double mx = phx - mean.x, my = phy - mean.y;
                 const double nn = mx * mx + my * my;
                 if (!found || nn < bn) { bx = mx; by = my; bn = nn; found = true; }
             }
@@ -388,7 +386,7 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
     const unsigned q = blockIdx.x, p = QUERY ? A.particle_idx[q] : q;
     const int t = threadIdx.x;
     MatchCtx M;
-    M.dirp_s = &S.dirp; M.pool = A.pool; M.visits = A.visits; M.occ = A.occ; M.inv_n = A.inv_n; M.g = A.geom[p];
+    M.dirp_s = &S.dirp; M.pool = A.pool; M.visits = A.visits; M.means = A.means; M.occ = A.occ; M.inv_n = A.inv_n; M.g = A.geom[p];
     M.zero_patch = A.zero_patch;
 
     if (t == 0) {
@@ -876,15 +874,42 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
             if (mode == 0 || nid < 0) continue;
             int4* dst = A.pool.cells + (size_t)nid * kPatchCells;
             int4* vdst = reinterpret_cast<int4*>(A.pool.visits + (size_t)nid * kPatchCells);
+            int4* mdst = reinterpret_cast<int4*>(A.pool.means + (size_t)nid * kPatchCells);
             if (mode == 1) {
                 for (int i = lane; i < kPatchCells; i += 32) dst[i] = make_int4(0, 0, 0, 0);
                 for (int i = lane; i < kPatchCells / 4; i += 32) vdst[i] = make_int4(0, 0, 0, 0);
+                // means are only defined (and only read) where n > 0: nothing to initialise
                 A.pool.occ[(size_t)nid * kPatch + lane] = 0u;
             } else {
+                // four independent 16-byte loads in flight per lane, then the stores (source and destination come from
+                // the same array: the compiler keeps a plain copy loop strictly load -> store -> load)
                 const int4* src = A.pool.cells + (size_t)id * kPatchCells;
-                for (int i = lane; i < kPatchCells; i += 32) dst[i] = __ldcg(src + i);
                 const int4* vsrc = reinterpret_cast<const int4*>(A.pool.visits + (size_t)id * kPatchCells);
-                for (int i = lane; i < kPatchCells / 4; i += 32) vdst[i] = __ldcg(vsrc + i);
+                bool hits = false;
+                for (int i0 = lane; i0 < kPatchCells; i0 += 128) {
+                    int4 c[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) c[k] = __ldcg(src + i0 + 32 * k);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { dst[i0 + 32 * k] = c[k]; hits = hits || c[k].z != 0; }
+                }
+                for (int i0 = lane; i0 < kPatchCells / 4; i0 += 128) {
+                    int4 c[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) c[k] = __ldcg(vsrc + i0 + 32 * k);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) vdst[i0 + 32 * k] = c[k];
+                }
+                if (__any_sync(0xffffffffu, hits)) {  // free-space patches (most of them) have no mean to copy
+                    const int4* msrc = reinterpret_cast<const int4*>(A.pool.means + (size_t)id * kPatchCells);
+                    for (int i0 = lane; i0 < kPatchCells; i0 += 128) {
+                        int4 c[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) c[k] = __ldcg(msrc + i0 + 32 * k);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) mdst[i0 + 32 * k] = c[k];
+                    }
+                }
                 A.pool.occ[(size_t)nid * kPatch + lane] = __ldcg(A.pool.occ + (size_t)id * kPatch + lane);
             }
             __syncwarp();
@@ -1046,6 +1071,7 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
             if (slot_of[q] == slot) { ax += rec[q].hx; ay += rec[q].hy; cnt++; }  // acc += (float)phit, smmap.h:51-52
         cell[0] = __float_as_int(ax); cell[1] = __float_as_int(ay);
         cell[2] = n0 + cnt; *visp = v0 + cnt;
+        A.pool.means[(size_t)id * kPatchCells + ((x & 31) << kPatchMag) + (y & 31)] = cell_mean(__float_as_int(ax), __float_as_int(ay), n0 + cnt);
         const bool was = occ_default(n0, v0), is = occ_default(n0 + cnt, v0 + cnt);
         if (was != is) {  // other cells of the row may flip at the same time: atomics on the bitmap word
             unsigned* w = A.pool.occ + (size_t)id * kPatch + (x & 31);
@@ -1192,6 +1218,10 @@ __global__ void __launch_bounds__(256) k_digest(DigestArgs A) {
             // the warp holds row i >> 5 of the patch: its occupancy bits must equal the bitmap word
             const unsigned bits = __ballot_sync(0xffffffffu, occ_default(c.z, c.w));
             if (lane == 0 && bits != A.occ[(size_t)id * kPatch + (i >> kPatchMag)]) bad++;
+            if (c.z > 0) {  // and the stored mean must be the one recomputed from acc and n, bit for bit
+                const double2 want = cell_mean(c.x, c.y, c.z), have = A.means[(size_t)id * kPatchCells + i];
+                if (__double_as_longlong(want.x) != __double_as_longlong(have.x) || __double_as_longlong(want.y) != __double_as_longlong(have.y)) bad++;
+            }
             if (!c.w && !c.z) continue;
             int wx = px * kPatch + (i >> 5) - g.sx2, wy = py * kPatch + (i & 31) - g.sy2;
             cells++; sn += (unsigned)c.z; sv += (unsigned)c.w;
@@ -1258,6 +1288,7 @@ __global__ void k_install_patches(int* dirp, Geom g, const int* __restrict__ coo
         const int4 c = staged[(size_t)k * kPatchCells + i];
         pool.cells[(size_t)id * kPatchCells + i] = make_int4(c.x, c.y, c.z, 0);
         pool.visits[(size_t)id * kPatchCells + i] = c.w;
+        pool.means[(size_t)id * kPatchCells + i] = cell_mean(c.x, c.y, c.z);
         const unsigned bits = __ballot_sync(0xffffffffu, occ_default(c.z, c.w));
         if ((i & 31) == 0) pool.occ[(size_t)id * kPatch + (i >> kPatchMag)] = bits;
     }

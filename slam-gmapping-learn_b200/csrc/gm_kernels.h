@@ -9,7 +9,7 @@ struct ScanMatchArgs {
     const double* ranges; const double* angles;
     double* poses;
     const Geom* geom; const int* dir; int dir_cap;
-    const int4* pool; const int* visits;
+    const int4* pool; const int* visits; const double2* means;
     const unsigned* occ;  // occupancy bitmap of the pool (gm_device.cuh)
     const double* inv_n;
     double minimum_score;
@@ -51,7 +51,7 @@ struct RemapArgs {
 };
 struct SweepArgs { Pool pool; int* refcnt_new; };
 struct DigestArgs {
-    const Geom* geom; const int* dir; int dir_cap; const int4* pool; const int* visits; const unsigned* occ;
+    const Geom* geom; const int* dir; int dir_cap; const int4* pool; const int* visits; const double2* means; const unsigned* occ;
     unsigned first; unsigned long long* out;  // 7 words per particle: the six of gm_digest + mismatching occupancy-bitmap rows
 };
 

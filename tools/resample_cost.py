@@ -18,6 +18,8 @@ poses = log.odom[10][None, :] + rng.normal(0, [0.01, 0.01, 0.005], size=(n, 3))
 ctx.register(log.ranges[10], poses[idx], idx)
 st = ctx.stats()
 print({"distinct_parents": int(len(set(idx.tolist()))), "ms_remap": st["ms_remap"], "ms_register_after_resample": st["ms_register"],
-       "ms_register_steady": base["ms_register"], "cow_copies": st["cow_copies"], "pool_in_use_before": base["pool_in_use"], "pool_in_use_after": st["pool_in_use"]})
+       "ms_register_steady": base["ms_register"], "cow_copies": st["cow_copies"],
+       "phase_kcycles_per_cta_steady": [round(c / n / 1e3, 1) for c in base["register_phase_cycles"]],
+       "phase_kcycles_per_cta_after": [round(c / n / 1e3, 1) for c in st["register_phase_cycles"]], "pool_in_use_before": base["pool_in_use"], "pool_in_use_after": st["pool_in_use"]})
 ctx.register(log.ranges[11], poses[idx] + 0.01)
 print({"ms_register_next": ctx.stats()["ms_register"], "cow_copies_next": ctx.stats()["cow_copies"]})
