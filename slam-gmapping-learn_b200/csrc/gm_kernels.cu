@@ -135,10 +135,12 @@ template <bool DEF> __device__ __forceinline__ bool is_free(int n, int v, const 
 // K1: kernelSize 1 and fullnessThreshold 0.1 (the defaults) -> specialised, branch-light window code
 template <bool K1>
 // (fqx, fqy): the beam-independent free-cell index offset when it exists (see derive_params), else fqx == INT_MIN
-__device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M, double lpx, double lpy, double r, double c, double s,
-                                           double free_off, int fqx, int fqy, double& bmx, double& bmy) {
+// (phx, phy): the beam end point lp + r * (c, s).  r, c and s themselves are only needed for the free point when its
+// cell offset is not a constant (fqx == INT_MIN): they are re-read then (`ranges`, and the plain trig table at tab_s).
+__device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M, double lpx, double lpy, double phx, double phy, unsigned b,
+                                           unsigned tab_s, const double* __restrict__ ranges, double free_off, int fqx, int fqy,
+                                           double& bmx, double& bmy) {
     const Geom& g = M.g;
-    const double phx = lpx + r * c, phy = lpy + r * s;
     int ihx, ihy;
     cell_index2(phx - P.cx, phy - P.cy, P.delta, P.inv_delta, ihx, ihy);
     ihx += g.sx2; ihy += g.sy2;
@@ -190,6 +192,9 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
         int ifx, ify;
         if (fqx != INT_MIN) { ifx = fqx + g.sx2; ify = fqy + g.sy2; }
         else {
+            const double r = __ldg(ranges + b);
+            double c, s;
+            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c), "=d"(s) : "r"(tab_s + b * 16u));
             const double pfx = (lpx + (r - free_off) * c) - phx, pfy = (lpy + (r - free_off) * s) - phy;
             ifx = cell_index(pfx - P.cx, P.delta, P.inv_delta) + g.sx2;
             ify = cell_index(pfy - P.cy, P.delta, P.inv_delta) + g.sy2;
@@ -243,7 +248,10 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
             if (cell_addr(g, *M.dirp_s, x0 + xx, y0 + yy, ci)) { cell = __ldg(M.pool + ci); cell.w = __ldg(M.visits + ci); }
             if (!is_occ<false>(cell.z, cell.w, P)) continue;
             if (!have_free) {
-                const double pfx = (lpx + (r - free_off) * c) - phx, pfy = (lpy + (r - free_off) * s) - phy;
+                const double r = __ldg(ranges + b);
+            double c, s;
+            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c), "=d"(s) : "r"(tab_s + b * 16u));
+            const double pfx = (lpx + (r - free_off) * c) - phx, pfy = (lpy + (r - free_off) * s) - phy;
                 ifx = cell_index(pfx - P.cx, P.delta, P.inv_delta) + g.sx2;
                 ify = cell_index(pfy - P.cy, P.delta, P.inv_delta) + g.sy2;
                 have_free = true;
@@ -319,7 +327,7 @@ struct SmShared {
     double cur[3], init[3], key[3], currentScore, bestScore, adelta, ldelta;
     double prev[3];        // the pose the last winning move started from
     unsigned refinement, evals, evaluated, valid_lik;
-    int phase, key_ok[3], last_move;
+    int phase, key_ok[3], key_kind[3], fill_kind[3], last_move;  // table kinds: 0 (cos, sin), 1 end-point offsets r * (cos, sin)
 };
 
 // candidate pose m of a hill-climb round around `cur` (scanmatcher.cpp:441-494: Front, Back, Left, Right, TurnLeft, TurnRight)
@@ -336,11 +344,11 @@ __device__ __forceinline__ void candidate(const double* cur, int m, double ldelt
 }
 
 // thread 0: make logical table `which` hold theta (recompute only when its key differs)
-__device__ __forceinline__ void want_table(SmShared& S, int which, double theta, int& nfill) {
+__device__ __forceinline__ void want_table(SmShared& S, int which, double theta, int kind, int& nfill) {
     const int phys = S.tab_of[which];
-    if (!S.key_ok[phys] || S.key[phys] != theta) {
-        S.key[phys] = theta; S.key_ok[phys] = 1;
-        S.fill[nfill] = phys; S.fill_theta[nfill] = theta; nfill++;
+    if (!S.key_ok[phys] || S.key[phys] != theta || S.key_kind[phys] != kind) {
+        S.key[phys] = theta; S.key_ok[phys] = 1; S.key_kind[phys] = kind;
+        S.fill[nfill] = phys; S.fill_theta[nfill] = theta; S.fill_kind[nfill] = kind; nfill++;
     }
 }
 
@@ -349,7 +357,7 @@ __device__ __forceinline__ void want_table(SmShared& S, int which, double theta,
 // gain included) is the previous currentScore, strictly below the present one, so it cannot win the `localScore >
 // currentScore` test of scanmatcher.cpp:510.  When that candidate is bit for bit the previous pose ((x + d) - d == x almost
 // always) it is counted but not evaluated.
-__device__ __noinline__ void plan_round(const DevParams& P, SmShared& S) {
+__device__ __noinline__ void plan_round(const DevParams& P, SmShared& S, int kind) {
     const bool halved = S.bestScore >= S.currentScore;
     if (halved) { S.refinement++; S.adelta *= .5; S.ldelta *= .5; }
     S.bestScore = S.currentScore;
@@ -366,7 +374,7 @@ __device__ __noinline__ void plan_round(const DevParams& P, SmShared& S) {
         candidate(S.cur, m, S.ldelta, S.adelta, cm);
         laser_pose(P, cm[0], cm[1], cm[2], lx, ly, lt);
         S.lx[m] = lx; S.ly[m] = ly;
-        if (m >= 4) want_table(S, m - 3, lt, nfill);
+        if (m >= 4) want_table(S, m - 3, lt, kind, nfill);
         S.cand[nc++] = m;
     }
     for (int j = nfill; j < 3; j++) S.fill[j] = -1;
@@ -384,6 +392,9 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
     const DevParams& P = A.P;
     double2* const tabs = reinterpret_cast<double2*>(smem_raw);
     const unsigned q = blockIdx.x, p = QUERY ? A.particle_idx[q] : q;
+    // score() with the default window and a beam-independent free-cell offset: the tables hold the end-point offsets
+    // r * (cos, sin), NaN for the beams score() skips, and the beam loop reads nothing else
+    const int premul = (K1 && A.P.free_q[0][0] != INT_MIN) ? 1 : 0;
     const int t = threadIdx.x;
     MatchCtx M;
     M.dirp_s = &S.dirp; M.pool = A.pool; M.visits = A.visits; M.means = A.means; M.occ = A.occ; M.inv_n = A.inv_n; M.g = A.geom[p];
@@ -400,7 +411,7 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
         laser_pose(P, S.cur[0], S.cur[1], S.cur[2], lx, ly, lt);
         S.lx[0] = lx; S.ly[0] = ly;
         int nfill = 0;
-        want_table(S, 0, lt, nfill);
+        want_table(S, 0, lt, A.query == 1 ? 0 : premul, nfill);
         S.fill[1] = S.fill[2] = -1;
         S.ncand = 1; S.mode = A.query == 1 ? 1 : 0; S.phase = (A.query == 0 || A.query == 1) ? 3 : 0;
     }
@@ -413,11 +424,17 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
             const int phys = S.fill[j];
             if (phys < 0) break;
             const double theta = S.fill_theta[j];
+            const int kind = S.fill_kind[j];
             double2* tab = tabs + (size_t)phys * P.nbeams;
             for (unsigned b = P.beam_skip + t; b < P.nbeams; b += kSmThreads) {
                 double sn, cs;
                 sincos(theta + __ldg(A.angles + b), &sn, &cs);
-                tab[b] = make_double2(cs, sn);
+                if (kind) {
+                    const double r = __ldg(A.ranges + b);
+                    const bool skip = !beam_selected(P, b) || r > P.usable_range || r == 0.0;  // scanmatcher.h:189-196
+                    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+                    tab[b] = skip ? make_double2(nan, nan) : make_double2(r * cs, r * sn);
+                } else tab[b] = make_double2(cs, sn);
             }
             filled = true;
         }
@@ -436,15 +453,23 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
             const double free_off = mode ? P.free_off_lik : P.free_off_score;
             const int fqx = P.free_q[mode][0], fqy = P.free_q[mode][1];
             const double cexp = P.cexp, clik = P.clik, noHit = P.no_hit;
+            const bool offsets = premul && mode == 0;  // the table in use holds end-point offsets
             for (unsigned b = P.beam_skip + grp; b < P.nbeams; b += ngroups) {
-                const double r = __ldg(A.ranges + b);
-                // score() also skips r == 0 (scanmatcher.h:195); likelihoodAndScore() does not (:303-308)
-                if (!beam_selected(P, b) || r > P.usable_range || (mode == 0 && r == 0.0)) continue;
                 double2 cs;
                 asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(cs.x), "=d"(cs.y) : "r"(tab_s + b * 16u));
+                double phx, phy;
+                if (offsets) {
+                    if (cs.x != cs.x) continue;  // a beam score() skips
+                    phx = mlx + cs.x; phy = mly + cs.y;
+                } else {
+                    const double r = __ldg(A.ranges + b);
+                    // score() also skips r == 0 (scanmatcher.h:195); likelihoodAndScore() does not (:303-308)
+                    if (!beam_selected(P, b) || r > P.usable_range || (mode == 0 && r == 0.0)) continue;
+                    phx = mlx + r * cs.x; phy = mly + r * cs.y;
+                }
                 double mx, my;
                 valid++;
-                const bool found = beam_match<K1>(P, M, mlx, mly, r, cs.x, cs.y, free_off, fqx, fqy, mx, my);
+                const bool found = beam_match<K1>(P, M, mlx, mly, phx, phy, b, tab_s, A.ranges, free_off, fqx, fqy, mx, my);
                 if (found) { acc_s += exp_neg((mx * cexp) * mx + (my * cexp) * my, A.inv_n + kInvTable); cnt++; }  // ((-1/sigma)*mu)*mu, point.h:34-49
                 if (mode) { const double f = clik * (mx * mx + my * my); acc_l += found ? f : noHit; }
             }
@@ -496,12 +521,12 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
                     S.tab_of[0] = S.tab_of[bm - 3]; S.tab_of[bm - 3] = o;
                 }
             }
-            if (S.currentScore > S.bestScore || S.refinement < P.opt_iters) { plan_round(P, S); continue; }
+            if (S.currentScore > S.bestScore || S.refinement < P.opt_iters) { plan_round(P, S, premul); continue; }
         } else if (S.phase == 0) {
             double v = 0.;
             for (int w = 0; w < kSmThreads / 32; w++) v += S.red[w];
             S.currentScore = v;
-            plan_round(P, S);
+            plan_round(P, S, premul);
             continue;
         } else {
             // phase 2: likelihoodAndScore of the accepted pose; phase 3: standalone query
@@ -532,7 +557,7 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
         laser_pose(P, S.cur[0], S.cur[1], S.cur[2], lx, ly, lt);
         S.lx[0] = lx; S.ly[0] = ly;
         int nfill = 0;
-        want_table(S, 0, lt, nfill);
+        want_table(S, 0, lt, 0, nfill);
         for (int j = nfill; j < 3; j++) S.fill[j] = -1;
         S.ncand = 1; S.mode = 1; S.phase = 2;
     }
