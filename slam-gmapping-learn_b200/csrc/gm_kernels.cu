@@ -109,6 +109,7 @@ struct MatchCtx {
     // the particle's directory, read through a shared-memory slot at every use: kept in registers the compiler spends ten
     // instructions per lookup rebuilding the 64-bit address from the kernel parameters instead
     const int* const* dirp_s;
+    const int4* bbox_s;  // shared: cell bounding box of the allocated patches {x_lo, y_lo, x_hi, y_hi} (inclusive; empty: lo > hi)
     const int4* __restrict__ pool;
     const int* __restrict__ visits;
     const double2* __restrict__ means;
@@ -201,7 +202,9 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
         }
         const int fx0 = x0 + ifx, fy0 = y0 + ify, fx1 = x1 + ifx, fy1 = y1 + ify;
         bool fcheck = true;  // false: every free cell of this window is unknown, i.e. passes
-        if (fx1 < 0 || fy1 < 0 || (fx0 >> kPatchMag) >= g.npx || (fy0 >> kPatchMag) >= g.npy) fcheck = false;
+        const int4 bb = *M.bbox_s;
+        if (fx1 < bb.x || fy1 < bb.y || fx0 > bb.z || fy0 > bb.w) fcheck = false;  // clear of every allocated patch (the usual case)
+        else if (fx1 < 0 || fy1 < 0 || (fx0 >> kPatchMag) >= g.npx || (fy0 >> kPatchMag) >= g.npy) fcheck = false;
         else if (fx0 >= 0 && fy0 >= 0 && (fx0 >> kPatchMag) == (fx1 >> kPatchMag) && (fy0 >> kPatchMag) == (fy1 >> kPatchMag) &&
                  dir_at(M, fx0 >> kPatchMag, fy0 >> kPatchMag) < 0) fcheck = false;
         // occupied cells in ascending bit order == the reference's xx-outer / yy-inner scan order
@@ -314,6 +317,8 @@ struct SmShared {
     int fill[3];           // physical trig tables to recompute before evaluating (-1: none)
     int tab_of[3];         // physical table of: the current theta, theta + adelta, theta - adelta
     const int* dirp;       // directory of this CTA's particle
+    int4 bbox;             // see MatchCtx::bbox_s
+    int bb_lo_x, bb_lo_y, bb_hi_x, bb_hi_y;  // its reduction: patch coordinates
     int ncand;             // poses to evaluate: 1, or the 6 moves of a round, or 5 of them (see plan_round)
     int cand[6];           // which moves
     int skip;              // the move left out (-1: none)
@@ -397,7 +402,7 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
     const int premul = (K1 && A.P.free_q[0][0] != INT_MIN) ? 1 : 0;
     const int t = threadIdx.x;
     MatchCtx M;
-    M.dirp_s = &S.dirp; M.pool = A.pool; M.visits = A.visits; M.means = A.means; M.occ = A.occ; M.inv_n = A.inv_n; M.g = A.geom[p];
+    M.dirp_s = &S.dirp; M.bbox_s = &S.bbox; M.pool = A.pool; M.visits = A.visits; M.means = A.means; M.occ = A.occ; M.inv_n = A.inv_n; M.g = A.geom[p];
     M.zero_patch = A.zero_patch;
 
     if (t == 0) {
@@ -415,6 +420,20 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
         S.fill[1] = S.fill[2] = -1;
         S.ncand = 1; S.mode = A.query == 1 ? 1 : 0; S.phase = (A.query == 0 || A.query == 1) ? 3 : 0;
     }
+    if (K1) {
+        // bounding box of the allocated patches: the free-cell windows (half a map away, see beam_match) normally miss it
+        if (t == 0) { S.bb_lo_x = INT_MAX; S.bb_lo_y = INT_MAX; S.bb_hi_x = -1; S.bb_hi_y = -1; }
+        __syncthreads();
+        const int* dirp = A.dir + (size_t)p * A.dir_cap;
+        int lox = INT_MAX, loy = INT_MAX, hix = -1, hiy = -1;
+        for (int e = t; e < M.g.npx * M.g.npy; e += kSmThreads)
+            if (__ldg(dirp + e) >= 0) { const int px = e / M.g.npy, py = e - px * M.g.npy; lox = min(lox, px); hix = max(hix, px); loy = min(loy, py); hiy = max(hiy, py); }
+        lox = __reduce_min_sync(0xffffffffu, lox); loy = __reduce_min_sync(0xffffffffu, loy);
+        hix = __reduce_max_sync(0xffffffffu, hix); hiy = __reduce_max_sync(0xffffffffu, hiy);
+        if ((t & 31) == 0 && hix >= 0) { atomicMin(&S.bb_lo_x, lox); atomicMin(&S.bb_lo_y, loy); atomicMax(&S.bb_hi_x, hix); atomicMax(&S.bb_hi_y, hiy); }
+        __syncthreads();
+        if (t == 0) S.bbox = S.bb_hi_x < 0 ? make_int4(1, 1, 0, 0) : make_int4(S.bb_lo_x << kPatchMag, S.bb_lo_y << kPatchMag, (S.bb_hi_x << kPatchMag) + kPatch - 1, (S.bb_hi_y << kPatchMag) + kPatch - 1);
+    } else if (t == 0) S.bbox = make_int4(INT_MIN, INT_MIN, INT_MAX, INT_MAX);
     for (;;) {
         __syncthreads();  // the plan is visible
         if (S.done) break;
