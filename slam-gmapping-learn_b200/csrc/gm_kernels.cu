@@ -749,7 +749,7 @@ __device__ __forceinline__ int line_minor(const Line& L, int j) {
 // The patches (as px, py pairs) under chunk `chunk` of the line p0 -> p1 (p1 excluded), without walking it: a chunk of
 // kRayChunk <= 32 cells crosses at most one patch boundary along the major axis, and between two cells the minor
 // coordinate moves monotonically by at most one per step, so each of the (at most two) major-axis segments lies in the
-// patch rows of its first and last cell.  Returns the number of pairs written (<= 4, duplicates possible).
+// patch rows of its first and last cell.  Returns the number of pairs written (0 or 4, with duplicates).
 __device__ __forceinline__ int item_patches(int p0x, int p0y, int p1x, int p1y, int chunk, int (&px)[4], int (&py)[4]) {
     const Line L = make_line(p0x, p0y, p1x, p1y);
     const int m = L.n - 1, jlo = L.from_end ? 1 : 0;
@@ -757,18 +757,20 @@ __device__ __forceinline__ int item_patches(int p0x, int p0y, int p1x, int p1y, 
     if (j0 > j1) return 0;
     const int a0 = L.a_lo + j0, a1 = L.a_lo + j1;
     const int aB = ((a0 >> kPatchMag) + 1) << kPatchMag;  // first major coordinate of the next patch
-    int n = 0;
-    auto put = [&](int a, int b) {
-        px[n] = (L.steep ? b : a) >> kPatchMag; py[n] = (L.steep ? a : b) >> kPatchMag; n++;
-    };
+    // four fixed slots (a slot that is not needed repeats an earlier one): indexing the arrays with a running count would
+    // put them in local memory
     const int e1 = min(a1, aB - 1);
-    put(a0, line_minor(L, j0));
-    if (e1 != a0) put(e1, line_minor(L, e1 - L.a_lo));
-    if (aB <= a1) {
-        put(aB, line_minor(L, aB - L.a_lo));
-        if (a1 != aB) put(a1, line_minor(L, j1));
-    }
-    return n;
+    const bool second = aB <= a1;
+    const int b0 = line_minor(L, j0);
+    const int b1 = e1 != a0 ? line_minor(L, e1 - L.a_lo) : b0;
+    const int a2 = second ? aB : a0, a3 = second ? a1 : a0;
+    const int b2 = second ? line_minor(L, aB - L.a_lo) : b0;
+    const int b3 = second ? (a1 != aB ? line_minor(L, j1) : b2) : b0;
+    px[0] = (L.steep ? b0 : a0) >> kPatchMag; py[0] = (L.steep ? a0 : b0) >> kPatchMag;
+    px[1] = (L.steep ? b1 : e1) >> kPatchMag; py[1] = (L.steep ? e1 : b1) >> kPatchMag;
+    px[2] = (L.steep ? b2 : a2) >> kPatchMag; py[2] = (L.steep ? a2 : b2) >> kPatchMag;
+    px[3] = (L.steep ? b3 : a3) >> kPatchMag; py[3] = (L.steep ? a3 : b3) >> kPatchMag;
+    return 4;
 }
 
 constexpr int kRegThreads = 1024;
