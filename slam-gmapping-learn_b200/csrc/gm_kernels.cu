@@ -156,38 +156,54 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
         // shifted to the window's first column; no cell is read unless it is occupied.
         const int pxa = x0 >> kPatchMag, pya = y0 >> kPatchMag, pxb = x1 >> kPatchMag, pyb = y1 >> kPatchMag;
         const bool twoy = pyb != pya, twox = pxb != pxa;
-        // four directory entries (-1 outside the directory) with predicated loads: lanes whose window crosses a patch edge
-        // are few, but nearly every warp has one, and a branch would run its body for the whole warp
-        const bool xa_in = (unsigned)pxa < (unsigned)g.npx, xb_in = (unsigned)pxb < (unsigned)g.npx;
-        const bool ya_in = (unsigned)pya < (unsigned)g.npy, yb_in = (unsigned)pyb < (unsigned)g.npy;
+        const bool xa_in = (unsigned)pxa < (unsigned)g.npx, ya_in = (unsigned)pya < (unsigned)g.npy;
         const int* da = *M.dirp_s + (pxa * g.npy + pya);
-        const int* dc = da + (twox ? g.npy : 0);
-        const int ida = ldg_if(da, xa_in && ya_in, -1);
-        const int idb = ldg_if(da + 1, twoy && xa_in && yb_in, twoy ? -1 : ida);
-        const int idc = ldg_if(dc, twox && xb_in && ya_in, twox ? -1 : ida);
-        const int idd = ldg_if(dc + 1, twox && twoy && xb_in && yb_in, twox ? (twoy ? -1 : idc) : idb);
-        if ((ida & idb & idc & idd) < 0) return false;  // every patch unknown: nothing can match
-        // unknown patches read the all-zero patch
-        const unsigned zp = (unsigned)M.zero_patch;  // = pool capacity > every patch id; -1 as unsigned is larger still
-        const unsigned ea = min((unsigned)ida, zp), eb = min((unsigned)idb, zp), ec = min((unsigned)idc, zp), ed = min((unsigned)idd, zp);
-        const int nxa = ((pxa + 1) << kPatchMag) - x0;  // window rows inside patches a / b
         const unsigned ysh = (unsigned)(y0 & 31);
-        unsigned mask = 0;
+        unsigned mask, ea, eb, ec, ed, base = 0;
+        int nxa, nya;
+        // a warp works on the six candidate poses of five or six neighbouring beams: its windows lie within a few cells of
+        // each other, and most of the time none of them crosses a patch edge
+        const bool fast = __all_sync(__activemask(), !twox && !twoy);
+        if (fast) {
+            const int ida = ldg_if(da, xa_in && ya_in, -1);
+            if (ida < 0) return false;
+            const unsigned* w = M.occ + (((unsigned)ida << kPatchMag) + (unsigned)(x0 & 31));  // rows x0 .. x0 + 2: consecutive words
+            const unsigned w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+            mask = ((w0 >> ysh) & 7u) | (((w1 >> ysh) & 7u) << 8) | (((w2 >> ysh) & 7u) << 16);
+            base = ((unsigned)ida << 10) + ((unsigned)(x0 & 31) << kPatchMag) + ysh;
+            ea = eb = ec = ed = (unsigned)ida; nxa = nya = kPatch;
+        } else {
+            // four directory entries (-1 outside the directory) with predicated loads: a branch would run its body for the
+            // whole warp on behalf of the one lane that needs it
+            const bool xb_in = (unsigned)pxb < (unsigned)g.npx, yb_in = (unsigned)pyb < (unsigned)g.npy;
+            const int* dc = da + (twox ? g.npy : 0);
+            const int ida = ldg_if(da, xa_in && ya_in, -1);
+            const int idb = ldg_if(da + 1, twoy && xa_in && yb_in, twoy ? -1 : ida);
+            const int idc = ldg_if(dc, twox && xb_in && ya_in, twox ? -1 : ida);
+            const int idd = ldg_if(dc + 1, twox && twoy && xb_in && yb_in, twox ? (twoy ? -1 : idc) : idb);
+            if ((ida & idb & idc & idd) < 0) return false;  // every patch unknown: nothing can match
+            // unknown patches read the all-zero patch
+            const unsigned zp = (unsigned)M.zero_patch;  // = pool capacity > every patch id; -1 as unsigned is larger still
+            ea = min((unsigned)ida, zp); eb = min((unsigned)idb, zp); ec = min((unsigned)idc, zp); ed = min((unsigned)idd, zp);
+            nxa = ((pxa + 1) << kPatchMag) - x0;  // window rows inside patches a / b
+            nya = ((pya + 1) << kPatchMag) - y0;
+            mask = 0;
 #pragma unroll
-        for (int xx = 0; xx < 3; xx++) {
-            const unsigned row = (unsigned)((x0 + xx) & 31);
-            const unsigned lo = __ldg(M.occ + (((xx < nxa ? ea : ec) << kPatchMag) + row));
-            const unsigned hi = twoy ? __ldg(M.occ + (((xx < nxa ? eb : ed) << kPatchMag) + row)) : 0u;
-            mask |= (__funnelshift_r(lo, hi, ysh) & 7u) << (8 * xx);  // bit 8 * xx + yy: ascending bits == scan order
+            for (int xx = 0; xx < 3; xx++) {
+                const unsigned row = (unsigned)((x0 + xx) & 31);
+                const unsigned lo = __ldg(M.occ + (((xx < nxa ? ea : ec) << kPatchMag) + row));
+                const unsigned hi = twoy ? __ldg(M.occ + (((xx < nxa ? eb : ed) << kPatchMag) + row)) : 0u;
+                mask |= (__funnelshift_r(lo, hi, ysh) & 7u) << (8 * xx);  // bit 8 * xx + yy: ascending bits == scan order
+            }
         }
         if (!mask) return false;
         // cell index (patch * 1024 + cell) of the window cell at mask bit i = 8 * xx + yy
-        const int nya = ((pya + 1) << kPatchMag) - y0;
         auto cell_of = [&](int i) -> unsigned {
             const int xx = i >> 3, yy = i & 7;
             const unsigned e = xx < nxa ? (yy < nya ? ea : eb) : (yy < nya ? ec : ed);
             return (e << 10) + ((unsigned)((x0 + xx) & 31) << kPatchMag) + (unsigned)((y0 + yy) & 31);
         };
+        auto cell_of_fast = [&](int i) -> unsigned { return base + (((unsigned)i & 0x18u) << 2) + ((unsigned)i & 7u); };
         // free window (the reference's `ipfree` quirk: world2map applied to the difference pfree - phit).  |pfree - phit|
         // <= free_off, so for score() the index is the same for every beam and comes precomputed in (fqx, fqy)
         int ifx, ify;
@@ -209,20 +225,23 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
                  dir_at(M, fx0 >> kPatchMag, fy0 >> kPatchMag) < 0) fcheck = false;
         // occupied cells in ascending bit order == the reference's xx-outer / yy-inner scan order
         if (!fcheck) {
-            // two cells per trip: their load -> reciprocal -> distance chains are independent and overlap; the comparisons
-            // still run in scan order (i before j), so ties resolve as in the reference
-            while (mask) {
-                const int i = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const bool two = mask != 0;
-                const int j = two ? __ffs(mask) - 1 : i;
-                mask &= mask - 1;  // no-op when mask is already 0
-                const double2 ma = ldg_d2(M.means + cell_of(i)), mb = ldg_d2(M.means + cell_of(j));  // mean(), smmap.h:24
-                const double ax = phx - ma.x, ay = phy - ma.y, bxx = phx - mb.x, byy = phy - mb.y;
-                const double na = ax * ax + ay * ay, nb = bxx * bxx + byy * byy;
-                if (!found || na < bn) { bx = ax; by = ay; bn = na; found = true; }
-                if (two && nb < bn) { bx = bxx; by = byy; bn = nb; }
-            }
+            // two cells per trip: their load -> distance chains are independent and overlap; the comparisons still run in
+            // scan order (i before j), so ties resolve as in the reference
+            auto pair_loop = [&](auto cell) {
+                while (mask) {
+                    const int i = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const bool two = mask != 0;
+                    const int j = two ? __ffs(mask) - 1 : i;
+                    mask &= mask - 1;  // no-op when mask is already 0
+                    const double2 ma = ldg_d2(M.means + cell(i)), mb = ldg_d2(M.means + cell(j));  // mean(), smmap.h:24
+                    const double ax = phx - ma.x, ay = phy - ma.y, bxx = phx - mb.x, byy = phy - mb.y;
+                    const double na = ax * ax + ay * ay, nb = bxx * bxx + byy * byy;
+                    if (!found || na < bn) { bx = ax; by = ay; bn = na; found = true; }
+                    if (two && nb < bn) { bx = bxx; by = byy; bn = nb; }
+                }
+            };
+            if (fast) pair_loop(cell_of_fast); else pair_loop(cell_of);
         } else {
             while (mask) {
                 const int i = __ffs(mask) - 1;
