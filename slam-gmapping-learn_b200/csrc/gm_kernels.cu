@@ -816,7 +816,7 @@ __device__ __forceinline__ RegSmem carve(unsigned char* raw, int bitmap_words, i
     return m;
 }
 
-__global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
+__global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevParams& P = A.P;
     const unsigned p = blockIdx.x;
@@ -828,7 +828,7 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
     BeamRec* rec = M.rec;
     __shared__ unsigned long long s_free, s_hit, s_cow, s_alloc;
     __shared__ int s_part[kRegThreads / 32];
-    __shared__ int s_nactive;
+    __shared__ int s_nactive, s_nwork;
     __shared__ int s_tile_id[kMaxTiles];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 
@@ -924,19 +924,34 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
     const int nactive = s_nactive;
     PHASE(2);
 
-    // ---- 2. copy-on-write: a warp per active patch
-    for (int wi = warp; wi < nwords; wi += nw) {
-        unsigned bits = active[wi];
-        while (bits) {
-            int bit = __ffs(bits) - 1; bits &= bits - 1;
-            int e = (wi << 5) + bit;
-            int id = dirp[e], nid = id, mode = 0;  // 0 keep, 1 zero-fill new, 2 copy
-            if (lane == 0) {
-                if (id < 0) { nid = pool_alloc(A.pool, A.counters); mode = 1; }
-                else if (__ldcg(A.pool.refcnt + id) > 1) { nid = pool_alloc(A.pool, A.counters); mode = 2; }
-            }
-            nid = __shfl_sync(0xffffffffu, nid, 0); mode = __shfl_sync(0xffffffffu, mode, 0);
-            if (mode == 0 || nid < 0) continue;
+    // directory entry of the rank-th active patch, from the prefix sums
+    auto entry_of_rank = [&](int rank) -> int {
+        int lo = 0, hi = nwords - 1;  // last word whose prefix <= rank and that holds the rank-th bit
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((int)M.prefix[mid] <= rank) lo = mid; else hi = mid - 1; }
+        return (lo << 5) + (int)__fns(active[lo], 0, rank - (int)M.prefix[lo] + 1);
+    };
+
+    // ---- 2. copy-on-write.  (a) a thread per active patch reads its directory entry and reference count and lists the
+    // entries that need a patch of their own (the tile area is free until phase 3); (b) a warp per listed entry.
+    int* work = reinterpret_cast<int*>(M.tiles);
+    const int work_cap = max(A.tile_cap * kTileWords, A.sort_n * (kHitBytes / 4));
+    for (int r0 = 0; r0 < nactive; r0 += work_cap) {
+        if (threadIdx.x == 0) s_nwork = 0;
+        __syncthreads();
+        for (int r = r0 + threadIdx.x; r < min(nactive, r0 + work_cap); r += blockDim.x) {
+            const int e = entry_of_rank(r);
+            const int id = dirp[e];
+            if (id < 0 || __ldcg(A.pool.refcnt + id) > 1) work[atomicAdd(&s_nwork, 1)] = e;
+        }
+        __syncthreads();
+        const int nwork = s_nwork;
+        for (int k = warp; k < nwork; k += nw) {
+            const int e = work[k];
+            const int id = dirp[e], mode = id < 0 ? 1 : 2;  // 1 zero-fill a new patch, 2 copy
+            int nid = -1;
+            if (lane == 0) nid = pool_alloc(A.pool, A.counters);
+            nid = __shfl_sync(0xffffffffu, nid, 0);
+            if (nid < 0) continue;
             int4* dst = A.pool.cells + (size_t)nid * kPatchCells;
             int4* vdst = reinterpret_cast<int4*>(A.pool.visits + (size_t)nid * kPatchCells);
             int4* mdst = reinterpret_cast<int4*>(A.pool.means + (size_t)nid * kPatchCells);
@@ -990,6 +1005,7 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
                 } else atomicAdd(&s_alloc, 1ull);
             }
         }
+        __syncthreads();
     }
     __threadfence();
     __syncthreads();
@@ -1003,10 +1019,7 @@ __global__ void __launch_bounds__(kRegThreads) k_register(RegisterArgs A) {
         const int ntile = min(A.tile_cap, nactive - first);
         for (int i = threadIdx.x; i < ntile * kTileWords; i += blockDim.x) M.tiles[i] = 0u;
         if ((int)threadIdx.x < ntile) {  // patch of tile t: the directory entry of rank first + t, found from the prefix sums
-            const int rank = first + threadIdx.x;
-            int lo = 0, hi = nwords - 1;  // last word whose prefix <= rank and that holds the rank-th bit
-            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((int)M.prefix[mid] <= rank) lo = mid; else hi = mid - 1; }
-            s_tile_id[threadIdx.x] = dirp[(lo << 5) + (int)__fns(active[lo], 0, rank - (int)M.prefix[lo] + 1)];
+            s_tile_id[threadIdx.x] = dirp[entry_of_rank(first + threadIdx.x)];
         }
         __syncthreads();
         // the counting below keeps to shared memory: meanwhile pull the visit planes of this pass (4 KB per patch) into
