@@ -40,8 +40,9 @@ if ROOT not in sys.path:
 METRIC = "scans/sec at 4096 particles x 1081 beams"
 BYTES_PER_BEAM_EVAL = 144  # (2k+1)^2 x 16 B at kernelSize 1
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_scanmatch launch over 4096 particles, from the ncu --set full capture
-# summarised in profiles/r01_summary.md section 4 (0.90 GB + 0.43 GB); scaled with the particles per GPU
-KERNEL_TRAFFIC_BYTES = 1.33e9
+# summarised in profiles/r01_summary.md section 4 (0.51 GB + 0.40 GB); scaled with the particles per GPU
+KERNEL_TRAFFIC_BYTES = 0.91e9
+PATCH_BYTES = 16384 + 4096 + 16384 + 128  # cells + visit counters + means + occupancy bitmap of one 32 x 32 patch
 PARAMS = dict(maxrange=30.0, maxUrange=29.0, sigma=0.05, kernelSize=1, lstep=0.05, astep=0.05, iterations=5, lsigma=0.075,
               ogain=3.0, lskip=0, srr=0.01, srt=0.01, str=0.01, stt=0.01, resampleThreshold=0.5, delta=0.05,
               xmin=-100.0, ymin=-100.0, xmax=100.0, ymax=100.0)
@@ -238,7 +239,7 @@ def main():
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "%d particles x %d beams (270 deg, 0.25 deg), 0.05 m grid, 200x200 m map, synthetic 18x12 m room log" % (n, B),
                            "particles": n, "beams": B, "particles_per_gpu": nl,
-                           "l2": "inputs larger than L2 (per-scan working set ~%.1f GB of map patches per GPU)" % (nl * 70 * 16384 / 1e9),
+                           "l2": "inputs larger than L2 (%.1f GB of map patches resident per GPU, every particle's active area is read and written every scan)" % (s1["pool_in_use"] * PATCH_BYTES / 1e9),
                            "resamples_in_timed_region": proc.resamples() - resamples0, "params": "gfs-carmen defaults, maxUrange 29 / maxrange 30",
                            "api": "GMapping::GridSlamProcessor::processScan (C++ host layer over the C ABI)"},
                 "beam_evals_per_s": beam_evals / (dev_ms * 1e-3), "beam_evals_per_scan": beam_evals, "score_evals_per_particle": score_evals / n,
@@ -246,7 +247,7 @@ def main():
                 "host_ms": {k[8:]: per[k] for k in hkeys},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": KERNEL_TRAFFIC_BYTES * (n / world) / 4096.0,
                              "kernel": "k_scanmatch", "peak_source": peak_src, "bytes_per_beam_eval": BYTES_PER_BEAM_EVAL,
-                             "note": "achieved = algorithmic bytes / CUDA-event time; traffic = DRAM bytes of the ncu capture in profiles/ (the window reads are served from L1/L2)"},
+                             "note": "achieved = algorithmic bytes (144 B per window search actually run, SURVEY.md 8d) / CUDA-event time; it exceeds the DRAM peak because the kernel does not fetch those bytes: an occupancy bitmap and per-cell means replace the nine 16-byte cell reads, and what it does read is served from L1/L2 -- traffic = DRAM bytes of the ncu capture in profiles/"},
                 "e2e": {"value": 1000.0 / wall_ms, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": wall_ms},
                 "gpu_launches": int(launches), "clocks": clk.summary()}
         if not args.no_cpu_baseline and world == 1:

@@ -1,7 +1,8 @@
 /* gm_b200.h -- C ABI of the B200-native GMapping per-scan particle update.
  *
  * One gm_ctx per GMapping::GridSlamProcessor (per GPU).  The context owns, in HBM: the patch pool
- * (32x32-cell patches of 16-byte cells), per-particle patch directories + map geometry, refcounts,
+ * (32x32-cell patches: 16-byte cells {acc, n}, a visit-counter plane, and two derived planes -- per-cell means and an
+ * occupancy bitmap -- 36.1 KiB per patch), per-particle patch directories + map geometry, refcounts,
  * the beam table and the matcher parameters.  The host owns poses, weights, the trajectory tree and
  * the drand48 stream.
  *
@@ -39,7 +40,7 @@ typedef struct gm_ctx gm_ctx;
 typedef struct gm_config {
     int32_t device;         /* CUDA device ordinal */
     uint32_t max_particles; /* capacity; gm_init_particles may use fewer */
-    uint64_t pool_patches;  /* patch-pool capacity (16 KiB each); 0 = size from free HBM */
+    uint64_t pool_patches;  /* patch-pool capacity (36.1 KiB each); 0 = half of the free HBM */
     uint32_t block_threads; /* threads per particle CTA, 0 = default (256) */
     uint32_t flags;         /* reserved, 0 */
     uint32_t global_particles; /* multi-GPU: particles over all ranks (sizes the weight buffers); 0 = max_particles */

@@ -705,8 +705,8 @@ __global__ void k_relayout_commit(RelayoutArgs A) {
 //   2. make every active patch private: create it, or copy it when another particle still references
 //      it (harray2d.h:169-185 copies always; copying only shared patches yields identical cells);
 //   3. visits++ along the rays (scanmatcher.cpp:317-325); integer atomics commute, so the counts are bit-exact;
-//   4. endpoint hits (scanmatcher.cpp:327-334): float `acc` is order dependent, so hits are sorted by
-//      (cell, beam) and each cell's run is accumulated sequentially in beam order by one thread.
+//   4. endpoint hits (scanmatcher.cpp:327-334): float `acc` is order dependent, so hits are grouped by cell (a hash
+//      table in shared memory) and each cell's beams are accumulated in ascending order by its first beam.
 // Ray walks (1 and 3): rays are cut into work items of 32 cells; a thread starts its item from the closed form of the
 // reference's Bresenham state and steps incrementally, looking the patch up again only when the cell leaves it.
 struct BeamRec { int p1x, p1y; float hx, hy; int flags; };  // flags: 1 = ray is traced, 2 = endpoint is a hit, 4 = ... inside the map
