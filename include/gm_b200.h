@@ -147,6 +147,12 @@ int gm_resample_indexes(gm_ctx* ctx, const double* weights, uint32_t n, double u
  * and the first-scan loop gridslamprocessor.cpp:617-633: (optional) remap particle j <- parent idx[j] by
  * patch-reference copy, then computeActiveArea (scanmatcher.cpp:83-254) + registerScan (:266-354) for all. */
 int gm_register(gm_ctx* ctx, const double* ranges, const double* poses /*N*3*/, const uint32_t* idx_or_null);
+/* replaces: the particle copy alone of GridSlamProcessor::resample, gridslamprocessor.hxx:184-213 (Particle copy =
+ * HierarchicalArray2D copy by patch reference): particle j <- parent idx[j].  For callers that register FIRST:
+ * gm_register(ranges, poses, NULL) for every particle at its scan-matched pose, then gm_copy_particles(idx), gives the maps
+ * of gm_register(ranges, poses_of_parents, idx) -- a child starts from its parent's pose and map, so registering the scan
+ * before or after the copy writes the same cells -- and lets the registration start before Neff is known. */
+int gm_copy_particles(gm_ctx* ctx, const uint32_t* idx /*N*/);
 
 /* replaces: ScanMatcher::computeActiveArea, scanmatcher/scanmatcher.cpp:83-254, as far as it is observable: the
  * bounding box of the scan at each particle's pose and the Map::resize it triggers.  (The active patch set itself
@@ -182,6 +188,8 @@ int gm_dist_allgather(gm_ctx* ctx, const double* local, uint32_t count, double* 
  * packed on the owner, sent with ncclSend/ncclRecv and installed in spare slots; then the local patch-reference
  * remap and the registration run as in gm_register.  poses: the n local particles. */
 int gm_dist_register(gm_ctx* ctx, const double* ranges, const double* poses, const uint32_t* idx_global);
+/* gm_copy_particles across ranks: the migration and the remap of gm_dist_register without the registration */
+int gm_dist_copy_particles(gm_ctx* ctx, const uint32_t* idx_global /*N global*/);
 /* planning only (no device work): which global parents this rank must import for idx_global, in import order;
  * returns the count, fills parents_out (capacity n) -- used by the tests of the host-side logic */
 int gm_dist_plan(uint32_t n_local, int rank, int world, const uint32_t* idx_global, uint32_t* parents_out, uint32_t* local_idx_out);

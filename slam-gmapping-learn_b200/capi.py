@@ -91,6 +91,7 @@ def load_library(path=LIB_PATH):
     L.gm_normalize_neff.argtypes = [vp, dp, C.c_uint32, C.c_double, dp, dp]
     L.gm_resample_indexes.argtypes = [vp, dp, C.c_uint32, C.c_double, up, up]
     L.gm_register.argtypes = [vp, dp, dp, up]
+    L.gm_copy_particles.argtypes = [vp, up]
     L.gm_map_info_get.argtypes = [vp, C.c_uint32, C.POINTER(MapInfo)]
     L.gm_download_map.argtypes = [vp, C.c_uint32, C.POINTER(MapInfo), vp, vp, C.c_uint32]
     L.gm_map_digest.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
@@ -213,6 +214,10 @@ class GmContext:
             idx = np.ascontiguousarray(idx, dtype=np.uint32); assert idx.shape == (self.n,)
             ip = _up(idx)
         self._ck(self.L.gm_register(self.h, _dp(r), _dp(p), ip))
+
+    def copy_particles(self, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.uint32); assert idx.shape == (self.n,)
+        self._ck(self.L.gm_copy_particles(self.h, _up(idx)))
 
     # ---- read-back
     def map_info(self, particle):

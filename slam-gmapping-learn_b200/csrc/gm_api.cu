@@ -46,7 +46,12 @@ int gm_create(gm_ctx** out, const gm_config* cfg) {
     ctx = c;
 #define CKC(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { fail(nullptr, GM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2_)); gm_destroy(c); return GM_ERR_CUDA; } } while (0)
     CKC(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
-    CKC(cudaEventCreate(&c->ev0)); CKC(cudaEventCreate(&c->ev1));
+    {
+        int lo = 0, hi = 0;  // the weight kernels are one CTA each: let them in ahead of the registration's grid
+        CKC(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CKC(cudaStreamCreateWithPriority(&c->st_w, cudaStreamNonBlocking, hi));
+    }
+    CKC(cudaEventCreate(&c->ev0)); CKC(cudaEventCreate(&c->ev1)); CKC(cudaEventCreate(&c->evw0)); CKC(cudaEventCreate(&c->evw1));
     size_t cap = cfg->pool_patches;
     if (!cap) {
         size_t free_b = 0, total_b = 0;
@@ -114,6 +119,9 @@ int gm_destroy(gm_ctx* c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->st) cudaStreamDestroy(c->st);
+    if (c->st_w) cudaStreamDestroy(c->st_w);
+    if (c->evw0) cudaEventDestroy(c->evw0);
+    if (c->evw1) cudaEventDestroy(c->evw1);
     delete c;
     return GM_OK;
 }
@@ -267,34 +275,38 @@ int gm_scanmatch(gm_ctx* ctx, const double* ranges, double* poses_inout, double 
 }
 
 int gm_normalize_neff(gm_ctx* ctx, const double* log_weights, uint32_t n, double obs_sigma_gain, double* weights_out, double* neff_out) {
-    if (int r = ready(ctx, true)) return r;
+    if (int r = ready_weights(ctx)) return r;
+    if (!ctx->inited) return fail(ctx, GM_ERR_ARG, "gm_init_particles has not been called");
     if (!log_weights || !n || n > ctx->weights_cap) return fail(ctx, GM_ERR_ARG, "gm_normalize_neff: bad argument");
-    CK(cudaMemcpyAsync(ctx->d_logw, log_weights, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaEventRecord(ctx->ev0, ctx->st));
-    launch_normalize(ctx->d_logw, n, obs_sigma_gain, ctx->d_w, ctx->d_neff, ctx->st);
-    CK(cudaEventRecord(ctx->ev1, ctx->st));
+    cudaStream_t sw = ctx->st_w;  // not ordered after a registration in flight on ctx->st
+    CK(cudaMemcpyAsync(ctx->d_logw, log_weights, sizeof(double) * n, cudaMemcpyHostToDevice, sw));
+    CK(cudaEventRecord(ctx->evw0, sw));
+    launch_normalize(ctx->d_logw, n, obs_sigma_gain, ctx->d_w, ctx->d_neff, sw);
+    CK(cudaEventRecord(ctx->evw1, sw));
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_normalize")) return r;
-    if (weights_out) CK(cudaMemcpyAsync(weights_out, ctx->d_w, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->st));
-    if (neff_out) CK(cudaMemcpyAsync(neff_out, ctx->d_neff, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));
-    CK(cudaEventElapsedTime(&ctx->stats.ms_weights, ctx->ev0, ctx->ev1));
+    if (weights_out) CK(cudaMemcpyAsync(weights_out, ctx->d_w, sizeof(double) * n, cudaMemcpyDeviceToHost, sw));
+    if (neff_out) CK(cudaMemcpyAsync(neff_out, ctx->d_neff, sizeof(double), cudaMemcpyDeviceToHost, sw));
+    CK(cudaStreamSynchronize(sw));
+    CK(cudaEventElapsedTime(&ctx->stats.ms_weights, ctx->evw0, ctx->evw1));
     ctx->stats.total_ms[1] += ctx->stats.ms_weights;
     return GM_OK;
 }
 
 int gm_resample_indexes(gm_ctx* ctx, const double* weights, uint32_t n, double u01, uint32_t* idx_out, uint32_t* emitted_out) {
-    if (int r = ready(ctx, true)) return r;
+    if (int r = ready_weights(ctx)) return r;
+    if (!ctx->inited) return fail(ctx, GM_ERR_ARG, "gm_init_particles has not been called");
     if (!weights || !idx_out || !n || n > ctx->weights_cap) return fail(ctx, GM_ERR_ARG, "gm_resample_indexes: bad argument");
-    CK(cudaMemcpyAsync(ctx->d_w, weights, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemsetAsync(ctx->d_emitted, 0, sizeof(unsigned), ctx->st));
-    launch_resample(ctx->d_w, n, u01, ctx->d_cum, ctx->d_tgt, ctx->d_widx, ctx->d_emitted, ctx->st);
+    cudaStream_t sw = ctx->st_w;
+    CK(cudaMemcpyAsync(ctx->d_w, weights, sizeof(double) * n, cudaMemcpyHostToDevice, sw));
+    CK(cudaMemsetAsync(ctx->d_emitted, 0, sizeof(unsigned), sw));
+    launch_resample(ctx->d_w, n, u01, ctx->d_cum, ctx->d_tgt, ctx->d_widx, ctx->d_emitted, sw);
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_resample")) return r;
-    CK(cudaMemcpyAsync(idx_out, ctx->d_widx, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(idx_out, ctx->d_widx, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, sw));
     uint32_t em = 0;
-    CK(cudaMemcpyAsync(&em, ctx->d_emitted, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaMemcpyAsync(&em, ctx->d_emitted, sizeof(uint32_t), cudaMemcpyDeviceToHost, sw));
+    CK(cudaStreamSynchronize(sw));
     if (emitted_out) *emitted_out = em;
     return GM_OK;
 }
@@ -465,6 +477,15 @@ int gm_register(gm_ctx* ctx, const double* ranges, const double* poses, const ui
     CK(cudaEventRecord(ctx->ev0, ctx->st));
     if (int rc = gmi_bounds_and_resize(ctx)) return rc;
     return gmi_register_update(ctx);
+}
+
+int gm_copy_particles(gm_ctx* ctx, const uint32_t* idx) {
+    if (int r = ready(ctx, true)) return r;  // completes a registration in flight: the copies take the registered maps
+    if (!idx) return fail(ctx, GM_ERR_ARG, "gm_copy_particles: null argument");
+    if (ctx->dist) return fail(ctx, GM_ERR_ARG, "gm_copy_particles: sharded context, use gm_dist_copy_particles");
+    if (int r = gmi_remap(ctx, idx, ctx->n)) return r;
+    ctx->stats.total_ms[2] += ctx->stats.ms_remap;
+    return GM_OK;
 }
 
 int gm_compute_active_area(gm_ctx* ctx, const double* ranges, const double* poses) {

@@ -22,7 +22,8 @@ inline std::string& create_error() { static thread_local std::string e; return e
 struct gm_ctx {
     int device = 0;
     cudaStream_t st = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t st_w = nullptr;  // weights (normalize / resample indexes): independent of the maps, may overtake a registration
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evw0 = nullptr, evw1 = nullptr;
     uint32_t max_particles = 0, n = 0, threads = 256;
     DevParams P{};
     bool laser_set = false, match_set = false, inited = false;
@@ -161,6 +162,11 @@ inline int ready(gm_ctx* ctx, bool need_particles) {
     if (need_particles && !ctx->inited) return fail(ctx, GM_ERR_ARG, "gm_init_particles has not been called");
     if (int r = bind(ctx)) return r;
     return ctx->reg_pending ? gmi_register_finish(ctx) : GM_OK;  // an asynchronous registration reports here
+}
+// entry points that touch weights only: they run on their own stream and leave a registration in flight alone
+inline int ready_weights(gm_ctx* ctx) {
+    if (!ctx) return GM_ERR_ARG;
+    return bind(ctx);
 }
 
 

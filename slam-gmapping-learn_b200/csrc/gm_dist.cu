@@ -168,6 +168,113 @@ static void plan_imports(uint32_t n, int rank, const uint32_t* idx, std::vector<
     }
 }
 
+// the parents of `idx_global` that live on other ranks migrate into spare slots, then the ordinary patch-reference remap
+static int dist_migrate_and_remap(gm_ctx* ctx, const uint32_t* idx_global, const char* who) {
+    gm_dist* d = ctx->dist;
+    const uint32_t n = ctx->n;
+    const int world = d->world, rank = d->rank;
+    const uint32_t N = n * (uint32_t)world;
+    for (uint32_t i = 0; i < N; i++)
+        if (idx_global[i] >= N) return fail(ctx, GM_ERR_ARG, "%s: parent index %u >= %u", who, idx_global[i], N);
+    // ---- plan: imports of this rank (grouped by owner) and, for every other rank, what it imports from us
+    std::vector<uint32_t> imports, local_idx;
+    plan_imports(n, rank, idx_global, imports, local_idx);
+    if (n + imports.size() > ctx->max_particles)
+        return fail(ctx, GM_ERR_ARG, "%s: %zu imported parents do not fit the %u spare particle slots", who, imports.size(), ctx->max_particles - n);
+    std::vector<std::vector<int> > sends(world);  // local slots to send to each rank, ascending
+    size_t nsend = 0;
+    for (int g = 0; g < world; g++) {
+        if (g == rank) continue;
+        std::vector<uint32_t> imp_g, unused;
+        plan_imports(n, g, idx_global, imp_g, unused);
+        for (uint32_t p : imp_g)
+            if (p / n == (uint32_t)rank) sends[g].push_back((int)(p - (uint32_t)rank * n));
+        nsend += sends[g].size();
+    }
+    std::vector<size_t> recv_from(world, 0);  // imports per owner; the import list is ascending, hence grouped by owner
+    for (uint32_t p : imports) recv_from[p / n]++;
+    const size_t nrecv = imports.size();
+
+    CK(cudaEventRecord(d->e0, ctx->st));
+    if (nsend + nrecv) {
+        if (nsend + nrecv > d->meta_cap) {
+            const size_t cap = (nsend + nrecv) * 2;
+            CK(dalloc(d->d_slots, cap)); CK(dalloc(d->d_meta_send, cap * gm::kMetaInts)); CK(dalloc(d->d_meta_recv, cap * gm::kMetaInts));
+            CK(dalloc(d->d_off, cap));
+            d->meta_cap = cap;
+        }
+        // ---- 1. patch counts of what we send; exchange the counts
+        std::vector<int> slots;
+        for (int g = 0; g < world; g++) slots.insert(slots.end(), sends[g].begin(), sends[g].end());
+        std::vector<int> meta_send(nsend * gm::kMetaInts), meta_recv(nrecv * gm::kMetaInts);
+        if (nsend) {
+            CK(cudaMemcpyAsync(d->d_slots, slots.data(), sizeof(int) * nsend, cudaMemcpyHostToDevice, ctx->st));
+            gm::k_dist_count<<<(unsigned)nsend, 256, 0, ctx->st>>>(d->d_slots, ctx->geom, ctx->dir, ctx->dir_cap, d->d_meta_send);
+            ctx->stats.launches++;
+        }
+        NK(g_nccl.GroupStart());
+        {
+            size_t so = 0, ro = 0;
+            for (int g = 0; g < world; g++) {
+                if (g == rank) continue;
+                if (!sends[g].empty()) NK(g_nccl.Send(d->d_meta_send + so * gm::kMetaInts, sends[g].size() * gm::kMetaInts, ncclInt32, g, d->comm, ctx->st));
+                if (recv_from[g]) NK(g_nccl.Recv(d->d_meta_recv + ro * gm::kMetaInts, recv_from[g] * gm::kMetaInts, ncclInt32, g, d->comm, ctx->st));
+                so += sends[g].size(); ro += recv_from[g];
+            }
+        }
+        NK(g_nccl.GroupEnd());
+        if (nsend) CK(cudaMemcpyAsync(meta_send.data(), d->d_meta_send, sizeof(int) * meta_send.size(), cudaMemcpyDeviceToHost, ctx->st));
+        if (nrecv) CK(cudaMemcpyAsync(meta_recv.data(), d->d_meta_recv, sizeof(int) * meta_recv.size(), cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        // ---- 2. byte offsets, buffers, pack, exchange the data
+        std::vector<unsigned long long> send_off(nsend + 1, 0), recv_off(nrecv + 1, 0);
+        for (size_t s = 0; s < nsend; s++) send_off[s + 1] = send_off[s] + gm::packed_bytes(meta_send[gm::kMetaInts * s]);
+        int need_cap = 0, max_count = 0;
+        for (size_t k = 0; k < nrecv; k++) {
+            recv_off[k + 1] = recv_off[k] + gm::packed_bytes(meta_recv[gm::kMetaInts * k]);
+            need_cap = std::max(need_cap, meta_recv[gm::kMetaInts * k + 1] * meta_recv[gm::kMetaInts * k + 2]);
+            max_count = std::max(max_count, meta_recv[gm::kMetaInts * k]);
+        }
+        if (send_off[nsend] > d->send_cap) { CK(dalloc(d->d_send, (size_t)send_off[nsend])); d->send_cap = send_off[nsend]; }
+        if (recv_off[nrecv] > d->recv_cap) { CK(dalloc(d->d_recv, (size_t)recv_off[nrecv])); d->recv_cap = recv_off[nrecv]; }
+        if (nsend) {
+            CK(cudaMemcpyAsync(d->d_off, send_off.data(), sizeof(unsigned long long) * nsend, cudaMemcpyHostToDevice, ctx->st));
+            gm::k_dist_pack<<<(unsigned)nsend, 512, 0, ctx->st>>>(d->d_slots, ctx->geom, ctx->dir, ctx->dir_cap, ctx->pool.cells, ctx->pool.visits, d->d_off, d->d_send);
+            ctx->stats.launches++;
+        }
+        NK(g_nccl.GroupStart());
+        {
+            size_t so = 0, ro = 0;
+            for (int g = 0; g < world; g++) {
+                if (g == rank) continue;
+                const size_t ns = sends[g].size(), nr = recv_from[g];
+                if (ns) NK(g_nccl.Send(d->d_send + send_off[so], (size_t)(send_off[so + ns] - send_off[so]), ncclChar, g, d->comm, ctx->st));
+                if (nr) NK(g_nccl.Recv(d->d_recv + recv_off[ro], (size_t)(recv_off[ro + nr] - recv_off[ro]), ncclChar, g, d->comm, ctx->st));
+                so += ns; ro += nr;
+            }
+        }
+        NK(g_nccl.GroupEnd());
+        // ---- 3. install the received parents in the spare slots n .. n + nrecv - 1
+        if (nrecv) {
+            CK(cudaStreamSynchronize(ctx->st));  // d_off is reused below
+            if (int r = gmi_ensure_dir_cap(ctx, need_cap)) return r;
+            CK(cudaMemcpyAsync(d->d_off, recv_off.data(), sizeof(unsigned long long) * nrecv, cudaMemcpyHostToDevice, ctx->st));
+            const size_t smem = (size_t)std::max(max_count, 1) * sizeof(int);
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(gm::k_dist_install, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gm::k_dist_install<<<(unsigned)nrecv, 512, smem, ctx->st>>>((int)n, ctx->geom, ctx->dir, ctx->dir_cap, ctx->pool, d->d_off, d->d_recv, ctx->d_counters);
+            ctx->stats.launches++;
+        }
+        if (int rc = check_launch(ctx, "patch migration")) return rc;
+        ctx->stats.migrated_particles = nrecv;
+        ctx->stats.migrated_bytes = recv_off[nrecv];
+    }
+    CK(cudaEventRecord(d->e1, ctx->st));
+    // ---- 4. the ordinary remap, children of imported parents read from the spare slots
+    if (int r = gmi_remap(ctx, local_idx.data(), n + (uint32_t)nrecv)) return r;
+    CK(cudaEventElapsedTime(&ctx->stats.ms_migrate, d->e0, d->e1));
+    return GM_OK;
+}
+
 extern "C" {
 
 void gmi_dist_destroy(gm_ctx* ctx) {
@@ -241,116 +348,23 @@ int gm_dist_register(gm_ctx* ctx, const double* ranges, const double* poses, con
     if (int r = ready(ctx, true)) return r;
     if (!ctx->dist) return fail(ctx, GM_ERR_ARG, "gm_dist_register: gm_dist_init has not been called");
     if (!ranges || !poses) return fail(ctx, GM_ERR_ARG, "gm_dist_register: null argument");
-    gm_dist* d = ctx->dist;
-    const uint32_t n = ctx->n;
-    const int world = d->world, rank = d->rank;
     if (int r = gmi_stage(ctx, ranges, poses)) return r;
     ctx->stats.ms_migrate = 0.f; ctx->stats.migrated_particles = 0; ctx->stats.migrated_bytes = 0;
-
-    if (idx_global) {
-        const uint32_t N = n * (uint32_t)world;
-        for (uint32_t i = 0; i < N; i++)
-            if (idx_global[i] >= N) return fail(ctx, GM_ERR_ARG, "gm_dist_register: parent index %u >= %u", idx_global[i], N);
-        // ---- plan: imports of this rank (grouped by owner) and, for every other rank, what it imports from us
-        std::vector<uint32_t> imports, local_idx;
-        plan_imports(n, rank, idx_global, imports, local_idx);
-        if (n + imports.size() > ctx->max_particles)
-            return fail(ctx, GM_ERR_ARG, "gm_dist_register: %zu imported parents do not fit the %u spare particle slots", imports.size(), ctx->max_particles - n);
-        std::vector<std::vector<int> > sends(world);  // local slots to send to each rank, ascending
-        size_t nsend = 0;
-        for (int g = 0; g < world; g++) {
-            if (g == rank) continue;
-            std::vector<uint32_t> imp_g, unused;
-            plan_imports(n, g, idx_global, imp_g, unused);
-            for (uint32_t p : imp_g)
-                if (p / n == (uint32_t)rank) sends[g].push_back((int)(p - (uint32_t)rank * n));
-            nsend += sends[g].size();
-        }
-        std::vector<size_t> recv_from(world, 0);  // imports per owner; the import list is ascending, hence grouped by owner
-        for (uint32_t p : imports) recv_from[p / n]++;
-        const size_t nrecv = imports.size();
-
-        CK(cudaEventRecord(d->e0, ctx->st));
-        if (nsend + nrecv) {
-            if (nsend + nrecv > d->meta_cap) {
-                const size_t cap = (nsend + nrecv) * 2;
-                CK(dalloc(d->d_slots, cap)); CK(dalloc(d->d_meta_send, cap * gm::kMetaInts)); CK(dalloc(d->d_meta_recv, cap * gm::kMetaInts));
-                CK(dalloc(d->d_off, cap));
-                d->meta_cap = cap;
-            }
-            // ---- 1. patch counts of what we send; exchange the counts
-            std::vector<int> slots;
-            for (int g = 0; g < world; g++) slots.insert(slots.end(), sends[g].begin(), sends[g].end());
-            std::vector<int> meta_send(nsend * gm::kMetaInts), meta_recv(nrecv * gm::kMetaInts);
-            if (nsend) {
-                CK(cudaMemcpyAsync(d->d_slots, slots.data(), sizeof(int) * nsend, cudaMemcpyHostToDevice, ctx->st));
-                gm::k_dist_count<<<(unsigned)nsend, 256, 0, ctx->st>>>(d->d_slots, ctx->geom, ctx->dir, ctx->dir_cap, d->d_meta_send);
-                ctx->stats.launches++;
-            }
-            NK(g_nccl.GroupStart());
-            {
-                size_t so = 0, ro = 0;
-                for (int g = 0; g < world; g++) {
-                    if (g == rank) continue;
-                    if (!sends[g].empty()) NK(g_nccl.Send(d->d_meta_send + so * gm::kMetaInts, sends[g].size() * gm::kMetaInts, ncclInt32, g, d->comm, ctx->st));
-                    if (recv_from[g]) NK(g_nccl.Recv(d->d_meta_recv + ro * gm::kMetaInts, recv_from[g] * gm::kMetaInts, ncclInt32, g, d->comm, ctx->st));
-                    so += sends[g].size(); ro += recv_from[g];
-                }
-            }
-            NK(g_nccl.GroupEnd());
-            if (nsend) CK(cudaMemcpyAsync(meta_send.data(), d->d_meta_send, sizeof(int) * meta_send.size(), cudaMemcpyDeviceToHost, ctx->st));
-            if (nrecv) CK(cudaMemcpyAsync(meta_recv.data(), d->d_meta_recv, sizeof(int) * meta_recv.size(), cudaMemcpyDeviceToHost, ctx->st));
-            CK(cudaStreamSynchronize(ctx->st));
-            // ---- 2. byte offsets, buffers, pack, exchange the data
-            std::vector<unsigned long long> send_off(nsend + 1, 0), recv_off(nrecv + 1, 0);
-            for (size_t s = 0; s < nsend; s++) send_off[s + 1] = send_off[s] + gm::packed_bytes(meta_send[gm::kMetaInts * s]);
-            int need_cap = 0, max_count = 0;
-            for (size_t k = 0; k < nrecv; k++) {
-                recv_off[k + 1] = recv_off[k] + gm::packed_bytes(meta_recv[gm::kMetaInts * k]);
-                need_cap = std::max(need_cap, meta_recv[gm::kMetaInts * k + 1] * meta_recv[gm::kMetaInts * k + 2]);
-                max_count = std::max(max_count, meta_recv[gm::kMetaInts * k]);
-            }
-            if (send_off[nsend] > d->send_cap) { CK(dalloc(d->d_send, (size_t)send_off[nsend])); d->send_cap = send_off[nsend]; }
-            if (recv_off[nrecv] > d->recv_cap) { CK(dalloc(d->d_recv, (size_t)recv_off[nrecv])); d->recv_cap = recv_off[nrecv]; }
-            if (nsend) {
-                CK(cudaMemcpyAsync(d->d_off, send_off.data(), sizeof(unsigned long long) * nsend, cudaMemcpyHostToDevice, ctx->st));
-                gm::k_dist_pack<<<(unsigned)nsend, 512, 0, ctx->st>>>(d->d_slots, ctx->geom, ctx->dir, ctx->dir_cap, ctx->pool.cells, ctx->pool.visits, d->d_off, d->d_send);
-                ctx->stats.launches++;
-            }
-            NK(g_nccl.GroupStart());
-            {
-                size_t so = 0, ro = 0;
-                for (int g = 0; g < world; g++) {
-                    if (g == rank) continue;
-                    const size_t ns = sends[g].size(), nr = recv_from[g];
-                    if (ns) NK(g_nccl.Send(d->d_send + send_off[so], (size_t)(send_off[so + ns] - send_off[so]), ncclChar, g, d->comm, ctx->st));
-                    if (nr) NK(g_nccl.Recv(d->d_recv + recv_off[ro], (size_t)(recv_off[ro + nr] - recv_off[ro]), ncclChar, g, d->comm, ctx->st));
-                    so += ns; ro += nr;
-                }
-            }
-            NK(g_nccl.GroupEnd());
-            // ---- 3. install the received parents in the spare slots n .. n + nrecv - 1
-            if (nrecv) {
-                CK(cudaStreamSynchronize(ctx->st));  // d_off is reused below
-                if (int r = gmi_ensure_dir_cap(ctx, need_cap)) return r;
-                CK(cudaMemcpyAsync(d->d_off, recv_off.data(), sizeof(unsigned long long) * nrecv, cudaMemcpyHostToDevice, ctx->st));
-                const size_t smem = (size_t)std::max(max_count, 1) * sizeof(int);
-                if (smem > 48 * 1024) CK(cudaFuncSetAttribute(gm::k_dist_install, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                gm::k_dist_install<<<(unsigned)nrecv, 512, smem, ctx->st>>>((int)n, ctx->geom, ctx->dir, ctx->dir_cap, ctx->pool, d->d_off, d->d_recv, ctx->d_counters);
-                ctx->stats.launches++;
-            }
-            if (int rc = check_launch(ctx, "patch migration")) return rc;
-            ctx->stats.migrated_particles = nrecv;
-            ctx->stats.migrated_bytes = recv_off[nrecv];
-        }
-        CK(cudaEventRecord(d->e1, ctx->st));
-        // ---- 4. the ordinary remap, children of imported parents read from the spare slots
-        if (int r = gmi_remap(ctx, local_idx.data(), n + (uint32_t)nrecv)) return r;
-        CK(cudaEventElapsedTime(&ctx->stats.ms_migrate, d->e0, d->e1));
-    }
+    if (idx_global)
+        if (int r = dist_migrate_and_remap(ctx, idx_global, "gm_dist_register")) return r;
     CK(cudaEventRecord(ctx->ev0, ctx->st));
     if (int rc = gmi_bounds_and_resize(ctx)) return rc;
     return gmi_register_update(ctx);
+}
+
+int gm_dist_copy_particles(gm_ctx* ctx, const uint32_t* idx_global) {
+    if (int r = ready(ctx, true)) return r;  // completes a registration in flight: the copies take the registered maps
+    if (!ctx->dist) return fail(ctx, GM_ERR_ARG, "gm_dist_copy_particles: gm_dist_init has not been called");
+    if (!idx_global) return fail(ctx, GM_ERR_ARG, "gm_dist_copy_particles: null argument");
+    ctx->stats.ms_remap = 0.f; ctx->stats.ms_migrate = 0.f; ctx->stats.migrated_particles = 0; ctx->stats.migrated_bytes = 0;
+    if (int r = dist_migrate_and_remap(ctx, idx_global, "gm_dist_copy_particles")) return r;
+    ctx->stats.total_ms[2] += ctx->stats.ms_remap; ctx->stats.total_ms[4] += ctx->stats.ms_migrate;
+    return GM_OK;
 }
 
 }  // extern "C"

@@ -152,6 +152,12 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     // brought up to date by getTrajectories() or refreshTreeWeights().  Default: false, the reference's behaviour.
     void setlazyTreeWeights(bool lazy) { m_lazyTree = lazy; }
     bool getlazyTreeWeights() const { return m_lazyTree; }
+    // B200 build: register the scan right after scan matching (before Neff and the resampling decision are known) so the
+    // kernels overlap the host-side bookkeeping; a resampling then only copies particles (same maps as the reference's
+    // copy-then-register order).  On by default.  Off: the reference's order, and Particle::map may be read
+    // inside onResampleUpdate().
+    void setearlyRegistration(bool early) { m_earlyRegistration = early; }
+    bool getearlyRegistration() const { return m_earlyRegistration; }
     void refreshTreeWeights();
     // occupancy grid of one local particle's map computed on the GPU (what gmapping/src/slam_gmapping.cpp:956-993 fills by
     // walking smap.cell(p) on the host): data[y * width + x] = -1 unknown, 100 if n/visits > occThresh, else 0;
@@ -201,6 +207,7 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     void resetTree();
     double propagateWeights();
     void registerAll(const double* plainReading, const unsigned int* parents);
+    void copyAll(const unsigned int* parents);
     void markMapsStale();
 
     std::shared_ptr<b200::DeviceContext> m_device;
@@ -209,6 +216,7 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     unsigned int m_firstLocal, m_localCount;
     unsigned int m_treeEpoch;
     bool m_lazyTree = false;
+    bool m_earlyRegistration = true, m_registeredEarly = false;
     bool m_weightsChanged = true;  // a particle's log-weight changed since the last normalize()
     mutable bool m_treeDirty = false;
     double m_hostMs[4];

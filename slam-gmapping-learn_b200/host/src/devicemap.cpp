@@ -73,6 +73,9 @@ void DeviceContext::configure(const ScanMatcher& m) {
 // refresh the host mirror: geometry + every allocated patch
 void DeviceMapResidency::pull(void* hostMap) {
     ScanMatcherMap& map = *static_cast<ScanMatcherMap*>(hostMap);
+    if (ctx->mapsAhead)
+        b200::fatal("Particle::map was read between scan matching and registration (from onResampleUpdate?) while early registration is on: "
+                    "the device map already holds the current scan there; call GridSlamProcessor::setearlyRegistration(false) to read maps in that window");
     stale = false;  // first: the accessors used below call sync() again
     gm_map_info info;
     ctx->check(gm_map_info_get(ctx->h, slot, &info), "gm_map_info_get");

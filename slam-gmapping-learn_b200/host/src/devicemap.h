@@ -28,6 +28,8 @@ class DeviceContext {
     void configure(const ScanMatcher& m);
     gm_ctx* h = nullptr;
     unsigned int particles = 0;
+    // GridSlamProcessor's early registration: the device maps hold a scan the reference has not registered yet
+    bool mapsAhead = false;
 
   private:
     bool m_haveLaser = false, m_haveParams = false;

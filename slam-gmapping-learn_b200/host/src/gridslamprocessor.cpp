@@ -294,6 +294,13 @@ void GridSlamProcessor::registerAll(const double* plainReading, const unsigned i
     markMapsStale();
 }
 
+// particle copy by patch reference alone: the scan is already in the parents' maps (early registration)
+void GridSlamProcessor::copyAll(const unsigned int* parents) {
+    if (m_world > 1) m_device->check(gm_dist_copy_particles(m_device->h, parents), "gm_dist_copy_particles");
+    else m_device->check(gm_copy_particles(m_device->h, parents), "gm_copy_particles");
+    markMapsStale();
+}
+
 // resample (reference: gridslamprocessor.hxx:131-302)
 bool GridSlamProcessor::resample(const double* plainReading, int adaptSize, const RangeReading* reading) {
     const size_t n = m_particles.size();
@@ -306,7 +313,8 @@ bool GridSlamProcessor::resample(const double* plainReading, int adaptSize, cons
             p.node = node;
             p.previousIndex = (int)i;
         }
-        registerAll(plainReading, 0);
+        if (!m_registeredEarly) registerAll(plainReading, 0);
+        m_device->mapsAhead = false;
         return false;
     }
     if (m_infoStream) m_infoStream << "*************RESAMPLE***************" << endl;
@@ -348,7 +356,11 @@ bool GridSlamProcessor::resample(const double* plainReading, int adaptSize, cons
         p.setWeight(0);
     }
     m_weightsChanged = true;
-    registerAll(plainReading, m_indexes.data());
+    // a child starts from its parent's pose and map: registering the scan in the parent before the copy (early
+    // registration) or in the child after it (the reference's order) writes the same cells
+    if (m_registeredEarly) copyAll(m_indexes.data());
+    else registerAll(plainReading, m_indexes.data());
+    m_device->mapsAhead = false;
     return true;
 }
 
@@ -501,6 +513,15 @@ bool GridSlamProcessor::processScan(const RangeReading& reading, int adaptPartic
                 m_outputStream << endl;
             }
             onScanmatchUpdate();
+            // early registration: the scan goes into every particle's map at its scan-matched pose now, and the kernels run
+            // while the host normalises the weights, decides about resampling and grows the trajectory tree.  Until the
+            // point where the reference registers (inside resample()) the device maps are one scan ahead of the
+            // reference's: reading Particle::map in that window (from onResampleUpdate) is refused, see setearlyRegistration
+            m_registeredEarly = false;
+            sw.lap();
+            normalizeIfNeeded();  // first: a one-CTA kernel that would otherwise queue behind the registration's grid
+            m_hostMs[2] += sw.lap();
+            if (m_earlyRegistration) { registerAll(plain.data(), 0); m_registeredEarly = true; m_device->mapsAhead = true; }
             sw.lap();
             // updateTreeWeights(false): the weights and Neff are needed now; the propagation into the trajectory tree can only be
             // observed before the second updateTreeWeights below through onResampleUpdate(), i.e. when the filter resamples --

@@ -230,6 +230,33 @@ def test_copy_on_write_refcounts():
     ctx.close()
 
 
+def test_register_then_copy_equals_copy_then_register():
+    """GridSlamProcessor's early registration: registering the scan in every particle at its own pose and then copying
+    particle j <- idx[j] gives, bit for bit, the maps of the reference's order (copy, then register each child at its
+    parent's pose) -- including the derived planes gm_map_digest verifies."""
+    def world():
+        return _random_world(11, beams=181, particles=8, scans=3)
+    idx = np.array([0, 0, 2, 2, 2, 5, 7, 7], dtype=np.uint32)
+    log, m, a, maps, poses, rng = world()
+    r = log.ranges[2]
+    own = poses[:8] + rng.normal(0, [0.02, 0.02, 0.01], size=(8, 3))  # each particle's scan-matched pose
+    a.register(r, own[idx], idx)  # the reference's order
+    da = a.digests()
+    log, m, b, maps_b, poses_b, rng_b = world()
+    b.register(r, own)  # early registration ...
+    b.copy_particles(idx)  # ... then the resampling copies
+    db = b.digests()
+    for k in ("patches", "cells", "sum_n", "sum_visits", "hash_counts", "hash_acc"):
+        assert np.array_equal(da[k], db[k]), k
+    # and a further scan registers identically on both (copy-on-write of the shared patches)
+    nxt = own[idx] + 0.01
+    a.register(log.ranges[1], nxt); b.register(log.ranges[1], nxt)
+    da, db = a.digests(), b.digests()
+    for k in ("patches", "cells", "sum_n", "sum_visits", "hash_counts", "hash_acc"):
+        assert np.array_equal(da[k], db[k]), k
+    a.close(); b.close()
+
+
 def test_errors_are_loud():
     import importlib
     gm = importlib.import_module("slam-gmapping-learn_b200")
