@@ -39,6 +39,7 @@ void gmh_destroy(void* h) { delete static_cast<Handle*>(h); }
 void* gmh_clone(void* h) { return new Handle(*static_cast<Handle*>(h)); }
 int gmh_dist_unique_id(void* id128) { return gm_dist_unique_id(id128); }
 void gmh_set_distributed(void* h, int rank, int world, const void* id) { static_cast<Handle*>(h)->gsp->setDistributed(rank, world, id); }
+void gmh_set_early_registration(void* h, int on) { static_cast<Handle*>(h)->gsp->setearlyRegistration(on != 0); }
 
 // params: maxUrange maxrange sigma kernelSize lstep astep iterations lsigma ogain lskip srr srt str stt linearUpdate
 //         angularUpdate resampleThreshold period generateMap minimumScore            (20 doubles)

@@ -36,6 +36,7 @@ def load():
     L.gmh_destroy.argtypes = [vp]
     L.gmh_dist_unique_id.argtypes = [vp]
     L.gmh_set_distributed.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.gmh_set_early_registration.argtypes = [vp, C.c_int]
     L.gmh_setup.argtypes = [vp, C.c_uint, dp, dp, dp]
     L.gmh_init.argtypes = [vp, C.c_uint] + [C.c_double] * 5 + [dp, C.c_ulong]
     L.gmh_process_scan.argtypes = [vp, dp, C.c_uint, dp, C.c_double]
@@ -71,13 +72,15 @@ class Processor:
     """GMapping::GridSlamProcessor (C++) behind ctypes."""
 
     def __init__(self, angles, particles, init_pose, bounds=(-100., -100., 100., 100.), delta=0.05, seed=12345, laser_pose=(0., 0., 0.),
-                 rank=0, world=1, nccl_id=None, verbose=False, **params):
+                 rank=0, world=1, nccl_id=None, verbose=False, early_registration=True, **params):
         L = load()
         self.L = L
         self.h = L.gmh_create(1 if verbose else 0)
         if world > 1:
             self._id = C.create_string_buffer(nccl_id, 128)
             L.gmh_set_distributed(self.h, rank, world, self._id)
+        if not early_registration:
+            L.gmh_set_early_registration(self.h, 0)  # the reference's order: copy the resampled particles, then register
         p = dict(DEFAULTS); p.update(params)
         pv = np.array([float(p[k]) for k in PARAM_ORDER], dtype=np.float64)
         a = np.ascontiguousarray(angles, dtype=np.float64); lp = np.ascontiguousarray(laser_pose, dtype=np.float64)

@@ -205,6 +205,33 @@ def test_clone_continues_identically_and_occupancy_grid():
 
 
 @pytest.mark.gpu
+def test_reference_order_and_early_registration_agree():
+    """setearlyRegistration(false) keeps the reference's order (copy the resampled particles, then register the scan in
+    every child); the default registers first and copies afterwards.  Same drand48 stream in, bit-identical filter out:
+    poses, weights, resample indexes, every map -- and both follow the reference trace."""
+    build_host()
+    hostapi = importlib.import_module("slam-gmapping-learn_b200.hostapi")
+    g = Golden("room181_k2_lskip")
+    p = g.p
+    runs = []
+    for early in (True, False):
+        a = hostapi.Processor(g.angles, p["particles"], g.head_init, bounds=(p["xmin"], p["ymin"], p["xmax"], p["ymax"]), delta=p["delta"],
+                              seed=p["seed"], early_registration=early, **{k: p[k] for k in hostapi.PARAM_ORDER})
+        idx = []
+        for i in range(len(g.ranges)):
+            a.process_scan(g.ranges[i], g.odom[i], g.stamps[i])
+            if a.last_resampled():
+                idx.append(a.indexes().copy())
+        runs.append((a.state(), a.map_digests(), a.resamples(), a.neff(), idx))
+        a.close()
+    (s0, d0, r0, n0, i0), (s1, d1, r1, n1, i1) = runs
+    assert r0 == r1 and r0 > 0 and n0 == n1
+    assert np.array_equal(s0, s1) and np.array_equal(d0, d1)
+    assert len(i0) == len(i1) and all(np.array_equal(x, y) for x, y in zip(i0, i1))
+    assert np.abs(s0[:, :3] - g.state[len(g.ranges) - 1][:, :3]).max() < 1e-4
+
+
+@pytest.mark.gpu
 def test_thousand_scans_free_running():
     """BASELINE.json configs[0]/[1]: 30 particles, 181-beam scans, 1000 scans, free running through the C++ API against the
     unmodified reference (fixture: Neff and flags for every scan, all poses / log-weights every 10th scan): the filter never
