@@ -231,6 +231,12 @@ class GmContext:
             self._ck(self.L.gm_download_map(self.h, particle, C.byref(mi), coords.ctypes.data, cells.ctypes.data, n))
         return mi, coords, cells
 
+    def upload_map(self, particle, info, coords, cells):
+        """the inverse of download_map: replace one particle's map by host content"""
+        coords = np.ascontiguousarray(coords, dtype=np.int32); cells = np.ascontiguousarray(cells, dtype=CELL_DTYPE)
+        assert coords.shape[0] == cells.shape[0]
+        self._ck(self.L.gm_upload_map(self.h, particle, C.byref(info), coords.ctypes.data, cells.ctypes.data, coords.shape[0]))
+
     def digests(self, first=0, count=None):
         count = self.n - first if count is None else count
         out = np.zeros(count, dtype=DIGEST_DTYPE)

@@ -257,6 +257,35 @@ def test_register_then_copy_equals_copy_then_register():
     a.close(); b.close()
 
 
+def test_download_upload_round_trip():
+    """gm_download_map -> gm_upload_map into another context: same digest (which also proves the derived planes --
+    visit plane, means, occupancy bitmap -- rebuilt on install), same scan-matching results, and the uploaded maps keep
+    registering like the originals."""
+    import importlib
+    gm = importlib.import_module("slam-gmapping-learn_b200")
+    log, m, a, maps, poses, rng = _random_world(13, beams=181, particles=4, scans=4)
+    b = gm.GmContext(4, pool_patches=4096)
+    b.set_laser(log.laser.angles())
+    b.set_matching(urange=80.0, range_=81.0)
+    b.init_particles(4)
+    for j in range(4):
+        info, coords, cells = a.download_map(j)
+        assert coords.shape[0] > 0
+        b.upload_map(j, info, coords, cells)
+    da, db = a.digests(), b.digests()
+    for k in ("patches", "cells", "sum_n", "sum_visits", "hash_counts", "hash_acc"):
+        assert np.array_equal(da[k], db[k]), k
+    init = poses + rng.normal(0, [0.03, 0.03, 0.01], size=(4, 3))
+    ra, rb = a.scanmatch(log.ranges[3], init, 0.0), b.scanmatch(log.ranges[3], init, 0.0)
+    for x, y in zip(ra, rb):
+        assert np.array_equal(x, y)
+    a.register(log.ranges[3], ra[0]); b.register(log.ranges[3], rb[0])
+    da, db = a.digests(), b.digests()
+    for k in ("patches", "cells", "sum_n", "sum_visits", "hash_counts", "hash_acc"):
+        assert np.array_equal(da[k], db[k]), k
+    a.close(); b.close()
+
+
 def test_errors_are_loud():
     import importlib
     gm = importlib.import_module("slam-gmapping-learn_b200")
