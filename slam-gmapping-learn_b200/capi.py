@@ -94,6 +94,7 @@ def load_library(path=LIB_PATH):
     L.gm_copy_particles.argtypes = [vp, up]
     L.gm_map_info_get.argtypes = [vp, C.c_uint32, C.POINTER(MapInfo)]
     L.gm_download_map.argtypes = [vp, C.c_uint32, C.POINTER(MapInfo), vp, vp, C.c_uint32]
+    L.gm_upload_map.argtypes = [vp, C.c_uint32, C.POINTER(MapInfo), vp, vp, C.c_uint32]
     L.gm_map_digest.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
     L.gm_export_occupancy.argtypes = [vp, C.c_uint32, C.c_double, vp, C.c_uint32, C.c_uint32]
     L.gm_optimize.argtypes = [vp, C.c_uint32, up, dp, dp, dp, dp]

@@ -225,8 +225,8 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
                  dir_at(M, fx0 >> kPatchMag, fy0 >> kPatchMag) < 0) fcheck = false;
         // occupied cells in ascending bit order == the reference's xx-outer / yy-inner scan order
         if (!fcheck) {
-            // two cells per trip: their load -> distance chains are independent and overlap; the comparisons still run in
-            // scan order (i before j), so ties resolve as in the reference
+            // three cells per trip (a wall in the window is usually three to six cells): their load -> distance chains are
+            // independent and overlap; the comparisons still run in scan order, so ties resolve as in the reference
             auto pair_loop = [&](auto cell) {
                 while (mask) {
                     const int i = __ffs(mask) - 1;
@@ -234,11 +234,15 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
                     const bool two = mask != 0;
                     const int j = two ? __ffs(mask) - 1 : i;
                     mask &= mask - 1;  // no-op when mask is already 0
-                    const double2 ma = ldg_d2(M.means + cell(i)), mb = ldg_d2(M.means + cell(j));  // mean(), smmap.h:24
-                    const double ax = phx - ma.x, ay = phy - ma.y, bxx = phx - mb.x, byy = phy - mb.y;
-                    const double na = ax * ax + ay * ay, nb = bxx * bxx + byy * byy;
+                    const bool three = mask != 0;
+                    const int k = three ? __ffs(mask) - 1 : i;
+                    mask &= mask - 1;
+                    const double2 ma = ldg_d2(M.means + cell(i)), mb = ldg_d2(M.means + cell(j)), mc = ldg_d2(M.means + cell(k));  // mean(), smmap.h:24
+                    const double ax = phx - ma.x, ay = phy - ma.y, bxx = phx - mb.x, byy = phy - mb.y, cx = phx - mc.x, cy = phy - mc.y;
+                    const double na = ax * ax + ay * ay, nb = bxx * bxx + byy * byy, nc2 = cx * cx + cy * cy;
                     if (!found || na < bn) { bx = ax; by = ay; bn = na; found = true; }
                     if (two && nb < bn) { bx = bxx; by = byy; bn = nb; }
+                    if (three && nc2 < bn) { bx = cx; by = cy; bn = nc2; }
                 }
             };
             if (fast) pair_loop(cell_of_fast); else pair_loop(cell_of);
