@@ -37,6 +37,13 @@ def check_maps(ctx, f, want_rows, what):
         np.testing.assert_allclose(a1, a2, rtol=1e-6, atol=1e-5, err_msg="%s: acc of particle %d" % (what, j))
 
 
+def test_teacher_forced_trace_with_few_visit_tiles(monkeypatch):
+    """the same trace with half the shared memory for k_register's visit tiles: the active area no longer fits one
+    pass, so the multi-pass ray counting (and the chunked copy-on-write work list) must give the same maps"""
+    monkeypatch.setenv("GM_B200_REGISTER_SMEM_KB", "110")
+    test_teacher_forced_trace("room1081_n8")
+
+
 @pytest.mark.parametrize("case", CASES)
 def test_teacher_forced_trace(case):
     from gpu_common import context_for
