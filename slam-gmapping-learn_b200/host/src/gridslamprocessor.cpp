@@ -443,11 +443,12 @@ bool GridSlamProcessor::processScan(const RangeReading& reading, int adaptPartic
         const double sx = mm.srr * fabs(delta.x) + mm.str * fabs(delta.theta) + sxy * fabs(delta.y);
         const double sy = mm.srr * fabs(delta.y) + mm.str * fabs(delta.theta) + sxy * fabs(delta.x);
         const double st = mm.stt * fabs(delta.theta) + mm.srt * sqrt(delta.x * delta.x + delta.y * delta.y);
+        Drand48Stream draws;  // the drand48() stream, stepped inline for these 3 x N samples
         for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it) {
             OrientedPoint noisy(delta);
-            noisy.x += sampleGaussian(sx);
-            noisy.y += sampleGaussian(sy);
-            noisy.theta += sampleGaussian(st);
+            noisy.x += draws.gaussian(sx);
+            noisy.y += draws.gaussian(sy);
+            noisy.theta += draws.gaussian(st);
             noisy.theta = fmod(noisy.theta, 2 * M_PI);
             if (noisy.theta > M_PI) noisy.theta -= 2 * M_PI;
             it->pose = absoluteSum(it->pose, noisy);

@@ -61,6 +61,20 @@ def test_reference_consumer_compiles_against_our_headers():
         assert sym in out, sym
 
 
+def test_drand48_stream_matches_libc():
+    """the motion model steps the drand48 sequence inline (Drand48Stream): its samples and the state it hands back to
+    libc must be exactly those of drand48() / sampleGaussian()"""
+    import subprocess
+    os.makedirs(os.path.join(ROOT, "tests", "_build"), exist_ok=True)
+    exe = os.path.join(ROOT, "tests", "_build", "drand48_stream_check")
+    host = os.path.join(ROOT, "slam-gmapping-learn_b200", "host")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-I", os.path.join(host, "include"), os.path.join(ROOT, "tests", "drand48_stream_check.cpp"),
+                    os.path.join(host, "src", "utils.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "mismatches 0, next draw equal 1" in out.stdout and "uniform mismatches 0" in out.stdout
+
+
 def test_product_does_not_link_the_oracle():
     out = subprocess.run(["ldd", os.path.join(HOST, "libgridfastslam_b200.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out and "libgm_b200.so" in out
