@@ -19,6 +19,7 @@
 #include <gmapping/utils/point.h>
 
 #include <climits>
+#include <cstddef>
 #include <deque>
 #include <fstream>
 #include <limits>
@@ -37,6 +38,9 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     struct TNode {
         TNode(const OrientedPoint& pose, double weight, TNode* parent = 0, unsigned int childs = 0);
         ~TNode();
+        // B200 build: nodes come from per-thread slabs (one is created per particle and scan; `new` / `delete` work as ever)
+        static void* operator new(std::size_t size);
+        static void operator delete(void* p, std::size_t size) noexcept;
         OrientedPoint pose;
         double weight;
         double accWeight;  // sum of the (normalised) weights of the leaves below this node

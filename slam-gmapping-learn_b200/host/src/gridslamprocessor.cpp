@@ -50,6 +50,43 @@ GridSlamProcessor::TNode::~TNode() {
     assert(!childs);
 }
 
+// slab allocation of trajectory nodes: a free list per thread over slabs that are never returned (a node may be deleted
+// by another thread than the one that made it; it then joins that thread's list)
+namespace {
+struct NodeArena {
+    struct Free { Free* next; };
+    Free* head = nullptr;
+};
+NodeArena& nodeArena() {
+    static thread_local NodeArena* a = new NodeArena;  // leaked on purpose: nodes may be deleted during thread shutdown
+    return *a;
+}
+}  // namespace
+
+void* GridSlamProcessor::TNode::operator new(std::size_t size) {
+    if (size != sizeof(TNode)) return ::operator new(size);
+    NodeArena& a = nodeArena();
+    if (!a.head) {
+        const std::size_t count = 4096, stride = (sizeof(TNode) + 15) & ~(std::size_t)15;
+        char* slab = static_cast<char*>(::operator new(count * stride));
+        for (std::size_t i = 0; i < count; i++) {
+            NodeArena::Free* f = reinterpret_cast<NodeArena::Free*>(slab + (count - 1 - i) * stride);
+            f->next = a.head; a.head = f;
+        }
+    }
+    NodeArena::Free* f = a.head;
+    a.head = f->next;
+    return f;
+}
+
+void GridSlamProcessor::TNode::operator delete(void* p, std::size_t size) noexcept {
+    if (!p) return;
+    if (size != sizeof(TNode)) { ::operator delete(p); return; }
+    NodeArena& a = nodeArena();
+    NodeArena::Free* f = static_cast<NodeArena::Free*>(p);
+    f->next = a.head; a.head = f;
+}
+
 GridSlamProcessor::Particle::Particle(const ScanMatcherMap& m)
     : map(m), pose(0, 0, 0), previousPose(0, 0, 0), weight(0), weightSum(0), gweight(0), previousIndex(0), node(0) {}
 
