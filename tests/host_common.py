@@ -5,6 +5,9 @@ from __future__ import annotations
 import importlib
 import os
 import subprocess
+import tempfile
+
+import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "slam-gmapping-learn_b200")
@@ -42,3 +45,95 @@ def driver_args(p):
     if not p["generate_map"]:
         cmd.append("-no-generateMap")
     return cmd
+
+
+def build_mock():
+    """tests/mock/gm_mock.c + oracle/gm_oracle.c -> tests/_build/libgm_mock.so: the C ABI of include/gm_b200.h implemented on
+    the CPU with the oracle.  TEST INFRASTRUCTURE: preloaded (LD_PRELOAD) into the driver by the CPU tests of the host
+    layer so that GridSlamProcessor's host-side logic runs without a GPU; never part of the product."""
+    os.makedirs(BUILD, exist_ok=True)
+    lib = os.path.join(BUILD, "libgm_mock.so")
+    srcs = [os.path.join(ROOT, "tests", "mock", "gm_mock.c"), os.path.join(ROOT, "oracle", "gm_oracle.c")]
+    deps = srcs + [os.path.join(ROOT, "oracle", "gm_oracle.h"), os.path.join(ROOT, "include", "gm_b200.h")]
+    if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
+        subprocess.check_call(["gcc", "-O2", "-std=c11", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wextra", "-Wno-unused-parameter",
+                               "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "oracle"), "-o", lib] + srcs + ["-lm"])
+    return lib
+
+
+def mock_env():
+    """environment that makes a process using the host layer resolve the gm_* C ABI to the CPU mock"""
+    env = dict(os.environ)
+    env["LD_PRELOAD"] = build_mock()
+    return env
+
+
+def golden_log(g, path):
+    synth = importlib.import_module("slam-gmapping-learn_b200.synth")
+    laser = synth.LaserSpec(g.B, 1.0 if g.B == 181 else 0.25, float(g.ranges.max()))
+    log = synth.SynthLog(laser, g.ranges, g.odom, g.odom, g.stamps, {})
+    synth.write_carmen(log, path)
+
+
+def free_run(case, env=None, extra=()):
+    from common import Golden
+    from oracle.trace import read_trace
+    """the reference-facing driver, linked with our libraries, over a golden log -> (fixture, trace)"""
+    exe = build_driver()
+    g = Golden(case)
+    with tempfile.TemporaryDirectory() as td:
+        lp, tp = os.path.join(td, "in.log"), os.path.join(td, "trace.bin")
+        golden_log(g, lp)
+        cmd = [exe, "-mode", "trace", "-log", lp, "-out", tp, "-probe", "2", "-maps-every", str(g.p["maps_every"])] + driver_args(g.p) + list(extra)
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        assert res.returncode == 0, res.stderr[-2000:]
+        tr = read_trace(tp)
+    return g, tr
+
+
+def check_trace(case, g, tr, exact=False):
+    from common import digest_rows
+    """trace of the driver linked with our libraries against the golden trace of the unmodified reference.  exact=True (CPU
+    mock of the C ABI, whose arithmetic is the oracle's): floating-point results must be the reference's bit for bit."""
+    ptol, rtol3, rtol6, rtol4 = (0.0, 0.0, 0.0, 0.0) if exact else (1e-4, 1e-3, 1e-6, 1e-4)
+    R = tr["readings"]
+    assert len(R) == g.S
+    assert np.allclose(tr["angles"], g.angles, rtol=0, atol=0)
+    k_dig = 0
+    dig_scans = list(g.dig_scan)
+    for i, r in enumerate(R):
+        assert np.array_equal(r["ranges"], g.ranges[i])
+        assert r["processed"] == bool(g.processed[i]), "%s[%d] gate" % (case, i)
+        assert np.abs(r["pre_pose"] - g.pre_pose[i]).max() <= ptol, "%s[%d] motion-model poses" % (case, i)
+        if not r["processed"]:
+            continue
+        assert r["resampled"] == bool(g.resampled[i]), "%s[%d] resample decision" % (case, i)
+        if "smat" in r:
+            ref = g.smat[i]
+            assert np.abs(r["smat"][:, 10:13] - ref[:, 10:13]).max() <= ptol, "%s[%d] scan-matched poses" % (case, i)
+            np.testing.assert_allclose(r["smat"][:, 8], ref[:, 8], rtol=rtol3, err_msg="%s[%d] log-likelihood" % (case, i))
+            np.testing.assert_allclose(r["smat"][:, 3], ref[:, 3], rtol=rtol6, err_msg="%s[%d] optimize score via m_matcher" % (case, i))
+            np.testing.assert_allclose(r["probes"][:, 4:7], g.probes[i][:len(r["probes"]), 4:7], rtol=rtol6, atol=0 if exact else 1e-9)
+            # ScanMatcher::likelihood(lmax, mean, cov, ...) and optimize(mean, cov, ...) on particle 0's map
+            np.testing.assert_allclose(r["like"][:5], g.like[i][:5], rtol=rtol6, atol=0 if exact else 1e-9, err_msg="%s[%d] likelihood()" % (case, i))
+            np.testing.assert_allclose(r["like"][5:11], g.like[i][5:11], rtol=rtol4, atol=0 if exact else 1e-12, err_msg="%s[%d] likelihood() covariance" % (case, i))
+            np.testing.assert_allclose(r["like"][11:15], g.like[i][11:15], rtol=rtol6, atol=0 if exact else 1e-9, err_msg="%s[%d] optimize(mean, cov)" % (case, i))
+            np.testing.assert_allclose(r["like"][15:21], g.like[i][15:21], rtol=rtol4, atol=0 if exact else 1e-12, err_msg="%s[%d] optimize(mean, cov) covariance" % (case, i))
+        if r["resampled"]:
+            assert np.array_equal(r["indexes"], g.ridx[i]), "%s[%d] resample indexes" % (case, i)
+            np.testing.assert_allclose(r["neff_at_resample"], g.rneff[i], rtol=rtol6)
+        st = r["state"]
+        assert np.abs(st[:, :3] - g.state[i][:, :3]).max() <= ptol, "%s[%d] poses" % (case, i)
+        np.testing.assert_allclose(st[:, 3:5], g.state[i][:, 3:5], rtol=rtol3, atol=0 if exact else 1e-6, err_msg="%s[%d] weight / weightSum" % (case, i))
+        assert np.array_equal(st[:, 5], g.state[i][:, 5]), "%s[%d] previousIndex" % (case, i)
+        np.testing.assert_allclose(r["neff"], g.neff[i], rtol=rtol6)
+        if "digests" in r and i in dig_scans:
+            k = dig_scans.index(i)
+            got, want = digest_rows(r["digests"]), digest_rows(g.digests[k])
+            assert np.array_equal(got[:, :5], want[:, :5]), "%s[%d] integer map digests through the host mirror" % (case, i)
+            assert np.array_equal(r["geometry"], g.geometry[k]), "%s[%d] map geometry" % (case, i)
+            k_dig += 1
+    fin = tr["final"]
+    assert np.array_equal(digest_rows(fin["digests"])[:, :5], digest_rows(g.digests[-1])[:, :5])
+    assert fin["best"] == int(g.best)
+    assert k_dig >= 1

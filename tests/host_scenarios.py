@@ -1,0 +1,154 @@
+"""Scenarios of the C++ host layer driven through slam-gmapping-learn_b200/hostapi.py (ctypes view of GridSlamProcessor) and the
+gfs_b200 CLI.  The `-m gpu` tests of tests/test_host_layer.py call them in process on the B200; tests/test_host_layer_cpu.py
+runs this file in a subprocess with the CPU mock of the C ABI preloaded (tests/mock/gm_mock.c), where everything the host
+layer computes itself must still match the unmodified reference's trace.
+
+    python tests/host_scenarios.py clone | order | cli | long[:SCANS]
+"""
+import ctypes
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, HERE):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from common import Golden, digest_rows  # noqa: E402
+from host_common import HOST, build_host, golden_log  # noqa: E402
+
+synth = importlib.import_module("slam-gmapping-learn_b200.synth")
+
+
+def scenario_cli():
+    build_host()
+    g = Golden("room181_resize")
+    with tempfile.TemporaryDirectory() as td:
+        lp, gp = os.path.join(td, "in.log"), os.path.join(td, "out.gfs")
+        golden_log(g, lp)
+        res = subprocess.run([os.path.join(HOST, "gfs_b200"), "-filename", lp, "-outfilename", gp, "-particles", "12", "-randseed", "12345",
+                              "-xmin", "-4", "-ymin", "-4", "-xmax", "4", "-ymax", "4"], capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stderr[-2000:]
+        info = json.loads(res.stdout.strip().splitlines()[-1])
+        assert info["processed"] == int(g.processed.sum()) and info["read"] == g.S
+        txt = open(gp).read()
+        for tag in ("ODOM ", "ODO_UPDATE 12 ", "FRAME ", "LASER_READING 181 ", "SM_UPDATE 12 ", "NEFF "):
+            assert tag in txt, tag
+        neff = [float(l.split()[1]) for l in txt.splitlines() if l.startswith("NEFF")]
+        want = g.neff[g.processed & ~np.isnan(g.smat[:, 0, 0])]
+        # the .gfs NEFF record is written before resampling: compare with the reference where no resample happened
+        assert len(neff) == len(want)
+
+
+def scenario_clone():
+    """GridSlamProcessor::clone() (gridslamprocessor.cpp:38-97): the copy, fed the same readings and the same drand48
+    stream, stays bit-identical to the original -- poses, weights, resample indexes and every particle map."""
+    build_host()
+    hostapi = importlib.import_module("slam-gmapping-learn_b200.hostapi")
+    libc = ctypes.CDLL("libc.so.6")
+    libc.seed48.restype = ctypes.POINTER(ctypes.c_ushort * 3)
+    g = Golden("room181_n30")
+    p = g.p
+    a = hostapi.Processor(g.angles, p["particles"], g.head_init, bounds=(p["xmin"], p["ymin"], p["xmax"], p["ymax"]), delta=p["delta"], seed=p["seed"],
+                          **{k: p[k] for k in hostapi.PARAM_ORDER})
+    for i in range(12):
+        a.process_scan(g.ranges[i], g.odom[i], g.stamps[i])
+    b = a.clone()
+    assert np.array_equal(a.state(), b.state()) and np.array_equal(a.map_digests(), b.map_digests())
+    saved = (ctypes.c_ushort * 3)(*libc.seed48((ctypes.c_ushort * 3)(0, 0, 0)).contents)  # read the drand48 state ...
+    libc.seed48(saved)                                                                      # ... and put it back
+    for i in range(12, 24):
+        a.process_scan(g.ranges[i], g.odom[i], g.stamps[i])
+    resampled = a.resamples()
+    libc.seed48(saved)
+    for i in range(12, 24):
+        b.process_scan(g.ranges[i], g.odom[i], g.stamps[i])
+    assert np.array_equal(a.state(), b.state()), "clone diverged"
+    assert np.array_equal(a.map_digests(), b.map_digests())
+    assert b.resamples() == resampled and a.neff() == b.neff()
+    assert np.abs(a.state()[:, :3] - g.state[23][:, :3]).max() < 1e-4  # and both still follow the reference
+    # occupancy grid of the best particle through the C++ API
+    grid, origin = a.occupancy_grid(a.best(), 0.25)
+    assert grid.shape == (4000, 4000) and abs(origin[0] + 100.0) < 1e-9 and abs(origin[1] + 100.0) < 1e-9
+    assert (grid == 100).sum() > 200 and (grid == 0).sum() > 20000 and (grid == -1).sum() > 15000000
+    x, y = g.state[23][a.best(), 0], g.state[23][a.best(), 1]
+    assert grid[int(round((y + 100) / 0.05)), int(round((x + 100) / 0.05))] == 0  # the robot stands in free space
+    assert a.occupancy(a.best(), x, y) < 0.1
+    a.close(); b.close()
+
+
+def scenario_order():
+    """setearlyRegistration(false) keeps the reference's order (copy the resampled particles, then register the scan in
+    every child); the default registers first and copies afterwards.  Same drand48 stream in, bit-identical filter out:
+    poses, weights, resample indexes, every map -- and both follow the reference trace."""
+    build_host()
+    hostapi = importlib.import_module("slam-gmapping-learn_b200.hostapi")
+    g = Golden("room181_k2_lskip")
+    p = g.p
+    runs = []
+    for early in (True, False):
+        a = hostapi.Processor(g.angles, p["particles"], g.head_init, bounds=(p["xmin"], p["ymin"], p["xmax"], p["ymax"]), delta=p["delta"],
+                              seed=p["seed"], early_registration=early, **{k: p[k] for k in hostapi.PARAM_ORDER})
+        idx = []
+        for i in range(len(g.ranges)):
+            a.process_scan(g.ranges[i], g.odom[i], g.stamps[i])
+            if a.last_resampled():
+                idx.append(a.indexes().copy())
+        runs.append((a.state(), a.map_digests(), a.resamples(), a.neff(), idx))
+        a.close()
+    (s0, d0, r0, n0, i0), (s1, d1, r1, n1, i1) = runs
+    assert r0 == r1 and r0 > 0 and n0 == n1
+    assert np.array_equal(s0, s1) and np.array_equal(d0, d1)
+    assert len(i0) == len(i1) and all(np.array_equal(x, y) for x, y in zip(i0, i1))
+    assert np.abs(s0[:, :3] - g.state[len(g.ranges) - 1][:, :3]).max() < 1e-4
+
+
+def scenario_long(limit=None):
+    """BASELINE.json configs[0]/[1]: 30 particles, 181-beam scans, 1000 scans, free running through the C++ API against the
+    unmodified reference (fixture: Neff and flags for every scan, all poses / log-weights every 10th scan): the filter never
+    leaves the reference's trajectory -- same resampling scans, same indexes, poses within 1e-4, log-weights within 1e-3."""
+    build_host()
+    hostapi = importlib.import_module("slam-gmapping-learn_b200.hostapi")
+    z = np.load(os.path.join(ROOT, "tests", "golden", "room181_long.npz"))
+    p = json.loads(str(z["params"]))
+    log = synth.make_log("room", synth.LMS200, scans=int(z["scans"]), step=0.25, seed=int(z["log_seed"]))
+    assert np.array_equal(log.laser.angles(), z["angles"])
+    f = hostapi.Processor(z["angles"], p["particles"], z["head_init"], bounds=(p["xmin"], p["ymin"], p["xmax"], p["ymax"]), delta=p["delta"],
+                          seed=p["seed"], **{k: p[k] for k in hostapi.PARAM_ORDER})
+    kept = {int(s): k for k, s in enumerate(z["kept"])}
+    rsc = {int(s): k for k, s in enumerate(z["ridx_scans"])}
+    worst_pose = worst_w = 0.0
+    scans = int(z["scans"]) if limit is None else min(int(limit), int(z["scans"]))
+    for i in range(scans):
+        done = f.process_scan(log.ranges[i], log.odom[i], log.stamps[i])
+        assert done == bool(z["processed"][i])
+        assert f.last_resampled() == bool(z["resampled"][i]), "scan %d: resampling decision" % i
+        assert abs(f.neff() - z["neff"][i]) <= 1e-6 * z["neff"][i], "scan %d: Neff" % i
+        if i in rsc:
+            assert np.array_equal(f.indexes(), z["ridx"][rsc[i]]), "scan %d: resample indexes" % i
+        if i in kept:
+            st = f.state(); k = kept[i]
+            worst_pose = max(worst_pose, float(np.abs(st[:, :3] - z["poses"][k]).max()))
+            worst_w = max(worst_w, float(np.abs(st[:, 3:5] - z["weights"][k]).max() / max(1.0, np.abs(z["weights"][k]).max())))
+            assert np.array_equal(st[:, 5], z["prev"][k])
+    assert worst_pose < 1e-4 and worst_w < 1e-3, (worst_pose, worst_w)
+    if scans == int(z["scans"]):
+        d = f.map_digests()
+        assert np.array_equal(d[:, :5], digest_rows(z["digests"])[:, :5]), "final maps: (n, visits) of every cell of every particle"
+        assert f.best() == int(z["best"])
+    f.close()
+    return worst_pose, worst_w
+
+
+if __name__ == "__main__":
+    name, _, arg = sys.argv[1].partition(":")
+    fn = {"cli": scenario_cli, "clone": scenario_clone, "order": scenario_order, "long": scenario_long}[name]
+    out = fn(int(arg)) if arg else fn()
+    print("scenario %s ok %s" % (sys.argv[1], "" if out is None else out))

@@ -1,0 +1,367 @@
+/* tests/mock/gm_mock.c -- TEST INFRASTRUCTURE, NOT PRODUCT.
+ *
+ * A stand-in for libgm_b200.so that implements the C ABI of include/gm_b200.h on the CPU with the oracle
+ * (oracle/gm_oracle.c), so that the C++ host layer (slam-gmapping-learn_b200/host: GridSlamProcessor::processScan's
+ * orchestration, the trajectory tree, the host map mirror, the .gfs trace, ScanMatcher's standalone entry points) can be
+ * exercised by the `-m "not gpu"` tests on a machine without a GPU.  It is built into tests/_build/libgm_mock.so and
+ * injected with LD_PRELOAD by tests/test_host_layer_cpu.py only; nothing under slam-gmapping-learn_b200/ knows it exists
+ * and the product library still refuses to run without a CUDA device.
+ *
+ * Semantics follow the comments of include/gm_b200.h; the multi-GPU entry points are not mocked (they fail loudly).
+ */
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "gm_b200.h"
+#include "gm_oracle.h"
+
+struct gm_ctx {
+    uint32_t max_particles, n, weights_cap;
+    orc_matcher sm;
+    int laser_set, match_set, inited;
+    orc_map** maps; /* [max_particles] */
+    gm_stats stats;
+    char err[256];
+};
+
+static char g_create_err[256] = "";
+
+static int fail(gm_ctx* c, int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c ? c->err : g_create_err, 256, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+const char* gm_last_error(const gm_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+
+void gm_default_matching(gm_match_params* p) {
+    orc_matcher m;
+    orc_matcher_defaults(&m);
+    memset(p, 0, sizeof *p);
+    p->laser_max_range = m.laser_max_range; p->usable_range = m.usable_range;
+    p->gaussian_sigma = m.gaussian_sigma; p->likelihood_sigma = m.likelihood_sigma;
+    p->kernel_size = m.kernel_size; p->generate_map = m.generate_map;
+    p->opt_linear_delta = m.opt_linear_delta; p->opt_angular_delta = m.opt_angular_delta;
+    p->opt_recursive_iterations = m.opt_recursive_iterations; p->likelihood_skip = m.likelihood_skip;
+    p->enlarge_step = m.enlarge_step; p->fullness_threshold = m.fullness_threshold;
+    p->angular_odometry_reliability = m.angular_odometry_reliability; p->linear_odometry_reliability = m.linear_odometry_reliability;
+    p->free_cell_ratio = m.free_cell_ratio; p->initial_beams_skip = m.initial_beams_skip;
+}
+
+int gm_create(gm_ctx** out, const gm_config* cfg) {
+    if (!out || !cfg || !cfg->max_particles) return fail(NULL, GM_ERR_ARG, "gm_create: bad argument");
+    gm_ctx* c = (gm_ctx*)calloc(1, sizeof *c);
+    c->max_particles = cfg->max_particles;
+    c->weights_cap = cfg->global_particles > cfg->max_particles ? cfg->global_particles : cfg->max_particles;
+    c->maps = (orc_map**)calloc(c->max_particles, sizeof(orc_map*));
+    orc_matcher_defaults(&c->sm);
+    c->stats.pool_capacity = cfg->pool_patches;
+    *out = c;
+    return GM_OK;
+}
+
+static void drop_maps(gm_ctx* c) {
+    for (uint32_t i = 0; i < c->max_particles; i++) { orc_map_free(c->maps[i]); c->maps[i] = NULL; }
+}
+
+int gm_destroy(gm_ctx* c) {
+    if (!c) return GM_ERR_ARG;
+    drop_maps(c);
+    free(c->maps);
+    free(c);
+    return GM_OK;
+}
+
+int gm_set_laser(gm_ctx* c, uint32_t nbeams, const double* angles, const double laser_pose[3]) {
+    if (!c) return GM_ERR_ARG;
+    if (!angles || !laser_pose) return fail(c, GM_ERR_ARG, "gm_set_laser: null argument");
+    if (nbeams == 0 || nbeams >= GM_MAXBEAMS) return fail(c, GM_ERR_ARG, "gm_set_laser: %u beams (must be in [1, %d))", nbeams, GM_MAXBEAMS);
+    c->sm.beams = nbeams;
+    memcpy(c->sm.angles, angles, sizeof(double) * nbeams);
+    memcpy(c->sm.laser_pose, laser_pose, sizeof(double) * 3);
+    c->laser_set = 1;
+    return GM_OK;
+}
+
+int gm_set_matching(gm_ctx* c, const gm_match_params* p) {
+    if (!c) return GM_ERR_ARG;
+    if (!p) return fail(c, GM_ERR_ARG, "gm_set_matching: null argument");
+    if (p->kernel_size < 0 || p->kernel_size > 8) return fail(c, GM_ERR_ARG, "gm_set_matching: kernel_size %d outside [0,8]", p->kernel_size);
+    orc_matcher* m = &c->sm;
+    m->laser_max_range = p->laser_max_range; m->usable_range = p->usable_range;
+    m->gaussian_sigma = p->gaussian_sigma; m->likelihood_sigma = p->likelihood_sigma;
+    m->kernel_size = p->kernel_size; m->generate_map = p->generate_map;
+    m->opt_linear_delta = p->opt_linear_delta; m->opt_angular_delta = p->opt_angular_delta;
+    m->opt_recursive_iterations = p->opt_recursive_iterations; m->likelihood_skip = p->likelihood_skip;
+    m->enlarge_step = p->enlarge_step; m->fullness_threshold = p->fullness_threshold;
+    m->angular_odometry_reliability = p->angular_odometry_reliability; m->linear_odometry_reliability = p->linear_odometry_reliability;
+    m->free_cell_ratio = p->free_cell_ratio; m->initial_beams_skip = p->initial_beams_skip;
+    c->match_set = 1;
+    return GM_OK;
+}
+
+int gm_init_particles(gm_ctx* c, uint32_t n, const double center[2], double world_w, double world_h, double delta) {
+    if (!c) return GM_ERR_ARG;
+    if (!center || !n || n > c->max_particles || !(delta > 0)) return fail(c, GM_ERR_ARG, "gm_init_particles: bad argument (n=%u, max=%u)", n, c->max_particles);
+    drop_maps(c);
+    for (uint32_t i = 0; i < n; i++) c->maps[i] = orc_map_new(center[0], center[1], world_w, world_h, delta);
+    if (c->maps[0]->npx <= 0 || c->maps[0]->npy <= 0) { drop_maps(c); return fail(c, GM_ERR_ARG, "gm_init_particles: map smaller than one patch"); }
+    c->n = n;
+    c->inited = 1;
+    return GM_OK;
+}
+
+uint32_t gm_particles(const gm_ctx* c) { return c ? c->n : 0; }
+
+static int ready(gm_ctx* c) {
+    if (!c) return GM_ERR_ARG;
+    if (!c->inited) return fail(c, GM_ERR_ARG, "gm_init_particles has not been called");
+    if (!c->laser_set) return fail(c, GM_ERR_ARG, "gm_set_laser has not been called");
+    if (!c->match_set) return fail(c, GM_ERR_ARG, "gm_set_matching has not been called");
+    return GM_OK;
+}
+
+static int check_idx(gm_ctx* c, uint32_t count, const uint32_t* idx) {
+    for (uint32_t i = 0; i < count; i++)
+        if (idx[i] >= c->n) return fail(c, GM_ERR_ARG, "eval: particle index %u >= %u", idx[i], c->n);
+    return GM_OK;
+}
+
+int gm_score(gm_ctx* c, uint32_t count, const uint32_t* idx, const double* poses, const double* ranges, double* score_out) {
+    int r = ready(c);
+    if (r) return r;
+    if (!count) return GM_OK;
+    if (!idx || !poses || !ranges) return fail(c, GM_ERR_ARG, "eval: null argument");
+    if ((r = check_idx(c, count, idx))) return r;
+    for (uint32_t i = 0; i < count; i++) {
+        double s = orc_score(&c->sm, c->maps[idx[i]], poses + 3 * i, ranges);
+        if (score_out) score_out[i] = s;
+    }
+    return GM_OK;
+}
+
+int gm_likelihood_and_score(gm_ctx* c, uint32_t count, const uint32_t* idx, const double* poses, const double* ranges,
+                            double* s_out, double* l_out, uint32_t* c_out) {
+    int r = ready(c);
+    if (r) return r;
+    if (!count) return GM_OK;
+    if (!idx || !poses || !ranges) return fail(c, GM_ERR_ARG, "eval: null argument");
+    if ((r = check_idx(c, count, idx))) return r;
+    for (uint32_t i = 0; i < count; i++) {
+        double s, l;
+        uint32_t k = orc_likelihood_and_score(&c->sm, c->maps[idx[i]], poses + 3 * i, ranges, &s, &l);
+        if (s_out) s_out[i] = s;
+        if (l_out) l_out[i] = l;
+        if (c_out) c_out[i] = k;
+    }
+    return GM_OK;
+}
+
+int gm_optimize(gm_ctx* c, uint32_t count, const uint32_t* idx, const double* poses_in, const double* ranges, double* poses_out,
+                double* score_out) {
+    int r = ready(c);
+    if (r) return r;
+    if (!count) return GM_OK;
+    if (!idx || !poses_in || !ranges) return fail(c, GM_ERR_ARG, "eval: null argument");
+    if ((r = check_idx(c, count, idx))) return r;
+    for (uint32_t i = 0; i < count; i++) {
+        double out[3];
+        double s = orc_optimize(&c->sm, c->maps[idx[i]], poses_in + 3 * i, ranges, out);
+        if (poses_out) memcpy(poses_out + 3 * i, out, sizeof out);
+        if (score_out) score_out[i] = s;
+    }
+    return GM_OK;
+}
+
+int gm_scanmatch(gm_ctx* c, const double* ranges, double* poses, double minimum_score, double* score_out, double* s_out,
+                 double* l_out, uint32_t* c_out, uint32_t* evals_out) {
+    int r = ready(c);
+    if (r) return r;
+    if (!ranges || !poses) return fail(c, GM_ERR_ARG, "gm_scanmatch: null argument");
+    const uint64_t calls0 = c->sm.score_calls, beams0 = c->sm.beam_evals;
+    for (uint32_t i = 0; i < c->n; i++) {
+        double corrected[3], s, l;
+        const uint64_t k0 = c->sm.score_calls;
+        const double score = orc_optimize(&c->sm, c->maps[i], poses + 3 * i, ranges, corrected);
+        if (evals_out) evals_out[i] = (uint32_t)(c->sm.score_calls - k0);
+        if (score > minimum_score) memcpy(poses + 3 * i, corrected, sizeof corrected);
+        const uint32_t k = orc_likelihood_and_score(&c->sm, c->maps[i], poses + 3 * i, ranges, &s, &l);
+        if (score_out) score_out[i] = score;
+        if (s_out) s_out[i] = s;
+        if (l_out) l_out[i] = l;
+        if (c_out) c_out[i] = k;
+    }
+    c->stats.score_evals = c->sm.score_calls - calls0; c->stats.beam_evals = c->sm.beam_evals - beams0;
+    c->stats.total_score_evals += c->stats.score_evals; c->stats.total_beam_evals += c->stats.beam_evals;
+    c->stats.total_scanmatches++;
+    return GM_OK;
+}
+
+int gm_normalize_neff(gm_ctx* c, const double* logw, uint32_t n, double gain, double* w_out, double* neff_out) {
+    if (!c) return GM_ERR_ARG;
+    if (!c->inited) return fail(c, GM_ERR_ARG, "gm_init_particles has not been called");
+    if (!logw || !n || n > c->weights_cap) return fail(c, GM_ERR_ARG, "gm_normalize_neff: bad argument");
+    double* w = (double*)malloc(sizeof(double) * n);
+    const double neff = orc_normalize(logw, n, gain, w);
+    if (w_out) memcpy(w_out, w, sizeof(double) * n);
+    if (neff_out) *neff_out = neff;
+    free(w);
+    return GM_OK;
+}
+
+int gm_resample_indexes(gm_ctx* c, const double* w, uint32_t n, double u01, uint32_t* idx_out, uint32_t* emitted_out) {
+    if (!c) return GM_ERR_ARG;
+    if (!c->inited) return fail(c, GM_ERR_ARG, "gm_init_particles has not been called");
+    if (!w || !idx_out || !n || n > c->weights_cap) return fail(c, GM_ERR_ARG, "gm_resample_indexes: bad argument");
+    const uint32_t k = orc_resample_indexes(w, n, u01, idx_out);
+    if (emitted_out) *emitted_out = k;
+    return GM_OK;
+}
+
+static int remap(gm_ctx* c, const uint32_t* idx) {
+    for (uint32_t j = 0; j < c->n; j++)
+        if (idx[j] >= c->n) return fail(c, GM_ERR_ARG, "remap: parent index %u >= %u", idx[j], c->n);
+    orc_map** next = (orc_map**)calloc(c->n, sizeof(orc_map*));
+    for (uint32_t j = 0; j < c->n; j++) next[j] = orc_map_clone(c->maps[idx[j]]);
+    for (uint32_t j = 0; j < c->n; j++) { orc_map_free(c->maps[j]); c->maps[j] = next[j]; }
+    free(next);
+    return GM_OK;
+}
+
+int gm_copy_particles(gm_ctx* c, const uint32_t* idx) {
+    int r = ready(c);
+    if (r) return r;
+    if (!idx) return fail(c, GM_ERR_ARG, "gm_copy_particles: null argument");
+    return remap(c, idx);
+}
+
+int gm_register(gm_ctx* c, const double* ranges, const double* poses, const uint32_t* idx) {
+    int r = ready(c);
+    if (r) return r;
+    if (!ranges || !poses) return fail(c, GM_ERR_ARG, "gm_register: null argument");
+    if (idx && (r = remap(c, idx))) return r;
+    for (uint32_t i = 0; i < c->n; i++) {
+        orc_compute_active_area(&c->sm, c->maps[i], poses + 3 * i, ranges);
+        orc_register_scan(&c->sm, c->maps[i], poses + 3 * i, ranges);
+    }
+    c->stats.total_registers++;
+    return GM_OK;
+}
+
+int gm_compute_active_area(gm_ctx* c, const double* ranges, const double* poses) {
+    int r = ready(c);
+    if (r) return r;
+    if (!ranges || !poses) return fail(c, GM_ERR_ARG, "gm_compute_active_area: null argument");
+    for (uint32_t i = 0; i < c->n; i++) orc_compute_active_area(&c->sm, c->maps[i], poses + 3 * i, ranges);
+    return GM_OK;
+}
+
+int gm_upload_map(gm_ctx* c, uint32_t particle, const gm_map_info* info, const int32_t* coords, const gm_cell* cells, uint32_t npatches) {
+    int r = ready(c);
+    if (r) return r;
+    if (particle >= c->n || !info || (npatches && (!coords || !cells))) return fail(c, GM_ERR_ARG, "gm_upload_map: bad argument");
+    if (info->patches_x <= 0 || info->patches_y <= 0) return fail(c, GM_ERR_ARG, "gm_upload_map: empty directory");
+    for (uint32_t k = 0; k < npatches; k++)
+        if (coords[2 * k] < 0 || coords[2 * k] >= info->patches_x || coords[2 * k + 1] < 0 || coords[2 * k + 1] >= info->patches_y)
+            return fail(c, GM_ERR_ARG, "gm_upload_map: patch (%d,%d) outside the %dx%d directory", coords[2 * k], coords[2 * k + 1], info->patches_x, info->patches_y);
+    orc_map* old = c->maps[particle];
+    orc_map* m = (orc_map*)calloc(1, sizeof *m);
+    m->cx = old->cx; m->cy = old->cy; m->delta = old->delta;
+    m->npx = info->patches_x; m->npy = info->patches_y;
+    m->map_w = m->npx << ORC_PATCH_MAG; m->map_h = m->npy << ORC_PATCH_MAG;
+    m->world_w = m->map_w * m->delta; m->world_h = m->map_h * m->delta;
+    m->size_x2 = info->size_x2; m->size_y2 = info->size_y2;
+    const size_t nd = (size_t)m->npx * m->npy;
+    m->dir = (orc_cell**)calloc(nd, sizeof(orc_cell*));
+    m->active = (uint8_t*)calloc(nd, 1);
+    for (uint32_t k = 0; k < npatches; k++) {
+        orc_cell** slot = &m->dir[(size_t)coords[2 * k] * m->npy + coords[2 * k + 1]];
+        if (!*slot) *slot = (orc_cell*)malloc(sizeof(orc_cell) * 1024);
+        memcpy(*slot, cells + (size_t)1024 * k, sizeof(orc_cell) * 1024);
+    }
+    orc_map_free(old);
+    c->maps[particle] = m;
+    return GM_OK;
+}
+
+int gm_download_map(gm_ctx* c, uint32_t particle, gm_map_info* info, int32_t* coords, gm_cell* cells, uint32_t max_patches) {
+    int r = ready(c);
+    if (r) return r;
+    if (particle >= c->n || !info) return fail(c, GM_ERR_ARG, "gm_download_map: bad argument");
+    const orc_map* m = c->maps[particle];
+    info->center_x = m->cx; info->center_y = m->cy; info->delta = m->delta;
+    info->size_x2 = m->size_x2; info->size_y2 = m->size_y2; info->patches_x = m->npx; info->patches_y = m->npy;
+    info->allocated_patches = (int32_t)orc_map_patch_count(m); info->reserved = 0;
+    if (!coords || !cells || !max_patches || !info->allocated_patches) return GM_OK;
+    orc_map_export(m, coords, (orc_cell*)cells, max_patches); /* px-major directory order, gm_cell == orc_cell */
+    return GM_OK;
+}
+
+int gm_map_info_get(gm_ctx* c, uint32_t particle, gm_map_info* info) { return gm_download_map(c, particle, info, NULL, NULL, 0); }
+
+int gm_export_occupancy(gm_ctx* c, uint32_t particle, double occ_thresh, int8_t* out, uint32_t width, uint32_t height) {
+    int r = ready(c);
+    if (r) return r;
+    if (particle >= c->n || !out || !width || !height) return fail(c, GM_ERR_ARG, "gm_export_occupancy: bad argument");
+    const orc_map* m = c->maps[particle];
+    if ((int)width != m->map_w || (int)height != m->map_h)
+        return fail(c, GM_ERR_ARG, "gm_export_occupancy: the map is %d x %d cells, the buffer %u x %u", m->map_w, m->map_h, width, height);
+    for (uint32_t y = 0; y < height; y++)
+        for (uint32_t x = 0; x < width; x++) {
+            const orc_cell* p = m->dir[(size_t)(x >> ORC_PATCH_MAG) * m->npy + (y >> ORC_PATCH_MAG)];
+            int8_t v = -1;
+            if (p) {
+                const orc_cell* a = &p[((x & 31) << ORC_PATCH_MAG) + (y & 31)];
+                if (a->visits) v = ((double)a->n / (double)a->visits > occ_thresh) ? 100 : 0;
+            }
+            out[(size_t)y * width + x] = v;
+        }
+    return GM_OK;
+}
+
+int gm_map_digest(gm_ctx* c, uint32_t first, uint32_t count, gm_digest* out) {
+    int r = ready(c);
+    if (r) return r;
+    if (!out || first + count > c->n) return fail(c, GM_ERR_ARG, "gm_map_digest: bad argument");
+    for (uint32_t i = 0; i < count; i++) {
+        orc_digest d;
+        orc_map_digest(c->maps[first + i], &d);
+        out[i].patches = d.patches; out[i].cells = d.cells; out[i].sum_n = d.sum_n; out[i].sum_visits = d.sum_visits;
+        out[i].hash_counts = d.hash_counts; out[i].hash_acc = d.hash_acc;
+    }
+    return GM_OK;
+}
+
+int gm_clone(gm_ctx* src, gm_ctx** out) {
+    if (!src || !out) return GM_ERR_ARG;
+    gm_ctx* d = (gm_ctx*)calloc(1, sizeof *d);
+    *d = *src;
+    d->maps = (orc_map**)calloc(src->max_particles, sizeof(orc_map*));
+    for (uint32_t i = 0; i < src->n; i++) d->maps[i] = orc_map_clone(src->maps[i]);
+    *out = d;
+    return GM_OK;
+}
+
+int gm_set_async_register(gm_ctx* c, int on) { (void)on; return c ? GM_OK : GM_ERR_ARG; }
+int gm_synchronize(gm_ctx* c) { return c ? GM_OK : GM_ERR_ARG; }
+
+int gm_get_stats(gm_ctx* c, gm_stats* out) {
+    if (!c || !out) return GM_ERR_ARG;
+    uint64_t used = 0;
+    for (uint32_t i = 0; i < c->n; i++) used += (uint64_t)orc_map_patch_count(c->maps[i]);
+    c->stats.pool_in_use = used;
+    *out = c->stats;
+    return GM_OK;
+}
+
+/* ---- multi-GPU: not mocked */
+int gm_dist_unique_id(void* id_out) { (void)id_out; return fail(NULL, GM_ERR_NO_DEVICE, "gm_mock: the multi-GPU entry points are not mocked"); }
+int gm_dist_init(gm_ctx* c, int rank, int world, const void* id) { (void)rank; (void)world; (void)id; return fail(c, GM_ERR_NO_DEVICE, "gm_mock: the multi-GPU entry points are not mocked"); }
+int gm_dist_allgather(gm_ctx* c, const double* local, uint32_t count, double* all) { (void)local; (void)count; (void)all; return fail(c, GM_ERR_NO_DEVICE, "gm_mock: the multi-GPU entry points are not mocked"); }
+int gm_dist_register(gm_ctx* c, const double* ranges, const double* poses, const uint32_t* idx) { (void)ranges; (void)poses; (void)idx; return fail(c, GM_ERR_NO_DEVICE, "gm_mock: the multi-GPU entry points are not mocked"); }
+int gm_dist_copy_particles(gm_ctx* c, const uint32_t* idx) { (void)idx; return fail(c, GM_ERR_NO_DEVICE, "gm_mock: the multi-GPU entry points are not mocked"); }

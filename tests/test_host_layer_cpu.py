@@ -1,0 +1,30 @@
+"""The C++ host layer on a machine WITHOUT a GPU: GridSlamProcessor::processScan's orchestration, the trajectory tree, the
+resample bookkeeping, the host map mirror, ScanMatcher's standalone entry points and the .gfs writer run against
+tests/mock/gm_mock.c -- the C ABI of include/gm_b200.h implemented with the oracle and injected with LD_PRELOAD (test
+infrastructure: the product never loads it, and without the preload it still refuses to run without a CUDA device).
+
+The mock's arithmetic is the oracle's, which is bit-for-bit the reference's, and the host layer's own arithmetic (motion
+model, drand48 stream, weights) restates the reference's: the driver written against the reference's API, linked with our
+host library, must therefore reproduce the golden traces of the unmodified reference EXACTLY (tolerance 0)."""
+import subprocess
+import sys
+
+import pytest
+
+from common import CASES
+from host_common import ROOT, check_trace, free_run, mock_env
+
+import os
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_free_running_trace_is_the_reference_trace_bit_for_bit(case):
+    g, tr = free_run(case, env=mock_env())
+    check_trace(case, g, tr, exact=True)
+
+
+@pytest.mark.parametrize("scenario", ["clone", "order", "cli", "long:120"])
+def test_host_scenarios_on_the_mock(scenario):
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host_scenarios.py"), scenario], capture_output=True, text=True,
+                         timeout=900, env=mock_env())
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-3000:]
