@@ -131,6 +131,18 @@ class TraceProcessor : public GridSlamProcessor {
         w.vec("STAT", st);
         double ne = m_neff; w.rec("NEFF", &ne, 8);
         w.vec("WGTS", m_weights);
+        // trajectory tree as updateTreeWeights left it: per particle, walking node -> root through the public TNode fields:
+        // chain length, the leaf's accWeight, sum of accWeight, position-weighted sum of accWeight, sum of visitCounter, sum of childs
+        std::vector<double> tree;
+        for (auto& p : m_particles) {
+            double depth = 0, sum = 0, wsum = 0, visits = 0, childs = 0;
+            for (const TNode* n = p.node; n; n = n->parent) {
+                depth += 1; sum += n->accWeight; wsum += depth * n->accWeight; visits += n->visitCounter; childs += n->childs;
+            }
+            const double row[6] = {depth, p.node ? p.node->accWeight : 0., sum, wsum, visits, childs};
+            tree.insert(tree.end(), row, row + 6);
+        }
+        w.vec("TREE", tree);
     }
     static MapDigest digest(const ScanMatcherMap& m, std::vector<int32_t>* full) {
         MapDigest d; memset(&d, 0, sizeof d);

@@ -60,6 +60,9 @@ def read_trace(path):
             cur["neff"] = float(np.frombuffer(p, dtype="<f8")[0])
         elif tag == "WGTS":
             cur["weights"] = np.frombuffer(p, dtype="<f8").copy()
+        elif tag == "TREE":
+            # per particle: chain length, leaf accWeight, sum accWeight, position-weighted sum, sum visitCounter, sum childs
+            cur["tree"] = np.frombuffer(p, dtype="<f8").reshape(-1, 6).copy()
         elif tag == "MDIG":
             d = np.frombuffer(p, dtype=DIGEST_DTYPE).copy()
             (cur if cur is not None else final)["digests"] = d

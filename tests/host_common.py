@@ -127,6 +127,10 @@ def check_trace(case, g, tr, exact=False):
         np.testing.assert_allclose(st[:, 3:5], g.state[i][:, 3:5], rtol=rtol3, atol=0 if exact else 1e-6, err_msg="%s[%d] weight / weightSum" % (case, i))
         assert np.array_equal(st[:, 5], g.state[i][:, 5]), "%s[%d] previousIndex" % (case, i)
         np.testing.assert_allclose(r["neff"], g.neff[i], rtol=rtol6)
+        # the trajectory tree as the second updateTreeWeights left it (gridslamprocessor_tree.cpp:235-346): chain lengths, visit
+        # counters and child counts exactly, accumulated weights like the weights they are sums of
+        assert np.array_equal(r["tree"][:, [0, 4, 5]], g.tree[i][:, [0, 4, 5]]), "%s[%d] trajectory tree shape / visit counters" % (case, i)
+        np.testing.assert_allclose(r["tree"][:, 1:4], g.tree[i][:, 1:4], rtol=rtol6, atol=0 if exact else 1e-12, err_msg="%s[%d] TNode::accWeight" % (case, i))
         if "digests" in r and i in dig_scans:
             k = dig_scans.index(i)
             got, want = digest_rows(r["digests"]), digest_rows(g.digests[k])

@@ -82,19 +82,19 @@ def run_case(name, log_kw, par):
     )
     assert a["ranges"].shape == (S, B) and a["pre_pose"].shape == (S, N, 3)
     smat = np.full((S, N, 15), np.nan); probes = np.full((S, 10, 8), np.nan); like = np.full((S, 22), np.nan)
-    state = np.full((S, N, 6), np.nan); neff = np.full(S, np.nan); weights = np.full((S, N), np.nan)
+    state = np.full((S, N, 6), np.nan); neff = np.full(S, np.nan); weights = np.full((S, N), np.nan); tree = np.full((S, N, 6), np.nan)
     ridx = np.zeros((S, N), dtype=np.uint32); rw = np.full((S, N), np.nan); rneff = np.full(S, np.nan)
     dig_scan, digs, geos = [], [], []
     for i, r in enumerate(R):
         if "smat" in r: smat[i] = r["smat"]
         if "probes" in r and len(r["probes"]): probes[i, :len(r["probes"])] = r["probes"]
         if "like" in r: like[i] = r["like"]
-        if "state" in r: state[i] = r["state"]; neff[i] = r["neff"]; weights[i] = r["weights"]
+        if "state" in r: state[i] = r["state"]; neff[i] = r["neff"]; weights[i] = r["weights"]; tree[i] = r["tree"]
         if "indexes" in r: ridx[i] = r["indexes"]; rw[i] = r["w_at_resample"]; rneff[i] = r["neff_at_resample"]
         if "digests" in r: dig_scan.append(i); digs.append(r["digests"]); geos.append(r["geometry"])
     # the driver also dumps all maps after the last reading
     dig_scan.append(S - 1); digs.append(tr["final"]["digests"]); geos.append(tr["final"]["geometry"])
-    a.update(smat=smat, probes=probes, like=like, state=state, neff=neff, weights=weights, ridx=ridx, rw=rw, rneff=rneff,
+    a.update(smat=smat, probes=probes, like=like, state=state, tree=tree, neff=neff, weights=weights, ridx=ridx, rw=rw, rneff=rneff,
              dig_scan=np.array(dig_scan), digests=np.stack(digs), geometry=np.stack(geos),
              best=np.array(tr["final"]["best"]))
     path = os.path.join(GOLD, name + ".npz")
