@@ -411,19 +411,18 @@ void GridSlamProcessor::normalizeIfNeeded() {
 void GridSlamProcessor::updateTreeWeights(bool weightsAlreadyNormalized) {
     if (!weightsAlreadyNormalized) normalizeIfNeeded();
     if (m_lazyTree) { m_treeDirty = true; return; }
-    resetTree();
     propagateWeights();
 }
 
 void GridSlamProcessor::refreshTreeWeights() {
     if (!m_treeDirty || m_weights.size() != m_particles.size()) return;
-    resetTree();
     propagateWeights();
     m_treeDirty = false;
 }
 
 // zero accWeight / visitCounter on every node reachable from a particle (reference: gridslamprocessor_tree.cpp:255-268);
-// the epoch stamp stops each walk at the first ancestor another particle already reset in this pass
+// the epoch stamp stops each walk at the first ancestor another particle already reset in this pass.  propagateWeights()
+// does not need it: it resets each node on its first visit of a pass.
 void GridSlamProcessor::resetTree() {
     m_treeEpoch++;
     for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it)
@@ -434,9 +433,11 @@ void GridSlamProcessor::resetTree() {
         }
 }
 
-// push a leaf's weight towards the root: a node forwards its sum once all of its children have reported
-static double pushUp(GridSlamProcessor::TNode* n, double weight) {
+// push a leaf's weight towards the root: a node forwards its sum once all of its children have reported.  A node seen for
+// the first time in this pass (stale epoch stamp) starts from zero -- the reference's resetTree() folded into the walk.
+static double pushUp(GridSlamProcessor::TNode* n, double weight, unsigned int epoch) {
     while (n) {
+        if (n->epoch != epoch) { n->epoch = epoch; n->visitCounter = 0; n->accWeight = 0; }
         n->visitCounter++;
         n->accWeight += weight;
         assert(n->visitCounter <= n->childs);
@@ -447,14 +448,21 @@ static double pushUp(GridSlamProcessor::TNode* n, double weight) {
     return weight;
 }
 
+// resetTree + propagateWeights of the reference (gridslamprocessor_tree.cpp:255-346) in ONE walk: every node below which a
+// particle lives is reached by this walk (a node waits for all of its children, and every child subtree ends in leaves that
+// report), in the same order and with the same additions as the reference's second pass, so accWeight / visitCounter end
+// up bit-identical; the separate zeroing pass over every ancestry chain (half of the pointer chasing) is gone.
 double GridSlamProcessor::propagateWeights() {
+    const unsigned int epoch = ++m_treeEpoch;
     double rootWeight = 0, leafSum = 0;
     for (size_t i = 0; i < m_particles.size(); i++) {
         const double w = m_weights[i];
         leafSum += w;
         TNode* n = m_particles[i].node;
+        n->epoch = epoch;
+        n->visitCounter = 0;
         n->accWeight = w;
-        rootWeight += pushUp(n->parent, n->accWeight);
+        rootWeight += pushUp(n->parent, n->accWeight, epoch);
     }
     if (fabs(leafSum - 1.0) > 0.0001 || fabs(rootWeight - 1.0) > 0.0001) {
         std::cerr << "ERROR: root->accWeight=" << rootWeight << "    sum_leaf_weights=" << leafSum << endl;
@@ -565,7 +573,7 @@ bool GridSlamProcessor::processScan(const RangeReading& reading, int adaptPartic
             // observed before the second updateTreeWeights below through onResampleUpdate(), i.e. when the filter resamples --
             // otherwise it is skipped here and the second call, which recomputes every node, does it once
             normalizeIfNeeded();
-            if (m_neff < m_resampleThreshold * m_particles.size() && !m_lazyTree) { resetTree(); propagateWeights(); }
+            if (m_neff < m_resampleThreshold * m_particles.size() && !m_lazyTree) propagateWeights();
             m_hostMs[2] += sw.lap();
             if (m_infoStream) m_infoStream << "neff= " << m_neff << endl;
             if (m_outputStream.is_open()) {
