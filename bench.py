@@ -43,6 +43,7 @@ BYTES_PER_BEAM_EVAL = 144  # (2k+1)^2 x 16 B at kernelSize 1
 # summarised in profiles/r01_summary.md section 4 (0.51 GB + 0.40 GB); scaled with the particles per GPU
 KERNEL_TRAFFIC_BYTES = 0.91e9
 PATCH_BYTES = 16384 + 4096 + 16384 + 128  # cells + visit counters + means + occupancy bitmap of one 32 x 32 patch
+CPU_BASELINE_PARTICLES = 48  # bounded sample of the cpu_baseline leg: ~12 s of single-core reference work over the bench's scans
 PARAMS = dict(maxrange=30.0, maxUrange=29.0, sigma=0.05, kernelSize=1, lstep=0.05, astep=0.05, iterations=5, lsigma=0.075,
               ogain=3.0, lskip=0, srr=0.01, srt=0.01, str=0.01, stt=0.01, resampleThreshold=0.5, delta=0.05,
               xmin=-100.0, ymin=-100.0, xmax=100.0, ymax=100.0)
@@ -254,12 +255,12 @@ def main():
             with tempfile.TemporaryDirectory() as td:
                 ns = min(1 + W + K, 40)
                 lp = os.path.join(td, "bench.log"); synth.write_carmen(synth.make_log("room", synth.UTM30, scans=ns, step=0.25, seed=1), lp)
-                r = run_cpu_reference(16, ns, 1, lp)
+                r = run_cpu_reference(CPU_BASELINE_PARTICLES, ns, 1, lp)
             if r is not None:
                 rate, ms, wall = r
                 line["cpu_baseline"] = {"value": rate / n, "unit": "scans/s", "cores": 1, "kind": "reference",
-                                        "sample": "unmodified reference, 16 particles x %d matched scans of the same log on 1 core "
-                                                  "(%.0f ms per scan, %.1f s wall), scaled linearly to %d particles" % (ns - 1, ms, wall, n)}
+                                        "sample": "unmodified reference, %d particles x %d matched scans of the same log on 1 core "
+                                                  "(%.0f ms per scan, %.1f s wall), scaled linearly to %d particles" % (CPU_BASELINE_PARTICLES, ns - 1, ms, wall, n)}
         print(json.dumps(line))
     proc.close()
     if dist is not None:
