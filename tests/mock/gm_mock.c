@@ -7,13 +7,17 @@
  * injected with LD_PRELOAD by tests/test_host_layer_cpu.py only; nothing under slam-gmapping-learn_b200/ knows it exists
  * and the product library still refuses to run without a CUDA device.
  *
- * Semantics follow the comments of include/gm_b200.h; the multi-GPU entry points are not mocked (they fail loudly).
+ * Semantics follow the comments of include/gm_b200.h.  The multi-rank entry points (gm_dist_*) exchange through files in
+ * $GM_MOCK_DIST_DIR, one process per rank: enough to run the sharded host logic of two ranks on one CPU box.
  */
+#define _DEFAULT_SOURCE /* usleep */
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "gm_b200.h"
 #include "gm_oracle.h"
@@ -25,6 +29,9 @@ struct gm_ctx {
     orc_map** maps; /* [max_particles] */
     gm_stats stats;
     char err[256];
+    struct dist_state* dist; /* multi-rank runs: see the end of this file */
+    uint8_t *dist_sent_prev, *dist_sent_prev2;
+    unsigned long dist_seq_prev, dist_seq_prev2;
 };
 
 static char g_create_err[256] = "";
@@ -339,6 +346,7 @@ int gm_map_digest(gm_ctx* c, uint32_t first, uint32_t count, gm_digest* out) {
 
 int gm_clone(gm_ctx* src, gm_ctx** out) {
     if (!src || !out) return GM_ERR_ARG;
+    if (src->dist) return fail(src, GM_ERR_ARG, "gm_clone: a sharded context cannot be cloned");
     gm_ctx* d = (gm_ctx*)calloc(1, sizeof *d);
     *d = *src;
     d->maps = (orc_map**)calloc(src->max_particles, sizeof(orc_map*));
@@ -359,9 +367,179 @@ int gm_get_stats(gm_ctx* c, gm_stats* out) {
     return GM_OK;
 }
 
-/* ---- multi-GPU: not mocked */
-int gm_dist_unique_id(void* id_out) { (void)id_out; return fail(NULL, GM_ERR_NO_DEVICE, "gm_mock: the multi-GPU entry points are not mocked"); }
-int gm_dist_init(gm_ctx* c, int rank, int world, const void* id) { (void)rank; (void)world; (void)id; return fail(c, GM_ERR_NO_DEVICE, "gm_mock: the multi-GPU entry points are not mocked"); }
-int gm_dist_allgather(gm_ctx* c, const double* local, uint32_t count, double* all) { (void)local; (void)count; (void)all; return fail(c, GM_ERR_NO_DEVICE, "gm_mock: the multi-GPU entry points are not mocked"); }
-int gm_dist_register(gm_ctx* c, const double* ranges, const double* poses, const uint32_t* idx) { (void)ranges; (void)poses; (void)idx; return fail(c, GM_ERR_NO_DEVICE, "gm_mock: the multi-GPU entry points are not mocked"); }
-int gm_dist_copy_particles(gm_ctx* c, const uint32_t* idx) { (void)idx; return fail(c, GM_ERR_NO_DEVICE, "gm_mock: the multi-GPU entry points are not mocked"); }
+/* ---- multi-rank: one process per rank, exchange through files in $GM_MOCK_DIST_DIR/<communicator id> (written under a
+ * temporary name and renamed, so a reader that sees a file sees all of it).  Sequence numbers keep the calls of the ranks in
+ * step; a rank deletes what it wrote two exchanges ago (no peer can still need it: a peer is at most one exchange behind). */
+struct dist_state { int rank, world; unsigned long seq; char dir[400]; };
+
+int gm_dist_unique_id(void* id_out) {
+    unsigned char* b = (unsigned char*)id_out;
+    FILE* f = fopen("/dev/urandom", "rb");
+    if (!f || fread(b, 1, GM_DIST_ID_BYTES, f) != GM_DIST_ID_BYTES) { if (f) fclose(f); return fail(NULL, GM_ERR_ARG, "gm_mock: /dev/urandom"); }
+    fclose(f);
+    return GM_OK;
+}
+
+int gm_dist_init(gm_ctx* c, int rank, int world, const void* id) {
+    if (!c || !id || world < 1 || rank < 0 || rank >= world) return fail(c, GM_ERR_ARG, "gm_dist_init: bad argument");
+    const char* base = getenv("GM_MOCK_DIST_DIR");
+    if (!base) return fail(c, GM_ERR_NO_DEVICE, "gm_mock: GM_MOCK_DIST_DIR is not set (multi-rank runs of the mock exchange through files)");
+    struct dist_state* d = (struct dist_state*)calloc(1, sizeof *d);
+    d->rank = rank; d->world = world;
+    const unsigned char* b = (const unsigned char*)id;
+    int n = snprintf(d->dir, sizeof d->dir, "%s/comm_", base);
+    for (int i = 0; i < 12; i++) n += snprintf(d->dir + n, sizeof d->dir - n, "%02x", b[i]);
+    mkdir(d->dir, 0700); /* EEXIST from the other ranks is fine */
+    c->dist = d;
+    return GM_OK;
+}
+
+static void dist_path(const struct dist_state* d, char* out, size_t cap, const char* kind, unsigned long seq, unsigned who, int tmp) {
+    snprintf(out, cap, "%s/%s_%lu_%u%s", d->dir, kind, seq, who, tmp ? ".tmp" : ".bin");
+}
+
+static int dist_write(gm_ctx* c, const char* kind, unsigned long seq, unsigned who, const void* data, size_t bytes) {
+    struct dist_state* d = c->dist;
+    char tmp[480], fin[480];
+    dist_path(d, tmp, sizeof tmp, kind, seq, who, 1); dist_path(d, fin, sizeof fin, kind, seq, who, 0);
+    FILE* f = fopen(tmp, "wb");
+    if (!f || fwrite(data, 1, bytes, f) != bytes) { if (f) fclose(f); return fail(c, GM_ERR_INTERNAL, "gm_mock: cannot write %s", tmp); }
+    fclose(f);
+    if (rename(tmp, fin)) return fail(c, GM_ERR_INTERNAL, "gm_mock: cannot rename %s", tmp);
+    return GM_OK;
+}
+
+/* wait (up to 120 s) for a peer's file, return its content (malloc) */
+static int dist_read(gm_ctx* c, const char* kind, unsigned long seq, unsigned who, void** data, size_t* bytes) {
+    char fin[480];
+    dist_path(c->dist, fin, sizeof fin, kind, seq, who, 0);
+    FILE* f = NULL;
+    for (int spin = 0; spin < 600000 && !(f = fopen(fin, "rb")); spin++) usleep(200);
+    if (!f) return fail(c, GM_ERR_INTERNAL, "gm_mock: timed out waiting for %s", fin);
+    fseek(f, 0, SEEK_END);
+    *bytes = (size_t)ftell(f);
+    fseek(f, 0, SEEK_SET);
+    *data = malloc(*bytes ? *bytes : 1);
+    const size_t got = fread(*data, 1, *bytes, f);
+    fclose(f);
+    if (got != *bytes) { free(*data); return fail(c, GM_ERR_INTERNAL, "gm_mock: short read of %s", fin); }
+    return GM_OK;
+}
+
+static void dist_unlink(const struct dist_state* d, const char* kind, unsigned long seq, unsigned who) {
+    char fin[480];
+    dist_path(d, fin, sizeof fin, kind, seq, who, 0);
+    unlink(fin);
+}
+
+int gm_dist_allgather(gm_ctx* c, const double* local, uint32_t count, double* all) {
+    if (!c || !c->dist) return fail(c, GM_ERR_ARG, "gm_dist_allgather: gm_dist_init has not been called");
+    if (!local || !all) return fail(c, GM_ERR_ARG, "gm_dist_allgather: null argument");
+    struct dist_state* d = c->dist;
+    const unsigned long seq = ++d->seq;
+    int r = dist_write(c, "ag", seq, (unsigned)d->rank, local, sizeof(double) * count);
+    if (r) return r;
+    for (int g = 0; g < d->world; g++) {
+        void* buf; size_t bytes;
+        if ((r = dist_read(c, "ag", seq, (unsigned)g, &buf, &bytes))) return r;
+        if (bytes != sizeof(double) * count) { free(buf); return fail(c, GM_ERR_ARG, "gm_dist_allgather: rank %d sent %zu bytes, expected %zu", g, bytes, sizeof(double) * count); }
+        memcpy(all + (size_t)g * count, buf, bytes);
+        free(buf);
+    }
+    if (seq > 2) dist_unlink(d, "ag", seq - 2, (unsigned)d->rank);
+    return GM_OK;
+}
+
+/* a map on the wire: 5 doubles (cx cy world_w world_h delta), 7 ints (map_w map_h size_x2 size_y2 npx npy patches), coords, cells */
+static void* map_pack(const orc_map* m, size_t* bytes) {
+    const int64_t np = orc_map_patch_count(m);
+    *bytes = 5 * sizeof(double) + 7 * sizeof(int32_t) + (size_t)np * (2 * sizeof(int32_t) + 1024 * sizeof(orc_cell));
+    char* buf = (char*)malloc(*bytes);
+    const double h[5] = {m->cx, m->cy, m->world_w, m->world_h, m->delta};
+    const int32_t g[7] = {m->map_w, m->map_h, m->size_x2, m->size_y2, m->npx, m->npy, (int32_t)np};
+    memcpy(buf, h, sizeof h); memcpy(buf + sizeof h, g, sizeof g);
+    int32_t* coords = (int32_t*)(buf + sizeof h + sizeof g);
+    orc_map_export(m, coords, (orc_cell*)(coords + 2 * np), np);
+    return buf;
+}
+
+static orc_map* map_unpack(const void* data) {
+    const char* buf = (const char*)data;
+    double h[5]; int32_t g[7];
+    memcpy(h, buf, sizeof h); memcpy(g, buf + sizeof h, sizeof g);
+    orc_map* m = (orc_map*)calloc(1, sizeof *m);
+    m->cx = h[0]; m->cy = h[1]; m->world_w = h[2]; m->world_h = h[3]; m->delta = h[4];
+    m->map_w = g[0]; m->map_h = g[1]; m->size_x2 = g[2]; m->size_y2 = g[3]; m->npx = g[4]; m->npy = g[5];
+    const size_t nd = (size_t)m->npx * m->npy;
+    m->dir = (orc_cell**)calloc(nd, sizeof(orc_cell*));
+    m->active = (uint8_t*)calloc(nd, 1);
+    const int32_t* coords = (const int32_t*)(buf + sizeof h + sizeof g);
+    const orc_cell* cells = (const orc_cell*)(coords + 2 * (size_t)g[6]);
+    for (int32_t k = 0; k < g[6]; k++) {
+        orc_cell* p = (orc_cell*)malloc(sizeof(orc_cell) * 1024);
+        memcpy(p, cells + (size_t)1024 * k, sizeof(orc_cell) * 1024);
+        m->dir[(size_t)coords[2 * k] * m->npy + coords[2 * k + 1]] = p;
+    }
+    return m;
+}
+
+/* particle copy across ranks: child j of this rank continues the GLOBAL parent idx_global[first + j].  Parents that live here
+ * and have children elsewhere are published once each; parents that live elsewhere are fetched once each. */
+static int dist_remap(gm_ctx* c, const uint32_t* idx_global) {
+    struct dist_state* d = c->dist;
+    const uint32_t nl = c->n, first = (uint32_t)d->rank * nl, total = nl * (uint32_t)d->world;
+    const unsigned long seq = ++d->seq;
+    int r;
+    for (uint32_t j = 0; j < total; j++)
+        if (idx_global[j] >= total) return fail(c, GM_ERR_ARG, "gm_dist: parent index %u >= %u", idx_global[j], total);
+    /* publish */
+    uint8_t* sent = (uint8_t*)calloc(nl, 1);
+    for (uint32_t j = 0; j < total; j++) {
+        const uint32_t p = idx_global[j];
+        if (j / nl == (uint32_t)d->rank || p / nl != (uint32_t)d->rank || sent[p - first]) continue;
+        size_t bytes; void* buf = map_pack(c->maps[p - first], &bytes);
+        r = dist_write(c, "map", seq, p, buf, bytes);
+        free(buf);
+        if (r) { free(sent); return r; }
+        sent[p - first] = 1;
+    }
+    /* fetch + local clones */
+    orc_map** next = (orc_map**)calloc(nl, sizeof(orc_map*));
+    uint64_t imported = 0, imported_bytes = 0;
+    for (uint32_t j = 0; j < nl; j++) {
+        const uint32_t p = idx_global[first + j];
+        if (p / nl == (uint32_t)d->rank) { next[j] = orc_map_clone(c->maps[p - first]); continue; }
+        if (j && idx_global[first + j - 1] == p) { next[j] = orc_map_clone(next[j - 1]); continue; } /* systematic resampling: equal parents are adjacent */
+        void* buf; size_t bytes;
+        if ((r = dist_read(c, "map", seq, p, &buf, &bytes))) { free(sent); return r; }
+        next[j] = map_unpack(buf);
+        free(buf);
+        imported++; imported_bytes += bytes;
+    }
+    for (uint32_t j = 0; j < nl; j++) { orc_map_free(c->maps[j]); c->maps[j] = next[j]; }
+    free(next);
+    /* what this rank published two exchanges ago is no longer needed by anybody */
+    if (c->dist_sent_prev2) { for (uint32_t k = 0; k < nl; k++) if (c->dist_sent_prev2[k]) dist_unlink(d, "map", c->dist_seq_prev2, first + k); free(c->dist_sent_prev2); }
+    c->dist_sent_prev2 = c->dist_sent_prev; c->dist_seq_prev2 = c->dist_seq_prev;
+    c->dist_sent_prev = sent; c->dist_seq_prev = seq;
+    c->stats.migrated_particles = imported; c->stats.migrated_bytes = imported_bytes;
+    return GM_OK;
+}
+
+int gm_dist_copy_particles(gm_ctx* c, const uint32_t* idx_global) {
+    int r = ready(c);
+    if (r) return r;
+    if (!c->dist) return fail(c, GM_ERR_ARG, "gm_dist_copy_particles: gm_dist_init has not been called");
+    if (!idx_global) return fail(c, GM_ERR_ARG, "gm_dist_copy_particles: null argument");
+    return dist_remap(c, idx_global);
+}
+
+int gm_dist_register(gm_ctx* c, const double* ranges, const double* poses, const uint32_t* idx_global) {
+    int r = ready(c);
+    if (r) return r;
+    if (!c->dist) return fail(c, GM_ERR_ARG, "gm_dist_register: gm_dist_init has not been called");
+    if (!ranges || !poses) return fail(c, GM_ERR_ARG, "gm_dist_register: null argument");
+    c->stats.migrated_particles = 0; c->stats.migrated_bytes = 0;
+    if (idx_global && (r = dist_remap(c, idx_global))) return r;
+    return gm_register(c, ranges, poses, NULL);
+}

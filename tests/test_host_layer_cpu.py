@@ -28,3 +28,16 @@ def test_host_scenarios_on_the_mock(scenario):
     res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host_scenarios.py"), scenario], capture_output=True, text=True,
                          timeout=900, env=mock_env())
     assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-3000:]
+
+
+def test_sharded_filter_two_ranks_on_the_mock(tmp_path):
+    """the N > 1 host path on CPU: two torchrun ranks (gloo), each with its slice of the particles behind the mock, follow the
+    reference trace bit for bit; resampled parents cross the rank boundary (tests/dist_check.py asserts that they do)"""
+    env = mock_env()
+    env["GM_MOCK_DIST_DIR"] = str(tmp_path)
+    port = 29700 + (os.getpid() % 200)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "dist_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert res.returncode == 0, (res.stdout[-2000:], res.stderr[-4000:])
+    assert "dist_check room181_n30: ok" in res.stdout and "dist_check room181_k2_lskip: ok" in res.stdout
