@@ -188,6 +188,48 @@ class TraceProcessor : public GridSlamProcessor {
             w.vec("MCEL", cells);
         }
     }
+    // What the ROS node does every map_update_interval (gmapping/src/slam_gmapping.cpp:866-993, SlamGMapping::updateMap),
+    // restated against the same public API: a standalone ScanMatcher replays the best particle's trajectory (leaf -> root)
+    // into a fresh ScanMatcherMap, then every cell is thresholded into the occupancy-grid message.  Record: digest +
+    // geometry of that map, the counts of unknown / free / occupied grid cells and a hash of the grid.
+    void dumpRosMap(double xmin, double ymin, double xmax, double ymax, double delta, double maxRange, double maxUrange, double occ_thresh) {
+        if (!w.f) return;
+        ScanMatcher matcher;
+        matcher.setLaserParameters(m_matcher.laserBeams(), const_cast<double*>(m_matcher.laserAngles()), m_matcher.getlaserPose());
+        matcher.setlaserMaxRange(maxRange);
+        matcher.setusableRange(maxUrange);
+        matcher.setgenerateMap(true);
+        Particle best = getParticles()[getBestParticleIndex()];  // a copy, like slam_gmapping.cpp:879
+        Point center;
+        center.x = (xmin + xmax) / 2.0;
+        center.y = (ymin + ymax) / 2.0;
+        ScanMatcherMap smap(center, xmin, ymin, xmax, ymax, delta);
+        int nodes = 0;
+        for (TNode* n = best.node; n; n = n->parent) {
+            if (!n->reading) continue;
+            matcher.invalidateActiveArea();
+            matcher.computeActiveArea(smap, n->pose, &((*n->reading)[0]));
+            matcher.registerScan(smap, n->pose, &((*n->reading)[0]));
+            nodes++;
+        }
+        MapDigest d = digest(smap, nullptr);
+        int64_t unknown = 0, freec = 0, occupied = 0;
+        uint64_t h = 0;
+        for (int x = 0; x < smap.getMapSizeX(); x++)
+            for (int y = 0; y < smap.getMapSizeY(); y++) {
+                IntPoint p(x, y);
+                const double occ = smap.cell(p);
+                const int v = occ < 0 ? -1 : (occ > occ_thresh ? 100 : 0);
+                if (v < 0) { unknown++; continue; }
+                (v ? occupied : freec)++;
+                h += mix64((((uint64_t)(uint32_t)x << 32) | (uint32_t)y) ^ mix64((uint64_t)v + 7));
+            }
+        const Point wmin = smap.map2world(IntPoint(0, 0)), wmax = smap.map2world(IntPoint(smap.getMapSizeX(), smap.getMapSizeY()));
+        w.rec("UMAP", &d, sizeof d);
+        const double info[12] = {(double)nodes, (double)smap.getMapSizeX(), (double)smap.getMapSizeY(), wmin.x, wmin.y, wmax.x, wmax.y,
+                                 (double)unknown, (double)freec, (double)occupied, (double)(h >> 32), (double)(h & 0xffffffffu)};
+        w.rec("UINF", info, sizeof info);
+    }
     size_t size() const { return m_particles.size(); }
     int count() const { return m_count; }
 };
@@ -303,6 +345,7 @@ int main(int argc, char** argv) {
     }
     if (gsp.w.f) {
         gsp.dumpMaps(true);
+        gsp.dumpRosMap(o.xmin, o.ymin, o.xmax, o.ymax, o.delta, o.maxrange, o.maxurange, 0.25);
         gsp.w.rec("DONE", nullptr, 0);
         fclose(gsp.w.f);
     }

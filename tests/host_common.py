@@ -140,4 +140,11 @@ def check_trace(case, g, tr, exact=False):
     fin = tr["final"]
     assert np.array_equal(digest_rows(fin["digests"])[:, :5], digest_rows(g.digests[-1])[:, :5])
     assert fin["best"] == int(g.best)
+    # the ROS node's updateMap (slam_gmapping.cpp:866-993) as the driver restates it: a standalone ScanMatcher replays the best
+    # trajectory into a fresh host ScanMatcherMap (computeActiveArea + registerScan), every cell is read back and thresholded
+    got, want = digest_rows(fin["ros_map_digest"]), digest_rows(g.ros_map_digest)
+    assert np.array_equal(got[:, :5], want[:, :5]), "%s: map rebuilt from the best trajectory, integer digest" % case
+    if exact:
+        assert np.array_equal(got, want), "%s: map rebuilt from the best trajectory, float accumulators" % case
+    assert np.array_equal(fin["ros_map_info"], g.ros_map_info), "%s: occupancy grid of the rebuilt map (size, origin, cell counts, hash)" % case
     assert k_dig >= 1

@@ -96,7 +96,7 @@ def run_case(name, log_kw, par):
     dig_scan.append(S - 1); digs.append(tr["final"]["digests"]); geos.append(tr["final"]["geometry"])
     a.update(smat=smat, probes=probes, like=like, state=state, tree=tree, neff=neff, weights=weights, ridx=ridx, rw=rw, rneff=rneff,
              dig_scan=np.array(dig_scan), digests=np.stack(digs), geometry=np.stack(geos),
-             best=np.array(tr["final"]["best"]))
+             best=np.array(tr["final"]["best"]), ros_map_digest=tr["final"]["ros_map_digest"], ros_map_info=tr["final"]["ros_map_info"])
     path = os.path.join(GOLD, name + ".npz")
     np.savez_compressed(path, **a)
     print("%-18s readings %3d processed %3d resamples %2d  %6.1f KB   %s" % (
