@@ -31,7 +31,7 @@ using namespace GMapping;
 namespace {
 
 struct Opts {
-    std::string mode = "time", log, out;
+    std::string mode = "time", log, out, gfs;
     int particles = 30, max_scans = 1 << 30, maps_every = 0, seed = 12345, probe_particles = 2;
     double xmin = -100, ymin = -100, xmax = 100, ymax = 100, delta = 0.05;
     double sigma = 0.05, maxrange = 80, maxurange = 80, lstep = 0.05, astep = 0.05, lsigma = 0.075, ogain = 3;
@@ -249,7 +249,7 @@ int main(int argc, char** argv) {
 #define S(flag, field) if (arg(i, argc, argv, flag, v)) { o.field = v; continue; }
 #define I(flag, field) if (arg(i, argc, argv, flag, v)) { o.field = atoi(v.c_str()); continue; }
 #define D(flag, field) if (arg(i, argc, argv, flag, v)) { o.field = atof(v.c_str()); continue; }
-        S("-mode", mode) S("-log", log) S("-out", out)
+        S("-mode", mode) S("-log", log) S("-out", out) S("-gfs", gfs)
         I("-particles", particles) I("-scans", max_scans) I("-maps-every", maps_every) I("-seed", seed) I("-probe", probe_particles)
         D("-xmin", xmin) D("-ymin", ymin) D("-xmax", xmax) D("-ymax", ymax) D("-delta", delta)
         D("-sigma", sigma) D("-maxrange", maxrange) D("-maxUrange", maxurange) D("-lstep", lstep) D("-astep", astep)
@@ -290,6 +290,9 @@ int main(int argc, char** argv) {
     gsp.setUpdatePeriod(o.period);
     gsp.setgenerateMap(o.generate_map);
     gsp.setminimumScore(o.min_score);
+
+    // the .gfs trace the reference's log drivers write (gsp_thread.cpp:330-337 opens it the same way, before init)
+    if (!o.gfs.empty()) gsp.outputStream().open(o.gfs.c_str());
 
     bool inited = false;
     if (o.mode == "trace" && !o.out.empty()) {
@@ -349,6 +352,7 @@ int main(int argc, char** argv) {
         gsp.w.rec("DONE", nullptr, 0);
         fclose(gsp.w.f);
     }
+    if (gsp.outputStream().is_open()) gsp.outputStream().close();
     std::cerr.rdbuf(old_cerr);
     std::cout.rdbuf(old_cout);
     double sum = 0, sum_sm = 0;

@@ -2,6 +2,7 @@
 reference's headers and API) is compiled UNCHANGED against our headers and linked with our libraries."""
 from __future__ import annotations
 
+import hashlib
 import importlib
 import os
 import subprocess
@@ -84,10 +85,12 @@ def free_run(case, env=None, extra=()):
     with tempfile.TemporaryDirectory() as td:
         lp, tp = os.path.join(td, "in.log"), os.path.join(td, "trace.bin")
         golden_log(g, lp)
-        cmd = [exe, "-mode", "trace", "-log", lp, "-out", tp, "-probe", "2", "-maps-every", str(g.p["maps_every"])] + driver_args(g.p) + list(extra)
+        gp = os.path.join(td, "trace.gfs")
+        cmd = [exe, "-mode", "trace", "-log", lp, "-out", tp, "-gfs", gp, "-probe", "2", "-maps-every", str(g.p["maps_every"])] + driver_args(g.p) + list(extra)
         res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
         assert res.returncode == 0, res.stderr[-2000:]
         tr = read_trace(tp)
+        tr["gfs"] = open(gp, "rb").read()  # what GridSlamProcessor::outputStream() received
     return g, tr
 
 
@@ -140,6 +143,12 @@ def check_trace(case, g, tr, exact=False):
     fin = tr["final"]
     assert np.array_equal(digest_rows(fin["digests"])[:, :5], digest_rows(g.digests[-1])[:, :5])
     assert fin["best"] == int(g.best)
+    # the .gfs trace (gridslamprocessor.cpp:454-475, 570-606; gridslamprocessor.hxx:159-167): the same records in the same order;
+    # with the reference's arithmetic underneath (mock) the same bytes
+    tags = " ".join(l.split(b" ", 1)[0].decode() for l in tr["gfs"].splitlines() if l)
+    assert tags == str(g.gfs_tags), "%s: .gfs record sequence" % case
+    if exact:
+        assert len(tr["gfs"]) == int(g.gfs_bytes) and hashlib.sha256(tr["gfs"]).hexdigest() == str(g.gfs_sha256), "%s: .gfs bytes" % case
     # the ROS node's updateMap (slam_gmapping.cpp:866-993) as the driver restates it: a standalone ScanMatcher replays the best
     # trajectory into a fresh host ScanMatcherMap (computeActiveArea + registerScan), every cell is read back and thresholded
     got, want = digest_rows(fin["ros_map_digest"]), digest_rows(g.ros_map_digest)

@@ -13,6 +13,7 @@ and what the GPU parity tests compare against; the GPU box never sees /root/refe
 """
 from __future__ import annotations
 
+import hashlib
 import importlib
 import json
 import os
@@ -62,7 +63,8 @@ def run_case(name, log_kw, par):
     with tempfile.TemporaryDirectory() as td:
         lp, tp = os.path.join(td, "in.log"), os.path.join(td, "trace.bin")
         synth.write_carmen(log, lp)
-        cmd = [REF, "-mode", "trace", "-log", lp, "-out", tp, "-probe", "2", "-maps-every", str(p["maps_every"])]
+        gp = os.path.join(td, "trace.gfs")
+        cmd = [REF, "-mode", "trace", "-log", lp, "-out", tp, "-gfs", gp, "-probe", "2", "-maps-every", str(p["maps_every"])]
         for k in ("particles", "seed", "kernelSize", "iterations", "lskip"):
             cmd += ["-" + k, str(int(p[k]))]
         for k in ("xmin", "ymin", "xmax", "ymax", "delta", "sigma", "maxrange", "maxUrange", "lstep", "astep", "lsigma", "ogain",
@@ -72,6 +74,7 @@ def run_case(name, log_kw, par):
             cmd.append("-no-generateMap")
         out = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout
         tr = read_trace(tp)
+        gfs = open(gp, "rb").read()  # the .gfs file the reference itself writes (GridSlamProcessor::outputStream())
     R = tr["readings"]
     S, N, B = len(R), tr["head"]["particles"], tr["head"]["beams"]
     a = dict(
@@ -97,6 +100,8 @@ def run_case(name, log_kw, par):
     a.update(smat=smat, probes=probes, like=like, state=state, tree=tree, neff=neff, weights=weights, ridx=ridx, rw=rw, rneff=rneff,
              dig_scan=np.array(dig_scan), digests=np.stack(digs), geometry=np.stack(geos),
              best=np.array(tr["final"]["best"]), ros_map_digest=tr["final"]["ros_map_digest"], ros_map_info=tr["final"]["ros_map_info"])
+    a.update(gfs_sha256=np.array(hashlib.sha256(gfs).hexdigest()), gfs_bytes=np.array(len(gfs)),
+             gfs_tags=np.array(" ".join(l.split(b" ", 1)[0].decode() for l in gfs.splitlines() if l)))
     path = os.path.join(GOLD, name + ".npz")
     np.savez_compressed(path, **a)
     print("%-18s readings %3d processed %3d resamples %2d  %6.1f KB   %s" % (
