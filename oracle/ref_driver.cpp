@@ -19,6 +19,7 @@
 #include <iostream>
 #include <sstream>
 #include <string>
+#include <set>
 #include <vector>
 
 #include <gmapping/gridfastslam/gridslamprocessor.h>
@@ -230,6 +231,31 @@ class TraceProcessor : public GridSlamProcessor {
                                  (double)unknown, (double)freec, (double)occupied, (double)(h >> 32), (double)(h & 0xffffffffu)};
         w.rec("UINF", info, sizeof info);
     }
+    // getTrajectories() (gridslamprocessor_tree.cpp:57-147): a deep copy of the trajectory tree, one leaf per particle, shared
+    // ancestors copied once.  Per leaf, walking the COPY: chain length, sums of pose x / y / theta, sum of accWeight, sum of
+    // childs, nodes that carry a reading, nodes shared with the previous particle's chain.  Then the copy is freed leaf by leaf.
+    void dumpTrajectories() {
+        if (!w.f) return;
+        TNodeVector leaves = getTrajectories();
+        std::vector<double> rows;
+        std::set<const TNode*> prev;
+        for (size_t i = 0; i < leaves.size(); i++) {
+            double depth = 0, sx = 0, sy = 0, st = 0, acc = 0, childs = 0, readings = 0, shared = 0;
+            std::set<const TNode*> mine;
+            for (const TNode* n = leaves[i]; n; n = n->parent) {
+                depth += 1; sx += n->pose.x; sy += n->pose.y; st += n->pose.theta; acc += n->accWeight; childs += n->childs;
+                readings += n->reading ? 1 : 0; shared += prev.count(n) ? 1 : 0;
+                mine.insert(n);
+            }
+            bool isOriginal = false;  // the copy must not alias the filter's own nodes
+            for (auto& p : m_particles) for (const TNode* n = p.node; n; n = n->parent) if (mine.count(n)) isOriginal = true;
+            const double row[9] = {depth, sx, sy, st, acc, childs, readings, shared, isOriginal ? 1. : 0.};
+            rows.insert(rows.end(), row, row + 9);
+            prev.swap(mine);
+        }
+        w.vec("TRAJ", rows);
+        for (size_t i = 0; i < leaves.size(); i++) delete leaves[i];  // ~TNode releases ancestors when their last child goes
+    }
     size_t size() const { return m_particles.size(); }
     int count() const { return m_count; }
 };
@@ -348,6 +374,7 @@ int main(int argc, char** argv) {
     }
     if (gsp.w.f) {
         gsp.dumpMaps(true);
+        gsp.dumpTrajectories();
         gsp.dumpRosMap(o.xmin, o.ymin, o.xmax, o.ymax, o.delta, o.maxrange, o.maxurange, 0.25);
         gsp.w.rec("DONE", nullptr, 0);
         fclose(gsp.w.f);

@@ -75,6 +75,8 @@ def read_trace(path):
             a = np.frombuffer(p, dtype="<i4")
             final["best"] = int(a[0])
             final["best_cells"] = a[1:].reshape(-1, 6).copy()  # wx wy n visits accx_bits accy_bits
+        elif tag == "TRAJ":  # getTrajectories(): per leaf depth, sum x y theta, sum accWeight, sum childs, readings, shared, aliasing
+            final["trajectories"] = np.frombuffer(p, dtype="<f8").reshape(-1, 9).copy()
         elif tag == "UMAP":  # the ROS node's map rebuild from the best trajectory (ref_driver.cpp dumpRosMap)
             final["ros_map_digest"] = np.frombuffer(p, dtype=DIGEST_DTYPE).copy()
         elif tag == "UINF":  # nodes, map size x y, world min x y, world max x y, unknown / free / occupied cells, grid hash hi lo

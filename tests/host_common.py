@@ -143,6 +143,11 @@ def check_trace(case, g, tr, exact=False):
     fin = tr["final"]
     assert np.array_equal(digest_rows(fin["digests"])[:, :5], digest_rows(g.digests[-1])[:, :5])
     assert fin["best"] == int(g.best)
+    # getTrajectories() (gridslamprocessor_tree.cpp:57-147): the deep copy has the reference's shape (chain lengths, child counts,
+    # readings, sharing between neighbouring particles, no aliasing of the live tree) and carries its poses and weights
+    got, want = fin["trajectories"], g.trajectories
+    assert np.array_equal(got[:, [0, 5, 6, 7, 8]], want[:, [0, 5, 6, 7, 8]]) and not got[:, 8].any(), "%s: getTrajectories() tree shape" % case
+    np.testing.assert_allclose(got[:, 1:5], want[:, 1:5], rtol=rtol4, atol=0 if exact else 1e-3, err_msg="%s: getTrajectories() poses / accWeight" % case)
     # the .gfs trace (gridslamprocessor.cpp:454-475, 570-606; gridslamprocessor.hxx:159-167): the same records in the same order;
     # with the reference's arithmetic underneath (mock) the same bytes
     tags = " ".join(l.split(b" ", 1)[0].decode() for l in tr["gfs"].splitlines() if l)
