@@ -329,11 +329,20 @@ def test_occupancy_export_and_standalone_optimize():
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", ["laser_offset", "odo_gain", "beams_skip", "kernel0", "kernel3", "threshold", "beams2047", "lskip3"])
+@pytest.mark.parametrize("variant", ["laser_offset", "odo_gain", "beams_skip", "kernel0", "kernel3", "threshold", "beams2047", "lskip3",
+                                     "delta025", "delta03", "corner_origin", "corner_origin_k2", "half_cell_centre", "centre_offset"])
 def test_parameter_variants_vs_oracle(variant):
     """Paths that the default configuration never takes: laser mounted off-centre (scanmatcher.h:177-180), the odometry
     prior of optimize() (scanmatcher.cpp:497-509), initialBeamsSkip, other kernel sizes, a non-default fullnessThreshold
-    (generic occupancy test), the largest beam count the reference allows (2047), likelihoodSkip."""
+    (generic occupancy test), the largest beam count the reference allows (2047), likelihoodSkip; other grid resolutions
+    (0.025 m as in BASELINE.json's fifth configuration; 0.03 m, whose reciprocal is not a short binary fraction); and map
+    frames whose centre is not the origin.  The centre matters because of the reference's `ipfree = world2map(pfree - phit)`
+    (scanmatcher.h:208-210, 320-322): world2map of a DIFFERENCE adds sizeX2 - centre/delta, so with the map's lower corner at
+    the origin ("corner_origin": world 0..40 m, the room around (20, 20)) the free cell really is the cell in front of the hit
+    and the scan matcher's free-cell test reads allocated, visited cells for every beam -- with a centred map it lands half a
+    map away on unknown cells.  (In that frame score()'s own free cell, 3.5 mm in front of the hit, IS the hit cell, so score() is
+    zero everywhere and only likelihoodAndScore matches; "half_cell_centre" moves the frame by half a cell, where the rounding
+    puts score()'s free cell one cell in front of or on the hit depending on the beam direction.)"""
     import importlib
     gm = importlib.import_module("slam-gmapping-learn_b200")
     synth = importlib.import_module("slam-gmapping-learn_b200.synth")
@@ -349,15 +358,23 @@ def test_parameter_variants_vs_oracle(variant):
     if variant == "kernel3": kw["kernel"] = 3
     if variant == "threshold": extra = dict(fullness_threshold=0.25)
     if variant == "lskip3": kw["lskip"] = 3
+    bounds, delta, shift = (-100., -100., 100., 100.), 0.05, np.zeros(3)
+    if variant == "delta025": delta = 0.025
+    if variant == "delta03": delta = 0.03
+    if variant.startswith("corner_origin"): bounds, shift = (0., 0., 40., 40.), np.array([20., 20., 0.])
+    if variant == "corner_origin_k2": kw["kernel"] = 2
+    if variant == "half_cell_centre": bounds, shift = (0.025, 0.025, 40.025, 40.025), np.array([20., 20., 0.])
+    if variant == "centre_offset": bounds, shift = (-30., -10., 50., 90.), np.array([7.3, 38.1, 0.])
+    log.odom = log.odom + shift[None, :]  # the same room somewhere else in the world
     n = 4
     m = orc.make_matcher(laser.angles(), lp, **kw)
     for k, v in extra.items():
         setattr(m, k, v)
-    ctx = gm.GmContext(n, pool_patches=4096)
+    ctx = gm.GmContext(n, pool_patches=16384 if delta < 0.05 else 4096)
     ctx.set_laser(laser.angles(), lp)
     ctx.set_matching(**kw, **extra)
-    ctx.init_particles(n)
-    maps = [orc.Map() for _ in range(n)]
+    ctx.init_particles(n, bounds=bounds, delta=delta)
+    maps = [orc.Map((bounds[0] + bounds[2]) * .5, (bounds[1] + bounds[3]) * .5, bounds[2] - bounds[0], bounds[3] - bounds[1], delta) for _ in range(n)]
     rng = np.random.default_rng(3)
     for k in range(4):
         poses = log.odom[k][None, :] + rng.normal(0, [0.02, 0.02, 0.01], size=(n, 3))
@@ -379,5 +396,20 @@ def test_parameter_variants_vs_oracle(variant):
         assert abs(sc[j] - so) <= TIGHT * max(1.0, abs(so)) and np.abs(out[j] - po).max() <= TIGHT, variant
         s1, l1, c1 = orc.likelihood_and_score(m, maps[j], po, r)
         assert abs(l[j] - l1) <= TIGHT * max(1.0, abs(l1)) and c[j] == c1 and abs(s[j] - s1) <= TIGHT * max(1.0, abs(s1)), variant
-    assert sc.max() > 5
+    if variant.startswith("corner_origin"):
+        assert sc.max() == 0 and c.max() > 20  # score() cannot match in this frame (see above), likelihoodAndScore does
+    else:
+        assert sc.max() > 5
+    if variant.startswith("corner_origin") or variant == "half_cell_centre":
+        # the point of this variant: the free-cell test must have rejected matches that a centred map accepts
+        mc = orc.make_matcher(laser.angles(), lp, **kw)
+        centred = [orc.Map() for _ in range(n)]
+        rng2 = np.random.default_rng(3)
+        for k in range(4):
+            poses = (log.odom[k] - shift)[None, :] + rng2.normal(0, [0.02, 0.02, 0.01], size=(n, 3))
+            for j in range(n):
+                orc.register(mc, centred[j], poses[j], log.ranges[k])
+        s_c, _, c_c = orc.likelihood_and_score(mc, centred[0], init[0] - shift, r)
+        s_o, _, c_o = orc.likelihood_and_score(m, maps[0], init[0], r)
+        assert c_o != c_c or abs(s_o - s_c) > 1e-6, "the free-cell test made no difference: the variant does not exercise it"
     ctx.close()
