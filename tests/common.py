@@ -10,7 +10,7 @@ import numpy as np
 from oracle import orc
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["room181_n30", "room181_resize", "room1081_n8", "room181_k2_lskip"]
+CASES = ["room181_n30", "room181_resize", "room1081_n8", "room181_k2_lskip", "room181_halfcell", "room181_d025"]
 
 
 class Golden:

@@ -48,6 +48,16 @@ CASES = {
     "room181_k2_lskip": (dict(world="room", laser="LMS200", scans=16, step=0.5),
                          dict(particles=6, kernelSize=2, lskip=2, generate_map=False, minimumScore=60.0,
                               linearUpdate=0.4, angularUpdate=0.2, srr=0.05, srt=0.1, str=0.05, stt=0.1, maps_every=4)),
+    # map frame with its lower corner half a cell off the origin and the room around (20, 20): the reference's
+    # ipfree = world2map(pfree - phit) (scanmatcher.h:208-210, 320-322) then lands ON the neighbourhood of the hit, so the
+    # free-cell test reads allocated, visited cells, and score()'s free-cell offset depends on the beam direction
+    "room181_halfcell": (dict(world="room", laser="LMS200", scans=14, step=0.5, shift=(20.0, 20.0, 0.0)),
+                         dict(particles=6, xmin=0.025, ymin=0.025, xmax=40.025, ymax=40.025, linearUpdate=0.4, angularUpdate=0.2,
+                              srr=0.05, srt=0.1, str=0.05, stt=0.1, maps_every=4)),
+    # BASELINE.json's fifth configuration uses a 0.025 m grid
+    "room181_d025": (dict(world="room", laser="LMS200", scans=12, step=0.5),
+                     dict(particles=6, delta=0.025, xmin=-50., ymin=-50., xmax=50., ymax=50., linearUpdate=0.4, angularUpdate=0.2,
+                          srr=0.05, srt=0.1, str=0.05, stt=0.1, maps_every=4)),
 }
 
 DEFAULTS = dict(particles=30, xmin=-100., ymin=-100., xmax=100., ymax=100., delta=0.05, sigma=0.05, maxrange=80., maxUrange=80.,
@@ -59,7 +69,10 @@ DEFAULTS = dict(particles=30, xmin=-100., ymin=-100., xmax=100., ymax=100., delt
 def run_case(name, log_kw, par):
     p = dict(DEFAULTS); p.update(par)
     lk = dict(log_kw); laser = getattr(synth, lk.pop("laser"))
+    shift = lk.pop("shift", None)
     log = synth.make_log(laser=laser, **lk)
+    if shift is not None:  # the same room somewhere else in the world
+        log.odom = np.round(log.odom + np.asarray(shift)[None, :], 6)
     with tempfile.TemporaryDirectory() as td:
         lp, tp = os.path.join(td, "in.log"), os.path.join(td, "trace.bin")
         synth.write_carmen(log, lp)
