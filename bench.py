@@ -127,7 +127,7 @@ def reference_arm(args):
         return
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     procs = max(1, min(cores, 64))
-    pp = 16  # particles per process
+    pp = CPU_BASELINE_PARTICLES  # particles per process: every core runs the same bounded sample as the cpu_baseline leg
     scans = min(1 + args.warmup + args.steps, 40)  # the same log prefix the GPU arm runs (first scan registers only)
     synth, log = make_log(scans)
     with tempfile.TemporaryDirectory() as td:
