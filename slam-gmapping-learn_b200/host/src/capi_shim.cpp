@@ -39,6 +39,22 @@ void gmh_destroy(void* h) { delete static_cast<Handle*>(h); }
 void* gmh_clone(void* h) { return new Handle(*static_cast<Handle*>(h)); }
 int gmh_dist_unique_id(void* id128) { return gm_dist_unique_id(id128); }
 void gmh_set_distributed(void* h, int rank, int world, const void* id) { static_cast<Handle*>(h)->gsp->setDistributed(rank, world, id); }
+void gmh_set_lazy_tree(void* h, int on) { static_cast<Handle*>(h)->gsp->setlazyTreeWeights(on != 0); }
+void gmh_refresh_tree(void* h) { static_cast<Handle*>(h)->gsp->refreshTreeWeights(); }
+// the trajectory tree seen from each particle, walking node -> root: chain length, the leaf's accWeight, sum of accWeight,
+// position-weighted sum of accWeight, sum of visitCounter, sum of childs (6 doubles per particle; the rows the tests' golden
+// traces hold for the reference)
+void gmh_tree_rows(void* hv, double* rows) {
+    const GridSlamProcessor::ParticleVector& ps = static_cast<Handle*>(hv)->gsp->getParticles();
+    for (size_t i = 0; i < ps.size(); i++) {
+        double depth = 0, sum = 0, wsum = 0, visits = 0, childs = 0;
+        for (const GridSlamProcessor::TNode* n = ps[i].node; n; n = n->parent) {
+            depth += 1; sum += n->accWeight; wsum += depth * n->accWeight; visits += n->visitCounter; childs += n->childs;
+        }
+        double* r = rows + 6 * i;
+        r[0] = depth; r[1] = ps[i].node ? ps[i].node->accWeight : 0.; r[2] = sum; r[3] = wsum; r[4] = visits; r[5] = childs;
+    }
+}
 void gmh_set_early_registration(void* h, int on) { static_cast<Handle*>(h)->gsp->setearlyRegistration(on != 0); }
 
 // params: maxUrange maxrange sigma kernelSize lstep astep iterations lsigma ogain lskip srr srt str stt linearUpdate

@@ -37,6 +37,9 @@ def load():
     L.gmh_dist_unique_id.argtypes = [vp]
     L.gmh_set_distributed.argtypes = [vp, C.c_int, C.c_int, vp]
     L.gmh_set_early_registration.argtypes = [vp, C.c_int]
+    L.gmh_set_lazy_tree.argtypes = [vp, C.c_int]
+    L.gmh_refresh_tree.argtypes = [vp]
+    L.gmh_tree_rows.argtypes = [vp, dp]
     L.gmh_setup.argtypes = [vp, C.c_uint, dp, dp, dp]
     L.gmh_init.argtypes = [vp, C.c_uint] + [C.c_double] * 5 + [dp, C.c_ulong]
     L.gmh_process_scan.argtypes = [vp, dp, C.c_uint, dp, C.c_double]
@@ -72,13 +75,15 @@ class Processor:
     """GMapping::GridSlamProcessor (C++) behind ctypes."""
 
     def __init__(self, angles, particles, init_pose, bounds=(-100., -100., 100., 100.), delta=0.05, seed=12345, laser_pose=(0., 0., 0.),
-                 rank=0, world=1, nccl_id=None, verbose=False, early_registration=True, **params):
+                 rank=0, world=1, nccl_id=None, verbose=False, early_registration=True, lazy_tree=False, **params):
         L = load()
         self.L = L
         self.h = L.gmh_create(1 if verbose else 0)
         if world > 1:
             self._id = C.create_string_buffer(nccl_id, 128)
             L.gmh_set_distributed(self.h, rank, world, self._id)
+        if lazy_tree:
+            L.gmh_set_lazy_tree(self.h, 1)  # TNode::accWeight is brought up to date on demand (refresh_tree / getTrajectories)
         if not early_registration:
             L.gmh_set_early_registration(self.h, 0)  # the reference's order: copy the resampled particles, then register
         p = dict(DEFAULTS); p.update(params)
@@ -107,6 +112,13 @@ class Processor:
 
     def state(self):
         a = np.zeros((self.n, 6)); self.L.gmh_state(self.h, _dp(a)); return a
+
+    def tree_rows(self):
+        """per particle, walking its trajectory leaf -> root: depth, leaf accWeight, sum accWeight, weighted sum, sum visitCounter, sum childs"""
+        a = np.zeros((self.n, 6)); self.L.gmh_tree_rows(self.h, _dp(a)); return a
+
+    def refresh_tree(self):
+        self.L.gmh_refresh_tree(self.h)
 
     def indexes(self):
         a = np.zeros(self.n, dtype=np.uint32); self.L.gmh_indexes(self.h, a.ctypes.data); return a

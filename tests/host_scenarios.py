@@ -3,7 +3,7 @@ gfs_b200 CLI.  The `-m gpu` tests of tests/test_host_layer.py call them in proce
 runs this file in a subprocess with the CPU mock of the C ABI preloaded (tests/mock/gm_mock.c), where everything the host
 layer computes itself must still match the unmodified reference's trace.
 
-    python tests/host_scenarios.py clone | order | cli | long[:SCANS]
+    python tests/host_scenarios.py clone | order | cli | lazy_tree | long[:SCANS]
 """
 import ctypes
 import importlib
@@ -110,6 +110,34 @@ def scenario_order():
     assert np.abs(s0[:, :3] - g.state[len(g.ranges) - 1][:, :3]).max() < 1e-4
 
 
+def scenario_lazy_tree():
+    """setlazyTreeWeights(true): processScan only normalises the weights; TNode::accWeight is brought up to date on demand.
+    The filter itself must not notice (same poses, weights, resampling, maps), and after refreshTreeWeights() the tree is the
+    eager one -- which, per the golden trace, is the reference's."""
+    build_host()
+    hostapi = importlib.import_module("slam-gmapping-learn_b200.hostapi")
+    g = Golden("room181_k2_lskip")
+    p = g.p
+    runs = []
+    for lazy in (False, True):
+        a = hostapi.Processor(g.angles, p["particles"], g.head_init, bounds=(p["xmin"], p["ymin"], p["xmax"], p["ymax"]), delta=p["delta"],
+                              seed=p["seed"], lazy_tree=lazy, **{k: p[k] for k in hostapi.PARAM_ORDER})
+        for i in range(len(g.ranges)):
+            a.process_scan(g.ranges[i], g.odom[i], g.stamps[i])
+        stale = a.tree_rows()
+        a.refresh_tree()
+        runs.append((a.state(), a.map_digests(), a.resamples(), a.neff(), stale, a.tree_rows()))
+        a.close()
+    (s0, d0, r0, n0, stale0, t0), (s1, d1, r1, n1, stale1, t1) = runs
+    assert r0 == r1 and r0 > 0 and n0 == n1 and np.array_equal(s0, s1) and np.array_equal(d0, d1)
+    assert np.array_equal(stale0, t0)            # eager: nothing left to refresh
+    assert not np.array_equal(stale1[:, 1:4], t1[:, 1:4])  # lazy: the weights in the tree were stale until asked for
+    assert np.array_equal(t0, t1)
+    last = len(g.ranges) - 1
+    assert np.array_equal(t0[:, [0, 4, 5]], g.tree[last][:, [0, 4, 5]])
+    np.testing.assert_allclose(t0[:, 1:4], g.tree[last][:, 1:4], rtol=1e-4, atol=1e-9)
+
+
 def scenario_long(limit=None):
     """BASELINE.json configs[0]/[1]: 30 particles, 181-beam scans, 1000 scans, free running through the C++ API against the
     unmodified reference (fixture: Neff and flags for every scan, all poses / log-weights every 10th scan): the filter never
@@ -149,6 +177,6 @@ def scenario_long(limit=None):
 
 if __name__ == "__main__":
     name, _, arg = sys.argv[1].partition(":")
-    fn = {"cli": scenario_cli, "clone": scenario_clone, "order": scenario_order, "long": scenario_long}[name]
+    fn = {"cli": scenario_cli, "clone": scenario_clone, "order": scenario_order, "long": scenario_long, "lazy_tree": scenario_lazy_tree}[name]
     out = fn(int(arg)) if arg else fn()
     print("scenario %s ok %s" % (sys.argv[1], "" if out is None else out))

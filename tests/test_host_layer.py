@@ -121,5 +121,10 @@ def test_reference_order_and_early_registration_agree():
 
 
 @pytest.mark.gpu
+def test_lazy_tree_weights():
+    host_scenarios.scenario_lazy_tree()
+
+
+@pytest.mark.gpu
 def test_thousand_scans_free_running():
     host_scenarios.scenario_long()
