@@ -25,6 +25,7 @@
 #include <gmapping/gridfastslam/gridslamprocessor.h>
 #include <gmapping/log/carmenconfiguration.h>
 #include <gmapping/log/sensorstream.h>
+#include <gmapping/scanmatcher/scanmatcherprocessor.h>
 #include <gmapping/utils/stat.h>
 
 using namespace GMapping;
@@ -260,6 +261,42 @@ class TraceProcessor : public GridSlamProcessor {
     int count() const { return m_count; }
 };
 
+// ScanMatcherProcessor (scanmatcher/scanmatcherprocessor.cpp): incremental scan matching of the log's first readings against one
+// map, no particle filter.  Record: pose after every reading, then digest + geometry of its map.
+void dumpScanMatcherProcessor(Writer& w, const SensorMap& sensorMap, const std::string& log, const Opts& o, int max_readings) {
+    if (!w.f) return;
+    ScanMatcherProcessor smp(o.xmin, o.ymin, o.xmax, o.ymax, o.delta, o.delta);
+    smp.setSensorMap(sensorMap);
+    smp.setMatchingParameters(o.maxurange, o.maxrange, o.sigma, o.kernel, o.lstep, o.astep, o.iterations, false);
+    smp.setRegistrationParameters(300., 150.);
+    smp.matcher().setgenerateMap(o.generate_map);  // the reference's ScanMatcher leaves m_generateMap uninitialised
+    smp.init();
+    std::ifstream is(log.c_str());
+    InputSensorStream input(sensorMap, is);
+    std::vector<double> poses;
+    int n = 0;
+    while (input && n < max_readings) {
+        const SensorReading* r = nullptr;
+        input >> r;
+        if (!r) continue;
+        const RangeReading* rr = dynamic_cast<const RangeReading*>(r);
+        if (rr) {
+            smp.processScan(*rr);
+            const OrientedPoint p = smp.getPose();
+            poses.push_back(p.x); poses.push_back(p.y); poses.push_back(p.theta);
+            n++;
+        }
+        delete r;
+    }
+    w.vec("SMPP", poses);
+    const ScanMatcherMap& m = smp.getMap();
+    MapDigest d = TraceProcessor::digest(m, nullptr);
+    w.rec("SMPD", &d, sizeof d);
+    IntPoint c = m.world2map(m.getCenter());
+    const int32_t geo[6] = {c.x, c.y, m.getMapSizeX(), m.getMapSizeY(), m.storage().getXSize(), m.storage().getYSize()};
+    w.rec("SMPG", geo, sizeof geo);
+}
+
 bool arg(int& i, int argc, char** argv, const char* name, std::string& v) {
     if (strcmp(argv[i], name)) return false;
     if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", name); exit(2); }
@@ -376,6 +413,7 @@ int main(int argc, char** argv) {
         gsp.dumpMaps(true);
         gsp.dumpTrajectories();
         gsp.dumpRosMap(o.xmin, o.ymin, o.xmax, o.ymax, o.delta, o.maxrange, o.maxurange, 0.25);
+        dumpScanMatcherProcessor(gsp.w, sensorMap, o.log, o, 12);
         gsp.w.rec("DONE", nullptr, 0);
         fclose(gsp.w.f);
     }

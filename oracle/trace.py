@@ -81,6 +81,12 @@ def read_trace(path):
             final["ros_map_digest"] = np.frombuffer(p, dtype=DIGEST_DTYPE).copy()
         elif tag == "UINF":  # nodes, map size x y, world min x y, world max x y, unknown / free / occupied cells, grid hash hi lo
             final["ros_map_info"] = np.frombuffer(p, dtype="<f8").copy()
+        elif tag == "SMPP":  # ScanMatcherProcessor: pose after every reading
+            final["smp_poses"] = np.frombuffer(p, dtype="<f8").reshape(-1, 3).copy()
+        elif tag == "SMPD":
+            final["smp_digest"] = np.frombuffer(p, dtype=DIGEST_DTYPE).copy()
+        elif tag == "SMPG":
+            final["smp_geometry"] = np.frombuffer(p, dtype="<i4").copy()
         elif tag == "DONE":
             pass
         else:

@@ -1,0 +1,52 @@
+// scanmatcherprocessor.h -- GMapping::ScanMatcherProcessor with the reference's API
+// (include/gmapping/scanmatcher/scanmatcherprocessor.h): incremental scan matching against ONE map, no particle filter
+// (SURVEY.md §8 row f4).  The map is an ordinary ScanMatcherMap; the first matcher call makes it device-resident
+// (single-map context), so optimize() and registerScan() run in the same sm_100a kernels as the particle filter's.
+#ifndef GMB200_SCANMATCHERPROCESSOR_H
+#define GMB200_SCANMATCHERPROCESSOR_H
+#include <gmapping/log/sensorlog.h>
+#include <gmapping/scanmatcher/scanmatcher.h>
+#include <gmapping/scanmatcher/scanmatcher_export.h>
+#include <gmapping/sensor/sensor_range/rangereading.h>
+#include <gmapping/sensor/sensor_range/rangesensor.h>
+
+#include <string>
+
+namespace GMapping {
+
+class SCANMATCHER_EXPORT ScanMatcherProcessor {
+  public:
+    // an empty map with the frame (centre, world size, resolution) of `m`
+    ScanMatcherProcessor(const ScanMatcherMap& m);
+    ScanMatcherProcessor(double xmin, double ymin, double xmax, double ymax, double delta, double patchdelta);
+    virtual ~ScanMatcherProcessor();
+    // odometry step since the last reading rotated into the map frame -> hill-climb from there -> register the scan when the
+    // match is poor enough to need it (score < regScore), at the odometry pose when it is worse than critScore
+    virtual void processScan(const RangeReading& reading);
+    void setSensorMap(const SensorMap& smap, std::string sensorName = "FLASER");
+    void init();
+    void setMatchingParameters(double urange, double range, double sigma, int kernsize, double lopt, double aopt, int iterations,
+                               bool computeCovariance = false);
+    void setRegistrationParameters(double regScore, double critScore);
+    OrientedPoint getPose() const;
+    inline const ScanMatcherMap& getMap() const { return m_map; }
+    inline ScanMatcher& matcher() { return m_matcher; }
+    inline void setmaxMove(double mmove) { m_maxMove = mmove; }
+    bool useICP;
+
+  protected:
+    ScanMatcher m_matcher;
+    bool m_computeCovariance;
+    bool m_first;
+    SensorMap m_sensorMap;
+    double m_regScore, m_critScore;
+    unsigned int m_beams;
+    double m_maxMove;
+    ScanMatcherMap m_map;
+    OrientedPoint m_pose;
+    OrientedPoint m_odoPose;
+    int m_count;
+};
+
+}  // namespace GMapping
+#endif

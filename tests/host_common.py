@@ -148,6 +148,11 @@ def check_trace(case, g, tr, exact=False):
     got, want = fin["trajectories"], g.trajectories
     assert np.array_equal(got[:, [0, 5, 6, 7, 8]], want[:, [0, 5, 6, 7, 8]]) and not got[:, 8].any(), "%s: getTrajectories() tree shape" % case
     np.testing.assert_allclose(got[:, 1:5], want[:, 1:5], rtol=rtol4, atol=0 if exact else 1e-3, err_msg="%s: getTrajectories() poses / accWeight" % case)
+    # ScanMatcherProcessor (scanmatcher/scanmatcherprocessor.cpp): incremental matching against one map
+    assert fin["smp_poses"].shape == g.smp_poses.shape
+    assert np.abs(fin["smp_poses"] - g.smp_poses).max() <= ptol, "%s: ScanMatcherProcessor poses" % case
+    assert np.array_equal(digest_rows(fin["smp_digest"])[:, :5], digest_rows(g.smp_digest)[:, :5]), "%s: ScanMatcherProcessor map" % case
+    assert np.array_equal(fin["smp_geometry"], g.smp_geometry), "%s: ScanMatcherProcessor map geometry" % case
     # the .gfs trace (gridslamprocessor.cpp:454-475, 570-606; gridslamprocessor.hxx:159-167): the same records in the same order;
     # with the reference's arithmetic underneath (mock) the same bytes
     tags = " ".join(l.split(b" ", 1)[0].decode() for l in tr["gfs"].splitlines() if l)

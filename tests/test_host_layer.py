@@ -57,7 +57,8 @@ def test_reference_consumer_compiles_against_our_headers():
     assert os.path.exists(exe)
     out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(HOST, "libgridfastslam_b200.so")], capture_output=True, text=True).stdout
     for sym in ("GridSlamProcessor11processScan", "GridSlamProcessor4init", "ScanMatcher12registerScan", "ScanMatcher8optimize",
-                "MotionModel14drawFromMotion", "CarmenConfiguration16computeSensorMap", "sampleGaussian"):
+                "MotionModel14drawFromMotion", "CarmenConfiguration16computeSensorMap", "sampleGaussian",
+                "ScanMatcherProcessor11processScan"):
         assert sym in out, sym
 
 
