@@ -167,3 +167,11 @@ def check_trace(case, g, tr, exact=False):
         assert np.array_equal(got, want), "%s: map rebuilt from the best trajectory, float accumulators" % case
     assert np.array_equal(fin["ros_map_info"], g.ros_map_info), "%s: occupancy grid of the rebuilt map (size, origin, cell counts, hash)" % case
     assert k_dig >= 1
+
+
+def free_port():
+    """a TCP port nobody listens on right now (torch.distributed rendezvous of the multi-process CPU tests)"""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]

@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from host_common import PKG, build_host
+from host_common import PKG, build_host, free_port
 from oracle import orc
 
 
@@ -67,7 +67,7 @@ def test_migration_plan_two_ranks_gloo():
     build_host()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 500)
+    port = free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, 64, q)) for r in range(2)]
     for p in procs:
         p.start()

@@ -12,7 +12,7 @@ import sys
 import pytest
 
 from common import CASES
-from host_common import ROOT, check_trace, free_run, mock_env
+from host_common import ROOT, check_trace, free_port, free_run, mock_env
 
 import os
 
@@ -35,7 +35,7 @@ def test_sharded_filter_two_ranks_on_the_mock(tmp_path):
     reference trace bit for bit; resampled parents cross the rank boundary (tests/dist_check.py asserts that they do)"""
     env = mock_env()
     env["GM_MOCK_DIST_DIR"] = str(tmp_path)
-    port = 29700 + (os.getpid() % 200)
+    port = free_port()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "dist_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
