@@ -24,6 +24,7 @@
 
 #include <gmapping/gridfastslam/gridslamprocessor.h>
 #include <gmapping/log/carmenconfiguration.h>
+#include <gmapping/log/sensorlog.h>
 #include <gmapping/log/sensorstream.h>
 #include <gmapping/scanmatcher/scanmatcherprocessor.h>
 #include <gmapping/utils/stat.h>
@@ -414,6 +415,15 @@ int main(int argc, char** argv) {
         gsp.dumpTrajectories();
         gsp.dumpRosMap(o.xmin, o.ymin, o.xmax, o.ymax, o.delta, o.maxrange, o.maxurange, 0.25);
         dumpScanMatcherProcessor(gsp.w, sensorMap, o.log, o, 12);
+        {   // SensorLog (log/sensorlog.cpp): the whole log in memory and the bounding box gfs_nogui's -autosize uses
+            SensorLog slog(sensorMap);
+            std::ifstream ls(o.log.c_str());
+            slog.load(ls);
+            double bx0, by0, bx1, by1;
+            const OrientedPoint start = slog.boundingBox(bx0, by0, bx1, by1);
+            const double row[8] = {(double)slog.size(), bx0, by0, bx1, by1, start.x, start.y, start.theta};
+            gsp.w.rec("BBOX", row, sizeof row);
+        }
         gsp.w.rec("DONE", nullptr, 0);
         fclose(gsp.w.f);
     }

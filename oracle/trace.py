@@ -87,6 +87,8 @@ def read_trace(path):
             final["smp_digest"] = np.frombuffer(p, dtype=DIGEST_DTYPE).copy()
         elif tag == "SMPG":
             final["smp_geometry"] = np.frombuffer(p, dtype="<i4").copy()
+        elif tag == "BBOX":  # SensorLog: readings, boundingBox xmin ymin xmax ymax, first range pose
+            final["sensorlog_bbox"] = np.frombuffer(p, dtype="<f8").copy()
         elif tag == "DONE":
             pass
         else:

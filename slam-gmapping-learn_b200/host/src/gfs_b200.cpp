@@ -5,9 +5,15 @@
 //            [-lstep m] [-astep rad] [-iterations n] [-lsigma s] [-ogain g] [-lskip n] [-srr v -srt v -str v -stt v]
 //            [-linearUpdate m] [-angularUpdate rad] [-resampleThreshold f] [-xmin m -ymin m -xmax m -ymax m -delta m]
 //            [-randseed s] [-scans n] [-no-generateMap] [-verbose]
-// Defaults are gfs-carmen's (gfs-carmen/gfs-carmen.cpp:52-84).
+//            [-lobsGain g] [-generateMap] [-autosize] [-minimumScore s] [-maxMove m] [-regscore s] [-critscore s]
+//            [-linearOdometryReliability v] [-angularOdometryReliability v] [-llsamplerange v] [-llsamplestep v]
+//            [-lasamplerange v] [-lasamplestep v]                      (the option names of gui/gsp_thread.cpp:97-144)
+// Defaults are gfs-carmen's (gfs-carmen/gfs-carmen.cpp:52-84).  -autosize sizes the map like gfs_nogui does
+// (gsp_thread.cpp:315-324, 634-642): the extent of the poses in the log (SensorLog::boundingBox) grown by three times the
+// maximum range, and the filter starts at the first range reading's pose.
 #include <gmapping/gridfastslam/gridslamprocessor.h>
 #include <gmapping/log/carmenconfiguration.h>
+#include <gmapping/log/sensorlog.h>
 #include <gmapping/log/sensorstream.h>
 #include <gmapping/utils/stat.h>
 
@@ -28,12 +34,17 @@ int main(int argc, char** argv) {
         {"particles", 30}, {"maxUrange", 80}, {"maxrange", 80}, {"sigma", 0.05}, {"kernelSize", 1}, {"lstep", 0.05}, {"astep", 0.05},
         {"iterations", 5}, {"lsigma", 0.075}, {"ogain", 3}, {"lskip", 0}, {"srr", 0.01}, {"srt", 0.01}, {"str", 0.01}, {"stt", 0.01},
         {"linearUpdate", 1.0}, {"angularUpdate", 0.5}, {"resampleThreshold", 0.5}, {"xmin", -100}, {"ymin", -100}, {"xmax", 100},
-        {"ymax", 100}, {"delta", 0.05}, {"randseed", 0}, {"scans", 1e9}, {"minimumScore", 0}, {"period", -1}};
+        {"ymax", 100}, {"delta", 0.05}, {"randseed", 0}, {"scans", 1e9}, {"minimumScore", 0}, {"period", -1},
+        {"maxMove", 1}, {"regscore", 1e4}, {"critscore", 0}, {"linearOdometryReliability", 0}, {"angularOdometryReliability", 0},
+        {"llsamplerange", 0.01}, {"llsamplestep", 0.01}, {"lasamplerange", 0.005}, {"lasamplestep", 0.005}};
     std::string filename, outfilename;
-    bool generateMap = true, verbose = false;
+    bool generateMap = true, verbose = false, autosize = false;
     for (int i = 1; i < argc; i++) {
-        const std::string a = argv[i];
+        std::string a = argv[i];
         if (a == "-no-generateMap") { generateMap = false; continue; }
+        if (a == "-generateMap") { generateMap = true; continue; }
+        if (a == "-autosize") { autosize = true; continue; }
+        if (a == "-lobsGain") a = "-ogain";  // gfs_nogui's name for the likelihood gain
         if (a == "-verbose") { verbose = true; continue; }
         if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); return 2; }
         if (a == "-filename") { filename = argv[++i]; continue; }
@@ -63,6 +74,24 @@ int main(int argc, char** argv) {
     gsp.setUpdatePeriod(num["period"]);
     gsp.setgenerateMap(generateMap);
     gsp.setminimumScore(num["minimumScore"]);
+    gsp.setmaxMove(num["maxMove"]);
+    gsp.setregScore(num["regscore"]);
+    gsp.setcritScore(num["critscore"]);
+    gsp.m_matcher.setlinearOdometryReliability(num["linearOdometryReliability"]);
+    gsp.m_matcher.setangularOdometryReliability(num["angularOdometryReliability"]);
+    gsp.setllsamplerange(num["llsamplerange"]);
+    gsp.setllsamplestep(num["llsamplestep"]);
+    gsp.setlasamplerange(num["lasamplerange"]);
+    gsp.setlasamplestep(num["lasamplestep"]);
+    OrientedPoint autoStart;
+    if (autosize) {
+        SensorLog whole(sensorMap);
+        std::ifstream all(filename.c_str());
+        whole.load(all);
+        autoStart = whole.boundingBox(num["xmin"], num["ymin"], num["xmax"], num["ymax"]);
+        const double margin = 3 * num["maxrange"];
+        num["xmin"] -= margin; num["ymin"] -= margin; num["xmax"] += margin; num["ymax"] += margin;
+    }
     if (!outfilename.empty()) gsp.outputStream().open(outfilename.c_str());
 
     bool inited = false;
@@ -76,7 +105,7 @@ int main(int argc, char** argv) {
         const RangeReading* rr = dynamic_cast<const RangeReading*>(r);
         if (rr) {
             if (!inited) {
-                gsp.init((unsigned int)num["particles"], num["xmin"], num["ymin"], num["xmax"], num["ymax"], num["delta"], rr->getPose());
+                gsp.init((unsigned int)num["particles"], num["xmin"], num["ymin"], num["xmax"], num["ymax"], num["delta"], autosize ? autoStart : rr->getPose());
                 if (num["randseed"] != 0) sampleGaussian(1, (unsigned long)num["randseed"]);
                 inited = true;
             }
@@ -103,8 +132,8 @@ int main(int argc, char** argv) {
     const int best = inited ? gsp.getBestParticleIndex() : -1;
     const int matched = processedN > 1 ? processedN - 1 : 0;
     printf("{\"impl\": \"b200\", \"particles\": %d, \"read\": %d, \"processed\": %d, \"ms_total\": %.3f, \"ms_per_matched_scan\": %.4f, "
-           "\"device_ms_per_matched_scan\": %.4f, \"beam_evals_per_matched_scan\": %.0f, \"best_particle\": %d}\n",
+           "\"device_ms_per_matched_scan\": %.4f, \"beam_evals_per_matched_scan\": %.0f, \"best_particle\": %d, \"map\": [%.3f, %.3f, %.3f, %.3f]}\n",
            (int)num["particles"], readN, processedN, msTotal, matched ? msMatched / matched : 0.0, matched ? msDevice / matched : 0.0,
-           matched ? (double)beamEvals / matched : 0.0, best);
+           matched ? (double)beamEvals / matched : 0.0, best, num["xmin"], num["ymin"], num["xmax"], num["ymax"]);
     return 0;
 }

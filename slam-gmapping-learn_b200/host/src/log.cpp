@@ -193,17 +193,27 @@ std::istream& SensorLog::load(std::istream& is) {
     }
     return is;
 }
+// Extent of the poses in the log and the pose of the first range reading (reference: log/sensorlog.cpp:121-150), with the
+// reference's behaviour kept where it is odd, because gfs_nogui-style drivers size their maps from it (-autosize):
+//   * odometry readings and range readings both count; a reading of any other kind counts as the point (0, 0);
+//   * ymin is NOT a minimum: the reference assigns the current y on both branches of its comparison, so ymin ends up as
+//     the y of the last reading of the log.
 OrientedPoint SensorLog::boundingBox(double& xmin, double& ymin, double& xmax, double& ymax) const {
-    xmin = ymin = 1e6; xmax = ymax = -1e6;
-    bool first = true;
+    xmin = ymin = 1e6;
+    xmax = ymax = -1e6;
     OrientedPoint start;
+    bool haveStart = false;
     for (const_iterator it = begin(); it != end(); ++it) {
-        const RangeReading* rr = dynamic_cast<const RangeReading*>(*it);
-        if (!rr) continue;
-        const OrientedPoint p = rr->getPose();
-        if (first) { start = p; first = false; }
-        xmin = xmin < p.x ? xmin : p.x; ymin = ymin < p.y ? ymin : p.y;
-        xmax = xmax > p.x ? xmax : p.x; ymax = ymax > p.y ? ymax : p.y;
+        double x = 0., y = 0.;
+        if (const OdometryReading* o = dynamic_cast<const OdometryReading*>(*it)) { x = o->getPose().x; y = o->getPose().y; }
+        if (const RangeReading* rr = dynamic_cast<const RangeReading*>(*it)) {
+            x = rr->getPose().x; y = rr->getPose().y;
+            if (!haveStart) { start = rr->getPose(); haveStart = true; }
+        }
+        if (x < xmin) xmin = x;
+        if (x > xmax) xmax = x;
+        ymin = y;  // sic
+        if (y > ymax) ymax = y;
     }
     return start;
 }

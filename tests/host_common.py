@@ -148,6 +148,8 @@ def check_trace(case, g, tr, exact=False):
     got, want = fin["trajectories"], g.trajectories
     assert np.array_equal(got[:, [0, 5, 6, 7, 8]], want[:, [0, 5, 6, 7, 8]]) and not got[:, 8].any(), "%s: getTrajectories() tree shape" % case
     np.testing.assert_allclose(got[:, 1:5], want[:, 1:5], rtol=rtol4, atol=0 if exact else 1e-3, err_msg="%s: getTrajectories() poses / accWeight" % case)
+    # SensorLog::load + boundingBox (log/sensorlog.cpp): readings in the log, extent (with the reference's ymin quirk), first pose
+    assert np.array_equal(fin["sensorlog_bbox"], g.sensorlog_bbox), "%s: SensorLog::boundingBox %r != %r" % (case, fin["sensorlog_bbox"], g.sensorlog_bbox)
     # ScanMatcherProcessor (scanmatcher/scanmatcherprocessor.cpp): incremental matching against one map
     assert fin["smp_poses"].shape == g.smp_poses.shape
     assert np.abs(fin["smp_poses"] - g.smp_poses).max() <= ptol, "%s: ScanMatcherProcessor poses" % case

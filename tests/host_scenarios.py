@@ -45,6 +45,15 @@ def scenario_cli():
         want = g.neff[g.processed & ~np.isnan(g.smat[:, 0, 0])]
         # the .gfs NEFF record is written before resampling: compare with the reference where no resample happened
         assert len(neff) == len(want)
+        # gfs_nogui's option names and -autosize (gui/gsp_thread.cpp:97-144, 315-324, 634-642): the map is sized from the poses
+        # in the log (SensorLog::boundingBox, golden) grown by 3 x maxrange, and the filter starts at the first range pose
+        res = subprocess.run([os.path.join(HOST, "gfs_b200"), "-filename", lp, "-particles", "4", "-randseed", "12345", "-autosize", "-maxrange", "20",
+                              "-maxUrange", "20", "-lobsGain", "3", "-generateMap", "-scans", "3", "-linearOdometryReliability", "0", "-llsamplerange", "0.01"],
+                             capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stderr[-2000:]
+        info = json.loads(res.stdout.strip().splitlines()[-1])
+        bb = g.sensorlog_bbox
+        assert np.allclose(info["map"], [bb[1] - 60, bb[2] - 60, bb[3] + 60, bb[4] + 60], atol=1e-3) and info["processed"] == 3
 
 
 def scenario_clone():
