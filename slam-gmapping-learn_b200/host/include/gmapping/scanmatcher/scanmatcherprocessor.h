@@ -16,36 +16,40 @@ namespace GMapping {
 
 class SCANMATCHER_EXPORT ScanMatcherProcessor {
   public:
-    // an empty map with the frame (centre, world size, resolution) of `m`
+    // ---- construction: an empty map with the frame (centre, world size, resolution) of `m`, or from explicit bounds
     ScanMatcherProcessor(const ScanMatcherMap& m);
     ScanMatcherProcessor(double xmin, double ymin, double xmax, double ymax, double delta, double patchdelta);
     virtual ~ScanMatcherProcessor();
-    // odometry step since the last reading rotated into the map frame -> hill-climb from there -> register the scan when the
-    // match is poor enough to need it (score < regScore), at the odometry pose when it is worse than critScore
-    virtual void processScan(const RangeReading& reading);
+
+    // ---- configuration
     void setSensorMap(const SensorMap& smap, std::string sensorName = "FLASER");
-    void init();
     void setMatchingParameters(double urange, double range, double sigma, int kernsize, double lopt, double aopt, int iterations,
                                bool computeCovariance = false);
     void setRegistrationParameters(double regScore, double critScore);
+    void setmaxMove(double mmove) { m_maxMove = mmove; }
+    ScanMatcher& matcher() { return m_matcher; }
+    bool useICP;  // icpOptimize instead of the hill-climb (not on the B200 path: aborts when used)
+
+    // ---- operation
+    void init();
+    // odometry step since the last reading rotated into the map frame -> hill-climb from there -> register the scan when the
+    // match is poor enough to need it (score < regScore), at the odometry pose when it is worse than critScore
+    virtual void processScan(const RangeReading& reading);
     OrientedPoint getPose() const;
-    inline const ScanMatcherMap& getMap() const { return m_map; }
-    inline ScanMatcher& matcher() { return m_matcher; }
-    inline void setmaxMove(double mmove) { m_maxMove = mmove; }
-    bool useICP;
+    const ScanMatcherMap& getMap() const { return m_map; }
 
   protected:
-    ScanMatcher m_matcher;
-    bool m_computeCovariance;
-    bool m_first;
-    SensorMap m_sensorMap;
-    double m_regScore, m_critScore;
-    unsigned int m_beams;
-    double m_maxMove;
+    // what is being estimated
     ScanMatcherMap m_map;
-    OrientedPoint m_pose;
-    OrientedPoint m_odoPose;
-    int m_count;
+    OrientedPoint m_pose, m_odoPose;  // pose estimate; odometry pose of the previous reading
+    int m_count;                      // readings integrated so far
+    bool m_first;
+    // how
+    ScanMatcher m_matcher;
+    SensorMap m_sensorMap;
+    unsigned int m_beams;
+    double m_regScore, m_critScore, m_maxMove;
+    bool m_computeCovariance;
 };
 
 }  // namespace GMapping

@@ -15,14 +15,14 @@ const double kDefaultMaxMove = 1.;     // squared odometry jump (m^2) above whic
 }  // namespace
 
 ScanMatcherProcessor::ScanMatcherProcessor(const ScanMatcherMap& m)
-    : useICP(false), m_computeCovariance(false), m_first(true), m_regScore(kDefaultRegScore), m_critScore(.5 * kDefaultRegScore), m_beams(0),
-      m_maxMove(kDefaultMaxMove), m_map(m.getCenter(), m.getWorldSizeX(), m.getWorldSizeY(), m.getResolution()), m_pose(0, 0, 0), m_count(0) {}
+    : useICP(false), m_map(m.getCenter(), m.getWorldSizeX(), m.getWorldSizeY(), m.getResolution()), m_pose(0, 0, 0), m_count(0), m_first(true),
+      m_beams(0), m_regScore(kDefaultRegScore), m_critScore(.5 * kDefaultRegScore), m_maxMove(kDefaultMaxMove), m_computeCovariance(false) {}
 
 // the reference passes `patchdelta`, not `delta`, as the map resolution (scanmatcherprocessor.cpp:25-27); kept
 ScanMatcherProcessor::ScanMatcherProcessor(double xmin, double ymin, double xmax, double ymax, double delta, double patchdelta)
-    : useICP(false), m_computeCovariance(false), m_first(true), m_regScore(kDefaultRegScore), m_critScore(.5 * kDefaultRegScore), m_beams(0),
-      m_maxMove(kDefaultMaxMove), m_map(Point((xmax + xmin) * .5, (ymax + ymin) * .5), xmax - xmin, ymax - ymin, patchdelta), m_pose(0, 0, 0),
-      m_count(0) {
+    : useICP(false), m_map(Point((xmax + xmin) * .5, (ymax + ymin) * .5), xmax - xmin, ymax - ymin, patchdelta), m_pose(0, 0, 0), m_count(0),
+      m_first(true), m_beams(0), m_regScore(kDefaultRegScore), m_critScore(.5 * kDefaultRegScore), m_maxMove(kDefaultMaxMove),
+      m_computeCovariance(false) {
     (void)delta;
 }
 
