@@ -20,7 +20,7 @@ from common import CASES, Golden  # noqa: E402
 from host_common import driver_args, golden_log  # noqa: E402
 
 HOST = os.path.join(ROOT, "slam-gmapping-learn_b200", "host")
-SRCS = [os.path.join(HOST, "src", f) for f in ("utils.cpp", "motionmodel.cpp", "log.cpp", "devicemap.cpp", "scanmatcher.cpp", "gridslamprocessor.cpp")]
+SRCS = [os.path.join(HOST, "src", f) for f in ("utils.cpp", "motionmodel.cpp", "log.cpp", "devicemap.cpp", "scanmatcher.cpp", "scanmatcherprocessor.cpp", "gridslamprocessor.cpp")]
 CSRC = [os.path.join(ROOT, "tests", "mock", "gm_mock.c"), os.path.join(ROOT, "oracle", "gm_oracle.c")]
 FLAGS = ["-g", "-O1", "-std=c++14", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-w", "-I", os.path.join(HOST, "include"),
          "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "oracle")]
