@@ -159,9 +159,43 @@ def run_long(name="room181_long", scans=1000, particles=30):
     print("%-18s readings %4d processed %4d resamples %3d  %7.1f KB" % (name, S, int(processed.sum()), int(resampled.sum()), os.path.getsize(path) / 1024))
 
 
+def run_units(name="units"):
+    """Known-answer vectors of the building blocks (Bresenham lines, systematic resampling, Gaussian sampler, motion model,
+    world2map) straight from the reference: oracle/_ref/ref_units (oracle/ref_units.cpp) -> tests/golden/units.npz."""
+    import struct
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_units")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    with tempfile.TemporaryDirectory() as td:
+        bp = os.path.join(td, "units.bin")
+        subprocess.run([exe, bp], check=True)
+        buf = open(bp, "rb").read()
+    off = 0
+    out = {}
+    rs_n, rs_seed, rs_w, rs_idx = [], [], [], []
+    while off < len(buf):
+        tag = buf[off:off + 4].decode(); n = struct.unpack_from("<Q", buf, off + 4)[0]
+        p = buf[off + 12:off + 12 + n]; off += 12 + n
+        if tag == "LINE": out["lines"] = np.frombuffer(p, dtype="<i8").reshape(-1, 6).copy()
+        elif tag == "RSHD": h = np.frombuffer(p, dtype="<f8"); rs_n.append(int(h[0])); rs_seed.append(int(h[1]))
+        elif tag == "RSWT": rs_w.append(np.frombuffer(p, dtype="<f8").copy())
+        elif tag == "RSIX": rs_idx.append(np.frombuffer(p, dtype="<u4").copy())
+        elif tag == "GAUS": out["gauss"] = np.frombuffer(p, dtype="<f8").copy()
+        elif tag == "MOTN": out["motion"] = np.frombuffer(p, dtype="<f8").copy()
+        elif tag == "W2MP": out["w2m"] = np.frombuffer(p, dtype="<f8").reshape(-1, 8).copy()
+        else: raise ValueError(tag)
+    out.update(rs_n=np.array(rs_n), rs_seed=np.array(rs_seed), rs_w=np.concatenate(rs_w), rs_idx=np.concatenate(rs_idx))
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("%-18s lines %d resample cases %d gaussians %d motion rows %d world2map rows %d  %6.1f KB" % (
+        name, len(out["lines"]), len(rs_n), len(out["gauss"]) - 1, (len(out["motion"]) - 1) // 12, len(out["w2m"]), os.path.getsize(path) / 1024))
+
+
 def main():
     if "long" in sys.argv[1:]:
         run_long(); return
+    if "units" in sys.argv[1:]:
+        run_units(); return
     if not os.path.exists(REF):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
     os.makedirs(GOLD, exist_ok=True)
