@@ -41,3 +41,22 @@ def test_sharded_filter_two_ranks_on_the_mock(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert res.returncode == 0, (res.stdout[-2000:], res.stderr[-4000:])
     assert "dist_check room181_n30: ok" in res.stdout and "dist_check room181_k2_lskip: ok" in res.stdout
+
+
+def test_building_blocks_of_the_host_layer_are_the_references(tmp_path):
+    """oracle/ref_units.cpp -- written against the reference's headers: GridLineTraversal::gridLine, uniform_resampler,
+    sampleGaussian, MotionModel::drawFromMotion, ScanMatcherMap::world2map / map2world / isInside -- compiled UNCHANGED against
+    our include tree and libraries writes the same bytes as when it is linked with the reference (sha256 in tests/golden/units.npz).
+    No device is involved: none of these calls reaches the C ABI."""
+    import hashlib
+    import numpy as np
+    from host_common import HOST, PKG, build_host
+    build_host()
+    exe, out = str(tmp_path / "units_b200"), str(tmp_path / "units.bin")
+    subprocess.check_call(["g++", "-O2", "-std=c++14", "-ffp-contract=off", "-w", "-I", os.path.join(HOST, "include"), "-I", os.path.join(ROOT, "include"),
+                           "-o", exe, os.path.join(ROOT, "oracle", "ref_units.cpp"), "-L", HOST, "-lgridfastslam_b200", "-L", PKG, "-lgm_b200",
+                           "-Wl,-rpath," + HOST, "-Wl,-rpath," + PKG])
+    subprocess.check_call([exe, out])
+    z = np.load(os.path.join(ROOT, "tests", "golden", "units.npz"))
+    data = open(out, "rb").read()
+    assert len(data) == int(z["units_bytes"]) and hashlib.sha256(data).hexdigest() == str(z["units_sha256"])

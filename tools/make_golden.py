@@ -171,7 +171,7 @@ def run_units(name="units"):
         subprocess.run([exe, bp], check=True)
         buf = open(bp, "rb").read()
     off = 0
-    out = {}
+    out = {"units_sha256": np.array(hashlib.sha256(buf).hexdigest()), "units_bytes": np.array(len(buf))}
     rs_n, rs_seed, rs_w, rs_idx = [], [], [], []
     while off < len(buf):
         tag = buf[off:off + 4].decode(); n = struct.unpack_from("<Q", buf, off + 4)[0]
