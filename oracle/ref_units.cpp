@@ -5,6 +5,7 @@
 //   sampleGaussian / pf_ran_gaussian     utils/stat.cpp:31-65
 //   MotionModel::drawFromMotion          gridfastslam/motionmodel.cpp:40-60
 //   Map::world2map / map2world           include/gmapping/grid/map.h:283-298
+//   point / orientedpoint algebra        include/gmapping/utils/point.h:22-220;  evalLogGaussian  utils/stat.cpp:73-77
 // Output: one binary file of tagged records (the format of ref_driver's traces), turned into tests/golden/units.npz by
 // tools/make_golden.py units.  The inputs come from a fixed 64-bit LCG so that the test can regenerate them.
 #include <cstdint>
@@ -136,6 +137,22 @@ int main(int argc, char** argv) {
             }
         }
         rec("W2MP", rows.data(), rows.size() * sizeof(double));
+    }
+    // ---- point algebra (utils/point.h) and evalLogGaussian (utils/stat.cpp): rows of 23 doubles per random pair of poses
+    {
+        std::vector<double> rows;
+        for (int k = 0; k < 500; k++) {
+            const OrientedPoint a(uni() * 40 - 20, uni() * 40 - 20, uni() * 12 - 6), b(uni() * 40 - 20, uni() * 40 - 20, uni() * 12 - 6);
+            const Point q(uni() * 4 - 2, uni() * 4 - 2);
+            const double v = uni() * 3 - 1.5;
+            const OrientedPoint d = absoluteDifference(a, b), s = absoluteSum(a, b), plus = a + b, minus = a - b, scaled = a * v;
+            const Point moved = absoluteSum(a, q), pq = Point(a.x, a.y) - q;
+            const double row[23] = {d.x, d.y, d.theta, s.x, s.y, s.theta, plus.x, plus.y, plus.theta, minus.x, minus.y, minus.theta,
+                                    scaled.x, scaled.y, scaled.theta, moved.x, moved.y, pq * q, euclidianDist(a, b), euclidianDist(a, q),
+                                    euclidianDist(q, a), evalLogGaussian(k % 9 == 0 ? -1. : uni() * 2, uni() * 3 - 1.5), (double)k};
+            rows.insert(rows.end(), row, row + 23);
+        }
+        rec("PTOP", rows.data(), rows.size() * sizeof(double));
     }
     fclose(g_f);
     return 0;
