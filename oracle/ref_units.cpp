@@ -154,6 +154,74 @@ int main(int argc, char** argv) {
         }
         rec("PTOP", rows.data(), rows.size() * sizeof(double));
     }
+    // ---- ScanMatcherMap / HierarchicalArray2D / PointAccumulator on the host (grid/map.h, grid/harray2d.h, scanmatcher/smmap.h):
+    // on-demand patch allocation through the non-const cell(), copies that SHARE patches until allocActiveArea() gives the
+    // active ones a private copy, resize (crop + extend), toDoubleMap.  One summary row per stage.
+    {
+        std::vector<double> rows;
+        struct Sum {
+            static void of(const ScanMatcherMap& m, std::vector<double>& out) {
+                double patches = 0, cells = 0, n = 0, visits = 0, occ = 0, ent = 0, mx = 0, my = 0;
+                uint64_t h = 0;
+                const HierarchicalArray2D<PointAccumulator>& st = m.storage();
+                for (int px = 0; px < st.getXSize(); px++)
+                    for (int py = 0; py < st.getYSize(); py++) {
+                        if (!st.m_cells[px][py].m_reference) continue;
+                        patches++;
+                        const Array2D<PointAccumulator>& patch = *st.m_cells[px][py];
+                        for (int lx = 0; lx < 32; lx++)
+                            for (int ly = 0; ly < 32; ly++) {
+                                const PointAccumulator& a = patch.m_cells[lx][ly];
+                                if (!a.visits && !a.n) continue;
+                                cells++; n += a.n; visits += a.visits; occ += (double)a; ent += a.entropy();
+                                if (a.n) { const Point mu = a.mean(); mx += mu.x; my += mu.y; }
+                                uint32_t ax, ay; memcpy(&ax, &a.acc.x, 4); memcpy(&ay, &a.acc.y, 4);
+                                h += mix64(((uint64_t)(uint32_t)(px * 32 + lx) << 32 | (uint32_t)(py * 32 + ly)) ^ mix64(((uint64_t)ax << 32) | ay) ^ ((uint64_t)a.n << 20) ^ (uint64_t)a.visits);
+                            }
+                    }
+                const IntPoint c = m.world2map(m.getCenter());
+                const double row[16] = {patches, cells, n, visits, occ, ent, mx, my, (double)(h >> 32), (double)(h & 0xffffffffu), (double)c.x, (double)c.y,
+                                        (double)m.getMapSizeX(), (double)m.getMapSizeY(), (double)st.getXSize(), (double)st.getYSize()};
+                out.insert(out.end(), row, row + 16);
+            }
+        };
+        ScanMatcherMap map(Point(1.0, -2.0), 20., 16., 0.05);
+        for (int k = 0; k < 3000; k++) {
+            const Point p(1.0 + (uni() - .5) * 14, -2.0 + (uni() - .5) * 10);
+            const IntPoint ip = map.world2map(p);
+            if (map.isInside(ip)) map.cell(ip).update(k % 3 != 0, p);
+        }
+        Sum::of(map, rows);
+        ScanMatcherMap copy(map);  // shares every patch with `map`
+        for (int k = 0; k < 500; k++) {
+            const Point p(1.0 + (uni() - .5) * 6, -2.0 + (uni() - .5) * 6);
+            const IntPoint ip = copy.world2map(p);
+            if (copy.isInside(ip)) copy.cell(ip).update(true, p);  // lands in the shared patch (or in a new one owned by the copy)
+        }
+        Sum::of(map, rows); Sum::of(copy, rows);
+        HierarchicalArray2D<PointAccumulator>::PointSet active;
+        for (int k = 0; k < 40; k++) active.insert(copy.storage().patchIndexes(copy.world2map(Point(1.0 + (uni() - .5) * 8, -2.0 + (uni() - .5) * 8))));
+        copy.storage().setActiveArea(active, true);
+        copy.storage().allocActiveArea();  // private copies of the active patches
+        for (int k = 0; k < 500; k++) {
+            const Point p(1.0 + (uni() - .5) * 8, -2.0 + (uni() - .5) * 8);
+            const IntPoint ip = copy.world2map(p);
+            if (copy.isInside(ip)) copy.cell(ip).update(k % 2 == 0, p);
+        }
+        Sum::of(map, rows); Sum::of(copy, rows);
+        copy.resize(-6.3, -9.1, 12.7, 3.2);  // crops on one side, extends on the other
+        Sum::of(copy, rows);
+        {
+            Map<double, DoubleArray2D, false>* dm = copy.toDoubleMap();
+            double s = 0, unknown = 0;
+            for (int x = 0; x < dm->getMapSizeX(); x++)
+                for (int y = 0; y < dm->getMapSizeY(); y++) { const double v = dm->cell(IntPoint(x, y)); if (v < 0) unknown++; else s += v * (1 + (x % 7) + 3 * (y % 5)); }
+            const double row[16] = {s, unknown, (double)dm->getMapSizeX(), (double)dm->getMapSizeY()};
+            rows.insert(rows.end(), row, row + 16);
+            delete dm;
+        }
+        rec("HMAP", rows.data(), rows.size() * sizeof(double));
+    }
     fclose(g_f);
     return 0;
 }

@@ -183,6 +183,7 @@ def run_units(name="units"):
         elif tag == "GAUS": out["gauss"] = np.frombuffer(p, dtype="<f8").copy()
         elif tag == "MOTN": out["motion"] = np.frombuffer(p, dtype="<f8").copy()
         elif tag == "W2MP": out["w2m"] = np.frombuffer(p, dtype="<f8").reshape(-1, 8).copy()
+        elif tag == "HMAP": out["host_map"] = np.frombuffer(p, dtype="<f8").reshape(-1, 16).copy()
         elif tag == "PTOP": out["point_ops"] = np.frombuffer(p, dtype="<f8").reshape(-1, 23).copy()
         else: raise ValueError(tag)
     out.update(rs_n=np.array(rs_n), rs_seed=np.array(rs_seed), rs_w=np.concatenate(rs_w), rs_idx=np.concatenate(rs_idx))
