@@ -60,3 +60,17 @@ def test_building_blocks_of_the_host_layer_are_the_references(tmp_path):
     z = np.load(os.path.join(ROOT, "tests", "golden", "units.npz"))
     data = open(out, "rb").read()
     assert len(data) == int(z["units_bytes"]) and hashlib.sha256(data).hexdigest() == str(z["units_sha256"])
+
+
+def test_mock_implements_the_whole_c_abi():
+    """the CPU mock must keep up with include/gm_b200.h: every declared entry point is defined by it (gm_dist_plan, host-only
+    planning code without device work, is the product's own)"""
+    import ctypes
+    import re
+    from host_common import build_mock
+    hdr = open(os.path.join(ROOT, "include", "gm_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(gm_[a-z_]+)\s*\(", hdr)) - {"gm_ctx", "gm_dist_plan"})
+    out = subprocess.run(["nm", "-D", "--defined-only", build_mock()], capture_output=True, text=True).stdout
+    defined = set(re.findall(r" T (gm_[a-z_]+)", out))
+    missing = [f for f in declared if f not in defined]
+    assert not missing, missing
