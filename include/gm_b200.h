@@ -87,8 +87,9 @@ typedef struct gm_stats {
     uint64_t free_updates, hit_updates; /* last gm_register: visits++ along rays / endpoint updates */
     uint64_t resizes;         /* particles whose map was resized in the last gm_register */
     float ms_scanmatch, ms_register, ms_remap, ms_weights; /* CUDA-event device time of the last calls */
-    float ms_migrate, ms_allgather;  /* multi-GPU: last gm_dist_register's patch migration / last gm_dist_allgather */
-    uint64_t migrated_particles, migrated_bytes; /* last gm_dist_register: imported parents, bytes received */
+    float ms_migrate;   /* multi-GPU: device time of the last patch migration (pull kernels) */
+    float ms_allgather; /* multi-GPU: HOST ms the last gm_scanmatch_weights waited, after its own kernel, for the other ranks' rows */
+    uint64_t migrated_particles, migrated_bytes; /* last migration: imported parents, bytes read from peers */
     uint32_t launches;        /* kernels launched by this context since gm_create */
     uint32_t reserved;
     /* last gm_register: SM cycles summed over CTAs per phase of k_register (beam setup, ray marking, ranks, copy-on-write,
@@ -99,6 +100,7 @@ typedef struct gm_stats {
     /* running totals since gm_create: device ms of scanmatch, weights, remap, register, migrate, allgather; work; call counts */
     double total_ms[6];
     uint64_t total_beam_evals, total_score_evals, total_scanmatches, total_registers;
+    uint64_t total_migrated_particles, total_migrated_bytes; /* multi-GPU, since gm_create */
 } gm_stats;
 
 int gm_create(gm_ctx** out, const gm_config* cfg);
@@ -135,6 +137,17 @@ int gm_optimize(gm_ctx* ctx, uint32_t count, const uint32_t* particle_idx, const
  * evals_out: number of score() evaluations per particle.  Any *_out may be NULL. */
 int gm_scanmatch(gm_ctx* ctx, const double* ranges, double* poses_inout, double minimum_score,
                  double* score_out, double* s_out, double* l_out, uint32_t* c_out, uint32_t* evals_out);
+
+/* replaces: GridSlamProcessor::scanMatch (gridslamprocessor.hxx:15-75) together with the normalize() of the updateTreeWeights
+ * that follows it (gridslamprocessor.cpp:586, hxx:82-121), as ONE stream-ordered sequence with a single host synchronisation:
+ * scan matching of the n local particles at poses_local (n*3), log_weights[i] + l[i] for all N particles (the reference's
+ * `weight += l`, hxx:50-52; log_weights = Particle::weight before this scan), the normalised weights and Neff.
+ * rows_out: N * 5 doubles = x, y, theta, optimize()'s score, l per particle.  On a sharded context (gm_dist_init) N = n * world
+ * in global particle order: every rank's rows arrive in every rank's HBM from the scan-match kernel's epilogue (peer stores
+ * over NVLink, no separate collective), and every rank computes the same weights.  weights_out (N) / neff_out may be NULL. */
+int gm_scanmatch_weights(gm_ctx* ctx, const double* ranges, const double* poses_local, double minimum_score,
+                         const double* log_weights /*N*/, double obs_sigma_gain, double* rows_out /*N*5*/,
+                         double* weights_out /*N*/, double* neff_out);
 
 /* replaces: GridSlamProcessor::normalize, gridslamprocessor.hxx:82-121 (sequential sums kept) */
 int gm_normalize_neff(gm_ctx* ctx, const double* log_weights, uint32_t n, double obs_sigma_gain,
@@ -175,18 +188,20 @@ int gm_download_map(gm_ctx* ctx, uint32_t particle, gm_map_info* info, int32_t* 
 int gm_export_occupancy(gm_ctx* ctx, uint32_t particle, double occ_thresh, int8_t* out, uint32_t width, uint32_t height);
 int gm_map_digest(gm_ctx* ctx, uint32_t first, uint32_t count, gm_digest* out /*count*/);
 
-/* ---- multi-GPU (one process and one gm_ctx per GPU; NCCL over NVLink).  Rank r owns the global particles
- * [r*n, (r+1)*n), n = gm_particles(ctx); the host state (poses, weights, trajectory tree, drand48 stream) is replicated.
+/* ---- multi-GPU (one process and one gm_ctx per GPU of one node; peer memory over NVLink / NVSwitch).  Rank r owns the global
+ * particles [r*n, (r+1)*n), n = gm_particles(ctx); the host state (poses, weights, trajectory tree, drand48 stream) is
+ * replicated.  Every rank's patch pool, directories and result buffers are mapped into every other rank with CUDA IPC; a small
+ * POSIX shared-memory segment named after `id` carries the handles and the flags the ranks synchronise on.
  * replaces: nothing in the reference (it is single-threaded); see DESIGN.md "multi-GPU". */
 #define GM_DIST_ID_BYTES 128
-int gm_dist_unique_id(void* id_out /* GM_DIST_ID_BYTES */);  /* ncclGetUniqueId, call on one rank and broadcast */
+int gm_dist_unique_id(void* id_out /* GM_DIST_ID_BYTES */);  /* random session id: call on one rank, hand the bytes to all */
+/* after gm_init_particles, collectively on all ranks: exports this rank's allocations, maps everybody else's */
 int gm_dist_init(gm_ctx* ctx, int rank, int world, const void* id /* GM_DIST_ID_BYTES */);
-/* all-gather `count` doubles per rank (host buffers; out has world*count doubles in rank order) */
-int gm_dist_allgather(gm_ctx* ctx, const double* local, uint32_t count, double* all);
 /* gm_register across ranks: idx_global[N] are the resampled parents as GLOBAL particle indexes (identical on every
- * rank) or NULL.  Parents that live on another rank are migrated here first: their patch directory and patches are
- * packed on the owner, sent with ncclSend/ncclRecv and installed in spare slots; then the local patch-reference
- * remap and the registration run as in gm_register.  poses: the n local particles. */
+ * rank) or NULL.  Parents that live on another rank are pulled here first: a kernel on this GPU reads the owner's patch
+ * directory and patches out of the owner's HBM (peer loads) into spare particle slots, copying a patch that several imported
+ * parents share once; then the local patch-reference remap and the registration run as in gm_register.
+ * poses: the n local particles. */
 int gm_dist_register(gm_ctx* ctx, const double* ranges, const double* poses, const uint32_t* idx_global);
 /* gm_copy_particles across ranks: the migration and the remap of gm_dist_register without the registration */
 int gm_dist_copy_particles(gm_ctx* ctx, const uint32_t* idx_global /*N global*/);

@@ -14,7 +14,7 @@ EXPORTS = ["gm_create", "gm_destroy", "gm_last_error", "gm_set_laser", "gm_set_m
            "gm_init_particles", "gm_score", "gm_likelihood_and_score", "gm_scanmatch", "gm_normalize_neff",
            "gm_resample_indexes", "gm_register", "gm_map_info_get", "gm_download_map", "gm_map_digest",
            "gm_get_stats", "gm_particles", "gm_optimize", "gm_compute_active_area", "gm_upload_map", "gm_export_occupancy", "gm_clone", "gm_set_async_register", "gm_synchronize",
-           "gm_dist_unique_id", "gm_dist_init", "gm_dist_allgather", "gm_dist_register", "gm_dist_plan"]
+           "gm_dist_unique_id", "gm_dist_init", "gm_dist_register", "gm_dist_copy_particles", "gm_dist_plan", "gm_scanmatch_weights"]
 
 
 class GmError(RuntimeError):
@@ -53,7 +53,8 @@ class Stats(C.Structure):
                 ("launches", C.c_uint32), ("reserved", C.c_uint32), ("register_phase_cycles", C.c_uint64 * 8),
                 ("max_active_patches", C.c_uint32), ("register_tile_cap", C.c_uint32),
                 ("total_ms", C.c_double * 6), ("total_beam_evals", C.c_uint64), ("total_score_evals", C.c_uint64),
-                ("total_scanmatches", C.c_uint64), ("total_registers", C.c_uint64)]
+                ("total_scanmatches", C.c_uint64), ("total_registers", C.c_uint64),
+                ("total_migrated_particles", C.c_uint64), ("total_migrated_bytes", C.c_uint64)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("reserved", "register_phase_cycles", "total_ms")}

@@ -53,11 +53,15 @@ int gm_create(gm_ctx** out, const gm_config* cfg) {
     }
     CKC(cudaEventCreate(&c->ev0)); CKC(cudaEventCreate(&c->ev1)); CKC(cudaEventCreate(&c->evw0)); CKC(cudaEventCreate(&c->evw1));
     size_t cap = cfg->pool_patches;
-    if (!cap) {
+    {
+        // 0 = half of the free HBM; an explicit request is honoured up to 80 % of it (a larger one would only fail in cudaMalloc)
         size_t free_b = 0, total_b = 0;
         CKC(cudaMemGetInfo(&free_b, &total_b));
-        cap = (size_t)((double)free_b * 0.5 / (kPatchCells * (sizeof(int4) + sizeof(int) + sizeof(double2)) + kPatch * sizeof(unsigned)));
-        cap = std::min<size_t>(cap, (size_t)1 << 22);  // 64 GiB of patches at most by default
+        const double per_patch = kPatchCells * (sizeof(int4) + sizeof(int) + sizeof(double2)) + kPatch * sizeof(unsigned) + 4 * sizeof(int);
+        const size_t half = (size_t)((double)free_b * 0.5 / per_patch), most = (size_t)((double)free_b * 0.8 / per_patch);
+        if (!cap) cap = std::min<size_t>(half, (size_t)1 << 22);  // 64 GiB of patches at most by default
+        else if (cap > most) cap = most;
+        if (cap < 64) cap = 64;
     }
     if (cap > ((size_t)1 << 22) - 2) cap = ((size_t)1 << 22) - 2;  // cell indexes (patch * 1024 + cell) stay below 2^32
     c->pool.cap = (int)cap;
@@ -80,6 +84,14 @@ int gm_create(gm_ctx** out, const gm_config* cfg) {
     CKC(dalloc(c->d_score, N)); CKC(dalloc(c->d_s, N)); CKC(dalloc(c->d_l, N));
     CKC(dalloc(c->d_c, N)); CKC(dalloc(c->d_evals, N)); CKC(dalloc(c->d_idx, N)); CKC(dalloc(c->d_emitted, 1));
     CKC(dalloc(c->d_counters, 1));
+    CKC(dalloc(c->d_rows, (size_t)c->weights_cap * 5));
+    CKC(dalloc(c->d_done, 1));
+    CKC(cudaMemsetAsync(c->d_done, 0, sizeof(unsigned), c->st));
+    // pinned staging: ranges + local poses + all log-weights in; rows + weights + Neff + counters out
+    c->h_in_bytes = sizeof(double) * (GM_MAXBEAMS + (size_t)N * 3 + c->weights_cap);
+    c->h_out_bytes = sizeof(double) * ((size_t)c->weights_cap * 6 + 2) + sizeof(Counters);
+    CKC(cudaHostAlloc(reinterpret_cast<void**>(&c->h_in), c->h_in_bytes, cudaHostAllocDefault));
+    CKC(cudaHostAlloc(reinterpret_cast<void**>(&c->h_out), c->h_out_bytes, cudaHostAllocDefault));
     CKC(dalloc(c->d_digest, (size_t)N * 7));
     CKC(dalloc(c->d_count, 1));
     {
@@ -115,6 +127,9 @@ int gm_destroy(gm_ctx* c) {
     cudaFree(c->d_c); cudaFree(c->d_evals); cudaFree(c->d_idx); cudaFree(c->d_emitted);
     cudaFree(c->d_w); cudaFree(c->d_widx); cudaFree(c->d_logw); cudaFree(c->d_cum); cudaFree(c->d_tgt); cudaFree(c->d_neff);
     cudaFree(c->d_qidx); cudaFree(c->d_qposes); cudaFree(c->d_qposes_out); cudaFree(c->d_qs); cudaFree(c->d_ql); cudaFree(c->d_qc);
+    cudaFree(c->d_rows); cudaFree(c->d_done);
+    if (c->h_in) cudaFreeHost(c->h_in);
+    if (c->h_out) cudaFreeHost(c->h_out);
     cudaFree(c->d_occ); cudaFree(c->d_counters); cudaFree(c->d_inv_n); cudaFree(c->d_digest); cudaFree(c->d_list); cudaFree(c->d_count); cudaFree(c->d_export);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -274,6 +289,73 @@ int gm_scanmatch(gm_ctx* ctx, const double* ranges, double* poses_inout, double 
     return GM_OK;
 }
 
+// scanMatch + weight += l + normalize as one stream-ordered sequence: one upload (pinned), k_scanmatch, [sharded: the rows of
+// every rank land in every rank's HBM from the kernel's epilogue], k_normalize, one download, ONE synchronisation.
+int gm_scanmatch_weights(gm_ctx* ctx, const double* ranges, const double* poses_local, double minimum_score, const double* log_weights,
+                         double obs_sigma_gain, double* rows_out, double* weights_out, double* neff_out) {
+    if (int r = ready(ctx, true)) return r;
+    if (!ranges || !poses_local || !log_weights || !rows_out) return fail(ctx, GM_ERR_ARG, "gm_scanmatch_weights: null argument");
+    const uint32_t n = ctx->n, nb = ctx->P.nbeams;
+    uint32_t N = n, first = 0;
+    ScanMatchArgs a{};
+    a.query = -1;
+    a.nranks = 1; a.rows[0] = ctx->d_rows; a.first_global = 0; a.done_counter = ctx->d_done; a.flag = nullptr; a.seq = 0;
+    if (ctx->dist) {
+        if (int r = gmi_dist_rows(ctx, &a)) return r;
+        N = n * (uint32_t)a.nranks; first = a.first_global;
+    }
+    if (N > ctx->weights_cap) return fail(ctx, GM_ERR_ARG, "gm_scanmatch_weights: %u particles over all ranks, the context was created for %u", N, ctx->weights_cap);
+    double* hin = reinterpret_cast<double*>(ctx->h_in);
+    memcpy(hin, ranges, sizeof(double) * nb);
+    memcpy(hin + nb, poses_local, sizeof(double) * 3 * n);
+    memcpy(hin + nb + 3 * (size_t)n, log_weights, sizeof(double) * N);
+    CK(cudaMemcpyAsync(ctx->d_ranges, hin, sizeof(double) * nb, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->d_poses, hin + nb, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->d_logw, hin + nb + 3 * (size_t)n, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->st));
+    if (int r = zero_counters(ctx)) return r;
+    a.P = ctx->P; a.ranges = ctx->d_ranges; a.angles = ctx->d_angles; a.poses = ctx->d_poses;
+    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.visits = ctx->pool.visits; a.means = ctx->pool.means; a.occ = ctx->pool.occ; a.inv_n = ctx->d_inv_n;
+    a.minimum_score = minimum_score;
+    a.score = ctx->d_score; a.s = ctx->d_s; a.l = ctx->d_l; a.c = ctx->d_c; a.evals = ctx->d_evals;
+    a.counters = ctx->d_counters;
+    a.zero_patch = ctx->pool.cap;
+    derive_params(a.P);
+    a.valid_score_beams = count_score_beams(ctx, ranges);
+    if (int r = prepare_scanmatch(ctx)) return r;
+    CK(cudaEventRecord(ctx->ev0, ctx->st));
+    launch_scanmatch(a, n, ctx->st);
+    CK(cudaEventRecord(ctx->ev1, ctx->st));
+    ctx->stats.launches++;
+    if (int r = check_launch(ctx, "k_scanmatch")) return r;
+    const double* rows = ctx->d_rows;
+    if (ctx->dist)
+        if (int r = gmi_dist_wait_rows(ctx, &rows)) return r;  // every rank's slice has landed in this rank's gather buffer
+    CK(cudaEventRecord(ctx->evw0, ctx->st));
+    launch_normalize(ctx->d_logw, rows, N, obs_sigma_gain, ctx->d_w, ctx->d_neff, ctx->st);
+    CK(cudaEventRecord(ctx->evw1, ctx->st));
+    ctx->stats.launches++;
+    if (int r = check_launch(ctx, "k_normalize")) return r;
+    double* hout = reinterpret_cast<double*>(ctx->h_out);
+    CK(cudaMemcpyAsync(hout, rows, sizeof(double) * 5 * N, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(hout + 5 * (size_t)N, ctx->d_w, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(hout + 6 * (size_t)N, ctx->d_neff, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(hout + 6 * (size_t)N + 2, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    memcpy(rows_out, hout, sizeof(double) * 5 * N);
+    if (weights_out) memcpy(weights_out, hout + 5 * (size_t)N, sizeof(double) * N);
+    if (neff_out) *neff_out = hout[6 * (size_t)N];
+    Counters h;
+    memcpy(&h, hout + 6 * (size_t)N + 2, sizeof h);
+    (void)first;
+    ctx->stats.score_evals = h.score_evals; ctx->stats.beam_evals = h.beam_evals;
+    CK(cudaEventElapsedTime(&ctx->stats.ms_scanmatch, ctx->ev0, ctx->ev1));
+    CK(cudaEventElapsedTime(&ctx->stats.ms_weights, ctx->evw0, ctx->evw1));
+    ctx->stats.total_ms[0] += ctx->stats.ms_scanmatch; ctx->stats.total_ms[1] += ctx->stats.ms_weights;
+    ctx->stats.total_beam_evals += h.beam_evals; ctx->stats.total_score_evals += h.score_evals;
+    ctx->stats.total_scanmatches++;
+    return GM_OK;
+}
+
 int gm_normalize_neff(gm_ctx* ctx, const double* log_weights, uint32_t n, double obs_sigma_gain, double* weights_out, double* neff_out) {
     if (int r = ready_weights(ctx)) return r;
     if (!ctx->inited) return fail(ctx, GM_ERR_ARG, "gm_init_particles has not been called");
@@ -281,7 +363,7 @@ int gm_normalize_neff(gm_ctx* ctx, const double* log_weights, uint32_t n, double
     cudaStream_t sw = ctx->st_w;  // not ordered after a registration in flight on ctx->st
     CK(cudaMemcpyAsync(ctx->d_logw, log_weights, sizeof(double) * n, cudaMemcpyHostToDevice, sw));
     CK(cudaEventRecord(ctx->evw0, sw));
-    launch_normalize(ctx->d_logw, n, obs_sigma_gain, ctx->d_w, ctx->d_neff, sw);
+    launch_normalize(ctx->d_logw, nullptr, n, obs_sigma_gain, ctx->d_w, ctx->d_neff, sw);
     CK(cudaEventRecord(ctx->evw1, sw));
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_normalize")) return r;
@@ -313,48 +395,50 @@ int gm_resample_indexes(gm_ctx* ctx, const double* weights, uint32_t n, double u
 
 // computeActiveArea's observable part for all particles: bounding box of the scan at the pose in d_poses and the
 // Map::resize it triggers (scanmatcher.cpp:96-166, map.h:218-241, harray2d.h:80-109).  d_ranges / d_poses are staged.
-int gmi_bounds_and_resize(gm_ctx* ctx) {
+// Nothing here waits for the device: k_relayout* look at k_bounds' counters themselves (no-ops unless a particle left its
+// map), and a resize that needs a longer directory stride than the allocation has makes them -- and k_register -- stand
+// down; gmi_register_finish then grows the directories and runs the sequence again (gmi_grow_and_redo).
+static void launch_bounds_and_relayout(gm_ctx* ctx, int new_cap, int* dir_out) {
     const uint32_t n = ctx->n;
-    // ---- computeActiveArea: bounding box + Map::resize (scanmatcher.cpp:96-166)
     BoundsArgs b;
     b.P = ctx->P; b.ranges = ctx->d_ranges; b.angles = ctx->d_angles; b.poses = ctx->d_poses;
     b.geom = ctx->geom; b.geom_new = ctx->geom_new; b.shift = ctx->shift; b.counters = ctx->d_counters;
     launch_bounds(b, n, ctx->threads, ctx->st);
-    ctx->stats.launches++;
-    if (int rc = check_launch(ctx, "k_bounds")) return rc;
-    Counters h;
-    if (int rc = read_counters(ctx, h)) return rc;
-    if (h.error) return fail(ctx, h.error, "gm_register: a ray exceeds the reference's %d-point line buffer", kLineCap);
-    if (h.any_resize) {
-        RelayoutArgs r;
-        r.geom = ctx->geom; r.geom_new = ctx->geom_new; r.shift = ctx->shift;
-        r.dir = ctx->dir; r.dir_cap_old = ctx->dir_cap; r.pool = ctx->pool;
-        int new_cap = std::max(ctx->dir_cap, h.need_dir_cap);
-        int* grown = nullptr;
-        if (new_cap > ctx->dir_cap) {
-            // directory stride grows for everybody: dir_alt is re-allocated as scratch, a new buffer becomes dir
-            const size_t dn = (size_t)ctx->max_particles * new_cap;
-            CK(dalloc(ctx->dir_alt, dn));
-            CK(cudaMalloc(reinterpret_cast<void**>(&grown), dn * sizeof(int)));
-            launch_fill_int(grown, dn, -1, ctx->st);
-            ctx->stats.launches++;
-        }
-        r.dir_alt = ctx->dir_alt; r.dir_cap_new = new_cap; r.dir_out = grown ? grown : ctx->dir;
-        launch_relayout(r, n, ctx->st);
-        launch_relayout_commit(r, n, ctx->st);
-        launch_merge_free(ctx->pool, ctx->st);
-        ctx->stats.launches += 3;
-        if (int rc = check_launch(ctx, "relayout")) { if (grown) cudaFree(grown); return rc; }
-        CK(cudaStreamSynchronize(ctx->st));
-        if (grown) {
-            cudaFree(ctx->dir);
-            ctx->dir = grown;
-            ctx->dir_cap = new_cap;
-            launch_fill_int(ctx->dir_alt, (size_t)ctx->max_particles * new_cap, -1, ctx->st);
-            ctx->stats.launches++;
-        }
-    }
+    RelayoutArgs r;
+    r.counters = ctx->d_counters;
+    r.geom = ctx->geom; r.geom_new = ctx->geom_new; r.shift = ctx->shift;
+    r.dir = ctx->dir; r.dir_cap_old = ctx->dir_cap; r.pool = ctx->pool;
+    r.dir_alt = ctx->dir_alt; r.dir_cap_new = new_cap; r.dir_out = dir_out ? dir_out : ctx->dir;
+    launch_relayout(r, n, ctx->st);
+    launch_relayout_commit(r, n, ctx->st);
+    launch_merge_free(ctx->pool, ctx->st);
+    ctx->stats.launches += 4;
+}
 
+int gmi_bounds_and_resize(gm_ctx* ctx) {
+    launch_bounds_and_relayout(ctx, ctx->dir_cap, nullptr);
+    return check_launch(ctx, "k_bounds / k_relayout");
+}
+
+// a Map::resize outgrew the directory stride: allocate longer directories for everybody, then bounds + relayout again into
+// them (the first attempt changed nothing: every kernel after k_bounds stood down)
+static int gmi_grow_dirs_and_relayout(gm_ctx* ctx, int new_cap) {
+    const size_t dn = (size_t)ctx->max_particles * new_cap;
+    int* grown = nullptr;
+    CK(dalloc(ctx->dir_alt, dn));
+    CK(cudaMalloc(reinterpret_cast<void**>(&grown), dn * sizeof(int)));
+    launch_fill_int(grown, dn, -1, ctx->st);
+    ctx->stats.launches++;
+    if (int rc = zero_counters(ctx)) { cudaFree(grown); return rc; }
+    launch_bounds_and_relayout(ctx, new_cap, grown);
+    if (int rc = check_launch(ctx, "relayout")) { cudaFree(grown); return rc; }
+    CK(cudaStreamSynchronize(ctx->st));
+    cudaFree(ctx->dir);
+    ctx->dir = grown;
+    ctx->dir_cap = new_cap;
+    ctx->dir_gen++;
+    launch_fill_int(ctx->dir_alt, dn, -1, ctx->st);
+    ctx->stats.launches++;
     return GM_OK;
 }
 
@@ -364,9 +448,7 @@ int gmi_bounds_and_resize(gm_ctx* ctx) {
 int gmi_stage(gm_ctx* ctx, const double* ranges, const double* poses) {
     CK(cudaMemcpyAsync(ctx->d_ranges, ranges, sizeof(double) * ctx->P.nbeams, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemcpyAsync(ctx->d_poses, poses, sizeof(double) * 3 * ctx->n, cudaMemcpyHostToDevice, ctx->st));
-    if (int r = zero_counters(ctx)) return r;
-    ctx->stats.ms_remap = 0.f;
-    return GM_OK;
+    return zero_counters(ctx);
 }
 
 // particle copy by patch reference (gridslamprocessor.hxx:184-213): slot j <- slot idx[j] for the ctx->n local
@@ -432,6 +514,21 @@ int gmi_register_finish(gm_ctx* ctx) {
     ctx->reg_pending = false;
     Counters h;
     if (int rc = read_counters(ctx, h)) return rc;
+    if (h.error == GM_ERR_LINE) return fail(ctx, h.error, "gm_register: a ray exceeds the reference's %d-point line buffer", kLineCap);
+    if (!h.error && h.need_dir_cap > ctx->dir_cap) {
+        // the rare slow path: the scan is still staged in d_ranges / d_poses, nothing but k_bounds has run
+        if (int rc = gmi_grow_dirs_and_relayout(ctx, h.need_dir_cap)) return rc;
+        const bool was_async = ctx->async_register;
+        ctx->async_register = true;
+        const int rc = gmi_register_update(ctx);
+        ctx->async_register = was_async;
+        if (rc) return rc;
+        ctx->reg_pending = false;
+        Counters h2;
+        if (int rc2 = read_counters(ctx, h2)) return rc2;
+        h2.resizes = h.resizes;
+        h = h2;
+    }
     int top = 0;
     CK(cudaMemcpyAsync(&top, ctx->pool.free_top, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
@@ -464,6 +561,7 @@ int gmi_ensure_dir_cap(gm_ctx* ctx, int need) {
     CK(dalloc(ctx->dir_alt, dn));
     launch_fill_int(ctx->dir_alt, dn, -1, ctx->st);
     ctx->dir_cap = need;
+    ctx->dir_gen++;
     ctx->stats.launches += 2;
     return check_launch(ctx, "directory growth");
 }
@@ -472,6 +570,7 @@ int gm_register(gm_ctx* ctx, const double* ranges, const double* poses, const ui
     if (int r = ready(ctx, true)) return r;
     if (!ranges || !poses) return fail(ctx, GM_ERR_ARG, "gm_register: null argument");
     if (int r = gmi_stage(ctx, ranges, poses)) return r;
+    ctx->stats.ms_remap = 0.f;
     if (idx)
         if (int r = gmi_remap(ctx, idx, ctx->n)) return r;
     CK(cudaEventRecord(ctx->ev0, ctx->st));
@@ -495,6 +594,11 @@ int gm_compute_active_area(gm_ctx* ctx, const double* ranges, const double* pose
     CK(cudaMemcpyAsync(ctx->d_poses, poses, sizeof(double) * 3 * ctx->n, cudaMemcpyHostToDevice, ctx->st));
     if (int r = zero_counters(ctx)) return r;
     if (int r = gmi_bounds_and_resize(ctx)) return r;
+    Counters h;
+    if (int r = read_counters(ctx, h)) return r;
+    if (h.error == GM_ERR_LINE) return fail(ctx, h.error, "gm_compute_active_area: a ray exceeds the reference's %d-point line buffer", kLineCap);
+    if (h.need_dir_cap > ctx->dir_cap)
+        if (int r = gmi_grow_dirs_and_relayout(ctx, h.need_dir_cap)) return r;
     CK(cudaStreamSynchronize(ctx->st));
     return GM_OK;
 }

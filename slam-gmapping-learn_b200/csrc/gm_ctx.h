@@ -58,6 +58,13 @@ struct gm_ctx {
     int reg_active_hint = 0;  // largest active-patch count seen by the last k_register (sizes its tile allocation)
     uint32_t weights_cap = 0;  // capacity of the weight buffers: max(max_particles, global particle count)
     struct gm_dist* dist = nullptr;  // multi-GPU state (gm_dist.cu), null on a single GPU
+    // gm_scanmatch_weights: result rows {x, y, theta, score, l} of all (global) particles, the CTA-completion counter of the
+    // kernel's epilogue, and pinned host staging for the one upload and the one download of a scan
+    double* d_rows = nullptr;
+    unsigned* d_done = nullptr;
+    unsigned char *h_in = nullptr, *h_out = nullptr; size_t h_in_bytes = 0, h_out_bytes = 0;
+    unsigned dir_gen = 0;  // bumped whenever dir / dir_alt are re-allocated (peers re-open their IPC mappings)
+    void (*fail_hook)(gm_ctx*) = nullptr;  // sharded contexts: tell the other ranks that this one failed (they stop waiting)
 };
 
 
@@ -67,6 +74,7 @@ inline int fail(gm_ctx* c, int code, const char* fmt, ...) {
     char buf[512];
     va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
     if (c) c->err = buf; else create_error() = buf;
+    if (c && c->fail_hook && code != GM_ERR_ARG) c->fail_hook(c);
     return code;
 }
 
@@ -179,4 +187,8 @@ int gmi_register_update(gm_ctx* ctx);
 int gmi_register_finish(gm_ctx* ctx);
 int gmi_ensure_dir_cap(gm_ctx* ctx, int need);
 void gmi_dist_destroy(gm_ctx* ctx);
+// sharded contexts: where k_scanmatch's epilogue writes the result rows (every rank's gather buffer) and the flag it raises;
+// then the wait for every rank's flag.  Single GPU: the context's own d_rows, no flag.
+int gmi_dist_rows(gm_ctx* ctx, ScanMatchArgs* a);
+int gmi_dist_wait_rows(gm_ctx* ctx, const double** rows);
 }

@@ -27,6 +27,7 @@ constexpr int kPatch = 32;
 constexpr int kPatchCells = 1024;
 constexpr int kLineCap = 20000;  // scanmatcher.cpp:55
 constexpr int kInvTable = 4096;  // exactly rounded 1./n for n < kInvTable (PointAccumulator::mean, smmap.h:24)
+constexpr int kMaxRanks = 16;   // GPUs of one node a filter can be sharded over
 constexpr int kExpTable = 128;   // 2^(j/128), stored behind the reciprocals (exp_neg in gm_kernels.cu)
 
 struct Geom { int sx2, sy2, npx, npy; };

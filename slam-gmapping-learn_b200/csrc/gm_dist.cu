@@ -1,17 +1,29 @@
-// gm_dist.cu -- multi-GPU particle sharding: NCCL all-gather of per-particle results and migration of resampled
-// parents' maps between ranks (one process and one gm_ctx per GPU, NVLink 5 / NVSwitch underneath NCCL).
+// gm_dist.cu -- multi-GPU particle sharding over PEER MEMORY: one process and one gm_ctx per GPU of one node, every rank's
+// patch pool, patch directories and result buffers mapped into every other rank with CUDA IPC (NVLink 5 / NVSwitch
+// underneath), no message-passing library on the data path.
 //
-// Rank r owns the global particles [r*n, (r+1)*n).  Scan matching and registration never leave the GPU that owns
-// the particle.  The only exchange is (1) an all-gather of poses / scores / log-likelihoods (5 doubles per particle)
-// and (2), when the filter resamples, the maps of parents whose children live on another rank: the owner packs the
-// parent's patch directory and its patches into one buffer per destination, ncclSend/ncclRecv moves it, the receiver
-// installs it in a spare particle slot; the ordinary patch-reference remap then points the children at it.
-// Systematic resampling keeps indexes ordered, so few parents cross a slice boundary.
+// Rank r owns the global particles [r*n, (r+1)*n).  Scan matching and registration never leave the GPU that owns the
+// particle.  The two exchanges of a scan:
+//   (1) the "all-gather" of the scan-match results is the epilogue of k_scanmatch itself: every CTA stores its particle's
+//       row {x, y, theta, score, l} into the gather buffer of EVERY rank (peer stores), the last CTA raises a flag in a small
+//       host-memory segment all ranks share; a rank launches k_normalize as soon as every rank's flag shows the scan;
+//   (2) when the filter resamples, a child whose parent lives on another rank PULLS the parent's map: a kernel on the
+//       child's GPU reads the owner's patch directory and patches straight out of the owner's HBM (peer loads), keyed by
+//       (owner, patch id) in a hash table so that a patch shared by several imported parents -- siblings of an earlier
+//       resampling -- is copied once and stays shared here; the ordinary patch-reference remap then points the children at
+//       the imported slots.  Two flag barriers bracket it: "my maps are complete" before anybody reads them, "I have pulled"
+//       before an owner frees or rewrites patches.
+// Systematic resampling keeps the index vector ordered, so few parents cross a slice boundary.
 //
-// NCCL is resolved with dlopen at run time (torch's bundled libnccl.so.2 when the process already loaded it, the
-// system one otherwise): single-GPU users do not need it.
-#include <dlfcn.h>
-#include <nccl.h>
+// The shared segment (POSIX shm, named after the 128-byte id every rank passes to gm_dist_init) carries the IPC handles and
+// the flags; it is registered with the CUDA driver so that kernels can write the flags.  Two ranks may share one GPU
+// (tests on a one-GPU box): nothing below depends on the peers being different devices.
+#include <fcntl.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
 
 #include <map>
 #include <set>
@@ -20,132 +32,162 @@
 
 namespace {
 
-struct NcclApi {
-    void* lib = nullptr;
-    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
-    decltype(&ncclCommInitRank) CommInitRank = nullptr;
-    decltype(&ncclCommDestroy) CommDestroy = nullptr;
-    decltype(&ncclAllGather) AllGather = nullptr;
-    decltype(&ncclSend) Send = nullptr;
-    decltype(&ncclRecv) Recv = nullptr;
-    decltype(&ncclGroupStart) GroupStart = nullptr;
-    decltype(&ncclGroupEnd) GroupEnd = nullptr;
-    decltype(&ncclGetErrorString) GetErrorString = nullptr;
-    std::string error;
-    bool load() {
-        if (lib) return true;
-        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
-            lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
-            if (lib) break;
-        }
-        if (!lib) { error = std::string("dlopen libnccl.so.2: ") + dlerror(); return false; }
-#define SYM(field, name) field = reinterpret_cast<decltype(field)>(dlsym(lib, name)); if (!field) { error = std::string("dlsym ") + name; return false; }
-        SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
-        SYM(AllGather, "ncclAllGather") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart")
-        SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
-#undef SYM
-        return true;
-    }
+struct alignas(64) ShmRank {
+    uint32_t ready;     // 1: this rank's handles are published; 2: it has mapped everybody's
+    uint32_t dir_gen;   // generation of the directory allocations behind dir[] (re-opened by the peers when it changes)
+    int32_t dir_cur, geom_cur, dir_cap;
+    uint32_t n_local, max_particles;
+    int32_t pool_cap;
+    cudaIpcMemHandle_t cells, visits, gather[2], dir[2], geom[2];
+    alignas(64) uint32_t flag_rows;    // written by this rank's GPU: number of the last scan whose rows are in every gather buffer
+    alignas(64) uint32_t flag_maps;    // host: this rank's maps are complete and published for resampling #k
+    alignas(64) uint32_t flag_pulled;  // host: this rank has finished pulling for resampling #k
+    alignas(64) uint32_t flag_error;   // a rank that fails says so here: its peers stop waiting
 };
-NcclApi g_nccl;
+struct Shm {
+    uint32_t magic, world;
+    ShmRank r[gm::kMaxRanks];
+};
+constexpr uint32_t kShmMagic = 0x42323030u;
+
+inline uint32_t load_acquire(const uint32_t* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void store_release(uint32_t* p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline double now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
 
 }  // namespace
 
-struct gm_dist {
-    ncclComm_t comm = nullptr;
-    int rank = 0, world = 1;
-    double *d_gin = nullptr, *d_gout = nullptr; size_t gather_cap = 0;
-    unsigned char *d_send = nullptr, *d_recv = nullptr; size_t send_cap = 0, recv_cap = 0;
-    int *d_slots = nullptr, *d_meta_send = nullptr, *d_meta_recv = nullptr; size_t meta_cap = 0;
-    unsigned long long *d_off = nullptr; size_t off_cap = 0;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+struct PeerMap {  // a peer's allocations as seen from this process
+    int4* cells = nullptr; int* visits = nullptr; double* gather[2] = {nullptr, nullptr};
+    int* dir[2] = {nullptr, nullptr}; gm::Geom* geom[2] = {nullptr, nullptr};
+    uint32_t dir_gen = 0; bool dir_open = false;
 };
 
-#define NK(call)                                                                                                      \
-    do {                                                                                                              \
-        ncclResult_t r_ = (call);                                                                                     \
-        if (r_ != ncclSuccess) return fail(ctx, GM_ERR_CUDA, "%s: %s", #call, g_nccl.GetErrorString(r_));             \
-    } while (0)
+struct gm_dist {
+    int rank = 0, world = 1;
+    Shm* shm = nullptr; Shm* shm_dev = nullptr; bool registered = false;
+    char shm_name[64] = {0};
+    double* gather[2] = {nullptr, nullptr};
+    PeerMap peer[gm::kMaxRanks];
+    uint32_t rows_seq = 0, resample_seq = 0;
+    // what this rank last exported for its directories (the two buffers swap at every remap and are re-allocated on growth)
+    int* exp_dir[2] = {nullptr, nullptr}; gm::Geom* exp_geom[2] = {nullptr, nullptr};
+    // pull state
+    unsigned long long* hkey = nullptr; int* hval = nullptr; unsigned hcap = 0;
+    int *uniq_list = nullptr, *uniq_n = nullptr;
+    uint2* d_imports = nullptr; size_t imports_cap = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    double timeout_ms = 120e3;
+};
 
 namespace gm {
 
-constexpr int kMetaInts = 4;      // per migrated parent: patch count, npx, npy, reserved
-constexpr int kHeaderBytes = 32;  // packed parent: int[8] = sx2, sy2, npx, npy, count, 0, 0, 0
+struct PeerView { const int* dir; const Geom* geom; const int4* cells; const int* visits; int dir_cap; };
+struct PullArgs {
+    PeerView peer[kMaxRanks];
+    const uint2* imports;  // {owner rank, slot on the owner} per imported parent
+    int first_slot;        // local slot of import 0
+    Geom* geom; int* dir; int dir_cap;
+    Pool pool; Counters* ctr;
+    unsigned long long* hkey; int* hval; unsigned hmask;
+    int *uniq_list, *uniq_n; int uniq_cap;
+};
+constexpr unsigned long long kEmptyKey = ~0ull;
 
-__host__ __device__ inline unsigned long long packed_bytes(int count) {
-    return kHeaderBytes + (((unsigned long long)count * 4 + 15) & ~15ull) + (unsigned long long)count * kPatchCells * 16;
+// pass 1, one CTA per imported parent: geometry, and every allocated directory entry of the owner becomes a reference to the
+// hash slot of (owner, patch id) -- encoded as -2 - slot until pass 3 -- so that equal patches meet in one slot
+__global__ void __launch_bounds__(256) k_pull_scan(PullArgs A) {
+    const int k = blockIdx.x;
+    const uint2 imp = A.imports[k];
+    const PeerView V = A.peer[imp.x];
+    const Geom g = V.geom[imp.y];
+    const int slot = A.first_slot + k;
+    int* dirp = A.dir + (size_t)slot * A.dir_cap;
+    const int nent = g.npx * g.npy;
+    if (nent > A.dir_cap) { if (threadIdx.x == 0) atomicCAS(&A.ctr->error, 0, -2); return; }
+    const int* rdir = V.dir + (size_t)imp.y * V.dir_cap;
+    for (int e = threadIdx.x; e < A.dir_cap; e += blockDim.x) {
+        int out = -1;
+        const int rid = e < nent ? __ldcg(rdir + e) : -1;
+        if (rid >= 0) {
+            const unsigned long long key = ((unsigned long long)imp.x << 32) | (unsigned)rid;
+            unsigned h = (unsigned)mix64(key) & A.hmask;
+            for (unsigned probe = 0; probe <= A.hmask; probe++) {
+                const unsigned long long prev = atomicCAS(A.hkey + h, kEmptyKey, key);
+                if (prev == kEmptyKey) {
+                    const int u = atomicAdd(A.uniq_n, 1);
+                    if (u < A.uniq_cap) A.uniq_list[u] = (int)h; else atomicCAS(&A.ctr->error, 0, -3);  // more patches than the pool holds
+                    out = -2 - (int)h;
+                    break;
+                }
+                if (prev == key) { out = -2 - (int)h; break; }
+                h = (h + 1) & A.hmask;
+            }
+            if (out == -1) atomicCAS(&A.ctr->error, 0, -3);  // table full: more distinct patches than the pool could hold anyway
+        }
+        dirp[e] = out;
+    }
+    if (threadIdx.x == 0) A.geom[slot] = g;
 }
 
-// per parent to send: how many patches it holds and its directory shape
-__global__ void k_dist_count(const int* __restrict__ slots, const Geom* __restrict__ geom, const int* __restrict__ dir, int dir_cap, int* __restrict__ meta) {
-    __shared__ int s_count;
-    const int s = blockIdx.x, slot = slots[s];
-    const Geom g = geom[slot];
-    if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
-    int c = 0;
-    for (int e = threadIdx.x; e < g.npx * g.npy; e += blockDim.x) c += dir[(size_t)slot * dir_cap + e] >= 0;
-    if (c) atomicAdd(&s_count, c);
-    __syncthreads();
-    if (threadIdx.x == 0) { meta[kMetaInts * s] = s_count; meta[kMetaInts * s + 1] = g.npx; meta[kMetaInts * s + 2] = g.npy; meta[kMetaInts * s + 3] = 0; }
-}
-
-// pack one parent per block: header, directory entries that are allocated, their patches
-__global__ void __launch_bounds__(512) k_dist_pack(const int* __restrict__ slots, const Geom* __restrict__ geom, const int* __restrict__ dir, int dir_cap,
-                                                   const int4* __restrict__ pool, const int* __restrict__ visits, const unsigned long long* __restrict__ off, unsigned char* __restrict__ buf) {
-    __shared__ int s_n;
-    const int s = blockIdx.x, slot = slots[s];
-    const Geom g = geom[slot];
-    unsigned char* base = buf + off[s];
-    int* header = reinterpret_cast<int*>(base);
-    int* entries = reinterpret_cast<int*>(base + kHeaderBytes);
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    const int* dirp = dir + (size_t)slot * dir_cap;
-    for (int e = threadIdx.x; e < g.npx * g.npy; e += blockDim.x)
-        if (dirp[e] >= 0) entries[atomicAdd(&s_n, 1)] = e;
-    __syncthreads();
-    const int count = s_n;
-    if (threadIdx.x == 0) { header[0] = g.sx2; header[1] = g.sy2; header[2] = g.npx; header[3] = g.npy; header[4] = count; header[5] = header[6] = header[7] = 0; }
-    int4* cells = reinterpret_cast<int4*>(base + kHeaderBytes + (((unsigned long long)count * 4 + 15) & ~15ull));
-    for (long long i = threadIdx.x; i < (long long)count * kPatchCells; i += blockDim.x) {
-        const int k = (int)(i >> 10);
-        const size_t ci = (size_t)dirp[entries[k]] * kPatchCells + (i & 1023);
-        int4 c = __ldcg(pool + ci);
-        c.w = __ldcg(visits + ci);  // on the wire a cell is the reference's PointAccumulator: {acc.x, acc.y, n, visits}
-        cells[i] = c;
+// pass 2, CTAs stride over the distinct patches: take a local patch, copy cells + visit counters out of the owner's HBM,
+// rebuild the derived planes (means where n > 0, occupancy bitmap)
+__global__ void __launch_bounds__(256) k_pull_copy(PullArgs A) {
+    __shared__ int s_id;
+    const int total = min(*A.uniq_n, A.uniq_cap);
+    for (int u = blockIdx.x; u < total; u += gridDim.x) {
+        const int h = A.uniq_list[u];
+        const unsigned long long key = A.hkey[h];
+        const PeerView V = A.peer[(unsigned)(key >> 32)];
+        const unsigned rid = (unsigned)key;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_id = pool_alloc(A.pool, A.ctr);
+            A.hval[h] = s_id;
+            if (s_id >= 0) A.pool.refcnt[s_id] = 0;
+        }
+        __syncthreads();
+        const int id = s_id;
+        if (id < 0) continue;
+        const int4* src = V.cells + (size_t)rid * kPatchCells;
+        const int* vsrc = V.visits + (size_t)rid * kPatchCells;
+        int4 c[4]; int v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { c[i] = __ldcg(src + i * 256 + threadIdx.x); v[i] = __ldcg(vsrc + i * 256 + threadIdx.x); }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int ci = i * 256 + threadIdx.x;  // a warp covers one patch row per trip
+            A.pool.cells[(size_t)id * kPatchCells + ci] = make_int4(c[i].x, c[i].y, c[i].z, 0);
+            A.pool.visits[(size_t)id * kPatchCells + ci] = v[i];
+            if (c[i].z > 0) A.pool.means[(size_t)id * kPatchCells + ci] = cell_mean(c[i].x, c[i].y, c[i].z);
+            const unsigned bits = __ballot_sync(0xffffffffu, occ_default(c[i].z, v[i]));
+            if ((threadIdx.x & 31) == 0) A.pool.occ[(size_t)id * kPatch + (ci >> kPatchMag)] = bits;
+        }
     }
 }
 
-// install one received parent per block into particle slot first_slot + block: geometry, a fresh directory, private patches
-__global__ void __launch_bounds__(512) k_dist_install(int first_slot, Geom* __restrict__ geom, int* __restrict__ dir, int dir_cap, Pool pool,
-                                                      const unsigned long long* __restrict__ off, const unsigned char* __restrict__ buf, Counters* ctr) {
-    extern __shared__ int s_ids[];  // patch id per entry (count ints)
-    const int k = blockIdx.x, slot = first_slot + k;
-    const unsigned char* base = buf + off[k];
-    const int* header = reinterpret_cast<const int*>(base);
-    const int* entries = reinterpret_cast<const int*>(base + kHeaderBytes);
-    const int count = header[4];
-    int* dirp = dir + (size_t)slot * dir_cap;
-    for (int e = threadIdx.x; e < dir_cap; e += blockDim.x) dirp[e] = -1;
-    if (threadIdx.x == 0) { Geom g; g.sx2 = header[0]; g.sy2 = header[1]; g.npx = header[2]; g.npy = header[3]; geom[slot] = g; }
-    __syncthreads();
-    for (int i = threadIdx.x; i < count; i += blockDim.x) {
-        const int id = pool_alloc(pool, ctr);
-        s_ids[i] = id;
-        if (id >= 0) { dirp[entries[i]] = id; pool.refcnt[id] = 1; }
-    }
-    __syncthreads();
-    const int4* cells = reinterpret_cast<const int4*>(base + kHeaderBytes + (((unsigned long long)count * 4 + 15) & ~15ull));
-    for (long long i = threadIdx.x; i < (long long)count * kPatchCells; i += blockDim.x) {
-        const int id = s_ids[i >> 10];
-        const int4 c = cells[i];
-        if (id >= 0) { pool.cells[(size_t)id * kPatchCells + (i & 1023)] = make_int4(c.x, c.y, c.z, 0); pool.visits[(size_t)id * kPatchCells + (i & 1023)] = c.w; pool.means[(size_t)id * kPatchCells + (i & 1023)] = cell_mean(c.x, c.y, c.z); }
-        // 512 threads, count * 1024 cells: every warp covers one whole patch row per trip
-        const unsigned bits = __ballot_sync(0xffffffffu, occ_default(c.z, c.w));
-        if (id >= 0 && (i & 31) == 0) pool.occ[(size_t)id * kPatch + ((i & 1023) >> kPatchMag)] = bits;
+// pass 3: directory entries become patch ids, reference counts are counted
+__global__ void __launch_bounds__(256) k_pull_fix(PullArgs A) {
+    int* dirp = A.dir + (size_t)(A.first_slot + blockIdx.x) * A.dir_cap;
+    for (int e = threadIdx.x; e < A.dir_cap; e += blockDim.x) {
+        const int v = dirp[e];
+        if (v > -2) continue;
+        const int id = A.hval[-2 - v];
+        dirp[e] = id;
+        if (id >= 0) atomicAdd(&A.pool.refcnt[id], 1);
     }
 }
+
+// leave the hash table empty for the next resampling (only the slots that were used)
+__global__ void k_pull_clear(PullArgs A, unsigned long long* bytes_out) {
+    const int total = min(*A.uniq_n, A.uniq_cap);
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < total; u += gridDim.x * blockDim.x) A.hkey[A.uniq_list[u]] = kEmptyKey;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *bytes_out = (unsigned long long)total;
+}
+__global__ void k_pull_reset(int* uniq_n) { *uniq_n = 0; }
 
 }  // namespace gm
 
@@ -168,109 +210,150 @@ static void plan_imports(uint32_t n, int rank, const uint32_t* idx, std::vector<
     }
 }
 
-// the parents of `idx_global` that live on other ranks migrate into spare slots, then the ordinary patch-reference remap
+// ---- flags
+static int dist_fail(gm_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[400];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    gm_dist* d = ctx->dist;
+    if (d && d->shm) store_release(&d->shm->r[d->rank].flag_error, 1u);  // peers stop waiting for this rank
+    return fail(ctx, code, "%s", buf);
+}
+
+// wait until `field` of rank g reaches `want` (sequence numbers only grow)
+template <class F>
+static int wait_flag(gm_ctx* ctx, int g, F field, uint32_t want, const char* what) {
+    gm_dist* d = ctx->dist;
+    const double t0 = now_ms();
+    for (unsigned spin = 0;; spin++) {
+        if ((int32_t)(load_acquire(field(d->shm->r[g])) - want) >= 0) return GM_OK;
+        if (load_acquire(&d->shm->r[g].flag_error)) return dist_fail(ctx, GM_ERR_CUDA, "%s: rank %d reported an error", what, g);
+        if ((spin & 63) == 63) {
+            sched_yield();
+            if (now_ms() - t0 > d->timeout_ms) return dist_fail(ctx, GM_ERR_CUDA, "%s: rank %d did not arrive within %.0f s", what, g, d->timeout_ms / 1e3);
+        }
+    }
+}
+
+// export (or re-export) this rank's directory / geometry allocations; dir and dir_alt swap at every remap
+static int publish_dirs(gm_ctx* ctx) {
+    gm_dist* d = ctx->dist;
+    ShmRank& me = d->shm->r[d->rank];
+    auto index_of = [](int* const* have, const int* p) { return have[0] == p ? 0 : have[1] == p ? 1 : -1; };
+    int cur = index_of(d->exp_dir, ctx->dir);
+    if (cur < 0 || index_of(d->exp_dir, ctx->dir_alt) < 0) {  // first time, or re-allocated by a directory growth
+        d->exp_dir[0] = ctx->dir; d->exp_dir[1] = ctx->dir_alt;
+        CK(cudaIpcGetMemHandle(&me.dir[0], ctx->dir));
+        CK(cudaIpcGetMemHandle(&me.dir[1], ctx->dir_alt));
+        me.dir_gen++;
+        cur = 0;
+    }
+    me.dir_cur = cur;
+    me.dir_cap = ctx->dir_cap;
+    if (!d->exp_geom[0]) {
+        d->exp_geom[0] = ctx->geom; d->exp_geom[1] = ctx->geom_alt;
+        CK(cudaIpcGetMemHandle(&me.geom[0], ctx->geom));
+        CK(cudaIpcGetMemHandle(&me.geom[1], ctx->geom_alt));
+    }
+    me.geom_cur = d->exp_geom[0] == ctx->geom ? 0 : 1;
+    return GM_OK;
+}
+
+static int open_peer_dirs(gm_ctx* ctx, int g) {
+    gm_dist* d = ctx->dist;
+    PeerMap& pm = d->peer[g];
+    const ShmRank& sr = d->shm->r[g];
+    if (pm.dir_open && pm.dir_gen == sr.dir_gen) return GM_OK;
+    if (pm.dir_open) { cudaIpcCloseMemHandle(pm.dir[0]); cudaIpcCloseMemHandle(pm.dir[1]); pm.dir_open = false; }
+    for (int k = 0; k < 2; k++) CK(cudaIpcOpenMemHandle(reinterpret_cast<void**>(&pm.dir[k]), sr.dir[k], cudaIpcMemLazyEnablePeerAccess));
+    if (!pm.geom[0])
+        for (int k = 0; k < 2; k++) CK(cudaIpcOpenMemHandle(reinterpret_cast<void**>(&pm.geom[k]), sr.geom[k], cudaIpcMemLazyEnablePeerAccess));
+    pm.dir_gen = sr.dir_gen; pm.dir_open = true;
+    return GM_OK;
+}
+
+// the parents of `idx_global` that live on other ranks are pulled into spare slots, then the ordinary patch-reference remap
 static int dist_migrate_and_remap(gm_ctx* ctx, const uint32_t* idx_global, const char* who) {
     gm_dist* d = ctx->dist;
     const uint32_t n = ctx->n;
     const int world = d->world, rank = d->rank;
     const uint32_t N = n * (uint32_t)world;
-    for (uint32_t i = 0; i < N; i++)
-        if (idx_global[i] >= N) return fail(ctx, GM_ERR_ARG, "%s: parent index %u >= %u", who, idx_global[i], N);
-    // ---- plan: imports of this rank (grouped by owner) and, for every other rank, what it imports from us
+    bool any_cross = false;
+    for (uint32_t i = 0; i < N; i++) {
+        if (idx_global[i] >= N) return dist_fail(ctx, GM_ERR_ARG, "%s: parent index %u >= %u", who, idx_global[i], N);
+        any_cross = any_cross || idx_global[i] / n != i / n;
+    }
     std::vector<uint32_t> imports, local_idx;
     plan_imports(n, rank, idx_global, imports, local_idx);
-    if (n + imports.size() > ctx->max_particles)
-        return fail(ctx, GM_ERR_ARG, "%s: %zu imported parents do not fit the %u spare particle slots", who, imports.size(), ctx->max_particles - n);
-    std::vector<std::vector<int> > sends(world);  // local slots to send to each rank, ascending
-    size_t nsend = 0;
-    for (int g = 0; g < world; g++) {
-        if (g == rank) continue;
-        std::vector<uint32_t> imp_g, unused;
-        plan_imports(n, g, idx_global, imp_g, unused);
-        for (uint32_t p : imp_g)
-            if (p / n == (uint32_t)rank) sends[g].push_back((int)(p - (uint32_t)rank * n));
-        nsend += sends[g].size();
-    }
-    std::vector<size_t> recv_from(world, 0);  // imports per owner; the import list is ascending, hence grouped by owner
-    for (uint32_t p : imports) recv_from[p / n]++;
-    const size_t nrecv = imports.size();
+    ctx->stats.ms_migrate = 0.f; ctx->stats.migrated_particles = 0; ctx->stats.migrated_bytes = 0;
+    if (!any_cross) return gmi_remap(ctx, local_idx.data(), n);  // every rank sees the same index vector: nobody waits for anybody
+    const size_t nimp = imports.size();
+    if (n + nimp > ctx->max_particles)
+        return dist_fail(ctx, GM_ERR_ARG, "%s: %zu imported parents do not fit the %u spare particle slots", who, nimp, ctx->max_particles - n);
+    std::vector<char> imports_from_me(world, 0);  // ranks that read this rank's maps
+    for (uint32_t i = 0; i < N; i++)
+        if (idx_global[i] / n == (uint32_t)rank && i / n != (uint32_t)rank) imports_from_me[i / n] = 1;
 
+    // ---- barrier A: this rank's maps are complete (the caller finished any registration in flight) and published
+    const uint32_t k = ++d->resample_seq;
+    if (int r = publish_dirs(ctx)) return r;
+    store_release(&d->shm->r[rank].flag_maps, k);
+    int need_cap = ctx->dir_cap;
+    std::set<int> owners;
+    for (uint32_t p : imports) owners.insert((int)(p / n));
+    for (int g : owners) {
+        if (int r = wait_flag(ctx, g, [](ShmRank& s) { return &s.flag_maps; }, k, who)) return r;
+        if (int r = open_peer_dirs(ctx, g)) return r;
+        need_cap = std::max(need_cap, (int)d->shm->r[g].dir_cap);
+    }
     CK(cudaEventRecord(d->e0, ctx->st));
-    if (nsend + nrecv) {
-        if (nsend + nrecv > d->meta_cap) {
-            const size_t cap = (nsend + nrecv) * 2;
-            CK(dalloc(d->d_slots, cap)); CK(dalloc(d->d_meta_send, cap * gm::kMetaInts)); CK(dalloc(d->d_meta_recv, cap * gm::kMetaInts));
-            CK(dalloc(d->d_off, cap));
-            d->meta_cap = cap;
+    if (nimp) {
+        if (need_cap > ctx->dir_cap) {
+            if (int r = gmi_ensure_dir_cap(ctx, need_cap)) return r;  // (re-published at the next resampling; nobody reads it now)
         }
-        // ---- 1. patch counts of what we send; exchange the counts
-        std::vector<int> slots;
-        for (int g = 0; g < world; g++) slots.insert(slots.end(), sends[g].begin(), sends[g].end());
-        std::vector<int> meta_send(nsend * gm::kMetaInts), meta_recv(nrecv * gm::kMetaInts);
-        if (nsend) {
-            CK(cudaMemcpyAsync(d->d_slots, slots.data(), sizeof(int) * nsend, cudaMemcpyHostToDevice, ctx->st));
-            gm::k_dist_count<<<(unsigned)nsend, 256, 0, ctx->st>>>(d->d_slots, ctx->geom, ctx->dir, ctx->dir_cap, d->d_meta_send);
-            ctx->stats.launches++;
+        // ---- pull: the owners' directories and patches are read in place, over NVLink
+        if (nimp > d->imports_cap) { CK(dalloc(d->d_imports, nimp * 2)); d->imports_cap = nimp * 2; }
+        std::vector<uint2> imp(nimp);
+        for (size_t i = 0; i < nimp; i++) imp[i] = make_uint2(imports[i] / n, imports[i] % n);
+        CK(cudaMemcpyAsync(d->d_imports, imp.data(), sizeof(uint2) * nimp, cudaMemcpyHostToDevice, ctx->st));
+        if (int r = zero_counters(ctx)) return r;
+        gm::PullArgs a{};
+        for (int g : owners) {
+            const ShmRank& sr = d->shm->r[g];
+            const PeerMap& pm = d->peer[g];
+            a.peer[g].dir = pm.dir[sr.dir_cur]; a.peer[g].geom = pm.geom[sr.geom_cur];
+            a.peer[g].cells = pm.cells; a.peer[g].visits = pm.visits; a.peer[g].dir_cap = sr.dir_cap;
         }
-        NK(g_nccl.GroupStart());
-        {
-            size_t so = 0, ro = 0;
-            for (int g = 0; g < world; g++) {
-                if (g == rank) continue;
-                if (!sends[g].empty()) NK(g_nccl.Send(d->d_meta_send + so * gm::kMetaInts, sends[g].size() * gm::kMetaInts, ncclInt32, g, d->comm, ctx->st));
-                if (recv_from[g]) NK(g_nccl.Recv(d->d_meta_recv + ro * gm::kMetaInts, recv_from[g] * gm::kMetaInts, ncclInt32, g, d->comm, ctx->st));
-                so += sends[g].size(); ro += recv_from[g];
-            }
-        }
-        NK(g_nccl.GroupEnd());
-        if (nsend) CK(cudaMemcpyAsync(meta_send.data(), d->d_meta_send, sizeof(int) * meta_send.size(), cudaMemcpyDeviceToHost, ctx->st));
-        if (nrecv) CK(cudaMemcpyAsync(meta_recv.data(), d->d_meta_recv, sizeof(int) * meta_recv.size(), cudaMemcpyDeviceToHost, ctx->st));
-        CK(cudaStreamSynchronize(ctx->st));
-        // ---- 2. byte offsets, buffers, pack, exchange the data
-        std::vector<unsigned long long> send_off(nsend + 1, 0), recv_off(nrecv + 1, 0);
-        for (size_t s = 0; s < nsend; s++) send_off[s + 1] = send_off[s] + gm::packed_bytes(meta_send[gm::kMetaInts * s]);
-        int need_cap = 0, max_count = 0;
-        for (size_t k = 0; k < nrecv; k++) {
-            recv_off[k + 1] = recv_off[k] + gm::packed_bytes(meta_recv[gm::kMetaInts * k]);
-            need_cap = std::max(need_cap, meta_recv[gm::kMetaInts * k + 1] * meta_recv[gm::kMetaInts * k + 2]);
-            max_count = std::max(max_count, meta_recv[gm::kMetaInts * k]);
-        }
-        if (send_off[nsend] > d->send_cap) { CK(dalloc(d->d_send, (size_t)send_off[nsend])); d->send_cap = send_off[nsend]; }
-        if (recv_off[nrecv] > d->recv_cap) { CK(dalloc(d->d_recv, (size_t)recv_off[nrecv])); d->recv_cap = recv_off[nrecv]; }
-        if (nsend) {
-            CK(cudaMemcpyAsync(d->d_off, send_off.data(), sizeof(unsigned long long) * nsend, cudaMemcpyHostToDevice, ctx->st));
-            gm::k_dist_pack<<<(unsigned)nsend, 512, 0, ctx->st>>>(d->d_slots, ctx->geom, ctx->dir, ctx->dir_cap, ctx->pool.cells, ctx->pool.visits, d->d_off, d->d_send);
-            ctx->stats.launches++;
-        }
-        NK(g_nccl.GroupStart());
-        {
-            size_t so = 0, ro = 0;
-            for (int g = 0; g < world; g++) {
-                if (g == rank) continue;
-                const size_t ns = sends[g].size(), nr = recv_from[g];
-                if (ns) NK(g_nccl.Send(d->d_send + send_off[so], (size_t)(send_off[so + ns] - send_off[so]), ncclChar, g, d->comm, ctx->st));
-                if (nr) NK(g_nccl.Recv(d->d_recv + recv_off[ro], (size_t)(recv_off[ro + nr] - recv_off[ro]), ncclChar, g, d->comm, ctx->st));
-                so += ns; ro += nr;
-            }
-        }
-        NK(g_nccl.GroupEnd());
-        // ---- 3. install the received parents in the spare slots n .. n + nrecv - 1
-        if (nrecv) {
-            CK(cudaStreamSynchronize(ctx->st));  // d_off is reused below
-            if (int r = gmi_ensure_dir_cap(ctx, need_cap)) return r;
-            CK(cudaMemcpyAsync(d->d_off, recv_off.data(), sizeof(unsigned long long) * nrecv, cudaMemcpyHostToDevice, ctx->st));
-            const size_t smem = (size_t)std::max(max_count, 1) * sizeof(int);
-            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(gm::k_dist_install, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gm::k_dist_install<<<(unsigned)nrecv, 512, smem, ctx->st>>>((int)n, ctx->geom, ctx->dir, ctx->dir_cap, ctx->pool, d->d_off, d->d_recv, ctx->d_counters);
-            ctx->stats.launches++;
-        }
+        a.imports = d->d_imports; a.first_slot = (int)n;
+        a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool; a.ctr = ctx->d_counters;
+        a.hkey = d->hkey; a.hval = d->hval; a.hmask = d->hcap - 1; a.uniq_list = d->uniq_list; a.uniq_n = d->uniq_n; a.uniq_cap = ctx->pool.cap;
+        gm::k_pull_scan<<<(unsigned)nimp, 256, 0, ctx->st>>>(a);
+        gm::k_pull_copy<<<148 * 8, 256, 0, ctx->st>>>(a);
+        gm::k_pull_fix<<<(unsigned)nimp, 256, 0, ctx->st>>>(a);
+        gm::k_pull_clear<<<64, 256, 0, ctx->st>>>(a, reinterpret_cast<unsigned long long*>(ctx->d_digest));
+        gm::k_pull_reset<<<1, 1, 0, ctx->st>>>(d->uniq_n);
+        ctx->stats.launches += 5;
         if (int rc = check_launch(ctx, "patch migration")) return rc;
-        ctx->stats.migrated_particles = nrecv;
-        ctx->stats.migrated_bytes = recv_off[nrecv];
     }
     CK(cudaEventRecord(d->e1, ctx->st));
-    // ---- 4. the ordinary remap, children of imported parents read from the spare slots
-    if (int r = gmi_remap(ctx, local_idx.data(), n + (uint32_t)nrecv)) return r;
+    // ---- pool exhaustion is reported here, before any child is pointed at a map with holes
+    unsigned long long uniq = 0;
+    if (nimp) {
+        Counters h;
+        CK(cudaMemcpyAsync(&uniq, ctx->d_digest, sizeof uniq, cudaMemcpyDeviceToHost, ctx->st));
+        if (int r = read_counters(ctx, h)) return r;
+        if (h.error == GM_ERR_POOL) return dist_fail(ctx, GM_ERR_POOL, "%s: patch pool of %d patches exhausted while importing %zu parents", who, ctx->pool.cap, nimp);
+        if (h.error) return dist_fail(ctx, h.error, "%s: device-side error %d while importing parents", who, h.error);
+    } else CK(cudaStreamSynchronize(ctx->st));
+    // ---- barrier B: nobody frees or rewrites a patch while a peer may still be reading it
+    store_release(&d->shm->r[rank].flag_pulled, k);
+    for (int g = 0; g < world; g++)
+        if (imports_from_me[g])
+            if (int r = wait_flag(ctx, g, [](ShmRank& s) { return &s.flag_pulled; }, k, who)) return r;
+    ctx->stats.migrated_particles = nimp;
+    ctx->stats.migrated_bytes = uniq * (unsigned long long)(kPatchCells * 20) + (unsigned long long)nimp * ctx->dir_cap * 4;
+    ctx->stats.total_migrated_particles += ctx->stats.migrated_particles; ctx->stats.total_migrated_bytes += ctx->stats.migrated_bytes;
+    // ---- the ordinary remap, children of imported parents read from the spare slots
+    if (int r = gmi_remap(ctx, local_idx.data(), n + (uint32_t)nimp)) return r;
     CK(cudaEventElapsedTime(&ctx->stats.ms_migrate, d->e0, d->e1));
     return GM_OK;
 }
@@ -280,58 +363,137 @@ extern "C" {
 void gmi_dist_destroy(gm_ctx* ctx) {
     gm_dist* d = ctx->dist;
     if (!d) return;
-    if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
-    cudaFree(d->d_gin); cudaFree(d->d_gout); cudaFree(d->d_send); cudaFree(d->d_recv);
-    cudaFree(d->d_slots); cudaFree(d->d_meta_send); cudaFree(d->d_meta_recv); cudaFree(d->d_off);
+    for (int g = 0; g < d->world; g++) {
+        if (g == d->rank) continue;
+        PeerMap& pm = d->peer[g];
+        if (pm.cells) cudaIpcCloseMemHandle(pm.cells);
+        if (pm.visits) cudaIpcCloseMemHandle(pm.visits);
+        for (int k = 0; k < 2; k++) {
+            if (pm.gather[k]) cudaIpcCloseMemHandle(pm.gather[k]);
+            if (pm.dir[k]) cudaIpcCloseMemHandle(pm.dir[k]);
+            if (pm.geom[k]) cudaIpcCloseMemHandle(pm.geom[k]);
+        }
+    }
+    cudaFree(d->gather[0]); cudaFree(d->gather[1]);
+    cudaFree(d->hkey); cudaFree(d->hval); cudaFree(d->uniq_list); cudaFree(d->uniq_n); cudaFree(d->d_imports);
     if (d->e0) cudaEventDestroy(d->e0);
     if (d->e1) cudaEventDestroy(d->e1);
+    if (d->shm) {
+        if (d->registered) cudaHostUnregister(d->shm);
+        munmap(d->shm, sizeof(Shm));
+        if (d->shm_name[0]) shm_unlink(d->shm_name);  // normally gone already (rank 0 unlinks once everybody is attached)
+    }
     delete d;
     ctx->dist = nullptr;
+    ctx->fail_hook = nullptr;
 }
 
+// 128 random bytes that name the ranks' shared segment; call on one rank and hand the bytes to all of them
 int gm_dist_unique_id(void* id_out) {
     gm_ctx* ctx = nullptr;
     if (!id_out) return fail(ctx, GM_ERR_ARG, "gm_dist_unique_id: null argument");
-    if (!g_nccl.load()) return fail(ctx, GM_ERR_CUDA, "%s", g_nccl.error.c_str());
-    static_assert(sizeof(ncclUniqueId) == GM_DIST_ID_BYTES, "ncclUniqueId size");
-    ncclUniqueId id;
-    NK(g_nccl.GetUniqueId(&id));
-    memcpy(id_out, &id, sizeof id);
+    unsigned char* b = static_cast<unsigned char*>(id_out);
+    FILE* f = fopen("/dev/urandom", "rb");
+    const size_t got = f ? fread(b, 1, GM_DIST_ID_BYTES, f) : 0;
+    if (f) fclose(f);
+    if (got != GM_DIST_ID_BYTES) {
+        unsigned long long x = (unsigned long long)getpid() * 0x9E3779B97F4A7C15ull ^ (unsigned long long)(now_ms() * 1e3);
+        for (int i = 0; i < GM_DIST_ID_BYTES; i++) { x = x * 6364136223846793005ull + 1442695040888963407ull; b[i] = (unsigned char)(x >> 56); }
+    }
     return GM_OK;
 }
 
 int gm_dist_init(gm_ctx* ctx, int rank, int world, const void* id_bytes) {
     if (!ctx) return GM_ERR_ARG;
-    if (!id_bytes || world < 1 || rank < 0 || rank >= world) return fail(ctx, GM_ERR_ARG, "gm_dist_init: bad argument");
+    if (!id_bytes || world < 1 || world > gm::kMaxRanks || rank < 0 || rank >= world)
+        return fail(ctx, GM_ERR_ARG, "gm_dist_init: bad argument (rank %d of %d, at most %d ranks)", rank, world, gm::kMaxRanks);
+    if (!ctx->inited) return fail(ctx, GM_ERR_ARG, "gm_dist_init: call gm_init_particles first (the directories are exported)");
+    if ((uint64_t)ctx->n * world > ctx->weights_cap) return fail(ctx, GM_ERR_ARG, "gm_dist_init: %u x %d particles, gm_config.global_particles is %u", ctx->n, world, ctx->weights_cap);
     if (int r = bind(ctx)) return r;
-    if (!g_nccl.load()) return fail(ctx, GM_ERR_CUDA, "%s", g_nccl.error.c_str());
     gmi_dist_destroy(ctx);
     gm_dist* d = new gm_dist();
     d->rank = rank; d->world = world;
-    ncclUniqueId id;
-    memcpy(&id, id_bytes, sizeof id);
+    if (const char* e = getenv("GM_B200_DIST_TIMEOUT_S")) d->timeout_ms = atof(e) * 1e3;
     ctx->dist = d;
-    NK(g_nccl.CommInitRank(&d->comm, world, id, rank));
+    ctx->fail_hook = [](gm_ctx* c) { if (c->dist && c->dist->shm) store_release(&c->dist->shm->r[c->dist->rank].flag_error, 1u); };
+    // ---- the shared segment
+    const unsigned char* b = static_cast<const unsigned char*>(id_bytes);
+    int len = snprintf(d->shm_name, sizeof d->shm_name, "/gmb200_");
+    for (int i = 0; i < 16; i++) len += snprintf(d->shm_name + len, sizeof d->shm_name - len, "%02x", b[i]);
+    const int fd = shm_open(d->shm_name, O_CREAT | O_RDWR, 0600);
+    if (fd < 0) return fail(ctx, GM_ERR_CUDA, "gm_dist_init: shm_open(%s) failed", d->shm_name);
+    if (ftruncate(fd, sizeof(Shm))) { close(fd); return fail(ctx, GM_ERR_CUDA, "gm_dist_init: ftruncate(%s) failed", d->shm_name); }
+    void* m = mmap(nullptr, sizeof(Shm), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return fail(ctx, GM_ERR_CUDA, "gm_dist_init: mmap(%s) failed", d->shm_name);
+    d->shm = static_cast<Shm*>(m);  // a fresh segment is all zeros
+    CK(cudaHostRegister(d->shm, sizeof(Shm), cudaHostRegisterMapped | cudaHostRegisterPortable));
+    d->registered = true;
+    CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d->shm_dev), d->shm, 0));
+    // ---- this rank's buffers and handles
+    const size_t rows = (size_t)ctx->weights_cap * 5;
+    for (int k = 0; k < 2; k++) { CK(dalloc(d->gather[k], rows)); CK(cudaMemsetAsync(d->gather[k], 0, rows * sizeof(double), ctx->st)); }
+    d->hcap = 1024;
+    while (d->hcap < 2u * (unsigned)ctx->pool.cap && d->hcap < (1u << 30)) d->hcap <<= 1;
+    CK(dalloc(d->hkey, d->hcap)); CK(dalloc(d->hval, d->hcap)); CK(dalloc(d->uniq_list, (size_t)ctx->pool.cap + 1)); CK(dalloc(d->uniq_n, 1));
+    CK(cudaMemsetAsync(d->hkey, 0xff, sizeof(unsigned long long) * d->hcap, ctx->st));
+    CK(cudaMemsetAsync(d->uniq_n, 0, sizeof(int), ctx->st));
     CK(cudaEventCreate(&d->e0)); CK(cudaEventCreate(&d->e1));
+    CK(cudaStreamSynchronize(ctx->st));
+    ShmRank& me = d->shm->r[rank];
+    me.n_local = ctx->n; me.max_particles = ctx->max_particles; me.pool_cap = ctx->pool.cap;
+    CK(cudaIpcGetMemHandle(&me.cells, ctx->pool.cells));
+    CK(cudaIpcGetMemHandle(&me.visits, ctx->pool.visits));
+    for (int k = 0; k < 2; k++) CK(cudaIpcGetMemHandle(&me.gather[k], d->gather[k]));
+    if (int r = publish_dirs(ctx)) return r;
+    if (rank == 0) { d->shm->magic = kShmMagic; d->shm->world = (uint32_t)world; }
+    store_release(&me.ready, 1u);
+    // ---- everybody's handles
+    for (int g = 0; g < world; g++) {
+        if (int r = wait_flag(ctx, g, [](ShmRank& s) { return &s.ready; }, 1u, "gm_dist_init")) return r;
+        if (g == rank) continue;
+        const ShmRank& sr = d->shm->r[g];
+        if (sr.n_local != ctx->n) return dist_fail(ctx, GM_ERR_ARG, "gm_dist_init: rank %d holds %u particles, this rank %u", g, sr.n_local, ctx->n);
+        PeerMap& pm = d->peer[g];
+        CK(cudaIpcOpenMemHandle(reinterpret_cast<void**>(&pm.cells), sr.cells, cudaIpcMemLazyEnablePeerAccess));
+        CK(cudaIpcOpenMemHandle(reinterpret_cast<void**>(&pm.visits), sr.visits, cudaIpcMemLazyEnablePeerAccess));
+        for (int k = 0; k < 2; k++) CK(cudaIpcOpenMemHandle(reinterpret_cast<void**>(&pm.gather[k]), sr.gather[k], cudaIpcMemLazyEnablePeerAccess));
+        if (int r = open_peer_dirs(ctx, g)) return r;
+    }
+    store_release(&me.ready, 2u);
+    for (int g = 0; g < world; g++)
+        if (int r = wait_flag(ctx, g, [](ShmRank& s) { return &s.ready; }, 2u, "gm_dist_init")) return r;
+    if (rank == 0) shm_unlink(d->shm_name);  // every rank is attached: the name can go, the mapping lives on
+    d->shm_name[0] = 0;
     return GM_OK;
 }
 
-int gm_dist_allgather(gm_ctx* ctx, const double* local, uint32_t count, double* all) {
-    if (!ctx || !ctx->dist) return fail(ctx, GM_ERR_ARG, "gm_dist_allgather: gm_dist_init has not been called");
-    if (!local || !all || !count) return fail(ctx, GM_ERR_ARG, "gm_dist_allgather: bad argument");
-    if (int r = bind(ctx)) return r;
-    if (int r = gmi_register_finish(ctx)) return r;
+// where k_scanmatch's epilogue stores the result rows of this scan, and the flag it raises when the slice is complete
+int gmi_dist_rows(gm_ctx* ctx, ScanMatchArgs* a) {
     gm_dist* d = ctx->dist;
-    const size_t total = (size_t)count * d->world;
-    if (total > d->gather_cap) { CK(dalloc(d->d_gin, count)); CK(dalloc(d->d_gout, total)); d->gather_cap = total; }
-    CK(cudaMemcpyAsync(d->d_gin, local, sizeof(double) * count, cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaEventRecord(d->e0, ctx->st));
-    NK(g_nccl.AllGather(d->d_gin, d->d_gout, count, ncclDouble, d->comm, ctx->st));
-    CK(cudaEventRecord(d->e1, ctx->st));
-    CK(cudaMemcpyAsync(all, d->d_gout, sizeof(double) * total, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));
-    CK(cudaEventElapsedTime(&ctx->stats.ms_allgather, d->e0, d->e1));
+    const uint32_t seq = ++d->rows_seq;
+    const int buf = (int)(seq & 1u);  // a rank can be at most one scan ahead of a peer that still reads the previous rows
+    a->nranks = d->world;
+    for (int g = 0; g < d->world; g++) a->rows[g] = g == d->rank ? d->gather[buf] : d->peer[g].gather[buf];
+    a->first_global = (unsigned)d->rank * ctx->n;
+    a->done_counter = ctx->d_done;
+    a->flag = &d->shm_dev->r[d->rank].flag_rows;
+    a->seq = seq;
+    return GM_OK;
+}
+
+int gmi_dist_wait_rows(gm_ctx* ctx, const double** rows) {
+    gm_dist* d = ctx->dist;
+    const uint32_t seq = d->rows_seq;
+    if (int r = wait_flag(ctx, d->rank, [](ShmRank& s) { return &s.flag_rows; }, seq, "gm_scanmatch_weights")) return r;
+    const double t0 = now_ms();
+    for (int g = 0; g < d->world; g++)
+        if (g != d->rank)
+            if (int r = wait_flag(ctx, g, [](ShmRank& s) { return &s.flag_rows; }, seq, "gm_scanmatch_weights")) return r;
+    // not device time: how long this rank waited, after its own kernel, for the slowest rank's rows
+    ctx->stats.ms_allgather = (float)(now_ms() - t0);
     ctx->stats.total_ms[5] += ctx->stats.ms_allgather;
+    *rows = d->gather[seq & 1u];
     return GM_OK;
 }
 
@@ -348,10 +510,10 @@ int gm_dist_register(gm_ctx* ctx, const double* ranges, const double* poses, con
     if (int r = ready(ctx, true)) return r;
     if (!ctx->dist) return fail(ctx, GM_ERR_ARG, "gm_dist_register: gm_dist_init has not been called");
     if (!ranges || !poses) return fail(ctx, GM_ERR_ARG, "gm_dist_register: null argument");
-    if (int r = gmi_stage(ctx, ranges, poses)) return r;
-    ctx->stats.ms_migrate = 0.f; ctx->stats.migrated_particles = 0; ctx->stats.migrated_bytes = 0;
+    ctx->stats.ms_remap = 0.f; ctx->stats.ms_migrate = 0.f; ctx->stats.migrated_particles = 0; ctx->stats.migrated_bytes = 0;
     if (idx_global)
         if (int r = dist_migrate_and_remap(ctx, idx_global, "gm_dist_register")) return r;
+    if (int r = gmi_stage(ctx, ranges, poses)) return r;
     CK(cudaEventRecord(ctx->ev0, ctx->st));
     if (int rc = gmi_bounds_and_resize(ctx)) return rc;
     return gmi_register_update(ctx);
@@ -361,7 +523,7 @@ int gm_dist_copy_particles(gm_ctx* ctx, const uint32_t* idx_global) {
     if (int r = ready(ctx, true)) return r;  // completes a registration in flight: the copies take the registered maps
     if (!ctx->dist) return fail(ctx, GM_ERR_ARG, "gm_dist_copy_particles: gm_dist_init has not been called");
     if (!idx_global) return fail(ctx, GM_ERR_ARG, "gm_dist_copy_particles: null argument");
-    ctx->stats.ms_remap = 0.f; ctx->stats.ms_migrate = 0.f; ctx->stats.migrated_particles = 0; ctx->stats.migrated_bytes = 0;
+    ctx->stats.ms_remap = 0.f;
     if (int r = dist_migrate_and_remap(ctx, idx_global, "gm_dist_copy_particles")) return r;
     ctx->stats.total_ms[2] += ctx->stats.ms_remap; ctx->stats.total_ms[4] += ctx->stats.ms_migrate;
     return GM_OK;

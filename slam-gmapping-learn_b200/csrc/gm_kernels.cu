@@ -580,6 +580,12 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
             } else {
                 A.poses[3 * p] = S.cur[0]; A.poses[3 * p + 1] = S.cur[1]; A.poses[3 * p + 2] = S.cur[2];
                 A.score[p] = S.bestScore; A.s[p] = ss; A.l[p] = ll; A.c[p] = cc; A.evals[p] = S.evals;
+                // the all-gather of the sharded filter happens here: every rank's gather buffer gets this particle's row
+                // (its own HBM, or a peer's over NVLink); the flag below tells the ranks when a whole slice has landed
+                for (int r = 0; r < A.nranks; r++) {
+                    double* row = A.rows[r] + 5 * (size_t)(A.first_global + p);
+                    row[0] = S.cur[0]; row[1] = S.cur[1]; row[2] = S.cur[2]; row[3] = S.bestScore; row[4] = ll;
+                }
                 atomicAdd(&A.counters->score_evals, (unsigned long long)S.evals);
                 atomicAdd(&A.counters->beam_evals, (unsigned long long)S.evaluated * A.valid_score_beams + vv);
             }
@@ -602,6 +608,16 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
         want_table(S, 0, lt, 0, nfill);
         for (int j = nfill; j < 3; j++) S.fill[j] = -1;
         S.ncand = 1; S.mode = 1; S.phase = 2;
+    }
+    // the last CTA publishes the sequence number of this scan where every rank's host can see it (release pattern: rows,
+    // system-wide fence, count; the CTA that counts last fences again and writes the flag)
+    if (!QUERY && A.flag && t == 0) {
+        __threadfence_system();
+        if (atomicAdd(A.done_counter, 1u) == gridDim.x - 1) {
+            *A.done_counter = 0;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned*>(A.flag) = A.seq;
+        }
     }
 }
 
@@ -671,6 +687,7 @@ __global__ void __launch_bounds__(256) k_bounds(BoundsArgs A) {
 // outside the new directory lose this particle's reference (harray2d.h:80-109).
 __global__ void k_relayout(RelayoutArgs A) {
     const unsigned p = blockIdx.x;
+    if (A.counters->need_dir_cap > A.dir_cap_old && A.dir_cap_new == A.dir_cap_old) return;  // the host grows the stride first
     const int4 sh = A.shift[p];
     if (!sh.z) return;
     const Geom og = A.geom[p], ng = A.geom_new[p];
@@ -689,6 +706,7 @@ __global__ void k_relayout(RelayoutArgs A) {
 }
 __global__ void k_relayout_commit(RelayoutArgs A) {
     const unsigned p = blockIdx.x;
+    if (A.counters->need_dir_cap > A.dir_cap_old && A.dir_cap_new == A.dir_cap_old) return;
     const int4 sh = A.shift[p];
     const Geom ng = A.geom_new[p];
     // after a capacity growth every particle moves to the new stride; otherwise only resized ones change
@@ -824,6 +842,9 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevParams& P = A.P;
     const unsigned p = blockIdx.x;
+    // launched without waiting for k_bounds' verdict: stand down when a ray is too long, or when a resize needs a longer
+    // directory stride than the allocation has (the host grows it and registers again, see gmi_register_finish)
+    if (A.counters->error != 0 || A.counters->need_dir_cap > A.dir_cap) return;
     const Geom g = A.geom[p];
     int* dirp = A.dir + (size_t)p * A.dir_cap;
     const int nent = g.npx * g.npy, nwords = (nent + 31) >> 5;
@@ -1221,11 +1242,17 @@ __global__ void k_fill_geom(Geom* g, unsigned n, Geom v) {
 // ------------------------------------------------------------------------------------------------
 // normalize (gridslamprocessor.hxx:82-121).  exp() in parallel; the two sums are sequential in the
 // reference, so one thread walks them in order (N <= 64K doubles: tens of microseconds).
-__global__ void __launch_bounds__(1024) k_normalize(const double* __restrict__ logw, unsigned n, double gain_sigma,
+// With `rows` (gm_scanmatch_weights) the log-weights first take this scan's log-likelihood, weight += l
+// (gridslamprocessor.hxx:50-52; rows[5 i + 4] is particle i's l): the host applies the same single addition to its copy.
+__global__ void __launch_bounds__(1024) k_normalize(double* __restrict__ logw, const double* __restrict__ rows, unsigned n, double gain_sigma,
                                                     double* __restrict__ w, double* __restrict__ neff_out) {
     __shared__ double red[32];
     __shared__ double s_val;
     double lmax = -1.7976931348623157e308;
+    if (rows) {
+        for (unsigned i = threadIdx.x; i < n; i += blockDim.x) logw[i] = logw[i] + rows[5 * (size_t)i + 4];
+        __syncthreads();
+    }
     for (unsigned i = threadIdx.x; i < n; i += blockDim.x) { double v = logw[i]; lmax = v > lmax ? v : lmax; }
     lmax = warp_max(lmax);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lmax;
@@ -1424,7 +1451,9 @@ void launch_merge_free(const Pool& p, cudaStream_t st) { k_merge_free<<<1, 1024,
 void launch_pool_init(const Pool& p, cudaStream_t st) { k_pool_init<<<(p.cap + 255) / 256, 256, 0, st>>>(p); }
 void launch_fill_int(int* p, size_t n, int v, cudaStream_t st) { k_fill_int<<<1184, 256, 0, st>>>(p, n, v); }
 void launch_fill_geom(Geom* g, unsigned n, Geom v, cudaStream_t st) { k_fill_geom<<<(n + 255) / 256, 256, 0, st>>>(g, n, v); }
-void launch_normalize(const double* logw, unsigned n, double gain, double* w, double* neff, cudaStream_t st) { k_normalize<<<1, 1024, 0, st>>>(logw, n, gain, w, neff); }
+void launch_normalize(const double* logw, const double* rows, unsigned n, double gain, double* w, double* neff, cudaStream_t st) {
+    k_normalize<<<1, 1024, 0, st>>>(const_cast<double*>(logw), rows, n, gain, w, neff);
+}
 void launch_resample(const double* w, unsigned n, double u01, double* cum, double* tgt, unsigned* idx, unsigned* emitted, cudaStream_t st) {
     k_resample<<<1, 1024, 0, st>>>(w, n, u01, cum, tgt, idx, emitted);
 }

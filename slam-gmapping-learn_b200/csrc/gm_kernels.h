@@ -21,6 +21,14 @@ struct ScanMatchArgs {
     const unsigned* particle_idx;
     int zero_patch;  // pool index of the all-zero patch
     double* poses_out;  // query 2 (standalone optimize): climbed poses
+    // fused result rows (gm_scanmatch_weights): particle p writes {x, y, theta, optimize() score, l} to row first_global + p
+    // of rows[r] for every rank r -- rows[r] is rank r's gather buffer, its own HBM or a peer's mapped through CUDA IPC
+    // (stores over NVLink).  The last CTA to finish then publishes `seq` in *flag (host memory every rank can poll).
+    double* rows[kMaxRanks];
+    int nranks;             // 0: no rows
+    unsigned first_global;
+    unsigned* done_counter; // CTAs finished (device memory, left at 0)
+    unsigned* flag; unsigned seq;
 };
 struct BoundsArgs {
     DevParams P;
@@ -29,6 +37,7 @@ struct BoundsArgs {
     Counters* counters;
 };
 struct RelayoutArgs {
+    const Counters* counters;  // the kernels stand down when k_bounds asked for a longer directory stride than dir_cap_old
     Geom* geom; const Geom* geom_new; const int4* shift;
     const int* dir; int* dir_alt; int* dir_out;
     int dir_cap_old, dir_cap_new;
@@ -70,7 +79,7 @@ void launch_merge_free(const Pool& p, cudaStream_t st);
 void launch_pool_init(const Pool& p, cudaStream_t st);
 void launch_fill_int(int* p, size_t n, int v, cudaStream_t st);
 void launch_fill_geom(Geom* g, unsigned n, Geom v, cudaStream_t st);
-void launch_normalize(const double* logw, unsigned n, double gain, double* w, double* neff, cudaStream_t st);
+void launch_normalize(const double* logw, const double* rows, unsigned n, double gain, double* w, double* neff, cudaStream_t st);
 void launch_resample(const double* w, unsigned n, double u01, double* cum, double* tgt, unsigned* idx, unsigned* emitted, cudaStream_t st);
 void launch_digest(const DigestArgs& a, unsigned n, cudaStream_t st);
 void launch_export_occupancy(const int* dirp, Geom g, const int4* pool, const int* visits, double occ_thresh, signed char* out, int width, int height, cudaStream_t st);

@@ -141,7 +141,7 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
         // running totals since init(): device ms per stage (scanmatch, weights, remap, register, migrate, allgather), host ms
         // (motion, scanMatch call, tree weights, resample call), work done
         double totalMs[6], totalHostMs[4];
-        unsigned long long totalBeamEvals, totalScoreEvals, totalScanMatches;
+        unsigned long long totalBeamEvals, totalScoreEvals, totalScanMatches, totalMigratedParticles, totalMigratedBytes;
     };
     DeviceStats deviceStats() const;
     // Multi-GPU sharding (call before init): this process is rank `rank` of `world`, one GPU each; ncclId is the 128-byte
@@ -225,7 +225,7 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     mutable bool m_treeDirty = false;
     double m_hostMs[4];
     double m_hostMsTotal[4] = {0, 0, 0, 0};
-    std::vector<double> m_poseBuf, m_scoreBuf, m_likBuf;
+    std::vector<double> m_poseBuf, m_rowBuf, m_logwBuf;
 };
 
 typedef std::multimap<const GridSlamProcessor::TNode*, GridSlamProcessor::TNode*> TNodeMultimap;

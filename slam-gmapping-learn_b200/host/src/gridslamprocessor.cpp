@@ -103,6 +103,7 @@ GridSlamProcessor::GridSlamProcessor()
       m_linearThresholdDistance(0), m_angularThresholdDistance(0), m_infoStream(std::cout), m_rank(0), m_world(1), m_firstLocal(0),
       m_localCount(0), m_treeEpoch(0) {
     m_motionModel.srr = m_motionModel.srt = m_motionModel.str = m_motionModel.stt = 0;
+    m_hostMs[0] = m_hostMs[1] = m_hostMs[2] = m_hostMs[3] = 0;
     defaults(*this);
 }
 
@@ -112,6 +113,7 @@ GridSlamProcessor::GridSlamProcessor(std::ostream& infoS)
       m_linearThresholdDistance(0), m_angularThresholdDistance(0), m_infoStream(infoS), m_rank(0), m_world(1), m_firstLocal(0),
       m_localCount(0), m_treeEpoch(0) {
     m_motionModel.srr = m_motionModel.srt = m_motionModel.str = m_motionModel.stt = 0;
+    m_hostMs[0] = m_hostMs[1] = m_hostMs[2] = m_hostMs[3] = 0;
     defaults(*this);
 }
 
@@ -126,7 +128,7 @@ GridSlamProcessor::GridSlamProcessor(const GridSlamProcessor& gsp)
       m_xmax(gsp.m_xmax), m_ymax(gsp.m_ymax), m_delta(gsp.m_delta), m_regScore(gsp.m_regScore), m_critScore(gsp.m_critScore), m_maxMove(gsp.m_maxMove),
       m_linearThresholdDistance(gsp.m_linearThresholdDistance), m_angularThresholdDistance(gsp.m_angularThresholdDistance),
       m_obsSigmaGain(gsp.m_obsSigmaGain), m_infoStream(std::cout), m_rank(0), m_world(1), m_firstLocal(0), m_localCount(gsp.m_localCount),
-      m_treeEpoch(0) {
+      m_treeEpoch(0), m_lazyTree(gsp.m_lazyTree), m_earlyRegistration(gsp.m_earlyRegistration) {
     if (gsp.m_world > 1) b200::fatal("GridSlamProcessor copy / clone(): a sharded filter cannot be cloned");
     m_hostMs[0] = m_hostMs[1] = m_hostMs[2] = m_hostMs[3] = 0;
     m_hostMsTotal[0] = m_hostMsTotal[1] = m_hostMsTotal[2] = m_hostMsTotal[3] = 0;
@@ -266,53 +268,50 @@ void GridSlamProcessor::markMapsStale() {
 }
 
 // ------------------------------------------------------------------------------------------ the GPU stages
-// scanMatch (reference: gridslamprocessor.hxx:15-75): optimize + accept/reject + likelihoodAndScore for all particles
+// scanMatch (reference: gridslamprocessor.hxx:15-75): optimize + accept/reject + likelihoodAndScore for all particles, and -- in
+// the same stream-ordered device sequence, one synchronisation -- the normalize() of the updateTreeWeights that follows
+// (gridslamprocessor.cpp:586): the device adds each particle's l to the log-weight it was given, exactly like the loop below.
+// Sharded: the rows of every rank's particles come back in global order (they reach every GPU from the kernel's epilogue).
 void GridSlamProcessor::scanMatch(const double* plainReading) {
     const size_t n = m_particles.size(), nl = m_localCount;
-    m_poseBuf.resize(3 * nl); m_scoreBuf.resize(n); m_likBuf.resize(n);
+    m_poseBuf.resize(3 * nl); m_rowBuf.resize(5 * n); m_logwBuf.resize(n);
     for (size_t j = 0; j < nl; j++) {
         const OrientedPoint& q = m_particles[m_firstLocal + j].pose;
         m_poseBuf[3 * j] = q.x; m_poseBuf[3 * j + 1] = q.y; m_poseBuf[3 * j + 2] = q.theta;
     }
+    for (size_t i = 0; i < n; i++) m_logwBuf[i] = m_particles[i].weight;
+    m_weights.resize(n);
     m_device->configure(m_matcher);
-    m_device->check(gm_scanmatch(m_device->h, plainReading, m_poseBuf.data(), m_minimumScore, m_scoreBuf.data(), 0, m_likBuf.data(), 0, 0),
-                    "gm_scanmatch");
-    std::vector<double> all;  // rows of (x, y, theta, score, l) for all particles, in global order
-    if (m_world > 1) {
-        std::vector<double> mine(5 * nl);
-        for (size_t j = 0; j < nl; j++) {
-            mine[5 * j] = m_poseBuf[3 * j]; mine[5 * j + 1] = m_poseBuf[3 * j + 1]; mine[5 * j + 2] = m_poseBuf[3 * j + 2];
-            mine[5 * j + 3] = m_scoreBuf[j]; mine[5 * j + 4] = m_likBuf[j];
-        }
-        all.resize(5 * n);
-        m_device->check(gm_dist_allgather(m_device->h, mine.data(), (uint32_t)(5 * nl), all.data()), "gm_dist_allgather");
-    }
+    m_device->check(gm_scanmatch_weights(m_device->h, plainReading, m_poseBuf.data(), m_minimumScore, m_logwBuf.data(), m_obsSigmaGain,
+                                         m_rowBuf.data(), m_weights.data(), &m_neff),
+                    "gm_scanmatch_weights");
     double sumScore = 0;
     for (size_t i = 0; i < n; i++) {
         Particle& p = m_particles[i];
-        const double score = m_world > 1 ? all[5 * i + 3] : m_scoreBuf[i], lik = m_world > 1 ? all[5 * i + 4] : m_likBuf[i];
+        const double* row = &m_rowBuf[5 * i];
+        const double score = row[3], lik = row[4];
         sumScore += score;
         if (!(score > m_minimumScore) && m_infoStream) {
             m_infoStream << "Scan Matching Failed, using odometry. Likelihood=" << lik << endl;
             m_infoStream << "lp:" << m_lastPartPose.x << " " << m_lastPartPose.y << " " << m_lastPartPose.theta << endl;
             m_infoStream << "op:" << m_odoPose.x << " " << m_odoPose.y << " " << m_odoPose.theta << endl;
         }
-        p.pose = m_world > 1 ? OrientedPoint(all[5 * i], all[5 * i + 1], all[5 * i + 2])
-                             : OrientedPoint(m_poseBuf[3 * i], m_poseBuf[3 * i + 1], m_poseBuf[3 * i + 2]);
+        p.pose = OrientedPoint(row[0], row[1], row[2]);
         p.weight += lik;
         p.weightSum += lik;
+        m_logwBuf[i] = p.weight;  // what m_weights / m_neff were computed from
     }
-    m_weightsChanged = true;
+    m_weightsChanged = false;
     if (m_infoStream) m_infoStream << "Average Scan Matching Score=" << sumScore / n << endl;
 }
 
 // normalize (reference: gridslamprocessor.hxx:82-121): weights = softmax(gain * log-weights), Neff = 1 / sum w^2
 void GridSlamProcessor::normalize() {
     const size_t n = m_particles.size();
-    std::vector<double> logw(n);
-    for (size_t i = 0; i < n; i++) logw[i] = m_particles[i].weight;
+    m_logwBuf.resize(n);
+    for (size_t i = 0; i < n; i++) m_logwBuf[i] = m_particles[i].weight;
     m_weights.resize(n);
-    m_device->check(gm_normalize_neff(m_device->h, logw.data(), (uint32_t)n, m_obsSigmaGain, m_weights.data(), &m_neff), "gm_normalize_neff");
+    m_device->check(gm_normalize_neff(m_device->h, m_logwBuf.data(), (uint32_t)n, m_obsSigmaGain, m_weights.data(), &m_neff), "gm_normalize_neff");
 }
 
 // particle copy by patch reference (when `parents` is given) + computeActiveArea + registerScan for every particle
@@ -405,7 +404,11 @@ bool GridSlamProcessor::resample(const double* plainReading, int adaptSize, cons
 // normalize() unless no log-weight changed since the last time (the second updateTreeWeights of a processScan that did
 // not resample sees the log-weights of the first: same weights, same Neff)
 void GridSlamProcessor::normalizeIfNeeded() {
-    if (m_weightsChanged || m_weights.size() != m_particles.size()) { normalize(); m_weightsChanged = false; }
+    const size_t n = m_particles.size();
+    bool same = !m_weightsChanged && m_weights.size() == n && m_logwBuf.size() == n;
+    // a subclass may have touched a log-weight in one of the hooks (m_particles is protected): compare with what was normalised
+    for (size_t i = 0; same && i < n; i++) same = m_particles[i].weight == m_logwBuf[i];
+    if (!same) { normalize(); m_weightsChanged = false; }
 }
 
 void GridSlamProcessor::updateTreeWeights(bool weightsAlreadyNormalized) {
@@ -680,6 +683,7 @@ GridSlamProcessor::DeviceStats GridSlamProcessor::deviceStats() const {
     for (int k = 0; k < 6; k++) d.totalMs[k] = s.total_ms[k];
     for (int k = 0; k < 4; k++) d.totalHostMs[k] = m_hostMsTotal[k];
     d.totalBeamEvals = s.total_beam_evals; d.totalScoreEvals = s.total_score_evals; d.totalScanMatches = s.total_scanmatches;
+    d.totalMigratedParticles = s.total_migrated_particles; d.totalMigratedBytes = s.total_migrated_bytes;
     d.msHostMotion = m_hostMs[0]; d.msHostScanMatch = m_hostMs[1]; d.msHostTreeWeights = m_hostMs[2]; d.msHostResample = m_hostMs[3];
     d.msMigrate = s.ms_migrate; d.msAllGather = s.ms_allgather; d.migratedParticles = s.migrated_particles; d.migratedBytes = s.migrated_bytes;
     return d;
@@ -689,6 +693,9 @@ void GridSlamProcessor::setDistributed(int rank, int world, const void* ncclId) 
     if (world < 1 || rank < 0 || rank >= world || (world > 1 && !ncclId)) b200::fatal("GridSlamProcessor::setDistributed: bad rank / world / id");
     m_rank = rank;
     m_world = world;
+    // every rank carries the whole trajectory tree: the weight propagation (O(particles) pointer chasing per scan, replicated)
+    // is deferred to the readers of TNode::accWeight -- getTrajectories() / refreshTreeWeights() -- unless asked otherwise
+    if (world > 1) m_lazyTree = true;
     if (ncclId) memcpy(m_ncclId, ncclId, sizeof m_ncclId);
 }
 

@@ -30,9 +30,12 @@ def make(g, rank, world, nccl_id):
 def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
     mock = "libgm_mock" in os.environ.get("LD_PRELOAD", "")
-    dev = "cpu" if mock else "cuda"
+    # GM_DIST_SAME_GPU: both ranks drive GPU 0 (a one-GPU box): the filter's own exchange is peer memory through CUDA IPC and
+    # does not care; torch.distributed, which only carries the session id and the final tallies, falls back to gloo
+    same_gpu = bool(os.environ.get("GM_DIST_SAME_GPU"))
+    dev = "cpu" if (mock or same_gpu) else "cuda"
     ptol, rtol = (0.0, 0.0) if mock else (1e-4, 1e-3)
-    if mock:
+    if mock or same_gpu:
         dist.init_process_group("gloo")
     else:
         torch.cuda.set_device(local)
@@ -44,7 +47,7 @@ def main():
         dist.broadcast(t, 0)
         return bytes(t.cpu().tolist())
 
-    for case in ("room181_n30", "room181_k2_lskip"):
+    for case in os.environ.get("GM_DIST_CASES", "room181_n30,room181_k2_lskip").split(","):
         g = Golden(case)
         sharded = make(g, rank, world, fresh_id())
         lo, hi = sharded.local_range()

@@ -147,45 +147,29 @@ def scenario_lazy_tree():
     np.testing.assert_allclose(t0[:, 1:4], g.tree[last][:, 1:4], rtol=1e-4, atol=1e-9)
 
 
-def scenario_long(limit=None):
+def scenario_long(limit=None, fixture="room181_long"):
     """BASELINE.json configs[0]/[1]: 30 particles, 181-beam scans, 1000 scans, free running through the C++ API against the
     unmodified reference (fixture: Neff and flags for every scan, all poses / log-weights every 10th scan): the filter never
-    leaves the reference's trajectory -- same resampling scans, same indexes, poses within 1e-4, log-weights within 1e-3."""
+    leaves the reference's trajectory -- same resampling scans, same indexes, poses within 1e-4, log-weights within 1e-3.
+    Other fixtures of the same kind: room1081_c3 (BASELINE.json configs[2], 512 particles x 1081 beams, 56 scans of the
+    benchmark's log with the benchmark's parameters) and room181_n32 (32 particles, the sharded-parity prelude of bench.py)."""
     build_host()
-    hostapi = importlib.import_module("slam-gmapping-learn_b200.hostapi")
-    z = np.load(os.path.join(ROOT, "tests", "golden", "room181_long.npz"))
-    p = json.loads(str(z["params"]))
-    log = synth.make_log("room", synth.LMS200, scans=int(z["scans"]), step=0.25, seed=int(z["log_seed"]))
-    assert np.array_equal(log.laser.angles(), z["angles"])
-    f = hostapi.Processor(z["angles"], p["particles"], z["head_init"], bounds=(p["xmin"], p["ymin"], p["xmax"], p["ymax"]), delta=p["delta"],
-                          seed=p["seed"], **{k: p[k] for k in hostapi.PARAM_ORDER})
-    kept = {int(s): k for k, s in enumerate(z["kept"])}
-    rsc = {int(s): k for k, s in enumerate(z["ridx_scans"])}
-    worst_pose = worst_w = 0.0
-    scans = int(z["scans"]) if limit is None else min(int(limit), int(z["scans"]))
-    for i in range(scans):
-        done = f.process_scan(log.ranges[i], log.odom[i], log.stamps[i])
-        assert done == bool(z["processed"][i])
-        assert f.last_resampled() == bool(z["resampled"][i]), "scan %d: resampling decision" % i
-        assert abs(f.neff() - z["neff"][i]) <= 1e-6 * z["neff"][i], "scan %d: Neff" % i
-        if i in rsc:
-            assert np.array_equal(f.indexes(), z["ridx"][rsc[i]]), "scan %d: resample indexes" % i
-        if i in kept:
-            st = f.state(); k = kept[i]
-            worst_pose = max(worst_pose, float(np.abs(st[:, :3] - z["poses"][k]).max()))
-            worst_w = max(worst_w, float(np.abs(st[:, 3:5] - z["weights"][k]).max() / max(1.0, np.abs(z["weights"][k]).max())))
-            assert np.array_equal(st[:, 5], z["prev"][k])
-    assert worst_pose < 1e-4 and worst_w < 1e-3, (worst_pose, worst_w)
-    if scans == int(z["scans"]):
-        d = f.map_digests()
-        assert np.array_equal(d[:, :5], digest_rows(z["digests"])[:, :5]), "final maps: (n, visits) of every cell of every particle"
-        assert f.best() == int(z["best"])
-    f.close()
-    return worst_pose, worst_w
+    selfcheck = importlib.import_module("slam-gmapping-learn_b200.selfcheck")
+    r = selfcheck.follow(fixture, limit)
+    return r["worst_pose"], r["worst_weight"], r["resamples"]
+
+
+def scenario_c3(limit=None):
+    return scenario_long(limit, "room1081_c3")
+
+
+def scenario_n32(limit=None):
+    return scenario_long(limit, "room181_n32")
 
 
 if __name__ == "__main__":
     name, _, arg = sys.argv[1].partition(":")
-    fn = {"cli": scenario_cli, "clone": scenario_clone, "order": scenario_order, "long": scenario_long, "lazy_tree": scenario_lazy_tree}[name]
+    fn = {"cli": scenario_cli, "clone": scenario_clone, "order": scenario_order, "long": scenario_long, "lazy_tree": scenario_lazy_tree, "c3": scenario_c3,
+          "n32": scenario_n32}[name]
     out = fn(int(arg)) if arg else fn()
     print("scenario %s ok %s" % (sys.argv[1], "" if out is None else out))

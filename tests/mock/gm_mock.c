@@ -432,7 +432,7 @@ static void dist_unlink(const struct dist_state* d, const char* kind, unsigned l
     unlink(fin);
 }
 
-int gm_dist_allgather(gm_ctx* c, const double* local, uint32_t count, double* all) {
+static int dist_allgather(gm_ctx* c, const double* local, uint32_t count, double* all) {
     if (!c || !c->dist) return fail(c, GM_ERR_ARG, "gm_dist_allgather: gm_dist_init has not been called");
     if (!local || !all) return fail(c, GM_ERR_ARG, "gm_dist_allgather: null argument");
     struct dist_state* d = c->dist;
@@ -523,6 +523,7 @@ static int dist_remap(gm_ctx* c, const uint32_t* idx_global) {
     c->dist_sent_prev2 = c->dist_sent_prev; c->dist_seq_prev2 = c->dist_seq_prev;
     c->dist_sent_prev = sent; c->dist_seq_prev = seq;
     c->stats.migrated_particles = imported; c->stats.migrated_bytes = imported_bytes;
+    c->stats.total_migrated_particles += imported; c->stats.total_migrated_bytes += imported_bytes;
     return GM_OK;
 }
 
@@ -542,4 +543,39 @@ int gm_dist_register(gm_ctx* c, const double* ranges, const double* poses, const
     c->stats.migrated_particles = 0; c->stats.migrated_bytes = 0;
     if (idx_global && (r = dist_remap(c, idx_global))) return r;
     return gm_register(c, ranges, poses, NULL);
+}
+
+/* scanMatch + weight += l + normalize in one call; on a sharded context the rows of all ranks (exchanged through files here,
+ * through peer memory in the product) in global particle order */
+int gm_scanmatch_weights(gm_ctx* c, const double* ranges, const double* poses_local, double minimum_score, const double* log_weights,
+                         double gain, double* rows_out, double* weights_out, double* neff_out) {
+    int r = ready(c);
+    if (r) return r;
+    if (!ranges || !poses_local || !log_weights || !rows_out) return fail(c, GM_ERR_ARG, "gm_scanmatch_weights: null argument");
+    const uint32_t n = c->n, world = c->dist ? (uint32_t)c->dist->world : 1u, N = n * world;
+    if (N > c->weights_cap) return fail(c, GM_ERR_ARG, "gm_scanmatch_weights: %u particles over all ranks, the context was created for %u", N, c->weights_cap);
+    double* poses = (double*)malloc(sizeof(double) * 3 * n);
+    double* score = (double*)malloc(sizeof(double) * n);
+    double* l = (double*)malloc(sizeof(double) * n);
+    double* mine = (double*)malloc(sizeof(double) * 5 * n);
+    memcpy(poses, poses_local, sizeof(double) * 3 * n);
+    r = gm_scanmatch(c, ranges, poses, minimum_score, score, NULL, l, NULL, NULL);
+    for (uint32_t i = 0; i < n && !r; i++) {
+        mine[5 * i] = poses[3 * i]; mine[5 * i + 1] = poses[3 * i + 1]; mine[5 * i + 2] = poses[3 * i + 2];
+        mine[5 * i + 3] = score[i]; mine[5 * i + 4] = l[i];
+    }
+    if (!r) {
+        if (c->dist) r = dist_allgather(c, mine, 5 * n, rows_out);
+        else memcpy(rows_out, mine, sizeof(double) * 5 * n);
+    }
+    free(poses); free(score); free(l); free(mine);
+    if (r) return r;
+    double* logw = (double*)malloc(sizeof(double) * N);
+    double* w = (double*)malloc(sizeof(double) * N);
+    for (uint32_t i = 0; i < N; i++) logw[i] = log_weights[i] + rows_out[5 * (size_t)i + 4];
+    const double neff = orc_normalize(logw, N, gain, w);
+    if (weights_out) memcpy(weights_out, w, sizeof(double) * N);
+    if (neff_out) *neff_out = neff;
+    free(logw); free(w);
+    return GM_OK;
 }

@@ -1,4 +1,6 @@
-"""Two-GPU run of the sharded filter (needs >= 2 GPUs: `gpurun --gpus 2 -- python -m pytest tests -m gpu`)."""
+"""The sharded filter on real GPUs: two ranks, peer-memory exchange of the scan-match rows, pull migration of resampled
+parents -- on two GPUs when the box has them, otherwise both ranks on GPU 0 (CUDA IPC works within one device, so the
+whole exchange path runs on a one-GPU box too)."""
 import os
 import subprocess
 import sys
@@ -8,14 +10,30 @@ import pytest
 from host_common import ROOT, build_host
 
 
-@pytest.mark.gpu
-def test_sharded_filter_two_gpus():
+def run_dist_check(port, extra_env, timeout=600):
     import torch
+    env = dict(os.environ)
     if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    build_host()
+        env["GM_DIST_SAME_GPU"] = "1"
+        env["GM_B200_DEVICE"] = "0"
+    env.update(extra_env)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29611", os.path.join(ROOT, "tests", "dist_check.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "--master-port", str(port), os.path.join(ROOT, "tests", "dist_check.py")]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+
+
+@pytest.mark.gpu
+def test_sharded_filter_two_ranks():
+    build_host()
+    res = run_dist_check(29611, {})
     assert res.returncode == 0, (res.stdout[-2000:], res.stderr[-4000:])
-    assert "dist_check room181_n30: ok" in res.stdout
+    assert "dist_check room181_n30: ok" in res.stdout and "dist_check room181_k2_lskip: ok" in res.stdout
+
+
+@pytest.mark.gpu
+def test_pool_exhaustion_during_migration_is_loud():
+    """a pool too small for the imported parents: the run must die with the pool message on every rank, not continue with holes"""
+    build_host()
+    res = run_dist_check(29612, {"GM_B200_POOL_PATCHES": "1700", "GM_B200_DIST_TIMEOUT_S": "30", "GM_DIST_CASES": "room181_n30"}, timeout=300)
+    assert res.returncode != 0
+    assert "exhausted" in res.stderr, res.stderr[-3000:]

@@ -123,12 +123,13 @@ def run_case(name, log_kw, par):
         name, S, int(a["processed"].sum()), int(a["resampled"].sum()), os.path.getsize(path) / 1024, out.strip()[:80]))
 
 
-def run_long(name="room181_long", scans=1000, particles=30):
+def run_long(name="room181_long", scans=1000, particles=30, laser="LMS200", log_seed=7, every=10, step=0.25, **par):
     """BASELINE.json configs[0]/[1]: 30 particles, 181 beams, 1000 scans.  Too long for a full per-stage trace in the
     repository: the fixture keeps, per reading, the gate / resample flags, Neff, the resample indexes and the poses +
     log-weights of all particles (float64), plus the final map digests."""
     p = dict(DEFAULTS); p.update(dict(particles=particles, linearUpdate=0.2, angularUpdate=0.1, srr=0.05, srt=0.1, str=0.05, stt=0.1, maps_every=0))
-    log = synth.make_log(world="room", laser=synth.LMS200, scans=scans, step=0.25, seed=7)
+    p.update(par)
+    log = synth.make_log(world="room", laser=getattr(synth, laser), scans=scans, step=step, seed=log_seed)
     with tempfile.TemporaryDirectory() as td:
         lp, tp = os.path.join(td, "in.log"), os.path.join(td, "trace.bin")
         synth.write_carmen(log, lp)
@@ -150,9 +151,9 @@ def run_long(name="room181_long", scans=1000, particles=30):
     path = os.path.join(GOLD, name + ".npz")
     # Neff and the flags for every scan; poses / weights every 10th scan, at the last one and where the filter resampled
     rs = np.nonzero(resampled)[0]
-    keep = np.union1d(np.union1d(np.arange(0, S, 10), [S - 1]), rs)
+    keep = np.union1d(np.union1d(np.arange(0, S, every), [S - 1]), rs)
     np.savez_compressed(path, params=np.array(json.dumps(p)), head_init=tr["head"]["init"], angles=tr["angles"],
-                        log_seed=np.array(7), scans=np.array(scans), processed=processed, resampled=resampled, neff=neff,
+                        log_seed=np.array(log_seed), laser=np.array(laser), step=np.array(step), scans=np.array(scans), processed=processed, resampled=resampled, neff=neff,
                         ridx_scans=rs, ridx=ridx[rs], kept=keep,
                         poses=state[keep, :, :3], weights=state[keep, :, 3:5].astype(np.float64), prev=state[keep, :, 5].astype(np.int16),
                         digests=tr["final"]["digests"], geometry=tr["final"]["geometry"], best=np.array(tr["final"]["best"]))
@@ -196,6 +197,15 @@ def run_units(name="units"):
 def main():
     if "long" in sys.argv[1:]:
         run_long(); return
+    if "c3" in sys.argv[1:]:
+        # BASELINE.json configs[2] (SURVEY.md 8d "a >= 50-scan prefix of C3"): 512 particles x 1081 beams, the benchmark's log and
+        # parameters (ROS-default motion noise: the filter resamples); ~12 minutes of the reference on one core
+        run_long("room1081_c3", scans=56, particles=512, laser="UTM30", log_seed=1, every=8, maxrange=30.0, maxUrange=29.0,
+                 srr=0.1, srt=0.2, str=0.1, stt=0.2); return
+    if "n32" in sys.argv[1:]:
+        # 32 particles (divisible by 2, 4 and 8 ranks) for the sharded-parity prelude of bench.py
+        run_long("room181_n32", scans=40, particles=32, laser="LMS200", log_seed=1, every=5, step=0.5, linearUpdate=0.4, angularUpdate=0.2,
+                 srr=0.1, srt=0.2, str=0.1, stt=0.2); return
     if "units" in sys.argv[1:]:
         run_units(); return
     if not os.path.exists(REF):
