@@ -53,8 +53,12 @@ REFERENCE_PROCS = 16         # processes of the reference arm: the same on every
 LINEARITY_PARTICLES = 512    # one measured reference point at a large particle count next to the extrapolated one
 NOISE = {"ros": dict(srr=0.1, srt=0.2, str=0.1, stt=0.2),          # gmapping/src/slam_gmapping.cpp defaults
          "carmen": dict(srr=0.01, srt=0.01, str=0.01, stt=0.01)}  # gfs-carmen.cpp:52-84 (round 1's workload)
+# lobsGain: the weights are softmax(l / (ogain * N)) (gridslamprocessor.hxx:93), so gfs-carmen's ogain 3, tuned for its 30
+# particles, never lets Neff drop at 4096 (round 1: no resampling in the timed region).  The benchmark keeps that
+# configuration's EFFECTIVE gain, ogain * N = 90, at every particle count -- in both arms
+GAIN_TIMES_PARTICLES = 90.0
 PARAMS = dict(maxrange=30.0, maxUrange=29.0, sigma=0.05, kernelSize=1, lstep=0.05, astep=0.05, iterations=5, lsigma=0.075,
-              ogain=3.0, lskip=0, resampleThreshold=0.5, delta=0.05, xmin=-100.0, ymin=-100.0, xmax=100.0, ymax=100.0,
+              lskip=0, resampleThreshold=0.5, delta=0.05, xmin=-100.0, ymin=-100.0, xmax=100.0, ymax=100.0,
               linearUpdate=0.2, angularUpdate=0.1)
 
 
@@ -63,7 +67,8 @@ def workload_config(particles, noise):
     return {"workload": "%d particles x 1081 beams (270 deg, 0.25 deg), 0.05 m grid, 200x200 m map, synthetic 18x12 m room log, "
                         "every scan processed, motion noise %s" % (particles, noise),
             "particles": particles, "beams": 1081, "noise": noise,
-            "params": "gfs-carmen matcher defaults, maxUrange 29 / maxrange 30, " + ", ".join("%s %g" % kv for kv in NOISE[noise].items())}
+            "params": "gfs-carmen matcher defaults, maxUrange 29 / maxrange 30, lobsGain x particles = %g, " % GAIN_TIMES_PARTICLES +
+                      ", ".join("%s %g" % kv for kv in NOISE[noise].items())}
 
 
 def measured_peak():
@@ -128,6 +133,7 @@ def reference_cmd(particles, scans, log_path, noise):
            "-maxUrange", repr(PARAMS["maxUrange"]), "-linearUpdate", repr(PARAMS["linearUpdate"]), "-angularUpdate", repr(PARAMS["angularUpdate"])]
     for k, v in NOISE[noise].items():
         cmd += ["-" + k, repr(v)]
+    cmd += ["-ogain", repr(GAIN_TIMES_PARTICLES / particles)]  # a slice of the filter weighs like the whole filter
     return exe, cmd
 
 
@@ -259,7 +265,7 @@ def main():
                              delta=PARAMS["delta"], seed=12345, rank=rank, world=world, nccl_id=session_id(),
                              maxUrange=PARAMS["maxUrange"], maxrange=PARAMS["maxrange"], sigma=PARAMS["sigma"], kernelSize=PARAMS["kernelSize"],
                              lstep=PARAMS["lstep"], astep=PARAMS["astep"], iterations=PARAMS["iterations"], lsigma=PARAMS["lsigma"],
-                             ogain=PARAMS["ogain"], lskip=PARAMS["lskip"], srr=noise["srr"], srt=noise["srt"], str=noise["str"], stt=noise["stt"],
+                             ogain=GAIN_TIMES_PARTICLES / n, lskip=PARAMS["lskip"], srr=noise["srr"], srt=noise["srt"], str=noise["str"], stt=noise["stt"],
                              linearUpdate=PARAMS["linearUpdate"], angularUpdate=PARAMS["angularUpdate"], resampleThreshold=PARAMS["resampleThreshold"])
     for i in range(0, 1 + W):  # first scan registers only; then W warm-up steps
         assert proc.process_scan(log.ranges[i], log.odom[i], log.stamps[i])

@@ -21,8 +21,12 @@ typedef Array2D<double> DoubleArray2D;
 // link between a host Map object and its device-resident copy (implemented in scanmatcher/devicemap.cpp)
 struct MapResidency {
     virtual ~MapResidency() {}
-    virtual void pull(void* hostMap) = 0;  // refresh the host mirror from the device
-    bool stale = false;                    // device copy is newer than the host mirror
+    virtual void pull(void* hostMap) = 0;        // refresh the host mirror from the device
+    virtual void push(const void* hostMap) = 0;  // replace the device copy by the host mirror
+    bool stale = false;                          // device copy is newer than the host mirror
+    // the mirror was handed out for writing (non-const cell() / storage() / resize() / grow()) since the last transfer: the
+    // next device call on this map uploads it first, so that a host-side edit is never silently lost
+    bool hostDirty = false;
 };
 
 template <class Cell, class Storage, const bool isClass = true>
@@ -74,7 +78,7 @@ class Map {
 
     inline Cell& cell(int x, int y) { return cell(IntPoint(x, y)); }
     inline Cell& cell(const IntPoint& p) {
-        sync();
+        syncForWrite();
         assert(m_storage.cellState(p) & Inside);
         return m_storage.cell(p);
     }
@@ -95,7 +99,7 @@ class Map {
     inline bool isInside(double x, double y) const { return m_storage.cellState(world2map(x, y)) & Inside; }
     inline bool isInside(const Point& p) const { return m_storage.cellState(world2map(p)) & Inside; }
 
-    inline Storage& storage() { sync(); return m_storage; }
+    inline Storage& storage() { syncForWrite(); return m_storage; }
     inline const Storage& storage() const { sync(); return m_storage; }
     DoubleArray2D* toDoubleArray() const;
     Map<double, DoubleArray2D, false>* toDoubleMap() const;
@@ -103,6 +107,10 @@ class Map {
     // ---- device residency (B200 addition)
     inline void sync() const {
         if (m_residency && m_residency->stale) m_residency->pull(const_cast<Map*>(this));
+    }
+    inline void syncForWrite() {
+        sync();
+        if (m_residency) m_residency->hostDirty = true;
     }
     inline const std::shared_ptr<MapResidency>& residency() const { return m_residency; }
     inline void setResidency(const std::shared_ptr<MapResidency>& r) const { m_residency = r; }
@@ -162,6 +170,7 @@ Map<Cell, Storage, isClass>::Map(const Point& center, double xmin, double ymin, 
 // only its cell index does
 template <class Cell, class Storage, const bool isClass>
 void Map<Cell, Storage, isClass>::resize(double xmin, double ymin, double xmax, double ymax) {
+    syncForWrite();
     const IntPoint imin = world2map(xmin, ymin), imax = world2map(xmax, ymax);
     const int unit = 1 << m_storage.getPatchMagnitude();
     const int pxmin = (int)floor((float)imin.x / unit), pxmax = (int)ceil((float)imax.x / unit);
@@ -178,6 +187,7 @@ void Map<Cell, Storage, isClass>::resize(double xmin, double ymin, double xmax, 
 // like resize(), but never shrinks
 template <class Cell, class Storage, const bool isClass>
 void Map<Cell, Storage, isClass>::grow(double xmin, double ymin, double xmax, double ymax) {
+    syncForWrite();
     const IntPoint imin = world2map(xmin, ymin), imax = world2map(xmax, ymax);
     if (isInside(imin) && isInside(imax)) return;
     const IntPoint lo = min(imin, IntPoint(0, 0)), hi = max(imax, IntPoint(m_mapSizeX - 1, m_mapSizeY - 1));

@@ -213,6 +213,7 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     void registerAll(const double* plainReading, const unsigned int* parents);
     void copyAll(const unsigned int* parents);
     void markMapsStale();
+    void flushHostEdits();
 
     std::shared_ptr<b200::DeviceContext> m_device;
     int m_rank, m_world;

@@ -94,11 +94,42 @@ void DeviceMapResidency::pull(void* hostMap) {
     map.setGeometry(info.size_x2, info.size_y2, info.patches_x, info.patches_y);
 }
 
+// the host mirror replaces the device copy (gm_upload_map): geometry + every allocated patch
+static void uploadMap(DeviceContext& ctx, unsigned int slot, const ScanMatcherMap& map, const HierarchicalArray2D<PointAccumulator>& st,
+                      int sizeX2, int sizeY2) {
+    const int npx = st.getXSize(), npy = st.getYSize();
+    std::vector<int32_t> coords;
+    std::vector<gm_cell> cells;
+    for (int px = 0; px < npx; px++)
+        for (int py = 0; py < npy; py++) {
+            if (!st.m_cells[px][py]) continue;
+            const Array2D<PointAccumulator>& patch = *st.m_cells[px][py];
+            coords.push_back(px); coords.push_back(py);
+            const size_t at = cells.size();
+            cells.resize(at + 1024);
+            for (int lx = 0; lx < 32; lx++) std::memcpy(static_cast<void*>(cells.data() + at + 32 * lx), patch.m_cells[lx], sizeof(gm_cell) * 32);
+        }
+    const Point c = map.getCenter();
+    gm_map_info info;
+    std::memset(&info, 0, sizeof info);
+    info.center_x = c.x; info.center_y = c.y; info.delta = map.getDelta();
+    info.size_x2 = sizeX2; info.size_y2 = sizeY2; info.patches_x = npx; info.patches_y = npy;
+    ctx.check(gm_upload_map(ctx.h, slot, &info, coords.data(), cells.data(), (uint32_t)(coords.size() / 2)), "gm_upload_map");
+}
+
+void DeviceMapResidency::push(const void* hostMap) {
+    const ScanMatcherMap& map = *static_cast<const ScanMatcherMap*>(hostMap);
+    if (stale) b200::fatal("a device-resident map was written on the host while its device copy was newer");  // cannot happen: writers sync first
+    hostDirty = false;  // first: the const accessors below must not recurse
+    uploadMap(*ctx, slot, map, map.storage(), map.getSizeX2(), map.getSizeY2());
+}
+
 DeviceMapResidency* residencyOf(const ScanMatcherMap& map) { return dynamic_cast<DeviceMapResidency*>(map.residency().get()); }
 
 DeviceMapResidency* makeResident(const ScanMatcherMap& map, const ScanMatcher& m) {
     if (DeviceMapResidency* r = residencyOf(map)) {
         r->ctx->configure(m);
+        r->flush(map);
         return r;
     }
     // a plain host map: give it a single-map context and upload what it holds
@@ -114,22 +145,7 @@ DeviceMapResidency* makeResident(const ScanMatcherMap& map, const ScanMatcher& m
     ctx->check(gm_init_particles(ctx->h, 1, center, map.getMapSizeX() * map.getDelta(), map.getMapSizeY() * map.getDelta(), map.getDelta()),
                "gm_init_particles");
     ctx->particles = 1;
-    std::vector<int32_t> coords;
-    std::vector<gm_cell> cells;
-    for (int px = 0; px < npx; px++)
-        for (int py = 0; py < npy; py++) {
-            if (!st.m_cells[px][py]) continue;
-            const Array2D<PointAccumulator>& patch = *st.m_cells[px][py];
-            coords.push_back(px); coords.push_back(py);
-            const size_t at = cells.size();
-            cells.resize(at + 1024);
-            for (int lx = 0; lx < 32; lx++) std::memcpy(cells.data() + at + 32 * lx, patch.m_cells[lx], sizeof(gm_cell) * 32);
-        }
-    gm_map_info info;
-    std::memset(&info, 0, sizeof info);
-    info.center_x = c.x; info.center_y = c.y; info.delta = map.getDelta();
-    info.size_x2 = map.getSizeX2(); info.size_y2 = map.getSizeY2(); info.patches_x = npx; info.patches_y = npy;
-    ctx->check(gm_upload_map(ctx->h, 0, &info, coords.data(), cells.data(), (uint32_t)(coords.size() / 2)), "gm_upload_map");
+    uploadMap(*ctx, 0, map, st, map.getSizeX2(), map.getSizeY2());
     std::shared_ptr<DeviceMapResidency> r(new DeviceMapResidency);
     r->ctx = ctx;
     r->slot = 0;

@@ -44,6 +44,9 @@ struct DeviceMapResidency : public MapResidency {
     std::shared_ptr<DeviceContext> ctx;
     unsigned int slot = 0;
     void pull(void* hostMap) override;
+    void push(const void* hostMap) override;
+    // upload the mirror when the host may have written to it since the last transfer
+    inline void flush(const ScanMatcherMap& map) { if (hostDirty) push(&map); }
 };
 
 int deviceOrdinal();  // GM_B200_DEVICE, else LOCAL_RANK, else 0

@@ -262,6 +262,15 @@ void GridSlamProcessor::processTruePos(const OdometryReading& o) {
     }
 }
 
+// a subclass may have edited a particle's map through the host mirror (m_particles is protected; non-const cell() / storage()
+// / resize()): such maps go back to the device before the next stage reads them
+void GridSlamProcessor::flushHostEdits() {
+    for (size_t j = 0; j < m_localCount; j++) {
+        Particle& p = m_particles[m_firstLocal + j];
+        if (p.map.residency() && p.map.residency()->hostDirty) p.map.residency()->push(&p.map);
+    }
+}
+
 void GridSlamProcessor::markMapsStale() {
     for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it)
         if (it->map.residency()) it->map.residency()->stale = true;
@@ -282,6 +291,7 @@ void GridSlamProcessor::scanMatch(const double* plainReading) {
     for (size_t i = 0; i < n; i++) m_logwBuf[i] = m_particles[i].weight;
     m_weights.resize(n);
     m_device->configure(m_matcher);
+    flushHostEdits();
     m_device->check(gm_scanmatch_weights(m_device->h, plainReading, m_poseBuf.data(), m_minimumScore, m_logwBuf.data(), m_obsSigmaGain,
                                          m_rowBuf.data(), m_weights.data(), &m_neff),
                     "gm_scanmatch_weights");
@@ -323,6 +333,7 @@ void GridSlamProcessor::registerAll(const double* plainReading, const unsigned i
         m_poseBuf[3 * j] = q.x; m_poseBuf[3 * j + 1] = q.y; m_poseBuf[3 * j + 2] = q.theta;
     }
     m_device->configure(m_matcher);
+    flushHostEdits();
     if (m_world > 1)  // parents are global indexes; maps of parents on other ranks migrate here first
         m_device->check(gm_dist_register(m_device->h, plainReading, m_poseBuf.data(), parents), "gm_dist_register");
     else
@@ -332,6 +343,7 @@ void GridSlamProcessor::registerAll(const double* plainReading, const unsigned i
 
 // particle copy by patch reference alone: the scan is already in the parents' maps (early registration)
 void GridSlamProcessor::copyAll(const unsigned int* parents) {
+    flushHostEdits();
     if (m_world > 1) m_device->check(gm_dist_copy_particles(m_device->h, parents), "gm_dist_copy_particles");
     else m_device->check(gm_copy_particles(m_device->h, parents), "gm_copy_particles");
     markMapsStale();

@@ -66,7 +66,9 @@ def main():
             assert sharded.last_resampled() == bool(g.resampled[i])
             if g.resampled[i]:
                 assert np.array_equal(sharded.indexes(), g.ridx[i])
-                migrated += sharded.stats()["migrated_particles"]
+                st_ = sharded.stats()
+                migrated += st_["migrated_particles"]
+                print("dist_check %s rank %d scan %d: %d parents imported, pool in use %d" % (case, rank, i, st_["migrated_particles"], st_["pool_in_use"]), flush=True)
             if i in dig:
                 want = digest_rows(g.digests[dig.index(i)])[lo:hi]
                 assert np.array_equal(sharded.map_digests()[:, :5], want[:, :5]), (case, i, "map digests of the local slice")

@@ -34,6 +34,6 @@ def test_sharded_filter_two_ranks():
 def test_pool_exhaustion_during_migration_is_loud():
     """a pool too small for the imported parents: the run must die with the pool message on every rank, not continue with holes"""
     build_host()
-    res = run_dist_check(29612, {"GM_B200_POOL_PATCHES": "1700", "GM_B200_DIST_TIMEOUT_S": "30", "GM_DIST_CASES": "room181_n30"}, timeout=300)
+    res = run_dist_check(29612, {"GM_B200_POOL_PATCHES": "700", "GM_B200_DIST_TIMEOUT_S": "30", "GM_DIST_CASES": "room181_n30"}, timeout=300)
     assert res.returncode != 0
     assert "exhausted" in res.stderr, res.stderr[-3000:]

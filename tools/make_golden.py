@@ -200,8 +200,10 @@ def main():
     if "c3" in sys.argv[1:]:
         # BASELINE.json configs[2] (SURVEY.md 8d "a >= 50-scan prefix of C3"): 512 particles x 1081 beams, the benchmark's log and
         # parameters (ROS-default motion noise: the filter resamples); ~12 minutes of the reference on one core
+        # lobsGain: the weights are softmax(l / (ogain * N)) (gridslamprocessor.hxx:93), so gfs-carmen's ogain 3, tuned for 30
+        # particles, never lets Neff drop at 512; the benchmark keeps the 30-particle configuration's effective gain, ogain * N = 90
         run_long("room1081_c3", scans=56, particles=512, laser="UTM30", log_seed=1, every=8, maxrange=30.0, maxUrange=29.0,
-                 srr=0.1, srt=0.2, str=0.1, stt=0.2); return
+                 srr=0.1, srt=0.2, str=0.1, stt=0.2, ogain=90.0 / 512); return
     if "n32" in sys.argv[1:]:
         # 32 particles (divisible by 2, 4 and 8 ranks) for the sharded-parity prelude of bench.py
         run_long("room181_n32", scans=40, particles=32, laser="LMS200", log_seed=1, every=5, step=0.5, linearUpdate=0.4, angularUpdate=0.2,
