@@ -11,6 +11,8 @@
 //
 // Nothing here is copied from the reference; it only *calls* it.
 #include <chrono>
+#include <csetjmp>
+#include <csignal>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -262,6 +264,61 @@ class TraceProcessor : public GridSlamProcessor {
     int count() const { return m_count; }
 };
 
+// integrateScanSequence (gridslamprocessor_tree.cpp:149-224): a second, small filter replays the newest nodes of the first
+// filter's best trajectory.  The reference version moves every particle along the path (pose composed relative to the path, the
+// node's weight difference added), calls computeActiveArea -- which may resize the particle maps -- and grows one TNode per
+// particle and step; it registers nothing.  With assertions enabled the reference then ABORTS while freeing its private copy
+// of the path (the copied child counts are never released, assert(!childs) in ~TNode): all of its work is done by then, so
+// the abort is caught and the state dumped.  Record per particle: pose, weight, weightSum, trajectory depth, leaf pose, map geometry.
+sigjmp_buf g_abort_jmp;
+void onAbort(int) { siglongjmp(g_abort_jmp, 1); }
+
+void dumpIntegrate(Writer& w, const SensorMap& sensorMap, const TraceProcessor& src, const Opts& o, std::ostream& info) {
+    if (!w.f) return;
+    typedef GridSlamProcessor::TNode TNode;
+    const GridSlamProcessor::Particle& best = src.getParticles()[src.getBestParticleIndex()];
+    std::vector<const TNode*> path;  // newest first, nodes that carry a reading only (the root has none)
+    for (const TNode* n = best.node; n && path.size() < 6; n = n->parent)
+        if (n->reading) path.push_back(n);
+    TNode* leaf = 0;
+    for (size_t k = path.size(); k-- > 0;) {
+        TNode* c = new TNode(path[k]->pose, 0.25 * (double)(path.size() - k), leaf, 0);
+        c->reading = path[k]->reading;
+        leaf = c;
+    }
+    TraceProcessor g2(info);
+    g2.setSensorMap(sensorMap);
+    g2.setMatchingParameters(o.maxurange, o.maxrange, o.sigma, o.kernel, o.lstep, o.astep, o.iterations, o.lsigma, o.ogain, o.lskip);
+    g2.setMotionModelParameters(o.srr, o.srt, o.str, o.stt);
+    g2.setUpdateDistances(o.linear_update, o.angular_update, o.resample_thr);
+    g2.setgenerateMap(o.generate_map);
+    // a map far too small for the scans: computeActiveArea has to resize it
+    const OrientedPoint start(path.empty() ? 0. : path.back()->pose.x + 0.3, path.empty() ? 0. : path.back()->pose.y - 0.2, 0.4);
+    g2.GridSlamProcessor::init(3, start.x - 1.6, start.y - 1.6, start.x + 1.6, start.y + 1.6, o.delta, start);
+    if (leaf) {
+        struct sigaction sa, old;
+        memset(&sa, 0, sizeof sa);
+        sa.sa_handler = onAbort;
+        sigemptyset(&sa.sa_mask);
+        sigaction(SIGABRT, &sa, &old);
+        if (sigsetjmp(g_abort_jmp, 1) == 0) g2.integrateScanSequence(leaf);
+        sigaction(SIGABRT, &old, 0);
+    }
+    std::vector<double> rows;
+    for (size_t i = 0; i < g2.getParticles().size(); i++) {
+        const GridSlamProcessor::Particle& p = g2.getParticles()[i];
+        double depth = 0;
+        for (const TNode* n = p.node; n; n = n->parent) depth += 1;
+        const IntPoint c = p.map.world2map(p.map.getCenter());
+        const double row[16] = {p.pose.x, p.pose.y, p.pose.theta, p.weight, p.weightSum, depth, p.node ? p.node->pose.x : 0., p.node ? p.node->pose.y : 0.,
+                                p.node ? p.node->pose.theta : 0., (double)c.x, (double)c.y, (double)p.map.getMapSizeX(), (double)p.map.getMapSizeY(),
+                                (double)p.map.storage().getXSize(), (double)p.map.storage().getYSize(), (double)path.size()};
+        rows.insert(rows.end(), row, row + 16);
+    }
+    w.vec("ISEQ", rows);
+    delete leaf;  // our own path: ~TNode frees the ancestors
+}
+
 // ScanMatcherProcessor (scanmatcher/scanmatcherprocessor.cpp): incremental scan matching of the log's first readings against one
 // map, no particle filter.  Record: pose after every reading, then digest + geometry of its map.
 void dumpScanMatcherProcessor(Writer& w, const SensorMap& sensorMap, const std::string& log, const Opts& o, int max_readings) {
@@ -424,6 +481,7 @@ int main(int argc, char** argv) {
             const double row[8] = {(double)slog.size(), bx0, by0, bx1, by1, start.x, start.y, start.theta};
             gsp.w.rec("BBOX", row, sizeof row);
         }
+        dumpIntegrate(gsp.w, sensorMap, gsp, o, *info);
         gsp.w.rec("DONE", nullptr, 0);
         fclose(gsp.w.f);
     }

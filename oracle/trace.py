@@ -89,6 +89,8 @@ def read_trace(path):
             final["smp_geometry"] = np.frombuffer(p, dtype="<i4").copy()
         elif tag == "BBOX":  # SensorLog: readings, boundingBox xmin ymin xmax ymax, first range pose
             final["sensorlog_bbox"] = np.frombuffer(p, dtype="<f8").copy()
+        elif tag == "ISEQ":  # integrateScanSequence on a second filter: pose xyz, weight, weightSum, depth, leaf pose xyz, map geometry (6), path nodes
+            final["integrate"] = np.frombuffer(p, dtype="<f8").reshape(-1, 16).copy()
         elif tag == "DONE":
             pass
         else:

@@ -667,20 +667,53 @@ GridSlamProcessor::TNodeVector GridSlamProcessor::getTrajectories() const {
     return leaves;
 }
 
-// replay a stored trajectory (root first) into every particle map (reference: gridslamprocessor_tree.cpp:149-224)
+// move every particle along a stored trajectory (reference: gridslamprocessor_tree.cpp:149-224), oldest node first: the pose
+// is composed relative to the path, the node's weight difference is added to weight and weightSum, computeActiveArea runs for
+// the node's scan (it may resize the maps; nothing is registered) and every particle's own trajectory grows by one node.
+// The reference's quirks are kept: the rotation uses the NEW path heading (oldPose is overwritten before it is used), and
+// the weight difference is always taken against the FIRST node (oldWeight is never advanced).  Every node needs a reading,
+// like in the reference (it dereferences aux->reading); m_count and the tree weights are left alone.
+// (The reference then frees its private copy of the path with `delete` in a loop, which trips assert(!childs) for any path
+// longer than one node; there is no private copy here.)
 void GridSlamProcessor::integrateScanSequence(TNode* node) {
-    std::vector<TNode*> order;
-    for (TNode* n = node; n; n = n->parent) order.push_back(n);
+    std::vector<const TNode*> order;
+    for (const TNode* n = node; n; n = n->parent) order.push_back(n);
+    if (m_infoStream) m_infoStream << "Restoring State Nodes=" << (double)order.size() << endl;
+    bool first = true;
+    double oldWeight = 0;
+    OrientedPoint oldPose;
+    const size_t nl = m_localCount;
     for (size_t k = order.size(); k-- > 0;) {
-        TNode* n = order[k];
-        if (!n->reading) continue;
-        assert(n->reading->size() == m_beams);
-        for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it) it->pose = n->pose;
-        const std::vector<double> plain(n->reading->begin(), n->reading->end());
-        registerAll(plain.data(), 0);
-        m_count++;
+        const TNode* aux = order[k];
+        if (first) { oldPose = aux->pose; first = false; oldWeight = aux->weight; }
+        const OrientedPoint dp = aux->pose - oldPose;
+        const double dw = aux->weight - oldWeight;
+        oldPose = aux->pose;
+        if (!aux->reading) b200::fatal("GridSlamProcessor::integrateScanSequence: a node of the path has no reading");
+        assert(aux->reading->size() == m_beams);
+        const std::vector<double> plain(aux->reading->begin(), aux->reading->end());
+        for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it) {
+            const double s = sin(oldPose.theta - it->pose.theta), c = cos(oldPose.theta - it->pose.theta);
+            it->pose.x += c * dp.x - s * dp.y;
+            it->pose.y += s * dp.x + c * dp.y;
+            it->pose.theta += dp.theta;
+            it->pose.theta = atan2(sin(it->pose.theta), cos(it->pose.theta));
+            it->weight += dw;
+            it->weightSum += dw;
+            it->node = new TNode(it->pose, 0.0, it->node);
+        }
+        // computeActiveArea for every (local) particle in one call: the bounding box of the scan and the Map::resize it triggers
+        m_poseBuf.resize(3 * nl);
+        for (size_t j = 0; j < nl; j++) {
+            const OrientedPoint& q = m_particles[m_firstLocal + j].pose;
+            m_poseBuf[3 * j] = q.x; m_poseBuf[3 * j + 1] = q.y; m_poseBuf[3 * j + 2] = q.theta;
+        }
+        m_device->configure(m_matcher);
+        flushHostEdits();
+        m_device->check(gm_compute_active_area(m_device->h, plain.data(), m_poseBuf.data()), "gm_compute_active_area");
+        markMapsStale();
     }
-    updateTreeWeights(false);
+    m_weightsChanged = true;
 }
 
 // ------------------------------------------------------------------------------------------ B200 additions

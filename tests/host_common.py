@@ -155,6 +155,13 @@ def check_trace(case, g, tr, exact=False):
     assert np.abs(fin["smp_poses"] - g.smp_poses).max() <= ptol, "%s: ScanMatcherProcessor poses" % case
     assert np.array_equal(digest_rows(fin["smp_digest"])[:, :5], digest_rows(g.smp_digest)[:, :5]), "%s: ScanMatcherProcessor map" % case
     assert np.array_equal(fin["smp_geometry"], g.smp_geometry), "%s: ScanMatcherProcessor map geometry" % case
+    # integrateScanSequence (gridslamprocessor_tree.cpp:149-224) on a second, small filter: poses, weights, trajectory depth, the
+    # leaves' poses and the (resized) map geometry of every particle
+    got, want = fin["integrate"], g.integrate
+    assert got.shape == want.shape and want[0, 15] >= 2, "%s: integrateScanSequence record" % case
+    assert np.array_equal(got[:, 5], want[:, 5]) and np.array_equal(got[:, 9:], want[:, 9:]), "%s: integrateScanSequence depth / map geometry" % case
+    np.testing.assert_allclose(got[:, :5], want[:, :5], rtol=0, atol=0 if exact else 1e-12, err_msg="%s: integrateScanSequence poses / weights" % case)
+    np.testing.assert_allclose(got[:, 6:9], want[:, 6:9], rtol=0, atol=0 if exact else 1e-12, err_msg="%s: integrateScanSequence leaf poses" % case)
     # the .gfs trace (gridslamprocessor.cpp:454-475, 570-606; gridslamprocessor.hxx:159-167): the same records in the same order;
     # with the reference's arithmetic underneath (mock) the same bytes
     tags = " ".join(l.split(b" ", 1)[0].decode() for l in tr["gfs"].splitlines() if l)
