@@ -187,6 +187,11 @@ int gm_download_map(gm_ctx* ctx, uint32_t particle, gm_map_info* info, int32_t* 
  * (gm_map_info: patches_x * 32, patches_y * 32). */
 int gm_export_occupancy(gm_ctx* ctx, uint32_t particle, double occ_thresh, int8_t* out, uint32_t width, uint32_t height);
 int gm_map_digest(gm_ctx* ctx, uint32_t first, uint32_t count, gm_digest* out /*count*/);
+/* replaces: the MAP_CONSISTENCY_CHECK block of GridSlamProcessor::processScan, gridfastslam/gridslamprocessor.cpp:82-143 (every
+ * patch's share count against the number of particle maps that point at it): the references are recounted from the patch
+ * directories of the live particles and compared with the pool's reference counts, and "referenced" with "off the free stack".
+ * GM_ERR_INTERNAL on any difference.  mismatches_out / referenced_out may be NULL. */
+int gm_check_refcounts(gm_ctx* ctx, uint64_t* mismatches_out, uint64_t* referenced_out);
 
 /* ---- multi-GPU (one process and one gm_ctx per GPU of one node; peer memory over NVLink / NVSwitch).  Rank r owns the global
  * particles [r*n, (r+1)*n), n = gm_particles(ctx); the host state (poses, weights, trajectory tree, drand48 stream) is

@@ -45,6 +45,16 @@ def build_cuda(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines):
+    """an experimental build of the CUDA library with extra -D flags -> variants/libgm_b200.<name>.so (for A/B runs on the GPU box:
+    copy it over libgm_b200.so)"""
+    srcs = [os.path.join(CSRC, f) for f in ("gm_kernels.cu", "gm_api.cu", "gm_dist.cu")]
+    out = os.path.join(HERE, "variants", "libgm_b200.%s.so" % name)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.check_call([nvcc_path()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out] + srcs + ["-ldl"])
+    return out
+
+
 def build_host(force=False):
     """C++ host layer (GMapping::GridSlamProcessor over the C ABI) + log-driven CLI, if present."""
     mk = os.path.join(HOST, "Makefile")
@@ -60,5 +70,9 @@ def build_all(force=False, verbose=False):
 
 if __name__ == "__main__":
     import sys
-    build_all(force="-f" in sys.argv, verbose="-v" in sys.argv)
-    print(LIB)
+    if "--variant" in sys.argv:  # python build.py --variant r96 GM_SM_REGS=96
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        build_all(force="-f" in sys.argv, verbose="-v" in sys.argv)
+        print(LIB)

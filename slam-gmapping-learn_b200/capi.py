@@ -14,7 +14,7 @@ EXPORTS = ["gm_create", "gm_destroy", "gm_last_error", "gm_set_laser", "gm_set_m
            "gm_init_particles", "gm_score", "gm_likelihood_and_score", "gm_scanmatch", "gm_normalize_neff",
            "gm_resample_indexes", "gm_register", "gm_map_info_get", "gm_download_map", "gm_map_digest",
            "gm_get_stats", "gm_particles", "gm_optimize", "gm_compute_active_area", "gm_upload_map", "gm_export_occupancy", "gm_clone", "gm_set_async_register", "gm_synchronize",
-           "gm_dist_unique_id", "gm_dist_init", "gm_dist_register", "gm_dist_copy_particles", "gm_dist_plan", "gm_scanmatch_weights"]
+           "gm_dist_unique_id", "gm_dist_init", "gm_dist_register", "gm_dist_copy_particles", "gm_dist_plan", "gm_scanmatch_weights", "gm_check_refcounts"]
 
 
 class GmError(RuntimeError):
@@ -101,6 +101,8 @@ def load_library(path=LIB_PATH):
     L.gm_optimize.argtypes = [vp, C.c_uint32, up, dp, dp, dp, dp]
     L.gm_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.gm_particles.restype = C.c_uint32; L.gm_particles.argtypes = [vp]
+    L.gm_scanmatch_weights.argtypes = [vp, dp, dp, C.c_double, dp, C.c_double, dp, dp, dp]
+    L.gm_check_refcounts.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     _lib = L
     return L
 
@@ -198,6 +200,19 @@ class GmContext:
         c = np.zeros(self.n, dtype=np.uint32); ev = np.zeros(self.n, dtype=np.uint32)
         self._ck(self.L.gm_scanmatch(self.h, _dp(r), _dp(p), float(minimum_score), _dp(sc), _dp(s), _dp(l), _up(c), _up(ev)))
         return p, sc, s, l, c, ev
+
+    def scanmatch_weights(self, ranges, poses, log_weights, minimum_score=0.0, obs_sigma_gain=1.0):
+        """the fused call: -> (rows [N, 5] = x y theta score l, weights [N], neff)"""
+        r = self._ranges(ranges); p = _f64(poses).reshape(self.n, 3); lw = _f64(log_weights)
+        rows = np.zeros((len(lw), 5)); w = np.zeros(len(lw)); ne = C.c_double()
+        self._ck(self.L.gm_scanmatch_weights(self.h, _dp(r), _dp(p), float(minimum_score), _dp(lw), float(obs_sigma_gain), _dp(rows), _dp(w), C.byref(ne)))
+        return rows, w, ne.value
+
+    def check_refcounts(self):
+        """MAP_CONSISTENCY_CHECK: raises when a patch's reference count differs from the directories; -> referenced patches"""
+        bad = C.c_uint64(); used = C.c_uint64()
+        self._ck(self.L.gm_check_refcounts(self.h, C.byref(bad), C.byref(used)))
+        return used.value
 
     def normalize(self, log_weights, obs_sigma_gain=1.0):
         lw = _f64(log_weights); w = np.zeros_like(lw); ne = C.c_double()

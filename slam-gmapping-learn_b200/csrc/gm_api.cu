@@ -39,6 +39,7 @@ int gm_create(gm_ctx** out, const gm_config* cfg) {
     if (prop.major < 10) return fail(nullptr, GM_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
 
     gm_ctx* c = new gm_ctx();
+    c->cluster_below = (uint32_t)prop.multiProcessorCount * 4u;
     c->device = cfg->device;
     c->max_particles = cfg->max_particles;
     c->threads = cfg->block_threads ? cfg->block_threads : 256;
@@ -225,7 +226,7 @@ static int run_eval(gm_ctx* ctx, int mode, uint32_t count, const uint32_t* parti
     a.query = mode; a.particle_idx = ctx->d_qidx; a.zero_patch = ctx->pool.cap;
     derive_params(a.P);
     if (int r = prepare_scanmatch(ctx)) return r;
-    launch_scanmatch(a, count, ctx->st);
+    launch_scanmatch(a, count, 1, ctx->st);
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_scanmatch (query)")) return r;
     if (s_out) CK(cudaMemcpyAsync(s_out, ctx->d_qs, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->st));
@@ -270,7 +271,7 @@ int gm_scanmatch(gm_ctx* ctx, const double* ranges, double* poses_inout, double 
     a.valid_score_beams = count_score_beams(ctx, ranges);
     if (int r = prepare_scanmatch(ctx)) return r;
     CK(cudaEventRecord(ctx->ev0, ctx->st));
-    launch_scanmatch(a, n, ctx->st);
+    launch_scanmatch(a, n, scanmatch_cluster(ctx), ctx->st);
     CK(cudaEventRecord(ctx->ev1, ctx->st));
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_scanmatch")) return r;
@@ -323,7 +324,7 @@ int gm_scanmatch_weights(gm_ctx* ctx, const double* ranges, const double* poses_
     a.valid_score_beams = count_score_beams(ctx, ranges);
     if (int r = prepare_scanmatch(ctx)) return r;
     CK(cudaEventRecord(ctx->ev0, ctx->st));
-    launch_scanmatch(a, n, ctx->st);
+    launch_scanmatch(a, n, scanmatch_cluster(ctx), ctx->st);
     CK(cudaEventRecord(ctx->ev1, ctx->st));
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_scanmatch")) return r;
@@ -715,6 +716,27 @@ int gm_map_digest(gm_ctx* ctx, uint32_t first, uint32_t count, gm_digest* out) {
     unsigned long long bad = 0;
     for (uint32_t i = 0; i < count; i++) { memcpy(&out[i], &words[(size_t)i * 7], sizeof(gm_digest)); bad += words[(size_t)i * 7 + 6]; }
     if (bad) return fail(ctx, GM_ERR_INTERNAL, "gm_map_digest: %llu occupancy-bitmap rows disagree with their cells", bad);
+    return GM_OK;
+}
+
+int gm_check_refcounts(gm_ctx* ctx, uint64_t* mismatches_out, uint64_t* referenced_out) {
+    if (int r = ready(ctx, true)) return r;
+    unsigned long long* out = ctx->d_digest;  // scratch: three words
+    CK(cudaMemsetAsync(out, 0, 3 * sizeof(unsigned long long), ctx->st));
+    launch_recount(ctx->geom, ctx->dir, ctx->dir_cap, ctx->pool, ctx->refcnt_new, out, ctx->n, ctx->st);  // refcnt_new is all zero between remaps
+    ctx->stats.launches += 2;
+    if (int r = check_launch(ctx, "k_recount")) return r;
+    unsigned long long h[3] = {0, 0, 0};
+    int top = 0;
+    CK(cudaMemcpyAsync(h, out, sizeof h, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(&top, ctx->pool.free_top, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    if (mismatches_out) *mismatches_out = h[0] + h[2];
+    if (referenced_out) *referenced_out = h[1];
+    if (h[0] || h[2]) return fail(ctx, GM_ERR_INTERNAL, "gm_check_refcounts: %llu patches whose reference count differs from the directories, %llu dangling references", h[0], h[2]);
+    // every patch is either referenced or on the free stack
+    if ((unsigned long long)(ctx->pool.cap - top) != h[1])
+        return fail(ctx, GM_ERR_INTERNAL, "gm_check_refcounts: %llu patches are referenced but %d are off the free stack", h[1], ctx->pool.cap - top);
     return GM_OK;
 }
 

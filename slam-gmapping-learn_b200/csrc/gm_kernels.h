@@ -64,9 +64,9 @@ struct DigestArgs {
     unsigned first; unsigned long long* out;  // 7 words per particle: the six of gm_digest + mismatching occupancy-bitmap rows
 };
 
-size_t scanmatch_smem_bytes(unsigned nbeams);
-cudaError_t scanmatch_prepare(size_t smem);
-void launch_scanmatch(const ScanMatchArgs& a, unsigned n, cudaStream_t st);
+size_t scanmatch_smem_bytes(unsigned nbeams, int cluster);
+cudaError_t scanmatch_prepare(unsigned nbeams);
+void launch_scanmatch(const ScanMatchArgs& a, unsigned n, int cluster, cudaStream_t st);
 void launch_bounds(const BoundsArgs& a, unsigned n, unsigned threads, cudaStream_t st);
 void launch_relayout(const RelayoutArgs& a, unsigned n, cudaStream_t st);
 void launch_relayout_commit(const RelayoutArgs& a, unsigned n, cudaStream_t st);
@@ -77,6 +77,7 @@ void launch_remap(const RemapArgs& a, unsigned n, cudaStream_t st);
 void launch_sweep(const SweepArgs& a, cudaStream_t st);
 void launch_merge_free(const Pool& p, cudaStream_t st);
 void launch_pool_init(const Pool& p, cudaStream_t st);
+void launch_recount(const Geom* geom, const int* dir, int dir_cap, const Pool& pool, int* recount, unsigned long long* out, unsigned n, cudaStream_t st);
 void launch_fill_int(int* p, size_t n, int v, cudaStream_t st);
 void launch_fill_geom(Geom* g, unsigned n, Geom v, cudaStream_t st);
 void launch_normalize(const double* logw, const double* rows, unsigned n, double gain, double* w, double* neff, cudaStream_t st);

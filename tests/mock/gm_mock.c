@@ -344,6 +344,17 @@ int gm_map_digest(gm_ctx* c, uint32_t first, uint32_t count, gm_digest* out) {
     return GM_OK;
 }
 
+/* the mock's maps own their patches outright (orc_map_clone copies): there are no shared patches to miscount */
+int gm_check_refcounts(gm_ctx* c, uint64_t* mismatches_out, uint64_t* referenced_out) {
+    int r = ready(c);
+    if (r) return r;
+    uint64_t used = 0;
+    for (uint32_t i = 0; i < c->n; i++) used += (uint64_t)orc_map_patch_count(c->maps[i]);
+    if (mismatches_out) *mismatches_out = 0;
+    if (referenced_out) *referenced_out = used;
+    return GM_OK;
+}
+
 int gm_clone(gm_ctx* src, gm_ctx** out) {
     if (!src || !out) return GM_ERR_ARG;
     if (src->dist) return fail(src, GM_ERR_ARG, "gm_clone: a sharded context cannot be cloned");

@@ -11,18 +11,19 @@ pytestmark = pytest.mark.gpu
 SCANS = 4
 
 
-# 4096: BASELINE.json's shape; 512: one GPU's share of it on eight (and C3)
-@pytest.mark.parametrize("N", [4096, 512])
-def test_c4_shape_conservation_determinism_and_subset_parity(N):
+# 4096: BASELINE.json's shape; 512: one GPU's share of it on eight (and C3); 512 at 0.025 m: the grid of BASELINE.json's fifth
+# configuration.  `census` particles are followed by the oracle through every scan: the decision census (below)
+@pytest.mark.parametrize("N,delta,census", [(4096, 0.05, 256), (512, 0.05, 64), (512, 0.025, 64)])
+def test_c4_shape_conservation_determinism_and_subset_parity(N, delta, census):
     gm = importlib.import_module("slam-gmapping-learn_b200")
     synth = importlib.import_module("slam-gmapping-learn_b200.synth")
     log = synth.make_log("room", synth.UTM30, scans=SCANS + 1, step=0.25, seed=4)
-    ctx = gm.GmContext(N, pool_patches=N * 200)
-    ctx.set_laser(log.laser.angles()); ctx.set_matching(urange=29., range_=30.); ctx.init_particles(N)
+    ctx = gm.GmContext(N, pool_patches=N * (200 if delta == 0.05 else 520))
+    ctx.set_laser(log.laser.angles()); ctx.set_matching(urange=29., range_=30.); ctx.init_particles(N, delta=delta)
     m = orc.make_matcher(log.laser.angles(), urange=29., range_=30.)
     rng = np.random.default_rng(8)
-    subset = np.sort(rng.choice(N, size=6, replace=False))
-    maps = {int(j): orc.Map() for j in subset}
+    subset = np.sort(rng.choice(N // 2, size=census, replace=False))
+    maps = {int(j): orc.Map(delta=delta) for j in subset}
     prev = ctx.digests()
     for k in range(SCANS):
         poses = log.odom[k][None, :] + rng.normal(0, [0.02, 0.02, 0.01], size=(N, 3))
@@ -59,10 +60,20 @@ def test_c4_shape_conservation_determinism_and_subset_parity(N):
     # candidates k_scanmatch proves to be losers without evaluating them (the pose a winning move came from)
     be, ref_total = ctx.stats()["beam_evals"], int(ev.sum()) * 1081 + N * 1081
     assert 0.85 * ref_total < be <= ref_total and (ref_total - be) % 1081 == 0
+    # decision census: the kernel's score sums have a fixed shape of their own (per beam group, then over the groups), not the
+    # reference's sequential order, so a strict `>` of the hill-climb could in principle flip on a last-place difference.
+    # Every particle of the census must take the reference's decisions: the same number of score() evaluations, the same pose
+    calls = []
     for j in subset:
+        k0 = m.score_calls
         so, po = orc.optimize(m, maps[int(j)], init[j], r)
+        calls.append(m.score_calls - k0)
         s1, l1, c1 = orc.likelihood_and_score(m, maps[int(j)], po, r)
         assert np.abs(poses[j] - po).max() < 1e-9 and abs(l[j] - l1) <= 1e-9 * abs(l1) and c[j] == c1
+        assert abs(score[j] - so) <= 1e-9 * so
+    assert np.array_equal(ev[subset], np.array(calls, dtype=np.uint32)), "a hill-climb decision differs from the reference's"
+    print("decision census: %d of %d particles (%d x 1081 beams, delta %g) climb exactly like the oracle, %d score() evaluations"
+          % (len(subset), len(subset), N, delta, int(np.sum(calls))))
     # weights and resampling at full size against the oracle (sequential sums kept)
     w, neff = ctx.normalize(l, 3.0)
     wo, neffo = orc.normalize(l, 3.0)

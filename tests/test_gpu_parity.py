@@ -82,6 +82,9 @@ def test_teacher_forced_trace(case):
                 assert np.array_equal(idx, g.ridx[i]), "%s[%d] resample indexes" % (case, i)
                 assert emitted == g.N
                 ctx.register(ranges, g.state[i][:, :3], idx)
+                # the reference's MAP_CONSISTENCY_CHECK (gridslamprocessor.cpp:82-143) after every particle copy: reference counts
+                # recounted from the directories, "referenced" against "off the free stack"
+                assert ctx.check_refcounts() == ctx.stats()["pool_in_use"]
                 n_res += 1
             else:
                 np.testing.assert_allclose(w, g.weights[i], rtol=1e-12, atol=0)
@@ -96,6 +99,7 @@ def test_teacher_forced_trace(case):
     assert n_res == int(g.resampled.sum())
     st = ctx.stats()
     assert st["launches"] > 0 and st["pool_in_use"] > 0
+    assert ctx.check_refcounts() == st["pool_in_use"]
     ctx.close()
 
 
@@ -234,6 +238,28 @@ def test_copy_on_write_refcounts():
         mp = maps[2].clone(); orc.register(m, mp, p2[j], r); want.append(mp.digest())
     assert all(int(d["hash_counts"][j]) == want[j].hash_counts for j in range(6))
     assert in_use0 > 0
+    assert ctx.check_refcounts() == st["pool_in_use"]  # shared patches are counted once, with the right number of owners
+    ctx.close()
+
+
+def test_fused_scanmatch_weights_equals_the_separate_calls():
+    """gm_scanmatch_weights (one stream-ordered sequence, one synchronisation) against gm_scanmatch followed by the host's
+    `weight += l` and gm_normalize_neff: the same bits -- poses, scores, log-likelihoods, weights, Neff"""
+    log, m, ctx, maps, poses, rng = _random_world(21, beams=181, particles=7, scans=4)
+    r = log.ranges[3]
+    init = poses + rng.normal(0, [0.03, 0.03, 0.01], size=poses.shape)
+    logw = rng.normal(-40.0, 25.0, size=7)
+    p1, sc, s, l, c, ev = ctx.scanmatch(r, init, 0.0)
+    w1, neff1 = ctx.normalize(logw + l, 3.0)
+    rows, w2, neff2 = ctx.scanmatch_weights(r, init, logw, 0.0, 3.0)
+    assert np.array_equal(rows[:, :3], p1) and np.array_equal(rows[:, 3], sc) and np.array_equal(rows[:, 4], l)
+    assert np.array_equal(w1, w2) and neff1 == neff2
+    # and against the oracle, like everything else
+    for j in range(7):
+        so, po = orc.optimize(m, maps[j], init[j], r)
+        assert np.abs(rows[j, :3] - po).max() < 1e-9 and abs(rows[j, 3] - so) <= 1e-9 * so
+    wo, neffo = orc.normalize(logw + l, 3.0)
+    np.testing.assert_allclose(w2, wo, rtol=1e-13, atol=0)
     ctx.close()
 
 

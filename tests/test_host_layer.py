@@ -129,3 +129,19 @@ def test_lazy_tree_weights():
 @pytest.mark.gpu
 def test_thousand_scans_free_running():
     host_scenarios.scenario_long()
+
+
+@pytest.mark.gpu
+def test_c3_prefix_free_running():
+    """BASELINE.json configs[2] / SURVEY.md 8d's gate: 512 particles x 1081 beams, 56 scans of the benchmark's log with the
+    benchmark's parameters (the filter resamples), free running against the unmodified reference: decisions, indexes and the
+    final (n, visits) of every cell of every particle exact, Neff within 1e-6, poses within 1e-4, log-weights within 1e-3"""
+    worst_pose, worst_w, resamples = host_scenarios.scenario_c3()
+    assert resamples >= 1
+    print("C3 prefix: worst pose error %.3g, worst log-weight error %.3g, %d resamplings" % (worst_pose, worst_w, resamples))
+
+
+@pytest.mark.gpu
+def test_n32_fixture_single_gpu():
+    """the fixture bench.py's sharded-parity prelude follows on N > 1 GPUs, here on one"""
+    assert host_scenarios.scenario_n32()[2] >= 1
