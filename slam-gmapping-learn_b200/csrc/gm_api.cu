@@ -39,7 +39,6 @@ int gm_create(gm_ctx** out, const gm_config* cfg) {
     if (prop.major < 10) return fail(nullptr, GM_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
 
     gm_ctx* c = new gm_ctx();
-    c->cluster_below = (uint32_t)prop.multiProcessorCount * 4u;
     c->device = cfg->device;
     c->max_particles = cfg->max_particles;
     c->threads = cfg->block_threads ? cfg->block_threads : 256;
@@ -226,7 +225,7 @@ static int run_eval(gm_ctx* ctx, int mode, uint32_t count, const uint32_t* parti
     a.query = mode; a.particle_idx = ctx->d_qidx; a.zero_patch = ctx->pool.cap;
     derive_params(a.P);
     if (int r = prepare_scanmatch(ctx)) return r;
-    launch_scanmatch(a, count, 1, ctx->st);
+    launch_scanmatch(a, count, ctx->st);
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_scanmatch (query)")) return r;
     if (s_out) CK(cudaMemcpyAsync(s_out, ctx->d_qs, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->st));
@@ -271,7 +270,7 @@ int gm_scanmatch(gm_ctx* ctx, const double* ranges, double* poses_inout, double 
     a.valid_score_beams = count_score_beams(ctx, ranges);
     if (int r = prepare_scanmatch(ctx)) return r;
     CK(cudaEventRecord(ctx->ev0, ctx->st));
-    launch_scanmatch(a, n, scanmatch_cluster(ctx), ctx->st);
+    launch_scanmatch(a, n, ctx->st);
     CK(cudaEventRecord(ctx->ev1, ctx->st));
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_scanmatch")) return r;
@@ -324,7 +323,7 @@ int gm_scanmatch_weights(gm_ctx* ctx, const double* ranges, const double* poses_
     a.valid_score_beams = count_score_beams(ctx, ranges);
     if (int r = prepare_scanmatch(ctx)) return r;
     CK(cudaEventRecord(ctx->ev0, ctx->st));
-    launch_scanmatch(a, n, scanmatch_cluster(ctx), ctx->st);
+    launch_scanmatch(a, n, ctx->st);
     CK(cudaEventRecord(ctx->ev1, ctx->st));
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_scanmatch")) return r;

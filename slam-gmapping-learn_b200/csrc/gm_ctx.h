@@ -63,7 +63,6 @@ struct gm_ctx {
     double* d_rows = nullptr;
     unsigned* d_done = nullptr;
     unsigned char *h_in = nullptr, *h_out = nullptr; size_t h_in_bytes = 0, h_out_bytes = 0;
-    uint32_t cluster_below = 0;  // particle count up to which k_scanmatch runs as 2-CTA clusters (set from the SM count)
     unsigned dir_gen = 0;  // bumped whenever dir / dir_alt are re-allocated (peers re-open their IPC mappings)
     void (*fail_hook)(gm_ctx*) = nullptr;  // sharded contexts: tell the other ranks that this one failed (they stop waiting)
 };
@@ -159,15 +158,9 @@ inline void derive_params(DevParams& P) {
 }
 
 inline int prepare_scanmatch(gm_ctx* ctx) {
-    const size_t smem = scanmatch_smem_bytes(ctx->P.nbeams, 1);
-    if (smem != ctx->scanmatch_smem) { CK(scanmatch_prepare(ctx->P.nbeams)); ctx->scanmatch_smem = smem; }
+    const size_t smem = scanmatch_smem_bytes(ctx->P.nbeams);
+    if (smem != ctx->scanmatch_smem) { CK(scanmatch_prepare(smem)); ctx->scanmatch_smem = smem; }
     return GM_OK;
-}
-// CTAs per particle of the scanMatch launch: a 2-CTA cluster when the particles alone cannot fill the GPU (fewer than ~4 per SM),
-// where the duration is set by the longest hill-climbs and halving each one's latency pays; GM_B200_SCANMATCH_CLUSTER overrides
-inline int scanmatch_cluster(const gm_ctx* ctx) {
-    if (const char* e = getenv("GM_B200_SCANMATCH_CLUSTER")) return atoi(e) == 2 ? 2 : 1;
-    return ctx->n <= ctx->cluster_below ? 2 : 1;
 }
 
 inline int ready(gm_ctx* ctx, bool need_particles) {

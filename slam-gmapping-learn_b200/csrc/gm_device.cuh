@@ -26,6 +26,7 @@ constexpr int kPatchMag = 5;
 constexpr int kPatch = 32;
 constexpr int kPatchCells = 1024;
 constexpr int kLineCap = 20000;  // scanmatcher.cpp:55
+#define GM_MAXBEAMS_DEV 2048        // LASER_MAXBEAMS, scanmatcher.h:11 (== GM_MAXBEAMS of the C ABI)
 constexpr int kInvTable = 4096;  // exactly rounded 1./n for n < kInvTable (PointAccumulator::mean, smmap.h:24)
 constexpr int kMaxRanks = 16;   // GPUs of one node a filter can be sharded over
 constexpr int kExpTable = 128;   // 2^(j/128), stored behind the reciprocals (exp_neg in gm_kernels.cu)

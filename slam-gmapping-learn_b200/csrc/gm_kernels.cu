@@ -14,8 +14,6 @@
 #include <algorithm>
 #include <climits>
 
-#include <cooperative_groups.h>
-
 #include "gm_device.cuh"
 #include "gm_kernels.h"
 
@@ -104,20 +102,8 @@ __device__ __forceinline__ int ldg_if(const int* p, bool pred, int dflt) {
     return v;
 }
 
-// Work decomposition of a hill-climb round.  Beam b belongs to GROUP b % 144, and the score of a candidate pose is summed in a
-// fixed shape -- per group over its beams in ascending order, then over the 144 group sums (reduce_row) -- that does not depend
-// on how the groups are dealt to threads or CTAs.  One CTA per particle has 288 threads: 144 "quad" threads take one group
-// each and evaluate the FOUR translation candidates of a beam together (they share theta, hence the end-point offset, and
-// land within a cell or two of each other: one set of occupancy words and one load per cell mean serve all four), and 2 x 72
-// "turn" threads take two groups each for one of the two rotation candidates.  With a 2-CTA cluster per particle (few
-// particles per GPU: the tail of long climbs is latency bound) each CTA has 144 threads and takes half of the groups; the
-// group sums are exchanged through distributed shared memory and both CTAs take the same decisions from the same sums.
-constexpr int kSmGroups = 144;
-constexpr int kSmThreadsMax = 2 * kSmGroups;
-#ifndef GM_SM_REGS
-#define GM_SM_REGS 112
-#endif
-constexpr int kSmRegs = GM_SM_REGS;  // registers per thread of k_scanmatch: 112 x 288 threads = two CTAs per SM
+constexpr int kSmThreads = 288;
+constexpr int kSmGroups = kSmThreads / 6;  // 48 beam groups x 6 candidate poses: every thread works
 
 struct MatchCtx {
     // the particle's directory, read through a shared-memory slot at every use: kept in registers the compiler spends ten
@@ -151,9 +137,9 @@ template <bool DEF> __device__ __forceinline__ bool is_free(int n, int v, const 
 template <bool K1>
 // (fqx, fqy): the beam-independent free-cell index offset when it exists (see derive_params), else fqx == INT_MIN
 // (phx, phy): the beam end point lp + r * (c, s).  r, c and s themselves are only needed for the free point when its
-// cell offset is not a constant (fqx == INT_MIN): they are re-read then (`ranges`, and the beam's plain trig table entry at ent_s).
+// cell offset is not a constant (fqx == INT_MIN): they are re-read then (`ranges`, and the plain trig table at tab_s).
 __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M, double lpx, double lpy, double phx, double phy, unsigned b,
-                                           unsigned ent_s, const double* __restrict__ ranges, double free_off, int fqx, int fqy,
+                                           unsigned tab_s, const double* __restrict__ ranges, double free_off, int fqx, int fqy,
                                            double& bmx, double& bmy) {
     const Geom& g = M.g;
     int ihx, ihy;
@@ -225,7 +211,7 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
         else {
             const double r = __ldg(ranges + b);
             double c, s;
-            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c), "=d"(s) : "r"(ent_s));
+            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c), "=d"(s) : "r"(tab_s + b * 16u));
             const double pfx = (lpx + (r - free_off) * c) - phx, pfy = (lpy + (r - free_off) * s) - phy;
             ifx = cell_index(pfx - P.cx, P.delta, P.inv_delta) + g.sx2;
             ify = cell_index(pfy - P.cy, P.delta, P.inv_delta) + g.sy2;
@@ -290,7 +276,7 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
             if (!have_free) {
                 const double r = __ldg(ranges + b);
             double c, s;
-            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c), "=d"(s) : "r"(ent_s));
+            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c), "=d"(s) : "r"(tab_s + b * 16u));
             const double pfx = (lpx + (r - free_off) * c) - phx, pfy = (lpy + (r - free_off) * s) - phy;
                 ifx = cell_index(pfx - P.cx, P.delta, P.inv_delta) + g.sx2;
                 ify = cell_index(pfy - P.cy, P.delta, P.inv_delta) + g.sy2;
@@ -349,23 +335,22 @@ __device__ __forceinline__ bool beam_selected(const DevParams& P, unsigned b) {
 
 struct SmShared {
     // plan of the next evaluation step (thread 0 writes, everybody reads after a barrier)
-    double lx[6], ly[6];   // laser position of each candidate pose (all six of a round, also the one that is not evaluated)
+    double lx[6], ly[6];   // laser position of each candidate pose
     double fill_theta[3];  // theta for the trig tables listed in fill[]
     int fill[3];           // physical trig tables to recompute before evaluating (-1: none)
     int tab_of[3];         // physical table of: the current theta, theta + adelta, theta - adelta
     const int* dirp;       // directory of this CTA's particle
     int4 bbox;             // see MatchCtx::bbox_s
     int bb_lo_x, bb_lo_y, bb_hi_x, bb_hi_y;  // its reduction: patch coordinates
-    int ncand;             // poses to evaluate: 1, or the 6 moves of a round (one of them possibly left out, see plan_round)
+    int ncand;             // poses to evaluate: 1, or the 6 moves of a round, or 5 of them (see plan_round)
+    int cand[6];           // which moves
     int skip;              // the move left out (-1: none)
     int mode;              // 0 score(), 1 likelihoodAndScore()
     int done;
-    int buf;               // which half of part[] / cnt[] this step writes (a cluster peer may still read the other one)
-    // group sums, [buffer][row][group]: rows 0..5 = the six moves of a round; a single pose uses rows 0, 1 (score: the beams of a
-    // group alternate between two threads) and 2, 3 (log-likelihood)
-    double part[2][6][kSmGroups];
-    unsigned cnt[2][2][2];  // [buffer][cluster rank][matched beams, valid beams] of a likelihoodAndScore step
-    double red[6];          // the reduced rows
+    // reduction scratch
+    double part[kSmThreads];
+    double red[16], red_l[16];
+    unsigned red_c[16], red_v[16];
     // hill-climb state (thread 0 only; shared memory keeps it out of everybody's registers)
     double cur[3], init[3], key[3], currentScore, bestScore, adelta, ldelta;
     double prev[3];        // the pose the last winning move started from
@@ -386,20 +371,13 @@ __device__ __forceinline__ void candidate(const double* cur, int m, double ldelt
     }
 }
 
-// thread 0: make logical table `which` hold theta.  Any of the three physical tables that already holds it will do (after a
-// winning turn the old current theta is the new theta -+ adelta whenever (t + a) - a == t, which is almost always);
-// otherwise the slot is recomputed
+// thread 0: make logical table `which` hold theta (recompute only when its key differs)
 __device__ __forceinline__ void want_table(SmShared& S, int which, double theta, int kind, int& nfill) {
-    for (int o = which; o < 3; o++) {  // slots below `which` are already promised to this step
-        const int phys = S.tab_of[o];
-        if (S.key_ok[phys] && S.key[phys] == theta && S.key_kind[phys] == kind) {
-            S.tab_of[o] = S.tab_of[which]; S.tab_of[which] = phys;
-            return;
-        }
-    }
     const int phys = S.tab_of[which];
-    S.key[phys] = theta; S.key_ok[phys] = 1; S.key_kind[phys] = kind;
-    S.fill[nfill] = phys; S.fill_theta[nfill] = theta; S.fill_kind[nfill] = kind; nfill++;
+    if (!S.key_ok[phys] || S.key[phys] != theta || S.key_kind[phys] != kind) {
+        S.key[phys] = theta; S.key_ok[phys] = 1; S.key_kind[phys] = kind;
+        S.fill[nfill] = phys; S.fill_theta[nfill] = theta; S.fill_kind[nfill] = kind; nfill++;
+    }
 }
 
 // thread 0: plan one hill-climb round (scanmatcher.cpp:418-440).
@@ -418,154 +396,55 @@ __device__ __noinline__ void plan_round(const DevParams& P, SmShared& S, int kin
         if (back[0] == S.prev[0] && back[1] == S.prev[1] && back[2] == S.prev[2]) S.skip = S.last_move ^ 1;
     }
     int nfill = 0, nc = 0;
-    {   // the current theta first: a turn that won brought its table along (see the swap in the decision step)
-        double lx, ly, lt;
-        laser_pose(P, S.cur[0], S.cur[1], S.cur[2], lx, ly, lt);
-        want_table(S, 0, lt, kind, nfill);
-    }
+    double turn_theta[2] = {0., 0.};
     for (int m = 0; m < 6; m++) {
+        if (m == S.skip) continue;
         double cm[3], lx, ly, lt;
         candidate(S.cur, m, S.ldelta, S.adelta, cm);
         laser_pose(P, cm[0], cm[1], cm[2], lx, ly, lt);
         S.lx[m] = lx; S.ly[m] = ly;
-        if (m == S.skip) continue;
-        if (m >= 4) want_table(S, m - 3, lt, kind, nfill);
-        nc++;
+        if (m >= 4) turn_theta[m - 4] = lt;
+        S.cand[nc++] = m;
+    }
+    // the two tables beside the current one: after a winning turn the theta it came from is the new theta -+ adelta (bit for bit
+    // whenever (t + a) - a == t, i.e. almost always) and its table is still there -- in the other slot; swap rather than refill
+    {
+        const bool want1 = S.skip != 4, want2 = S.skip != 5;
+        auto holds = [&](int phys, double theta) { return S.key_ok[phys] && S.key[phys] == theta && S.key_kind[phys] == kind; };
+        const int a = S.tab_of[1], b = S.tab_of[2];
+        const bool a1 = want1 && holds(a, turn_theta[0]), b2 = want2 && holds(b, turn_theta[1]);
+        if (!a1 && !b2 && ((want1 && holds(b, turn_theta[0])) || (want2 && holds(a, turn_theta[1])))) { S.tab_of[1] = b; S.tab_of[2] = a; }
+        if (want1) want_table(S, 1, turn_theta[0], kind, nfill);
+        if (want2) want_table(S, 2, turn_theta[1], kind, nfill);
     }
     for (int j = nfill; j < 3; j++) S.fill[j] = -1;
     S.ncand = nc; S.mode = 0; S.phase = 1;
 }
 
-// sum of a row of group sums in a fixed shape: lane l adds groups l, l + 32, ... in ascending order, then the xor tree
-__device__ __forceinline__ double reduce_row(const double* row, int lane) {
-    double v = 0.;
-#pragma unroll
-    for (int j = 0; j < (kSmGroups + 31) / 32; j++) {
-        const int g = lane + 32 * j;
-        if (g < kSmGroups) v += row[g];
-    }
-    return warp_sum(v);
-}
-
-// The four translation candidates of a round for one beam, evaluated together (score(), kernelSize 1, default threshold, beam-
-// independent free-cell offset).  off = r * (cos, sin)(theta + angle): the candidates' end points are (lx[m] + off.x, ly[m] +
-// off.y) with lx[2] == lx[3] and ly[0] == ly[1] bit for bit (same theta, same laser offset), i.e. three distinct x and three
-// distinct y.  Their 3x3 windows lie in a box of at most 6 x 8 cells: its occupancy comes from one word (two across a patch
-// edge in y) per box row, every occupied cell of the box is loaded ONCE and offered, in the windows' common xx-outer / yy-inner
-// scan order, to the candidates whose window holds it -- each candidate sees exactly the comparisons of beam_match.
-// Returns false when the box is larger than that or a free-cell window could touch an allocated patch: the caller then
-// evaluates the candidates one by one.  skip: the move that is not evaluated (-1: none).  acc[m] += exp(...) where matched.
-__device__ __forceinline__ bool quad_match(const DevParams& P, const MatchCtx& M, const SmShared& S, double2 off, int skip, const double* __restrict__ pow2,
-                                           double (&acc)[4]) {
-    const Geom& g = M.g;
-    const double xp = S.lx[0] + off.x, xm = S.lx[1] + off.x, xc = S.lx[2] + off.x;
-    const double yc = S.ly[0] + off.y, ym = S.ly[2] + off.y, yp = S.ly[3] + off.y;
-    int ixp, ixm, ixc, iyc, iym, iyp;
-    cell_index2(xp - P.cx, yc - P.cy, P.delta, P.inv_delta, ixp, iyc);
-    cell_index2(xm - P.cx, ym - P.cy, P.delta, P.inv_delta, ixm, iym);
-    cell_index2(xc - P.cx, yp - P.cy, P.delta, P.inv_delta, ixc, iyp);
-    ixp += g.sx2; ixm += g.sx2; ixc += g.sx2; iyc += g.sy2; iym += g.sy2; iyp += g.sy2;
-    // the box (ldelta > 0: ixm <= ixc <= ixp and iym <= iyc <= iyp; anything else, NaN included, fails the size test)
-    const int x0 = ixm - 1, y0 = iym - 1;
-    const int rows = ixp - ixm + 3, cols = iyp - iym + 3;
-    if ((unsigned)(rows - 3) > 3u || (unsigned)(cols - 3) > 5u || ixc < ixm || ixc > ixp || iyc < iym || iyc > iyp) return false;
-    const int x1 = x0 + rows - 1, y1 = y0 + cols - 1;
-    {   // free-cell windows (beam_match): clear of every allocated patch, or this is not the fast path
-        const int ifx = P.free_q[0][0] + g.sx2, ify = P.free_q[0][1] + g.sy2;
-        const int4 bb = *M.bbox_s;
-        if (!(x1 + ifx < bb.x || y1 + ify < bb.y || x0 + ifx > bb.z || y0 + ify > bb.w)) return false;
-    }
-    // the (at most 2 x 2) patches under the box, unknown ones read the all-zero patch
-    const int pxa = x0 >> kPatchMag, pya = y0 >> kPatchMag, pxb = x1 >> kPatchMag, pyb = y1 >> kPatchMag;
-    const bool twoy = pyb != pya, twox = pxb != pxa;
-    const bool xa_in = (unsigned)pxa < (unsigned)g.npx, ya_in = (unsigned)pya < (unsigned)g.npy;
-    const bool xb_in = (unsigned)pxb < (unsigned)g.npx, yb_in = (unsigned)pyb < (unsigned)g.npy;
-    const int* da = *M.dirp_s + (pxa * g.npy + pya);
-    const int* dc = da + (twox ? g.npy : 0);
-    const int ida = ldg_if(da, xa_in && ya_in, -1);
-    const int idb = ldg_if(da + 1, twoy && xa_in && yb_in, twoy ? -1 : ida);
-    const int idc = ldg_if(dc, twox && xb_in && ya_in, twox ? -1 : ida);
-    const int idd = ldg_if(dc + 1, twox && twoy && xb_in && yb_in, twox ? (twoy ? -1 : idc) : idb);
-    if ((ida & idb & idc & idd) < 0) return true;  // every patch unknown: no candidate matches anything
-    const unsigned zp = (unsigned)M.zero_patch;
-    const unsigned ea = min((unsigned)ida, zp), eb = min((unsigned)idb, zp), ec = min((unsigned)idc, zp), ed = min((unsigned)idd, zp);
-    const int nxa = ((pxa + 1) << kPatchMag) - x0, nya = ((pya + 1) << kPatchMag) - y0;  // box rows / columns inside patches a / b
-    const unsigned ysh = (unsigned)(y0 & 31), colmask = (1u << cols) - 1u;
-    unsigned long long occ = 0ull;  // bit 8 * row + col of the box
-#pragma unroll
-    for (int r = 0; r < 6; r++) {
-        if (r < rows) {
-            const unsigned row = (unsigned)((x0 + r) & 31);
-            const unsigned lo = __ldg(M.occ + (((r < nxa ? ea : ec) << kPatchMag) + row));
-            const unsigned hi = twoy ? __ldg(M.occ + (((r < nxa ? eb : ed) << kPatchMag) + row)) : 0u;
-            occ |= (unsigned long long)(__funnelshift_r(lo, hi, ysh) & colmask) << (8 * r);
-        }
-    }
-    // window of candidate m inside the box: rows dr .. dr + 2, columns dc .. dc + 2
-    const unsigned long long w3 = 0x070707ull;
-    const unsigned long long w0 = skip == 0 ? 0ull : w3 << (8 * (ixp - ixm) + (iyc - iym));
-    const unsigned long long w1 = skip == 1 ? 0ull : w3 << (iyc - iym);
-    const unsigned long long w2 = skip == 2 ? 0ull : w3 << (8 * (ixc - ixm));
-    const unsigned long long w3m = skip == 3 ? 0ull : w3 << (8 * (ixc - ixm) + (iyp - iym));
-    unsigned long long todo = occ & (w0 | w1 | w2 | w3m);
-    const double inf = __longlong_as_double(0x7ff0000000000000ll);
-    double b0x = 0., b0y = 0., b0n = inf, b1x = 0., b1y = 0., b1n = inf, b2x = 0., b2y = 0., b2n = inf, b3x = 0., b3y = 0., b3n = inf;
-    while (todo) {
-        const int i = __ffsll((long long)todo) - 1;
-        todo &= todo - 1;
-        const int r = i >> 3, c = i & 7;
-        const unsigned e = r < nxa ? (c < nya ? ea : eb) : (c < nya ? ec : ed);
-        const double2 mean = ldg_d2(M.means + ((e << 10) + ((unsigned)((x0 + r) & 31) << kPatchMag) + (unsigned)((y0 + c) & 31)));  // mean(), smmap.h:24
-        const double dxp = xp - mean.x, dxm = xm - mean.x, dxc = xc - mean.x, dyc = yc - mean.y, dym = ym - mean.y, dyp = yp - mean.y;
-        const double sxc = dxc * dxc, syc = dyc * dyc;
-        const double n0 = dxp * dxp + syc, n1 = dxm * dxm + syc, n2 = sxc + dym * dym, n3 = sxc + dyp * dyp;
-        // strict <, cells in scan order: the first of equally near cells stays (scanmatcher.h:244-249)
-        if (((w0 >> i) & 1ull) && n0 < b0n) { b0x = dxp; b0y = dyc; b0n = n0; }
-        if (((w1 >> i) & 1ull) && n1 < b1n) { b1x = dxm; b1y = dyc; b1n = n1; }
-        if (((w2 >> i) & 1ull) && n2 < b2n) { b2x = dxc; b2y = dym; b2n = n2; }
-        if (((w3m >> i) & 1ull) && n3 < b3n) { b3x = dxc; b3y = dyp; b3n = n3; }
-    }
-    const double cexp = P.cexp;  // ((-1/sigma)*mu)*mu, point.h:34-49
-    if (b0n < inf) acc[0] += exp_neg((b0x * cexp) * b0x + (b0y * cexp) * b0y, pow2);
-    if (b1n < inf) acc[1] += exp_neg((b1x * cexp) * b1x + (b1y * cexp) * b1y, pow2);
-    if (b2n < inf) acc[2] += exp_neg((b2x * cexp) * b2x + (b2y * cexp) * b2y, pow2);
-    if (b3n < inf) acc[3] += exp_neg((b3x * cexp) * b3x + (b3y * cexp) * b3y, pow2);
-    return true;
-}
-
-// scanMatch for one particle per CTA (or per cluster of CL CTAs): hill-climb (optimize), accept/reject, likelihoodAndScore; or,
-// with A.query >= 0, one standalone score() / likelihoodAndScore() / optimize() per CTA.
-// dynamic shared memory: three tables of `tab_len` double2 each (this CTA's beams: (cos, sin) or end-point offsets).
+// scanMatch for one particle per CTA: hill-climb (optimize), accept/reject, likelihoodAndScore; or, with
+// A.query >= 0, one standalone score()/likelihoodAndScore() per CTA.
+// dynamic shared memory: three (cos, sin) tables of nbeams double2 each.
 // QUERY = (A.query >= 0); without it the particle is the block index, which keeps the per-particle pointers in uniform registers
-template <bool K1, bool QUERY, int CL>
-__global__ void __maxnreg__(kSmRegs) k_scanmatch(ScanMatchArgs A) {
-    constexpr int T = kSmThreadsMax / CL;  // threads of this CTA
-    constexpr int GC = kSmGroups / CL;     // groups of this CTA
+template <bool K1, bool QUERY>
+__global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SmShared S;
     const DevParams& P = A.P;
     double2* const tabs = reinterpret_cast<double2*>(smem_raw);
-    const unsigned rank = CL == 1 ? 0u : (unsigned)cooperative_groups::this_cluster().block_rank();
-    const unsigned q = blockIdx.x / CL, p = QUERY ? A.particle_idx[q] : q;
-    const int g_first = (int)rank * GC;                       // first group of this CTA
-    const int nk = ((int)P.nbeams + kSmGroups - 1) / kSmGroups;  // beams per group (at most)
-    const int tab_len = nk * GC;                              // entries per table: beam k * 144 + g  ->  k * GC + (g - g_first)
-    SmShared* const peer = CL == 1 ? nullptr : cooperative_groups::this_cluster().map_shared_rank(&S, rank ^ 1u);
+    const unsigned q = blockIdx.x, p = QUERY ? A.particle_idx[q] : q;
     // score() with the default window and a beam-independent free-cell offset: the tables hold the end-point offsets
     // r * (cos, sin), NaN for the beams score() skips, and the beam loop reads nothing else
     const int premul = (K1 && A.P.free_q[0][0] != INT_MIN) ? 1 : 0;
     const int t = threadIdx.x;
-    const int warp = t >> 5, lane = t & 31;
     MatchCtx M;
     M.dirp_s = &S.dirp; M.bbox_s = &S.bbox; M.pool = A.pool; M.visits = A.visits; M.means = A.means; M.occ = A.occ; M.inv_n = A.inv_n; M.g = A.geom[p];
     M.zero_patch = A.zero_patch;
-    const double* const pow2 = A.inv_n + kInvTable;
 
     if (t == 0) {
         S.dirp = A.dir + (size_t)p * A.dir_cap;
         S.init[0] = S.cur[0] = A.poses[3 * q]; S.init[1] = S.cur[1] = A.poses[3 * q + 1]; S.init[2] = S.cur[2] = A.poses[3 * q + 2];
         S.adelta = P.opt_angular_delta; S.ldelta = P.opt_linear_delta;
-        S.refinement = 0; S.evals = 1; S.evaluated = 1; S.bestScore = -1; S.done = 0; S.last_move = -1; S.skip = -1; S.buf = 0;
+        S.refinement = 0; S.evals = 1; S.evaluated = 1; S.bestScore = -1; S.done = 0; S.last_move = -1; S.skip = -1; S.cand[0] = 0;
         S.tab_of[0] = 0; S.tab_of[1] = 1; S.tab_of[2] = 2;
         S.key_ok[0] = S.key_ok[1] = S.key_ok[2] = 0;
         double lx, ly, lt;
@@ -582,151 +461,91 @@ __global__ void __maxnreg__(kSmRegs) k_scanmatch(ScanMatchArgs A) {
         __syncthreads();
         const int* dirp = A.dir + (size_t)p * A.dir_cap;
         int lox = INT_MAX, loy = INT_MAX, hix = -1, hiy = -1;
-        for (int e = t; e < M.g.npx * M.g.npy; e += T)
+        for (int e = t; e < M.g.npx * M.g.npy; e += kSmThreads)
             if (__ldg(dirp + e) >= 0) { const int px = e / M.g.npy, py = e - px * M.g.npy; lox = min(lox, px); hix = max(hix, px); loy = min(loy, py); hiy = max(hiy, py); }
-        const unsigned am = __activemask();
-        lox = __reduce_min_sync(am, lox); loy = __reduce_min_sync(am, loy);
-        hix = __reduce_max_sync(am, hix); hiy = __reduce_max_sync(am, hiy);
-        if (lane == 0 && hix >= 0) { atomicMin(&S.bb_lo_x, lox); atomicMin(&S.bb_lo_y, loy); atomicMax(&S.bb_hi_x, hix); atomicMax(&S.bb_hi_y, hiy); }
+        lox = __reduce_min_sync(0xffffffffu, lox); loy = __reduce_min_sync(0xffffffffu, loy);
+        hix = __reduce_max_sync(0xffffffffu, hix); hiy = __reduce_max_sync(0xffffffffu, hiy);
+        if ((t & 31) == 0 && hix >= 0) { atomicMin(&S.bb_lo_x, lox); atomicMin(&S.bb_lo_y, loy); atomicMax(&S.bb_hi_x, hix); atomicMax(&S.bb_hi_y, hiy); }
         __syncthreads();
         if (t == 0) S.bbox = S.bb_hi_x < 0 ? make_int4(1, 1, 0, 0) : make_int4(S.bb_lo_x << kPatchMag, S.bb_lo_y << kPatchMag, (S.bb_hi_x << kPatchMag) + kPatch - 1, (S.bb_hi_y << kPatchMag) + kPatch - 1);
     } else if (t == 0) S.bbox = make_int4(INT_MIN, INT_MIN, INT_MAX, INT_MAX);
-    if (CL > 1) cooperative_groups::this_cluster().sync();  // the peer's shared memory exists before anybody writes into it
     for (;;) {
         __syncthreads();  // the plan is visible
         if (S.done) break;
-        // ---- trig tables that changed (this CTA's beams)
+        // ---- trig tables that changed
         bool filled = false;
         for (int j = 0; j < 3; j++) {
             const int phys = S.fill[j];
             if (phys < 0) break;
             const double theta = S.fill_theta[j];
             const int kind = S.fill_kind[j];
-            double2* tab = tabs + (size_t)phys * tab_len;
-            for (int li = t; li < tab_len; li += T) {
-                const unsigned b = (unsigned)((li / GC) * kSmGroups + g_first + li % GC);
-                const double nan = __longlong_as_double(0x7ff8000000000000ll);
-                double2 v = make_double2(nan, nan);
-                if (b < P.nbeams && b >= P.beam_skip) {
-                    double sn, cs;
-                    sincos(theta + __ldg(A.angles + b), &sn, &cs);
-                    if (kind) {
-                        const double r = __ldg(A.ranges + b);
-                        const bool skip = !beam_selected(P, b) || r > P.usable_range || r == 0.0;  // scanmatcher.h:189-196
-                        if (!skip) v = make_double2(r * cs, r * sn);
-                    } else v = make_double2(cs, sn);
-                }
-                tab[li] = v;
+            double2* tab = tabs + (size_t)phys * P.nbeams;
+            for (unsigned b = P.beam_skip + t; b < P.nbeams; b += kSmThreads) {
+                double sn, cs;
+                sincos(theta + __ldg(A.angles + b), &sn, &cs);
+                if (kind) {
+                    const double r = __ldg(A.ranges + b);
+                    const bool skip = !beam_selected(P, b) || r > P.usable_range || r == 0.0;  // scanmatcher.h:189-196
+                    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+                    tab[b] = skip ? make_double2(nan, nan) : make_double2(r * cs, r * sn);
+                } else tab[b] = make_double2(cs, sn);
             }
             filled = true;
         }
         if (filled) __syncthreads();
-        // ---- evaluate
-        const int mode = S.mode, buf = S.buf;
-        const bool multi = S.ncand > 1;
+        // ---- evaluate: thread t works for candidate cand[t % ncand] on beams t / ncand, + ngroups, ...
+        const int mode = S.mode, nc = S.ncand;
+        const bool multi = nc > 1;
+        const int ngroups = nc == 6 ? kSmGroups : kSmThreads / nc, grp = nc == 6 ? t / 6 : t / nc;
+        const int m = multi ? S.cand[nc == 6 ? t % 6 : t - grp * nc] : 0;
+        double acc_s = 0., acc_l = 0.;
         unsigned cnt = 0, valid = 0;
-        // pfree offset: map.getDelta()*freeDelta in score() (scanmatcher.h:208), freeDelta in likelihoodAndScore() (:320)
-        const double free_off = mode ? P.free_off_lik : P.free_off_score;
-        const int fqx = mode ? P.free_q[1][0] : P.free_q[0][0], fqy = mode ? P.free_q[1][1] : P.free_q[0][1];  // (constant indexes)
-        // one pose, one beam: what the beam adds to the score (and to the log-likelihood) -- the single-candidate path
-        auto one_beam = [&](int m, unsigned tab_s, int li, unsigned b, bool offsets, double& acc_s, double& acc_l) {
+        if (grp < ngroups) {
             const double mlx = S.lx[m], mly = S.ly[m];
-            const unsigned ent_s = tab_s + (unsigned)li * 16u;
-            double2 cs;
-            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(cs.x), "=d"(cs.y) : "r"(ent_s));
-            double phx, phy;
-            if (offsets) {
-                if (cs.x != cs.x) return;  // a beam score() skips
-                phx = mlx + cs.x; phy = mly + cs.y;
-            } else {
-                if (cs.x != cs.x) return;  // outside the beam table / below initialBeamsSkip
-                const double r = __ldg(A.ranges + b);
-                // score() also skips r == 0 (scanmatcher.h:195); likelihoodAndScore() does not (:303-308)
-                if (!beam_selected(P, b) || r > P.usable_range || (mode == 0 && r == 0.0)) return;
-                phx = mlx + r * cs.x; phy = mly + r * cs.y;
-            }
-            double mx, my;
-            valid++;
-            const bool found = beam_match<K1>(P, M, mlx, mly, phx, phy, b, ent_s, A.ranges, free_off, fqx, fqy, mx, my);
-            if (found) { acc_s += exp_neg((mx * P.cexp) * mx + (my * P.cexp) * my, pow2); cnt++; }  // ((-1/sigma)*mu)*mu, point.h:34-49
-            if (mode) { const double f = P.clik * (mx * mx + my * my); acc_l += found ? f : P.no_hit; }
-        };
-        auto store = [&](int row, int g, double v) {
-            S.part[buf][row][g] = v;
-            if (CL > 1) peer->part[buf][row][g] = v;  // distributed shared memory: the peer reduces the same 144 sums
-        };
-        // ---- this thread's share of the step, as ONE loop nest for every role (one copy of the beam evaluation in the code):
-        //   quad thread (a round, t < GC): group t, every beam of it for the four translation candidates -- fused when it can be;
-        //   turn thread (a round, t >= GC): one rotation candidate, groups 2 w and 2 w + 1;
-        //   single pose: group t / 2, its beams alternately with the neighbouring thread.
-        // a0..a3: the four candidates' sums (quad), the two groups' sums (turn), score and log-likelihood (single pose)
-        const bool quad = multi && t < GC;
-        int m_first, m_count, gl, ngl, k0, kstep, tab_log;
-        if (quad) { m_first = 0; m_count = 4; gl = t; ngl = 1; k0 = 0; kstep = 1; tab_log = 0; }
-        else if (multi) {
-            const int u = t - GC, turn = u >= GC / 2 ? 1 : 0;
-            m_first = 4 + turn; m_count = 1; gl = 2 * (u - turn * (GC / 2)); ngl = 2; k0 = 0; kstep = 1; tab_log = 1 + turn;
-        } else { m_first = 0; m_count = 1; gl = t >> 1; ngl = 1; k0 = t & 1; kstep = 2; tab_log = 0; }
-        const unsigned tab_s = (unsigned)__cvta_generic_to_shared(tabs + (size_t)S.tab_of[tab_log] * tab_len);
-        const bool offsets = premul && mode == 0;  // the table in use holds end-point offsets
-        const int skip = multi ? S.skip : -1;
-        double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
-#pragma unroll 1
-        for (int h = 0; h < ngl; h++) {
-#pragma unroll 1
-            for (int k = k0; k < nk; k += kstep) {
-                const unsigned b = (unsigned)(k * kSmGroups + g_first + gl + h);
-                if (b >= P.nbeams) break;
-                const int li = k * GC + gl + h;
-                if (quad && offsets) {
-                    double2 off;
-                    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(off.x), "=d"(off.y) : "r"(tab_s + (unsigned)li * 16u));
-                    if (off.x != off.x) continue;  // a beam score() skips
-                    double acc[4] = {a0, a1, a2, a3};
-                    const bool fused = quad_match(P, M, S, off, skip, pow2, acc);
-                    a0 = acc[0]; a1 = acc[1]; a2 = acc[2]; a3 = acc[3];
-                    if (fused) continue;
+            const unsigned tab_s = (unsigned)__cvta_generic_to_shared(tabs + (size_t)S.tab_of[m < 4 ? 0 : m - 3] * P.nbeams);
+            // pfree offset: map.getDelta()*freeDelta in score() (scanmatcher.h:208), freeDelta in likelihoodAndScore() (:320)
+            const double free_off = mode ? P.free_off_lik : P.free_off_score;
+            const int fqx = mode ? P.free_q[1][0] : P.free_q[0][0], fqy = mode ? P.free_q[1][1] : P.free_q[0][1];  // (constant indexes)
+            const double cexp = P.cexp, clik = P.clik, noHit = P.no_hit;
+            const bool offsets = premul && mode == 0;  // the table in use holds end-point offsets
+            for (unsigned b = P.beam_skip + grp; b < P.nbeams; b += ngroups) {
+                double2 cs;
+                asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(cs.x), "=d"(cs.y) : "r"(tab_s + b * 16u));
+                double phx, phy;
+                if (offsets) {
+                    if (cs.x != cs.x) continue;  // a beam score() skips
+                    phx = mlx + cs.x; phy = mly + cs.y;
+                } else {
+                    const double r = __ldg(A.ranges + b);
+                    // score() also skips r == 0 (scanmatcher.h:195); likelihoodAndScore() does not (:303-308)
+                    if (!beam_selected(P, b) || r > P.usable_range || (mode == 0 && r == 0.0)) continue;
+                    phx = mlx + r * cs.x; phy = mly + r * cs.y;
                 }
-#pragma unroll 1
-                for (int mi = 0; mi < m_count; mi++) {
-                    const int m = m_first + mi;
-                    if (m == skip) continue;
-                    double add_s = 0., add_l = 0.;  // 0 + x == x: a sum receives exactly what the beam contributes
-                    one_beam(m, tab_s, li, b, offsets, add_s, add_l);
-                    const int slot = quad ? mi : h;
-                    a0 += slot == 0 ? add_s : 0.; a1 += slot == 1 ? add_s : 0.; a2 += slot == 2 ? add_s : 0.;
-                    a3 += slot == 3 ? add_s : (multi ? 0. : add_l);
-                }
+                double mx, my;
+                valid++;
+                const bool found = beam_match<K1>(P, M, mlx, mly, phx, phy, b, tab_s, A.ranges, free_off, fqx, fqy, mx, my);
+                if (found) { acc_s += exp_neg((mx * cexp) * mx + (my * cexp) * my, A.inv_n + kInvTable); cnt++; }  // ((-1/sigma)*mu)*mu, point.h:34-49
+                if (mode) { const double f = clik * (mx * mx + my * my); acc_l += found ? f : noHit; }
             }
         }
-        if (quad) { store(0, g_first + gl, a0); store(1, g_first + gl, a1); store(2, g_first + gl, a2); store(3, g_first + gl, a3); }
-        else if (multi) { store(m_first, g_first + gl, a0); store(m_first, g_first + gl + 1, a1); }
-        else {
-            store(t & 1, g_first + gl, a0); store(2 + (t & 1), g_first + gl, a3);
-            if (mode) {  // matched / valid beam counts: integers, any order
-                if (t < 2) S.cnt[buf][rank][t] = 0;
-                __syncthreads();
-                const unsigned am = __activemask();
-                cnt = __reduce_add_sync(am, cnt); valid = __reduce_add_sync(am, valid);
-                if (lane == 0) { atomicAdd(&S.cnt[buf][rank][0], cnt); atomicAdd(&S.cnt[buf][rank][1], valid); }
-                if (CL > 1) {
-                    __syncthreads();
-                    if (t < 2) peer->cnt[buf][rank][t] = S.cnt[buf][rank][t];
-                }
+        // ---- reduce (fixed shape: the sums do not depend on scheduling)
+        const int warp = t >> 5, lane = t & 31;
+        if (multi) {
+            S.part[t] = acc_s;
+            __syncthreads();
+            if (warp < nc) {  // warp w sums the partials of candidate cand[w]: lane j takes groups j and j + 32 (ngroups <= 64)
+                double v = lane < ngroups ? S.part[nc * lane + warp] : 0.;
+                if (lane + 32 < ngroups) v += S.part[nc * (lane + 32) + warp];
+                v = warp_sum(v);
+                if (lane == 0) S.red[S.cand[warp]] = v;
             }
-        }
-        // ---- reduce (fixed shape: the sums do not depend on scheduling, nor on the cluster size)
-        if (CL > 1) cooperative_groups::this_cluster().sync(); else __syncthreads();
-        if (warp < 4) {
-            const int nrows = multi ? 6 : (mode ? 4 : 2);
-            for (int row = warp; row < nrows; row += 4) {
-                const double v = reduce_row(S.part[buf][row], lane);
-                if (lane == 0) S.red[row] = v;
-            }
+        } else {
+            acc_s = warp_sum(acc_s); acc_l = warp_sum(acc_l);
+            cnt = __reduce_add_sync(0xffffffffu, cnt); valid = __reduce_add_sync(0xffffffffu, valid);
+            if (lane == 0) { S.red[warp] = acc_s; S.red_l[warp] = acc_l; S.red_c[warp] = cnt; S.red_v[warp] = valid; }
         }
         __syncthreads();
         if (t != 0) continue;
-        S.buf = buf ^ 1;
 
         // ---- thread 0: the reference's sequential decision logic
         if (S.phase == 1) {
@@ -758,45 +577,39 @@ __global__ void __maxnreg__(kSmRegs) k_scanmatch(ScanMatchArgs A) {
             }
             if (S.currentScore > S.bestScore || S.refinement < P.opt_iters) { plan_round(P, S, premul); continue; }
         } else if (S.phase == 0) {
-            S.currentScore = S.red[0] + S.red[1];
+            double v = 0.;
+            for (int w = 0; w < kSmThreads / 32; w++) v += S.red[w];
+            S.currentScore = v;
             plan_round(P, S, premul);
             continue;
         } else {
             // phase 2: likelihoodAndScore of the accepted pose; phase 3: standalone query
-            const double ss = S.red[0] + S.red[1];
-            double ll = 0.; unsigned cc = 0, vv = 0;
-            if (S.mode) {
-                ll = S.red[2] + S.red[3];
-                for (int r = 0; r < CL; r++) { cc += S.cnt[buf][r][0]; vv += S.cnt[buf][r][1]; }
-            }
-            if (rank == 0) {
-                if (S.phase == 3) {
-                    A.s[q] = ss;
-                    if (A.query == 1) { A.l[q] = ll; A.c[q] = cc; }
-                } else {
-                    A.poses[3 * p] = S.cur[0]; A.poses[3 * p + 1] = S.cur[1]; A.poses[3 * p + 2] = S.cur[2];
-                    A.score[p] = S.bestScore; A.s[p] = ss; A.l[p] = ll; A.c[p] = cc; A.evals[p] = S.evals;
-                    // the all-gather of the sharded filter happens here: every rank's gather buffer gets this particle's row
-                    // (its own HBM, or a peer's over NVLink); the flag below tells the ranks when a whole slice has landed
+            double ss = 0., ll = 0.; unsigned cc = 0, vv = 0;
+            for (int w = 0; w < kSmThreads / 32; w++) { ss += S.red[w]; ll += S.red_l[w]; cc += S.red_c[w]; vv += S.red_v[w]; }
+            if (S.phase == 3) {
+                A.s[q] = ss;
+                if (A.query == 1) { A.l[q] = ll; A.c[q] = cc; }
+            } else {
+                A.poses[3 * p] = S.cur[0]; A.poses[3 * p + 1] = S.cur[1]; A.poses[3 * p + 2] = S.cur[2];
+                A.score[p] = S.bestScore; A.s[p] = ss; A.l[p] = ll; A.c[p] = cc; A.evals[p] = S.evals;
+                // the all-gather of the sharded filter happens here: every rank's gather buffer gets this particle's row
+                // (its own HBM, or a peer's over NVLink); the flag below tells the ranks when a whole slice has landed
 #pragma unroll
-                    for (int r = 0; r < kMaxRanks; r++) {  // (constant indexes: the parameter block is not copied to local memory)
-                        if (r < A.nranks) {
-                            double* row = A.rows[r] + 5 * (size_t)(A.first_global + p);
-                            row[0] = S.cur[0]; row[1] = S.cur[1]; row[2] = S.cur[2]; row[3] = S.bestScore; row[4] = ll;
-                        }
+                for (int r = 0; r < kMaxRanks; r++) {  // (constant indexes: the parameter block is not copied to local memory)
+                    if (r < A.nranks) {
+                        double* row = A.rows[r] + 5 * (size_t)(A.first_global + p);
+                        row[0] = S.cur[0]; row[1] = S.cur[1]; row[2] = S.cur[2]; row[3] = S.bestScore; row[4] = ll;
                     }
-                    atomicAdd(&A.counters->score_evals, (unsigned long long)S.evals);
-                    atomicAdd(&A.counters->beam_evals, (unsigned long long)S.evaluated * A.valid_score_beams + vv);
                 }
+                atomicAdd(&A.counters->score_evals, (unsigned long long)S.evals);
+                atomicAdd(&A.counters->beam_evals, (unsigned long long)S.evaluated * A.valid_score_beams + vv);
             }
             S.done = 1;
             continue;
         }
         if (A.query == 2) {  // standalone optimize(): report the climbed pose and its score
-            if (rank == 0) {
-                A.poses_out[3 * q] = S.cur[0]; A.poses_out[3 * q + 1] = S.cur[1]; A.poses_out[3 * q + 2] = S.cur[2];
-                A.score[q] = S.bestScore;
-            }
+            A.poses_out[3 * q] = S.cur[0]; A.poses_out[3 * q + 1] = S.cur[1]; A.poses_out[3 * q + 2] = S.cur[2];
+            A.score[q] = S.bestScore;
             S.done = 1;
             continue;
         }
@@ -811,11 +624,11 @@ __global__ void __maxnreg__(kSmRegs) k_scanmatch(ScanMatchArgs A) {
         for (int j = nfill; j < 3; j++) S.fill[j] = -1;
         S.ncand = 1; S.mode = 1; S.phase = 2;
     }
-    // the last particle to finish publishes the sequence number of this scan where every rank's host can see it (release
-    // pattern: rows, system-wide fence, count; the CTA that counts last fences again and writes the flag)
-    if (!QUERY && A.flag && t == 0 && rank == 0) {
+    // the last CTA publishes the sequence number of this scan where every rank's host can see it (release pattern: rows,
+    // system-wide fence, count; the CTA that counts last fences again and writes the flag)
+    if (!QUERY && A.flag && t == 0) {
         __threadfence_system();
-        if (atomicAdd(A.done_counter, 1u) == gridDim.x / CL - 1) {
+        if (atomicAdd(A.done_counter, 1u) == gridDim.x - 1) {
             *A.done_counter = 0;
             __threadfence_system();
             *reinterpret_cast<volatile unsigned*>(A.flag) = A.seq;
@@ -1057,6 +870,7 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
     __shared__ int s_part[kRegThreads / 32];
     __shared__ int s_nactive, s_nwork;
     __shared__ int s_tile_id[kMaxTiles];
+    __shared__ int s_gitems[GM_MAXBEAMS_DEV / 32 + 2];  // prefix of the chunk counts of the groups of 32 neighbouring beams
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 
     long long tph = clock64();
@@ -1095,8 +909,13 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
             }
         }
         rec[b] = R;
-        M.items[b + 1] = (R.flags & 1) ? (ray_cells(p0x, p0y, R.p1x, R.p1y) + kRayChunk - 1) / kRayChunk : 0;
+        const int chunks = (R.flags & 1) ? (ray_cells(p0x, p0y, R.p1x, R.p1y) + kRayChunk - 1) / kRayChunk : 0;
+        M.items[b + 1] = chunks;
+        // a warp holds 32 neighbouring beams here: the longest of them sets the chunk count of the group (ray counting below)
+        const int gmax = __reduce_max_sync(__activemask(), chunks);
+        if (lane == 0) s_gitems[(b >> 5) + 1] = gmax;
     }
+    if (threadIdx.x == 0) s_gitems[0] = 0;
     __syncthreads();
     // work items of the ray walks: items[b] .. items[b+1] are beam b's chunks (inclusive scan by one warp)
     if (warp == 0) {
@@ -1109,9 +928,20 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
             run += __shfl_sync(0xffffffffu, v, 31);
         }
         if (lane == 0) M.items[0] = 0;
+    } else if (warp == 1) {
+        const int ng = ((int)P.nbeams + 31) >> 5;  // at most 64 groups: two per lane
+        int run = 0;
+        for (int g0 = 0; g0 < ng; g0 += 32) {
+            const int gi = g0 + lane;
+            int v = gi < ng ? s_gitems[gi + 1] : 0;
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+            if (gi < ng) s_gitems[gi + 1] = run + v;
+            run += __shfl_sync(0xffffffffu, v, 31);
+        }
     }
     __syncthreads();
     const int nitems = M.items[P.nbeams];
+    const int ngroups32 = ((int)P.nbeams + 31) >> 5, ngitems = s_gitems[ngroups32];
     PHASE(0);
 
     // ---- 1. active area: patches under the rays (from each chunk's end points, see item_patches)
@@ -1255,38 +1085,67 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
             const int id = s_tile_id[i >> 5];
             if (id >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.pool.visits + (size_t)id * kPatchCells + ((i & 31) << 5)));
         }
-        for (int it = threadIdx.x; it < nitems; it += blockDim.x) {
-            int lo = 0, hi = (int)P.nbeams - 1;
-            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (M.items[mid] <= it) lo = mid; else hi = mid - 1; }
-            const BeamRec R = rec[lo];
-            if (nactive > A.tile_cap) {  // several passes: skip the chunk unless one of its patches is counted in this one
-                int qx[4], qy[4];
-                const int nq = item_patches(p0x, p0y, R.p1x, R.p1y, it - M.items[lo], qx, qy);
-                bool mine = false;
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (k < nq && (unsigned)qx[k] < (unsigned)g.npx && (unsigned)qy[k] < (unsigned)g.npy) {
-                        const int e = qx[k] * g.npy + qy[k];
-                        const int slot = (int)M.prefix[e >> 5] + __popc(active[e >> 5] & ((1u << (e & 31)) - 1u)) - first;
-                        mine = mine || (unsigned)slot < (unsigned)ntile;
-                    }
-                if (!mine) continue;
+        // A work item is a chunk of kRayChunk steps, counted from the sensor cell, of 32 NEIGHBOURING beams, one beam per lane.
+        // Which cells a ray visits does not depend on the order: every lane walks the reference's Bresenham (gridlinetraversal.h:
+        // 20-108: major axis upward from the lower end point) from the sensor outward -- downward along the major axis when the
+        // sensor is the upper end -- with the walk's state kept as (inc, e): minor = b_lo + bstep * inc, inc = floor((2 db j + da) /
+        // (2 da)), e = the remainder.  Neighbouring beams cross the same cells until they fan out (0.25 deg: about 11 m at 5 cm):
+        // lanes in the same step whose cells coincide form runs, and one shared-memory atomic per run adds the run's length.
+        int gb = 0;
+        for (int it = warp; it < ngitems; it += nw) {
+            while (s_gitems[gb + 1] <= it) gb++;  // items come in ascending order: the search resumes where it stopped
+            const int i0 = (it - s_gitems[gb]) * kRayChunk;
+            const int b = (gb << 5) + lane;
+            BeamRec R; R.p1x = p0x; R.p1y = p0y; R.hx = R.hy = 0.f; R.flags = 0;
+            if (b < (int)P.nbeams) R = rec[b];
+            const Line L = make_line(p0x, p0y, R.p1x, R.p1y);
+            const int m = (R.flags & 1) ? L.n - 1 : 0;  // cells of the ray: every point but the end point
+            const int steps = max(0, min(kRayChunk, m - i0));
+            // the walk's state as the cell (x, y) itself and a remainder f that overflows (f >= 2 da) exactly when the minor
+            // coordinate moves: upward f = e, downward f = 2 da - 1 - e (then e - 2 db < 0  <=>  f + 2 db >= 2 da)
+            const int j = L.from_end ? m - i0 : i0;  // the sensor is the UPPER end of a from_end line: steps j = m down to 1
+            int inc = 0, e = L.da;
+            if (steps > 0 && L.da) {
+                const unsigned num = 2u * (unsigned)L.db * (unsigned)j + (unsigned)L.da, den = 2u * (unsigned)L.da;
+                int q = (int)((double)num * (1.0 / (double)den));  // exact after the one-step correction
+                long long rem = (long long)num - (long long)q * den;
+                if (rem >= (long long)den) { q++; rem -= den; } else if (rem < 0) { q--; rem += den; }
+                inc = q; e = (int)rem;
             }
-            unsigned* tile = nullptr;  // counters of the current patch, null when it is not in this pass / outside the map
-            walk_ray(p0x, p0y, R.p1x, R.p1y, it - M.items[lo], [&](int x, int y, int px, int py, bool np) {
-                if (np) {
-                    tile = nullptr;
-                    if ((unsigned)px < (unsigned)g.npx && (unsigned)py < (unsigned)g.npy) {
-                        const int e = px * g.npy + py;
-                        const int slot = (int)M.prefix[e >> 5] + __popc(active[e >> 5] & ((1u << (e & 31)) - 1u)) - first;
-                        if ((unsigned)slot < (unsigned)ntile) tile = M.tiles + slot * kTileWords;
+            const int two_db = 2 * L.db, two_da = 2 * L.da;
+            int f = L.from_end ? two_da - 1 - e : e;
+            const int dmaj = L.from_end ? -1 : 1, dmin = L.from_end ? -L.bstep : L.bstep;
+            int x = L.steep ? L.b_lo + L.bstep * inc : L.a_lo + j, y = L.steep ? L.a_lo + j : L.b_lo + L.bstep * inc;
+            const int sx0 = L.steep ? 0 : dmaj, sy0 = L.steep ? dmaj : 0, sx1 = L.steep ? dmin : 0, sy1 = L.steep ? 0 : dmin;
+            int lx = INT_MIN / 2, ly = INT_MIN / 2, base = -1;  // cell of the last patch lookup, tile of that patch (slot << 10)
+            const int smax = __reduce_max_sync(0xffffffffu, steps);
+            for (int sidx = 0; sidx < smax; sidx++) {
+                int key = -1;
+                if (sidx < steps) {
+                    if (((x ^ lx) | (y ^ ly)) >> kPatchMag) {  // another patch
+                        lx = x; ly = y; base = -1;
+                        const int px = x >> kPatchMag, py = y >> kPatchMag;
+                        if ((unsigned)px < (unsigned)g.npx && (unsigned)py < (unsigned)g.npy) {
+                            const int en = px * g.npy + py;
+                            const int sl = (int)M.prefix[en >> 5] + __popc(active[en >> 5] & ((1u << (en & 31)) - 1u)) - first;
+                            if ((unsigned)sl < (unsigned)ntile) base = sl << 10;
+                        }
                     }
+                    if (base >= 0) key = base | ((x & 31) << kPatchMag) | (y & 31);
+                    f += two_db;
+                    const bool carry = f >= two_da;
+                    f -= carry ? two_da : 0;
+                    x += sx0 + (carry ? sx1 : 0); y += sy0 + (carry ? sy1 : 0);
                 }
-                if (tile) {
-                    const int ci = ((x & 31) << kPatchMag) + (y & 31);
-                    atomicAdd(tile + (ci >> 1), 1u << ((ci & 1) << 4));
+                const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+                const bool head = lane == 0 || key != prev;
+                const unsigned heads = __ballot_sync(0xffffffffu, head);
+                if (head && key >= 0) {
+                    const unsigned after = (heads >> lane) >> 1;  // (lane 31: nothing after)
+                    const unsigned len = after ? (unsigned)__ffs(after) : 32u - (unsigned)lane;
+                    atomicAdd(M.tiles + (key >> 1), len << ((key & 1) << 4));
                 }
-            });
+            }
         }
         __syncthreads();
         PHASE(4);
@@ -1641,42 +1500,23 @@ void launch_release_particle(int* dirp, int nent, const Pool& pool, cudaStream_t
 void launch_install_patches(int* dirp, Geom g, const int* coords, const int4* staged, const Pool& pool, Counters* ctr, int n, cudaStream_t st) {
     k_install_patches<<<n, 256, 0, st>>>(dirp, g, coords, staged, pool, ctr);
 }
-// three tables of this CTA's beams: ceil(nbeams / 144) entries per group, 144 / CL groups
-size_t scanmatch_smem_bytes(unsigned nbeams, int cluster) { return (size_t)3 * ((nbeams + kSmGroups - 1) / kSmGroups) * (kSmGroups / cluster) * sizeof(double2); }
-template <bool K1, bool QUERY, int CL> static cudaError_t scanmatch_attr(size_t smem) {
-    return cudaFuncSetAttribute(k_scanmatch<K1, QUERY, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-}
-cudaError_t scanmatch_prepare(unsigned nbeams) {
-    const size_t s1 = scanmatch_smem_bytes(nbeams, 1), s2 = scanmatch_smem_bytes(nbeams, 2);
-    cudaError_t e = scanmatch_attr<true, false, 1>(s1);
-    if (e == cudaSuccess) e = scanmatch_attr<false, false, 1>(s1);
-    if (e == cudaSuccess) e = scanmatch_attr<true, true, 1>(s1);
-    if (e == cudaSuccess) e = scanmatch_attr<false, true, 1>(s1);
-    if (e == cudaSuccess) e = scanmatch_attr<true, false, 2>(s2);
-    if (e == cudaSuccess) e = scanmatch_attr<false, false, 2>(s2);
+size_t scanmatch_smem_bytes(unsigned nbeams) { return (size_t)3 * nbeams * sizeof(double2); }
+cudaError_t scanmatch_prepare(size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(k_scanmatch<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scanmatch<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scanmatch<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scanmatch<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     return e;
 }
-template <bool K1, bool QUERY, int CL> static void scanmatch_launch(const ScanMatchArgs& a, unsigned n, cudaStream_t st) {
-    const size_t smem = scanmatch_smem_bytes(a.P.nbeams, CL);
-    if (CL == 1) { k_scanmatch<K1, QUERY, CL><<<n, kSmThreadsMax, smem, st>>>(a); return; }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(n * CL); cfg.blockDim = dim3(kSmThreadsMax / CL); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, k_scanmatch<K1, QUERY, CL>, a);
-}
-// cluster: CTAs per particle (1 or 2) of the scanMatch launch; queries always use one
-void launch_scanmatch(const ScanMatchArgs& a, unsigned n, int cluster, cudaStream_t st) {
+void launch_scanmatch(const ScanMatchArgs& a, unsigned n, cudaStream_t st) {
+    const size_t smem = scanmatch_smem_bytes(a.P.nbeams);
     const bool k1 = a.P.kernel_size == 1 && a.P.thr_is_tenth;
     if (a.query < 0) {
-        if (cluster == 2) { if (k1) scanmatch_launch<true, false, 2>(a, n, st); else scanmatch_launch<false, false, 2>(a, n, st); }
-        else if (k1) scanmatch_launch<true, false, 1>(a, n, st);
-        else scanmatch_launch<false, false, 1>(a, n, st);
+        if (k1) k_scanmatch<true, false><<<n, kSmThreads, smem, st>>>(a);
+        else k_scanmatch<false, false><<<n, kSmThreads, smem, st>>>(a);
     } else {
-        if (k1) scanmatch_launch<true, true, 1>(a, n, st);
-        else scanmatch_launch<false, true, 1>(a, n, st);
+        if (k1) k_scanmatch<true, true><<<n, kSmThreads, smem, st>>>(a);
+        else k_scanmatch<false, true><<<n, kSmThreads, smem, st>>>(a);
     }
 }
 

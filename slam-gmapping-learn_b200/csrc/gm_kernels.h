@@ -64,9 +64,9 @@ struct DigestArgs {
     unsigned first; unsigned long long* out;  // 7 words per particle: the six of gm_digest + mismatching occupancy-bitmap rows
 };
 
-size_t scanmatch_smem_bytes(unsigned nbeams, int cluster);
-cudaError_t scanmatch_prepare(unsigned nbeams);
-void launch_scanmatch(const ScanMatchArgs& a, unsigned n, int cluster, cudaStream_t st);
+size_t scanmatch_smem_bytes(unsigned nbeams);
+cudaError_t scanmatch_prepare(size_t smem);
+void launch_scanmatch(const ScanMatchArgs& a, unsigned n, cudaStream_t st);
 void launch_bounds(const BoundsArgs& a, unsigned n, unsigned threads, cudaStream_t st);
 void launch_relayout(const RelayoutArgs& a, unsigned n, cudaStream_t st);
 void launch_relayout_commit(const RelayoutArgs& a, unsigned n, cudaStream_t st);

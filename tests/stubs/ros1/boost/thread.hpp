@@ -1,0 +1,1 @@
+#include "../stub_all.h"
