@@ -22,7 +22,8 @@ void gm_default_matching(gm_match_params* p) {  // scanmatcher.cpp:17-56
     p->initial_beams_skip = 0;
 }
 
-int gm_create(gm_ctx** out, const gm_config* cfg) {
+// share_with: take that context's patch pool and stream instead of allocating (gm_clone)
+static int create_ctx(gm_ctx** out, const gm_config* cfg, gm_ctx* share_with) {
     gm_ctx* ctx = nullptr;  // CK() reports into g_create_error while ctx is null
     if (!out || !cfg) return fail(nullptr, GM_ERR_ARG, "gm_create: null argument");
     *out = nullptr;
@@ -45,7 +46,8 @@ int gm_create(gm_ctx** out, const gm_config* cfg) {
     if (c->threads % 32 || c->threads > 256 || c->threads < 32) { delete c; return fail(nullptr, GM_ERR_ARG, "block_threads must be a multiple of 32 in [32,256]"); }
     ctx = c;
 #define CKC(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { fail(nullptr, GM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2_)); gm_destroy(c); return GM_ERR_CUDA; } } while (0)
-    CKC(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    if (share_with) c->st = share_with->st;
+    else CKC(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     {
         int lo = 0, hi = 0;  // the weight kernels are one CTA each: let them in ahead of the registration's grid
         CKC(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -53,7 +55,11 @@ int gm_create(gm_ctx** out, const gm_config* cfg) {
     }
     CKC(cudaEventCreate(&c->ev0)); CKC(cudaEventCreate(&c->ev1)); CKC(cudaEventCreate(&c->evw0)); CKC(cudaEventCreate(&c->evw1));
     size_t cap = cfg->pool_patches;
-    {
+    if (share_with) {
+        c->pool = share_with->pool;
+        c->refcnt_new = share_with->refcnt_new;
+        cap = (size_t)c->pool.cap;
+    } else {
         // 0 = half of the free HBM; an explicit request is honoured up to 80 % of it (a larger one would only fail in cudaMalloc)
         size_t free_b = 0, total_b = 0;
         CKC(cudaMemGetInfo(&free_b, &total_b));
@@ -62,7 +68,6 @@ int gm_create(gm_ctx** out, const gm_config* cfg) {
         if (!cap) cap = std::min<size_t>(half, (size_t)1 << 22);  // 64 GiB of patches at most by default
         else if (cap > most) cap = most;
         if (cap < 64) cap = 64;
-    }
     if (cap > ((size_t)1 << 22) - 2) cap = ((size_t)1 << 22) - 2;  // cell indexes (patch * 1024 + cell) stay below 2^32
     c->pool.cap = (int)cap;
     CKC(dalloc(c->pool.cells, (cap + 1) * kPatchCells));  // + the all-zero patch at index cap (unknown cells)
@@ -77,6 +82,7 @@ int gm_create(gm_ctx** out, const gm_config* cfg) {
     CKC(dalloc(c->pool.free_top, 1)); CKC(dalloc(c->pool.pending_n, 1));
     CKC(dalloc(c->refcnt_new, cap));
     CKC(cudaMemsetAsync(c->refcnt_new, 0, cap * sizeof(int), c->st));
+    }
     const uint32_t N = c->max_particles;
     c->weights_cap = std::max(cfg->max_particles, cfg->global_particles);
     CKC(dalloc(c->geom, N)); CKC(dalloc(c->geom_alt, N)); CKC(dalloc(c->geom_new, N)); CKC(dalloc(c->shift, N));
@@ -103,7 +109,7 @@ int gm_create(gm_ctx** out, const gm_config* cfg) {
         CKC(dalloc(c->d_inv_n, inv.size()));
         CKC(cudaMemcpy(c->d_inv_n, inv.data(), sizeof(double) * inv.size(), cudaMemcpyHostToDevice));
     }
-    launch_pool_init(c->pool, c->st);
+    if (!share_with) launch_pool_init(c->pool, c->st);
     CKC(cudaGetLastError());
     CKC(cudaStreamSynchronize(c->st));
 #undef CKC
@@ -113,6 +119,8 @@ int gm_create(gm_ctx** out, const gm_config* cfg) {
     return GM_OK;
 }
 
+int gm_create(gm_ctx** out, const gm_config* cfg) { return create_ctx(out, cfg, nullptr); }
+
 int gm_destroy(gm_ctx* c) {
     if (!c) return GM_OK;
     cudaSetDevice(c->device);
@@ -120,8 +128,24 @@ int gm_destroy(gm_ctx* c) {
     c->reg_pending = false;
     gmi_dist_destroy(c);
     if (c->st) cudaStreamSynchronize(c->st);
-    cudaFree(c->pool.cells); cudaFree(c->pool.visits); cudaFree(c->pool.means); cudaFree(c->pool.occ); cudaFree(c->pool.refcnt); cudaFree(c->pool.free_list); cudaFree(c->pool.pending);
-    cudaFree(c->pool.free_top); cudaFree(c->pool.pending_n); cudaFree(c->refcnt_new);
+    bool last = true;
+    if (c->share) {
+        // a context that shares its pool gives its references back; the pool and the stream go with the last user
+        if (c->inited && c->dir && c->share->users > 1) {
+            launch_release_slots(c->geom, c->dir, c->dir_cap, 0, c->n, c->pool, c->st);
+            launch_merge_free(c->pool, c->st);
+            cudaStreamSynchronize(c->st);
+        }
+        std::vector<gm_ctx*>& m = c->share->members;
+        m.erase(std::remove(m.begin(), m.end(), c), m.end());
+        last = --c->share->users == 0;
+        if (last) delete c->share;
+        c->share = nullptr;
+    }
+    if (last) {
+        cudaFree(c->pool.cells); cudaFree(c->pool.visits); cudaFree(c->pool.means); cudaFree(c->pool.occ); cudaFree(c->pool.refcnt); cudaFree(c->pool.free_list); cudaFree(c->pool.pending);
+        cudaFree(c->pool.free_top); cudaFree(c->pool.pending_n); cudaFree(c->refcnt_new);
+    }
     cudaFree(c->dir); cudaFree(c->dir_alt); cudaFree(c->geom); cudaFree(c->geom_alt); cudaFree(c->geom_new); cudaFree(c->shift);
     cudaFree(c->d_ranges); cudaFree(c->d_angles); cudaFree(c->d_poses); cudaFree(c->d_score); cudaFree(c->d_s); cudaFree(c->d_l);
     cudaFree(c->d_c); cudaFree(c->d_evals); cudaFree(c->d_idx); cudaFree(c->d_emitted);
@@ -133,7 +157,7 @@ int gm_destroy(gm_ctx* c) {
     cudaFree(c->d_occ); cudaFree(c->d_counters); cudaFree(c->d_inv_n); cudaFree(c->d_digest); cudaFree(c->d_list); cudaFree(c->d_count); cudaFree(c->d_export);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
-    if (c->st) cudaStreamDestroy(c->st);
+    if (c->st && last) cudaStreamDestroy(c->st);
     if (c->st_w) cudaStreamDestroy(c->st_w);
     if (c->evw0) cudaEventDestroy(c->evw0);
     if (c->evw1) cudaEventDestroy(c->evw1);
@@ -178,6 +202,7 @@ int gm_init_particles(gm_ctx* ctx, uint32_t n, const double center[2], double wo
     if (!ctx) return GM_ERR_ARG;
     if (!center || !n || n > ctx->max_particles || !(delta > 0)) return fail(ctx, GM_ERR_ARG, "gm_init_particles: bad argument (n=%u, max=%u)", n, ctx->max_particles);
     if (int r = bind(ctx)) return r;
+    if (ctx->share && ctx->share->users > 1) return fail(ctx, GM_ERR_ARG, "gm_init_particles: this context shares its patch pool with %d clone(s)", ctx->share->users - 1);
     // Map(center, worldSizeX, worldSizeY, delta): map.h:171-184; HierarchicalArray2D(xsize>>5, ysize>>5): harray2d.h:54-59
     const int xs = (int)ceil(world_w / delta), ys = (int)ceil(world_h / delta);
     Geom g;
@@ -461,10 +486,9 @@ int gmi_remap(gm_ctx* ctx, const uint32_t* idx, uint32_t src_limit) {
     CK(cudaEventRecord(ctx->ev0, ctx->st));
     RemapArgs r;
     r.idx = ctx->d_idx; r.geom = ctx->geom; r.geom_alt = ctx->geom_alt; r.dir = ctx->dir; r.dir_alt = ctx->dir_alt;
-    r.dir_cap = ctx->dir_cap; r.refcnt_new = ctx->refcnt_new;
-    launch_remap(r, n, ctx->st);
-    SweepArgs s; s.pool = ctx->pool; s.refcnt_new = ctx->refcnt_new;
-    launch_sweep(s, ctx->st);
+    r.dir_cap = ctx->dir_cap; r.refcnt = ctx->pool.refcnt;
+    launch_remap(r, n, ctx->st);  // the new generation takes its references first: a shared patch never drops to zero in between
+    launch_release_slots(ctx->geom, ctx->dir, ctx->dir_cap, 0, src_limit, ctx->pool, ctx->st);  // the old one, imported parents included
     launch_merge_free(ctx->pool, ctx->st);
     CK(cudaEventRecord(ctx->ev1, ctx->st));
     ctx->stats.launches += 3;
@@ -722,7 +746,14 @@ int gm_check_refcounts(gm_ctx* ctx, uint64_t* mismatches_out, uint64_t* referenc
     if (int r = ready(ctx, true)) return r;
     unsigned long long* out = ctx->d_digest;  // scratch: three words
     CK(cudaMemsetAsync(out, 0, 3 * sizeof(unsigned long long), ctx->st));
-    launch_recount(ctx->geom, ctx->dir, ctx->dir_cap, ctx->pool, ctx->refcnt_new, out, ctx->n, ctx->st);  // refcnt_new is all zero between remaps
+    // every context that shares the pool holds references: all their directories are counted (refcnt_new is all-zero scratch)
+    if (ctx->share) {
+        for (gm_ctx* m : ctx->share->members) {
+            if (m != ctx && m->reg_pending) { gm_ctx* self = ctx; ctx = m; const int r = gmi_register_finish(m); ctx = self; if (r) return fail(ctx, r, "gm_check_refcounts: %s", m->err.c_str()); }
+            if (m->inited) launch_recount(m->geom, m->dir, m->dir_cap, ctx->pool, ctx->refcnt_new, out, m->n, ctx->st);
+        }
+    } else launch_recount(ctx->geom, ctx->dir, ctx->dir_cap, ctx->pool, ctx->refcnt_new, out, ctx->n, ctx->st);
+    launch_recount_compare(ctx->pool, ctx->refcnt_new, out, ctx->st);
     ctx->stats.launches += 2;
     if (int r = check_launch(ctx, "k_recount")) return r;
     unsigned long long h[3] = {0, 0, 0};
@@ -750,32 +781,35 @@ int gm_clone(gm_ctx* src, gm_ctx** out) {
     cfg.device = src->device; cfg.max_particles = src->max_particles; cfg.pool_patches = (uint64_t)src->pool.cap;
     cfg.block_threads = src->threads; cfg.global_particles = src->weights_cap;
     gm_ctx* dst = nullptr;
-    if (int r = gm_create(&dst, &cfg)) return fail(src, r, "gm_clone: %s", gm_last_error(nullptr));
+    if (int r = create_ctx(&dst, &cfg, src)) return fail(src, r, "gm_clone: %s", gm_last_error(nullptr));
+    // the clone is a second set of patch directories over the SAME pool: a reference more per patch, no patch is copied
+    // (the reference's copy: HierarchicalArray2D copy by autoptr shares, harray2d.h:63-77); its kernels run on the same stream
+    if (!src->share) { src->share = new PoolShare(); src->share->members.push_back(src); }
+    dst->share = src->share;
+    dst->share->users++;
+    dst->share->members.push_back(dst);
     dst->P = src->P; dst->laser_set = src->laser_set; dst->match_set = src->match_set;
     memcpy(dst->angles_h, src->angles_h, sizeof src->angles_h);
     auto bail = [&](cudaError_t e, const char* what) {
+        dst->inited = false;
         gm_destroy(dst);
         return fail(src, GM_ERR_CUDA, "gm_clone: %s: %s", what, cudaGetErrorString(e));
     };
     cudaError_t e;
     if ((e = cudaMemcpyAsync(dst->d_angles, src->d_angles, sizeof(double) * GM_MAXBEAMS, cudaMemcpyDeviceToDevice, src->st)) != cudaSuccess) return bail(e, "angles");
     if (src->inited) {
-        dst->n = src->n; dst->dir_cap = src->dir_cap; dst->inited = true; dst->reg_active_hint = src->reg_active_hint;
-        const size_t dn = (size_t)src->max_particles * src->dir_cap, cap = (size_t)src->pool.cap;
+        dst->n = src->n; dst->dir_cap = src->dir_cap; dst->reg_active_hint = src->reg_active_hint;
+        const size_t dn = (size_t)src->max_particles * src->dir_cap;
         if ((e = dalloc(dst->dir, dn)) != cudaSuccess || (e = dalloc(dst->dir_alt, dn)) != cudaSuccess) return bail(e, "directories");
         if ((e = dalloc(dst->d_w, dst->weights_cap)) != cudaSuccess || (e = dalloc(dst->d_logw, dst->weights_cap)) != cudaSuccess ||
             (e = dalloc(dst->d_cum, dst->weights_cap)) != cudaSuccess || (e = dalloc(dst->d_tgt, dst->weights_cap)) != cudaSuccess ||
             (e = dalloc(dst->d_neff, 1)) != cudaSuccess || (e = dalloc(dst->d_widx, dst->weights_cap)) != cudaSuccess) return bail(e, "weight buffers");
-        // the whole pool is copied (ids stay valid); the clone costs as much HBM as the original
-        struct { void* d; const void* s; size_t bytes; } copies[] = {
-            {dst->pool.cells, src->pool.cells, (cap + 1) * kPatchCells * sizeof(int4)}, {dst->pool.visits, src->pool.visits, (cap + 1) * kPatchCells * sizeof(int)},
-            {dst->pool.means, src->pool.means, (cap + 1) * kPatchCells * sizeof(double2)},
-            {dst->pool.occ, src->pool.occ, (cap + 1) * kPatch * sizeof(unsigned)}, {dst->pool.refcnt, src->pool.refcnt, cap * sizeof(int)},
-            {dst->pool.free_list, src->pool.free_list, cap * sizeof(int)}, {dst->pool.free_top, src->pool.free_top, sizeof(int)},
-            {dst->dir, src->dir, dn * sizeof(int)}, {dst->geom, src->geom, sizeof(Geom) * src->max_particles}};
-        for (auto& c : copies)
-            if ((e = cudaMemcpyAsync(c.d, c.s, c.bytes, cudaMemcpyDeviceToDevice, src->st)) != cudaSuccess) return bail(e, "device copy");
+        if ((e = cudaMemcpyAsync(dst->dir, src->dir, dn * sizeof(int), cudaMemcpyDeviceToDevice, src->st)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(dst->geom, src->geom, sizeof(Geom) * src->max_particles, cudaMemcpyDeviceToDevice, src->st)) != cudaSuccess) return bail(e, "device copy");
         launch_fill_int(dst->dir_alt, dn, -1, src->st);
+        launch_addref_slots(dst->geom, dst->dir, dst->dir_cap, dst->n, dst->pool, src->st);
+        if ((e = cudaGetLastError()) != cudaSuccess) return bail(e, "launch");
+        dst->inited = true;
     }
     if ((e = cudaStreamSynchronize(src->st)) != cudaSuccess) return bail(e, "synchronize");
     dst->stats = src->stats;

@@ -19,7 +19,15 @@ using namespace gm;
 
 inline std::string& create_error() { static thread_local std::string e; return e; }
 
+// a patch pool and the stream its kernels are ordered on, shared by a context and its clones (gm_clone): the clones' patch
+// directories hold references into the same pool, copy-on-write keeps them apart
+struct PoolShare {
+    int users = 1;
+    std::vector<struct gm_ctx*> members;
+};
+
 struct gm_ctx {
+    PoolShare* share = nullptr;  // null: the context owns its pool alone
     int device = 0;
     cudaStream_t st = nullptr;
     cudaStream_t st_w = nullptr;  // weights (normalize / resample indexes): independent of the maps, may overtake a registration

@@ -8,7 +8,7 @@
 //   k_bounds      computeActiveArea's bounding box + Map::resize maths  (scanmatcher.cpp:83-166, map.h:218-241)
 //   k_relayout    HierarchicalArray2D::resize                           (harray2d.h:80-109)
 //   k_register    active area + copy-on-write + ray update + hits       (scanmatcher.cpp:168-354, harray2d.h:169-185)
-//   k_remap/k_sweep/k_merge_free   particle copy by patch reference     (gridslamprocessor.hxx:184-213)
+//   k_remap/k_release_slots/k_merge_free   particle copy by patch reference     (gridslamprocessor.hxx:184-213)
 //   k_normalize / k_resample       (gridslamprocessor.hxx:82-121, particlefilter.h:180-229)
 //   k_digest / k_export_* / k_export_occupancy / k_install_patches   map read-back, occupancy grid, upload
 #include <algorithm>
@@ -1257,8 +1257,10 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Particle copy by patch reference (gridslamprocessor.hxx:184-213: Particle copy -> HierarchicalArray2D
-// copy-ctor -> autoptr share++).  dir_alt[j] <- dir[idx[j]], new refcounts counted from scratch.
+// Particle copy by patch reference (gridslamprocessor.hxx:184-213: Particle copy -> HierarchicalArray2D copy-ctor -> autoptr
+// share++).  dir_alt[j] <- dir[idx[j]] and one more reference per patch; then the old generation's slots give theirs back
+// (k_release_slots).  References are counted incrementally -- never recounted from one context's directories -- because a
+// pool may be shared with clones of the filter (gm_clone), whose directories hold references too.
 __global__ void k_remap(RemapArgs A) {
     const unsigned j = blockIdx.x, src = A.idx[j];
     const Geom g = A.geom[src];
@@ -1267,18 +1269,29 @@ __global__ void k_remap(RemapArgs A) {
     for (int e = threadIdx.x; e < g.npx * g.npy; e += blockDim.x) {
         int id = s[e];
         d[e] = id;
-        if (id >= 0) atomicAdd(&A.refcnt_new[id], 1);
+        if (id >= 0) atomicAdd(&A.refcnt[id], 1);
     }
     if (threadIdx.x == 0) A.geom_alt[j] = g;
 }
-// patches nobody references any more go back to the free list
-__global__ void k_sweep(SweepArgs A) {
-    int id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= A.pool.cap) return;
-    int o = A.pool.refcnt[id], n = A.refcnt_new[id];
-    if (o > 0 && n == 0) A.pool.pending[atomicAdd(A.pool.pending_n, 1)] = id;
-    A.pool.refcnt[id] = n;
-    A.refcnt_new[id] = 0;
+// the references held by the directories of slots first .. first + gridDim.x - 1 are dropped (autoptr's destructor,
+// autoptr.h:42-53): a patch nobody references any more goes back to the free list (through `pending`)
+__global__ void k_release_slots(const Geom* __restrict__ geom, const int* __restrict__ dir, int dir_cap, unsigned first, Pool pool) {
+    const unsigned slot = first + blockIdx.x;
+    const Geom g = geom[slot];
+    const int* d = dir + (size_t)slot * dir_cap;
+    for (int e = threadIdx.x; e < g.npx * g.npy; e += blockDim.x) {
+        const int id = d[e];
+        if (id >= 0 && atomicSub(&pool.refcnt[id], 1) == 1) pool.pending[atomicAdd(pool.pending_n, 1)] = id;
+    }
+}
+// one more reference for every patch the directories of slots 0 .. gridDim.x - 1 point at (a clone takes its shares)
+__global__ void k_addref_slots(const Geom* __restrict__ geom, const int* __restrict__ dir, int dir_cap, Pool pool) {
+    const Geom g = geom[blockIdx.x];
+    const int* d = dir + (size_t)blockIdx.x * dir_cap;
+    for (int e = threadIdx.x; e < g.npx * g.npy; e += blockDim.x) {
+        const int id = d[e];
+        if (id >= 0) atomicAdd(&pool.refcnt[id], 1);
+    }
 }
 __global__ void k_merge_free(Pool pool) {
     int n = *pool.pending_n, top = *pool.free_top;
@@ -1310,6 +1323,8 @@ __global__ void k_recount_compare(Pool pool, int* __restrict__ recount, unsigned
 }
 void launch_recount(const Geom* geom, const int* dir, int dir_cap, const Pool& pool, int* recount, unsigned long long* out, unsigned n, cudaStream_t st) {
     k_recount<<<n, 256, 0, st>>>(geom, dir, dir_cap, pool.cap, recount, out);
+}
+void launch_recount_compare(const Pool& pool, int* recount, unsigned long long* out, cudaStream_t st) {
     k_recount_compare<<<(pool.cap + 255) / 256, 256, 0, st>>>(pool, recount, out);
 }
 
@@ -1533,7 +1548,12 @@ cudaError_t register_prepare(size_t smem) {
 }
 void launch_register(const RegisterArgs& a, unsigned n, size_t smem, cudaStream_t st) { k_register<<<n, kRegThreads, smem, st>>>(a); }
 void launch_remap(const RemapArgs& a, unsigned n, cudaStream_t st) { k_remap<<<n, 256, 0, st>>>(a); }
-void launch_sweep(const SweepArgs& a, cudaStream_t st) { k_sweep<<<(a.pool.cap + 255) / 256, 256, 0, st>>>(a); }
+void launch_release_slots(const Geom* geom, const int* dir, int dir_cap, unsigned first, unsigned count, const Pool& pool, cudaStream_t st) {
+    if (count) k_release_slots<<<count, 256, 0, st>>>(geom, dir, dir_cap, first, pool);
+}
+void launch_addref_slots(const Geom* geom, const int* dir, int dir_cap, unsigned count, const Pool& pool, cudaStream_t st) {
+    if (count) k_addref_slots<<<count, 256, 0, st>>>(geom, dir, dir_cap, pool);
+}
 void launch_merge_free(const Pool& p, cudaStream_t st) { k_merge_free<<<1, 1024, 0, st>>>(p); }
 void launch_pool_init(const Pool& p, cudaStream_t st) { k_pool_init<<<(p.cap + 255) / 256, 256, 0, st>>>(p); }
 void launch_fill_int(int* p, size_t n, int v, cudaStream_t st) { k_fill_int<<<1184, 256, 0, st>>>(p, n, v); }

@@ -56,9 +56,8 @@ struct RemapArgs {
     const unsigned* idx;
     const Geom* geom; Geom* geom_alt;
     const int* dir; int* dir_alt; int dir_cap;
-    int* refcnt_new;
+    int* refcnt;  // the pool's reference counts
 };
-struct SweepArgs { Pool pool; int* refcnt_new; };
 struct DigestArgs {
     const Geom* geom; const int* dir; int dir_cap; const int4* pool; const int* visits; const double2* means; const unsigned* occ;
     unsigned first; unsigned long long* out;  // 7 words per particle: the six of gm_digest + mismatching occupancy-bitmap rows
@@ -74,10 +73,12 @@ size_t register_smem_bytes(int bitmap_words, int sort_n, int nbeams, int tile_ca
 cudaError_t register_prepare(size_t smem);
 void launch_register(const RegisterArgs& a, unsigned n, size_t smem, cudaStream_t st);
 void launch_remap(const RemapArgs& a, unsigned n, cudaStream_t st);
-void launch_sweep(const SweepArgs& a, cudaStream_t st);
+void launch_release_slots(const Geom* geom, const int* dir, int dir_cap, unsigned first, unsigned count, const Pool& pool, cudaStream_t st);
+void launch_addref_slots(const Geom* geom, const int* dir, int dir_cap, unsigned count, const Pool& pool, cudaStream_t st);
 void launch_merge_free(const Pool& p, cudaStream_t st);
 void launch_pool_init(const Pool& p, cudaStream_t st);
 void launch_recount(const Geom* geom, const int* dir, int dir_cap, const Pool& pool, int* recount, unsigned long long* out, unsigned n, cudaStream_t st);
+void launch_recount_compare(const Pool& pool, int* recount, unsigned long long* out, cudaStream_t st);
 void launch_fill_int(int* p, size_t n, int v, cudaStream_t st);
 void launch_fill_geom(Geom* g, unsigned n, Geom v, cudaStream_t st);
 void launch_normalize(const double* logw, const double* rows, unsigned n, double gain, double* w, double* neff, cudaStream_t st);

@@ -168,6 +168,10 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     // (originX, originY) = world position of cell (0, 0)
     void exportOccupancyGrid(unsigned int particle, double occThresh, std::vector<signed char>& data, int& width, int& height,
                              double& originX, double& originY) const;
+    // the reference's MAP_CONSISTENCY_CHECK (gridfastslam/gridslamprocessor.cpp:82-143: every patch's share count against the
+    // number of particle maps that point at it) on the device: aborts with a message on any difference; returns the number of
+    // distinct patches the maps of this filter (and of its clones, which share the pool) reference
+    unsigned long long checkMapConsistency() const;
     // order-independent digests of the LOCAL particle maps (patches, cells, sum n, sum visits, hash of (cell, n, visits), hash of acc)
     std::vector<unsigned long long> mapDigests() const;
 

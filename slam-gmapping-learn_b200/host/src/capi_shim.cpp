@@ -135,6 +135,8 @@ void gmh_map_digests(void* hv, unsigned long long* out) {
     if (!d.empty()) memcpy(out, d.data(), sizeof(unsigned long long) * d.size());
 }
 
+unsigned long long gmh_check_maps(void* hv) { return static_cast<Handle*>(hv)->gsp->checkMapConsistency(); }
+
 // occupancy grid of one particle on the GPU; data has width*height bytes (query the size first with data == null)
 void gmh_occupancy_grid(void* hv, unsigned particle, double thresh, signed char* data, int* width, int* height, double* origin) {
     std::vector<signed char> buf;

@@ -759,6 +759,12 @@ void GridSlamProcessor::exportOccupancyGrid(unsigned int particle, double occThr
     originY = (0 - info.size_y2) * info.delta + info.center_y;
 }
 
+unsigned long long GridSlamProcessor::checkMapConsistency() const {
+    uint64_t bad = 0, used = 0;
+    m_device->check(gm_check_refcounts(m_device->h, &bad, &used), "gm_check_refcounts");
+    return used;
+}
+
 std::vector<unsigned long long> GridSlamProcessor::mapDigests() const {
     const size_t n = m_localCount;
     std::vector<gm_digest> d(n);

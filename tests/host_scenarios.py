@@ -69,8 +69,11 @@ def scenario_clone():
                           **{k: p[k] for k in hostapi.PARAM_ORDER})
     for i in range(12):
         a.process_scan(g.ranges[i], g.odom[i], g.stamps[i])
+    before = a.check_maps()
     b = a.clone()
     assert np.array_equal(a.state(), b.state()) and np.array_equal(a.map_digests(), b.map_digests())
+    # the clone is a second set of directories over the same patches: no patch was copied, every count is consistent
+    assert a.check_maps() == before and b.check_maps() == before
     saved = (ctypes.c_ushort * 3)(*libc.seed48((ctypes.c_ushort * 3)(0, 0, 0)).contents)  # read the drand48 state ...
     libc.seed48(saved)                                                                      # ... and put it back
     for i in range(12, 24):
@@ -81,6 +84,8 @@ def scenario_clone():
         b.process_scan(g.ranges[i], g.odom[i], g.stamps[i])
     assert np.array_equal(a.state(), b.state()), "clone diverged"
     assert np.array_equal(a.map_digests(), b.map_digests())
+    shared = a.check_maps()  # both filters wrote their own copies of the patches they touched (copy-on-write), counts still consistent
+    assert b.check_maps() == shared
     assert b.resamples() == resampled and a.neff() == b.neff()
     assert np.abs(a.state()[:, :3] - g.state[23][:, :3]).max() < 1e-4  # and both still follow the reference
     # occupancy grid of the best particle through the C++ API
@@ -90,7 +95,10 @@ def scenario_clone():
     x, y = g.state[23][a.best(), 0], g.state[23][a.best(), 1]
     assert grid[int(round((y + 100) / 0.05)), int(round((x + 100) / 0.05))] == 0  # the robot stands in free space
     assert a.occupancy(a.best(), x, y) < 0.1
-    a.close(); b.close()
+    b.close()  # the clone gives its references back; what only it referenced returns to the free list
+    alone = a.check_maps()
+    assert alone <= shared
+    a.close()
 
 
 def scenario_order():
