@@ -294,19 +294,20 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
     return found;
 }
 
-__device__ __noinline__ void sincos_cold(double t, double* s, double* c) { sincos(t, s, c); }
+__device__ __noinline__ double2 sincos_cold(double t) { double s, c; sincos(t, &s, &c); return make_double2(s, c); }  // (sin, cos), by value
 
-// the odometry prior of optimize() (scanmatcher.cpp:497-509); 1 unless the odometry reliabilities are set
-__device__ __noinline__ double odo_gain_of(double ang_rel, double lin_rel, const double* init, const double* cm) {
+// the odometry prior of optimize() (scanmatcher.cpp:497-509); 1 unless the odometry reliabilities are set.
+// (arguments by value: a pointer to a local array or to the kernel's parameter block would force either into local memory)
+__device__ __noinline__ double odo_gain_of(double ang_rel, double lin_rel, double ix, double iy, double it, double cx, double cy, double ct) {
     double odo_gain = 1;
     if (ang_rel > 0.) {
-        double dth = init[2] - cm[2];
+        double dth = it - ct;
         dth = atan2(sin(dth), cos(dth));
         dth *= dth;
         odo_gain *= exp(-ang_rel * dth);
     }
     if (lin_rel > 0.) {
-        double dx = init[0] - cm[0], dy = init[1] - cm[1];
+        double dx = ix - cx, dy = iy - cy;
         double drho = dx * dx + dy * dy;
         odo_gain *= exp(-lin_rel * drho);
     }
@@ -314,16 +315,18 @@ __device__ __noinline__ double odo_gain_of(double ang_rel, double lin_rel, const
 }
 
 // laser pose in the map frame (scanmatcher.h:177-180)
-__device__ __forceinline__ void laser_pose(const DevParams& P, double x, double y, double t, double& lx, double& ly, double& lt) {
-    if (P.laser_pose[0] == 0. && P.laser_pose[1] == 0.) {  // x + (c*0 - s*0) == x exactly
+__device__ __forceinline__ void laser_pose3(double lpx, double lpy, double lpt, double x, double y, double t, double& lx, double& ly, double& lt) {
+    if (lpx == 0. && lpy == 0.) {  // x + (c*0 - s*0) == x exactly
         lx = x; ly = y;
     } else {
-        double s, c;
-        sincos_cold(t, &s, &c);
-        lx = x + (c * P.laser_pose[0] - s * P.laser_pose[1]);
-        ly = y + (s * P.laser_pose[0] + c * P.laser_pose[1]);
+        const double2 sc = sincos_cold(t);
+        lx = x + (sc.y * lpx - sc.x * lpy);
+        ly = y + (sc.x * lpx + sc.y * lpy);
     }
-    lt = t + P.laser_pose[2];
+    lt = t + lpt;
+}
+__device__ __forceinline__ void laser_pose(const DevParams& P, double x, double y, double t, double& lx, double& ly, double& lt) {
+    laser_pose3(P.laser_pose[0], P.laser_pose[1], P.laser_pose[2], x, y, t, lx, ly, lt);
 }
 
 // beam i (counted from initialBeamsSkip) is evaluated iff the reference's `skip` counter wraps to 0
@@ -385,7 +388,7 @@ __device__ __forceinline__ void want_table(SmShared& S, int which, double theta,
 // gain included) is the previous currentScore, strictly below the present one, so it cannot win the `localScore >
 // currentScore` test of scanmatcher.cpp:510.  When that candidate is bit for bit the previous pose ((x + d) - d == x almost
 // always) it is counted but not evaluated.
-__device__ __noinline__ void plan_round(const DevParams& P, SmShared& S, int kind) {
+__device__ __noinline__ void plan_round(double lpx, double lpy, double lpt, SmShared& S, int kind) {
     const bool halved = S.bestScore >= S.currentScore;
     if (halved) { S.refinement++; S.adelta *= .5; S.ldelta *= .5; }
     S.bestScore = S.currentScore;
@@ -401,7 +404,7 @@ __device__ __noinline__ void plan_round(const DevParams& P, SmShared& S, int kin
         if (m == S.skip) continue;
         double cm[3], lx, ly, lt;
         candidate(S.cur, m, S.ldelta, S.adelta, cm);
-        laser_pose(P, cm[0], cm[1], cm[2], lx, ly, lt);
+        laser_pose3(lpx, lpy, lpt, cm[0], cm[1], cm[2], lx, ly, lt);
         S.lx[m] = lx; S.ly[m] = ly;
         if (m >= 4) turn_theta[m - 4] = lt;
         S.cand[nc++] = m;
@@ -559,7 +562,7 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
                 if (P.ang_rel > 0. || P.lin_rel > 0.) {
                     double cm[3];
                     candidate(S.cur, mm, S.ldelta, S.adelta, cm);
-                    odo_gain = odo_gain_of(P.ang_rel, P.lin_rel, S.init, cm);
+                    odo_gain = odo_gain_of(P.ang_rel, P.lin_rel, S.init[0], S.init[1], S.init[2], cm[0], cm[1], cm[2]);
                 }
                 const double localScore = odo_gain * S.red[mm];
                 if (localScore > S.currentScore) { S.currentScore = localScore; bm = mm; }
@@ -575,12 +578,12 @@ __global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
                     S.tab_of[0] = S.tab_of[bm - 3]; S.tab_of[bm - 3] = o;
                 }
             }
-            if (S.currentScore > S.bestScore || S.refinement < P.opt_iters) { plan_round(P, S, premul); continue; }
+            if (S.currentScore > S.bestScore || S.refinement < P.opt_iters) { plan_round(P.laser_pose[0], P.laser_pose[1], P.laser_pose[2], S, premul); continue; }
         } else if (S.phase == 0) {
             double v = 0.;
             for (int w = 0; w < kSmThreads / 32; w++) v += S.red[w];
             S.currentScore = v;
-            plan_round(P, S, premul);
+            plan_round(P.laser_pose[0], P.laser_pose[1], P.laser_pose[2], S, premul);
             continue;
         } else {
             // phase 2: likelihoodAndScore of the accepted pose; phase 3: standalone query
@@ -829,8 +832,18 @@ __device__ __forceinline__ int item_patches(int p0x, int p0y, int p1x, int p1y, 
     return 4;
 }
 
+// k_register comes in two shapes.  T8 = false: 1024 threads, one CTA per SM, 16-bit visit counters (a cell is crossed by at
+// most nbeams < 2048 rays), up to 112 tiles of 2 KB.  T8 = true: 512 threads, TWO CTAs per SM -- the kernel is a chain of
+// barrier-separated phases, several of them with little parallelism, and a second resident particle fills the issue slots
+// the first leaves idle -- with 8-bit counters, tiles of 1 KB.  Eight bits are enough away from the sensor: the rays that
+// cross a cell at Chebyshev distance i leave the sensor within an angular window of 3 / i rad, so with a minimum angular
+// spacing dtheta between beams at most 3 / (i dtheta) + 2 of them do; the host picks near_k such that this is below 200 for
+// i >= near_k (5 for 1081 beams at 0.25 deg), and the cells closer than near_k -- each ray's first near_k steps -- are
+// counted in a small window of 32-bit counters instead.  Beam tables without such a bound keep the 16-bit shape.
 constexpr int kRegThreads = 1024;
-constexpr int kTileWords = kPatchCells / 2;  // a tile counts visits of one patch: 1024 cells x 16 bit, two per word
+constexpr int kRegThreads8 = 512;
+constexpr int kNearMax = 16;  // largest near_k of the 8-bit shape: a window of 33 x 33 counters
+template <bool T8> struct TileFmt { static constexpr int words = T8 ? kPatchCells / 4 : kPatchCells / 2; };  // 32-bit words per tile
 // hit grouping (k_register phase 4), per unit of sort_n: 2 table keys (8 B) + 2 first + 2 last (4 B each) + 1 slot (4 B)
 constexpr int kHitBytes = 36;
 constexpr int kMaxTiles = 112;  // tiles that fit the 227 KB of shared memory a CTA can have
@@ -853,7 +866,9 @@ __device__ __forceinline__ RegSmem carve(unsigned char* raw, int bitmap_words, i
     return m;
 }
 
-__global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
+template <bool T8>
+__global__ void __launch_bounds__(T8 ? kRegThreads8 : kRegThreads, T8 ? 2 : 1) k_register(RegisterArgs A) {
+    constexpr int kTileWords = TileFmt<T8>::words;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevParams& P = A.P;
     const unsigned p = blockIdx.x;
@@ -871,6 +886,8 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
     __shared__ int s_nactive, s_nwork;
     __shared__ int s_tile_id[kMaxTiles];
     __shared__ int s_gitems[GM_MAXBEAMS_DEV / 32 + 2];  // prefix of the chunk counts of the groups of 32 neighbouring beams
+    __shared__ unsigned s_near[T8 ? (2 * kNearMax + 1) * (2 * kNearMax + 1) : 1];  // visit counts of the cells around the sensor
+    const int near_k = T8 ? A.near_k : 0, near_w = 2 * near_k + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 
     long long tph = clock64();
@@ -1075,6 +1092,8 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
     for (int first = 0; first < nactive && P.generate_map; first += A.tile_cap) {
         const int ntile = min(A.tile_cap, nactive - first);
         for (int i = threadIdx.x; i < ntile * kTileWords; i += blockDim.x) M.tiles[i] = 0u;
+        if (T8 && first == 0)
+            for (int i = threadIdx.x; i < near_w * near_w; i += blockDim.x) s_near[i] = 0u;
         if ((int)threadIdx.x < ntile) {  // patch of tile t: the directory entry of rank first + t, found from the prefix sums
             s_tile_id[threadIdx.x] = dirp[entry_of_rank(first + threadIdx.x)];
         }
@@ -1121,7 +1140,10 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
             const int smax = __reduce_max_sync(0xffffffffu, steps);
             for (int sidx = 0; sidx < smax; sidx++) {
                 int key = -1;
-                if (sidx < steps) {
+                if (T8 && i0 + sidx < near_k) {
+                    // the first near_k steps of every ray: the cells around the sensor, crossed by too many rays for 8 bits
+                    if (sidx < steps && first == 0) atomicAdd(&s_near[(x - p0x + near_k) * near_w + (y - p0y + near_k)], 1u);
+                } else if (sidx < steps) {
                     if (((x ^ lx) | (y ^ ly)) >> kPatchMag) {  // another patch
                         lx = x; ly = y; base = -1;
                         const int px = x >> kPatchMag, py = y >> kPatchMag;
@@ -1132,6 +1154,8 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
                         }
                     }
                     if (base >= 0) key = base | ((x & 31) << kPatchMag) | (y & 31);
+                }
+                if (sidx < steps) {
                     f += two_db;
                     const bool carry = f >= two_da;
                     f -= carry ? two_da : 0;
@@ -1143,7 +1167,8 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
                 if (head && key >= 0) {
                     const unsigned after = (heads >> lane) >> 1;  // (lane 31: nothing after)
                     const unsigned len = after ? (unsigned)__ffs(after) : 32u - (unsigned)lane;
-                    atomicAdd(M.tiles + (key >> 1), len << ((key & 1) << 4));
+                    if (T8) atomicAdd(M.tiles + (key >> 2), len << ((key & 3) << 3));
+                    else atomicAdd(M.tiles + (key >> 1), len << ((key & 1) << 4));
                 }
             }
         }
@@ -1168,7 +1193,7 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const int ci = g8 + 32 * k + lane;
-                c[k] = (tile[ci >> 1] >> ((ci & 1) << 4)) & 0xffffu;
+                c[k] = T8 ? (tile[ci >> 2] >> ((ci & 3) << 3)) & 0xffu : (tile[ci >> 1] >> ((ci & 1) << 4)) & 0xffffu;
                 v[k] = c[k] ? __ldcg(vis + ci) : 0;  // untouched cells cost no traffic
             }
 #pragma unroll
@@ -1176,6 +1201,7 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
                 const int ci = g8 + 32 * k + lane;
                 const int nvis = v[k] + (int)c[k];
                 if (c[k]) { vis[ci] = nvis; nfree += c[k]; }  // update(false) c times
+                if (T8 && c[k] >= 224u) atomicCAS(&A.counters->error, 0, -6);  // the 8-bit bound (<= 150 rays per cell) was wrong: say so
                 const unsigned roww = __shfl_sync(0xffffffffu, occ_old, k);
                 bool clear = false;
                 if (c[k] && ((roww >> lane) & 1u)) clear = !occ_default(__ldcg(cells + ci).z, nvis);
@@ -1183,6 +1209,24 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
                 if (lane == k) occ_new &= ~cleared;
             }
             if (occ_new != occ_old) occ[lane] = occ_new;
+        }
+        if (T8 && first == 0) {
+            __syncthreads();  // the tile flush above rewrites whole occupancy words: finish it before single bits are cleared here
+            // the window around the sensor: a thread per cell; its patch is active (the sensor's ray cells are) and private by now
+            for (int i = threadIdx.x; i < near_w * near_w; i += blockDim.x) {
+                const unsigned cnt = s_near[i];
+                if (!cnt) continue;
+                const int x = p0x - near_k + i / near_w, y = p0y - near_k + i % near_w;
+                if (x < 0 || y < 0 || (x >> kPatchMag) >= g.npx || (y >> kPatchMag) >= g.npy) continue;
+                const int id = dirp[(x >> kPatchMag) * g.npy + (y >> kPatchMag)];
+                if (id < 0) continue;
+                const size_t ci = (size_t)id * kPatchCells + ((x & 31) << kPatchMag) + (y & 31);
+                const int nvis = __ldcg(A.pool.visits + ci) + (int)cnt;
+                A.pool.visits[ci] = nvis;
+                nfree += cnt;
+                unsigned* w = A.pool.occ + (size_t)id * kPatch + (x & 31);
+                if (((__ldcg(w) >> (y & 31)) & 1u) && !occ_default(__ldcg(A.pool.cells + ci).z, nvis)) atomicAnd(w, ~(1u << (y & 31)));
+            }
         }
         __syncthreads();
         PHASE(5);
@@ -1538,15 +1582,20 @@ void launch_scanmatch(const ScanMatchArgs& a, unsigned n, cudaStream_t st) {
 void launch_bounds(const BoundsArgs& a, unsigned n, unsigned threads, cudaStream_t st) { k_bounds<<<n, threads, 0, st>>>(a); }
 void launch_relayout(const RelayoutArgs& a, unsigned n, cudaStream_t st) { k_relayout<<<n, 256, 0, st>>>(a); }
 void launch_relayout_commit(const RelayoutArgs& a, unsigned n, cudaStream_t st) { k_relayout_commit<<<n, 256, 0, st>>>(a); }
-size_t register_smem_bytes(int bitmap_words, int sort_n, int nbeams, int tile_cap) {
-    const size_t tiles = std::max((size_t)tile_cap * kTileWords * 4, (size_t)sort_n * kHitBytes);  // the hit table reuses the tile area
+// tile_bytes: 2048 (16-bit counters) or 1024 (8-bit)
+size_t register_smem_bytes(int bitmap_words, int sort_n, int nbeams, int tile_cap, int tile_bytes) {
+    const size_t tiles = std::max((size_t)tile_cap * tile_bytes, (size_t)sort_n * kHitBytes);  // the hit table reuses the tile area
     return align16((size_t)bitmap_words * 4) + align16((size_t)bitmap_words * 2) + align16((size_t)nbeams * sizeof(BeamRec)) +
            align16((size_t)(nbeams + 1) * 4) + tiles;
 }
-cudaError_t register_prepare(size_t smem) {
-    return cudaFuncSetAttribute(k_register, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t register_prepare(size_t smem, bool tiles8) {
+    return tiles8 ? cudaFuncSetAttribute(k_register<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                  : cudaFuncSetAttribute(k_register<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
-void launch_register(const RegisterArgs& a, unsigned n, size_t smem, cudaStream_t st) { k_register<<<n, kRegThreads, smem, st>>>(a); }
+void launch_register(const RegisterArgs& a, unsigned n, size_t smem, bool tiles8, cudaStream_t st) {
+    if (tiles8) k_register<true><<<n, kRegThreads8, smem, st>>>(a);
+    else k_register<false><<<n, kRegThreads, smem, st>>>(a);
+}
 void launch_remap(const RemapArgs& a, unsigned n, cudaStream_t st) { k_remap<<<n, 256, 0, st>>>(a); }
 void launch_release_slots(const Geom* geom, const int* dir, int dir_cap, unsigned first, unsigned count, const Pool& pool, cudaStream_t st) {
     if (count) k_release_slots<<<count, 256, 0, st>>>(geom, dir, dir_cap, first, pool);
