@@ -176,21 +176,6 @@ int gm_set_laser(gm_ctx* ctx, uint32_t nbeams, const double* angles, const doubl
     for (int i = 0; i < 3; i++) ctx->P.laser_pose[i] = laser_pose[i];
     CK(cudaMemcpyAsync(ctx->d_angles, angles, sizeof(double) * nbeams, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
-    {
-        // k_register's 8-bit shape: with a smallest angular spacing dtheta between two beams, at most 4 / (i dtheta) + 2 rays
-        // cross a cell at Chebyshev distance i from the sensor (1 / i for the cell itself, the rest for the rounding of both
-        // end points to cell centres); near_k = the distance from which that is below 150.  0: no bound (coincident beams)
-        std::vector<double> a(angles, angles + nbeams);
-        std::sort(a.begin(), a.end());
-        double dmin = 1e300;
-        for (uint32_t i = 1; i < nbeams; i++) dmin = std::min(dmin, a[i] - a[i - 1]);
-        ctx->near_k = 0;
-        if (nbeams < 2) ctx->near_k = 2;
-        else if (dmin > 0 && std::isfinite(dmin)) {
-            const double k = std::ceil(4.0 / (148.0 * dmin));
-            ctx->near_k = k <= 16 ? std::max(2, (int)k) : 0;  // 16 = kNearMax of k_register
-        }
-    }
     ctx->laser_set = true;
     return GM_OK;
 }
@@ -525,24 +510,17 @@ int gmi_register_update(gm_ctx* ctx) {
     int sort_n = 64;  // power of two >= nbeams: sizes the hit table of k_register
     while (sort_n < (int)ctx->P.nbeams) sort_n <<= 1;
     a.sort_n = sort_n;
-    // The kernel's shape (gm_kernels.cu): two 512-thread CTAs per SM with 8-bit visit counters when the beam table bounds the
-    // rays per cell (near_k, from the smallest angular spacing) and everything fits half an SM's shared memory; else one
-    // 1024-thread CTA per SM with 16-bit counters.  Visit-count tiles: as many as fit (one pass over the rays when the active
-    // area has at most that many patches).  GM_B200_REGISTER_SHAPE = 8 | 16 and GM_B200_REGISTER_TILES override (tests).
-    const size_t fixed = register_smem_bytes(a.bitmap_words, 0, (int)ctx->P.nbeams, 0, 0);
-    const size_t hits = (size_t)a.sort_n * 36;
-    const size_t budget8 = 110 * 1024, budget16 = 220 * 1024;  // of the 227 KB an SM has for one or two CTAs
-    bool tiles8 = ctx->near_k > 0 && fixed + std::max(hits, (size_t)48 * 1024) <= budget8;
-    if (const char* e = getenv("GM_B200_REGISTER_SHAPE")) tiles8 = tiles8 && atoi(e) != 16;
-    const size_t budget = tiles8 ? budget8 : budget16;
-    if (fixed + hits > budget) return fail(ctx, GM_ERR_ARG, "gm_register: patch directory of %d entries needs %zu B of shared memory", ctx->dir_cap, fixed);
-    int tile_cap = std::min(112, (int)((budget - fixed) / (tiles8 ? 1024 : 2048)));  // 112 = kMaxTiles of k_register
+    // visit-count tiles: as many as fit (one pass over the rays when the active area has at most that many patches);
+    // GM_B200_REGISTER_TILES caps them (tests of the multi-pass path)
+    const size_t fixed = register_smem_bytes(a.bitmap_words, 0, (int)ctx->P.nbeams, 0);
+    const size_t budget = 220 * 1024;  // of the 227 KB a CTA may use
+    if (fixed + (size_t)a.sort_n * 36 > budget) return fail(ctx, GM_ERR_ARG, "gm_register: patch directory of %d entries needs %zu B of shared memory", ctx->dir_cap, fixed);
+    int tile_cap = std::min(112, (int)((budget - fixed) / 2048));  // 112 = kMaxTiles of k_register
     if (const char* e = getenv("GM_B200_REGISTER_TILES")) tile_cap = std::max(1, std::min(tile_cap, atoi(e)));
     a.tile_cap = tile_cap;
-    a.near_k = tiles8 ? ctx->near_k : 0;
-    const size_t smem = register_smem_bytes(a.bitmap_words, a.sort_n, (int)ctx->P.nbeams, tile_cap, tiles8 ? 1024 : 2048);
-    if (smem != ctx->register_smem || tiles8 != ctx->register_tiles8) { CK(register_prepare(smem, tiles8)); ctx->register_smem = smem; ctx->register_tiles8 = tiles8; }
-    launch_register(a, n, smem, tiles8, ctx->st);
+    const size_t smem = register_smem_bytes(a.bitmap_words, a.sort_n, (int)ctx->P.nbeams, tile_cap);
+    if (smem != ctx->register_smem) { CK(register_prepare(smem)); ctx->register_smem = smem; }
+    launch_register(a, n, smem, ctx->st);
     launch_merge_free(ctx->pool, ctx->st);
     CK(cudaEventRecord(ctx->ev1, ctx->st));
     ctx->stats.launches += 2;

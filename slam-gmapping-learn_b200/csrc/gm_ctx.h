@@ -59,8 +59,7 @@ struct gm_ctx {
 
     gm_stats stats{};
     std::string err;
-    size_t register_smem = 0; bool register_tiles8 = false;
-    int near_k = 0;  // k_register's 8-bit shape: rays' first near_k steps go to the near-sensor window (0: 16-bit shape only)
+    size_t register_smem = 0;
     signed char* d_occ = nullptr; size_t occ_cap = 0;  // gm_export_occupancy staging
     bool async_register = false, reg_pending = false;  // gm_set_async_register: a registration may still be running
     int reg_tile_cap = 0;

@@ -832,18 +832,8 @@ __device__ __forceinline__ int item_patches(int p0x, int p0y, int p1x, int p1y, 
     return 4;
 }
 
-// k_register comes in two shapes.  T8 = false: 1024 threads, one CTA per SM, 16-bit visit counters (a cell is crossed by at
-// most nbeams < 2048 rays), up to 112 tiles of 2 KB.  T8 = true: 512 threads, TWO CTAs per SM -- the kernel is a chain of
-// barrier-separated phases, several of them with little parallelism, and a second resident particle fills the issue slots
-// the first leaves idle -- with 8-bit counters, tiles of 1 KB.  Eight bits are enough away from the sensor: the rays that
-// cross a cell at Chebyshev distance i leave the sensor within an angular window of 3 / i rad, so with a minimum angular
-// spacing dtheta between beams at most 3 / (i dtheta) + 2 of them do; the host picks near_k such that this is below 200 for
-// i >= near_k (5 for 1081 beams at 0.25 deg), and the cells closer than near_k -- each ray's first near_k steps -- are
-// counted in a small window of 32-bit counters instead.  Beam tables without such a bound keep the 16-bit shape.
 constexpr int kRegThreads = 1024;
-constexpr int kRegThreads8 = 512;
-constexpr int kNearMax = 16;  // largest near_k of the 8-bit shape: a window of 33 x 33 counters
-template <bool T8> struct TileFmt { static constexpr int words = T8 ? kPatchCells / 4 : kPatchCells / 2; };  // 32-bit words per tile
+constexpr int kTileWords = kPatchCells / 2;  // a tile counts visits of one patch: 1024 cells x 16 bit, two per word
 // hit grouping (k_register phase 4), per unit of sort_n: 2 table keys (8 B) + 2 first + 2 last (4 B each) + 1 slot (4 B)
 constexpr int kHitBytes = 36;
 constexpr int kMaxTiles = 112;  // tiles that fit the 227 KB of shared memory a CTA can have
@@ -866,9 +856,7 @@ __device__ __forceinline__ RegSmem carve(unsigned char* raw, int bitmap_words, i
     return m;
 }
 
-template <bool T8>
-__global__ void __launch_bounds__(T8 ? kRegThreads8 : kRegThreads, T8 ? 2 : 1) k_register(RegisterArgs A) {
-    constexpr int kTileWords = TileFmt<T8>::words;
+__global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevParams& P = A.P;
     const unsigned p = blockIdx.x;
@@ -886,8 +874,6 @@ __global__ void __launch_bounds__(T8 ? kRegThreads8 : kRegThreads, T8 ? 2 : 1) k
     __shared__ int s_nactive, s_nwork;
     __shared__ int s_tile_id[kMaxTiles];
     __shared__ int s_gitems[GM_MAXBEAMS_DEV / 32 + 2];  // prefix of the chunk counts of the groups of 32 neighbouring beams
-    __shared__ unsigned s_near[T8 ? (2 * kNearMax + 1) * (2 * kNearMax + 1) : 1];  // visit counts of the cells around the sensor
-    const int near_k = T8 ? A.near_k : 0, near_w = 2 * near_k + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 
     long long tph = clock64();
@@ -1092,8 +1078,6 @@ __global__ void __launch_bounds__(T8 ? kRegThreads8 : kRegThreads, T8 ? 2 : 1) k
     for (int first = 0; first < nactive && P.generate_map; first += A.tile_cap) {
         const int ntile = min(A.tile_cap, nactive - first);
         for (int i = threadIdx.x; i < ntile * kTileWords; i += blockDim.x) M.tiles[i] = 0u;
-        if (T8 && first == 0)
-            for (int i = threadIdx.x; i < near_w * near_w; i += blockDim.x) s_near[i] = 0u;
         if ((int)threadIdx.x < ntile) {  // patch of tile t: the directory entry of rank first + t, found from the prefix sums
             s_tile_id[threadIdx.x] = dirp[entry_of_rank(first + threadIdx.x)];
         }
@@ -1140,10 +1124,7 @@ __global__ void __launch_bounds__(T8 ? kRegThreads8 : kRegThreads, T8 ? 2 : 1) k
             const int smax = __reduce_max_sync(0xffffffffu, steps);
             for (int sidx = 0; sidx < smax; sidx++) {
                 int key = -1;
-                if (T8 && i0 + sidx < near_k) {
-                    // the first near_k steps of every ray: the cells around the sensor, crossed by too many rays for 8 bits
-                    if (sidx < steps && first == 0) atomicAdd(&s_near[(x - p0x + near_k) * near_w + (y - p0y + near_k)], 1u);
-                } else if (sidx < steps) {
+                if (sidx < steps) {
                     if (((x ^ lx) | (y ^ ly)) >> kPatchMag) {  // another patch
                         lx = x; ly = y; base = -1;
                         const int px = x >> kPatchMag, py = y >> kPatchMag;
@@ -1154,8 +1135,6 @@ __global__ void __launch_bounds__(T8 ? kRegThreads8 : kRegThreads, T8 ? 2 : 1) k
                         }
                     }
                     if (base >= 0) key = base | ((x & 31) << kPatchMag) | (y & 31);
-                }
-                if (sidx < steps) {
                     f += two_db;
                     const bool carry = f >= two_da;
                     f -= carry ? two_da : 0;
@@ -1167,8 +1146,7 @@ __global__ void __launch_bounds__(T8 ? kRegThreads8 : kRegThreads, T8 ? 2 : 1) k
                 if (head && key >= 0) {
                     const unsigned after = (heads >> lane) >> 1;  // (lane 31: nothing after)
                     const unsigned len = after ? (unsigned)__ffs(after) : 32u - (unsigned)lane;
-                    if (T8) atomicAdd(M.tiles + (key >> 2), len << ((key & 3) << 3));
-                    else atomicAdd(M.tiles + (key >> 1), len << ((key & 1) << 4));
+                    atomicAdd(M.tiles + (key >> 1), len << ((key & 1) << 4));
                 }
             }
         }
@@ -1193,7 +1171,7 @@ __global__ void __launch_bounds__(T8 ? kRegThreads8 : kRegThreads, T8 ? 2 : 1) k
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const int ci = g8 + 32 * k + lane;
-                c[k] = T8 ? (tile[ci >> 2] >> ((ci & 3) << 3)) & 0xffu : (tile[ci >> 1] >> ((ci & 1) << 4)) & 0xffffu;
+                c[k] = (tile[ci >> 1] >> ((ci & 1) << 4)) & 0xffffu;
                 v[k] = c[k] ? __ldcg(vis + ci) : 0;  // untouched cells cost no traffic
             }
 #pragma unroll
@@ -1201,7 +1179,6 @@ __global__ void __launch_bounds__(T8 ? kRegThreads8 : kRegThreads, T8 ? 2 : 1) k
                 const int ci = g8 + 32 * k + lane;
                 const int nvis = v[k] + (int)c[k];
                 if (c[k]) { vis[ci] = nvis; nfree += c[k]; }  // update(false) c times
-                if (T8 && c[k] >= 224u) atomicCAS(&A.counters->error, 0, -6);  // the 8-bit bound (<= 150 rays per cell) was wrong: say so
                 const unsigned roww = __shfl_sync(0xffffffffu, occ_old, k);
                 bool clear = false;
                 if (c[k] && ((roww >> lane) & 1u)) clear = !occ_default(__ldcg(cells + ci).z, nvis);
@@ -1209,24 +1186,6 @@ __global__ void __launch_bounds__(T8 ? kRegThreads8 : kRegThreads, T8 ? 2 : 1) k
                 if (lane == k) occ_new &= ~cleared;
             }
             if (occ_new != occ_old) occ[lane] = occ_new;
-        }
-        if (T8 && first == 0) {
-            __syncthreads();  // the tile flush above rewrites whole occupancy words: finish it before single bits are cleared here
-            // the window around the sensor: a thread per cell; its patch is active (the sensor's ray cells are) and private by now
-            for (int i = threadIdx.x; i < near_w * near_w; i += blockDim.x) {
-                const unsigned cnt = s_near[i];
-                if (!cnt) continue;
-                const int x = p0x - near_k + i / near_w, y = p0y - near_k + i % near_w;
-                if (x < 0 || y < 0 || (x >> kPatchMag) >= g.npx || (y >> kPatchMag) >= g.npy) continue;
-                const int id = dirp[(x >> kPatchMag) * g.npy + (y >> kPatchMag)];
-                if (id < 0) continue;
-                const size_t ci = (size_t)id * kPatchCells + ((x & 31) << kPatchMag) + (y & 31);
-                const int nvis = __ldcg(A.pool.visits + ci) + (int)cnt;
-                A.pool.visits[ci] = nvis;
-                nfree += cnt;
-                unsigned* w = A.pool.occ + (size_t)id * kPatch + (x & 31);
-                if (((__ldcg(w) >> (y & 31)) & 1u) && !occ_default(__ldcg(A.pool.cells + ci).z, nvis)) atomicAnd(w, ~(1u << (y & 31)));
-            }
         }
         __syncthreads();
         PHASE(5);
@@ -1582,20 +1541,15 @@ void launch_scanmatch(const ScanMatchArgs& a, unsigned n, cudaStream_t st) {
 void launch_bounds(const BoundsArgs& a, unsigned n, unsigned threads, cudaStream_t st) { k_bounds<<<n, threads, 0, st>>>(a); }
 void launch_relayout(const RelayoutArgs& a, unsigned n, cudaStream_t st) { k_relayout<<<n, 256, 0, st>>>(a); }
 void launch_relayout_commit(const RelayoutArgs& a, unsigned n, cudaStream_t st) { k_relayout_commit<<<n, 256, 0, st>>>(a); }
-// tile_bytes: 2048 (16-bit counters) or 1024 (8-bit)
-size_t register_smem_bytes(int bitmap_words, int sort_n, int nbeams, int tile_cap, int tile_bytes) {
-    const size_t tiles = std::max((size_t)tile_cap * tile_bytes, (size_t)sort_n * kHitBytes);  // the hit table reuses the tile area
+size_t register_smem_bytes(int bitmap_words, int sort_n, int nbeams, int tile_cap) {
+    const size_t tiles = std::max((size_t)tile_cap * kTileWords * 4, (size_t)sort_n * kHitBytes);  // the hit table reuses the tile area
     return align16((size_t)bitmap_words * 4) + align16((size_t)bitmap_words * 2) + align16((size_t)nbeams * sizeof(BeamRec)) +
            align16((size_t)(nbeams + 1) * 4) + tiles;
 }
-cudaError_t register_prepare(size_t smem, bool tiles8) {
-    return tiles8 ? cudaFuncSetAttribute(k_register<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                  : cudaFuncSetAttribute(k_register<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t register_prepare(size_t smem) {
+    return cudaFuncSetAttribute(k_register, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
-void launch_register(const RegisterArgs& a, unsigned n, size_t smem, bool tiles8, cudaStream_t st) {
-    if (tiles8) k_register<true><<<n, kRegThreads8, smem, st>>>(a);
-    else k_register<false><<<n, kRegThreads, smem, st>>>(a);
-}
+void launch_register(const RegisterArgs& a, unsigned n, size_t smem, cudaStream_t st) { k_register<<<n, kRegThreads, smem, st>>>(a); }
 void launch_remap(const RemapArgs& a, unsigned n, cudaStream_t st) { k_remap<<<n, 256, 0, st>>>(a); }
 void launch_release_slots(const Geom* geom, const int* dir, int dir_cap, unsigned first, unsigned count, const Pool& pool, cudaStream_t st) {
     if (count) k_release_slots<<<count, 256, 0, st>>>(geom, dir, dir_cap, first, pool);

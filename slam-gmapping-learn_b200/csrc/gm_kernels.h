@@ -51,7 +51,6 @@ struct RegisterArgs {
     Counters* counters;
     int bitmap_words, sort_n;
     int tile_cap;  // visit-count tiles (active patches) per pass of the free-space update
-    int near_k;    // 8-bit tiles: rays' first near_k steps are counted in a window of 32-bit counters around the sensor
 };
 struct RemapArgs {
     const unsigned* idx;
@@ -70,9 +69,9 @@ void launch_scanmatch(const ScanMatchArgs& a, unsigned n, cudaStream_t st);
 void launch_bounds(const BoundsArgs& a, unsigned n, unsigned threads, cudaStream_t st);
 void launch_relayout(const RelayoutArgs& a, unsigned n, cudaStream_t st);
 void launch_relayout_commit(const RelayoutArgs& a, unsigned n, cudaStream_t st);
-size_t register_smem_bytes(int bitmap_words, int sort_n, int nbeams, int tile_cap, int tile_bytes);
-cudaError_t register_prepare(size_t smem, bool tiles8);
-void launch_register(const RegisterArgs& a, unsigned n, size_t smem, bool tiles8, cudaStream_t st);
+size_t register_smem_bytes(int bitmap_words, int sort_n, int nbeams, int tile_cap);
+cudaError_t register_prepare(size_t smem);
+void launch_register(const RegisterArgs& a, unsigned n, size_t smem, cudaStream_t st);
 void launch_remap(const RemapArgs& a, unsigned n, cudaStream_t st);
 void launch_release_slots(const Geom* geom, const int* dir, int dir_cap, unsigned first, unsigned count, const Pool& pool, cudaStream_t st);
 void launch_addref_slots(const Geom* geom, const int* dir, int dir_cap, unsigned count, const Pool& pool, cudaStream_t st);

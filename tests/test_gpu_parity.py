@@ -37,21 +37,11 @@ def check_maps(ctx, f, want_rows, what):
         np.testing.assert_allclose(a1, a2, rtol=1e-6, atol=1e-5, err_msg="%s: acc of particle %d" % (what, j))
 
 
-@pytest.mark.parametrize("shape", ["8", "16"])
-def test_teacher_forced_trace_with_few_visit_tiles(monkeypatch, shape):
+def test_teacher_forced_trace_with_few_visit_tiles(monkeypatch):
     """the same trace with room for 24 visit tiles only: the active area no longer fits one pass, so the multi-pass ray
-    counting (and the chunked copy-on-write work list) must give the same maps -- in both shapes of k_register"""
+    counting (and the chunked copy-on-write work list) must give the same maps"""
     monkeypatch.setenv("GM_B200_REGISTER_TILES", "24")
-    monkeypatch.setenv("GM_B200_REGISTER_SHAPE", shape)
     test_teacher_forced_trace("room1081_n8")
-
-
-@pytest.mark.parametrize("case", ["room1081_n8", "room181_resize", "room181_d025"])
-def test_teacher_forced_trace_with_16_bit_tiles(monkeypatch, case):
-    """k_register's other shape (one 1024-thread CTA per SM, 16-bit visit counters: what beam tables without a bound on the
-    rays per cell get) must write the same maps as the default 8-bit shape the other tests run"""
-    monkeypatch.setenv("GM_B200_REGISTER_SHAPE", "16")
-    test_teacher_forced_trace(case)
 
 
 @pytest.mark.parametrize("case", CASES)

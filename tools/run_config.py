@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--noise", type=float, default=0.01, help="motion noise srr=srt=str=stt")
     ap.add_argument("--ogain", type=float, default=3.0, help="likelihood gain (obsSigmaGain): small values spread the weights and force real resampling")
     ap.add_argument("--resample-threshold", type=float, default=0.5, help="resample when Neff < threshold * N (> 1: every scan)")
+    ap.add_argument("--steady", action="store_true", help="do not read the statistics after every scan (that completes the registration "
+                    "in flight): wall_ms_per_scan_after_setup is then the steady-state wall clock, the per-stage means come from running totals")
     args = ap.parse_args()
     import torch
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -64,7 +66,8 @@ def main():
         if i == 3:  # scans 0-2 carry one-off costs: registration only, NCCL connection set-up, first pool growth
             torch.cuda.synchronize(); t_steady = time.perf_counter()
         proc.process_scan(log.ranges[i], log.odom[i], log.stamps[i])
-        stats.append(proc.stats())  # (completes the registration in flight: this tool does not measure the overlap, bench.py does)
+        if not args.steady or i == 2 or i == args.scans - 1:
+            stats.append(proc.stats())  # (completes the registration in flight)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     wall_steady = (time.perf_counter() - t_steady) / (args.scans - 3) if t_steady is not None and args.scans > 3 else None
@@ -73,6 +76,10 @@ def main():
     truth_err = float(np.hypot(*(st[best, :2] - log.truth[-1, :2])))
     free_b, total_b = torch.cuda.mem_get_info()
     keys = ("ms_scanmatch", "ms_weights", "ms_remap", "ms_register", "ms_migrate", "ms_allgather")
+    if args.steady:  # two snapshots (after scan 2, after the last scan): per-stage means from the running totals
+        a, b = stats[0], stats[-1]
+        mean = {k: (b["total_" + k] - a["total_" + k]) / max(1, args.scans - 3) for k in keys}
+        stats = [None, None, None, dict(b, **mean)]
     out = {"config": args.config, "rank": rank, "world": world, "particles": c["particles"], "beams": log.laser.beams, "delta": c["delta"],
            "scans": args.scans, "resamples": proc.resamples(), "wall_ms_per_scan": 1000 * wall / args.scans,
            "wall_ms_per_scan_after_setup": None if wall_steady is None else 1000 * wall_steady,
@@ -81,8 +88,8 @@ def main():
            "migrate_ms_median_when_resampling": float(np.median([s["ms_migrate"] for s in stats[3:] if s["ms_migrate"] > 0] or [0.0])),  # scans 0-2: registration only / NCCL connection setup
            "stage_ms": {k[3:]: float(np.mean([s[k] for s in stats[3:]])) for k in keys},
            "pool_patches_in_use": stats[-1]["pool_in_use"], "patches_per_particle": stats[-1]["pool_in_use"] / max(1, (proc.local_range()[1] - proc.local_range()[0])),
-           "hbm_used_gb": (total_b - free_b) / 2**30, "migrated_particles": float(np.sum([s["migrated_particles"] for s in stats])),
-           "migrated_mb": float(np.sum([s["migrated_bytes"] for s in stats])) / 2**20, "neff_last": proc.neff(),
+           "hbm_used_gb": (total_b - free_b) / 2**30, "migrated_particles": float(stats[-1]["total_migrated_particles"]),
+           "migrated_mb": float(stats[-1]["total_migrated_bytes"]) / 2**20, "neff_last": proc.neff(),
            "distinct_parents_last": int(len(set(proc.indexes().tolist()))) if proc.resamples() else None,
            "best_particle_error_m": truth_err}
     if dist is not None:
