@@ -223,6 +223,12 @@ int gm_clone(gm_ctx* src, gm_ctx** out);
  * device-side errors (pool exhausted) of that registration are reported by the NEXT call on the context -- every entry
  * point first collects a pending registration -- or by gm_synchronize.  Default: off (every call is complete at return). */
 int gm_set_async_register(gm_ctx* ctx, int on);
+/* With on != 0, gm_scanmatch_weights also registers the scan in every local particle at its scan-matched pose -- what
+ * gm_register(ranges, matched poses, NULL) would do, i.e. the caller registers FIRST and copies resampled particles afterwards
+ * (gm_copy_particles) -- queued on the device right behind the scan match, while the weights are normalised and handed to the
+ * host on a second stream: on a sharded context the wait for the other ranks' rows is then hidden behind the registration.
+ * The registration is collected like an asynchronous one (by the next entry point or gm_synchronize).  Default: off. */
+int gm_set_fused_register(gm_ctx* ctx, int on);
 int gm_synchronize(gm_ctx* ctx);
 
 int gm_get_stats(gm_ctx* ctx, gm_stats* out);

@@ -54,6 +54,7 @@ static int create_ctx(gm_ctx** out, const gm_config* cfg, gm_ctx* share_with) {
         CKC(cudaStreamCreateWithPriority(&c->st_w, cudaStreamNonBlocking, hi));
     }
     CKC(cudaEventCreate(&c->ev0)); CKC(cudaEventCreate(&c->ev1)); CKC(cudaEventCreate(&c->evw0)); CKC(cudaEventCreate(&c->evw1));
+    CKC(cudaEventCreate(&c->evr0)); CKC(cudaEventCreate(&c->evr1)); CKC(cudaEventCreateWithFlags(&c->ev_sm, cudaEventDisableTiming));
     size_t cap = cfg->pool_patches;
     if (share_with) {
         c->pool = share_with->pool;
@@ -90,6 +91,7 @@ static int create_ctx(gm_ctx** out, const gm_config* cfg, gm_ctx* share_with) {
     CKC(dalloc(c->d_score, N)); CKC(dalloc(c->d_s, N)); CKC(dalloc(c->d_l, N));
     CKC(dalloc(c->d_c, N)); CKC(dalloc(c->d_evals, N)); CKC(dalloc(c->d_idx, N)); CKC(dalloc(c->d_emitted, 1));
     CKC(dalloc(c->d_counters, 1));
+    CKC(dalloc(c->d_counters_sm, 1));
     CKC(dalloc(c->d_rows, (size_t)c->weights_cap * 5));
     CKC(dalloc(c->d_done, 1));
     CKC(cudaMemsetAsync(c->d_done, 0, sizeof(unsigned), c->st));
@@ -151,12 +153,15 @@ int gm_destroy(gm_ctx* c) {
     cudaFree(c->d_c); cudaFree(c->d_evals); cudaFree(c->d_idx); cudaFree(c->d_emitted);
     cudaFree(c->d_w); cudaFree(c->d_widx); cudaFree(c->d_logw); cudaFree(c->d_cum); cudaFree(c->d_tgt); cudaFree(c->d_neff);
     cudaFree(c->d_qidx); cudaFree(c->d_qposes); cudaFree(c->d_qposes_out); cudaFree(c->d_qs); cudaFree(c->d_ql); cudaFree(c->d_qc);
-    cudaFree(c->d_rows); cudaFree(c->d_done);
+    cudaFree(c->d_rows); cudaFree(c->d_done); cudaFree(c->d_counters_sm);
     if (c->h_in) cudaFreeHost(c->h_in);
     if (c->h_out) cudaFreeHost(c->h_out);
     cudaFree(c->d_occ); cudaFree(c->d_counters); cudaFree(c->d_inv_n); cudaFree(c->d_digest); cudaFree(c->d_list); cudaFree(c->d_count); cudaFree(c->d_export);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->evr0) cudaEventDestroy(c->evr0);
+    if (c->evr1) cudaEventDestroy(c->evr1);
+    if (c->ev_sm) cudaEventDestroy(c->ev_sm);
     if (c->st && last) cudaStreamDestroy(c->st);
     if (c->st_w) cudaStreamDestroy(c->st_w);
     if (c->evw0) cudaEventDestroy(c->evw0);
@@ -337,12 +342,12 @@ int gm_scanmatch_weights(gm_ctx* ctx, const double* ranges, const double* poses_
     CK(cudaMemcpyAsync(ctx->d_ranges, hin, sizeof(double) * nb, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemcpyAsync(ctx->d_poses, hin + nb, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemcpyAsync(ctx->d_logw, hin + nb + 3 * (size_t)n, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->st));
-    if (int r = zero_counters(ctx)) return r;
+    CK(cudaMemsetAsync(ctx->d_counters_sm, 0, sizeof(Counters), ctx->st));
     a.P = ctx->P; a.ranges = ctx->d_ranges; a.angles = ctx->d_angles; a.poses = ctx->d_poses;
     a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.visits = ctx->pool.visits; a.means = ctx->pool.means; a.occ = ctx->pool.occ; a.inv_n = ctx->d_inv_n;
     a.minimum_score = minimum_score;
     a.score = ctx->d_score; a.s = ctx->d_s; a.l = ctx->d_l; a.c = ctx->d_c; a.evals = ctx->d_evals;
-    a.counters = ctx->d_counters;
+    a.counters = ctx->d_counters_sm;
     a.zero_patch = ctx->pool.cap;
     derive_params(a.P);
     a.valid_score_beams = count_score_beams(ctx, ranges);
@@ -352,20 +357,37 @@ int gm_scanmatch_weights(gm_ctx* ctx, const double* ranges, const double* poses_
     CK(cudaEventRecord(ctx->ev1, ctx->st));
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_scanmatch")) return r;
+    // the weights take the other stream from here: with gm_set_fused_register the registration of this scan is queued right
+    // behind the scan match (the matched poses and the scan are on the device already) and runs while this rank waits for the
+    // other ranks' rows, normalises and hands the results to the host
+    cudaStream_t sw = ctx->st_w;
+    CK(cudaEventRecord(ctx->ev_sm, ctx->st));
+    CK(cudaStreamWaitEvent(sw, ctx->ev_sm, 0));
+    if (ctx->fused_register) {
+        if (int r = zero_counters(ctx)) return r;
+        ctx->stats.ms_remap = 0.f; ctx->stats.ms_migrate = 0.f; ctx->stats.migrated_particles = 0; ctx->stats.migrated_bytes = 0;
+        CK(cudaEventRecord(ctx->evr0, ctx->st));
+        if (int r = gmi_bounds_and_resize(ctx)) return r;
+        const bool was_async = ctx->async_register;
+        ctx->async_register = true;  // collected by the next entry point, whatever the mode: the point is not to wait here
+        const int r = gmi_register_update(ctx);
+        ctx->async_register = was_async;
+        if (r) return r;
+    }
     const double* rows = ctx->d_rows;
     if (ctx->dist)
         if (int r = gmi_dist_wait_rows(ctx, &rows)) return r;  // every rank's slice has landed in this rank's gather buffer
-    CK(cudaEventRecord(ctx->evw0, ctx->st));
-    launch_normalize(ctx->d_logw, rows, N, obs_sigma_gain, ctx->d_w, ctx->d_neff, ctx->st);
-    CK(cudaEventRecord(ctx->evw1, ctx->st));
+    CK(cudaEventRecord(ctx->evw0, sw));
+    launch_normalize(ctx->d_logw, rows, N, obs_sigma_gain, ctx->d_w, ctx->d_neff, sw);
+    CK(cudaEventRecord(ctx->evw1, sw));
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_normalize")) return r;
     double* hout = reinterpret_cast<double*>(ctx->h_out);
-    CK(cudaMemcpyAsync(hout, rows, sizeof(double) * 5 * N, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaMemcpyAsync(hout + 5 * (size_t)N, ctx->d_w, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaMemcpyAsync(hout + 6 * (size_t)N, ctx->d_neff, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaMemcpyAsync(hout + 6 * (size_t)N + 2, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaMemcpyAsync(hout, rows, sizeof(double) * 5 * N, cudaMemcpyDeviceToHost, sw));
+    CK(cudaMemcpyAsync(hout + 5 * (size_t)N, ctx->d_w, sizeof(double) * N, cudaMemcpyDeviceToHost, sw));
+    CK(cudaMemcpyAsync(hout + 6 * (size_t)N, ctx->d_neff, sizeof(double), cudaMemcpyDeviceToHost, sw));
+    CK(cudaMemcpyAsync(hout + 6 * (size_t)N + 2, ctx->d_counters_sm, sizeof(Counters), cudaMemcpyDeviceToHost, sw));
+    CK(cudaStreamSynchronize(sw));
     memcpy(rows_out, hout, sizeof(double) * 5 * N);
     if (weights_out) memcpy(weights_out, hout + 5 * (size_t)N, sizeof(double) * N);
     if (neff_out) *neff_out = hout[6 * (size_t)N];
@@ -522,7 +544,7 @@ int gmi_register_update(gm_ctx* ctx) {
     if (smem != ctx->register_smem) { CK(register_prepare(smem)); ctx->register_smem = smem; }
     launch_register(a, n, smem, ctx->st);
     launch_merge_free(ctx->pool, ctx->st);
-    CK(cudaEventRecord(ctx->ev1, ctx->st));
+    CK(cudaEventRecord(ctx->evr1, ctx->st));
     ctx->stats.launches += 2;
     if (int rc = check_launch(ctx, "k_register")) return rc;
     ctx->reg_pending = true;
@@ -556,7 +578,7 @@ int gmi_register_finish(gm_ctx* ctx) {
     int top = 0;
     CK(cudaMemcpyAsync(&top, ctx->pool.free_top, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
-    CK(cudaEventElapsedTime(&ctx->stats.ms_register, ctx->ev0, ctx->ev1));
+    CK(cudaEventElapsedTime(&ctx->stats.ms_register, ctx->evr0, ctx->evr1));
     ctx->stats.total_ms[3] += ctx->stats.ms_register; ctx->stats.total_ms[2] += ctx->stats.ms_remap; ctx->stats.total_ms[4] += ctx->stats.ms_migrate;
     ctx->stats.total_registers++;
     ctx->stats.cow_copies = h.cow_copies; ctx->stats.patch_allocs = h.patch_allocs;
@@ -597,7 +619,7 @@ int gm_register(gm_ctx* ctx, const double* ranges, const double* poses, const ui
     ctx->stats.ms_remap = 0.f;
     if (idx)
         if (int r = gmi_remap(ctx, idx, ctx->n)) return r;
-    CK(cudaEventRecord(ctx->ev0, ctx->st));
+    CK(cudaEventRecord(ctx->evr0, ctx->st));
     if (int rc = gmi_bounds_and_resize(ctx)) return rc;
     return gmi_register_update(ctx);
 }
@@ -789,6 +811,7 @@ int gm_clone(gm_ctx* src, gm_ctx** out) {
     dst->share->users++;
     dst->share->members.push_back(dst);
     dst->P = src->P; dst->laser_set = src->laser_set; dst->match_set = src->match_set;
+    dst->async_register = src->async_register; dst->fused_register = src->fused_register;
     memcpy(dst->angles_h, src->angles_h, sizeof src->angles_h);
     auto bail = [&](cudaError_t e, const char* what) {
         dst->inited = false;
@@ -822,6 +845,14 @@ int gm_set_async_register(gm_ctx* ctx, int on) {
     if (int r = bind(ctx)) return r;
     if (int r = gmi_register_finish(ctx)) return r;
     ctx->async_register = on != 0;
+    return GM_OK;
+}
+
+int gm_set_fused_register(gm_ctx* ctx, int on) {
+    if (!ctx) return GM_ERR_ARG;
+    if (int r = bind(ctx)) return r;
+    if (int r = gmi_register_finish(ctx)) return r;
+    ctx->fused_register = on != 0;
     return GM_OK;
 }
 

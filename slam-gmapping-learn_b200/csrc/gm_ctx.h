@@ -32,6 +32,8 @@ struct gm_ctx {
     cudaStream_t st = nullptr;
     cudaStream_t st_w = nullptr;  // weights (normalize / resample indexes): independent of the maps, may overtake a registration
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evw0 = nullptr, evw1 = nullptr;
+    cudaEvent_t evr0 = nullptr, evr1 = nullptr;  // the registration's own pair: it may run while a scan match is being timed
+    cudaEvent_t ev_sm = nullptr;                 // k_scanmatch done (st_w waits for it before normalising)
     uint32_t max_particles = 0, n = 0, threads = 256;
     DevParams P{};
     bool laser_set = false, match_set = false, inited = false;
@@ -52,6 +54,8 @@ struct gm_ctx {
     unsigned* d_qidx = nullptr; double *d_qposes = nullptr, *d_qposes_out = nullptr, *d_qs = nullptr, *d_ql = nullptr; unsigned* d_qc = nullptr;
     uint32_t q_cap = 0;
     Counters* d_counters = nullptr;
+    Counters* d_counters_sm = nullptr;  // gm_scanmatch_weights' own: a registration queued right behind the scan match zeroes the others
+    bool fused_register = false;        // gm_set_fused_register
     double* d_inv_n = nullptr;
     size_t scanmatch_smem = 0;
     unsigned long long* d_digest = nullptr;

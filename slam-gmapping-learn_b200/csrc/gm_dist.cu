@@ -514,7 +514,7 @@ int gm_dist_register(gm_ctx* ctx, const double* ranges, const double* poses, con
     if (idx_global)
         if (int r = dist_migrate_and_remap(ctx, idx_global, "gm_dist_register")) return r;
     if (int r = gmi_stage(ctx, ranges, poses)) return r;
-    CK(cudaEventRecord(ctx->ev0, ctx->st));
+    CK(cudaEventRecord(ctx->evr0, ctx->st));
     if (int rc = gmi_bounds_and_resize(ctx)) return rc;
     return gmi_register_update(ctx);
 }

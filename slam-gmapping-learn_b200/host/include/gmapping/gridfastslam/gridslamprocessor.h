@@ -162,6 +162,12 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     // inside onResampleUpdate().
     void setearlyRegistration(bool early) { m_earlyRegistration = early; }
     bool getearlyRegistration() const { return m_earlyRegistration; }
+    // B200 build: queue the registration on the device right behind the scan match (gm_set_fused_register), so that it runs while
+    // the weights come back to the host -- on a sharded filter, while this rank waits for the other ranks' results.  The device
+    // maps are then one scan ahead already inside onScanmatchUpdate() (reading Particle::map there aborts with a message, as in
+    // onResampleUpdate()).  Needs early registration.  Default: on for a sharded filter, off on a single GPU.  Call before init().
+    void setregisterWithScanMatch(bool on) { m_fusedRegister = on ? 1 : 0; }
+    bool getregisterWithScanMatch() const { return m_fusedRegister > 0 || (m_fusedRegister < 0 && m_world > 1); }
     void refreshTreeWeights();
     // occupancy grid of one local particle's map computed on the GPU (what gmapping/src/slam_gmapping.cpp:956-993 fills by
     // walking smap.cell(p) on the host): data[y * width + x] = -1 unknown, 100 if n/visits > occThresh, else 0;
@@ -226,6 +232,7 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     unsigned int m_treeEpoch;
     bool m_lazyTree = false;
     bool m_earlyRegistration = true, m_registeredEarly = false;
+    int m_fusedRegister = -1;  // -1: by default (on when sharded)
     bool m_weightsChanged = true;  // a particle's log-weight changed since the last normalize()
     mutable bool m_treeDirty = false;
     double m_hostMs[4];

@@ -55,6 +55,7 @@ void gmh_tree_rows(void* hv, double* rows) {
         r[0] = depth; r[1] = ps[i].node ? ps[i].node->accWeight : 0.; r[2] = sum; r[3] = wsum; r[4] = visits; r[5] = childs;
     }
 }
+void gmh_set_register_with_scanmatch(void* h, int on) { static_cast<Handle*>(h)->gsp->setregisterWithScanMatch(on != 0); }
 void gmh_set_early_registration(void* h, int on) { static_cast<Handle*>(h)->gsp->setearlyRegistration(on != 0); }
 
 // params: maxUrange maxrange sigma kernelSize lstep astep iterations lsigma ogain lskip srr srt str stt linearUpdate

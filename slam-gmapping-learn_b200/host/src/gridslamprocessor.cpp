@@ -128,7 +128,7 @@ GridSlamProcessor::GridSlamProcessor(const GridSlamProcessor& gsp)
       m_xmax(gsp.m_xmax), m_ymax(gsp.m_ymax), m_delta(gsp.m_delta), m_regScore(gsp.m_regScore), m_critScore(gsp.m_critScore), m_maxMove(gsp.m_maxMove),
       m_linearThresholdDistance(gsp.m_linearThresholdDistance), m_angularThresholdDistance(gsp.m_angularThresholdDistance),
       m_obsSigmaGain(gsp.m_obsSigmaGain), m_infoStream(std::cout), m_rank(0), m_world(1), m_firstLocal(0), m_localCount(gsp.m_localCount),
-      m_treeEpoch(0), m_lazyTree(gsp.m_lazyTree), m_earlyRegistration(gsp.m_earlyRegistration) {
+      m_treeEpoch(0), m_lazyTree(gsp.m_lazyTree), m_earlyRegistration(gsp.m_earlyRegistration), m_fusedRegister(gsp.m_fusedRegister) {
     if (gsp.m_world > 1) b200::fatal("GridSlamProcessor copy / clone(): a sharded filter cannot be cloned");
     m_hostMs[0] = m_hostMs[1] = m_hostMs[2] = m_hostMs[3] = 0;
     m_hostMsTotal[0] = m_hostMsTotal[1] = m_hostMsTotal[2] = m_hostMsTotal[3] = 0;
@@ -227,6 +227,7 @@ void GridSlamProcessor::init(unsigned int size, double xmin, double ymin, double
     // the registration kernels keep running while processScan finishes its host-side bookkeeping (tree weights) and the
     // caller prepares the next reading; the next device call collects them
     m_device->check(gm_set_async_register(m_device->h, 1), "gm_set_async_register");
+    m_device->check(gm_set_fused_register(m_device->h, getregisterWithScanMatch() && m_earlyRegistration ? 1 : 0), "gm_set_fused_register");
 
     TNode* root = new TNode(initialPose, 0, 0, 0);
     ScanMatcherMap mirror(Point(center[0], center[1]), 0., 0., delta);  // geometry + cells arrive with the first pull
@@ -557,7 +558,10 @@ bool GridSlamProcessor::processScan(const RangeReading& reading, int adaptPartic
 
         if (m_count > 0) {
             sw.lap();
+            m_registeredEarly = false;
+            const bool fused = getregisterWithScanMatch() && m_earlyRegistration;
             scanMatch(plain.data());
+            if (fused) { m_registeredEarly = true; m_device->mapsAhead = true; markMapsStale(); }  // the registration is already queued
             m_hostMs[1] = sw.lap();
             if (m_outputStream.is_open()) {
                 m_outputStream << "LASER_READING " << reading.size() << " ";
@@ -578,11 +582,10 @@ bool GridSlamProcessor::processScan(const RangeReading& reading, int adaptPartic
             // while the host normalises the weights, decides about resampling and grows the trajectory tree.  Until the
             // point where the reference registers (inside resample()) the device maps are one scan ahead of the
             // reference's: reading Particle::map in that window (from onResampleUpdate) is refused, see setearlyRegistration
-            m_registeredEarly = false;
             sw.lap();
             normalizeIfNeeded();  // first: a one-CTA kernel that would otherwise queue behind the registration's grid
             m_hostMs[2] += sw.lap();
-            if (m_earlyRegistration) { registerAll(plain.data(), 0); m_registeredEarly = true; m_device->mapsAhead = true; }
+            if (m_earlyRegistration && !m_registeredEarly) { registerAll(plain.data(), 0); m_registeredEarly = true; m_device->mapsAhead = true; }
             sw.lap();
             // updateTreeWeights(false): the weights and Neff are needed now; the propagation into the trajectory tree can only be
             // observed before the second updateTreeWeights below through onResampleUpdate(), i.e. when the filter resamples --

@@ -37,6 +37,7 @@ def load():
     L.gmh_dist_unique_id.argtypes = [vp]
     L.gmh_set_distributed.argtypes = [vp, C.c_int, C.c_int, vp]
     L.gmh_set_early_registration.argtypes = [vp, C.c_int]
+    L.gmh_set_register_with_scanmatch.argtypes = [vp, C.c_int]
     L.gmh_set_lazy_tree.argtypes = [vp, C.c_int]
     L.gmh_refresh_tree.argtypes = [vp]
     L.gmh_tree_rows.argtypes = [vp, dp]
@@ -76,7 +77,7 @@ class Processor:
     """GMapping::GridSlamProcessor (C++) behind ctypes."""
 
     def __init__(self, angles, particles, init_pose, bounds=(-100., -100., 100., 100.), delta=0.05, seed=12345, laser_pose=(0., 0., 0.),
-                 rank=0, world=1, nccl_id=None, verbose=False, early_registration=True, lazy_tree=False, **params):
+                 rank=0, world=1, nccl_id=None, verbose=False, early_registration=True, lazy_tree=False, register_with_scanmatch=None, **params):
         L = load()
         self.L = L
         self.h = L.gmh_create(1 if verbose else 0)
@@ -85,6 +86,8 @@ class Processor:
             L.gmh_set_distributed(self.h, rank, world, self._id)
         if lazy_tree:
             L.gmh_set_lazy_tree(self.h, 1)  # TNode::accWeight is brought up to date on demand (refresh_tree / getTrajectories)
+        if register_with_scanmatch is not None:  # default: on for a sharded filter, off on one GPU
+            L.gmh_set_register_with_scanmatch(self.h, 1 if register_with_scanmatch else 0)
         if not early_registration:
             L.gmh_set_early_registration(self.h, 0)  # the reference's order: copy the resampled particles, then register
         p = dict(DEFAULTS); p.update(params)

@@ -110,9 +110,11 @@ def scenario_order():
     g = Golden("room181_k2_lskip")
     p = g.p
     runs = []
-    for early in (True, False):
+    # early registration (the default), the reference's order, and early registration queued on the device right behind the scan
+    # match (setregisterWithScanMatch: the default of a sharded filter)
+    for early, fused in ((True, False), (False, False), (True, True)):
         a = hostapi.Processor(g.angles, p["particles"], g.head_init, bounds=(p["xmin"], p["ymin"], p["xmax"], p["ymax"]), delta=p["delta"],
-                              seed=p["seed"], early_registration=early, **{k: p[k] for k in hostapi.PARAM_ORDER})
+                              seed=p["seed"], early_registration=early, register_with_scanmatch=fused, **{k: p[k] for k in hostapi.PARAM_ORDER})
         idx = []
         for i in range(len(g.ranges)):
             a.process_scan(g.ranges[i], g.odom[i], g.stamps[i])
@@ -120,10 +122,11 @@ def scenario_order():
                 idx.append(a.indexes().copy())
         runs.append((a.state(), a.map_digests(), a.resamples(), a.neff(), idx))
         a.close()
-    (s0, d0, r0, n0, i0), (s1, d1, r1, n1, i1) = runs
-    assert r0 == r1 and r0 > 0 and n0 == n1
-    assert np.array_equal(s0, s1) and np.array_equal(d0, d1)
-    assert len(i0) == len(i1) and all(np.array_equal(x, y) for x, y in zip(i0, i1))
+    (s0, d0, r0, n0, i0) = runs[0]
+    for (s1, d1, r1, n1, i1) in runs[1:]:
+        assert r0 == r1 and r0 > 0 and n0 == n1
+        assert np.array_equal(s0, s1) and np.array_equal(d0, d1)
+        assert len(i0) == len(i1) and all(np.array_equal(x, y) for x, y in zip(i0, i1))
     assert np.abs(s0[:, :3] - g.state[len(g.ranges) - 1][:, :3]).max() < 1e-4
 
 

@@ -30,6 +30,7 @@ struct gm_ctx {
     gm_stats stats;
     char err[256];
     struct dist_state* dist; /* multi-rank runs: see the end of this file */
+    int fused_register;
     uint8_t *dist_sent_prev, *dist_sent_prev2;
     unsigned long dist_seq_prev, dist_seq_prev2;
 };
@@ -367,6 +368,7 @@ int gm_clone(gm_ctx* src, gm_ctx** out) {
 }
 
 int gm_set_async_register(gm_ctx* c, int on) { (void)on; return c ? GM_OK : GM_ERR_ARG; }
+int gm_set_fused_register(gm_ctx* c, int on) { if (!c) return GM_ERR_ARG; c->fused_register = on != 0; return GM_OK; }
 int gm_synchronize(gm_ctx* c) { return c ? GM_OK : GM_ERR_ARG; }
 
 int gm_get_stats(gm_ctx* c, gm_stats* out) {
@@ -579,6 +581,7 @@ int gm_scanmatch_weights(gm_ctx* c, const double* ranges, const double* poses_lo
         if (c->dist) r = dist_allgather(c, mine, 5 * n, rows_out);
         else memcpy(rows_out, mine, sizeof(double) * 5 * n);
     }
+    if (!r && c->fused_register) r = gm_register(c, ranges, poses, NULL); /* the scan goes into every local map at its matched pose */
     free(poses); free(score); free(l); free(mine);
     if (r) return r;
     double* logw = (double*)malloc(sizeof(double) * N);
