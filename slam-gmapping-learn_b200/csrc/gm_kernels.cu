@@ -102,6 +102,9 @@ __device__ __forceinline__ int ldg_if(const int* p, bool pred, int dflt) {
     return v;
 }
 
+#ifndef GM_SM_MIN_CTAS
+#define GM_SM_MIN_CTAS 3  // resident CTAs per SM k_scanmatch is compiled for (72 registers); 4 (56 registers, spills) measured slower
+#endif
 constexpr int kSmThreads = 288;
 constexpr int kSmGroups = kSmThreads / 6;  // 48 beam groups x 6 candidate poses: every thread works
 
@@ -429,7 +432,7 @@ __device__ __noinline__ void plan_round(double lpx, double lpy, double lpt, SmSh
 // dynamic shared memory: three (cos, sin) tables of nbeams double2 each.
 // QUERY = (A.query >= 0); without it the particle is the block index, which keeps the per-particle pointers in uniform registers
 template <bool K1, bool QUERY>
-__global__ void __launch_bounds__(kSmThreads, 3) k_scanmatch(ScanMatchArgs A) {
+__global__ void __launch_bounds__(kSmThreads, GM_SM_MIN_CTAS) k_scanmatch(ScanMatchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SmShared S;
     const DevParams& P = A.P;
