@@ -149,6 +149,13 @@ int gm_scanmatch_weights(gm_ctx* ctx, const double* ranges, const double* poses_
                          const double* log_weights /*N*/, double obs_sigma_gain, double* rows_out /*N*5*/,
                          double* weights_out /*N*/, double* neff_out);
 
+/* gm_scanmatch_weights in two halves: _begin uploads and queues the kernels and returns at once, _end waits and hands out the
+ * results.  Host work that does not need the results (GridSlamProcessor grows the trajectory tree there) overlaps the scan
+ * match; no other entry point may be called on the context in between. */
+int gm_scanmatch_weights_begin(gm_ctx* ctx, const double* ranges, const double* poses_local, double minimum_score,
+                               const double* log_weights /*N*/, double obs_sigma_gain);
+int gm_scanmatch_weights_end(gm_ctx* ctx, double* rows_out /*N*5*/, double* weights_out /*N*/, double* neff_out);
+
 /* replaces: GridSlamProcessor::normalize, gridslamprocessor.hxx:82-121 (sequential sums kept) */
 int gm_normalize_neff(gm_ctx* ctx, const double* log_weights, uint32_t n, double obs_sigma_gain,
                       double* weights_out, double* neff_out);

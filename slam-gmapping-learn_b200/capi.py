@@ -14,7 +14,7 @@ EXPORTS = ["gm_create", "gm_destroy", "gm_last_error", "gm_set_laser", "gm_set_m
            "gm_init_particles", "gm_score", "gm_likelihood_and_score", "gm_scanmatch", "gm_normalize_neff",
            "gm_resample_indexes", "gm_register", "gm_map_info_get", "gm_download_map", "gm_map_digest",
            "gm_get_stats", "gm_particles", "gm_optimize", "gm_compute_active_area", "gm_upload_map", "gm_export_occupancy", "gm_clone", "gm_set_async_register", "gm_synchronize",
-           "gm_dist_unique_id", "gm_dist_init", "gm_dist_register", "gm_dist_copy_particles", "gm_dist_plan", "gm_scanmatch_weights", "gm_check_refcounts", "gm_set_fused_register"]
+           "gm_dist_unique_id", "gm_dist_init", "gm_dist_register", "gm_dist_copy_particles", "gm_dist_plan", "gm_scanmatch_weights", "gm_check_refcounts", "gm_set_fused_register", "gm_scanmatch_weights_begin", "gm_scanmatch_weights_end"]
 
 
 class GmError(RuntimeError):

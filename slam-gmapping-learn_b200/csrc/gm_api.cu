@@ -323,8 +323,16 @@ int gm_scanmatch(gm_ctx* ctx, const double* ranges, double* poses_inout, double 
 // every rank land in every rank's HBM from the kernel's epilogue], k_normalize, one download, ONE synchronisation.
 int gm_scanmatch_weights(gm_ctx* ctx, const double* ranges, const double* poses_local, double minimum_score, const double* log_weights,
                          double obs_sigma_gain, double* rows_out, double* weights_out, double* neff_out) {
+    if (int r = gm_scanmatch_weights_begin(ctx, ranges, poses_local, minimum_score, log_weights, obs_sigma_gain)) return r;
+    return gm_scanmatch_weights_end(ctx, rows_out, weights_out, neff_out);
+}
+
+// the launch half: uploads, k_scanmatch (and, fused, the registration behind it) are queued; the caller's host work overlaps them
+int gm_scanmatch_weights_begin(gm_ctx* ctx, const double* ranges, const double* poses_local, double minimum_score, const double* log_weights,
+                               double obs_sigma_gain) {
     if (int r = ready(ctx, true)) return r;
-    if (!ranges || !poses_local || !log_weights || !rows_out) return fail(ctx, GM_ERR_ARG, "gm_scanmatch_weights: null argument");
+    if (ctx->sw_pending) return fail(ctx, GM_ERR_ARG, "gm_scanmatch_weights_begin: the previous one has not been collected (gm_scanmatch_weights_end)");
+    if (!ranges || !poses_local || !log_weights) return fail(ctx, GM_ERR_ARG, "gm_scanmatch_weights: null argument");
     const uint32_t n = ctx->n, nb = ctx->P.nbeams;
     uint32_t N = n, first = 0;
     ScanMatchArgs a{};
@@ -374,6 +382,21 @@ int gm_scanmatch_weights(gm_ctx* ctx, const double* ranges, const double* poses_
         ctx->async_register = was_async;
         if (r) return r;
     }
+    ctx->sw_pending = true; ctx->sw_total = N; ctx->sw_gain = obs_sigma_gain;
+    (void)first;
+    return GM_OK;
+}
+
+// the collecting half: [sharded: wait for every rank's rows,] normalise on the second stream, one download, one synchronisation
+int gm_scanmatch_weights_end(gm_ctx* ctx, double* rows_out, double* weights_out, double* neff_out) {
+    if (!ctx) return GM_ERR_ARG;
+    if (int r = bind(ctx)) return r;
+    if (!ctx->sw_pending) return fail(ctx, GM_ERR_ARG, "gm_scanmatch_weights_end: nothing to collect (gm_scanmatch_weights_begin)");
+    if (!rows_out) return fail(ctx, GM_ERR_ARG, "gm_scanmatch_weights_end: null argument");
+    ctx->sw_pending = false;
+    const uint32_t N = ctx->sw_total;
+    const double obs_sigma_gain = ctx->sw_gain;
+    cudaStream_t sw = ctx->st_w;
     const double* rows = ctx->d_rows;
     if (ctx->dist)
         if (int r = gmi_dist_wait_rows(ctx, &rows)) return r;  // every rank's slice has landed in this rank's gather buffer
@@ -393,7 +416,6 @@ int gm_scanmatch_weights(gm_ctx* ctx, const double* ranges, const double* poses_
     if (neff_out) *neff_out = hout[6 * (size_t)N];
     Counters h;
     memcpy(&h, hout + 6 * (size_t)N + 2, sizeof h);
-    (void)first;
     ctx->stats.score_evals = h.score_evals; ctx->stats.beam_evals = h.beam_evals;
     CK(cudaEventElapsedTime(&ctx->stats.ms_scanmatch, ctx->ev0, ctx->ev1));
     CK(cudaEventElapsedTime(&ctx->stats.ms_weights, ctx->evw0, ctx->evw1));

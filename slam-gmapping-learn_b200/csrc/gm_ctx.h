@@ -56,6 +56,7 @@ struct gm_ctx {
     Counters* d_counters = nullptr;
     Counters* d_counters_sm = nullptr;  // gm_scanmatch_weights' own: a registration queued right behind the scan match zeroes the others
     bool fused_register = false;        // gm_set_fused_register
+    bool sw_pending = false; uint32_t sw_total = 0; double sw_gain = 1;  // between gm_scanmatch_weights_begin and _end
     double* d_inv_n = nullptr;
     size_t scanmatch_smem = 0;
     unsigned long long* d_digest = nullptr;
@@ -181,6 +182,7 @@ inline int ready(gm_ctx* ctx, bool need_particles) {
     if (!ctx->match_set) return fail(ctx, GM_ERR_ARG, "gm_set_matching has not been called");
     if (need_particles && !ctx->inited) return fail(ctx, GM_ERR_ARG, "gm_init_particles has not been called");
     if (int r = bind(ctx)) return r;
+    if (ctx->sw_pending) return fail(ctx, GM_ERR_ARG, "a gm_scanmatch_weights_begin is waiting for its gm_scanmatch_weights_end");
     return ctx->reg_pending ? gmi_register_finish(ctx) : GM_OK;  // an asynchronous registration reports here
 }
 // entry points that touch weights only: they run on their own stream and leave a registration in flight alone

@@ -213,7 +213,7 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     std::ostream& m_infoStream;
 
   private:
-    void scanMatch(const double* plainReading);
+    void scanMatch(const double* plainReading, const RangeReading* reading);
     void normalize();
     void normalizeIfNeeded();
     bool resample(const double* plainReading, int adaptParticles, const RangeReading* rr = 0);
@@ -238,6 +238,7 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     double m_hostMs[4];
     double m_hostMsTotal[4] = {0, 0, 0, 0};
     std::vector<double> m_poseBuf, m_rowBuf, m_logwBuf;
+    TNodeVector m_newNodes;  // this scan's trajectory nodes, made while the GPU matches the scan (scanMatch -> resample)
 };
 
 typedef std::multimap<const GridSlamProcessor::TNode*, GridSlamProcessor::TNode*> TNodeMultimap;

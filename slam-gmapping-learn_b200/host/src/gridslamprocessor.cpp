@@ -282,7 +282,7 @@ void GridSlamProcessor::markMapsStale() {
 // the same stream-ordered device sequence, one synchronisation -- the normalize() of the updateTreeWeights that follows
 // (gridslamprocessor.cpp:586): the device adds each particle's l to the log-weight it was given, exactly like the loop below.
 // Sharded: the rows of every rank's particles come back in global order (they reach every GPU from the kernel's epilogue).
-void GridSlamProcessor::scanMatch(const double* plainReading) {
+void GridSlamProcessor::scanMatch(const double* plainReading, const RangeReading* reading) {
     const size_t n = m_particles.size(), nl = m_localCount;
     m_poseBuf.resize(3 * nl); m_rowBuf.resize(5 * n); m_logwBuf.resize(n);
     for (size_t j = 0; j < nl; j++) {
@@ -293,9 +293,18 @@ void GridSlamProcessor::scanMatch(const double* plainReading) {
     m_weights.resize(n);
     m_device->configure(m_matcher);
     flushHostEdits();
-    m_device->check(gm_scanmatch_weights(m_device->h, plainReading, m_poseBuf.data(), m_minimumScore, m_logwBuf.data(), m_obsSigmaGain,
-                                         m_rowBuf.data(), m_weights.data(), &m_neff),
-                    "gm_scanmatch_weights");
+    m_device->check(gm_scanmatch_weights_begin(m_device->h, plainReading, m_poseBuf.data(), m_minimumScore, m_logwBuf.data(), m_obsSigmaGain),
+                    "gm_scanmatch_weights_begin");
+    // While the GPU matches: the trajectory nodes this scan will add, one per particle, hung below the particles' present leaves
+    // (what resample() does for a filter that does not resample -- nearly every scan; a resampling re-hangs them, see there).
+    // Their poses are filled in once the scan match has delivered them.
+    m_newNodes.resize(n);
+    for (size_t i = 0; i < n; i++) {
+        TNode* node = new TNode(m_particles[i].pose, 0.0, m_particles[i].node, 0);
+        node->reading = reading;
+        m_newNodes[i] = node;
+    }
+    m_device->check(gm_scanmatch_weights_end(m_device->h, m_rowBuf.data(), m_weights.data(), &m_neff), "gm_scanmatch_weights_end");
     double sumScore = 0;
     for (size_t i = 0; i < n; i++) {
         Particle& p = m_particles[i];
@@ -353,15 +362,18 @@ void GridSlamProcessor::copyAll(const unsigned int* parents) {
 // resample (reference: gridslamprocessor.hxx:131-302)
 bool GridSlamProcessor::resample(const double* plainReading, int adaptSize, const RangeReading* reading) {
     const size_t n = m_particles.size();
+    const bool prepared = m_newNodes.size() == n;  // scanMatch() made this scan's nodes while the GPU was busy
     if (!(m_neff < m_resampleThreshold * n)) {
         // no resampling: every particle grows its own trajectory by one node and registers the scan
         for (size_t i = 0; i < n; i++) {
             Particle& p = m_particles[i];
-            TNode* node = new TNode(p.pose, 0.0, p.node, 0);
+            TNode* node = prepared ? m_newNodes[i] : new TNode(p.pose, 0.0, p.node, 0);
+            node->pose = p.pose;
             node->reading = reading;
             p.node = node;
             p.previousIndex = (int)i;
         }
+        m_newNodes.clear();
         if (!m_registeredEarly) registerAll(plainReading, 0);
         m_device->mapsAhead = false;
         return false;
@@ -389,14 +401,20 @@ bool GridSlamProcessor::resample(const double* plainReading, int adaptSize, cons
     std::vector<char> kept(n, 0);
     for (size_t j = 0; j < n; j++) {
         const Particle& src = m_particles[m_indexes[j]];
+        // a parent's first child takes the node prepared below the parent's leaf, further children get nodes of their own
+        TNode* node = (prepared && !kept[m_indexes[j]]) ? m_newNodes[m_indexes[j]] : new TNode(src.pose, 0, src.node, 0);
         kept[m_indexes[j]] = 1;
-        TNode* node = new TNode(src.pose, 0, src.node, 0);
+        node->pose = src.pose;
         node->reading = reading;
         next[j].pose = src.pose; next[j].previousPose = src.previousPose;
         next[j].weightSum = src.weightSum; next[j].gweight = src.gweight; next[j].node = node;
     }
     for (size_t i = 0; i < n; i++)
-        if (!kept[i]) { delete m_particles[i].node; m_particles[i].node = 0; }  // leaves of trajectories that died out
+        if (!kept[i]) {  // leaves of trajectories that died out (deleting the prepared node takes its parent, the leaf, along)
+            if (prepared) delete m_newNodes[i]; else delete m_particles[i].node;
+            m_particles[i].node = 0;
+        }
+    m_newNodes.clear();
     for (size_t j = 0; j < n; j++) {
         Particle& p = m_particles[j];
         p.pose = next[j].pose; p.previousPose = next[j].previousPose;
@@ -560,7 +578,7 @@ bool GridSlamProcessor::processScan(const RangeReading& reading, int adaptPartic
             sw.lap();
             m_registeredEarly = false;
             const bool fused = getregisterWithScanMatch() && m_earlyRegistration;
-            scanMatch(plain.data());
+            scanMatch(plain.data(), readingCopy);
             if (fused) { m_registeredEarly = true; m_device->mapsAhead = true; markMapsStale(); }  // the registration is already queued
             m_hostMs[1] = sw.lap();
             if (m_outputStream.is_open()) {
@@ -692,9 +710,10 @@ void GridSlamProcessor::integrateScanSequence(TNode* node) {
         const OrientedPoint dp = aux->pose - oldPose;
         const double dw = aux->weight - oldWeight;
         oldPose = aux->pose;
-        if (!aux->reading) b200::fatal("GridSlamProcessor::integrateScanSequence: a node of the path has no reading");
-        assert(aux->reading->size() == m_beams);
-        const std::vector<double> plain(aux->reading->begin(), aux->reading->end());
+        // (the reference dereferences aux->reading unconditionally, i.e. crashes on a node without one -- the root of every
+        // trajectory getTrajectories() returns; here such a node moves the particles but has no scan to bound)
+        std::vector<double> plain;
+        if (aux->reading) { assert(aux->reading->size() == m_beams); plain.assign(aux->reading->begin(), aux->reading->end()); }
         for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it) {
             const double s = sin(oldPose.theta - it->pose.theta), c = cos(oldPose.theta - it->pose.theta);
             it->pose.x += c * dp.x - s * dp.y;
@@ -705,6 +724,7 @@ void GridSlamProcessor::integrateScanSequence(TNode* node) {
             it->weightSum += dw;
             it->node = new TNode(it->pose, 0.0, it->node);
         }
+        if (plain.empty()) continue;
         // computeActiveArea for every (local) particle in one call: the bounding box of the scan and the Map::resize it triggers
         m_poseBuf.resize(3 * nl);
         for (size_t j = 0; j < nl; j++) {

@@ -31,6 +31,7 @@ struct gm_ctx {
     char err[256];
     struct dist_state* dist; /* multi-rank runs: see the end of this file */
     int fused_register;
+    double *sw_rows, *sw_w, sw_neff; uint32_t sw_total; /* between gm_scanmatch_weights_begin and _end */
     uint8_t *dist_sent_prev, *dist_sent_prev2;
     unsigned long dist_seq_prev, dist_seq_prev2;
 };
@@ -560,12 +561,19 @@ int gm_dist_register(gm_ctx* c, const double* ranges, const double* poses, const
 
 /* scanMatch + weight += l + normalize in one call; on a sharded context the rows of all ranks (exchanged through files here,
  * through peer memory in the product) in global particle order */
-int gm_scanmatch_weights(gm_ctx* c, const double* ranges, const double* poses_local, double minimum_score, const double* log_weights,
-                         double gain, double* rows_out, double* weights_out, double* neff_out) {
+int gm_scanmatch_weights_begin(gm_ctx* c, const double* ranges, const double* poses_local, double minimum_score, const double* log_weights,
+                               double gain) {
     int r = ready(c);
     if (r) return r;
-    if (!ranges || !poses_local || !log_weights || !rows_out) return fail(c, GM_ERR_ARG, "gm_scanmatch_weights: null argument");
+    if (c->sw_rows) return fail(c, GM_ERR_ARG, "gm_scanmatch_weights_begin: the previous one has not been collected");
+    if (!ranges || !poses_local || !log_weights) return fail(c, GM_ERR_ARG, "gm_scanmatch_weights: null argument");
     const uint32_t n = c->n, world = c->dist ? (uint32_t)c->dist->world : 1u, N = n * world;
+    if (N > c->weights_cap) return fail(c, GM_ERR_ARG, "gm_scanmatch_weights: %u particles over all ranks, the context was created for %u", N, c->weights_cap);
+    /* the mock computes everything here and keeps it for _end */
+    double* rows_out = (double*)malloc(sizeof(double) * 5 * N);
+    double* weights_out = (double*)malloc(sizeof(double) * N);
+    double neff_keep = 0, *neff_out = &neff_keep;
+    c->sw_total = N;
     if (N > c->weights_cap) return fail(c, GM_ERR_ARG, "gm_scanmatch_weights: %u particles over all ranks, the context was created for %u", N, c->weights_cap);
     double* poses = (double*)malloc(sizeof(double) * 3 * n);
     double* score = (double*)malloc(sizeof(double) * n);
@@ -583,7 +591,7 @@ int gm_scanmatch_weights(gm_ctx* c, const double* ranges, const double* poses_lo
     }
     if (!r && c->fused_register) r = gm_register(c, ranges, poses, NULL); /* the scan goes into every local map at its matched pose */
     free(poses); free(score); free(l); free(mine);
-    if (r) return r;
+    if (r) { free(rows_out); free(weights_out); return r; }
     double* logw = (double*)malloc(sizeof(double) * N);
     double* w = (double*)malloc(sizeof(double) * N);
     for (uint32_t i = 0; i < N; i++) logw[i] = log_weights[i] + rows_out[5 * (size_t)i + 4];
@@ -591,5 +599,24 @@ int gm_scanmatch_weights(gm_ctx* c, const double* ranges, const double* poses_lo
     if (weights_out) memcpy(weights_out, w, sizeof(double) * N);
     if (neff_out) *neff_out = neff;
     free(logw); free(w);
+    c->sw_rows = rows_out; c->sw_w = weights_out; c->sw_neff = neff_keep;
     return GM_OK;
+}
+
+int gm_scanmatch_weights_end(gm_ctx* c, double* rows_out, double* weights_out, double* neff_out) {
+    if (!c) return GM_ERR_ARG;
+    if (!c->sw_rows) return fail(c, GM_ERR_ARG, "gm_scanmatch_weights_end: nothing to collect");
+    if (!rows_out) return fail(c, GM_ERR_ARG, "gm_scanmatch_weights_end: null argument");
+    memcpy(rows_out, c->sw_rows, sizeof(double) * 5 * c->sw_total);
+    if (weights_out) memcpy(weights_out, c->sw_w, sizeof(double) * c->sw_total);
+    if (neff_out) *neff_out = c->sw_neff;
+    free(c->sw_rows); free(c->sw_w); c->sw_rows = NULL; c->sw_w = NULL;
+    return GM_OK;
+}
+
+int gm_scanmatch_weights(gm_ctx* c, const double* ranges, const double* poses_local, double minimum_score, const double* log_weights,
+                         double gain, double* rows_out, double* weights_out, double* neff_out) {
+    int r = gm_scanmatch_weights_begin(c, ranges, poses_local, minimum_score, log_weights, gain);
+    if (r) return r;
+    return gm_scanmatch_weights_end(c, rows_out, weights_out, neff_out);
 }
