@@ -1352,16 +1352,20 @@ __global__ void k_fill_geom(Geom* g, unsigned n, Geom v) {
 // reference, so one thread walks them in order (N <= 64K doubles: tens of microseconds).
 // With `rows` (gm_scanmatch_weights) the log-weights first take this scan's log-likelihood, weight += l
 // (gridslamprocessor.hxx:50-52; rows[5 i + 4] is particle i's l): the host applies the same single addition to its copy.
+// The sequential walks read a block-staged copy in shared memory: thread 0's chain of dependent additions then never waits
+// for a global load (behind a registration running on the other stream an L2 round trip per line tripled this kernel).
+constexpr unsigned kSeqChunk = 4096;
 __global__ void __launch_bounds__(1024) k_normalize(double* __restrict__ logw, const double* __restrict__ rows, unsigned n, double gain_sigma,
                                                     double* __restrict__ w, double* __restrict__ neff_out) {
     __shared__ double red[32];
     __shared__ double s_val;
+    __shared__ double stage[kSeqChunk];
     double lmax = -1.7976931348623157e308;
-    if (rows) {
-        for (unsigned i = threadIdx.x; i < n; i += blockDim.x) logw[i] = logw[i] + rows[5 * (size_t)i + 4];
-        __syncthreads();
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+        double v = logw[i];
+        if (rows) { v = v + rows[5 * (size_t)i + 4]; logw[i] = v; }
+        lmax = v > lmax ? v : lmax;
     }
-    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) { double v = logw[i]; lmax = v > lmax ? v : lmax; }
     lmax = warp_max(lmax);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lmax;
     __syncthreads();
@@ -1369,14 +1373,32 @@ __global__ void __launch_bounds__(1024) k_normalize(double* __restrict__ logw, c
     __syncthreads();
     lmax = s_val;
     const double gain = 1. / (gain_sigma * n);
-    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) w[i] = exp(gain * (logw[i] - lmax));
-    __syncthreads();
-    if (threadIdx.x == 0) { double wcum = 0; for (unsigned i = 0; i < n; i++) wcum += w[i]; s_val = wcum; }
+    double chain = 0;  // thread 0's running sum, carried over the chunks
+    for (unsigned base = 0; base < n; base += kSeqChunk) {
+        const unsigned m = min(kSeqChunk, n - base);
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < m; i += blockDim.x) { const double e = exp(gain * (logw[base + i] - lmax)); stage[i] = e; w[base + i] = e; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll 8
+            for (unsigned i = 0; i < m; i++) chain += stage[i];
+        }
+    }
+    if (threadIdx.x == 0) s_val = chain;
     __syncthreads();
     const double wcum = s_val;
-    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) w[i] = w[i] / wcum;
-    __syncthreads();
-    if (threadIdx.x == 0) { double ne = 0; for (unsigned i = 0; i < n; i++) { double x = w[i]; ne += x * x; } *neff_out = 1. / ne; }
+    chain = 0;
+    for (unsigned base = 0; base < n; base += kSeqChunk) {
+        const unsigned m = min(kSeqChunk, n - base);
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < m; i += blockDim.x) { const double x = w[base + i] / wcum; stage[i] = x; w[base + i] = x; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll 8
+            for (unsigned i = 0; i < m; i++) { const double x = stage[i]; chain += x * x; }
+        }
+    }
+    if (threadIdx.x == 0) *neff_out = 1. / chain;
 }
 
 // resampleIndexes (particlefilter.h:180-229).  The cumulative weights c[i] and the targets t[k] are the
@@ -1385,11 +1407,21 @@ __global__ void __launch_bounds__(1024) k_normalize(double* __restrict__ logw, c
 __global__ void __launch_bounds__(1024) k_resample(const double* __restrict__ w, unsigned n, double u01, double* __restrict__ cum,
                                                    double* __restrict__ tgt, unsigned* __restrict__ idx, unsigned* __restrict__ emitted) {
     __shared__ double s_interval;
-    if (threadIdx.x == 0) {
-        double c = 0;
-        for (unsigned i = 0; i < n; i++) { c += w[i]; cum[i] = c; }
-        s_interval = c / n;
+    __shared__ double stage[kSeqChunk];
+    double c = 0;
+    for (unsigned base = 0; base < n; base += kSeqChunk) {
+        const unsigned m = min(kSeqChunk, n - base);
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < m; i += blockDim.x) stage[i] = w[base + i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll 8
+            for (unsigned i = 0; i < m; i++) { c += stage[i]; stage[i] = c; }
+        }
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < m; i += blockDim.x) cum[base + i] = stage[i];
     }
+    if (threadIdx.x == 0) s_interval = c / n;
     __syncthreads();
     const double interval = s_interval;
     if (threadIdx.x == 0) {

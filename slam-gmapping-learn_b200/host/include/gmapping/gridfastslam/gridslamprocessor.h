@@ -8,6 +8,7 @@
 // from the host downloads that particle's patches on first use after every update (grid/map.h).
 #ifndef GMB200_GRIDSLAMPROCESSOR_H
 #define GMB200_GRIDSLAMPROCESSOR_H
+#include <stdint.h>
 #include <gmapping/gridfastslam/gridfastslam_export.h>
 #include <gmapping/gridfastslam/motionmodel.h>
 #include <gmapping/particlefilter/particlefilter.h>
@@ -238,6 +239,15 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     double m_hostMs[4];
     double m_hostMsTotal[4] = {0, 0, 0, 0};
     std::vector<double> m_poseBuf, m_rowBuf, m_logwBuf;
+    // the next reading's motion samples, drawn ahead (while the GPU registers the scan) on a look-ahead copy of the drand48
+    // stream: b, r of the 3 N polar samples, sin / cos of every particle's heading.  Adopted by the next processScan only if
+    // the C library's generator is still where the look-ahead started and no noise scale is zero (sampleGaussian(0) draws nothing)
+    struct MotionDraws {
+        bool valid = false;
+        uint64_t before = 0, after = 0;
+        std::vector<double> b, r, theta, sn, cs;
+    } m_motionDraws;
+    void prepareMotionDraws();
     TNodeVector m_newNodes;  // this scan's trajectory nodes, made while the GPU matches the scan (scanMatch -> resample)
 };
 

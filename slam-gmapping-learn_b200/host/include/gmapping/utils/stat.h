@@ -20,15 +20,18 @@ namespace GMapping {
 // Nothing else may call the drand48 family while one is alive.
 class Drand48Stream {
   public:
-    Drand48Stream() {
-        unsigned short zero[3] = {0, 0, 0};
-        const unsigned short* prev = seed48(zero);
-        m_x = (uint64_t)prev[0] | ((uint64_t)prev[1] << 16) | ((uint64_t)prev[2] << 32);
-    }
-    ~Drand48Stream() {
-        unsigned short s[3] = {(unsigned short)(m_x & 0xffff), (unsigned short)((m_x >> 16) & 0xffff), (unsigned short)((m_x >> 32) & 0xffff)};
+    Drand48Stream() : m_x(take()), m_detached(false) {}
+    // a look-ahead copy starting at `state`: the C library's generator is left alone (GridSlamProcessor draws the next
+    // reading's motion samples ahead of time and adopts them only if nothing else has drawn in between)
+    explicit Drand48Stream(uint64_t state) : m_x(state), m_detached(true) {}
+    ~Drand48Stream() { if (!m_detached) put(m_x); }
+    // the C library generator's 48-bit state: read (and leave unchanged) / replace
+    static uint64_t peek() { const uint64_t x = take(); put(x); return x; }
+    static void put(uint64_t x) {
+        unsigned short s[3] = {(unsigned short)(x & 0xffff), (unsigned short)((x >> 16) & 0xffff), (unsigned short)((x >> 32) & 0xffff)};
         seed48(s);
     }
+    uint64_t state() const { return m_x; }
     Drand48Stream(const Drand48Stream&) = delete;
     Drand48Stream& operator=(const Drand48Stream&) = delete;
     inline double next() {
@@ -48,9 +51,27 @@ class Drand48Stream {
         } while (w > 1.0 || w == 0.0);
         return sigma * b * std::sqrt(-2.0 * std::log(w) / w);
     }
+    // the sigma-independent part of gaussian(): the same draws, the sample is then sigma * b * r
+    inline void polar(double& b_out, double& r_out) {
+        double a, b, w, u;
+        do {
+            do { u = next(); } while (u == 0.0);
+            a = 2.0 * u - 1.0;
+            do { u = next(); } while (u == 0.0);
+            b = 2.0 * next() - 1.0;
+            w = a * a + b * b;
+        } while (w > 1.0 || w == 0.0);
+        b_out = b; r_out = std::sqrt(-2.0 * std::log(w) / w);
+    }
 
   private:
+    static uint64_t take() {  // reads the state; the generator is left zeroed until put()
+        unsigned short zero[3] = {0, 0, 0};
+        const unsigned short* prev = seed48(zero);
+        return (uint64_t)prev[0] | ((uint64_t)prev[1] << 16) | ((uint64_t)prev[2] << 32);
+    }
     uint64_t m_x;
+    bool m_detached;
 };
 
 // zero-mean Gaussian sample (polar Box-Muller over drand48).  S != 0 re-seeds with srand48(S) first;

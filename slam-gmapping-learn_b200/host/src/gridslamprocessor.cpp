@@ -522,16 +522,39 @@ bool GridSlamProcessor::processScan(const RangeReading& reading, int adaptPartic
         const double sx = mm.srr * fabs(delta.x) + mm.str * fabs(delta.theta) + sxy * fabs(delta.y);
         const double sy = mm.srr * fabs(delta.y) + mm.str * fabs(delta.theta) + sxy * fabs(delta.x);
         const double st = mm.stt * fabs(delta.theta) + mm.srt * sqrt(delta.x * delta.x + delta.y * delta.y);
-        Drand48Stream draws;  // the drand48() stream, stepped inline for these 3 x N samples
-        for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it) {
-            OrientedPoint noisy(delta);
-            noisy.x += draws.gaussian(sx);
-            noisy.y += draws.gaussian(sy);
-            noisy.theta += draws.gaussian(st);
-            noisy.theta = fmod(noisy.theta, 2 * M_PI);
-            if (noisy.theta > M_PI) noisy.theta -= 2 * M_PI;
-            it->pose = absoluteSum(it->pose, noisy);
+        MotionDraws& md = m_motionDraws;
+        const size_t n = m_particles.size();
+        if (md.valid && md.theta.size() == n && sx != 0 && sy != 0 && st != 0 && Drand48Stream::peek() == md.before) {
+            // the samples were drawn ahead of time (prepareMotionDraws): same draws, same expressions, the stream moves to where they end
+            Drand48Stream::put(md.after);
+            for (size_t i = 0; i < n; i++) {
+                OrientedPoint& pose = m_particles[i].pose;
+                OrientedPoint noisy(delta);
+                noisy.x += sx * md.b[3 * i] * md.r[3 * i];
+                noisy.y += sy * md.b[3 * i + 1] * md.r[3 * i + 1];
+                noisy.theta += st * md.b[3 * i + 2] * md.r[3 * i + 2];
+                noisy.theta = fmod(noisy.theta, 2 * M_PI);
+                if (noisy.theta > M_PI) noisy.theta -= 2 * M_PI;
+                if (pose.theta == md.theta[i]) {  // absoluteSum(pose, noisy) with the prepared sin / cos of pose.theta
+                    const double s = md.sn[i], c = md.cs[i];
+                    pose = OrientedPoint(c * noisy.x - s * noisy.y, s * noisy.x + c * noisy.y, noisy.theta) + pose;
+                } else {
+                    pose = absoluteSum(pose, noisy);
+                }
+            }
+        } else {
+            Drand48Stream draws;  // the drand48() stream, stepped inline for these 3 x N samples
+            for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it) {
+                OrientedPoint noisy(delta);
+                noisy.x += draws.gaussian(sx);
+                noisy.y += draws.gaussian(sy);
+                noisy.theta += draws.gaussian(st);
+                noisy.theta = fmod(noisy.theta, 2 * M_PI);
+                if (noisy.theta > M_PI) noisy.theta -= 2 * M_PI;
+                it->pose = absoluteSum(it->pose, noisy);
+            }
         }
+        md.valid = false;
     }
     m_hostMs[0] = sw.lap();
 
@@ -637,11 +660,31 @@ bool GridSlamProcessor::processScan(const RangeReading& reading, int adaptPartic
         m_count++;
         processed = true;
         for (ParticleVector::iterator it = m_particles.begin(); it != m_particles.end(); ++it) it->previousPose = it->pose;
+        // the GPU is registering the scan: the host uses the time for the part of the next reading's motion update that does
+        // not depend on the odometry (outside the stage times: it overlaps device work)
+        if (m_count > 1 && m_earlyRegistration) prepareMotionDraws();
     }
     for (int k = 0; k < 4; k++) m_hostMsTotal[k] += m_hostMs[k];
     if (m_outputStream.is_open()) m_outputStream << std::flush;
     m_readingCount++;
     return processed;
+}
+
+void GridSlamProcessor::prepareMotionDraws() {
+    MotionDraws& md = m_motionDraws;
+    const size_t n = m_particles.size();
+    md.b.resize(3 * n); md.r.resize(3 * n); md.theta.resize(n); md.sn.resize(n); md.cs.resize(n);
+    md.before = Drand48Stream::peek();
+    Drand48Stream ahead(md.before);
+    for (size_t i = 0; i < n; i++) {
+        ahead.polar(md.b[3 * i], md.r[3 * i]);
+        ahead.polar(md.b[3 * i + 1], md.r[3 * i + 1]);
+        ahead.polar(md.b[3 * i + 2], md.r[3 * i + 2]);
+        const double th = m_particles[i].pose.theta;
+        md.theta[i] = th; md.sn[i] = sin(th); md.cs[i] = cos(th);
+    }
+    md.after = ahead.state();
+    md.valid = true;
 }
 
 std::ofstream& GridSlamProcessor::outputStream() { return m_outputStream; }
