@@ -194,6 +194,11 @@ int gm_download_map(gm_ctx* ctx, uint32_t particle, gm_map_info* info, int32_t* 
  * (gm_map_info: patches_x * 32, patches_y * 32). */
 int gm_export_occupancy(gm_ctx* ctx, uint32_t particle, double occ_thresh, int8_t* out, uint32_t width, uint32_t height);
 int gm_map_digest(gm_ctx* ctx, uint32_t first, uint32_t count, gm_digest* out /*count*/);
+/* replaces: the bookkeeping behind ScanMatcher::registerScan's return value (scanmatcher/scanmatcher.cpp:317-341: the summed
+ * change of PointAccumulator::entropy(), include/gmapping/scanmatcher/smmap.h:68-79, over every cell update of the scan).  The sum
+ * telescopes per cell: out[i] = sum over the visited cells of map first + i of (entropy - log 2); the return value of a
+ * registration is this figure after it minus before it (equal to the reference's sequential sum up to rounding). */
+int gm_map_entropy(gm_ctx* ctx, uint32_t first, uint32_t count, double* out /*count*/);
 /* replaces: the MAP_CONSISTENCY_CHECK block of GridSlamProcessor::processScan, gridfastslam/gridslamprocessor.cpp:82-143 (every
  * patch's share count against the number of particle maps that point at it): the references are recounted from the patch
  * directories of the live particles and compared with the pool's reference counts, and "referenced" with "off the free stack".

@@ -331,7 +331,7 @@ void dumpScanMatcherProcessor(Writer& w, const SensorMap& sensorMap, const std::
     smp.init();
     std::ifstream is(log.c_str());
     InputSensorStream input(sensorMap, is);
-    std::vector<double> poses;
+    std::vector<double> poses, last;
     int n = 0;
     while (input && n < max_readings) {
         const SensorReading* r = nullptr;
@@ -342,11 +342,37 @@ void dumpScanMatcherProcessor(Writer& w, const SensorMap& sensorMap, const std::
             smp.processScan(*rr);
             const OrientedPoint p = smp.getPose();
             poses.push_back(p.x); poses.push_back(p.y); poses.push_back(p.theta);
+            last.resize(rr->size());
+            rr->rawView(last.data(), smp.getMap().getDelta());
             n++;
         }
         delete r;
     }
     w.vec("SMPP", poses);
+    // ScanMatcher::icpOptimize / icpStep (scanmatcher.cpp:356-375, scanmatcher.h:88-165) on the map built above, from two poses
+    // near the last one (the second with a heading beyond pi: the returned heading is wrapped).  Record: pose + score, twice each
+    if (!last.empty()) {
+        const OrientedPoint at = smp.getPose();
+        const OrientedPoint inits[2] = {OrientedPoint(at.x + 0.03, at.y - 0.02, at.theta + 0.01), OrientedPoint(at.x - 0.05, at.y + 0.04, at.theta + 2 * M_PI + 0.02)};
+        std::vector<double> icp;
+        for (int k = 0; k < 2; k++) {
+            OrientedPoint a(0, 0, 0), b(0, 0, 0);
+            const double so = smp.matcher().icpOptimize(a, smp.getMap(), inits[k], last.data());
+            const double ss = smp.matcher().icpStep(b, smp.getMap(), inits[k], last.data());
+            const double row[8] = {a.x, a.y, a.theta, so, b.x, b.y, b.theta, ss};
+            icp.insert(icp.end(), row, row + 8);
+        }
+        w.vec("ICPO", icp);
+        // ScanMatcher::registerScan's return value (scanmatcher.cpp:317-341: the summed entropy change of the cell updates) for
+        // two registrations of that scan into a copy of the map, the second from a slightly different pose
+        ScanMatcherMap copy(smp.getMap());
+        std::vector<double> gains;
+        for (int k = 0; k < 2; k++) {
+            smp.matcher().invalidateActiveArea();
+            gains.push_back(smp.matcher().registerScan(copy, OrientedPoint(at.x + 0.11 * k, at.y - 0.07 * k, at.theta + 0.05 * k), last.data()));
+        }
+        w.vec("RSEN", gains);
+    }
     const ScanMatcherMap& m = smp.getMap();
     MapDigest d = TraceProcessor::digest(m, nullptr);
     w.rec("SMPD", &d, sizeof d);

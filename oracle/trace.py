@@ -89,6 +89,10 @@ def read_trace(path):
             final["smp_geometry"] = np.frombuffer(p, dtype="<i4").copy()
         elif tag == "BBOX":  # SensorLog: readings, boundingBox xmin ymin xmax ymax, first range pose
             final["sensorlog_bbox"] = np.frombuffer(p, dtype="<f8").copy()
+        elif tag == "ICPO":  # ScanMatcher::icpOptimize / icpStep from two poses: (pose xyz, score) of each
+            final["icp"] = np.frombuffer(p, dtype="<f8").reshape(-1, 8).copy()
+        elif tag == "RSEN":  # ScanMatcher::registerScan return values (entropy change) of two standalone registrations
+            final["register_gain"] = np.frombuffer(p, dtype="<f8").copy()
         elif tag == "ISEQ":  # integrateScanSequence on a second filter: pose xyz, weight, weightSum, depth, leaf pose xyz, map geometry (6), path nodes
             final["integrate"] = np.frombuffer(p, dtype="<f8").reshape(-1, 16).copy()
         elif tag == "DONE":

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libgm_b200.so")
 
 EXPORTS = ["gm_create", "gm_destroy", "gm_last_error", "gm_set_laser", "gm_set_matching", "gm_default_matching",
            "gm_init_particles", "gm_score", "gm_likelihood_and_score", "gm_scanmatch", "gm_normalize_neff",
-           "gm_resample_indexes", "gm_register", "gm_map_info_get", "gm_download_map", "gm_map_digest",
+           "gm_resample_indexes", "gm_register", "gm_map_info_get", "gm_download_map", "gm_map_digest", "gm_map_entropy",
            "gm_get_stats", "gm_particles", "gm_optimize", "gm_compute_active_area", "gm_upload_map", "gm_export_occupancy", "gm_clone", "gm_set_async_register", "gm_synchronize",
            "gm_dist_unique_id", "gm_dist_init", "gm_dist_register", "gm_dist_copy_particles", "gm_dist_plan", "gm_scanmatch_weights", "gm_check_refcounts", "gm_set_fused_register", "gm_scanmatch_weights_begin", "gm_scanmatch_weights_end"]
 
@@ -97,6 +97,7 @@ def load_library(path=LIB_PATH):
     L.gm_download_map.argtypes = [vp, C.c_uint32, C.POINTER(MapInfo), vp, vp, C.c_uint32]
     L.gm_upload_map.argtypes = [vp, C.c_uint32, C.POINTER(MapInfo), vp, vp, C.c_uint32]
     L.gm_map_digest.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
+    L.gm_map_entropy.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
     L.gm_export_occupancy.argtypes = [vp, C.c_uint32, C.c_double, vp, C.c_uint32, C.c_uint32]
     L.gm_optimize.argtypes = [vp, C.c_uint32, up, dp, dp, dp, dp]
     L.gm_get_stats.argtypes = [vp, C.POINTER(Stats)]

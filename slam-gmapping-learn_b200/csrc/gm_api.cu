@@ -786,6 +786,21 @@ int gm_map_digest(gm_ctx* ctx, uint32_t first, uint32_t count, gm_digest* out) {
     return GM_OK;
 }
 
+int gm_map_entropy(gm_ctx* ctx, uint32_t first, uint32_t count, double* out) {
+    if (int r = ready(ctx, true)) return r;
+    if (!out || first + count > ctx->n) return fail(ctx, GM_ERR_ARG, "gm_map_entropy: bad argument");
+    if (!count) return GM_OK;
+    DigestArgs a;
+    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.visits = ctx->pool.visits; a.means = ctx->pool.means; a.occ = ctx->pool.occ; a.first = first; a.out = nullptr;
+    double* d = reinterpret_cast<double*>(ctx->d_digest);  // scratch: seven words per particle
+    launch_entropy(a, d, count, ctx->st);
+    ctx->stats.launches++;
+    if (int r = check_launch(ctx, "k_entropy")) return r;
+    CK(cudaMemcpyAsync(out, d, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return GM_OK;
+}
+
 int gm_check_refcounts(gm_ctx* ctx, uint64_t* mismatches_out, uint64_t* referenced_out) {
     if (int r = ready(ctx, true)) return r;
     unsigned long long* out = ctx->d_digest;  // scratch: three words

@@ -1446,6 +1446,34 @@ __global__ void __launch_bounds__(1024) k_resample(const double* __restrict__ w,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Sum over the visited cells of one map of PointAccumulator::entropy() - log 2 (smmap.h:68-79; a cell nobody has looked at
+// has entropy log 2 and contributes nothing).  registerScan's return value -- the sum of the entropy change of every cell
+// update, scanmatcher.cpp:317-341 -- telescopes per cell, so it is this quantity after the registration minus before.
+// Fixed thread -> cell assignment and a fixed reduction shape: the same map gives the same bits.
+__global__ void __launch_bounds__(256) k_entropy(DigestArgs A, double* out) {
+    __shared__ double red[8];
+    const unsigned p = A.first + blockIdx.x;
+    const Geom g = A.geom[p];
+    const int* dirp = A.dir + (size_t)p * A.dir_cap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double acc = 0.;
+    for (int e = warp; e < g.npx * g.npy; e += nw) {
+        const int id = dirp[e];
+        if (id < 0) continue;
+        for (int i = lane; i < kPatchCells; i += 32) {
+            const int n = A.pool[(size_t)id * kPatchCells + i].z, v = A.visits[(size_t)id * kPatchCells + i];
+            if (!v) continue;
+            double h = 0.;
+            if (n != v && n != 0) { const double x = (double)n / (double)v; h = -(x * log(x) + (1. - x) * log(1. - x)); }
+            acc += h - 0.6931471805599453;
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0.; for (int w = 0; w < nw; w++) t += red[w]; out[blockIdx.x] = t; }
+}
+
 __global__ void __launch_bounds__(256) k_digest(DigestArgs A) {
     __shared__ unsigned long long acc[7];
     const unsigned p = A.first + blockIdx.x;
@@ -1603,6 +1631,7 @@ void launch_resample(const double* w, unsigned n, double u01, double* cum, doubl
     k_resample<<<1, 1024, 0, st>>>(w, n, u01, cum, tgt, idx, emitted);
 }
 void launch_digest(const DigestArgs& a, unsigned n, cudaStream_t st) { k_digest<<<n, 256, 0, st>>>(a); }
+void launch_entropy(const DigestArgs& a, double* out, unsigned n, cudaStream_t st) { k_entropy<<<n, 256, 0, st>>>(a, out); }
 void launch_export_list(const int* dirp, Geom g, int* list, int* count, cudaStream_t st) { k_export_list<<<64, 256, 0, st>>>(dirp, g, list, count); }
 void launch_export_gather(const int4* pool, const int* visits, const int* list, int4* out, int n, cudaStream_t st) { k_export_gather<<<n, 256, 0, st>>>(pool, visits, list, out); }
 

@@ -48,7 +48,7 @@ class SCANMATCHER_EXPORT ScanMatcher {
     double optimize(OrientedPoint& mean, CovarianceMatrix& cov, const ScanMatcherMap& map, const OrientedPoint& p, const double* readings) const;
     double likelihood(double& lmax, OrientedPoint& mean, CovarianceMatrix& cov, const ScanMatcherMap& map, const OrientedPoint& p,
                       const double* readings);
-    // ICP variants (scanmatcher.cpp:356-375): not on the particle-update path; declared for source compatibility, abort if called
+    // ICP variants (scanmatcher.cpp:356-375, scanmatcher.h:88-165): host functions; the reference's pose correction is commented out, see scanmatcher.cpp
     double icpOptimize(OrientedPoint& pnew, const ScanMatcherMap& map, const OrientedPoint& p, const double* readings) const;
     double icpStep(OrientedPoint& pret, const ScanMatcherMap& map, const OrientedPoint& p, const double* readings) const;
 

@@ -28,7 +28,7 @@ class SCANMATCHER_EXPORT ScanMatcherProcessor {
     void setRegistrationParameters(double regScore, double critScore);
     void setmaxMove(double mmove) { m_maxMove = mmove; }
     ScanMatcher& matcher() { return m_matcher; }
-    bool useICP;  // icpOptimize instead of the hill-climb (not on the B200 path: aborts when used)
+    bool useICP;  // icpOptimize instead of the hill-climb
 
     // ---- operation
     void init();

@@ -5,6 +5,7 @@
 #include <cassert>
 #include <cmath>
 #include <cstring>
+#include <iostream>
 #include <vector>
 
 #include "devicemap.h"
@@ -127,10 +128,15 @@ double ScanMatcher::registerScan(ScanMatcherMap& map, const OrientedPoint& p, co
         b200::fatal("ScanMatcher::registerScan on one map of a device-resident particle set: register through GridSlamProcessor "
                     "(gm_register updates all particles in one launch)");
     const double pose[3] = {p.x, p.y, p.theta};
+    // the return value (scanmatcher.cpp:317-341): the summed entropy change of every cell update, only formed when free space
+    // is traced; it telescopes per cell, so it is the map's entropy figure after the registration minus before
+    double before = 0, after = 0;
+    if (m_generateMap) r->ctx->check(gm_map_entropy(r->ctx->h, 0, 1, &before), "gm_map_entropy");
     r->ctx->check(gm_register(r->ctx->h, readings, pose, nullptr), "gm_register");
+    if (m_generateMap) r->ctx->check(gm_map_entropy(r->ctx->h, 0, 1, &after), "gm_map_entropy");
     r->stale = true;
     m_activeAreaComputed = true;
-    return 0;
+    return after - before;
 }
 
 // ------------------------------------------------------------------------------------------ sampled variants
@@ -259,11 +265,63 @@ double ScanMatcher::likelihood(double& _lmax, OrientedPoint& _mean, CovarianceMa
     return log(lcum) + lmax;
 }
 
-// ICP variants (scanmatcher.cpp:356-375, scanmatcher.h icpStep): outside the per-scan particle update
-static double notOnPath(const char* what) {
-    b200::fatal(std::string(what) + " is not part of the per-scan particle update and is not implemented in this build (SURVEY.md §2 row 9)");
+// ICP variants (include/gmapping/scanmatcher/scanmatcher.h:88-165, scanmatcher/scanmatcher.cpp:356-375): outside the per-scan
+// particle update, host functions over the map's mirror.  In the reference the call that would turn the
+// point pairs into a pose correction (icpNonlinearStep) is commented out: icpStep pairs every selected beam's end point with
+// the nearest occupied cell mean of its window, reports how many pairs it found on stderr, returns the pose it was given
+// (heading wrapped) and score(map, p, readings).  icpOptimize therefore stops after one step with score(map, init, readings).
+double ScanMatcher::icpStep(OrientedPoint& pret, const ScanMatcherMap& map, const OrientedPoint& p, const double* readings) const {
+    OrientedPoint lp = p;
+    lp.x += cos(p.theta) * m_laserPose.x - sin(p.theta) * m_laserPose.y;
+    lp.y += sin(p.theta) * m_laserPose.x + cos(p.theta) * m_laserPose.y;
+    lp.theta += m_laserPose.theta;
+    // (the reference scales the free-cell offset by the resolution twice here: delta * (delta * freeCellRatio))
+    const double freeOffset = map.getDelta() * (map.getDelta() * m_freeCellRatio);
+    unsigned int skip = 0, npairs = 0;
+    for (unsigned int b = m_initialBeamsSkip; b < m_laserBeams; b++) {
+        const double r = readings[b];
+        skip++;
+        skip = skip > m_likelihoodSkip ? 0 : skip;
+        if (r > m_usableRange || r == 0.0) continue;
+        if (skip) continue;
+        const double dirx = cos(lp.theta + m_laserAngles[b]), diry = sin(lp.theta + m_laserAngles[b]);
+        const Point phit(lp.x + r * dirx, lp.y + r * diry);
+        const IntPoint iphit = map.world2map(phit);
+        const Point pfree = Point(lp.x + (r - freeOffset) * dirx, lp.y + (r - freeOffset) * diry) - phit;
+        const IntPoint ipfree = map.world2map(pfree);
+        bool found = false;
+        for (int xx = -m_kernelSize; xx <= m_kernelSize && !found; xx++)
+            for (int yy = -m_kernelSize; yy <= m_kernelSize; yy++) {
+                const IntPoint pr = iphit + IntPoint(xx, yy), pf = pr + ipfree;
+                const PointAccumulator& cell = map.cell(pr);
+                const PointAccumulator& fcell = map.cell(pf);
+                if (((double)cell) > m_fullnessThreshold && ((double)fcell) < m_fullnessThreshold) { found = true; break; }  // which cell wins does not matter: only the count is used
+            }
+        if (found) npairs++;
+    }
+    const OrientedPoint result(0, 0, 0);
+    std::cerr << "result(" << npairs << ")=" << result.x << " " << result.y << " " << result.theta << std::endl;
+    pret.x = p.x + result.x;
+    pret.y = p.y + result.y;
+    pret.theta = p.theta + result.theta;
+    pret.theta = atan2(sin(pret.theta), cos(pret.theta));
+    return score(map, p, readings);
 }
-double ScanMatcher::icpOptimize(OrientedPoint&, const ScanMatcherMap&, const OrientedPoint&, const double*) const { return notOnPath("ScanMatcher::icpOptimize"); }
-double ScanMatcher::icpStep(OrientedPoint&, const ScanMatcherMap&, const OrientedPoint&, const double*) const { return notOnPath("ScanMatcher::icpStep"); }
+
+double ScanMatcher::icpOptimize(OrientedPoint& pnew, const ScanMatcherMap& map, const OrientedPoint& init, const double* readings) const {
+    double currentScore;
+    double sc = score(map, init, readings);
+    OrientedPoint start = init;
+    pnew = init;
+    int iterations = 0;
+    do {
+        currentScore = sc;
+        sc = icpStep(pnew, map, start, readings);
+        start = pnew;
+        iterations++;
+    } while (sc > currentScore);
+    std::cerr << "i=" << iterations << std::endl;
+    return currentScore;
+}
 
 }  // namespace GMapping

@@ -155,6 +155,16 @@ def check_trace(case, g, tr, exact=False):
     assert np.abs(fin["smp_poses"] - g.smp_poses).max() <= ptol, "%s: ScanMatcherProcessor poses" % case
     assert np.array_equal(digest_rows(fin["smp_digest"])[:, :5], digest_rows(g.smp_digest)[:, :5]), "%s: ScanMatcherProcessor map" % case
     assert np.array_equal(fin["smp_geometry"], g.smp_geometry), "%s: ScanMatcherProcessor map geometry" % case
+    # ScanMatcher::icpOptimize / icpStep (scanmatcher.cpp:356-375, scanmatcher.h:88-165) on that map from two poses: the pose
+    # handed back (heading wrapped) and the score, which is score() at the initial pose
+    got, want = fin["icp"], g.icp
+    assert got.shape == want.shape == (2, 8), "%s: icp record" % case
+    np.testing.assert_allclose(got[:, [0, 1, 2, 4, 5, 6]], want[:, [0, 1, 2, 4, 5, 6]], rtol=0, atol=0 if exact else 1e-12, err_msg="%s: icpOptimize / icpStep poses" % case)
+    np.testing.assert_allclose(got[:, [3, 7]], want[:, [3, 7]], rtol=0 if exact else 1e-9, atol=0, err_msg="%s: icpOptimize / icpStep scores" % case)
+    # ScanMatcher::registerScan's return value (scanmatcher.cpp:317-341): the reference sums the entropy change update by update,
+    # the device forms entropy(after) - entropy(before) over the map -- equal up to the rounding of ~1e5 additions (and 0 without
+    # free-space tracing, where the reference adds nothing)
+    np.testing.assert_allclose(fin["register_gain"], g.register_gain, rtol=1e-9, atol=1e-9, err_msg="%s: registerScan return value" % case)
     # integrateScanSequence (gridslamprocessor_tree.cpp:149-224) on a second, small filter: poses, weights, trajectory depth, the
     # leaves' poses and the (resized) map geometry of every particle
     got, want = fin["integrate"], g.integrate

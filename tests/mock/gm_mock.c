@@ -346,6 +346,30 @@ int gm_map_digest(gm_ctx* c, uint32_t first, uint32_t count, gm_digest* out) {
     return GM_OK;
 }
 
+int gm_map_entropy(gm_ctx* c, uint32_t first, uint32_t count, double* out) {
+    int r = ready(c);
+    if (r) return r;
+    if (!out || first + count > c->n) return fail(c, GM_ERR_ARG, "gm_map_entropy: bad argument");
+    for (uint32_t k = 0; k < count; k++) {
+        const orc_map* m = c->maps[first + k];
+        const int64_t np = orc_map_patch_count(m);
+        int32_t* coords = (int32_t*)malloc(sizeof(int32_t) * 2 * (size_t)(np ? np : 1));
+        orc_cell* cells = (orc_cell*)malloc(sizeof(orc_cell) * 1024 * (size_t)(np ? np : 1));
+        orc_map_export(m, coords, cells, np);
+        double acc = 0;
+        for (int64_t i = 0; i < np * 1024; i++) {
+            const int n = cells[i].n, v = cells[i].visits;
+            if (!v) continue;
+            double h = 0;
+            if (n != v && n != 0) { const double x = (double)n / (double)v; h = -(x * log(x) + (1. - x) * log(1. - x)); }
+            acc += h - 0.6931471805599453;
+        }
+        out[k] = acc;
+        free(coords); free(cells);
+    }
+    return GM_OK;
+}
+
 /* the mock's maps own their patches outright (orc_map_clone copies): there are no shared patches to miscount */
 int gm_check_refcounts(gm_ctx* c, uint64_t* mismatches_out, uint64_t* referenced_out) {
     int r = ready(c);

@@ -115,7 +115,7 @@ def run_case(name, log_kw, par):
              best=np.array(tr["final"]["best"]), ros_map_digest=tr["final"]["ros_map_digest"], ros_map_info=tr["final"]["ros_map_info"],
              trajectories=tr["final"]["trajectories"], smp_poses=tr["final"]["smp_poses"], smp_digest=tr["final"]["smp_digest"],
              smp_geometry=tr["final"]["smp_geometry"], sensorlog_bbox=tr["final"]["sensorlog_bbox"],
-             integrate=tr["final"]["integrate"])
+             integrate=tr["final"]["integrate"], icp=tr["final"]["icp"], register_gain=tr["final"]["register_gain"])
     a.update(gfs_sha256=np.array(hashlib.sha256(gfs).hexdigest()), gfs_bytes=np.array(len(gfs)),
              gfs_tags=np.array(" ".join(l.split(b" ", 1)[0].decode() for l in gfs.splitlines() if l)))
     path = os.path.join(GOLD, name + ".npz")
