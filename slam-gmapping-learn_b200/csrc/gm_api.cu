@@ -53,6 +53,7 @@ static int create_ctx(gm_ctx** out, const gm_config* cfg, gm_ctx* share_with) {
         CKC(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CKC(cudaStreamCreateWithPriority(&c->st_w, cudaStreamNonBlocking, hi));
     }
+    if (const char* e = getenv("GM_B200_SM_WIDE_BELOW")) c->sm_wide_below = (uint32_t)std::max(0, atoi(e));
     CKC(cudaEventCreate(&c->ev0)); CKC(cudaEventCreate(&c->ev1)); CKC(cudaEventCreate(&c->evw0)); CKC(cudaEventCreate(&c->evw1));
     CKC(cudaEventCreate(&c->evr0)); CKC(cudaEventCreate(&c->evr1)); CKC(cudaEventCreateWithFlags(&c->ev_sm, cudaEventDisableTiming));
     size_t cap = cfg->pool_patches;
@@ -255,7 +256,7 @@ static int run_eval(gm_ctx* ctx, int mode, uint32_t count, const uint32_t* parti
     a.query = mode; a.particle_idx = ctx->d_qidx; a.zero_patch = ctx->pool.cap;
     derive_params(a.P);
     if (int r = prepare_scanmatch(ctx)) return r;
-    launch_scanmatch(a, count, ctx->st);
+    launch_scanmatch(a, count, false, ctx->st);
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_scanmatch (query)")) return r;
     if (s_out) CK(cudaMemcpyAsync(s_out, ctx->d_qs, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->st));
@@ -300,7 +301,7 @@ int gm_scanmatch(gm_ctx* ctx, const double* ranges, double* poses_inout, double 
     a.valid_score_beams = count_score_beams(ctx, ranges);
     if (int r = prepare_scanmatch(ctx)) return r;
     CK(cudaEventRecord(ctx->ev0, ctx->st));
-    launch_scanmatch(a, n, ctx->st);
+    launch_scanmatch(a, n, n <= ctx->sm_wide_below, ctx->st);
     CK(cudaEventRecord(ctx->ev1, ctx->st));
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_scanmatch")) return r;
@@ -361,7 +362,7 @@ int gm_scanmatch_weights_begin(gm_ctx* ctx, const double* ranges, const double* 
     a.valid_score_beams = count_score_beams(ctx, ranges);
     if (int r = prepare_scanmatch(ctx)) return r;
     CK(cudaEventRecord(ctx->ev0, ctx->st));
-    launch_scanmatch(a, n, ctx->st);
+    launch_scanmatch(a, n, n <= ctx->sm_wide_below, ctx->st);
     CK(cudaEventRecord(ctx->ev1, ctx->st));
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_scanmatch")) return r;

@@ -56,6 +56,9 @@ struct gm_ctx {
     Counters* d_counters = nullptr;
     Counters* d_counters_sm = nullptr;  // gm_scanmatch_weights' own: a registration queued right behind the scan match zeroes the others
     bool fused_register = false;        // gm_set_fused_register
+    // launches of at most this many particles use k_scanmatch's wide shape (GM_B200_SM_WIDE_BELOW).  Measured on a B200 at 1081 beams:
+    // 512 particles 1.32 -> 1.10 ms, 1024: 2.04 -> 1.87, 2048: 3.56 -> 3.51, 4096: 6.61 -> 6.77 (profiles/experiments_r02.json)
+    uint32_t sm_wide_below = 2048;
     bool sw_pending = false; uint32_t sw_total = 0; double sw_gain = 1;  // between gm_scanmatch_weights_begin and _end
     double* d_inv_n = nullptr;
     size_t scanmatch_smem = 0;

@@ -105,6 +105,9 @@ __device__ __forceinline__ int ldg_if(const int* p, bool pred, int dflt) {
 #ifndef GM_SM_MIN_CTAS
 #define GM_SM_MIN_CTAS 3  // resident CTAs per SM k_scanmatch is compiled for (72 registers); 4 (56 registers, spills) measured slower
 #endif
+#ifndef GM_SM_WIDE_CTAS
+#define GM_SM_WIDE_CTAS 2  // resident CTAs per SM of the wide (2 x 288 threads) shape
+#endif
 constexpr int kSmThreads = 288;
 constexpr int kSmGroups = kSmThreads / 6;  // 48 beam groups x 6 candidate poses: every thread works
 
@@ -364,6 +367,10 @@ struct SmShared {
     int phase, key_ok[3], key_kind[3], fill_kind[3], last_move;  // table kinds: 0 (cos, sin), 1 end-point offsets r * (cos, sin)
 };
 
+// the wide shape (two half-CTAs per particle, see k_scanmatch): what the upper half hands to the lower one
+template <int WIDE> struct SmWide { double s[kSmThreads], l[kSmThreads]; unsigned c[kSmThreads], v[kSmThreads]; };
+template <> struct SmWide<0> {};
+
 // candidate pose m of a hill-climb round around `cur` (scanmatcher.cpp:441-494: Front, Back, Left, Right, TurnLeft, TurnRight)
 __device__ __forceinline__ void candidate(const double* cur, int m, double ldelta, double adelta, double (&out)[3]) {
     out[0] = cur[0]; out[1] = cur[1]; out[2] = cur[2];
@@ -431,10 +438,18 @@ __device__ __noinline__ void plan_round(double lpx, double lpy, double lpt, SmSh
 // A.query >= 0, one standalone score()/likelihoodAndScore() per CTA.
 // dynamic shared memory: three (cos, sin) tables of nbeams double2 each.
 // QUERY = (A.query >= 0); without it the particle is the block index, which keeps the per-particle pointers in uniform registers
-template <bool K1, bool QUERY>
-__global__ void __launch_bounds__(kSmThreads, GM_SM_MIN_CTAS) k_scanmatch(ScanMatchArgs A) {
+//
+// Every thread sums the beams it is dealt in TWO chains -- the even and the odd ones of its sequence -- and adds the two at the
+// end.  WIDE = 1 is the shape for few particles per GPU (a launch that does not fill the machine is as long as its longest
+// hill climb, one dependent chain of evaluations): 2 x 288 threads per particle, the upper half takes the odd beams of the
+// lower half's sequences, hands its chains over through shared memory, and from there on everything is the narrow shape's.
+// Same sums in the same order: the two shapes give the same bits.
+template <bool K1, bool QUERY, int WIDE>
+__global__ void __launch_bounds__(kSmThreads * (1 + WIDE), WIDE ? GM_SM_WIDE_CTAS : GM_SM_MIN_CTAS) k_scanmatch(ScanMatchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SmShared S;
+    __shared__ SmWide<WIDE> W;
+    constexpr int kThreads = kSmThreads * (1 + WIDE);
     const DevParams& P = A.P;
     double2* const tabs = reinterpret_cast<double2*>(smem_raw);
     const unsigned q = blockIdx.x, p = QUERY ? A.particle_idx[q] : q;
@@ -442,6 +457,7 @@ __global__ void __launch_bounds__(kSmThreads, GM_SM_MIN_CTAS) k_scanmatch(ScanMa
     // r * (cos, sin), NaN for the beams score() skips, and the beam loop reads nothing else
     const int premul = (K1 && A.P.free_q[0][0] != INT_MIN) ? 1 : 0;
     const int t = threadIdx.x;
+    const int half = WIDE ? (t >= kSmThreads ? 1 : 0) : 0, tt = t - half * kSmThreads;  // tt: the thread of the narrow shape this one works for
     MatchCtx M;
     M.dirp_s = &S.dirp; M.bbox_s = &S.bbox; M.pool = A.pool; M.visits = A.visits; M.means = A.means; M.occ = A.occ; M.inv_n = A.inv_n; M.g = A.geom[p];
     M.zero_patch = A.zero_patch;
@@ -467,7 +483,7 @@ __global__ void __launch_bounds__(kSmThreads, GM_SM_MIN_CTAS) k_scanmatch(ScanMa
         __syncthreads();
         const int* dirp = A.dir + (size_t)p * A.dir_cap;
         int lox = INT_MAX, loy = INT_MAX, hix = -1, hiy = -1;
-        for (int e = t; e < M.g.npx * M.g.npy; e += kSmThreads)
+        for (int e = t; e < M.g.npx * M.g.npy; e += kThreads)
             if (__ldg(dirp + e) >= 0) { const int px = e / M.g.npy, py = e - px * M.g.npy; lox = min(lox, px); hix = max(hix, px); loy = min(loy, py); hiy = max(hiy, py); }
         lox = __reduce_min_sync(0xffffffffu, lox); loy = __reduce_min_sync(0xffffffffu, loy);
         hix = __reduce_max_sync(0xffffffffu, hix); hiy = __reduce_max_sync(0xffffffffu, hiy);
@@ -486,7 +502,7 @@ __global__ void __launch_bounds__(kSmThreads, GM_SM_MIN_CTAS) k_scanmatch(ScanMa
             const double theta = S.fill_theta[j];
             const int kind = S.fill_kind[j];
             double2* tab = tabs + (size_t)phys * P.nbeams;
-            for (unsigned b = P.beam_skip + t; b < P.nbeams; b += kSmThreads) {
+            for (unsigned b = P.beam_skip + t; b < P.nbeams; b += kThreads) {
                 double sn, cs;
                 sincos(theta + __ldg(A.angles + b), &sn, &cs);
                 if (kind) {
@@ -502,9 +518,9 @@ __global__ void __launch_bounds__(kSmThreads, GM_SM_MIN_CTAS) k_scanmatch(ScanMa
         // ---- evaluate: thread t works for candidate cand[t % ncand] on beams t / ncand, + ngroups, ...
         const int mode = S.mode, nc = S.ncand;
         const bool multi = nc > 1;
-        const int ngroups = nc == 6 ? kSmGroups : kSmThreads / nc, grp = nc == 6 ? t / 6 : t / nc;
-        const int m = multi ? S.cand[nc == 6 ? t % 6 : t - grp * nc] : 0;
-        double acc_s = 0., acc_l = 0.;
+        const int ngroups = nc == 6 ? kSmGroups : kSmThreads / nc, grp = nc == 6 ? tt / 6 : tt / nc;
+        const int m = multi ? S.cand[nc == 6 ? tt % 6 : tt - grp * nc] : 0;
+        double acc_s = 0., acc_l = 0., acc_s1 = 0., acc_l1 = 0.;  // chains of the even / odd beams of this thread's sequence
         unsigned cnt = 0, valid = 0;
         if (grp < ngroups) {
             const double mlx = S.lx[m], mly = S.ly[m];
@@ -514,7 +530,8 @@ __global__ void __launch_bounds__(kSmThreads, GM_SM_MIN_CTAS) k_scanmatch(ScanMa
             const int fqx = mode ? P.free_q[1][0] : P.free_q[0][0], fqy = mode ? P.free_q[1][1] : P.free_q[0][1];  // (constant indexes)
             const double cexp = P.cexp, clik = P.clik, noHit = P.no_hit;
             const bool offsets = premul && mode == 0;  // the table in use holds end-point offsets
-            for (unsigned b = P.beam_skip + grp; b < P.nbeams; b += ngroups) {
+            unsigned odd = (unsigned)half;  // (two passes, even beams then odd beams, measured slower than the predicated adds below)
+            for (unsigned b = P.beam_skip + grp + half * ngroups; b < P.nbeams; b += (WIDE ? 2 * ngroups : ngroups), odd ^= (WIDE ? 0u : 1u)) {
                 double2 cs;
                 asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(cs.x), "=d"(cs.y) : "r"(tab_s + b * 16u));
                 double phx, phy;
@@ -530,14 +547,24 @@ __global__ void __launch_bounds__(kSmThreads, GM_SM_MIN_CTAS) k_scanmatch(ScanMa
                 double mx, my;
                 valid++;
                 const bool found = beam_match<K1>(P, M, mlx, mly, phx, phy, b, tab_s, A.ranges, free_off, fqx, fqy, mx, my);
-                if (found) { acc_s += exp_neg((mx * cexp) * mx + (my * cexp) * my, A.inv_n + kInvTable); cnt++; }  // ((-1/sigma)*mu)*mu, point.h:34-49
-                if (mode) { const double f = clik * (mx * mx + my * my); acc_l += found ? f : noHit; }
+                if (found) {  // ((-1/sigma)*mu)*mu, point.h:34-49
+                    const double e = exp_neg((mx * cexp) * mx + (my * cexp) * my, A.inv_n + kInvTable);
+                    if (odd) acc_s1 += e; else acc_s += e;
+                    cnt++;
+                }
+                if (mode) { const double f = clik * (mx * mx + my * my), a = found ? f : noHit; if (odd) acc_l1 += a; else acc_l += a; }
             }
         }
+        if constexpr (WIDE != 0) {  // the upper half's chains go to the thread of the lower half they belong to
+            if (half) { W.s[tt] = acc_s1; W.l[tt] = acc_l1; W.c[tt] = cnt; W.v[tt] = valid; }
+            __syncthreads();
+            if (!half) { acc_s1 = W.s[tt]; acc_l1 = W.l[tt]; cnt += W.c[tt]; valid += W.v[tt]; }
+        }
+        acc_s = acc_s + acc_s1; acc_l = acc_l + acc_l1;
         // ---- reduce (fixed shape: the sums do not depend on scheduling)
         const int warp = t >> 5, lane = t & 31;
         if (multi) {
-            S.part[t] = acc_s;
+            if (!half) S.part[tt] = acc_s;
             __syncthreads();
             if (warp < nc) {  // warp w sums the partials of candidate cand[w]: lane j takes groups j and j + 32 (ngroups <= 64)
                 double v = lane < ngroups ? S.part[nc * lane + warp] : 0.;
@@ -548,7 +575,7 @@ __global__ void __launch_bounds__(kSmThreads, GM_SM_MIN_CTAS) k_scanmatch(ScanMa
         } else {
             acc_s = warp_sum(acc_s); acc_l = warp_sum(acc_l);
             cnt = __reduce_add_sync(0xffffffffu, cnt); valid = __reduce_add_sync(0xffffffffu, valid);
-            if (lane == 0) { S.red[warp] = acc_s; S.red_l[warp] = acc_l; S.red_c[warp] = cnt; S.red_v[warp] = valid; }
+            if (lane == 0 && !half) { S.red[warp] = acc_s; S.red_l[warp] = acc_l; S.red_c[warp] = cnt; S.red_v[warp] = valid; }
         }
         __syncthreads();
         if (t != 0) continue;
@@ -1583,21 +1610,28 @@ void launch_install_patches(int* dirp, Geom g, const int* coords, const int4* st
 }
 size_t scanmatch_smem_bytes(unsigned nbeams) { return (size_t)3 * nbeams * sizeof(double2); }
 cudaError_t scanmatch_prepare(size_t smem) {
-    cudaError_t e = cudaFuncSetAttribute(k_scanmatch<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scanmatch<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scanmatch<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scanmatch<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_scanmatch<true, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scanmatch<false, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scanmatch<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scanmatch<false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scanmatch<true, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scanmatch<false, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     return e;
 }
-void launch_scanmatch(const ScanMatchArgs& a, unsigned n, cudaStream_t st) {
+void launch_scanmatch(const ScanMatchArgs& a, unsigned n, bool wide, cudaStream_t st) {
     const size_t smem = scanmatch_smem_bytes(a.P.nbeams);
     const bool k1 = a.P.kernel_size == 1 && a.P.thr_is_tenth;
     if (a.query < 0) {
-        if (k1) k_scanmatch<true, false><<<n, kSmThreads, smem, st>>>(a);
-        else k_scanmatch<false, false><<<n, kSmThreads, smem, st>>>(a);
+        if (wide) {
+            if (k1) k_scanmatch<true, false, 1><<<n, 2 * kSmThreads, smem, st>>>(a);
+            else k_scanmatch<false, false, 1><<<n, 2 * kSmThreads, smem, st>>>(a);
+        } else {
+            if (k1) k_scanmatch<true, false, 0><<<n, kSmThreads, smem, st>>>(a);
+            else k_scanmatch<false, false, 0><<<n, kSmThreads, smem, st>>>(a);
+        }
     } else {
-        if (k1) k_scanmatch<true, true><<<n, kSmThreads, smem, st>>>(a);
-        else k_scanmatch<false, true><<<n, kSmThreads, smem, st>>>(a);
+        if (k1) k_scanmatch<true, true, 0><<<n, kSmThreads, smem, st>>>(a);
+        else k_scanmatch<false, true, 0><<<n, kSmThreads, smem, st>>>(a);
     }
 }
 

@@ -65,7 +65,7 @@ struct DigestArgs {
 
 size_t scanmatch_smem_bytes(unsigned nbeams);
 cudaError_t scanmatch_prepare(size_t smem);
-void launch_scanmatch(const ScanMatchArgs& a, unsigned n, cudaStream_t st);
+void launch_scanmatch(const ScanMatchArgs& a, unsigned n, bool wide, cudaStream_t st);
 void launch_bounds(const BoundsArgs& a, unsigned n, unsigned threads, cudaStream_t st);
 void launch_relayout(const RelayoutArgs& a, unsigned n, cudaStream_t st);
 void launch_relayout_commit(const RelayoutArgs& a, unsigned n, cudaStream_t st);

@@ -263,6 +263,26 @@ def test_fused_scanmatch_weights_equals_the_separate_calls():
     ctx.close()
 
 
+@pytest.mark.parametrize("beams", [181, 1081])
+def test_wide_scanmatch_shape_gives_the_same_bits(monkeypatch, beams):
+    """k_scanmatch's wide shape (2 x 288 threads per particle, chosen for few particles per GPU: GM_B200_SM_WIDE_BELOW) sums the
+    same beams in the same order as the narrow one: poses, scores, likelihoods, match counts and evaluation counts are
+    bit-identical, in score() mode (hill climb) and likelihoodAndScore() mode (final evaluation)"""
+    out = []
+    for below in ("0", "1000000"):
+        monkeypatch.setenv("GM_B200_SM_WIDE_BELOW", below)
+        log, m, ctx, maps, poses, rng = _random_world(33, beams=beams, particles=9, scans=4)
+        r = log.ranges[3]
+        init = poses + rng.normal(0, [0.04, 0.04, 0.015], size=poses.shape)
+        logw = rng.normal(-40.0, 25.0, size=9)
+        res = ctx.scanmatch(r, init, 0.0)
+        rows, w, neff = ctx.scanmatch_weights(r, init, logw, 0.0, 3.0)
+        out.append(tuple(res) + (rows, w, np.float64(neff)))
+        ctx.close()
+    for a, b in zip(*out):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
 def test_register_then_copy_equals_copy_then_register():
     """GridSlamProcessor's early registration: registering the scan in every particle at its own pose and then copying
     particle j <- idx[j] gives, bit for bit, the maps of the reference's order (copy, then register each child at its
