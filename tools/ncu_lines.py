@@ -8,7 +8,8 @@ import sys
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+kernel = ["-k", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []  # optional third argument: kernel name regex
+out = subprocess.run(["ncu", "-i", rep] + kernel + ["--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 fname = ""
 hdr = None
