@@ -162,6 +162,10 @@ int gm_normalize_neff(gm_ctx* ctx, const double* log_weights, uint32_t n, double
 /* replaces: uniform_resampler<double,double>::resampleIndexes, include/gmapping/particlefilter/particlefilter.h:180-229;
  * u01 is the caller's drand48() draw.  emitted_out: how many indexes the walk produced (== n normally). */
 int gm_resample_indexes(gm_ctx* ctx, const double* weights, uint32_t n, double u01, uint32_t* idx_out, uint32_t* emitted_out);
+/* replaces: the same with its `nparticles` argument set -- GridSlamProcessor::processScan(reading, adaptParticles),
+ * include/gmapping/gridfastslam/gridslamprocessor.hxx:153-156 -> particlefilter.h:196-203: the interval is the total weight over
+ * n_out and n_out indexes come out (idx_out has n_out entries). */
+int gm_resample_indexes_n(gm_ctx* ctx, const double* weights, uint32_t n, uint32_t n_out, double u01, uint32_t* idx_out, uint32_t* emitted_out);
 
 /* replaces: the particle-copy + registerScan loops of GridSlamProcessor::resample, gridslamprocessor.hxx:184-296,
  * and the first-scan loop gridslamprocessor.cpp:617-633: (optional) remap particle j <- parent idx[j] by
@@ -173,6 +177,9 @@ int gm_register(gm_ctx* ctx, const double* ranges, const double* poses /*N*3*/, 
  * of gm_register(ranges, poses_of_parents, idx) -- a child starts from its parent's pose and map, so registering the scan
  * before or after the copy writes the same cells -- and lets the registration start before Neff is known. */
 int gm_copy_particles(gm_ctx* ctx, const uint32_t* idx /*N*/);
+/* the same when the resampling changes the particle count (adaptParticles): the new generation has n_new particles
+ * (1 <= n_new <= gm_config.max_particles), particle j continues parent idx[j] of the old one.  Single-GPU contexts only. */
+int gm_copy_particles_n(gm_ctx* ctx, const uint32_t* idx /*n_new*/, uint32_t n_new);
 
 /* replaces: ScanMatcher::computeActiveArea, scanmatcher/scanmatcher.cpp:83-254, as far as it is observable: the
  * bounding box of the scan at each particle's pose and the Map::resize it triggers.  (The active patch set itself

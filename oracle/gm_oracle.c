@@ -488,18 +488,22 @@ double orc_normalize(const double* logw, uint32_t n, double obs_sigma_gain, doub
 /* uniform_resampler::resampleIndexes: particlefilter.h:180-229 with the drand48() draw passed in
  * as u01.  indexes(n) is zero-initialised; emission beyond n (reference: out-of-bounds write) is
  * dropped.  Returns the number of emitted indexes (== n except for FP corner cases). */
-uint32_t orc_resample_indexes(const double* w, uint32_t n, double u01, uint32_t* idx) {
+uint32_t orc_resample_indexes(const double* w, uint32_t n, double u01, uint32_t* idx) { return orc_resample_indexes_n(w, n, n, u01, idx); }
+
+/* the same with the `nparticles` argument (particlefilter.h:196-203: `if (nparticles > 0) n = nparticles;` -- the interval is
+ * the total weight over n_out, indexes(n_out)) */
+uint32_t orc_resample_indexes_n(const double* w, uint32_t n, uint32_t n_out, double u01, uint32_t* idx) {
     double cweight = 0;
     for (uint32_t i = 0; i < n; i++) cweight += w[i];
-    double interval = cweight / n;
+    double interval = cweight / n_out;
     double target = interval * u01;
     cweight = 0;
-    for (uint32_t i = 0; i < n; i++) idx[i] = 0;
+    for (uint32_t i = 0; i < n_out; i++) idx[i] = 0;
     uint32_t k = 0;
     for (uint32_t i = 0; i < n; i++) {
         cweight += w[i];
         while (cweight > target) {
-            if (k < n) idx[k] = i;
+            if (k < n_out) idx[k] = i;
             k++;
             target += interval;
         }

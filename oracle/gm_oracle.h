@@ -72,6 +72,7 @@ int orc_grid_line(int x0, int y0, int x1, int y1, int32_t* pts /* 2*n */, int ma
 
 double orc_normalize(const double* logw, uint32_t n, double obs_sigma_gain, double* w_out);
 uint32_t orc_resample_indexes(const double* w, uint32_t n, double u01, uint32_t* idx_out);
+uint32_t orc_resample_indexes_n(const double* w, uint32_t n, uint32_t n_out, double u01, uint32_t* idx_out);
 
 void orc_seed(long seed);
 double orc_sample_gaussian(double sigma);

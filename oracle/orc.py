@@ -82,6 +82,7 @@ def lib():
     L.orc_grid_line.restype = C.c_int; L.orc_grid_line.argtypes = [C.c_int] * 4 + [vp, C.c_int]
     L.orc_normalize.restype = C.c_double; L.orc_normalize.argtypes = [dp, C.c_uint32, C.c_double, dp]
     L.orc_resample_indexes.restype = C.c_uint32; L.orc_resample_indexes.argtypes = [dp, C.c_uint32, C.c_double, vp]
+    L.orc_resample_indexes_n.restype = C.c_uint32; L.orc_resample_indexes_n.argtypes = [dp, C.c_uint32, C.c_uint32, C.c_double, vp]
     L.orc_seed.argtypes = [C.c_long]
     L.orc_sample_gaussian.restype = C.c_double; L.orc_sample_gaussian.argtypes = [C.c_double]
     L.orc_draw_from_motion.argtypes = [dp, dp, dp] + [C.c_double] * 4 + [dp]
@@ -202,10 +203,12 @@ def normalize(logw, gain=1.0):
     return w, neff
 
 
-def resample_indexes(w, u01):
+def resample_indexes(w, u01, n_out=None):
+    """n_out: the `nparticles` argument of uniform_resampler::resampleIndexes (None: as many indexes as weights)"""
     w = np.ascontiguousarray(w, dtype=np.float64)
-    idx = np.zeros(len(w), dtype=np.uint32)
-    k = lib().orc_resample_indexes(_dp(w), len(w), u01, idx.ctypes.data)
+    n_out = len(w) if n_out is None else int(n_out)
+    idx = np.zeros(n_out, dtype=np.uint32)
+    k = lib().orc_resample_indexes_n(_dp(w), len(w), n_out, u01, idx.ctypes.data)
     return idx, k
 
 

@@ -94,6 +94,32 @@ int main(int argc, char** argv) {
         }
     }
 
+    // ---- the same with the `nparticles` argument (processScan's adaptParticles): fewer and more indexes than weights
+    {
+        uniform_resampler<double, double> resampler;
+        const int sizes[6][2] = {{12, 8}, {12, 30}, {30, 7}, {257, 64}, {1000, 4096}, {4096, 512}};
+        for (int c = 0; c < 18; c++) {
+            const int n = sizes[c % 6][0], n_out = sizes[c % 6][1];
+            std::vector<double> w(n);
+            double sum = 0;
+            const int shape = c / 6;  // 0: uniform-ish, 1: peaked, 2: with exact zeros
+            for (int i = 0; i < n; i++) {
+                double v = uni();
+                if (shape == 1) v = v * v * v * v;
+                if (shape == 2 && (i % 3) == 0) v = 0;
+                w[i] = v; sum += v;
+            }
+            for (int i = 0; i < n; i++) w[i] /= sum;
+            const long seed = 2000 + c;
+            srand48(seed);
+            std::vector<unsigned int> idx = resampler.resampleIndexes(w, n_out);
+            const double hdr[3] = {(double)n, (double)n_out, (double)seed};
+            rec("RAHD", hdr, sizeof hdr);
+            rec("RAWT", w.data(), w.size() * sizeof(double));
+            rec("RAIX", idx.data(), idx.size() * sizeof(unsigned int));
+        }
+    }
+
     // ---- Gaussian sampler: sampleGaussian(sigma, seed) seeds and draws; then a run of draws incl. sigma == 0 (no draw consumed)
     {
         std::vector<double> out;

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libgm_b200.so")
 
 EXPORTS = ["gm_create", "gm_destroy", "gm_last_error", "gm_set_laser", "gm_set_matching", "gm_default_matching",
            "gm_init_particles", "gm_score", "gm_likelihood_and_score", "gm_scanmatch", "gm_normalize_neff",
-           "gm_resample_indexes", "gm_register", "gm_map_info_get", "gm_download_map", "gm_map_digest", "gm_map_entropy",
+           "gm_resample_indexes", "gm_resample_indexes_n", "gm_copy_particles", "gm_copy_particles_n", "gm_register", "gm_map_info_get", "gm_download_map", "gm_map_digest", "gm_map_entropy",
            "gm_get_stats", "gm_particles", "gm_optimize", "gm_compute_active_area", "gm_upload_map", "gm_export_occupancy", "gm_clone", "gm_set_async_register", "gm_synchronize",
            "gm_dist_unique_id", "gm_dist_init", "gm_dist_register", "gm_dist_copy_particles", "gm_dist_plan", "gm_scanmatch_weights", "gm_check_refcounts", "gm_set_fused_register", "gm_scanmatch_weights_begin", "gm_scanmatch_weights_end"]
 
@@ -91,6 +91,8 @@ def load_library(path=LIB_PATH):
     L.gm_scanmatch.argtypes = [vp, dp, dp, C.c_double, dp, dp, dp, up, up]
     L.gm_normalize_neff.argtypes = [vp, dp, C.c_uint32, C.c_double, dp, dp]
     L.gm_resample_indexes.argtypes = [vp, dp, C.c_uint32, C.c_double, up, up]
+    L.gm_resample_indexes_n.argtypes = [vp, dp, C.c_uint32, C.c_uint32, C.c_double, up, up]
+    L.gm_copy_particles_n.argtypes = [vp, up, C.c_uint32]
     L.gm_register.argtypes = [vp, dp, dp, up]
     L.gm_copy_particles.argtypes = [vp, up]
     L.gm_map_info_get.argtypes = [vp, C.c_uint32, C.POINTER(MapInfo)]
@@ -220,9 +222,11 @@ class GmContext:
         self._ck(self.L.gm_normalize_neff(self.h, _dp(lw), len(lw), float(obs_sigma_gain), _dp(w), C.byref(ne)))
         return w, ne.value
 
-    def resample_indexes(self, weights, u01):
-        w = _f64(weights); idx = np.zeros(len(w), dtype=np.uint32); em = C.c_uint32()
-        self._ck(self.L.gm_resample_indexes(self.h, _dp(w), len(w), float(u01), _up(idx), C.byref(em)))
+    def resample_indexes(self, weights, u01, n_out=None):
+        """n_out: uniform_resampler::resampleIndexes' `nparticles` (processScan's adaptParticles); None = as many as weights"""
+        w = _f64(weights); n_out = len(w) if n_out is None else int(n_out)
+        idx = np.zeros(n_out, dtype=np.uint32); em = C.c_uint32()
+        self._ck(self.L.gm_resample_indexes_n(self.h, _dp(w), len(w), n_out, float(u01), _up(idx), C.byref(em)))
         return idx, em.value
 
     def register(self, ranges, poses, idx=None):
@@ -233,9 +237,16 @@ class GmContext:
             ip = _up(idx)
         self._ck(self.L.gm_register(self.h, _dp(r), _dp(p), ip))
 
-    def copy_particles(self, idx):
-        idx = np.ascontiguousarray(idx, dtype=np.uint32); assert idx.shape == (self.n,)
-        self._ck(self.L.gm_copy_particles(self.h, _up(idx)))
+    def copy_particles(self, idx, n_new=None):
+        """n_new: the new generation's particle count when the resampling changes it (len(idx) == n_new)"""
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        if n_new is None:
+            assert idx.shape == (self.n,)
+            self._ck(self.L.gm_copy_particles(self.h, _up(idx)))
+        else:
+            assert idx.shape == (n_new,)
+            self._ck(self.L.gm_copy_particles_n(self.h, _up(idx), int(n_new)))
+            self.n = int(n_new)
 
     # ---- read-back
     def map_info(self, particle):

@@ -446,16 +446,21 @@ int gm_normalize_neff(gm_ctx* ctx, const double* log_weights, uint32_t n, double
 }
 
 int gm_resample_indexes(gm_ctx* ctx, const double* weights, uint32_t n, double u01, uint32_t* idx_out, uint32_t* emitted_out) {
+    return gm_resample_indexes_n(ctx, weights, n, n, u01, idx_out, emitted_out);
+}
+
+int gm_resample_indexes_n(gm_ctx* ctx, const double* weights, uint32_t n, uint32_t n_out, double u01, uint32_t* idx_out, uint32_t* emitted_out) {
     if (int r = ready_weights(ctx)) return r;
     if (!ctx->inited) return fail(ctx, GM_ERR_ARG, "gm_init_particles has not been called");
-    if (!weights || !idx_out || !n || n > ctx->weights_cap) return fail(ctx, GM_ERR_ARG, "gm_resample_indexes: bad argument");
+    if (!weights || !idx_out || !n || n > ctx->weights_cap || !n_out || n_out > ctx->weights_cap)
+        return fail(ctx, GM_ERR_ARG, "gm_resample_indexes: bad argument (n=%u, n_out=%u, capacity %u)", n, n_out, ctx->weights_cap);
     cudaStream_t sw = ctx->st_w;
     CK(cudaMemcpyAsync(ctx->d_w, weights, sizeof(double) * n, cudaMemcpyHostToDevice, sw));
     CK(cudaMemsetAsync(ctx->d_emitted, 0, sizeof(unsigned), sw));
-    launch_resample(ctx->d_w, n, u01, ctx->d_cum, ctx->d_tgt, ctx->d_widx, ctx->d_emitted, sw);
+    launch_resample(ctx->d_w, n, n_out, u01, ctx->d_cum, ctx->d_tgt, ctx->d_widx, ctx->d_emitted, sw);
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_resample")) return r;
-    CK(cudaMemcpyAsync(idx_out, ctx->d_widx, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, sw));
+    CK(cudaMemcpyAsync(idx_out, ctx->d_widx, sizeof(uint32_t) * n_out, cudaMemcpyDeviceToHost, sw));
     uint32_t em = 0;
     CK(cudaMemcpyAsync(&em, ctx->d_emitted, sizeof(uint32_t), cudaMemcpyDeviceToHost, sw));
     CK(cudaStreamSynchronize(sw));
@@ -652,6 +657,19 @@ int gm_copy_particles(gm_ctx* ctx, const uint32_t* idx) {
     if (!idx) return fail(ctx, GM_ERR_ARG, "gm_copy_particles: null argument");
     if (ctx->dist) return fail(ctx, GM_ERR_ARG, "gm_copy_particles: sharded context, use gm_dist_copy_particles");
     if (int r = gmi_remap(ctx, idx, ctx->n)) return r;
+    ctx->stats.total_ms[2] += ctx->stats.ms_remap;
+    return GM_OK;
+}
+
+int gm_copy_particles_n(gm_ctx* ctx, const uint32_t* idx, uint32_t n_new) {
+    if (int r = ready(ctx, true)) return r;
+    if (!idx) return fail(ctx, GM_ERR_ARG, "gm_copy_particles_n: null argument");
+    if (ctx->dist) return fail(ctx, GM_ERR_ARG, "gm_copy_particles_n: the particle count of a sharded context is fixed");
+    if (!n_new || n_new > ctx->max_particles)
+        return fail(ctx, GM_ERR_ARG, "gm_copy_particles_n: %u particles, the context was created for at most %u", n_new, ctx->max_particles);
+    const uint32_t old = ctx->n;
+    ctx->n = n_new;  // the new generation has n_new slots, its parents are among the old one's
+    if (int r = gmi_remap(ctx, idx, old)) { ctx->n = old; return r; }
     ctx->stats.total_ms[2] += ctx->stats.ms_remap;
     return GM_OK;
 }

@@ -1431,7 +1431,9 @@ __global__ void __launch_bounds__(1024) k_normalize(double* __restrict__ logw, c
 // resampleIndexes (particlefilter.h:180-229).  The cumulative weights c[i] and the targets t[k] are the
 // reference's sequentially rounded sums (two serial chains); since both are monotone, the walk
 // "while (c[i] > target) emit i" is exactly idx[k] = min{ i : c[i] > t[k] }, found by binary search.
-__global__ void __launch_bounds__(1024) k_resample(const double* __restrict__ w, unsigned n, double u01, double* __restrict__ cum,
+// n_out = the `nparticles` argument (processScan's adaptParticles): the interval is the total weight over n_out and n_out
+// indexes come out (particlefilter.h:196-203).
+__global__ void __launch_bounds__(1024) k_resample(const double* __restrict__ w, unsigned n, unsigned n_out, double u01, double* __restrict__ cum,
                                                    double* __restrict__ tgt, unsigned* __restrict__ idx, unsigned* __restrict__ emitted) {
     __shared__ double s_interval;
     __shared__ double stage[kSeqChunk];
@@ -1448,17 +1450,17 @@ __global__ void __launch_bounds__(1024) k_resample(const double* __restrict__ w,
         __syncthreads();
         for (unsigned i = threadIdx.x; i < m; i += blockDim.x) cum[base + i] = stage[i];
     }
-    if (threadIdx.x == 0) s_interval = c / n;
+    if (threadIdx.x == 0) s_interval = c / n_out;
     __syncthreads();
     const double interval = s_interval;
     if (threadIdx.x == 0) {
         double t = interval * u01;
-        for (unsigned k = 0; k < n; k++) { tgt[k] = t; t += interval; }
+        for (unsigned k = 0; k < n_out; k++) { tgt[k] = t; t += interval; }
     }
     __syncthreads();
     const double total = cum[n - 1];
     unsigned cnt = 0;
-    for (unsigned k = threadIdx.x; k < n; k += blockDim.x) {
+    for (unsigned k = threadIdx.x; k < n_out; k += blockDim.x) {
         double t = tgt[k];
         unsigned r = 0;
         if (total > t) {
@@ -1661,8 +1663,8 @@ void launch_fill_geom(Geom* g, unsigned n, Geom v, cudaStream_t st) { k_fill_geo
 void launch_normalize(const double* logw, const double* rows, unsigned n, double gain, double* w, double* neff, cudaStream_t st) {
     k_normalize<<<1, 1024, 0, st>>>(const_cast<double*>(logw), rows, n, gain, w, neff);
 }
-void launch_resample(const double* w, unsigned n, double u01, double* cum, double* tgt, unsigned* idx, unsigned* emitted, cudaStream_t st) {
-    k_resample<<<1, 1024, 0, st>>>(w, n, u01, cum, tgt, idx, emitted);
+void launch_resample(const double* w, unsigned n, unsigned n_out, double u01, double* cum, double* tgt, unsigned* idx, unsigned* emitted, cudaStream_t st) {
+    k_resample<<<1, 1024, 0, st>>>(w, n, n_out, u01, cum, tgt, idx, emitted);
 }
 void launch_digest(const DigestArgs& a, unsigned n, cudaStream_t st) { k_digest<<<n, 256, 0, st>>>(a); }
 void launch_entropy(const DigestArgs& a, double* out, unsigned n, cudaStream_t st) { k_entropy<<<n, 256, 0, st>>>(a, out); }

@@ -82,7 +82,7 @@ void launch_recount_compare(const Pool& pool, int* recount, unsigned long long* 
 void launch_fill_int(int* p, size_t n, int v, cudaStream_t st);
 void launch_fill_geom(Geom* g, unsigned n, Geom v, cudaStream_t st);
 void launch_normalize(const double* logw, const double* rows, unsigned n, double gain, double* w, double* neff, cudaStream_t st);
-void launch_resample(const double* w, unsigned n, double u01, double* cum, double* tgt, unsigned* idx, unsigned* emitted, cudaStream_t st);
+void launch_resample(const double* w, unsigned n, unsigned n_out, double u01, double* cum, double* tgt, unsigned* idx, unsigned* emitted, cudaStream_t st);
 void launch_digest(const DigestArgs& a, unsigned n, cudaStream_t st);
 void launch_entropy(const DigestArgs& a, double* out, unsigned n, cudaStream_t st);
 void launch_export_occupancy(const int* dirp, Geom g, const int4* pool, const int* visits, double occ_thresh, signed char* out, int width, int height, cudaStream_t st);

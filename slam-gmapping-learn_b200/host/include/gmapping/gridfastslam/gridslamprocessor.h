@@ -155,6 +155,10 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     // updateTreeWeights() walks every node of the trajectory tree (O(particles x scans) while nothing is resampled away).
     // With lazy = true processScan only normalises the weights (Neff, resampling are unaffected); TNode::accWeight is
     // brought up to date by getTrajectories() or refreshTreeWeights().  Default: false, the reference's behaviour.
+    // processScan(reading, adaptParticles) may change the particle count while resampling (gridslamprocessor.hxx:153-156): any
+    // count up to the larger of init()'s and this one (call before init(); the device slots are sized there).  One GPU only.
+    void setmaxParticles(unsigned int n) { m_maxParticles = n; }
+    unsigned int getmaxParticles() const { return m_maxParticles; }
     void setlazyTreeWeights(bool lazy) { m_lazyTree = lazy; }
     bool getlazyTreeWeights() const { return m_lazyTree; }
     // B200 build: register the scan right after scan matching (before Neff and the resampling decision are known) so the
@@ -232,6 +236,7 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     unsigned int m_firstLocal, m_localCount;
     unsigned int m_treeEpoch;
     bool m_lazyTree = false;
+    unsigned int m_maxParticles = 0, m_particleSlots = 0;  // setmaxParticles(); device slots for particle maps (set by init)
     bool m_earlyRegistration = true, m_registeredEarly = false;
     int m_fusedRegister = -1;  // -1: by default (on when sharded)
     bool m_weightsChanged = true;  // a particle's log-weight changed since the last normalize()

@@ -92,6 +92,16 @@ int gmh_process_scan(void* hv, const double* ranges, unsigned n, const double* o
     return h->gsp->processScan(rr) ? 1 : 0;
 }
 
+// GridSlamProcessor::processScan(reading, adaptParticles): a resampling at this reading continues with `adapt` particles
+int gmh_process_scan_adapt(void* hv, const double* ranges, unsigned n, const double* odom, double stamp, int adapt) {
+    Handle* h = static_cast<Handle*>(hv);
+    RangeReading rr(n, ranges, h->laser, stamp);
+    rr.setPose(OrientedPoint(odom[0], odom[1], odom[2]));
+    h->gsp->lastResampled = false;
+    return h->gsp->processScan(rr, adapt) ? 1 : 0;
+}
+void gmh_set_max_particles(void* h, unsigned n) { static_cast<Handle*>(h)->gsp->setmaxParticles(n); }
+
 unsigned gmh_particles(void* hv) { return (unsigned)static_cast<Handle*>(hv)->gsp->getParticles().size(); }
 unsigned gmh_local_particles(void* hv) { return static_cast<Handle*>(hv)->gsp->localParticles(); }
 unsigned gmh_first_local(void* hv) { return static_cast<Handle*>(hv)->gsp->firstLocalParticle(); }

@@ -128,7 +128,7 @@ GridSlamProcessor::GridSlamProcessor(const GridSlamProcessor& gsp)
       m_xmax(gsp.m_xmax), m_ymax(gsp.m_ymax), m_delta(gsp.m_delta), m_regScore(gsp.m_regScore), m_critScore(gsp.m_critScore), m_maxMove(gsp.m_maxMove),
       m_linearThresholdDistance(gsp.m_linearThresholdDistance), m_angularThresholdDistance(gsp.m_angularThresholdDistance),
       m_obsSigmaGain(gsp.m_obsSigmaGain), m_infoStream(std::cout), m_rank(0), m_world(1), m_firstLocal(0), m_localCount(gsp.m_localCount),
-      m_treeEpoch(0), m_lazyTree(gsp.m_lazyTree), m_earlyRegistration(gsp.m_earlyRegistration), m_fusedRegister(gsp.m_fusedRegister) {
+      m_treeEpoch(0), m_lazyTree(gsp.m_lazyTree), m_maxParticles(gsp.m_maxParticles), m_particleSlots(gsp.m_particleSlots), m_earlyRegistration(gsp.m_earlyRegistration), m_fusedRegister(gsp.m_fusedRegister) {
     if (gsp.m_world > 1) b200::fatal("GridSlamProcessor copy / clone(): a sharded filter cannot be cloned");
     m_hostMs[0] = m_hostMs[1] = m_hostMs[2] = m_hostMs[3] = 0;
     m_hostMsTotal[0] = m_hostMsTotal[1] = m_hostMsTotal[2] = m_hostMsTotal[3] = 0;
@@ -218,7 +218,9 @@ void GridSlamProcessor::init(unsigned int size, double xmin, double ymin, double
     unsigned long long pool = (unsigned long long)m_localCount * 512;  // patches; GM_B200_POOL_PATCHES overrides
     if (pool < 65536) pool = 65536;
     // sharded: as many spare slots as local particles, for resampled parents imported from other ranks
-    m_device.reset(new b200::DeviceContext(m_world > 1 ? 2 * m_localCount : m_localCount, pool, size));
+    const unsigned int slots = m_world > 1 ? 2 * m_localCount : std::max(m_localCount, m_maxParticles);  // (adaptParticles: one GPU only)
+    m_particleSlots = m_world > 1 ? m_localCount : slots;
+    m_device.reset(new b200::DeviceContext(slots, pool, std::max(size, m_maxParticles)));
     m_device->configure(m_matcher);
     const double center[2] = {(xmin + xmax) * .5, (ymin + ymax) * .5};
     m_device->check(gm_init_particles(m_device->h, m_localCount, center, xmax - xmin, ymax - ymin, delta), "gm_init_particles");
@@ -379,14 +381,19 @@ bool GridSlamProcessor::resample(const double* plainReading, int adaptSize, cons
         return false;
     }
     if (m_infoStream) m_infoStream << "*************RESAMPLE***************" << endl;
-    if (adaptSize > 0 && (size_t)adaptSize != n)
-        b200::fatal("processScan(reading, adaptParticles): changing the particle count while resampling is not supported by the device layout");
+    // adaptParticles (gridslamprocessor.hxx:153-156, particlefilter.h:196-203): the new generation has that many particles
+    const size_t nn = adaptSize > 0 ? (size_t)adaptSize : n;
+    if (nn != n) {
+        if (m_world > 1) b200::fatal("processScan(reading, adaptParticles): a sharded filter keeps its particle count");
+        if (nn > m_particleSlots)
+            b200::fatal("processScan(reading, adaptParticles): more particles than the filter was set up for; call setmaxParticles() before init()");
+    }
     // systematic resampling; the single uniform draw is taken here, on the host stream (particlefilter.h:199)
     const double u01 = drand48();
-    m_indexes.resize(n);
+    m_indexes.resize(nn);
     uint32_t emitted = 0;
     static_assert(sizeof(unsigned int) == sizeof(uint32_t), "index type");
-    m_device->check(gm_resample_indexes(m_device->h, m_weights.data(), (uint32_t)n, u01, m_indexes.data(), &emitted), "gm_resample_indexes");
+    m_device->check(gm_resample_indexes_n(m_device->h, m_weights.data(), (uint32_t)n, (uint32_t)nn, u01, m_indexes.data(), &emitted), "gm_resample_indexes");
     if (m_outputStream.is_open()) {
         m_outputStream << "RESAMPLE " << m_indexes.size() << " ";
         for (size_t i = 0; i < m_indexes.size(); i++) m_outputStream << m_indexes[i] << " ";
@@ -397,9 +404,9 @@ bool GridSlamProcessor::resample(const double* plainReading, int adaptSize, cons
     // new generation: slot j continues parent m_indexes[j].  The maps stay where they are (slot j's host mirror is
     // bound to device slot j); gm_register re-points slot j's patch directory at its parent's patches.
     struct Carry { OrientedPoint pose, previousPose; double weightSum, gweight; TNode* node; };
-    std::vector<Carry> next(n);
+    std::vector<Carry> next(nn);
     std::vector<char> kept(n, 0);
-    for (size_t j = 0; j < n; j++) {
+    for (size_t j = 0; j < nn; j++) {
         const Particle& src = m_particles[m_indexes[j]];
         // a parent's first child takes the node prepared below the parent's leaf, further children get nodes of their own
         TNode* node = (prepared && !kept[m_indexes[j]]) ? m_newNodes[m_indexes[j]] : new TNode(src.pose, 0, src.node, 0);
@@ -415,7 +422,27 @@ bool GridSlamProcessor::resample(const double* plainReading, int adaptSize, cons
             m_particles[i].node = 0;
         }
     m_newNodes.clear();
-    for (size_t j = 0; j < n; j++) {
+    if (nn != n) {
+        // (the reference's bookkeeping of the leaves that died walks `j < m_indexes.size()`: with fewer particles it leaks the
+        // unselected ones beyond the new count, with more it reads past the old vector; here every unselected leaf is freed)
+        flushHostEdits();  // a parent may sit in a slot that is about to go
+        if (nn < n) m_particles.erase(m_particles.begin() + nn, m_particles.end());
+        else {
+            ScanMatcherMap mirror(Point((m_xmin + m_xmax) * .5, (m_ymin + m_ymax) * .5), 0., 0., m_delta);
+            m_particles.reserve(nn);
+            for (size_t j = n; j < nn; j++) {
+                m_particles.push_back(Particle(mirror));
+                std::shared_ptr<b200::DeviceMapResidency> r(new b200::DeviceMapResidency);
+                r->ctx = m_device;
+                r->slot = (unsigned int)j;
+                r->stale = true;
+                m_particles.back().map.setResidency(r);
+            }
+        }
+        m_localCount = (unsigned int)nn;
+        m_device->particles = (unsigned int)nn;
+    }
+    for (size_t j = 0; j < nn; j++) {
         Particle& p = m_particles[j];
         p.pose = next[j].pose; p.previousPose = next[j].previousPose;
         p.weightSum = next[j].weightSum; p.gweight = next[j].gweight; p.node = next[j].node;
@@ -425,7 +452,11 @@ bool GridSlamProcessor::resample(const double* plainReading, int adaptSize, cons
     m_weightsChanged = true;
     // a child starts from its parent's pose and map: registering the scan in the parent before the copy (early
     // registration) or in the child after it (the reference's order) writes the same cells
-    if (m_registeredEarly) copyAll(m_indexes.data());
+    if (nn != n) {  // the copies change the number of device maps; then, in the reference's order, the scan goes into every child
+        m_device->check(gm_copy_particles_n(m_device->h, m_indexes.data(), (uint32_t)nn), "gm_copy_particles_n");
+        markMapsStale();
+        if (!m_registeredEarly) registerAll(plainReading, 0);
+    } else if (m_registeredEarly) copyAll(m_indexes.data());
     else registerAll(plainReading, m_indexes.data());
     m_device->mapsAhead = false;
     return true;

@@ -44,6 +44,8 @@ def load():
     L.gmh_setup.argtypes = [vp, C.c_uint, dp, dp, dp]
     L.gmh_init.argtypes = [vp, C.c_uint] + [C.c_double] * 5 + [dp, C.c_ulong]
     L.gmh_process_scan.argtypes = [vp, dp, C.c_uint, dp, C.c_double]
+    L.gmh_process_scan_adapt.argtypes = [vp, dp, C.c_uint, dp, C.c_double, C.c_int]
+    L.gmh_set_max_particles.argtypes = [vp, C.c_uint]
     for f in ("gmh_particles", "gmh_local_particles", "gmh_first_local"):
         getattr(L, f).restype = C.c_uint; getattr(L, f).argtypes = [vp]
     L.gmh_neff.restype = C.c_double; L.gmh_neff.argtypes = [vp]
@@ -77,7 +79,8 @@ class Processor:
     """GMapping::GridSlamProcessor (C++) behind ctypes."""
 
     def __init__(self, angles, particles, init_pose, bounds=(-100., -100., 100., 100.), delta=0.05, seed=12345, laser_pose=(0., 0., 0.),
-                 rank=0, world=1, nccl_id=None, verbose=False, early_registration=True, lazy_tree=False, register_with_scanmatch=None, **params):
+                 rank=0, world=1, nccl_id=None, verbose=False, early_registration=True, lazy_tree=False, register_with_scanmatch=None,
+                 max_particles=0, **params):
         L = load()
         self.L = L
         self.h = L.gmh_create(1 if verbose else 0)
@@ -88,6 +91,8 @@ class Processor:
             L.gmh_set_lazy_tree(self.h, 1)  # TNode::accWeight is brought up to date on demand (refresh_tree / getTrajectories)
         if register_with_scanmatch is not None:  # default: on for a sharded filter, off on one GPU
             L.gmh_set_register_with_scanmatch(self.h, 1 if register_with_scanmatch else 0)
+        if max_particles:
+            L.gmh_set_max_particles(self.h, int(max_particles))  # room for process_scan(..., adapt=) to grow the particle set
         if not early_registration:
             L.gmh_set_early_registration(self.h, 0)  # the reference's order: copy the resampled particles, then register
         p = dict(DEFAULTS); p.update(params)
@@ -109,10 +114,15 @@ class Processor:
         except Exception:
             pass
 
-    def process_scan(self, ranges, odom, stamp):
+    def process_scan(self, ranges, odom, stamp, adapt=0):
+        """adapt: GridSlamProcessor::processScan's adaptParticles -- a resampling at this reading continues with that many particles"""
         r = np.ascontiguousarray(ranges, dtype=np.float64); o = np.ascontiguousarray(odom, dtype=np.float64)
         assert r.shape == (self.beams,)
-        return bool(self.L.gmh_process_scan(self.h, _dp(r), len(r), _dp(o), float(stamp)))
+        if not adapt:
+            return bool(self.L.gmh_process_scan(self.h, _dp(r), len(r), _dp(o), float(stamp)))
+        done = bool(self.L.gmh_process_scan_adapt(self.h, _dp(r), len(r), _dp(o), float(stamp), int(adapt)))
+        self.n = int(self.L.gmh_particles(self.h))
+        return done
 
     def state(self):
         a = np.zeros((self.n, 6)); self.L.gmh_state(self.h, _dp(a)); return a

@@ -130,6 +130,49 @@ def scenario_order():
     assert np.abs(s0[:, :3] - g.state[len(g.ranges) - 1][:, :3]).max() < 1e-4
 
 
+def scenario_adapt():
+    """processScan(reading, adaptParticles) (gridslamprocessor.hxx:153-156 -> particlefilter.h:196-203): the resampling at a reading
+    continues with another number of particles, fewer (30 -> 20) and then more (20 -> 26, room reserved with setmaxParticles).
+    The index vectors are the reference's arithmetic (pinned by tests/golden/units.npz: resampleIndexes(w, nparticles)); here: the
+    filter carries on, child j continues parent idx[j] (pose, weightSum, previousIndex, map), the reference counts of the patch
+    pool stay consistent, and the three registration orders (early, the reference's, queued behind the scan match) agree bit
+    for bit.  (The unmodified reference cannot serve as the oracle here: with fewer particles its bookkeeping leaks the dead
+    leaves beyond the new count and its own propagateWeights() assertion fires; with more it reads past the particle vector.)"""
+    build_host()
+    hostapi = importlib.import_module("slam-gmapping-learn_b200.hostapi")
+    g = Golden("room181_n30")
+    p = g.p
+    schedule = {6: 20, 7: 20, 12: 26}
+    runs = []
+    for early, fused in ((True, False), (False, False), (True, True)):
+        par = dict({k: p[k] for k in hostapi.PARAM_ORDER}, resampleThreshold=2.0)  # Neff < 2 N: every processed reading resamples
+        a = hostapi.Processor(g.angles, p["particles"], g.head_init, bounds=(p["xmin"], p["ymin"], p["xmax"], p["ymax"]), delta=p["delta"],
+                              seed=p["seed"], early_registration=early, register_with_scanmatch=fused, max_particles=32, **par)
+        counts, trail = [], []
+        for i in range(16):
+            before = a.state()
+            done = a.process_scan(g.ranges[i], g.odom[i], g.stamps[i], adapt=schedule.get(i, 0))
+            st = a.state()
+            counts.append(len(st))
+            if done and a.last_resampled():
+                idx = a.indexes()
+                want = schedule.get(i, 0) or len(before)
+                assert len(idx) == want == len(st), (i, len(idx), want, len(st))
+                assert np.array_equal(st[:, 5], idx) and np.all(idx < len(before)) and np.all(np.diff(idx.astype(np.int64)) >= 0)
+                assert np.all(st[:, 3] == 0)  # setWeight(0) after a resampling
+                trail.append(idx.copy())
+            assert a.check_maps() > 0
+        assert counts[5] == 30 and counts[6] == 20 and counts[11] == 20 and counts[12] == 26 and counts[-1] == 26, counts
+        assert len(a.map_digests()) == 26 and len(a.tree_rows()) == 26
+        runs.append((a.state(), a.map_digests(), trail, a.neff()))
+        a.close()
+    s0, d0, t0, n0 = runs[0]
+    for s1, d1, t1, n1 in runs[1:]:
+        assert np.array_equal(s0, s1) and np.array_equal(d0, d1) and n0 == n1
+        assert len(t0) == len(t1) and all(np.array_equal(x, y) for x, y in zip(t0, t1))
+    return "30 -> 20 -> 26 particles, %d resamplings" % len(t0)
+
+
 def scenario_lazy_tree():
     """setlazyTreeWeights(true): processScan only normalises the weights; TNode::accWeight is brought up to date on demand.
     The filter itself must not notice (same poses, weights, resampling, maps), and after refreshTreeWeights() the tree is the
@@ -181,6 +224,6 @@ def scenario_n32(limit=None):
 if __name__ == "__main__":
     name, _, arg = sys.argv[1].partition(":")
     fn = {"cli": scenario_cli, "clone": scenario_clone, "order": scenario_order, "long": scenario_long, "lazy_tree": scenario_lazy_tree, "c3": scenario_c3,
-          "n32": scenario_n32}[name]
+          "n32": scenario_n32, "adapt": scenario_adapt}[name]
     out = fn(int(arg)) if arg else fn()
     print("scenario %s ok %s" % (sys.argv[1], "" if out is None else out))

@@ -223,23 +223,34 @@ int gm_normalize_neff(gm_ctx* c, const double* logw, uint32_t n, double gain, do
     return GM_OK;
 }
 
-int gm_resample_indexes(gm_ctx* c, const double* w, uint32_t n, double u01, uint32_t* idx_out, uint32_t* emitted_out) {
+int gm_resample_indexes_n(gm_ctx* c, const double* w, uint32_t n, uint32_t n_out, double u01, uint32_t* idx_out, uint32_t* emitted_out) {
     if (!c) return GM_ERR_ARG;
     if (!c->inited) return fail(c, GM_ERR_ARG, "gm_init_particles has not been called");
-    if (!w || !idx_out || !n || n > c->weights_cap) return fail(c, GM_ERR_ARG, "gm_resample_indexes: bad argument");
-    const uint32_t k = orc_resample_indexes(w, n, u01, idx_out);
+    if (!w || !idx_out || !n || n > c->weights_cap || !n_out || n_out > c->weights_cap) return fail(c, GM_ERR_ARG, "gm_resample_indexes: bad argument");
+    const uint32_t k = orc_resample_indexes_n(w, n, n_out, u01, idx_out);
     if (emitted_out) *emitted_out = k;
     return GM_OK;
 }
 
-static int remap(gm_ctx* c, const uint32_t* idx) {
-    for (uint32_t j = 0; j < c->n; j++)
+int gm_resample_indexes(gm_ctx* c, const double* w, uint32_t n, double u01, uint32_t* idx_out, uint32_t* emitted_out) {
+    return gm_resample_indexes_n(c, w, n, n, u01, idx_out, emitted_out);
+}
+
+/* the new generation has n_new maps, map j a copy of the old generation's idx[j] */
+static int remap_n(gm_ctx* c, const uint32_t* idx, uint32_t n_new) {
+    for (uint32_t j = 0; j < n_new; j++)
         if (idx[j] >= c->n) return fail(c, GM_ERR_ARG, "remap: parent index %u >= %u", idx[j], c->n);
-    orc_map** next = (orc_map**)calloc(c->n, sizeof(orc_map*));
-    for (uint32_t j = 0; j < c->n; j++) next[j] = orc_map_clone(c->maps[idx[j]]);
-    for (uint32_t j = 0; j < c->n; j++) { orc_map_free(c->maps[j]); c->maps[j] = next[j]; }
+    orc_map** next = (orc_map**)calloc(n_new, sizeof(orc_map*));
+    for (uint32_t j = 0; j < n_new; j++) next[j] = orc_map_clone(c->maps[idx[j]]);
+    for (uint32_t j = 0; j < c->n; j++) { orc_map_free(c->maps[j]); c->maps[j] = NULL; }
+    for (uint32_t j = 0; j < n_new; j++) c->maps[j] = next[j];
+    c->n = n_new;
     free(next);
     return GM_OK;
+}
+
+static int remap(gm_ctx* c, const uint32_t* idx) {
+    return remap_n(c, idx, c->n);
 }
 
 int gm_copy_particles(gm_ctx* c, const uint32_t* idx) {
@@ -247,6 +258,15 @@ int gm_copy_particles(gm_ctx* c, const uint32_t* idx) {
     if (r) return r;
     if (!idx) return fail(c, GM_ERR_ARG, "gm_copy_particles: null argument");
     return remap(c, idx);
+}
+
+int gm_copy_particles_n(gm_ctx* c, const uint32_t* idx, uint32_t n_new) {
+    int r = ready(c);
+    if (r) return r;
+    if (!idx) return fail(c, GM_ERR_ARG, "gm_copy_particles_n: null argument");
+    if (c->dist) return fail(c, GM_ERR_ARG, "gm_copy_particles_n: the particle count of a sharded context is fixed");
+    if (!n_new || n_new > c->max_particles) return fail(c, GM_ERR_ARG, "gm_copy_particles_n: %u particles, the context was created for at most %u", n_new, c->max_particles);
+    return remap_n(c, idx, n_new);
 }
 
 int gm_register(gm_ctx* c, const double* ranges, const double* poses, const uint32_t* idx) {

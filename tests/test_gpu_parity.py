@@ -216,6 +216,62 @@ def test_normalize_and_resample_vs_oracle():
     ctx.close()
 
 
+def test_resample_and_copy_with_a_new_particle_count():
+    """processScan's adaptParticles on the device: k_resample with `nparticles` against the reference's own index vectors
+    (tests/golden/units.npz, made by oracle/ref_units.cpp from uniform_resampler::resampleIndexes(w, nparticles)), then
+    gm_copy_particles_n to fewer and to more particles: child j's map is parent idx[j]'s, the reference counts stay consistent,
+    and the next registration works on the new generation"""
+    import ctypes
+    import importlib
+    import os
+    gm = importlib.import_module("slam-gmapping-learn_b200")
+    units = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "units.npz"))
+    libc = ctypes.CDLL("libc.so.6"); libc.drand48.restype = ctypes.c_double; libc.srand48.argtypes = [ctypes.c_long]
+    ctx = gm.GmContext(4096, pool_patches=64)
+    ctx.set_laser(np.linspace(-1, 1, 181)); ctx.set_matching(); ctx.init_particles(4096)
+    w_off = i_off = 0
+    for n, n_out, seed in units["ra_hdr"]:
+        w = units["ra_w"][w_off:w_off + n]; want = units["ra_idx"][i_off:i_off + n_out]
+        w_off += n; i_off += n_out
+        libc.srand48(int(seed))
+        idx, em = ctx.resample_indexes(w, libc.drand48(), n_out=int(n_out))
+        assert np.array_equal(idx, want) and em == n_out, (n, n_out, seed)
+    ctx.close()
+    # 8 particles -> 5 -> 11 (the context has room for 12)
+    log, m, _, maps, poses, rng = _random_world(13, beams=181, particles=8, scans=3)
+    _.close()
+    laser = importlib.import_module("slam-gmapping-learn_b200.synth").LMS200
+    ctx = gm.GmContext(12, pool_patches=4096)
+    ctx.set_laser(laser.angles()); ctx.set_matching(urange=laser.max_range - 1.0, range_=laser.max_range); ctx.init_particles(8)
+    rng = np.random.default_rng(13)
+    for k in range(3):  # the same registrations as _random_world's (same seed)
+        ps = log.odom[k][None, :] + rng.normal(0, [0.02, 0.02, 0.01], size=(8, 3))
+        r = log.ranges[k].copy()
+        if k == 2:
+            r[3] = 0.0; r[7] = np.nan; r[11] = laser.max_range + 5; r[15] = laser.max_range - 1.0
+        ctx.register(r, ps)
+    base = ctx.digests()
+    assert [int(x) for x in base["hash_counts"]] == [mp.digest().hash_counts for mp in maps]
+    gen = list(range(8))
+    for idx in (np.array([0, 2, 2, 5, 7], dtype=np.uint32), np.array([0, 0, 1, 1, 1, 2, 3, 3, 4, 4, 4], dtype=np.uint32)):
+        ctx.copy_particles(idx, n_new=len(idx))
+        gen = [gen[i] for i in idx]
+        d = ctx.digests()
+        assert len(d["hash_counts"]) == len(idx)
+        assert [int(x) for x in d["hash_counts"]] == [int(base["hash_counts"][g]) for g in gen]
+        ctx.check_refcounts()
+    # the new generation registers a scan like any other: against the oracle maps of the ancestors
+    r = log.ranges[1]
+    ps = log.odom[1][None, :] + rng.normal(0, [0.02, 0.02, 0.01], size=(len(gen), 3))
+    ctx.register(r, ps)
+    d = ctx.digests()
+    for j, g in enumerate(gen):
+        mp = maps[g].clone(); orc.register(m, mp, ps[j], r)
+        assert int(d["hash_counts"][j]) == mp.digest().hash_counts and int(d["hash_acc"][j]) == mp.digest().hash_acc
+    ctx.check_refcounts()
+    ctx.close()
+
+
 def test_copy_on_write_refcounts():
     """resample to a single parent: children share patches (no deep copy), the next registration makes the
     touched patches private again, and the pool returns to its steady size."""

@@ -122,6 +122,11 @@ def test_reference_order_and_early_registration_agree():
 
 
 @pytest.mark.gpu
+def test_adapt_particles_changes_the_particle_count():
+    host_scenarios.scenario_adapt()
+
+
+@pytest.mark.gpu
 def test_lazy_tree_weights():
     host_scenarios.scenario_lazy_tree()
 

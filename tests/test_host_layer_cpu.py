@@ -23,7 +23,7 @@ def test_free_running_trace_is_the_reference_trace_bit_for_bit(case):
     check_trace(case, g, tr, exact=True)
 
 
-@pytest.mark.parametrize("scenario", ["clone", "order", "cli", "lazy_tree", "long:120", "n32"])
+@pytest.mark.parametrize("scenario", ["clone", "order", "cli", "lazy_tree", "long:120", "n32", "adapt"])
 def test_host_scenarios_on_the_mock(scenario):
     res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host_scenarios.py"), scenario], capture_output=True, text=True,
                          timeout=900, env=mock_env())

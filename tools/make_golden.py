@@ -175,6 +175,7 @@ def run_units(name="units"):
     off = 0
     out = {"units_sha256": np.array(hashlib.sha256(buf).hexdigest()), "units_bytes": np.array(len(buf))}
     rs_n, rs_seed, rs_w, rs_idx = [], [], [], []
+    ra_hdr, ra_w, ra_idx = [], [], []
     while off < len(buf):
         tag = buf[off:off + 4].decode(); n = struct.unpack_from("<Q", buf, off + 4)[0]
         p = buf[off + 12:off + 12 + n]; off += 12 + n
@@ -182,6 +183,9 @@ def run_units(name="units"):
         elif tag == "RSHD": h = np.frombuffer(p, dtype="<f8"); rs_n.append(int(h[0])); rs_seed.append(int(h[1]))
         elif tag == "RSWT": rs_w.append(np.frombuffer(p, dtype="<f8").copy())
         elif tag == "RSIX": rs_idx.append(np.frombuffer(p, dtype="<u4").copy())
+        elif tag == "RAHD": ra_hdr.append(np.frombuffer(p, dtype="<f8").astype(np.int64))
+        elif tag == "RAWT": ra_w.append(np.frombuffer(p, dtype="<f8").copy())
+        elif tag == "RAIX": ra_idx.append(np.frombuffer(p, dtype="<u4").copy())
         elif tag == "GAUS": out["gauss"] = np.frombuffer(p, dtype="<f8").copy()
         elif tag == "MOTN": out["motion"] = np.frombuffer(p, dtype="<f8").copy()
         elif tag == "W2MP": out["w2m"] = np.frombuffer(p, dtype="<f8").reshape(-1, 8).copy()
@@ -189,6 +193,7 @@ def run_units(name="units"):
         elif tag == "PTOP": out["point_ops"] = np.frombuffer(p, dtype="<f8").reshape(-1, 23).copy()
         else: raise ValueError(tag)
     out.update(rs_n=np.array(rs_n), rs_seed=np.array(rs_seed), rs_w=np.concatenate(rs_w), rs_idx=np.concatenate(rs_idx))
+    out.update(ra_hdr=np.stack(ra_hdr), ra_w=np.concatenate(ra_w), ra_idx=np.concatenate(ra_idx))  # rows of ra_hdr: n, n_out, seed
     path = os.path.join(GOLD, name + ".npz")
     np.savez_compressed(path, **out)
     print("%-18s lines %d resample cases %d gaussians %d motion rows %d world2map rows %d  %6.1f KB" % (
