@@ -47,7 +47,8 @@ if ROOT not in sys.path:
 
 METRIC = "scans/sec at 4096 particles x 1081 beams"
 BYTES_PER_BEAM_EVAL = 144  # (2k+1)^2 x 16 B at kernelSize 1
-PATCH_BYTES = 16384 + 4096 + 16384 + 128  # cells + visit counters + means + occupancy bitmap of one 32 x 32 patch
+PATCH_BYTES = 4096                        # visit counters of one 32 x 32 patch: all a free-space patch owns
+HIT_PLANES_BYTES = 16384 + 16384 + 128    # cells + means + occupancy bitmap, owned by the patches that hold end points
 CPU_BASELINE_PARTICLES = 48  # bounded sample of the cpu_baseline leg: ~15 s of single-core reference work over the bench's scans
 REFERENCE_PROCS = 16         # processes of the reference arm: the same on every box, so the per-N ratios share one denominator
 LINEARITY_PARTICLES = 512    # one measured reference point at a large particle count next to the extrapolated one
@@ -335,12 +336,14 @@ def main():
         roofline["frac"] = roofline["achieved"] / issue_peak if roofline["achieved"] else None
         rfacts = kernel_facts().get("k_register", {})
         free_upd, hit_upd, cow = s1["free_updates"], s1["hit_updates"], s1["cow_copies"]
-        reg_bytes = free_upd * 8 + hit_upd * 32 + cow * 2 * 20480  # last registration of the timed region (SURVEY.md 8d grid update)
+        # last registration of the timed region (SURVEY.md 8d grid update); a copy-on-write copy moves at least the 4 KB of visit
+        # counters each way (16 KB of cells more for a patch that holds end points: not counted)
+        reg_bytes = free_upd * 8 + hit_upd * 32 + cow * 2 * 4096
         reg_ms = s1["ms_register"]
         roofline_register = {"kernel": "k_register", "bound": "hbm", "unit": "GB/s", "achieved": reg_bytes / (reg_ms * 1e-3) / 1e9 if reg_ms else None,
                              "peak": peak, "frac": reg_bytes / (reg_ms * 1e-3) / 1e9 / peak if reg_ms else None,
                              "algorithmic_bytes": reg_bytes, "traffic": rfacts.get("dram_bytes_per_particle", 0) * nl or None,
-                             "note": "last registration of the timed region: 8 B per free-cell update, 32 B per hit, 2 x 20 KB per copy-on-write patch copy"}
+                             "note": "last registration of the timed region: 8 B per free-cell update, 32 B per hit, 2 x 4 KB per copy-on-write patch copy"}
         h2d = world * (2 * (B * 8 + nl * 24) + n * 8)
         d2h = world * (n * 48 + 8 + 2 * 160)
         config = workload_config(n, args.noise)
@@ -348,7 +351,7 @@ def main():
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config,
                 "details": {"particles_per_gpu": nl,
-                            "l2": "inputs larger than L2 (%.1f GB of map patches resident per GPU, every particle's active area is read and written every scan)" % (s1["pool_in_use"] * PATCH_BYTES / 1e9),
+                            "l2": "inputs larger than L2 (%.1f GB of map patches resident per GPU, every particle's active area is read and written every scan)" % ((s1["pool_in_use"] * PATCH_BYTES + s1["pool_hit_in_use"] * HIT_PLANES_BYTES) / 1e9),
                             "api": "GMapping::GridSlamProcessor::processScan (C++ host layer over the C ABI)"},
                 "resamples_in_timed_region": proc.resamples() - resamples0,
                 "migrated_particles": int(mig_p), "migrated_bytes": int(mig_b),

@@ -101,6 +101,9 @@ typedef struct gm_stats {
     double total_ms[6];
     uint64_t total_beam_evals, total_score_evals, total_scanmatches, total_registers;
     uint64_t total_migrated_particles, total_migrated_bytes; /* multi-GPU, since gm_create */
+    /* of the pool's patch ids, those that can hold end points (all planes, 36 KB each; the others are free-space patches: visit
+     * counters only, 4 KB) and how many of them were in use after the last gm_register */
+    uint64_t pool_hit_capacity, pool_hit_in_use;
 } gm_stats;
 
 int gm_create(gm_ctx** out, const gm_config* cfg);

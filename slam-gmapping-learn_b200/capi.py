@@ -54,7 +54,8 @@ class Stats(C.Structure):
                 ("max_active_patches", C.c_uint32), ("register_tile_cap", C.c_uint32),
                 ("total_ms", C.c_double * 6), ("total_beam_evals", C.c_uint64), ("total_score_evals", C.c_uint64),
                 ("total_scanmatches", C.c_uint64), ("total_registers", C.c_uint64),
-                ("total_migrated_particles", C.c_uint64), ("total_migrated_bytes", C.c_uint64)]
+                ("total_migrated_particles", C.c_uint64), ("total_migrated_bytes", C.c_uint64),
+                ("pool_hit_capacity", C.c_uint64), ("pool_hit_in_use", C.c_uint64)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("reserved", "register_phase_cycles", "total_ms")}

@@ -65,23 +65,31 @@ static int create_ctx(gm_ctx** out, const gm_config* cfg, gm_ctx* share_with) {
         // 0 = half of the free HBM; an explicit request is honoured up to 80 % of it (a larger one would only fail in cudaMalloc)
         size_t free_b = 0, total_b = 0;
         CKC(cudaMemGetInfo(&free_b, &total_b));
-        const double per_patch = kPatchCells * (sizeof(int4) + sizeof(int) + sizeof(double2)) + kPatch * sizeof(unsigned) + 4 * sizeof(int);
+        // hit-capable patches own a slice of every plane (36 KB), free-space patches only their visit counters (4 KB); the
+        // share of hit-capable ids is GM_B200_HIT_FRACTION (default 0.6: about half of the patches of an indoor map hold end
+        // points, and a hit-capable id can stand in for a free-space one but not the other way round)
+        double hit_fraction = 0.6;
+        if (const char* e = getenv("GM_B200_HIT_FRACTION")) hit_fraction = std::min(1.0, std::max(0.05, atof(e)));
+        const double per_hit = kPatchCells * (sizeof(int4) + sizeof(double2)) + kPatch * sizeof(unsigned), per_any = kPatchCells * sizeof(int) + 4 * sizeof(int);
+        const double per_patch = per_any + hit_fraction * per_hit;
         const size_t half = (size_t)((double)free_b * 0.5 / per_patch), most = (size_t)((double)free_b * 0.8 / per_patch);
-        if (!cap) cap = std::min<size_t>(half, (size_t)1 << 22);  // 64 GiB of patches at most by default
+        if (!cap) cap = std::min<size_t>(half, (size_t)1 << 22);  // 2^22 patches at most by default
         else if (cap > most) cap = most;
         if (cap < 64) cap = 64;
     if (cap > ((size_t)1 << 22) - 2) cap = ((size_t)1 << 22) - 2;  // cell indexes (patch * 1024 + cell) stay below 2^32
+    size_t cap_h = std::min(cap, std::max<size_t>(32, (size_t)std::ceil((double)cap * hit_fraction)));
     c->pool.cap = (int)cap;
-    CKC(dalloc(c->pool.cells, (cap + 1) * kPatchCells));  // + the all-zero patch at index cap (unknown cells)
-    CKC(cudaMemsetAsync(c->pool.cells + cap * kPatchCells, 0, kPatchCells * sizeof(int4), c->st));
+    c->pool.cap_h = (int)cap_h;
+    CKC(dalloc(c->pool.cells, (cap_h + 1) * kPatchCells));  // + the all-zero patch at index cap_h (unknown cells, free-space patches)
+    CKC(cudaMemsetAsync(c->pool.cells + cap_h * kPatchCells, 0, kPatchCells * sizeof(int4), c->st));
     CKC(dalloc(c->pool.visits, (cap + 1) * kPatchCells));
     CKC(cudaMemsetAsync(c->pool.visits + cap * kPatchCells, 0, kPatchCells * sizeof(int), c->st));
-    CKC(dalloc(c->pool.means, (cap + 1) * kPatchCells));
-    CKC(cudaMemsetAsync(c->pool.means + cap * kPatchCells, 0, kPatchCells * sizeof(double2), c->st));
-    CKC(dalloc(c->pool.occ, (cap + 1) * kPatch));
-    CKC(cudaMemsetAsync(c->pool.occ, 0, (cap + 1) * kPatch * sizeof(unsigned), c->st));
+    CKC(dalloc(c->pool.means, (cap_h + 1) * kPatchCells));
+    CKC(cudaMemsetAsync(c->pool.means + cap_h * kPatchCells, 0, kPatchCells * sizeof(double2), c->st));
+    CKC(dalloc(c->pool.occ, (cap_h + 1) * kPatch));
+    CKC(cudaMemsetAsync(c->pool.occ, 0, (cap_h + 1) * kPatch * sizeof(unsigned), c->st));
     CKC(dalloc(c->pool.refcnt, cap)); CKC(dalloc(c->pool.free_list, cap)); CKC(dalloc(c->pool.pending, cap));
-    CKC(dalloc(c->pool.free_top, 1)); CKC(dalloc(c->pool.pending_n, 1));
+    CKC(dalloc(c->pool.free_top, 2)); CKC(dalloc(c->pool.pending_n, 1));
     CKC(dalloc(c->refcnt_new, cap));
     CKC(cudaMemsetAsync(c->refcnt_new, 0, cap * sizeof(int), c->st));
     }
@@ -117,6 +125,7 @@ static int create_ctx(gm_ctx** out, const gm_config* cfg, gm_ctx* share_with) {
     CKC(cudaStreamSynchronize(c->st));
 #undef CKC
     c->stats.pool_capacity = cap;
+    c->stats.pool_hit_capacity = (uint64_t)c->pool.cap_h;
     c->stats.launches = 1;
     *out = c;
     return GM_OK;
@@ -253,7 +262,7 @@ static int run_eval(gm_ctx* ctx, int mode, uint32_t count, const uint32_t* parti
     a.P = ctx->P; a.ranges = ctx->d_ranges; a.angles = ctx->d_angles; a.poses = ctx->d_qposes;
     a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.visits = ctx->pool.visits; a.means = ctx->pool.means; a.occ = ctx->pool.occ; a.inv_n = ctx->d_inv_n;
     a.s = ctx->d_qs; a.l = ctx->d_ql; a.c = ctx->d_qc; a.score = ctx->d_qs; a.poses_out = ctx->d_qposes_out;
-    a.query = mode; a.particle_idx = ctx->d_qidx; a.zero_patch = ctx->pool.cap;
+    a.query = mode; a.particle_idx = ctx->d_qidx; a.zero_patch = ctx->pool.cap_h;
     derive_params(a.P);
     if (int r = prepare_scanmatch(ctx)) return r;
     launch_scanmatch(a, count, false, ctx->st);
@@ -296,7 +305,7 @@ int gm_scanmatch(gm_ctx* ctx, const double* ranges, double* poses_inout, double 
     a.minimum_score = minimum_score;
     a.score = ctx->d_score; a.s = ctx->d_s; a.l = ctx->d_l; a.c = ctx->d_c; a.evals = ctx->d_evals;
     a.counters = ctx->d_counters;
-    a.zero_patch = ctx->pool.cap;
+    a.zero_patch = ctx->pool.cap_h;
     derive_params(a.P);
     a.valid_score_beams = count_score_beams(ctx, ranges);
     if (int r = prepare_scanmatch(ctx)) return r;
@@ -357,7 +366,7 @@ int gm_scanmatch_weights_begin(gm_ctx* ctx, const double* ranges, const double* 
     a.minimum_score = minimum_score;
     a.score = ctx->d_score; a.s = ctx->d_s; a.l = ctx->d_l; a.c = ctx->d_c; a.evals = ctx->d_evals;
     a.counters = ctx->d_counters_sm;
-    a.zero_patch = ctx->pool.cap;
+    a.zero_patch = ctx->pool.cap_h;
     derive_params(a.P);
     a.valid_score_beams = count_score_beams(ctx, ranges);
     if (int r = prepare_scanmatch(ctx)) return r;
@@ -603,9 +612,11 @@ int gmi_register_finish(gm_ctx* ctx) {
         h2.resizes = h.resizes;
         h = h2;
     }
-    int top = 0;
-    CK(cudaMemcpyAsync(&top, ctx->pool.free_top, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    int tops[2] = {0, 0};  // free hit-capable / free-space patch ids
+    CK(cudaMemcpyAsync(tops, ctx->pool.free_top, sizeof tops, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
+    const int top = std::max(0, tops[0]) + std::max(0, tops[1]);
+    ctx->stats.pool_hit_in_use = (uint64_t)(ctx->pool.cap_h - std::max(0, tops[0]));
     CK(cudaEventElapsedTime(&ctx->stats.ms_register, ctx->evr0, ctx->evr1));
     ctx->stats.total_ms[3] += ctx->stats.ms_register; ctx->stats.total_ms[2] += ctx->stats.ms_remap; ctx->stats.total_ms[4] += ctx->stats.ms_migrate;
     ctx->stats.total_registers++;
@@ -760,7 +771,7 @@ int gm_download_map(gm_ctx* ctx, uint32_t particle, gm_map_info* info, int32_t* 
     }
     CK(cudaMemcpyAsync(ctx->d_list, list.data(), sizeof(int) * 2 * m, cudaMemcpyHostToDevice, ctx->st));
     if ((size_t)m > ctx->export_cap) { CK(dalloc(ctx->d_export, (size_t)m * kPatchCells)); ctx->export_cap = m; }
-    launch_export_gather(ctx->pool.cells, ctx->pool.visits, ctx->d_list, ctx->d_export, m, ctx->st);
+    launch_export_gather(ctx->pool.cells, ctx->pool.visits, ctx->pool.cap_h, ctx->d_list, ctx->d_export, m, ctx->st);
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_export_gather")) return r;
     CK(cudaMemcpyAsync(cells, ctx->d_export, sizeof(int4) * kPatchCells * (size_t)m, cudaMemcpyDeviceToHost, ctx->st));
@@ -778,7 +789,7 @@ int gm_export_occupancy(gm_ctx* ctx, uint32_t particle, double occ_thresh, int8_
         return fail(ctx, GM_ERR_ARG, "gm_export_occupancy: the map is %d x %d cells, the buffer %u x %u", g.npx << kPatchMag, g.npy << kPatchMag, width, height);
     const size_t bytes = (size_t)width * height;
     if (bytes > ctx->occ_cap) { CK(dalloc(ctx->d_occ, bytes)); ctx->occ_cap = bytes; }
-    launch_export_occupancy(ctx->dir + (size_t)particle * ctx->dir_cap, g, ctx->pool.cells, ctx->pool.visits, occ_thresh, ctx->d_occ, (int)width, (int)height, ctx->st);
+    launch_export_occupancy(ctx->dir + (size_t)particle * ctx->dir_cap, g, ctx->pool.cells, ctx->pool.visits, ctx->pool.cap_h, occ_thresh, ctx->d_occ, (int)width, (int)height, ctx->st);
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_export_occupancy")) return r;
     CK(cudaMemcpyAsync(out, ctx->d_occ, bytes, cudaMemcpyDeviceToHost, ctx->st));
@@ -791,7 +802,7 @@ int gm_map_digest(gm_ctx* ctx, uint32_t first, uint32_t count, gm_digest* out) {
     if (!out || first + count > ctx->n) return fail(ctx, GM_ERR_ARG, "gm_map_digest: bad argument");
     if (!count) return GM_OK;
     DigestArgs a;
-    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.visits = ctx->pool.visits; a.means = ctx->pool.means; a.occ = ctx->pool.occ; a.first = first; a.out = ctx->d_digest;
+    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.visits = ctx->pool.visits; a.means = ctx->pool.means; a.occ = ctx->pool.occ; a.first = first; a.out = ctx->d_digest; a.cap_h = ctx->pool.cap_h;
     launch_digest(a, count, ctx->st);
     ctx->stats.launches++;
     if (int r = check_launch(ctx, "k_digest")) return r;
@@ -810,7 +821,7 @@ int gm_map_entropy(gm_ctx* ctx, uint32_t first, uint32_t count, double* out) {
     if (!out || first + count > ctx->n) return fail(ctx, GM_ERR_ARG, "gm_map_entropy: bad argument");
     if (!count) return GM_OK;
     DigestArgs a;
-    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.visits = ctx->pool.visits; a.means = ctx->pool.means; a.occ = ctx->pool.occ; a.first = first; a.out = nullptr;
+    a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool.cells; a.visits = ctx->pool.visits; a.means = ctx->pool.means; a.occ = ctx->pool.occ; a.first = first; a.out = nullptr; a.cap_h = ctx->pool.cap_h;
     double* d = reinterpret_cast<double*>(ctx->d_digest);  // scratch: seven words per particle
     launch_entropy(a, d, count, ctx->st);
     ctx->stats.launches++;
@@ -835,10 +846,11 @@ int gm_check_refcounts(gm_ctx* ctx, uint64_t* mismatches_out, uint64_t* referenc
     ctx->stats.launches += 2;
     if (int r = check_launch(ctx, "k_recount")) return r;
     unsigned long long h[3] = {0, 0, 0};
-    int top = 0;
+    int tops[2] = {0, 0};
     CK(cudaMemcpyAsync(h, out, sizeof h, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaMemcpyAsync(&top, ctx->pool.free_top, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(tops, ctx->pool.free_top, sizeof tops, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
+    const int top = std::max(0, tops[0]) + std::max(0, tops[1]);
     if (mismatches_out) *mismatches_out = h[0] + h[2];
     if (referenced_out) *referenced_out = h[1];
     if (h[0] || h[2]) return fail(ctx, GM_ERR_INTERNAL, "gm_check_refcounts: %llu patches whose reference count differs from the directories, %llu dangling references", h[0], h[2]);

@@ -66,22 +66,33 @@ struct Counters {  // zeroed per stage, read back by the host
     unsigned long long reg_phase[8];
 };
 
+// Two kinds of patches share one id space.  Ids [0, cap_h) are HIT-CAPABLE: they own a slice of every plane.  Ids [cap_h, cap)
+// are FREE-SPACE patches: no cell of theirs has ever been an end point (n == 0 everywhere, acc == 0, no mean, no occupied bit),
+// so all they own is their slice of the visit counters -- 4 KB instead of 36 KB.  About half of the patches of an indoor map are
+// of this kind (profiles/r02_summary.md).  A free-space patch that receives its first hit moves to a hit-capable id
+// (k_register, "promotion"); a hit-capable id may also hold a patch without hits (the free-space stack ran dry, or the patch
+// was allocated by an upload).  Readers treat id >= cap_h as "n = 0".
 struct Pool {
-    int4* cells;       // [(cap+1)*1024] {acc.x, acc.y, n, 0}; patch `cap` is all zero
+    int4* cells;       // [(cap_h+1)*1024] {acc.x, acc.y, n, 0}; patch `cap_h` is all zero
     int* visits;       // [(cap+1)*1024]
-    double2* means;    // [(cap+1)*1024] mean() where n > 0
-    unsigned* occ;     // [(cap+1)*32] occupancy bitmap (see the layout note above)
+    double2* means;    // [(cap_h+1)*1024] mean() where n > 0
+    unsigned* occ;     // [(cap_h+1)*32] occupancy bitmap (see the layout note above); patch `cap_h` is all zero
     int* refcnt;       // [cap]
-    int* free_list;    // [cap] stack of free patch ids, top at *free_top
-    int* free_top;     // number of ids on the stack
+    int* free_list;    // [cap] two stacks of free patch ids: hit-capable ones in [0, cap_h), free-space ones in [cap_h, cap)
+    int* free_top;     // [2] number of ids on each stack (0: hit-capable, 1: free-space)
     int* pending;      // [cap] ids released during a kernel (merged afterwards)
     int* pending_n;
-    int cap;
+    int cap, cap_h;
 };
 
-// take a patch off the free stack (no pushes happen while a kernel runs: released patches go to `pending`)
-__device__ __forceinline__ int pool_alloc(const Pool& pool, Counters* ctr) {
-    int k = atomicSub(pool.free_top, 1) - 1;
+// take a patch off a free stack (no pushes happen while a kernel runs: released patches go to `pending`).  hit: the patch must be
+// able to hold end points; otherwise a free-space patch is preferred and a hit-capable one taken when there is none left
+__device__ __forceinline__ int pool_alloc(const Pool& pool, Counters* ctr, bool hit) {
+    if (!hit && pool.cap > pool.cap_h) {
+        const int k = atomicSub(pool.free_top + 1, 1) - 1;
+        if (k >= 0) return pool.free_list[pool.cap_h + k];
+    }
+    const int k = atomicSub(pool.free_top, 1) - 1;
     if (k < 0) { atomicCAS(&ctr->error, 0, -3); return -1; }
     return pool.free_list[k];
 }

@@ -37,7 +37,7 @@ struct alignas(64) ShmRank {
     uint32_t dir_gen;   // generation of the directory allocations behind dir[] (re-opened by the peers when it changes)
     int32_t dir_cur, geom_cur, dir_cap;
     uint32_t n_local, max_particles;
-    int32_t pool_cap;
+    int32_t pool_cap, pool_cap_h;  // patch ids, and how many of them are hit-capable (the rest: visit counters only)
     cudaIpcMemHandle_t cells, visits, gather[2], dir[2], geom[2];
     alignas(64) uint32_t flag_rows;    // written by this rank's GPU: number of the last scan whose rows are in every gather buffer
     alignas(64) uint32_t flag_maps;    // host: this rank's maps are complete and published for resampling #k
@@ -85,7 +85,7 @@ struct gm_dist {
 
 namespace gm {
 
-struct PeerView { const int* dir; const Geom* geom; const int4* cells; const int* visits; int dir_cap; };
+struct PeerView { const int* dir; const Geom* geom; const int4* cells; const int* visits; int dir_cap, cap_h; };
 struct PullArgs {
     PeerView peer[kMaxRanks];
     const uint2* imports;  // {owner rank, slot on the owner} per imported parent
@@ -133,8 +133,8 @@ __global__ void __launch_bounds__(256) k_pull_scan(PullArgs A) {
     if (threadIdx.x == 0) A.geom[slot] = g;
 }
 
-// pass 2, CTAs stride over the distinct patches: take a local patch, copy cells + visit counters out of the owner's HBM,
-// rebuild the derived planes (means where n > 0, occupancy bitmap)
+// pass 2, CTAs stride over the distinct patches: take a local patch of the owner's kind, copy the visit counters -- and, for a
+// hit-capable patch, the cells -- out of the owner's HBM, rebuild the derived planes (means where n > 0, occupancy bitmap)
 __global__ void __launch_bounds__(256) k_pull_copy(PullArgs A) {
     __shared__ int s_id;
     const int total = min(*A.uniq_n, A.uniq_cap);
@@ -144,24 +144,30 @@ __global__ void __launch_bounds__(256) k_pull_copy(PullArgs A) {
         const PeerView V = A.peer[(unsigned)(key >> 32)];
         const unsigned rid = (unsigned)key;
         __syncthreads();
+        const bool src_h = (int)rid < V.cap_h;
         if (threadIdx.x == 0) {
-            s_id = pool_alloc(A.pool, A.ctr);
+            s_id = pool_alloc(A.pool, A.ctr, src_h);
             A.hval[h] = s_id;
             if (s_id >= 0) A.pool.refcnt[s_id] = 0;
         }
         __syncthreads();
         const int id = s_id;
         if (id < 0) continue;
+        const bool dst_h = id < A.pool.cap_h;  // (a free-space patch lands on a hit-capable id when the other stack is empty)
         const int4* src = V.cells + (size_t)rid * kPatchCells;
         const int* vsrc = V.visits + (size_t)rid * kPatchCells;
         int4 c[4]; int v[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) { c[i] = __ldcg(src + i * 256 + threadIdx.x); v[i] = __ldcg(vsrc + i * 256 + threadIdx.x); }
+        for (int i = 0; i < 4; i++) {
+            c[i] = src_h ? __ldcg(src + i * 256 + threadIdx.x) : make_int4(0, 0, 0, 0);
+            v[i] = __ldcg(vsrc + i * 256 + threadIdx.x);
+        }
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int ci = i * 256 + threadIdx.x;  // a warp covers one patch row per trip
-            A.pool.cells[(size_t)id * kPatchCells + ci] = make_int4(c[i].x, c[i].y, c[i].z, 0);
             A.pool.visits[(size_t)id * kPatchCells + ci] = v[i];
+            if (!dst_h) continue;
+            A.pool.cells[(size_t)id * kPatchCells + ci] = make_int4(c[i].x, c[i].y, c[i].z, 0);
             if (c[i].z > 0) A.pool.means[(size_t)id * kPatchCells + ci] = cell_mean(c[i].x, c[i].y, c[i].z);
             const unsigned bits = __ballot_sync(0xffffffffu, occ_default(c[i].z, v[i]));
             if ((threadIdx.x & 31) == 0) A.pool.occ[(size_t)id * kPatch + (ci >> kPatchMag)] = bits;
@@ -182,10 +188,18 @@ __global__ void __launch_bounds__(256) k_pull_fix(PullArgs A) {
 }
 
 // leave the hash table empty for the next resampling (only the slots that were used)
+// (and count what was read from the peers: 4 KB of visit counters per patch, 16 KB of cells more for a hit-capable one;
+// *bytes_out is zeroed by the host)
 __global__ void k_pull_clear(PullArgs A, unsigned long long* bytes_out) {
     const int total = min(*A.uniq_n, A.uniq_cap);
-    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < total; u += gridDim.x * blockDim.x) A.hkey[A.uniq_list[u]] = kEmptyKey;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *bytes_out = (unsigned long long)total;
+    unsigned long long bytes = 0;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < total; u += gridDim.x * blockDim.x) {
+        const int h = A.uniq_list[u];
+        const unsigned long long key = A.hkey[h];
+        bytes += (int)(unsigned)key < A.peer[(unsigned)(key >> 32)].cap_h ? kPatchCells * 20ull : kPatchCells * 4ull;
+        A.hkey[h] = kEmptyKey;
+    }
+    if (bytes) atomicAdd(bytes_out, bytes);
 }
 __global__ void k_pull_reset(int* uniq_n) { *uniq_n = 0; }
 
@@ -321,11 +335,12 @@ static int dist_migrate_and_remap(gm_ctx* ctx, const uint32_t* idx_global, const
             const ShmRank& sr = d->shm->r[g];
             const PeerMap& pm = d->peer[g];
             a.peer[g].dir = pm.dir[sr.dir_cur]; a.peer[g].geom = pm.geom[sr.geom_cur];
-            a.peer[g].cells = pm.cells; a.peer[g].visits = pm.visits; a.peer[g].dir_cap = sr.dir_cap;
+            a.peer[g].cells = pm.cells; a.peer[g].visits = pm.visits; a.peer[g].dir_cap = sr.dir_cap; a.peer[g].cap_h = sr.pool_cap_h;
         }
         a.imports = d->d_imports; a.first_slot = (int)n;
         a.geom = ctx->geom; a.dir = ctx->dir; a.dir_cap = ctx->dir_cap; a.pool = ctx->pool; a.ctr = ctx->d_counters;
         a.hkey = d->hkey; a.hval = d->hval; a.hmask = d->hcap - 1; a.uniq_list = d->uniq_list; a.uniq_n = d->uniq_n; a.uniq_cap = ctx->pool.cap;
+        CK(cudaMemsetAsync(ctx->d_digest, 0, sizeof(unsigned long long), ctx->st));  // bytes read from the peers (k_pull_clear)
         gm::k_pull_scan<<<(unsigned)nimp, 256, 0, ctx->st>>>(a);
         gm::k_pull_copy<<<148 * 8, 256, 0, ctx->st>>>(a);
         gm::k_pull_fix<<<(unsigned)nimp, 256, 0, ctx->st>>>(a);
@@ -350,7 +365,7 @@ static int dist_migrate_and_remap(gm_ctx* ctx, const uint32_t* idx_global, const
         if (imports_from_me[g])
             if (int r = wait_flag(ctx, g, [](ShmRank& s) { return &s.flag_pulled; }, k, who)) return r;
     ctx->stats.migrated_particles = nimp;
-    ctx->stats.migrated_bytes = uniq * (unsigned long long)(kPatchCells * 20) + (unsigned long long)nimp * ctx->dir_cap * 4;
+    ctx->stats.migrated_bytes = uniq + (unsigned long long)nimp * ctx->dir_cap * 4;  // patch planes + directories
     ctx->stats.total_migrated_particles += ctx->stats.migrated_particles; ctx->stats.total_migrated_bytes += ctx->stats.migrated_bytes;
     // ---- the ordinary remap, children of imported parents read from the spare slots
     if (int r = gmi_remap(ctx, local_idx.data(), n + (uint32_t)nimp)) return r;
@@ -441,7 +456,7 @@ int gm_dist_init(gm_ctx* ctx, int rank, int world, const void* id_bytes) {
     CK(cudaEventCreate(&d->e0)); CK(cudaEventCreate(&d->e1));
     CK(cudaStreamSynchronize(ctx->st));
     ShmRank& me = d->shm->r[rank];
-    me.n_local = ctx->n; me.max_particles = ctx->max_particles; me.pool_cap = ctx->pool.cap;
+    me.n_local = ctx->n; me.max_particles = ctx->max_particles; me.pool_cap = ctx->pool.cap; me.pool_cap_h = ctx->pool.cap_h;
     CK(cudaIpcGetMemHandle(&me.cells, ctx->pool.cells));
     CK(cudaIpcGetMemHandle(&me.visits, ctx->pool.visits));
     for (int k = 0; k < 2; k++) CK(cudaIpcGetMemHandle(&me.gather[k], d->gather[k]));

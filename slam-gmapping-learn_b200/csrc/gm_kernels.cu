@@ -115,18 +115,29 @@ struct MatchCtx {
     // the particle's directory, read through a shared-memory slot at every use: kept in registers the compiler spends ten
     // instructions per lookup rebuilding the 64-bit address from the kernel parameters instead
     const int* const* dirp_s;
-    const int4* bbox_s;  // shared: cell bounding box of the allocated patches {x_lo, y_lo, x_hi, y_hi} (inclusive; empty: lo > hi)
+    const int4* bbox_s;  // shared: cell bounding box of the hit-capable patches {x_lo, y_lo, x_hi, y_hi} (inclusive; empty: lo > hi)
     const int4* __restrict__ pool;
     const int* __restrict__ visits;
     const double2* __restrict__ means;
     const unsigned* __restrict__ occ;
     const double* __restrict__ inv_n;
     Geom g;
-    int zero_patch;  // id of an all-zero patch: stands in for unallocated / outside patches (const Map::cell, map.h:347-354)
+    int zero_patch;  // = Pool::cap_h, the id of the all-zero patch of the hit planes: stands in for unallocated / outside patches (const
+                     // Map::cell, map.h:347-354) and for free-space patches (ids >= cap_h: n == 0 in every cell)
 };
 
 __device__ __forceinline__ int dir_at(const MatchCtx& M, int px, int py) {
     return ((unsigned)px < (unsigned)M.g.npx && (unsigned)py < (unsigned)M.g.npy) ? __ldg(*M.dirp_s + (px * M.g.npy + py)) : -1;
+}
+
+// (n, visits) of map cell (x, y): unknown (0, 0) outside the map or in an unallocated patch; n = 0 in a free-space patch
+__device__ __forceinline__ void cell_nv(const MatchCtx& M, int x, int y, int& n, int& v) {
+    long long ci;
+    n = 0; v = 0;
+    if (cell_addr(M.g, *M.dirp_s, x, y, ci)) {
+        v = __ldg(M.visits + ci);
+        if (ci < ((long long)M.zero_patch << 10)) n = __ldg(M.pool + ci).z;
+    }
 }
 
 // occupancy tests (smmap.h:25 against fullnessThreshold); DEF = the default threshold 0.1, decided in exact integers
@@ -172,7 +183,7 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
         const bool fast = __all_sync(__activemask(), !twox && !twoy);
         if (fast) {
             const int ida = ldg_if(da, xa_in && ya_in, -1);
-            if (ida < 0) return false;
+            if ((unsigned)ida >= (unsigned)M.zero_patch) return false;  // unknown, or a free-space patch: nothing occupied
             const unsigned* w = M.occ + (((unsigned)ida << kPatchMag) + (unsigned)(x0 & 31));  // rows x0 .. x0 + 2: consecutive words
             const unsigned w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
             mask = ((w0 >> ysh) & 7u) | (((w1 >> ysh) & 7u) << 8) | (((w2 >> ysh) & 7u) << 16);
@@ -228,7 +239,7 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
         if (fx1 < bb.x || fy1 < bb.y || fx0 > bb.z || fy0 > bb.w) fcheck = false;  // clear of every allocated patch (the usual case)
         else if (fx1 < 0 || fy1 < 0 || (fx0 >> kPatchMag) >= g.npx || (fy0 >> kPatchMag) >= g.npy) fcheck = false;
         else if (fx0 >= 0 && fy0 >= 0 && (fx0 >> kPatchMag) == (fx1 >> kPatchMag) && (fy0 >> kPatchMag) == (fy1 >> kPatchMag) &&
-                 dir_at(M, fx0 >> kPatchMag, fy0 >> kPatchMag) < 0) fcheck = false;
+                 (unsigned)dir_at(M, fx0 >> kPatchMag, fy0 >> kPatchMag) >= (unsigned)M.zero_patch) fcheck = false;  // unknown or free-space patch: every cell passes
         // occupied cells in ascending bit order == the reference's xx-outer / yy-inner scan order
         if (!fcheck) {
             // three cells per trip (a wall in the window is usually three to six cells): their load -> distance chains are
@@ -257,8 +268,8 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
                 const int i = __ffs(mask) - 1;
                 mask &= mask - 1;
                 const int xx = i >> 3, yy = i & 7;
-                long long fi; int fn = 0, fv = 0;
-                if (cell_addr(g, *M.dirp_s, x0 + xx + ifx, y0 + yy + ify, fi)) { fn = __ldg(M.pool + fi).z; fv = __ldg(M.visits + fi); }
+                int fn, fv;
+                cell_nv(M, x0 + xx + ifx, y0 + yy + ify, fn, fv);
                 if (!is_free<true>(fn, fv, P)) continue;
                 const double2 mean = ldg_d2(M.means + cell_of(i));
                 const double mx = phx - mean.x, my = phy - mean.y;
@@ -277,7 +288,10 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
         for (int yy = 0; yy <= 2 * k; yy++) {
             long long ci;
             int4 cell = make_int4(0, 0, 0, 0);
-            if (cell_addr(g, *M.dirp_s, x0 + xx, y0 + yy, ci)) { cell = __ldg(M.pool + ci); cell.w = __ldg(M.visits + ci); }
+            if (cell_addr(g, *M.dirp_s, x0 + xx, y0 + yy, ci)) {
+                if (ci < ((long long)M.zero_patch << 10)) cell = __ldg(M.pool + ci);
+                cell.w = __ldg(M.visits + ci);
+            }
             if (!is_occ<false>(cell.z, cell.w, P)) continue;
             if (!have_free) {
                 const double r = __ldg(ranges + b);
@@ -288,8 +302,8 @@ __device__ __forceinline__ bool beam_match(const DevParams& P, const MatchCtx& M
                 ify = cell_index(pfy - P.cy, P.delta, P.inv_delta) + g.sy2;
                 have_free = true;
             }
-            long long fi; int fn = 0, fv = 0;
-            if (cell_addr(g, *M.dirp_s, x0 + xx + ifx, y0 + yy + ify, fi)) { fn = __ldg(M.pool + fi).z; fv = __ldg(M.visits + fi); }
+            int fn, fv;
+            cell_nv(M, x0 + xx + ifx, y0 + yy + ify, fn, fv);
             if (!is_free<false>(fn, fv, P)) continue;
             const double inv = (cell.z >= 0 && cell.z < kInvTable) ? __ldg(M.inv_n + cell.z) : recip_slow(cell.z);
             const double mx = phx - (double)__int_as_float(cell.x) * inv, my = phy - (double)__int_as_float(cell.y) * inv;
@@ -478,13 +492,14 @@ __global__ void __launch_bounds__(kSmThreads * (1 + WIDE), WIDE ? GM_SM_WIDE_CTA
         S.ncand = 1; S.mode = A.query == 1 ? 1 : 0; S.phase = (A.query == 0 || A.query == 1) ? 3 : 0;
     }
     if (K1) {
-        // bounding box of the allocated patches: the free-cell windows (half a map away, see beam_match) normally miss it
+        // bounding box of the patches that can hold occupied cells (a cell of any other patch passes the free-cell test): the
+        // free-cell windows (half a map away, see beam_match) normally miss it
         if (t == 0) { S.bb_lo_x = INT_MAX; S.bb_lo_y = INT_MAX; S.bb_hi_x = -1; S.bb_hi_y = -1; }
         __syncthreads();
         const int* dirp = A.dir + (size_t)p * A.dir_cap;
         int lox = INT_MAX, loy = INT_MAX, hix = -1, hiy = -1;
         for (int e = t; e < M.g.npx * M.g.npy; e += kThreads)
-            if (__ldg(dirp + e) >= 0) { const int px = e / M.g.npy, py = e - px * M.g.npy; lox = min(lox, px); hix = max(hix, px); loy = min(loy, py); hiy = max(hiy, py); }
+            if ((unsigned)__ldg(dirp + e) < (unsigned)A.zero_patch) { const int px = e / M.g.npy, py = e - px * M.g.npy; lox = min(lox, px); hix = max(hix, px); loy = min(loy, py); hiy = max(hiy, py); }
         lox = __reduce_min_sync(0xffffffffu, lox); loy = __reduce_min_sync(0xffffffffu, loy);
         hix = __reduce_max_sync(0xffffffffu, hix); hiy = __reduce_max_sync(0xffffffffu, hiy);
         if ((t & 31) == 0 && hix >= 0) { atomicMin(&S.bb_lo_x, lox); atomicMin(&S.bb_lo_y, loy); atomicMax(&S.bb_hi_x, hix); atomicMax(&S.bb_hi_y, hiy); }
@@ -1038,31 +1053,27 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
         for (int k = warp; k < nwork; k += nw) {
             const int e = work[k];
             const int id = dirp[e], mode = id < 0 ? 1 : 2;  // 1 zero-fill a new patch, 2 copy
+            // a copy keeps the kind of its source; a new patch starts as a free-space patch (4 KB) and moves to a hit-capable id
+            // only if an end point lands in it (phase 4)
+            const bool src_h = mode == 2 && id < A.pool.cap_h;
             int nid = -1;
-            if (lane == 0) nid = pool_alloc(A.pool, A.counters);
+            if (lane == 0) nid = pool_alloc(A.pool, A.counters, src_h);
             nid = __shfl_sync(0xffffffffu, nid, 0);
             if (nid < 0) continue;
+            const bool dst_h = nid < A.pool.cap_h;  // (a free-space patch may land on a hit-capable id when the other stack is empty)
             int4* dst = A.pool.cells + (size_t)nid * kPatchCells;
             int4* vdst = reinterpret_cast<int4*>(A.pool.visits + (size_t)nid * kPatchCells);
             int4* mdst = reinterpret_cast<int4*>(A.pool.means + (size_t)nid * kPatchCells);
-            if (mode == 1) {
+            if (dst_h && !src_h) {  // hit planes of a patch without hits: n = 0, nothing occupied; means are only read where n > 0
                 for (int i = lane; i < kPatchCells; i += 32) dst[i] = make_int4(0, 0, 0, 0);
-                for (int i = lane; i < kPatchCells / 4; i += 32) vdst[i] = make_int4(0, 0, 0, 0);
-                // means are only defined (and only read) where n > 0: nothing to initialise
                 A.pool.occ[(size_t)nid * kPatch + lane] = 0u;
+            }
+            if (mode == 1) {
+                for (int i = lane; i < kPatchCells / 4; i += 32) vdst[i] = make_int4(0, 0, 0, 0);
             } else {
                 // four independent 16-byte loads in flight per lane, then the stores (source and destination come from
                 // the same array: the compiler keeps a plain copy loop strictly load -> store -> load)
-                const int4* src = A.pool.cells + (size_t)id * kPatchCells;
                 const int4* vsrc = reinterpret_cast<const int4*>(A.pool.visits + (size_t)id * kPatchCells);
-                bool hits = false;
-                for (int i0 = lane; i0 < kPatchCells; i0 += 128) {
-                    int4 c[4];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) c[k] = __ldcg(src + i0 + 32 * k);
-#pragma unroll
-                    for (int k = 0; k < 4; k++) { dst[i0 + 32 * k] = c[k]; hits = hits || c[k].z != 0; }
-                }
                 for (int i0 = lane; i0 < kPatchCells / 4; i0 += 128) {
                     int4 c[4];
 #pragma unroll
@@ -1070,17 +1081,28 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
 #pragma unroll
                     for (int k = 0; k < 4; k++) vdst[i0 + 32 * k] = c[k];
                 }
-                if (__any_sync(0xffffffffu, hits)) {  // free-space patches (most of them) have no mean to copy
-                    const int4* msrc = reinterpret_cast<const int4*>(A.pool.means + (size_t)id * kPatchCells);
+                if (src_h) {
+                    const int4* src = A.pool.cells + (size_t)id * kPatchCells;
+                    bool hits = false;
                     for (int i0 = lane; i0 < kPatchCells; i0 += 128) {
                         int4 c[4];
 #pragma unroll
-                        for (int k = 0; k < 4; k++) c[k] = __ldcg(msrc + i0 + 32 * k);
+                        for (int k = 0; k < 4; k++) c[k] = __ldcg(src + i0 + 32 * k);
 #pragma unroll
-                        for (int k = 0; k < 4; k++) mdst[i0 + 32 * k] = c[k];
+                        for (int k = 0; k < 4; k++) { dst[i0 + 32 * k] = c[k]; hits = hits || c[k].z != 0; }
                     }
+                    if (__any_sync(0xffffffffu, hits)) {  // (a hit-capable id may hold a patch without hits: no mean to copy)
+                        const int4* msrc = reinterpret_cast<const int4*>(A.pool.means + (size_t)id * kPatchCells);
+                        for (int i0 = lane; i0 < kPatchCells; i0 += 128) {
+                            int4 c[4];
+#pragma unroll
+                            for (int k = 0; k < 4; k++) c[k] = __ldcg(msrc + i0 + 32 * k);
+#pragma unroll
+                            for (int k = 0; k < 4; k++) mdst[i0 + 32 * k] = c[k];
+                        }
+                    }
+                    A.pool.occ[(size_t)nid * kPatch + lane] = __ldcg(A.pool.occ + (size_t)id * kPatch + lane);
                 }
-                A.pool.occ[(size_t)nid * kPatch + lane] = __ldcg(A.pool.occ + (size_t)id * kPatch + lane);
             }
             __syncwarp();
             if (lane == 0) {
@@ -1195,7 +1217,8 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
             // eight independent loads in flight per lane: the patch is private, plain read-modify-write of the visits
             // plane (a warp covers one row of the patch per k: 128 contiguous bytes).  More visits can only clear an
             // occupancy bit: lane k keeps the bitmap word of row k, and n is fetched for the few crossed cells whose bit is set
-            const unsigned occ_old = lane < 8 ? __ldcg(occ + lane) : 0u;
+            // (a free-space patch has no bitmap, and nothing in it is occupied)
+            const unsigned occ_old = (lane < 8 && id < A.pool.cap_h) ? __ldcg(occ + lane) : 0u;
             unsigned occ_new = occ_old;
             int v[8]; unsigned c[8];
 #pragma unroll
@@ -1220,6 +1243,7 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
         __syncthreads();
         PHASE(5);
     }
+    if (threadIdx.x == 0) s_nwork = 0;  // (for the promotion list below)
     __threadfence();
     __syncthreads();
 
@@ -1227,6 +1251,50 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
     // are grouped by cell in a shared-memory hash table (it reuses the tile area): slot = the cell's table entry, and per
     // slot the first and last beam that hit it.  The first beam of a cell then adds up the cell's beams in ascending
     // order by scanning slot_of[] from itself to the last one -- a handful of neighbouring beams in practice.
+    // First, the free-space patches that receive their first end point move to hit-capable ids ("promotion"): the first beam
+    // that claims the directory entry lists it, then a warp per listed entry takes a hit-capable patch, copies the visit
+    // counters, zeroes the hit planes and gives the old patch back.  (The patches are private since phase 2.)
+    {
+        int* promote = reinterpret_cast<int*>(M.tiles);  // the tile area is free again
+        // when the free-space updates took a single pass, s_tile_id still lists the patch of every active entry by rank: the
+        // usual answer ("already hit-capable") then costs no global load
+        const bool ranked = P.generate_map && nactive <= A.tile_cap;
+        for (int b = threadIdx.x; b < (int)P.nbeams; b += blockDim.x) {
+            if (!(rec[b].flags & 4)) continue;
+            const int e = (rec[b].p1x >> kPatchMag) * g.npy + (rec[b].p1y >> kPatchMag);
+            if (ranked && s_tile_id[(int)M.prefix[e >> 5] + __popc(active[e >> 5] & ((1u << (e & 31)) - 1u))] < A.pool.cap_h) continue;
+            const int id = dirp[e];
+            if (id >= A.pool.cap_h && atomicCAS(dirp + e, id, -2 - id) == id) promote[atomicAdd(&s_nwork, 1)] = e;  // (at most nbeams entries)
+        }
+        __syncthreads();
+        const int npromote = s_nwork;
+        for (int k = warp; k < npromote; k += nw) {
+            const int e = promote[k];
+            const int id = -2 - dirp[e];
+            int nid = -1;
+            if (lane == 0) nid = pool_alloc(A.pool, A.counters, true);
+            nid = __shfl_sync(0xffffffffu, nid, 0);
+            if (nid < 0) { if (lane == 0) dirp[e] = id; continue; }  // pool exhausted (flagged): the entry keeps its patch, the hit phase skips it
+            const int4* vsrc = reinterpret_cast<const int4*>(A.pool.visits + (size_t)id * kPatchCells);
+            int4* vdst = reinterpret_cast<int4*>(A.pool.visits + (size_t)nid * kPatchCells);
+            int4* dst = A.pool.cells + (size_t)nid * kPatchCells;
+            for (int i = lane; i < kPatchCells / 4; i += 32) vdst[i] = __ldcg(vsrc + i);
+            for (int i = lane; i < kPatchCells; i += 32) dst[i] = make_int4(0, 0, 0, 0);
+            A.pool.occ[(size_t)nid * kPatch + lane] = 0u;
+            __syncwarp();
+            if (lane == 0) {
+                A.pool.refcnt[nid] = 1;
+                dirp[e] = nid;
+                A.pool.refcnt[id] = 0;  // private since phase 2: this was its only reference
+                A.pool.pending[atomicAdd(A.pool.pending_n, 1)] = id;
+                atomicAdd(&s_alloc, 1ull);
+            }
+        }
+        if (npromote) {  // (uniform: the usual scan promotes nothing)
+            __threadfence();
+            __syncthreads();
+        }
+    }
     const int hs = A.sort_n << 1;  // table entries: a power of two >= 2 * nbeams
     unsigned long long* hkey = M.keys;
     int* hfirst = reinterpret_cast<int*>(hkey + hs);
@@ -1257,7 +1325,7 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
         if (slot < 0 || hfirst[slot] != b) continue;  // not the first beam of its cell
         const int x = rec[b].p1x, y = rec[b].p1y;
         int id = dirp[(x >> kPatchMag) * g.npy + (y >> kPatchMag)];
-        if (id < 0) continue;
+        if ((unsigned)id >= (unsigned)A.pool.cap_h) continue;  // no patch (pool exhausted, flagged)
         int* cell = reinterpret_cast<int*>(A.pool.cells + (size_t)id * kPatchCells + ((x & 31) << kPatchMag) + (y & 31));
         float ax = __int_as_float(__ldcg(cell)), ay = __int_as_float(__ldcg(cell + 1));
         int* visp = A.pool.visits + (size_t)id * kPatchCells + ((x & 31) << kPatchMag) + (y & 31);
@@ -1326,12 +1394,22 @@ __global__ void k_addref_slots(const Geom* __restrict__ geom, const int* __restr
         if (id >= 0) atomicAdd(&pool.refcnt[id], 1);
     }
 }
+// released ids go back to the stack of their kind (one CTA)
 __global__ void k_merge_free(Pool pool) {
-    int n = *pool.pending_n, top = *pool.free_top;
-    if (top < 0) top = 0;  // exhausted during the stage (error already flagged)
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) pool.free_list[top + i] = pool.pending[i];
+    __shared__ int s_add[2];
+    const int n = *pool.pending_n;
+    int top_h = pool.free_top[0], top_f = pool.free_top[1];
+    if (top_h < 0) top_h = 0;  // exhausted during the stage (error already flagged)
+    if (top_f < 0) top_f = 0;  // (ran dry: the hit-capable stack served the rest)
+    if (threadIdx.x < 2) s_add[threadIdx.x] = 0;
     __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.x == 0) { *pool.free_top = top + n; *pool.pending_n = 0; }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int id = pool.pending[i];
+        if (id < pool.cap_h) pool.free_list[top_h + atomicAdd(&s_add[0], 1)] = id;
+        else pool.free_list[pool.cap_h + top_f + atomicAdd(&s_add[1], 1)] = id;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { pool.free_top[0] = top_h + s_add[0]; pool.free_top[1] = top_f + s_add[1]; *pool.pending_n = 0; }
 }
 // MAP_CONSISTENCY_CHECK of the reference (gridslamprocessor.cpp:82-143: every patch's share count against the number of maps that
 // point at it): recount the references from the directories of the n live particles and compare with pool.refcnt; out[0] =
@@ -1363,8 +1441,11 @@ void launch_recount_compare(const Pool& pool, int* recount, unsigned long long* 
 
 __global__ void k_pool_init(Pool pool) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < pool.cap) { pool.free_list[i] = pool.cap - 1 - i; pool.refcnt[i] = 0; }
-    if (i == 0) { *pool.free_top = pool.cap; *pool.pending_n = 0; }
+    if (i < pool.cap) {  // both stacks hand out ascending ids
+        pool.free_list[i] = i < pool.cap_h ? pool.cap_h - 1 - i : pool.cap - 1 - (i - pool.cap_h);
+        pool.refcnt[i] = 0;
+    }
+    if (i == 0) { pool.free_top[0] = pool.cap_h; pool.free_top[1] = pool.cap - pool.cap_h; *pool.pending_n = 0; }
 }
 __global__ void k_fill_int(int* p, size_t n, int v) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
@@ -1490,7 +1571,7 @@ __global__ void __launch_bounds__(256) k_entropy(DigestArgs A, double* out) {
         const int id = dirp[e];
         if (id < 0) continue;
         for (int i = lane; i < kPatchCells; i += 32) {
-            const int n = A.pool[(size_t)id * kPatchCells + i].z, v = A.visits[(size_t)id * kPatchCells + i];
+            const int n = id < A.cap_h ? A.pool[(size_t)id * kPatchCells + i].z : 0, v = A.visits[(size_t)id * kPatchCells + i];
             if (!v) continue;
             double h = 0.;
             if (n != v && n != 0) { const double x = (double)n / (double)v; h = -(x * log(x) + (1. - x) * log(1. - x)); }
@@ -1518,12 +1599,13 @@ __global__ void __launch_bounds__(256) k_digest(DigestArgs A) {
         if (lane == 0) patches++;
         int px = e / g.npy, py = e % g.npy;
         const int4* pc = A.pool + (size_t)id * kPatchCells;
+        const bool hit_capable = id < A.cap_h;  // a free-space patch: visit counters only, n = 0 and acc = 0 everywhere
         for (int i = lane; i < kPatchCells; i += 32) {
-            int4 c = pc[i];
+            int4 c = hit_capable ? pc[i] : make_int4(0, 0, 0, 0);
             c.w = A.visits[(size_t)id * kPatchCells + i];
             // the warp holds row i >> 5 of the patch: its occupancy bits must equal the bitmap word
             const unsigned bits = __ballot_sync(0xffffffffu, occ_default(c.z, c.w));
-            if (lane == 0 && bits != A.occ[(size_t)id * kPatch + (i >> kPatchMag)]) bad++;
+            if (lane == 0 && hit_capable && bits != A.occ[(size_t)id * kPatch + (i >> kPatchMag)]) bad++;
             if (c.z > 0) {  // and the stored mean must be the one recomputed from acc and n, bit for bit
                 const double2 want = cell_mean(c.x, c.y, c.z), have = A.means[(size_t)id * kPatchCells + i];
                 if (__double_as_longlong(want.x) != __double_as_longlong(have.x) || __double_as_longlong(want.y) != __double_as_longlong(have.y)) bad++;
@@ -1549,10 +1631,10 @@ __global__ void k_export_list(const int* __restrict__ dirp, Geom g, int* __restr
         if (id >= 0) { int k = atomicAdd(count, 1); list[2 * k] = e; list[2 * k + 1] = id; }
     }
 }
-__global__ void k_export_gather(const int4* __restrict__ pool, const int* __restrict__ visits, const int* __restrict__ list, int4* __restrict__ out) {
+__global__ void k_export_gather(const int4* __restrict__ pool, const int* __restrict__ visits, int cap_h, const int* __restrict__ list, int4* __restrict__ out) {
     const int k = blockIdx.x, id = list[2 * k + 1];
     for (int i = threadIdx.x; i < kPatchCells; i += blockDim.x) {  // gm_cell: {acc.x, acc.y, n, visits}
-        int4 c = pool[(size_t)id * kPatchCells + i];
+        int4 c = id < cap_h ? pool[(size_t)id * kPatchCells + i] : make_int4(0, 0, 0, 0);
         c.w = visits[(size_t)id * kPatchCells + i];
         out[(size_t)k * kPatchCells + i] = c;
     }
@@ -1560,14 +1642,14 @@ __global__ void k_export_gather(const int4* __restrict__ pool, const int* __rest
 
 // occupancy grid of one particle (the nav_msgs::OccupancyGrid fill of gmapping/src/slam_gmapping.cpp:956-993):
 // out[y * width + x] = -1 unknown (never visited), 100 if n / visits > occ_thresh, else 0
-__global__ void k_export_occupancy(const int* __restrict__ dirp, Geom g, const int4* __restrict__ pool, const int* __restrict__ visits, double occ_thresh, signed char* __restrict__ out,
-                                   int width, int height) {
+__global__ void k_export_occupancy(const int* __restrict__ dirp, Geom g, const int4* __restrict__ pool, const int* __restrict__ visits, int cap_h, double occ_thresh,
+                                   signed char* __restrict__ out, int width, int height) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= width || y >= height) return;
     long long ci;
     signed char v = -1;
     if (cell_addr(g, dirp, x, y, ci)) {
-        int4 c = __ldg(pool + ci);
+        int4 c = ci < ((long long)cap_h << 10) ? __ldg(pool + ci) : make_int4(0, 0, 0, 0);
         c.w = __ldg(visits + ci);
         if (c.w) v = ((double)c.z / (double)c.w > occ_thresh) ? 100 : 0;
     }
@@ -1586,14 +1668,19 @@ __global__ void k_release_particle(int* dirp, int nent, Pool pool) {
 __global__ void k_install_patches(int* dirp, Geom g, const int* __restrict__ coords, const int4* __restrict__ staged, Pool pool, Counters* ctr) {
     __shared__ int s_id;
     const int k = blockIdx.x;
-    if (threadIdx.x == 0) s_id = pool_alloc(pool, ctr);
+    int any = 0;  // a patch with an end point in it (or a non-zero accumulator) needs the hit planes
+    for (int i = threadIdx.x; i < kPatchCells; i += blockDim.x) { const int4 c = staged[(size_t)k * kPatchCells + i]; any |= c.x | c.y | c.z; }
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) s_id = pool_alloc(pool, ctr, any != 0);
     __syncthreads();
     const int id = s_id;
     if (id < 0) return;
+    const bool hit_capable = id < pool.cap_h;
     for (int i = threadIdx.x; i < kPatchCells; i += blockDim.x) {  // blockDim is a multiple of 32: a warp covers one row per trip
         const int4 c = staged[(size_t)k * kPatchCells + i];
-        pool.cells[(size_t)id * kPatchCells + i] = make_int4(c.x, c.y, c.z, 0);
         pool.visits[(size_t)id * kPatchCells + i] = c.w;
+        if (!hit_capable) continue;
+        pool.cells[(size_t)id * kPatchCells + i] = make_int4(c.x, c.y, c.z, 0);
         pool.means[(size_t)id * kPatchCells + i] = cell_mean(c.x, c.y, c.z);
         const unsigned bits = __ballot_sync(0xffffffffu, occ_default(c.z, c.w));
         if ((i & 31) == 0) pool.occ[(size_t)id * kPatch + (i >> kPatchMag)] = bits;
@@ -1602,9 +1689,9 @@ __global__ void k_install_patches(int* dirp, Geom g, const int* __restrict__ coo
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-void launch_export_occupancy(const int* dirp, Geom g, const int4* pool, const int* visits, double occ_thresh, signed char* out, int width, int height, cudaStream_t st) {
+void launch_export_occupancy(const int* dirp, Geom g, const int4* pool, const int* visits, int cap_h, double occ_thresh, signed char* out, int width, int height, cudaStream_t st) {
     dim3 grid((width + 255) / 256, height);
-    k_export_occupancy<<<grid, 256, 0, st>>>(dirp, g, pool, visits, occ_thresh, out, width, height);
+    k_export_occupancy<<<grid, 256, 0, st>>>(dirp, g, pool, visits, cap_h, occ_thresh, out, width, height);
 }
 void launch_release_particle(int* dirp, int nent, const Pool& pool, cudaStream_t st) { k_release_particle<<<64, 256, 0, st>>>(dirp, nent, pool); }
 void launch_install_patches(int* dirp, Geom g, const int* coords, const int4* staged, const Pool& pool, Counters* ctr, int n, cudaStream_t st) {
@@ -1669,6 +1756,6 @@ void launch_resample(const double* w, unsigned n, unsigned n_out, double u01, do
 void launch_digest(const DigestArgs& a, unsigned n, cudaStream_t st) { k_digest<<<n, 256, 0, st>>>(a); }
 void launch_entropy(const DigestArgs& a, double* out, unsigned n, cudaStream_t st) { k_entropy<<<n, 256, 0, st>>>(a, out); }
 void launch_export_list(const int* dirp, Geom g, int* list, int* count, cudaStream_t st) { k_export_list<<<64, 256, 0, st>>>(dirp, g, list, count); }
-void launch_export_gather(const int4* pool, const int* visits, const int* list, int4* out, int n, cudaStream_t st) { k_export_gather<<<n, 256, 0, st>>>(pool, visits, list, out); }
+void launch_export_gather(const int4* pool, const int* visits, int cap_h, const int* list, int4* out, int n, cudaStream_t st) { k_export_gather<<<n, 256, 0, st>>>(pool, visits, cap_h, list, out); }
 
 }  // namespace gm

@@ -61,6 +61,7 @@ struct RemapArgs {
 struct DigestArgs {
     const Geom* geom; const int* dir; int dir_cap; const int4* pool; const int* visits; const double2* means; const unsigned* occ;
     unsigned first; unsigned long long* out;  // 7 words per particle: the six of gm_digest + mismatching occupancy-bitmap rows
+    int cap_h;                                // Pool::cap_h: ids at or above it are free-space patches (visit counters only)
 };
 
 size_t scanmatch_smem_bytes(unsigned nbeams);
@@ -85,10 +86,10 @@ void launch_normalize(const double* logw, const double* rows, unsigned n, double
 void launch_resample(const double* w, unsigned n, unsigned n_out, double u01, double* cum, double* tgt, unsigned* idx, unsigned* emitted, cudaStream_t st);
 void launch_digest(const DigestArgs& a, unsigned n, cudaStream_t st);
 void launch_entropy(const DigestArgs& a, double* out, unsigned n, cudaStream_t st);
-void launch_export_occupancy(const int* dirp, Geom g, const int4* pool, const int* visits, double occ_thresh, signed char* out, int width, int height, cudaStream_t st);
+void launch_export_occupancy(const int* dirp, Geom g, const int4* pool, const int* visits, int cap_h, double occ_thresh, signed char* out, int width, int height, cudaStream_t st);
 void launch_release_particle(int* dirp, int nent, const Pool& pool, cudaStream_t st);
 void launch_install_patches(int* dirp, Geom g, const int* coords, const int4* staged, const Pool& pool, Counters* ctr, int n, cudaStream_t st);
 void launch_export_list(const int* dirp, Geom g, int* list, int* count, cudaStream_t st);
-void launch_export_gather(const int4* pool, const int* visits, const int* list, int4* out, int n, cudaStream_t st);
+void launch_export_gather(const int4* pool, const int* visits, int cap_h, const int* list, int4* out, int n, cudaStream_t st);
 
 }  // namespace gm

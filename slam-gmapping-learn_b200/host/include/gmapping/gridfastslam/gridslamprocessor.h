@@ -135,6 +135,7 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     struct DeviceStats {
         double msScanMatch, msWeights, msRemap, msRegister, msMigrate, msAllGather;
         unsigned long long beamEvals, scoreEvals, cowCopies, patchAllocs, freeUpdates, hitUpdates, poolInUse, launches;
+        unsigned long long poolHitInUse;  // of poolInUse, the patches that hold end points (36 KB each; the others 4 KB)
         unsigned long long migratedParticles, migratedBytes;
         // wall clock of the host-side parts of the last processScan (ms): motion model, scanMatch call incl. transfers,
         // both updateTreeWeights (normalize on the GPU + tree propagation), resample call incl. registration

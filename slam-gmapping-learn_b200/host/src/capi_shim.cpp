@@ -124,19 +124,19 @@ void gmh_indexes(void* hv, unsigned* out) {
     if (!idx.empty()) memcpy(out, idx.data(), sizeof(unsigned) * idx.size());
 }
 
-// out[35]: ... then msHostMotion msHostScanMatch msHostTreeWeights msHostResample, 6 device totals, 4 host totals, 3 work totals
+// out[36]: ... then msHostMotion msHostScanMatch msHostTreeWeights msHostResample, 6 device totals, 4 host totals, 3 work totals
 // out[16]: msScanMatch msWeights msRemap msRegister msMigrate msAllGather beamEvals scoreEvals cowCopies patchAllocs freeUpdates
 //          hitUpdates poolInUse launches migratedParticles migratedBytes
 void gmh_device_stats(void* hv, double* out) {
     const GridSlamProcessor::DeviceStats d = static_cast<Handle*>(hv)->gsp->deviceStats();
-    const double v[35] = {d.msScanMatch, d.msWeights, d.msRemap, d.msRegister, d.msMigrate, d.msAllGather, (double)d.beamEvals, (double)d.scoreEvals,
+    const double v[36] = {d.msScanMatch, d.msWeights, d.msRemap, d.msRegister, d.msMigrate, d.msAllGather, (double)d.beamEvals, (double)d.scoreEvals,
                           (double)d.cowCopies, (double)d.patchAllocs, (double)d.freeUpdates, (double)d.hitUpdates, (double)d.poolInUse,
                           (double)d.launches, (double)d.migratedParticles, (double)d.migratedBytes,
                           d.msHostMotion, d.msHostScanMatch, d.msHostTreeWeights, d.msHostResample,
                           d.totalMs[0], d.totalMs[1], d.totalMs[2], d.totalMs[3], d.totalMs[4], d.totalMs[5],
                           d.totalHostMs[0], d.totalHostMs[1], d.totalHostMs[2], d.totalHostMs[3],
                           (double)d.totalBeamEvals, (double)d.totalScoreEvals, (double)d.totalScanMatches,
-                          (double)d.totalMigratedParticles, (double)d.totalMigratedBytes};
+                          (double)d.totalMigratedParticles, (double)d.totalMigratedBytes, (double)d.poolHitInUse};
     memcpy(out, v, sizeof v);
 }
 

@@ -821,7 +821,7 @@ GridSlamProcessor::DeviceStats GridSlamProcessor::deviceStats() const {
     m_device->check(gm_get_stats(m_device->h, &s), "gm_get_stats");
     d.msScanMatch = s.ms_scanmatch; d.msWeights = s.ms_weights; d.msRemap = s.ms_remap; d.msRegister = s.ms_register;
     d.beamEvals = s.beam_evals; d.scoreEvals = s.score_evals; d.cowCopies = s.cow_copies; d.patchAllocs = s.patch_allocs;
-    d.freeUpdates = s.free_updates; d.hitUpdates = s.hit_updates; d.poolInUse = s.pool_in_use; d.launches = s.launches;
+    d.freeUpdates = s.free_updates; d.hitUpdates = s.hit_updates; d.poolInUse = s.pool_in_use; d.poolHitInUse = s.pool_hit_in_use; d.launches = s.launches;
     for (int k = 0; k < 6; k++) d.totalMs[k] = s.total_ms[k];
     for (int k = 0; k < 4; k++) d.totalHostMs[k] = m_hostMsTotal[k];
     d.totalBeamEvals = s.total_beam_evals; d.totalScoreEvals = s.total_score_evals; d.totalScanMatches = s.total_scanmatches;

@@ -14,7 +14,7 @@ STAT_KEYS = ["ms_scanmatch", "ms_weights", "ms_remap", "ms_register", "ms_migrat
              "host_ms_motion", "host_ms_scanmatch", "host_ms_treeweights", "host_ms_resample",
              "total_ms_scanmatch", "total_ms_weights", "total_ms_remap", "total_ms_register", "total_ms_migrate", "total_ms_allgather",
              "total_host_ms_motion", "total_host_ms_scanmatch", "total_host_ms_treeweights", "total_host_ms_resample",
-             "total_beam_evals", "total_score_evals", "total_scanmatches", "total_migrated_particles", "total_migrated_bytes"]
+             "total_beam_evals", "total_score_evals", "total_scanmatches", "total_migrated_particles", "total_migrated_bytes", "pool_hit_in_use"]
 PARAM_ORDER = ["maxUrange", "maxrange", "sigma", "kernelSize", "lstep", "astep", "iterations", "lsigma", "ogain", "lskip", "srr", "srt", "str",
                "stt", "linearUpdate", "angularUpdate", "resampleThreshold", "period", "generate_map", "minimumScore"]
 DEFAULTS = dict(maxUrange=80., maxrange=80., sigma=0.05, kernelSize=1, lstep=0.05, astep=0.05, iterations=5, lsigma=0.075, ogain=3., lskip=0,
@@ -153,7 +153,7 @@ class Processor:
         f = self.L.gmh_first_local(self.h); return f, f + self.L.gmh_local_particles(self.h)
 
     def stats(self):
-        a = np.zeros(35); self.L.gmh_device_stats(self.h, _dp(a)); return dict(zip(STAT_KEYS, a.tolist()))
+        a = np.zeros(36); self.L.gmh_device_stats(self.h, _dp(a)); return dict(zip(STAT_KEYS, a.tolist()))
 
     def map_digests(self):
         nl = self.L.gmh_local_particles(self.h)

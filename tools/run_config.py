@@ -87,7 +87,8 @@ def main():
            "device_ms_per_scan_median": float(np.median([sum(s[k] for k in keys) for s in stats[3:]])),
            "migrate_ms_median_when_resampling": float(np.median([s["ms_migrate"] for s in stats[3:] if s["ms_migrate"] > 0] or [0.0])),  # scans 0-2: registration only / NCCL connection setup
            "stage_ms": {k[3:]: float(np.mean([s[k] for s in stats[3:]])) for k in keys},
-           "pool_patches_in_use": stats[-1]["pool_in_use"], "patches_per_particle": stats[-1]["pool_in_use"] / max(1, (proc.local_range()[1] - proc.local_range()[0])),
+           "pool_patches_in_use": stats[-1]["pool_in_use"], "pool_hit_patches_in_use": stats[-1]["pool_hit_in_use"],
+           "patch_gb_in_use": (stats[-1]["pool_in_use"] * 4096 + stats[-1]["pool_hit_in_use"] * 32896) / 2**30, "patches_per_particle": stats[-1]["pool_in_use"] / max(1, (proc.local_range()[1] - proc.local_range()[0])),
            "hbm_used_gb": (total_b - free_b) / 2**30, "migrated_particles": float(stats[-1]["total_migrated_particles"]),
            "migrated_mb": float(stats[-1]["total_migrated_bytes"]) / 2**20, "neff_last": proc.neff(),
            "distinct_parents_last": int(len(set(proc.indexes().tolist()))) if proc.resamples() else None,
