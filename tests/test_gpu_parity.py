@@ -44,6 +44,22 @@ def test_teacher_forced_trace_with_few_visit_tiles(monkeypatch):
     test_teacher_forced_trace("room1081_n8")
 
 
+@pytest.mark.parametrize("fraction", ["1.0", "0.25"])
+def test_teacher_forced_trace_with_other_pool_splits(monkeypatch, fraction):
+    """the patch pool's split into hit-capable ids and free-space ids (visit counters only) must not show: with every id
+    hit-capable (1.0: the layout without the split, no promotion ever) and with few of them (0.25: patches start on the cheap
+    side, move when their first end point arrives, and the free-space stack is what new patches come from) the trace is the same"""
+    monkeypatch.setenv("GM_B200_HIT_FRACTION", fraction)
+    test_teacher_forced_trace("room181_n30")
+    test_teacher_forced_trace("room181_k2_lskip")  # end points only (generateMap off): every patch is promoted
+
+
+def test_free_space_stack_runs_dry(monkeypatch):
+    """a pool whose free-space side is tiny: new patches and copies fall back to hit-capable ids, nothing changes in the maps"""
+    monkeypatch.setenv("GM_B200_HIT_FRACTION", "0.97")
+    test_teacher_forced_trace("room181_resize")
+
+
 @pytest.mark.parametrize("case", CASES)
 def test_teacher_forced_trace(case):
     from gpu_common import context_for
