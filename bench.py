@@ -297,9 +297,10 @@ def main():
     per = {k: (s1["total_" + k] - s0["total_" + k]) / K for k in keys + hkeys}
     # device time of a step: the kernels of every stage; ms_allgather is host time spent waiting for the other ranks' rows
     # (their kernels, measured on their own clocks) and is reported, not added
-    # a sharded filter queues the registration behind the scan match and normalises the weights on a second stream meanwhile
-    # (setregisterWithScanMatch): k_normalize then overlaps k_register and is not on the device's critical path
-    dev_keys = ("ms_scanmatch", "ms_remap", "ms_register", "ms_migrate") + (("ms_weights",) if world == 1 else ())
+    # the filter queues the registration behind the scan match and normalises the weights on a second stream meanwhile
+    # (setregisterWithScanMatch, the default of a plain GridSlamProcessor and of a sharded one): k_normalize then overlaps
+    # k_register and is not on the device's critical path -- it is listed in stage_ms, not added
+    dev_keys = ("ms_scanmatch", "ms_remap", "ms_register", "ms_migrate")
     dev_ms_local = sum(per[k] for k in dev_keys)
     wall_ms_local = (t1 - t0) * 1000.0 / K
     sm_ms = per["ms_scanmatch"]

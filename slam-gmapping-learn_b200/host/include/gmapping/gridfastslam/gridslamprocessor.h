@@ -173,7 +173,7 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     // maps are then one scan ahead already inside onScanmatchUpdate() (reading Particle::map there aborts with a message, as in
     // onResampleUpdate()).  Needs early registration.  Default: on for a sharded filter, off on a single GPU.  Call before init().
     void setregisterWithScanMatch(bool on) { m_fusedRegister = on ? 1 : 0; }
-    bool getregisterWithScanMatch() const { return m_fusedRegister > 0 || (m_fusedRegister < 0 && m_world > 1); }
+    bool getregisterWithScanMatch() const;  // default: on for a sharded filter and for a plain GridSlamProcessor (no subclass, no hook)
     void refreshTreeWeights();
     // occupancy grid of one local particle's map computed on the GPU (what gmapping/src/slam_gmapping.cpp:956-993 fills by
     // walking smap.cell(p) on the host): data[y * width + x] = -1 unknown, 100 if n/visits > occThresh, else 0;
@@ -239,7 +239,7 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     bool m_lazyTree = false;
     unsigned int m_maxParticles = 0, m_particleSlots = 0;  // setmaxParticles(); device slots for particle maps (set by init)
     bool m_earlyRegistration = true, m_registeredEarly = false;
-    int m_fusedRegister = -1;  // -1: by default (on when sharded)
+    int m_fusedRegister = -1;  // -1: by default (see getregisterWithScanMatch)
     bool m_weightsChanged = true;  // a particle's log-weight changed since the last normalize()
     mutable bool m_treeDirty = false;
     double m_hostMs[4];

@@ -34,7 +34,8 @@ struct Handle {
 
 extern "C" {
 
-void* gmh_create(int verbose) { return new Handle(verbose != 0); }
+// (the counting subclass reads no map in its hook: it takes the default of a plain GridSlamProcessor, see getregisterWithScanMatch)
+void* gmh_create(int verbose) { Handle* h = new Handle(verbose != 0); h->gsp->setregisterWithScanMatch(true); return h; }
 void gmh_destroy(void* h) { delete static_cast<Handle*>(h); }
 void* gmh_clone(void* h) { return new Handle(*static_cast<Handle*>(h)); }
 int gmh_dist_unique_id(void* id128) { return gm_dist_unique_id(id128); }

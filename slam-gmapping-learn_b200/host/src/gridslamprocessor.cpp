@@ -6,6 +6,8 @@
 // fires), tree weights again -- because the drand48 stream, the .gfs trace and the virtual hooks are all visible
 // to users.  The four stages that are O(particles x beams) are single calls into the C ABI.
 #include <gmapping/gridfastslam/gridslamprocessor.h>
+
+#include <typeinfo>
 #include <gmapping/utils/stat.h>
 #include <stdlib.h>
 
@@ -699,6 +701,15 @@ bool GridSlamProcessor::processScan(const RangeReading& reading, int adaptPartic
     if (m_outputStream.is_open()) m_outputStream << std::flush;
     m_readingCount++;
     return processed;
+}
+
+// The registration queued on the device right behind the scan match: what it takes away is the window in which an overridden
+// onScanmatchUpdate() could still read the maps without this scan in them.  A filter object that is a plain GridSlamProcessor
+// has no such hook (the ROS wrapper and gfs-carmen use it that way), neither has a sharded one a use for it: on by default
+// there, off for subclasses unless they ask (setregisterWithScanMatch).
+bool GridSlamProcessor::getregisterWithScanMatch() const {
+    if (m_fusedRegister >= 0) return m_fusedRegister > 0;
+    return m_world > 1 || typeid(*this) == typeid(GridSlamProcessor);
 }
 
 void GridSlamProcessor::prepareMotionDraws() {

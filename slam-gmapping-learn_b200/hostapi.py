@@ -89,7 +89,7 @@ class Processor:
             L.gmh_set_distributed(self.h, rank, world, self._id)
         if lazy_tree:
             L.gmh_set_lazy_tree(self.h, 1)  # TNode::accWeight is brought up to date on demand (refresh_tree / getTrajectories)
-        if register_with_scanmatch is not None:  # default: on for a sharded filter, off on one GPU
+        if register_with_scanmatch is not None:  # default: on (like a plain GridSlamProcessor object; subclasses with hooks: off unless sharded)
             L.gmh_set_register_with_scanmatch(self.h, 1 if register_with_scanmatch else 0)
         if max_particles:
             L.gmh_set_max_particles(self.h, int(max_particles))  # room for process_scan(..., adapt=) to grow the particle set
