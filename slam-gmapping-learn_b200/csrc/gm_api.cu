@@ -626,7 +626,9 @@ int gmi_register_finish(gm_ctx* ctx) {
     ctx->reg_active_hint = h.max_active;
     ctx->stats.max_active_patches = (uint32_t)h.max_active; ctx->stats.register_tile_cap = (uint32_t)ctx->reg_tile_cap;
     for (int k = 0; k < 8; k++) ctx->stats.register_phase_cycles[k] = h.reg_phase[k];
-    if (h.error == GM_ERR_POOL) return fail(ctx, GM_ERR_POOL, "gm_register: patch pool of %d patches exhausted", ctx->pool.cap);
+    if (h.error == GM_ERR_POOL)
+        return fail(ctx, GM_ERR_POOL, "gm_register: patch pool exhausted (%d patch ids, %d of them able to hold end points: %d and %d free; "
+                    "GM_B200_POOL_PATCHES / gm_config.pool_patches, GM_B200_HIT_FRACTION)", ctx->pool.cap, ctx->pool.cap_h, std::max(0, tops[0]) + std::max(0, tops[1]), std::max(0, tops[0]));
     if (h.error) return fail(ctx, h.error, "gm_register: device-side error %d", h.error);
     return GM_OK;
 }

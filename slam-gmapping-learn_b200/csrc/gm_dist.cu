@@ -356,7 +356,7 @@ static int dist_migrate_and_remap(gm_ctx* ctx, const uint32_t* idx_global, const
         Counters h;
         CK(cudaMemcpyAsync(&uniq, ctx->d_digest, sizeof uniq, cudaMemcpyDeviceToHost, ctx->st));
         if (int r = read_counters(ctx, h)) return r;
-        if (h.error == GM_ERR_POOL) return dist_fail(ctx, GM_ERR_POOL, "%s: patch pool of %d patches exhausted while importing %zu parents", who, ctx->pool.cap, nimp);
+        if (h.error == GM_ERR_POOL) return dist_fail(ctx, GM_ERR_POOL, "%s: patch pool exhausted (%d patch ids, %d of them able to hold end points) while importing %zu parents", who, ctx->pool.cap, ctx->pool.cap_h, nimp);
         if (h.error) return dist_fail(ctx, h.error, "%s: device-side error %d while importing parents", who, h.error);
     } else CK(cudaStreamSynchronize(ctx->st));
     // ---- barrier B: nobody frees or rewrites a patch while a peer may still be reading it
