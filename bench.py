@@ -344,6 +344,10 @@ def main():
         roofline_register = {"kernel": "k_register", "bound": "hbm", "unit": "GB/s", "achieved": reg_bytes / (reg_ms * 1e-3) / 1e9 if reg_ms else None,
                              "peak": peak, "frac": reg_bytes / (reg_ms * 1e-3) / 1e9 / peak if reg_ms else None,
                              "algorithmic_bytes": reg_bytes, "traffic": rfacts.get("dram_bytes_per_particle", 0) * nl or None,
+                             # what actually binds it (ncu: issue slots busy 57 %, DRAM 11 % of peak): warp instructions per second
+                             "issue": ({"achieved": rfacts["warp_instructions_per_particle"] * nl / (reg_ms * 1e-3) / 1e9, "peak": issue_peak, "unit": "Gwarp-inst/s",
+                                        "frac": rfacts["warp_instructions_per_particle"] * nl / (reg_ms * 1e-3) / 1e9 / issue_peak}
+                                       if reg_ms and rfacts.get("warp_instructions_per_particle") else None),
                              "note": "last registration of the timed region: 8 B per free-cell update, 32 B per hit, 2 x 4 KB per copy-on-write patch copy"}
         h2d = world * (2 * (B * 8 + nl * 24) + n * 8)
         d2h = world * (n * 48 + 8 + 2 * 160)
