@@ -138,7 +138,7 @@ GridSlamProcessor::GridSlamProcessor(const GridSlamProcessor& gsp)
     m_device.reset(new b200::DeviceContext(*gsp.m_device, 0));
     const TNodeVector leaves = gsp.getTrajectories();
     ScanMatcherMap mirror(Point((m_xmin + m_xmax) * .5, (m_ymin + m_ymax) * .5), 0., 0., m_delta);
-    m_particles.reserve(gsp.m_particles.size());
+    m_particles.reserve(std::max(gsp.m_particles.size(), (size_t)m_particleSlots));
     for (size_t i = 0; i < gsp.m_particles.size(); i++) {
         const Particle& src = gsp.m_particles[i];
         m_particles.push_back(Particle(mirror));
@@ -235,7 +235,9 @@ void GridSlamProcessor::init(unsigned int size, double xmin, double ymin, double
 
     TNode* root = new TNode(initialPose, 0, 0, 0);
     ScanMatcherMap mirror(Point(center[0], center[1]), 0., 0., delta);  // geometry + cells arrive with the first pull
-    m_particles.reserve(size);
+    // room for every particle the filter may ever hold (adaptParticles): growing must not reallocate -- copying a Particle turns
+    // its map into a plain host copy
+    m_particles.reserve(std::max(size, m_particleSlots));
     for (unsigned int i = 0; i < size; i++) {
         m_particles.push_back(Particle(mirror));
         Particle& p = m_particles.back();
@@ -431,7 +433,7 @@ bool GridSlamProcessor::resample(const double* plainReading, int adaptSize, cons
         if (nn < n) m_particles.erase(m_particles.begin() + nn, m_particles.end());
         else {
             ScanMatcherMap mirror(Point((m_xmin + m_xmax) * .5, (m_ymin + m_ymax) * .5), 0., 0., m_delta);
-            m_particles.reserve(nn);
+            if (nn > m_particles.capacity()) b200::fatal("processScan(reading, adaptParticles): internal: the particle vector was not reserved for growth");
             for (size_t j = n; j < nn; j++) {
                 m_particles.push_back(Particle(mirror));
                 std::shared_ptr<b200::DeviceMapResidency> r(new b200::DeviceMapResidency);

@@ -132,7 +132,7 @@ def scenario_order():
 
 def scenario_adapt():
     """processScan(reading, adaptParticles) (gridslamprocessor.hxx:153-156 -> particlefilter.h:196-203): the resampling at a reading
-    continues with another number of particles, fewer (30 -> 20) and then more (20 -> 26, room reserved with setmaxParticles).
+    continues with another number of particles, fewer (30 -> 20) and then more (20 -> 34, room reserved with setmaxParticles).
     The index vectors are the reference's arithmetic (pinned by tests/golden/units.npz: resampleIndexes(w, nparticles)); here: the
     filter carries on, child j continues parent idx[j] (pose, weightSum, previousIndex, map), the reference counts of the patch
     pool stay consistent, and the three registration orders (early, the reference's, queued behind the scan match) agree bit
@@ -142,12 +142,12 @@ def scenario_adapt():
     hostapi = importlib.import_module("slam-gmapping-learn_b200.hostapi")
     g = Golden("room181_n30")
     p = g.p
-    schedule = {6: 20, 7: 20, 12: 26}
+    schedule = {6: 20, 7: 20, 12: 34}  # (34 > the 30 the filter starts with: the particle vector must have been reserved for it)
     runs = []
     for early, fused in ((True, False), (False, False), (True, True)):
         par = dict({k: p[k] for k in hostapi.PARAM_ORDER}, resampleThreshold=2.0)  # Neff < 2 N: every processed reading resamples
         a = hostapi.Processor(g.angles, p["particles"], g.head_init, bounds=(p["xmin"], p["ymin"], p["xmax"], p["ymax"]), delta=p["delta"],
-                              seed=p["seed"], early_registration=early, register_with_scanmatch=fused, max_particles=32, **par)
+                              seed=p["seed"], early_registration=early, register_with_scanmatch=fused, max_particles=36, **par)
         counts, trail = [], []
         for i in range(16):
             before = a.state()
@@ -162,15 +162,15 @@ def scenario_adapt():
                 assert np.all(st[:, 3] == 0)  # setWeight(0) after a resampling
                 trail.append(idx.copy())
             assert a.check_maps() > 0
-        assert counts[5] == 30 and counts[6] == 20 and counts[11] == 20 and counts[12] == 26 and counts[-1] == 26, counts
-        assert len(a.map_digests()) == 26 and len(a.tree_rows()) == 26
+        assert counts[5] == 30 and counts[6] == 20 and counts[11] == 20 and counts[12] == 34 and counts[-1] == 34, counts
+        assert len(a.map_digests()) == 34 and len(a.tree_rows()) == 34
         runs.append((a.state(), a.map_digests(), trail, a.neff()))
         a.close()
     s0, d0, t0, n0 = runs[0]
     for s1, d1, t1, n1 in runs[1:]:
         assert np.array_equal(s0, s1) and np.array_equal(d0, d1) and n0 == n1
         assert len(t0) == len(t1) and all(np.array_equal(x, y) for x, y in zip(t0, t1))
-    return "30 -> 20 -> 26 particles, %d resamplings" % len(t0)
+    return "30 -> 20 -> 34 particles, %d resamplings" % len(t0)
 
 
 def scenario_lazy_tree():

@@ -29,6 +29,32 @@ int main(int argc, char** argv) {
         if (n == 10) { GridSlamProcessor::TNodeVector t = gsp->getTrajectories(); gsp->integrateScanSequence(t[0]); for (size_t i = 0; i < t.size(); i++) delete t[i]; }
         delete r;
     }
+    // adaptParticles: a third filter that resamples at every reading and goes 8 -> 5 -> 11 particles
+    {
+        std::ifstream is2(argv[1]); InputSensorStream input2(sm, is2);
+        GridSlamProcessor g3(devnull);
+        g3.setSensorMap(sm);
+        g3.setMatchingParameters(80, 80, 0.05, 1, 0.05, 0.05, 5, 0.075, 3, 0);
+        g3.setMotionModelParameters(0.1, 0.2, 0.1, 0.2);
+        g3.setUpdateDistances(0.0, 0.0, 2.0);
+        g3.setgenerateMap(true);
+        g3.setmaxParticles(12);
+        static const int adapt[8] = {0, 0, 0, 5, 5, 11, 0, 0};
+        bool up = false; int k = 0;
+        while (input2 && k < 8) {
+            const SensorReading* r = 0; input2 >> r; if (!r) continue;
+            const RangeReading* rr = dynamic_cast<const RangeReading*>(r);
+            if (!rr) { delete r; continue; }
+            if (!up) { g3.init(8, -100, -100, 100, 100, 0.05, rr->getPose()); up = true; }
+            g3.processScan(*rr, adapt[k]);
+            k++;
+            delete r;
+        }
+        GridSlamProcessor::TNodeVector t = g3.getTrajectories();
+        std::cout << "adapt particles " << g3.getParticles().size() << " trajectories " << t.size() << std::endl;
+        for (size_t i = 0; i < t.size(); i++) delete t[i];
+        if (g3.getParticles().size() != 11) return 3;
+    }
     // read a map through the mirror, copy a particle like the ROS node
     GridSlamProcessor::Particle best = gsp->getParticles()[gsp->getBestParticleIndex()];
     double occ = best.map.cell(best.map.world2map(Point(best.pose.x, best.pose.y)));
