@@ -140,6 +140,8 @@ int gm_destroy(gm_ctx* c) {
     c->reg_pending = false;
     gmi_dist_destroy(c);
     if (c->st) cudaStreamSynchronize(c->st);
+    for (void* p : c->retired) cudaFree(p);
+    c->retired.clear();
     bool last = true;
     if (c->share) {
         // a context that shares its pool gives its references back; the pool and the stream go with the last user
@@ -509,6 +511,7 @@ int gmi_bounds_and_resize(gm_ctx* ctx) {
 static int gmi_grow_dirs_and_relayout(gm_ctx* ctx, int new_cap) {
     const size_t dn = (size_t)ctx->max_particles * new_cap;
     int* grown = nullptr;
+    release_exported(ctx, ctx->dir_alt); ctx->dir_alt = nullptr;
     CK(dalloc(ctx->dir_alt, dn));
     CK(cudaMalloc(reinterpret_cast<void**>(&grown), dn * sizeof(int)));
     launch_fill_int(grown, dn, -1, ctx->st);
@@ -517,7 +520,7 @@ static int gmi_grow_dirs_and_relayout(gm_ctx* ctx, int new_cap) {
     launch_bounds_and_relayout(ctx, new_cap, grown);
     if (int rc = check_launch(ctx, "relayout")) { cudaFree(grown); return rc; }
     CK(cudaStreamSynchronize(ctx->st));
-    cudaFree(ctx->dir);
+    release_exported(ctx, ctx->dir);
     ctx->dir = grown;
     ctx->dir_cap = new_cap;
     ctx->dir_gen++;
@@ -643,8 +646,9 @@ int gmi_ensure_dir_cap(gm_ctx* ctx, int need) {
     CK(cudaMemcpy2DAsync(grown, sizeof(int) * need, ctx->dir, sizeof(int) * ctx->dir_cap, sizeof(int) * ctx->dir_cap, ctx->max_particles,
                          cudaMemcpyDeviceToDevice, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
-    cudaFree(ctx->dir);
+    release_exported(ctx, ctx->dir);
     ctx->dir = grown;
+    release_exported(ctx, ctx->dir_alt); ctx->dir_alt = nullptr;
     CK(dalloc(ctx->dir_alt, dn));
     launch_fill_int(ctx->dir_alt, dn, -1, ctx->st);
     ctx->dir_cap = need;

@@ -59,6 +59,9 @@ struct gm_ctx {
     // launches of at most this many particles use k_scanmatch's wide shape (GM_B200_SM_WIDE_BELOW).  Measured on a B200 at 1081 beams:
     // 512 particles 1.32 -> 1.10 ms, 1024: 2.04 -> 1.87, 2048: 3.56 -> 3.51, 4096: 6.61 -> 6.77 (profiles/experiments_r02.json)
     uint32_t sm_wide_below = 2048;
+    // directory buffers a sharded context outgrew: its peers may still have them mapped (CUDA IPC), and freeing exported memory
+    // before every importer has closed it is undefined -- they are freed with the context
+    std::vector<void*> retired;
     bool sw_pending = false; uint32_t sw_total = 0; double sw_gain = 1;  // between gm_scanmatch_weights_begin and _end
     double* d_inv_n = nullptr;
     size_t scanmatch_smem = 0;
@@ -103,6 +106,12 @@ inline int fail(gm_ctx* c, int code, const char* fmt, ...) {
 template <class T> inline cudaError_t dalloc(T*& p, size_t count) {
     if (p) { cudaFree(p); p = nullptr; }
     return cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T));
+}
+
+// free a directory buffer -- later, if peers may have it mapped
+inline void release_exported(gm_ctx* ctx, void* p) {
+    if (!p) return;
+    if (ctx->dist) ctx->retired.push_back(p); else cudaFree(p);
 }
 
 inline int bind(gm_ctx* ctx) {

@@ -31,6 +31,17 @@ def test_sharded_filter_two_ranks():
 
 
 @pytest.mark.gpu
+def test_sharded_filter_whose_maps_outgrow_their_directories():
+    """room181_resize starts from an 8 x 8 m map: Map::resize on the first scans, the directory stride grows on both ranks (the
+    exported directory buffers are retired, not freed: a peer may still have them mapped), the handles are published again and
+    the resampling that follows pulls parents through the re-opened mappings"""
+    build_host()
+    res = run_dist_check(29613, {"GM_DIST_CASES": "room181_resize"})
+    assert res.returncode == 0, (res.stdout[-2000:], res.stderr[-4000:])
+    assert "dist_check room181_resize: ok" in res.stdout
+
+
+@pytest.mark.gpu
 def test_pool_exhaustion_during_migration_is_loud():
     """a pool too small for the imported parents: the run must die with the pool message on every rank, not continue with holes"""
     build_host()
