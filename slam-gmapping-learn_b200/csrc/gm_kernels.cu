@@ -909,6 +909,10 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
     // directory stride than the allocation has (the host grows it and registers again, see gmi_register_finish)
     if (A.counters->error != 0 || A.counters->need_dir_cap > A.dir_cap) return;
     const Geom g = A.geom[p];
+    if (g.npx > 2047 || g.npy > 2047) {  // the ray walk packs a cell into one word, 16 bits a coordinate (3.2 km a side at 5 cm)
+        if (threadIdx.x == 0) atomicCAS(&A.counters->error, 0, -2);
+        return;
+    }
     int* dirp = A.dir + (size_t)p * A.dir_cap;
     const int nent = g.npx * g.npy, nwords = (nent + 31) >> 5;
     const RegSmem M = carve(smem_raw, A.bitmap_words, A.sort_n, (int)P.nbeams);
@@ -1170,27 +1174,37 @@ __global__ void __launch_bounds__(kRegThreads, 1) k_register(RegisterArgs A) {
             const int two_db = 2 * L.db, two_da = 2 * L.da;
             int f = L.from_end ? two_da - 1 - e : e;
             const int dmaj = L.from_end ? -1 : 1, dmin = L.from_end ? -L.bstep : L.bstep;
-            int x = L.steep ? L.b_lo + L.bstep * inc : L.a_lo + j, y = L.steep ? L.a_lo + j : L.b_lo + L.bstep * inc;
+            const int x = L.steep ? L.b_lo + L.bstep * inc : L.a_lo + j, y = L.steep ? L.a_lo + j : L.b_lo + L.bstep * inc;
             const int sx0 = L.steep ? 0 : dmaj, sy0 = L.steep ? dmaj : 0, sx1 = L.steep ? dmin : 0, sy1 = L.steep ? 0 : dmin;
-            int lx = INT_MIN / 2, ly = INT_MIN / 2, base = -1;  // cell of the last patch lookup, tile of that patch (slot << 10)
+            // the cell as ONE word, x in the upper and y in the lower half (k_bounds put both ends of every ray inside the map, and
+            // the map has fewer than 65536 cells a side -- checked at the top of the kernel): a step is one add, "another patch"
+            // one masked compare
+            unsigned xy = ((unsigned)x << 16) | ((unsigned)y & 0xffffu);
+            const unsigned d0 = (unsigned)(sx0 * 65536 + sy0), d1 = d0 + (unsigned)(sx1 * 65536 + sy1);
+            const int k0 = sx0 * kPatch + sy0, k1 = k0 + sx1 * kPatch + sy1;  // the same steps in a tile's cell index (x-major)
+            unsigned lxy = ~xy;  // cell of the last patch lookup (none yet)
+            int base = -1;       // tile of that patch (slot << 10), and the cell's counter in it while the walk stays in the patch
+            int kk = 0;
             const int smax = __reduce_max_sync(0xffffffffu, steps);
             for (int sidx = 0; sidx < smax; sidx++) {
                 int key = -1;
                 if (sidx < steps) {
-                    if (((x ^ lx) | (y ^ ly)) >> kPatchMag) {  // another patch
-                        lx = x; ly = y; base = -1;
-                        const int px = x >> kPatchMag, py = y >> kPatchMag;
-                        if ((unsigned)px < (unsigned)g.npx && (unsigned)py < (unsigned)g.npy) {
+                    if ((xy ^ lxy) & 0xffe0ffe0u) {  // another patch
+                        lxy = xy; base = -1;
+                        const int px = (int)(xy >> (16 + kPatchMag)), py = (int)((xy & 0xffffu) >> kPatchMag);
+                        if (px < g.npx && py < g.npy) {
                             const int en = px * g.npy + py;
                             const int sl = (int)M.prefix[en >> 5] + __popc(active[en >> 5] & ((1u << (en & 31)) - 1u)) - first;
                             if ((unsigned)sl < (unsigned)ntile) base = sl << 10;
                         }
+                        kk = base | (int)((xy >> (16 - kPatchMag)) & 0x3e0u) | (int)(xy & 31u);
                     }
-                    if (base >= 0) key = base | ((x & 31) << kPatchMag) | (y & 31);
+                    if (base >= 0) key = kk;
                     f += two_db;
                     const bool carry = f >= two_da;
                     f -= carry ? two_da : 0;
-                    x += sx0 + (carry ? sx1 : 0); y += sy0 + (carry ? sy1 : 0);
+                    xy += carry ? d1 : d0;
+                    kk += carry ? k1 : k0;  // (meaningless once the walk leaves the patch: the next trip looks the new one up)
                 }
                 const int prev = __shfl_up_sync(0xffffffffu, key, 1);
                 const bool head = lane == 0 || key != prev;
