@@ -52,6 +52,10 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
         mutable unsigned int visitCounter;
         mutable bool flag;
         mutable unsigned int epoch;  // B200 build: pass stamp so that shared ancestors are reset once per pass
+        // B200 build: getTrajectories() notes each node's copy here (valid while copyEpoch is the filter's current one) instead of
+        // looking nodes up in a map
+        mutable TNode* copy;
+        mutable unsigned int copyEpoch;
     };
     typedef std::vector<GridSlamProcessor::TNode*> TNodeVector;
     typedef std::deque<GridSlamProcessor::TNode*> TNodeDeque;
@@ -236,6 +240,7 @@ class GRIDFASTSLAM_EXPORT GridSlamProcessor {
     unsigned char m_ncclId[128];
     unsigned int m_firstLocal, m_localCount;
     unsigned int m_treeEpoch;
+    mutable unsigned int m_copyEpoch = 0;
     bool m_lazyTree = false;
     unsigned int m_maxParticles = 0, m_particleSlots = 0;  // setmaxParticles(); device slots for particle maps (set by init)
     bool m_earlyRegistration = true, m_registeredEarly = false;

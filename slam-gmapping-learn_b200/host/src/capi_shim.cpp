@@ -1,5 +1,6 @@
 // capi_shim.cpp -- a flat C view of GMapping::GridSlamProcessor for bench.py and the tests (ctypes): every call
 // goes through the same C++ API a C++ consumer would use.
+#include <set>
 #include <gmapping/gridfastslam/gridslamprocessor.h>
 #include <gmapping/utils/stat.h>
 
@@ -145,6 +146,19 @@ void gmh_device_stats(void* hv, double* out) {
 void gmh_map_digests(void* hv, unsigned long long* out) {
     const std::vector<unsigned long long> d = static_cast<Handle*>(hv)->gsp->mapDigests();
     if (!d.empty()) memcpy(out, d.data(), sizeof(unsigned long long) * d.size());
+}
+
+// getTrajectories(): deep copy of the trajectory tree; returns the number of nodes in the copy and frees it again
+// (-> tests: shape; tools: what a clone() costs on the host)
+unsigned long long gmh_copy_trajectories(void* hv, int count_nodes) {
+    GridSlamProcessor::TNodeVector t = static_cast<Handle*>(hv)->gsp->getTrajectories();
+    unsigned long long nodes = t.size();
+    std::set<const GridSlamProcessor::TNode*> seen;
+    if (count_nodes) nodes = 0;
+    for (size_t i = 0; count_nodes && i < t.size(); i++)
+        for (const GridSlamProcessor::TNode* n = t[i]; n && seen.insert(n).second; n = n->parent) nodes++;
+    for (size_t i = 0; i < t.size(); i++) delete t[i];
+    return nodes;
 }
 
 unsigned long long gmh_check_maps(void* hv) { return static_cast<Handle*>(hv)->gsp->checkMapConsistency(); }

@@ -43,7 +43,7 @@ static const double kOdometryJumpWarning = 20;  // metres between two readings (
 
 // ------------------------------------------------------------------------------------------ trajectory tree
 GridSlamProcessor::TNode::TNode(const OrientedPoint& p, double w, TNode* n, unsigned int c)
-    : pose(p), weight(w), accWeight(0), gweight(0), parent(n), reading(0), childs(c), visitCounter(0), flag(false), epoch(0) {
+    : pose(p), weight(w), accWeight(0), gweight(0), parent(n), reading(0), childs(c), visitCounter(0), flag(false), epoch(0), copy(0), copyEpoch(0) {
     if (parent) parent->childs++;
 }
 
@@ -752,25 +752,32 @@ void GridSlamProcessor::onOdometryUpdate() {}
 // (reference: gridslamprocessor_tree.cpp:57-147)
 GridSlamProcessor::TNodeVector GridSlamProcessor::getTrajectories() const {
     const_cast<GridSlamProcessor*>(this)->refreshTreeWeights();
-    std::map<const TNode*, TNode*> copyOf;
+    // every node remembers its copy for the duration of this call (TNode::copy, stamped with a fresh epoch): one pass, no map
+    if (++m_copyEpoch == 0) {  // the stamp wrapped: no stale stamp may look current
+        for (ParticleVector::const_iterator it = m_particles.begin(); it != m_particles.end(); ++it)
+            for (const TNode* n = it->node; n; n = n->parent) n->copyEpoch = 0;
+        m_copyEpoch = 1;
+    }
+    const unsigned int stamp = m_copyEpoch;
     TNodeVector leaves;
     leaves.reserve(m_particles.size());
+    std::vector<const TNode*> chain;
     for (ParticleVector::const_iterator it = m_particles.begin(); it != m_particles.end(); ++it) {
         // collect the not-yet-copied part of this particle's chain, then build it top-down
-        std::vector<const TNode*> chain;
+        chain.clear();
         const TNode* n = it->node;
-        while (n && !copyOf.count(n)) { chain.push_back(n); n = n->parent; }
-        TNode* parentCopy = n ? copyOf[n] : 0;
+        while (n && n->copyEpoch != stamp) { chain.push_back(n); n = n->parent; }
+        TNode* parentCopy = n ? n->copy : 0;
         for (size_t k = chain.size(); k-- > 0;) {
             const TNode* src = chain[k];
             TNode* c = new TNode(src->pose, src->weight, parentCopy, 0);
             c->reading = src->reading;
             c->accWeight = src->accWeight;
             c->gweight = src->gweight;
-            copyOf[src] = c;
+            src->copy = c; src->copyEpoch = stamp;
             parentCopy = c;
         }
-        leaves.push_back(copyOf[it->node]);
+        leaves.push_back(it->node ? it->node->copy : 0);
     }
     return leaves;
 }

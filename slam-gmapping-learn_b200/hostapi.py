@@ -57,6 +57,7 @@ def load():
     L.gmh_map_digests.argtypes = [vp, vp]
     L.gmh_clone.restype = vp; L.gmh_clone.argtypes = [vp]
     L.gmh_check_maps.restype = C.c_ulonglong; L.gmh_check_maps.argtypes = [vp]
+    L.gmh_copy_trajectories.restype = C.c_ulonglong; L.gmh_copy_trajectories.argtypes = [vp, C.c_int]
     L.gmh_occupancy_grid.argtypes = [vp, C.c_uint, C.c_double, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), dp]
     L.gmh_occupancy.restype = C.c_double; L.gmh_occupancy.argtypes = [vp, C.c_uint, C.c_double, C.c_double]
     _lib = L
@@ -158,6 +159,11 @@ class Processor:
     def map_digests(self):
         nl = self.L.gmh_local_particles(self.h)
         a = np.zeros((nl, 6), dtype=np.uint64); self.L.gmh_map_digests(self.h, a.ctypes.data); return a
+
+    def copy_trajectories(self, count_nodes=True):
+        """GridSlamProcessor::getTrajectories() (the deep copy of the trajectory tree a clone() makes), freed again; -> nodes copied
+        (count_nodes=False: only the copy and its release, for timing; returns the number of leaves)"""
+        return int(self.L.gmh_copy_trajectories(self.h, 1 if count_nodes else 0))
 
     def check_maps(self):
         """MAP_CONSISTENCY_CHECK on the device (aborts the process on a mismatch); -> distinct patches referenced in the pool"""
