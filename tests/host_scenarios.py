@@ -72,6 +72,10 @@ def scenario_clone():
     before = a.check_maps()
     b = a.clone()
     assert np.array_equal(a.state(), b.state()) and np.array_equal(a.map_digests(), b.map_digests())
+    # getTrajectories() (what the copy was made with: each node notes its copy under a stamp, no map): the original's tree and the
+    # clone's have the same number of distinct nodes and the same rows seen from every particle, call after call
+    na, nb = a.copy_trajectories(), b.copy_trajectories()
+    assert na == nb == a.copy_trajectories() and na >= 12 + 1 and np.array_equal(a.tree_rows(), b.tree_rows())
     # the clone is a second set of directories over the same patches: no patch was copied, every count is consistent
     assert a.check_maps() == before and b.check_maps() == before
     saved = (ctypes.c_ushort * 3)(*libc.seed48((ctypes.c_ushort * 3)(0, 0, 0)).contents)  # read the drand48 state ...
